@@ -1,0 +1,337 @@
+/*
+ * rfx.h — C ABI of the B200-native screen-space post-processing engine.
+ *
+ * This is the drop-in boundary for the per-pixel hot path of 0beqz/realism-effects
+ * (SSGI trace -> temporal reprojection -> Poisson denoise -> GI compose, plus HBAO,
+ * TRAA and motion blur).  Every entry point is `extern "C"`, takes plain pointers /
+ * sizes / POD structs, returns an rfx_status, never throws and never aborts.
+ *
+ * The reference has no native interface (it is WebGL2 fragment shaders driven by JS);
+ * what an FFI for this path would bind is one call per fullscreen draw.  Each launch
+ * function below names the reference draw it replaces (paths relative to the
+ * reference checkout, `src/...`).
+ *
+ * Conventions
+ *  - Matrices are 16 fp32, column-major (three.js Matrix4.elements layout).
+ *  - Planes are pitched 2-D arrays in device memory, row 0 = GL texel row 0 (v = 0).
+ *    Pixel centre uv = ((x+0.5)/W, (y+0.5)/H)            (src/utils/shader/basic.vert:3-4)
+ *  - The context is NOT thread-safe.  Launches are enqueued on the given stream (or the
+ *    context's own stream when `stream == NULL`) and return immediately.
+ *  - Uniform values the reference derives from non-deterministic sources (blue-noise
+ *    index, delta time, window size) are explicit parameters.
+ */
+#ifndef RFX_H
+#define RFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFX_VERSION 1
+
+typedef enum rfx_status {
+  RFX_OK = 0,
+  RFX_ERR_INVALID_ARG = 1,   /* NULL pointer, bad enum, bad count                */
+  RFX_ERR_BAD_FORMAT = 2,    /* plane has the wrong rfx_format for this binding  */
+  RFX_ERR_SIZE_MISMATCH = 3, /* plane sizes inconsistent with each other         */
+  RFX_ERR_CUDA = 4,          /* a CUDA runtime call failed (see rfx_last_error)  */
+  RFX_ERR_NOT_READY = 5,     /* e.g. env map / blue noise not set                */
+  RFX_ERR_UNSUPPORTED = 6,   /* valid in the reference, not implemented here     */
+  RFX_ERR_NCCL = 7
+} rfx_status;
+
+/* Texel formats at the boundary = the reference's GL formats. */
+typedef enum rfx_format {
+  RFX_FMT_R32F = 0,    /* depth (DEPTH32F), marginal / conditional CDF tables      */
+  RFX_FMT_RGBA32F = 1, /* gBuffer, velocity, ssgi trace output, TR output, composed */
+  RFX_FMT_RGBA16F = 2, /* Poisson targets, AO target, composer buffers, env map     */
+  RFX_FMT_RGBA8 = 3    /* blue noise                                                */
+} rfx_format;
+
+typedef struct rfx_plane {
+  void* ptr;          /* device pointer (cudaMalloc / cudaMallocPitch), 16-B aligned */
+  uint32_t width;     /* texels */
+  uint32_t height;    /* texels */
+  uint64_t pitch;     /* bytes between rows, multiple of 16                          */
+  int32_t format;     /* rfx_format                                                  */
+  int32_t _reserved;
+} rfx_plane;
+
+typedef struct rfx_ctx rfx_ctx;
+
+/* Camera block shared by the passes.  Mirrors the uniforms
+ *   projectionMatrix / projectionMatrixInverse / cameraMatrixWorld / viewMatrix /
+ *   cameraNear / cameraFar and the PERSPECTIVE_CAMERA define
+ * (src/ssgi/pass/SSGIPass.js:33-38,82-87; src/temporal-reproject/TemporalReprojectPass.js:89-93;
+ *  src/denoise/pass/DenoiserComposePass.js:88-99). */
+typedef struct rfx_camera {
+  float projection[16];
+  float projection_inverse[16];
+  float camera_matrix_world[16];
+  float view_matrix[16]; /* camera.matrixWorldInverse */
+  float near_plane;
+  float far_plane;
+  int32_t perspective; /* 1 = PERSPECTIVE_CAMERA defined */
+  int32_t _pad;
+} rfx_camera;
+
+/* ------------------------------------------------------------------------------------
+ * K1  SSGI / SSR trace     replaces the fullscreen draw of src/ssgi/pass/SSGIPass.js:93-94
+ *     (shader src/ssgi/shader/ssgi.frag + ssgi_utils.frag; uniforms SSGIMaterial.js:15-42,
+ *      defines :44-51, per-frame SSGIPass.js:82-91, options SSGIOptions.js:26-48)
+ * ---------------------------------------------------------------------------------- */
+enum {
+  RFX_SSGI_IMPORTANCE_SAMPLING = 1u << 0, /* #define importanceSampling            */
+  RFX_SSGI_MISSED_RAYS = 1u << 1,         /* #define missedRays                    */
+  RFX_SSGI_USE_DIRECT_LIGHT = 1u << 2,    /* #define useDirectLight                */
+  RFX_SSGI_USE_ENVMAP = 1u << 3           /* #define USE_ENVMAP                    */
+};
+enum { RFX_MODE_SSGI = 0, RFX_MODE_SSR = 1 };
+
+typedef struct rfx_ssgi_params {
+  rfx_camera cam;
+  float ray_distance;          /* uniform rayDistance  (option `distance`)          */
+  float thickness;             /* uniform thickness                                  */
+  float env_blur;              /* uniform envBlur                                    */
+  float max_env_map_mip_level; /* uniform maxEnvMapMipLevel (Utils.js:30-34)         */
+  int32_t steps;               /* #define steps                                      */
+  int32_t refine_steps;        /* #define refineSteps                                */
+  int32_t mode;                /* RFX_MODE_SSGI / RFX_MODE_SSR                       */
+  uint32_t flags;              /* RFX_SSGI_*                                         */
+  int32_t blue_noise_index;    /* uniform blueNoiseIndex (BlueNoiseUtils.js:19-28)   */
+  int32_t _pad;
+} rfx_ssgi_params;
+
+/* ------------------------------------------------------------------------------------
+ * K2  temporal reprojection   replaces src/temporal-reproject/TemporalReprojectPass.js:192-193
+ *     (shader temporal_reproject.frag + reproject.frag; uniforms
+ *      material/TemporalReprojectMaterial.js:45-68; defines TemporalReprojectPass.js:77-117)
+ * ---------------------------------------------------------------------------------- */
+enum { RFX_INPUT_DIFFUSE_SPECULAR = 0, RFX_INPUT_DIFFUSE = 1, RFX_INPUT_SPECULAR = 2 };
+
+typedef struct rfx_temporal_params {
+  rfx_camera cam; /* un-jittered projection (TemporalReprojectPass.js:168-175) */
+  float prev_view_matrix[16];
+  float prev_camera_matrix_world[16];
+  float prev_projection[16];
+  float prev_projection_inverse[16];
+  float camera_pos[3];
+  float max_blend;
+  float prev_camera_pos[3]; /* uploaded by the reference, unused by the shader */
+  float neighborhood_clamp_intensity;
+  float keep_data;        /* 1, or 0 for the frame after reset()                    */
+  float confidence_power; /* #define confidencePower                                */
+  int32_t full_accumulate; /* uniform fullAccumulate (already AND-ed with !didCameraMove) */
+  int32_t texture_count;   /* 1 or 2                                                 */
+  int32_t input_type;      /* RFX_INPUT_*                                            */
+  int32_t log_transform;   /* #define logTransform                                   */
+  int32_t reproject_specular[2];
+  int32_t history_linear;  /* 1: history planes are sampled LINEAR (Poisson targets /
+                              FramebufferTexture), 0: NEAREST                        */
+  int32_t _pad;
+} rfx_temporal_params;
+
+/* ------------------------------------------------------------------------------------
+ * K3  Poisson denoise pass   replaces ONE iteration of the loop at
+ *     src/denoise/pass/PoissonDenoisePass.js:135-149 (shader poisson_denoise.frag;
+ *     uniforms PoissonDenoisePass.js:48-69)
+ * ---------------------------------------------------------------------------------- */
+typedef struct rfx_poisson_params {
+  float radius, phi, luma_phi, depth_phi, normal_phi, roughness_phi, specular_phi;
+  int32_t texture_count;          /* 1 or 2                                          */
+  int32_t is_texture_specular[2]; /* #define isTextureSpecular                       */
+  int32_t gbuffer_texture;        /* 1: GBUFFER_TEXTURE (packed gBuffer plane),
+                                     0: velocity-layout plane (normal in .b, depth in .a) */
+  int32_t input_linear;           /* filter of in0/in1: 0 NEAREST (pass 0 reads the TR
+                                     targets), 1 LINEAR (passes >= 1 read dnA/dnB)   */
+  int32_t blue_noise_index;
+  int32_t _pad;
+} rfx_poisson_params;
+
+/* K4  GI compose   replaces src/denoise/pass/DenoiserComposePass.js:129-135 */
+typedef struct rfx_compose_params {
+  rfx_camera cam;
+  int32_t input_type; /* RFX_INPUT_* */
+  int32_t _pad;
+} rfx_compose_params;
+
+/* K6  HBAO   replaces src/ao/AOPass.js:108-109 with src/hbao/shader/hbao.frag
+ *     (uniforms AOPass.js:36-54, defaults src/ao/AOEffect.js:8-21) */
+typedef struct rfx_hbao_params {
+  float projection_view[16]; /* projectionMatrix * matrixWorldInverse (AOPass.js:93-96) */
+  float projection_inverse[16];
+  float camera_matrix_world[16];
+  float ao_distance, distance_power, bias, thickness;
+  int32_t spp;
+  int32_t blue_noise_index;
+} rfx_hbao_params;
+
+/* K7  AO compose   src/ao/shader/ao_compose.frag:6-16 */
+typedef struct rfx_ao_compose_params {
+  float power;
+  float color[3];
+} rfx_ao_compose_params;
+
+/* K8  motion blur   src/motion-blur/shader/motion_blur.frag:11-44,
+ *     host values src/motion-blur/MotionBlurEffect.js:87-102 */
+typedef struct rfx_motion_blur_params {
+  float intensity, jitter;
+  float delta_time;    /* already max(1/1000, deltaTime)                            */
+  float resolution[2]; /* uniform resolution (window.innerWidth/innerHeight)        */
+  int32_t frame;       /* blue-noise index; 0 selects the tiled lookup              */
+  int32_t samples;     /* #define samples                                           */
+  int32_t _pad;
+} rfx_motion_blur_params;
+
+/* Environment map + importance-sampling tables (struct EquirectHdrInfo, ssgi.frag:27-36;
+ * built by src/ssgi/utils/EquirectHdrInfoUniform.js:149-245). */
+typedef struct rfx_env_desc {
+  const void* map_rgba16f; /* HOST pointer, mip 0, width*height*4 halfs, tightly packed */
+  uint32_t width, height;
+  const float* marginal;    /* HOST, `height` floats (may be NULL when no importance sampling) */
+  const float* conditional; /* HOST, width*height floats                                       */
+  float total_sum_whole, total_sum_decimal;
+} rfx_env_desc;
+
+/* ---- context ---------------------------------------------------------------------- */
+rfx_status rfx_ctx_create(int device, rfx_ctx** out);
+void rfx_ctx_destroy(rfx_ctx* ctx);
+const char* rfx_last_error(const rfx_ctx* ctx);
+int rfx_version(void);
+void* rfx_ctx_stream(rfx_ctx* ctx);      /* the context's cudaStream_t             */
+rfx_status rfx_ctx_sync(rfx_ctx* ctx);   /* cudaStreamSynchronize(ctx stream)      */
+uint64_t rfx_launch_count(const rfx_ctx* ctx); /* kernels launched so far by this ctx */
+
+/* blue noise: 128x128 RGBA8 in GL texel order (flipY already applied)
+ * (src/utils/BlueNoiseUtils.js:6-15) */
+rfx_status rfx_blue_noise_set(rfx_ctx* ctx, const uint8_t* rgba8_host, uint32_t width, uint32_t height);
+/* env map: uploads mip 0, builds the box-filter mip chain on the device
+ * (generateMipmaps, src/ssgi/SSGIEffect.js:324-329) and uploads the CDF tables */
+rfx_status rfx_env_set(rfx_ctx* ctx, const rfx_env_desc* env);
+rfx_status rfx_env_clear(rfx_ctx* ctx);
+
+/* ---- planes ------------------------------------------------------------------------ */
+rfx_status rfx_plane_alloc(rfx_ctx* ctx, int32_t format, uint32_t width, uint32_t height, rfx_plane* out);
+rfx_status rfx_plane_free(rfx_ctx* ctx, rfx_plane* plane);
+rfx_status rfx_plane_clear(rfx_ctx* ctx, void* stream, const rfx_plane* plane);
+/* host <-> device, asynchronous on `stream` when the host memory is pinned */
+rfx_status rfx_plane_upload(rfx_ctx* ctx, void* stream, const rfx_plane* dst, const void* host, uint64_t host_pitch);
+rfx_status rfx_plane_download(rfx_ctx* ctx, void* stream, const rfx_plane* src, void* host, uint64_t host_pitch);
+rfx_status rfx_host_alloc(rfx_ctx* ctx, uint64_t bytes, void** out); /* pinned */
+rfx_status rfx_host_free(rfx_ctx* ctx, void* p);
+uint32_t rfx_format_bytes(int32_t format);
+
+/* ---- pass launches ------------------------------------------------------------------
+ * `row0,row1` select the output rows [row0,row1) this call writes (row-block sharding,
+ * SURVEY.md §8e); pass 0,0 for the whole plane.  Input planes are always full frames. */
+
+/* K1. velocity / direct_light / accumulated may be NULL (null sampler => (0,0,0,1),
+ * SURVEY.md D4).  out: RGBA32F (8 packed halfs, gbuffer_packing.glsl:65-83). */
+rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_params* p,
+                                 const rfx_plane* depth, const rfx_plane* gbuffer,
+                                 const rfx_plane* velocity, const rfx_plane* direct_light,
+                                 const rfx_plane* accumulated, const rfx_plane* out,
+                                 uint32_t row0, uint32_t row1);
+
+/* K2. input: K1 output (RGBA32F packed) for DIFFUSE_SPECULAR, RGBA16F colour for DIFFUSE
+ * (TRAA).  history[i]/out[i], i < texture_count.  history RGBA16F, out RGBA32F (SSGI) or
+ * RGBA16F (TRAA).  Discarded pixels keep the previous contents of out. */
+rfx_status rfx_temporal_reproject_launch(rfx_ctx* ctx, void* stream, const rfx_temporal_params* p,
+                                         const rfx_plane* input, const rfx_plane* velocity,
+                                         const rfx_plane* history0, const rfx_plane* history1,
+                                         const rfx_plane* out0, const rfx_plane* out1,
+                                         uint32_t row0, uint32_t row1);
+
+/* K3. gbuffer_or_normal: packed gBuffer (gbuffer_texture=1) or velocity-layout plane.
+ * in: RGBA32F or RGBA16F; out: RGBA16F. */
+rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_poisson_params* p,
+                                      const rfx_plane* depth, const rfx_plane* gbuffer_or_normal,
+                                      const rfx_plane* in0, const rfx_plane* in1,
+                                      const rfx_plane* out0, const rfx_plane* out1,
+                                      uint32_t row0, uint32_t row1);
+
+/* K4. diffuse/specular: RGBA16F Poisson targets; out: RGBA32F. */
+rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_params* p,
+                                 const rfx_plane* depth, const rfx_plane* gbuffer,
+                                 const rfx_plane* diffuse_gi, const rfx_plane* specular_gi,
+                                 const rfx_plane* out, uint32_t row0, uint32_t row1);
+
+/* K5. src/ssgi/shader/ssgi_compose.frag:20-44 (no fog). gi RGBA32F, scene RGBA16F, out RGBA16F */
+rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* depth,
+                                   const rfx_plane* gi, const rfx_plane* scene,
+                                   const rfx_plane* out, uint32_t row0, uint32_t row1);
+
+/* K6. out RGBA16F (rgb = world normal, a = ao); background pixels are not written. */
+rfx_status rfx_hbao_launch(rfx_ctx* ctx, void* stream, const rfx_hbao_params* p,
+                           const rfx_plane* depth, const rfx_plane* out,
+                           uint32_t row0, uint32_t row1);
+
+/* K7. ao RGBA16F (.a), input/out RGBA16F */
+rfx_status rfx_ao_compose_launch(rfx_ctx* ctx, void* stream, const rfx_ao_compose_params* p,
+                                 const rfx_plane* depth, const rfx_plane* ao,
+                                 const rfx_plane* input, const rfx_plane* out,
+                                 uint32_t row0, uint32_t row1);
+
+/* K8. velocity RGBA32F, input/out RGBA16F (input sampled LINEAR) */
+rfx_status rfx_motion_blur_launch(rfx_ctx* ctx, void* stream, const rfx_motion_blur_params* p,
+                                  const rfx_plane* velocity, const rfx_plane* input,
+                                  const rfx_plane* out, uint32_t row0, uint32_t row1);
+
+/* K9. src/traa/shader/traa_compose.frag:3-6  accumulated RGBA16F -> out RGBA16F (a = 1) */
+rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* accumulated,
+                                   const rfx_plane* out, uint32_t row0, uint32_t row1);
+
+/* ---- SSGI chain (native mirror of SSGIEffect.update, src/ssgi/SSGIEffect.js:372-404 +
+ *      src/denoise/Denoiser.js:97-107): owns ssgiOut / trOut / dnA / dnB / composed and the
+ *      cross-frame state (prev matrices, keepData, history). ---------------------------- */
+typedef struct rfx_ssgi_chain rfx_ssgi_chain;
+
+typedef struct rfx_ssgi_chain_options {
+  uint32_t width, height;
+  int32_t denoise_iterations;  /* option denoiseIterations (=> 2*iterations K3 passes) */
+  int32_t steps, refine_steps;
+  float distance, thickness, env_blur;
+  float radius, phi, luma_phi, depth_phi, normal_phi, roughness_phi, specular_phi;
+  uint32_t ssgi_flags;         /* RFX_SSGI_* */
+  int32_t mode;                /* RFX_MODE_* */
+  int32_t blue_noise_start;    /* startIndex of BlueNoiseUtils.js:19 (pinned)          */
+  int32_t use_cuda_graph;      /* capture the frame into a CUDA graph                   */
+} rfx_ssgi_chain_options;
+
+typedef struct rfx_ssgi_frame {
+  rfx_camera cam;              /* current camera (un-jittered)                          */
+  const rfx_plane* depth;
+  const rfx_plane* gbuffer;
+  const rfx_plane* velocity;   /* VelocityDepthNormalPass layout                        */
+  const rfx_plane* direct_light; /* may be NULL                                         */
+  float camera_pos[3];
+  int32_t camera_moved;        /* didCameraMove(...) (src/utils/SceneUtils.js:17-27)    */
+} rfx_ssgi_frame;
+
+rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt, rfx_ssgi_chain** out);
+void rfx_ssgi_chain_destroy(rfx_ssgi_chain* chain);
+rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* chain);
+rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
+/* which: 0 composed (RGBA32F), 1 ssgiOut, 2/3 trOut[0/1], 4/5 dnB[0/1] */
+rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* chain, int32_t which, rfx_plane* out);
+/* host-buffer frame: uploads the four input planes from (pinned) host memory, renders,
+ * downloads `composed` into out_host.  This is the call `bench.py`'s e2e leg times. */
+typedef struct rfx_ssgi_host_frame {
+  rfx_camera cam;
+  const float* depth;             /* W*H      fp32 */
+  const float* gbuffer;           /* W*H*4    fp32 */
+  const float* velocity;          /* W*H*4    fp32 */
+  const uint16_t* direct_light;   /* W*H*4    fp16, may be NULL */
+  float camera_pos[3];
+  int32_t camera_moved;
+  float* out_composed;            /* W*H*4    fp32 */
+} rfx_ssgi_host_frame;
+rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* chain, const rfx_ssgi_host_frame* frame);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFX_H */

@@ -1,0 +1,216 @@
+// k_denoise.cu — K3 Poisson bilateral denoise, K4 GI compose, K5 ssgi compose (sm_100a).
+//
+// K3 replaces reference src/denoise/shader/poisson_denoise.frag:126-208 (one ping-pong pass of
+// src/denoise/pass/PoissonDenoisePass.js:135-149); K4 replaces the fullscreen draw of
+// src/denoise/pass/DenoiserComposePass.js:58-85 (+ denoiser_compose_functions.glsl:53-107);
+// K5 replaces src/ssgi/shader/ssgi_compose.frag:20-44.
+#include "rfx_kernels.h"
+
+namespace rfx {
+
+// luminance() of poisson_denoise.frag:28
+RFX_D float lum_p(v3 a) { return powf(dot(mk3(0.2125f, 0.7154f, 0.0721f), a), 0.125f); }
+
+template <bool LINEAR, bool HALF>
+RFX_D v4 fetch_in(const PV& t, v2 uv) {
+  if (LINEAR) return tex_h4_linear(t, uv);  // Poisson targets are RGBA16F + LinearFilter (PoissonDenoisePass.js:75-81)
+  if (HALF) return tex_h4_nearest(t, uv);
+  return f4v(tex_f4_nearest(t, uv));        // pass 0 reads the NEAREST fp32 temporal targets
+}
+
+template <int TC, bool GB, bool LINEAR, bool HALF>
+__global__ void __launch_bounds__(kThreads) poisson_kernel(const __grid_constant__ PoissonArgs a) {
+  int x, y;
+  block_pixel(x, y, a.row0 & ~1);
+  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  // helper pixels beyond the edge evaluate at the clamped texel (clamp-to-edge sampling)
+  const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
+  const v2 vUv = pixel_uv(x, y, a.W, a.H);
+
+  const float depth = ld_r32f(a.depth, xc, yc);
+  const float fwd = fwidth_f(depth);
+  const float4 gbc = ld_f4(a.gb, xc, yc);                  // packed gBuffer texel or velocity-layout texel
+  const v3 normal = unpackNormal(GB ? gbc.y : gbc.z);      // getNormal()  :80-87
+  const float fwn = length(fwidth_3(normal));              // :172
+  if (!active) return;
+  if (depth == 1.0f && fwd == 0.0f) return;                // discard :129-132 (target keeps its texel)
+
+  // mat = getMaterial(gBufferTexture, vUv) — without GBUFFER_TEXTURE the sampler is null => texel (0,0,0,1)
+  const float roughness = GB ? gb_roughness(gbc.z) : gb_roughness(0.0f);
+
+  const PV* ins[2] = {&a.in0, TC == 1 ? &a.in0 : &a.in1};
+  const int spec[2] = {a.spec0, a.spec1};
+  v3 rgb[2];
+  float alpha[2], lumc[2], age[2], tw[2];
+#pragma unroll
+  for (int i = 0; i < TC; i++) {  // :138-164
+    const PV& tex = spec[i] ? *ins[1] : a.in0;
+    v4 t = fetch_in<LINEAR, HALF>(tex, vUv);
+    age[i] = 1.0f / powf(t.w + 1.0f, 1.2f * a.phi);
+    v3 c = xyz(t) * 1.0003f;
+    c = vlog1p_(c);
+    rgb[i] = c; alpha[i] = t.w; lumc[i] = lum_p(c); tw[i] = 1.0f;
+  }
+  const float glossiness = fmaxf(0.0f, 4.0f * (1.0f - roughness / 0.25f));
+  const float specularFactor = expf(-glossiness * a.specular_phi);
+  float flatness = 1.0f - fminf(fwn, 1.0f);
+  flatness = flatness * flatness * 0.75f + 0.25f;  // pow(flatness, 2.) * 0.75 + 0.25
+
+  // rotate the poisson disk by blueNoise().r : (sin, cos) of (k/255)*2*pi from the host table
+  const uchar4 bn = __ldg(a.blue.tex + ((y + a.blue.shift.sy) % a.blue.size) * a.blue.size + ((x + a.blue.shift.sx) % a.blue.size));
+  const float2 sc = __ldg(a.rot_table + bn.x);
+  const float k = a.radius * flatness;
+  const float m00 = k * sc.y, m01 = k * -sc.x, m10 = k * sc.x, m11 = k * sc.y;  // mat2 columns (c,-s),(s,c)
+  const float resx = (float)a.W, resy = (float)a.H;
+  const float SQ = 1.41421356237f;
+  const float px[8] = {-1.0f, 0.0f, 1.0f, 0.0f, -0.25f * SQ, 0.25f * SQ, 0.25f * SQ, -0.25f * SQ};
+  const float py[8] = {0.0f, -1.0f, 0.0f, 1.0f, -0.25f * SQ, -0.25f * SQ, 0.25f * SQ, 0.25f * SQ};
+
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float ox = px[i] / resx, oy = py[i] / resy;
+    const v2 nuv = mk2(vUv.x + (m00 * ox + m10 * oy), vUv.y + (m01 * ox + m11 * oy));
+    // getBasicNeighborWeight :52-78
+    const int nx = nearest_i(nuv.x, a.W), ny = nearest_i(nuv.y, a.H);
+    const float4 g = ld_f4(a.gb, nx, ny);
+    const float ndepth = GB ? ld_r32f(a.depth, nx, ny) : g.w;
+    float wBasic = 0.0f;
+    if (ndepth != 1.0f) {
+      const v3 nn = unpackNormal(GB ? g.y : g.z);
+      const float normalDiff = 1.0f - fmaxf(dot(normal, nn), 0.0f);
+      const float depthDiff = 10000.0f * fabsf(depth - ndepth);
+      if (GB) {
+        const float roughnessDiff = fabsf(roughness - gb_roughness(g.z));
+        wBasic = expf(-normalDiff * a.normal_phi - depthDiff * a.depth_phi - roughnessDiff * a.roughness_phi);
+      } else {
+        wBasic = expf(-normalDiff * a.normal_phi - depthDiff * a.depth_phi);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < TC; j++) {  // applyWeight :102-124
+      float w = wBasic;
+      const PV& tex = spec[j] ? *ins[1] : a.in0;
+      if (spec[j]) w *= specularFactor;
+      v4 t = fetch_in<LINEAR, HALF>(tex, nuv);
+      v3 c = vlog1p_(xyz(t));
+      const float disocclW = powf(w, 0.1f);
+      float lumaDiff = fabsf(lumc[j] - lum_p(c));
+      lumaDiff = fminf(lumaDiff, 0.5f);
+      const float lumaFactor = expf(-lumaDiff * a.luma_phi);
+      w = mixf(w * lumaFactor, disocclW, age[j]) * age[j];
+      w *= (w < 0.0001f) ? 0.0f : 1.0f;  // step(0.0001, w)
+      rgb[j] = rgb[j] + w * c;
+      tw[j] += w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TC; j++) {  // outputTexel :94-100
+    v3 c = vexpm1_(rgb[j] / tw[j]);
+    const OutV& o = j == 0 ? a.out0 : a.out1;
+    st_h4(o.p, o.pitch, x, y, mk4(c, alpha[j]));
+  }
+}
+
+cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s) {
+  const int rb = a.row0 & ~1;
+  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+#define RFX_LP(TC, GB, LIN, HALF) poisson_kernel<TC, GB, LIN, HALF><<<grid, kThreads, 0, s>>>(a)
+  const bool lin = a.input_linear, half = a.in_half, gb = a.gbuffer_texture;
+  if (lin && !half) return cudaErrorInvalidValue;
+  if (a.texture_count == 2) {
+    if (gb) { if (lin) RFX_LP(2, true, true, true); else if (half) RFX_LP(2, true, false, true); else RFX_LP(2, true, false, false); }
+    else    { if (lin) RFX_LP(2, false, true, true); else if (half) RFX_LP(2, false, false, true); else RFX_LP(2, false, false, false); }
+  } else {
+    if (gb) { if (lin) RFX_LP(1, true, true, true); else if (half) RFX_LP(1, true, false, true); else RFX_LP(1, true, false, false); }
+    else    { if (lin) RFX_LP(1, false, true, true); else if (half) RFX_LP(1, false, false, true); else RFX_LP(1, false, false, false); }
+  }
+#undef RFX_LP
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_constant__ ComposeArgs a) {
+  int x, y;
+  block_pixel(x, y, a.row0 & ~1);
+  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
+  const float depth = ld_r32f(a.depth, xc, yc);
+  const float fwd = fwidth_f(depth);
+  if (!active) return;
+  if (depth == 1.0f && fwd == 0.0f) return;  // DenoiserComposePass.js:61-64
+  const v2 vUv = pixel_uv(x, y, a.W, a.H);
+  const float4 g = ld_f4(a.gb, x, y);
+  const v3 diffuse = xyz(floatToVec4(g.x));
+  const v3 wn = unpackNormal(g.y);
+  const float rough0 = gb_roughness(g.z), metalness = gb_metalness(g.z);
+  const v3 emissive = decodeRGBE8(floatToVec4(g.w));
+
+  const v3 viewNormal = mul_dir_left(wn, a.cam.camera_matrix_world);
+  const float gz = a.cam.perspective ? perspectiveDepthToViewZ(depth, a.cam.near_plane, a.cam.far_plane)
+                                     : orthographicDepthToViewZ(depth, a.cam.near_plane, a.cam.far_plane);
+  const float viewZ = -gz;
+  // getViewPosition  denoiser_compose_functions.glsl:13-20
+  const float clipW = a.cam.projection.m[2 * 4 + 3] * viewZ + a.cam.projection.m[3 * 4 + 3];
+  v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
+  clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
+  v3 viewPos = xyz(mul(a.cam.projection_inverse, clip));
+  viewPos.z = -viewZ;
+  const v3 viewDir = normalize(viewPos);
+  // pixel-centre fetch of the LINEAR Poisson targets (literal bilinear, like the GL sampler)
+  const v4 dgi = tex_h4_linear(a.diffuse, vUv);
+  const v4 sgi = tex_h4_linear(a.specular, vUv);
+
+  // constructGlobalIllumination :53-107
+  const float roughness = rough0 * rough0;
+  const v3 normal = mul_dir_left(viewNormal, a.cam.view_matrix);
+  v3 T, B;
+  const v3 v = -viewDir;
+  v3 V = mul_dir_left(v, a.cam.view_matrix);
+  const v3 N = normal;
+  Onb(N, T, B);
+  V = ToLocal(T, B, N, V);
+  // r2 = 0.25 => phi = pi/2: (cos, sin) correctly rounded in fp32
+  const float phi = 2.0f * 3.1415926535897932384626433832795f * 0.25f;
+  const float cphi = -4.37113883e-08f;  // (float)cos((double)phi), phi = fp32(pi/2)
+  const float sphi = 1.0f;
+  (void)phi;
+  v3 Hh = SampleGGXVNDF_cs(V, roughness, roughness, 0.25f, cphi, sphi);
+  if (Hh.z < 0.0f) Hh = -Hh;
+  v3 l = normalize(reflect(-V, Hh));
+  l = ToWorld(T, B, N, l);
+  l = xyz(mul(mk4(l, 1.0f), a.cam.camera_matrix_world));  // vec4(l, 1.) * cameraMatrixWorld  (:81)
+  l = normalize(l);
+  if (dot(viewNormal, l) < 0.0f) l = -l;
+  const v3 h = normalize(v + l);
+  const float VoH = fmaxf(1e-6f, dot(v, h));
+  const v3 f0 = mix(mk3(0.04f), diffuse, metalness);
+  const v3 F = f0 + (mk3(1.0f) - f0) * powf(1.0f - VoH, 5.0f);
+  const v3 diffuseComponent = diffuse * (1.0f - metalness) * (mk3(1.0f) - F) * xyz(dgi);
+  const v3 specularComponent = xyz(sgi) * F;
+  const v3 gi = diffuseComponent + specularComponent + emissive;
+  st_f4(a.out.p, a.out.pitch, x, y, make_float4(gi.x, gi.y, gi.z, 1.0f));
+}
+
+cudaError_t launch_gi_compose(const ComposeArgs& a, cudaStream_t s) {
+  if (a.input_type != RFX_INPUT_DIFFUSE_SPECULAR) return cudaErrorNotSupported;
+  const int rb = a.row0 & ~1;
+  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  gi_compose_kernel<<<grid, kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) ssgi_compose_kernel(const __grid_constant__ SsgiComposeArgs a) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = a.row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.W || y >= a.row1) return;
+  const float depth = ld_r32f(a.depth, x, y);
+  v3 c;
+  if (depth == 1.0f) c = xyz(tex_h4_linear(a.scene, pixel_uv(x, y, a.W, a.H)));
+  else c = xyz(f4v(ld_f4(a.gi, x, y)));
+  st_h4(a.out.p, a.out.pitch, x, y, mk4(c, 1.0f));
+}
+cudaError_t launch_ssgi_compose(const SsgiComposeArgs& a, cudaStream_t s) {
+  dim3 grid((a.W + 31) / 32, (a.row1 - a.row0 + 7) / 8);
+  ssgi_compose_kernel<<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace rfx

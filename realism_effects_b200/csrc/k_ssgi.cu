@@ -1,0 +1,396 @@
+// k_ssgi.cu — K1 SSGI / SSR depth-buffer ray march (sm_100a).
+//
+// Replaces the fullscreen draw of reference src/ssgi/pass/SSGIPass.js:93-94
+// (shader src/ssgi/shader/ssgi.frag:105-503 + ssgi_utils.frag).
+//
+// Blackwell mapping: one thread per pixel, a warp owns an 8x4 pixel tile laid out in 2x2 quads so
+// the implicit-LOD env fetch (ssgi_utils.frag:218) gets its quad derivatives from two shuffles.
+// The march is a data-dependent gather over the (L2-resident) depth plane; the ray positions do not
+// depend on the fetched depths, so the taps of a batch of RFX_MARCH_BATCH steps are issued together
+// (memory-level parallelism instead of a 19-deep dependent chain) and tested in order afterwards.
+// All blue-noise driven transcendentals (sin/cos of 2*pi*k/255, the march step profile
+// 1-exp(-0.25 (i+b-0.5)^2)) come from small host-built tables indexed by the 8-bit noise value.
+#include "rfx_kernels.h"
+
+#ifndef RFX_MARCH_BATCH
+#define RFX_MARCH_BATCH 4
+#endif
+
+namespace rfx {
+
+#define SSGI_EPSILON 0.00001f
+#define SSGI_ONE_MINUS_EPSILON (1.0f - 0.00001f)
+#define PI_F 3.1415926535897932384626433832795f
+
+RFX_D float lum_s(v3 a) { return dot(mk3(0.2125f, 0.7154f, 0.0721f), a); }  // ssgi_utils.frag:3
+
+struct SsgiCtx {
+  const SsgiArgs& a;
+  __device__ SsgiCtx(const SsgiArgs& a_) : a(a_) {}
+  RFX_D float getViewZ(float depth) const {  // ssgi_utils.frag:7-13
+    if (a.cam.perspective) return a.near_mul_far / (a.far_minus_near * depth - a.cam.far_plane);
+    return depth * a.near_minus_far - a.cam.near_plane;
+  }
+  RFX_D v2 viewSpaceToScreenSpace(v3 p) const {  // :26-33
+    v4 pc = mul(a.cam.projection, mk4(p, 1.0f));
+    return mk2(pc.x / pc.w * 0.5f + 0.5f, pc.y / pc.w * 0.5f + 0.5f);
+  }
+};
+
+RFX_D v2 equirectDirectionToUv(v3 d) {  // ssgi_utils.frag:64-74
+  v2 uv = mk2(atan2f(d.z, d.x), acosf(d.y));
+  uv = mk2(uv.x / (2.0f * PI_F), uv.y / PI_F);
+  uv.x += 0.5f;
+  uv.y = 1.0f - uv.y;
+  return uv;
+}
+RFX_D v3 equirectUvToDirection(v2 uv) {  // :77-86
+  uv.x -= 0.5f;
+  uv.y = 1.0f - uv.y;
+  float theta = uv.x * 2.0f * PI_F;
+  float phi = uv.y * PI_F;
+  float sinPhi = sinf(phi);
+  return mk3(sinPhi * cosf(theta), cosf(phi), sinPhi * sinf(theta));
+}
+RFX_D float F_Schlick1(float f0, float f90, float theta) { return f0 + (f90 - f0) * powf(1.0f - theta, 5.0f); }
+RFX_D float D_GTR2(float roughness, float NoH) {  // D_GTR(roughness, NoH, 2.)
+  float a2 = roughness * roughness;
+  float t = (NoH * NoH) * (a2 * a2 - 1.0f) + 1.0f;
+  return a2 / (PI_F * (t * t));
+}
+RFX_D float SmithG(float NDotV, float alphaG) {
+  float a = alphaG * alphaG;
+  float b = NDotV * NDotV;
+  return (2.0f * NDotV) / (NDotV + sqrtf(a + b - a * b));
+}
+RFX_D float GGXVNDFPdf(float NoH, float NoV, float roughness) {
+  float D = D_GTR2(roughness, NoH);
+  float G1 = SmithG(NoV, roughness * roughness);
+  return (D * G1) / fmaxf(0.00001f, 4.0f * NoV);
+}
+RFX_D float evalDisneyDiffuse(float NoL, float NoV, float LoH, float roughness, float metalness) {
+  float FD90 = 0.5f + 2.0f * roughness * (LoH * LoH);
+  float a = F_Schlick1(1.0f, FD90, NoL);
+  float b = F_Schlick1(1.0f, FD90, NoV);
+  return (a * b / PI_F) * (1.0f - metalness);
+}
+RFX_D float evalDisneySpecular(float roughness, float NoH, float NoV, float NoL) {
+  float D = D_GTR2(roughness, NoH);
+  float ag = 0.5f + roughness * 0.5f;
+  ag = ag * ag;
+  float a2 = ag * ag;  // GeometryTerm: a2 = roughness * roughness with roughness := pow(.5 + r*.5, 2.)
+  float G = SmithG(NoV, a2) * SmithG(NoL, a2);
+  return D * G / (4.0f * NoL * NoV);
+}
+RFX_D v3 cosineSampleHemisphere_cs(v3 n, float ux, float sth, float cth) {  // ssgi_utils.frag:183-191
+  float r = sqrtf(ux);
+  v3 b = normalize(cross(n, mk3(0.0f, 1.0f, 1.0f)));
+  v3 t = cross(b, n);
+  return normalize(r * sth * b + sqrtf(1.0f - ux) * n + r * cth * t);
+}
+RFX_D void calculateAngles(v3 l, v3 v, v3 n, float& NoL, float& NoH, float& LoH, float& VoH) {  // ssgi.frag:93-100
+  v3 h = normalize(v + l);
+  NoL = clampf(dot(n, l), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
+  NoH = clampf(dot(n, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
+  LoH = clampf(dot(l, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
+  VoH = clampf(dot(v, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
+}
+
+// textureLod(map, uv, lod) with linear-mipmap-linear / clamp
+RFX_D v3 env_trilinear(const EnvD& e, v2 uv, float lod) {
+  float l = clampf(lod, 0.0f, (float)(e.levels - 1));
+  int l0 = (int)floorf(l);
+  int l1 = min(l0 + 1, e.levels - 1);
+  float f = l - (float)l0;
+  v4 A = tex_h4_linear(e.mip[l0], uv);
+  if (f == 0.0f || l1 == l0) return xyz(A);
+  v4 B = tex_h4_linear(e.mip[l1], uv);
+  return mk3(mixf(A.x, B.x, f), mixf(A.y, B.y, f), mixf(A.z, B.z, f));
+}
+
+// getEnvColor  ssgi.frag:311-346
+RFX_D v3 getEnvColor(const SsgiArgs& a, v3 l, float roughness, bool isDiffuseSample, bool isEnvSample) {
+  if (!(a.flags & RFX_SSGI_USE_ENVMAP)) return mk3(0.0f);
+  v3 reflectedWS = normalize(mul_dir_left(l, a.cam.view_matrix));
+  float mip = a.env_blur * a.max_env_mip;
+  if (!isDiffuseSample && roughness < 0.15f) mip *= roughness / 0.15f;
+  v3 s = env_trilinear(a.env, equirectDirectionToUv(reflectedWS), mip);
+  float maxEnvLum = isEnvSample ? 100.0f : 25.0f;
+  float envLum = lum_s(s);
+  if (envLum > maxEnvLum) s = s * (maxEnvLum / envLum);
+  return s;
+}
+
+RFX_D float getSaturation(v3 c) {  // :348-360
+  float mx = fmaxf(fmaxf(c.x, c.y), c.z), mn = fminf(fminf(c.x, c.y), c.z);
+  if (mx == mn) return 0.0f;
+  return (mx - mn) / mx;
+}
+
+// RayMarch + BinarySearch  ssgi.frag:441-503.  `dir` is l scaled in place like the shader's inout.
+// Returns the hit uv; sets hit=false and hitPos=(10e9) on a miss.
+RFX_D v2 rayMarch(const SsgiArgs& a, const SsgiCtx& c, v3& dir, v3& hitPos, int noiseB, bool& hit) {
+  dir = dir * (a.ray_distance / (float)a.steps);
+  v2 uv = mk2(0.0f, 0.0f);
+  hit = false;
+  const float* cs_row = a.step_table + noiseB;  // cs(i, b) at [(i-1)*256 + b]
+  int i = 1;
+  while (i < a.steps && !hit) {
+    v3 pos[RFX_MARCH_BATCH];
+    v2 uvs[RFX_MARCH_BATCH];
+    float dep[RFX_MARCH_BATCH];
+    v3 p = hitPos;
+#pragma unroll
+    for (int k = 0; k < RFX_MARCH_BATCH; k++) {  // issue the whole batch of depth taps before testing any
+      const int ii = min(i + k, a.steps - 1);
+      const float cs = __ldg(cs_row + (ii - 1) * 256);
+      p = p + dir * cs;
+      pos[k] = p;
+      uvs[k] = c.viewSpaceToScreenSpace(p);
+      dep[k] = tex_r32f_nearest(a.depth, uvs[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < RFX_MARCH_BATCH; k++) {
+      if (!hit && i + k < a.steps) {
+        const float z = c.getViewZ(dep[k]);
+        const float diff = z - pos[k].z;
+        hitPos = pos[k];
+        uv = uvs[k];
+        if (diff >= 0.0f && diff < a.thickness) hit = true;
+      }
+    }
+    i += RFX_MARCH_BATCH;
+  }
+  if (!hit) {
+    hitPos = mk3(10.0e9f);
+    return uv;
+  }
+  if (a.refine_steps == 0) return uv;
+  // BinarySearch
+  dir = dir * 0.5f;
+  hitPos = hitPos - dir;
+  for (int r = 0; r < a.refine_steps; r++) {
+    v2 u = c.viewSpaceToScreenSpace(hitPos);
+    const float z = c.getViewZ(tex_r32f_nearest(a.depth, u));
+    const float diff = z - hitPos.z;
+    dir = dir * 0.5f;
+    if (diff >= 0.0f) hitPos = hitPos - dir; else hitPos = hitPos + dir;
+  }
+  return c.viewSpaceToScreenSpace(hitPos);
+}
+
+struct PixelMat {
+  v3 diffuse;
+  float roughness, metalness;
+};
+
+// doSample  ssgi.frag:362-439
+RFX_D v3 doSample(const SsgiArgs& a, const SsgiCtx& c, const PixelMat& m, v3 viewPos, v3 viewNormal, float roughnessSq, bool isDiffuseSample,
+                  bool isEnvSample, float NoV, float NoL, float NoH, float LoH, int noiseB, v3& l, v3& hitPos, float& brdf, float& pdf) {
+  const float cosTheta = fmaxf(0.0f, dot(viewNormal, l));
+  if (isDiffuseSample) {
+    brdf = evalDisneyDiffuse(NoL, NoV, LoH, roughnessSq, m.metalness);
+    pdf = NoL / PI_F;
+  } else {
+    brdf = evalDisneySpecular(roughnessSq, NoH, NoV, NoL);
+    pdf = GGXVNDFPdf(NoH, NoV, roughnessSq);
+  }
+  brdf *= cosTheta;
+  pdf = fmaxf(SSGI_EPSILON, pdf);
+  hitPos = viewPos;
+  bool hit;
+  const v2 coords = rayMarch(a, c, l, hitPos, noiseB, hit);
+  const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
+  if (!hit && !allowMissedRays) return getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  v2 vel = mk2(0.0f, 0.0f);
+  if (a.velocity.p) { float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }  // :400 (null sampler => 0)
+  const v2 ruv = coords - vel;
+  const v3 envColor = getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  v3 SSGI;
+  if (ruv.x >= 0.0f && ruv.x <= 1.0f && ruv.y >= 0.0f && ruv.y <= 1.0f) {
+    v3 rgi = mk3(0.0f);
+    if (a.accumulated.p) rgi = xyz(f4v(tex_f4_nearest(a.accumulated, ruv)));
+    const float saturation = getSaturation(m.diffuse);
+    rgi = mix(rgi, mk3(lum_s(rgi)), (1.0f - roughnessSq) * saturation * 0.4f);
+    const float border = 0.15f;
+    float bf = smoothstepf(0.0f, border, coords.x) * smoothstepf(1.0f, 1.0f - border, coords.x) * smoothstepf(0.0f, border, coords.y) *
+               smoothstepf(1.0f, 1.0f - border, coords.y);
+    bf = sqrtf(bf);
+    SSGI = mix(envColor, rgi, bf);
+  } else {
+    return envColor;
+  }
+  if (allowMissedRays) {  // envMapSample is vec3(0.) here (:393,430-436)
+    if (0.0f > lum_s(SSGI)) SSGI = mk3(0.0f);
+  }
+  return SSGI;
+}
+
+template <int MODE, bool IS>
+__global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
+  int x, y;
+  block_pixel(x, y, a.row0 & ~1);
+  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const SsgiCtx c(a);
+  const uchar4 bn = __ldg(a.blue.tex + ((y + a.blue.shift.sy) % a.blue.size) * a.blue.size + ((x + a.blue.shift.sx) % a.blue.size));
+  const v4 random = mk4((float)bn.x / 255.0f, (float)bn.y / 255.0f, (float)bn.z / 255.0f, (float)bn.w / 255.0f);
+
+  // env importance sample: CDF lookup + implicit-LOD colour fetch need all four quad lanes
+  v2 cdfUv = mk2(0.0f, 0.0f);
+  float lambda = 0.0f;
+  if (IS) {
+    const float v = ld_r32f(a.env.marginal, nearest_i(random.x, a.env.marginal.w), 0);                                     // ssgi_utils.frag:212
+    const float u = ld_r32f(a.env.conditional, nearest_i(random.y, a.env.conditional.w), nearest_i(v, a.env.conditional.h));  // :213
+    cdfUv = mk2(u, v);
+    const unsigned full = 0xffffffffu;
+    const v2 ux = mk2(__shfl_xor_sync(full, u, 1), __shfl_xor_sync(full, v, 1));
+    const v2 uy = mk2(__shfl_xor_sync(full, u, 2), __shfl_xor_sync(full, v, 2));
+    const v2 sz = mk2(a.env.size_x, a.env.size_y);
+    const v2 ddx = (ux - cdfUv) * sz, ddy = (uy - cdfUv) * sz;
+    const float rho = fmaxf(length(ddx), length(ddy));
+    lambda = rho > 0.0f ? log2f(rho) : -1000.0f;
+  }
+  if (!active) return;
+
+  const v2 vUv = pixel_uv(x, y, a.W, a.H);
+  const float unpackedDepth = ld_r32f(a.depth, x, y);
+  if (unpackedDepth == 1.0f) {  // background :109-113
+    v4 dl = mk4(0.0f, 0.0f, 0.0f, 1.0f);
+    if (a.direct.p) dl = tex_h4_linear(a.direct, vUv);
+    st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(dl, dl));
+    return;
+  }
+  const float4 g = ld_f4(a.gb, x, y);
+  PixelMat m;
+  m.diffuse = xyz(floatToVec4(g.x));
+  const v3 worldNormal = unpackNormal(g.y);
+  m.roughness = gb_roughness(g.z);
+  m.metalness = gb_metalness(g.z);
+  const float roughnessSq = clampf(m.roughness * m.roughness, 0.000001f, 1.0f);
+
+  const float viewZ = c.getViewZ(unpackedDepth);
+  // getViewPosition  ssgi_utils.frag:17-24
+  v3 viewPos;
+  {
+    const float clipW = a.cam.projection.m[2 * 4 + 3] * viewZ + a.cam.projection.m[3 * 4 + 3];
+    v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
+    clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
+    viewPos = xyz(mul(a.cam.projection_inverse, clip));
+    viewPos.z = viewZ;
+  }
+  const v3 viewDir = normalize(viewPos);
+  const v3 viewNormal = normalize(mul_dir_left(worldNormal, a.cam.camera_matrix_world));
+  const v3 n = viewNormal;
+  const v3 v = -viewDir;
+  const float NoV = fmaxf(SSGI_EPSILON, dot(n, v));
+  v3 V = mul_dir_left(v, a.cam.view_matrix);
+  const v3 N = worldNormal;
+  v3 T, B;
+  Onb(N, T, B);
+  V = ToLocal(T, B, N, V);
+  const v3 f0 = mix(mk3(0.04f), m.diffuse, m.metalness);
+
+  const float2 sc = __ldg(a.rot_table + bn.y);  // (sin, cos) of 2*pi*random.g
+  v3 Hh = SampleGGXVNDF_cs(V, roughnessSq, roughnessSq, random.x, sc.y, sc.x);
+  if (Hh.z < 0.0f) Hh = -Hh;
+  v3 l = normalize(reflect(-V, Hh));
+  l = ToWorld(T, B, N, l);
+  l = mul_dir_left(l, a.cam.camera_matrix_world);
+  l = normalize(l);
+  float NoL, NoH, LoH, VoH;
+  calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+
+  bool isDiffuseSample = false;
+  if (MODE == RFX_MODE_SSGI) {
+    const v3 F = f0 + (mk3(1.0f) - f0) * powf(1.0f - VoH, 5.0f);
+    float diffW = (1.0f - m.metalness) * lum_s(m.diffuse);
+    float specW = lum_s(F);
+    diffW = fmaxf(diffW, SSGI_EPSILON);
+    specW = fmaxf(specW, SSGI_EPSILON);
+    const float invW = 1.0f / (diffW + specW);
+    diffW *= invW;
+    isDiffuseSample = random.z < diffW;
+  }
+
+  float emsPdf = 1.0f, emsProbability = 0.0f;
+  bool emsIsEnvSample = false;
+  v3 envMisDir = mk3(0.0f);
+  if (IS) {  // ssgi.frag:197-215, ssgi_utils.frag:210-225
+    envMisDir = equirectUvToDirection(cdfUv);
+    const v3 color = env_trilinear(a.env, cdfUv, lambda);
+    const float totalSum = a.env.total_sum_whole + a.env.total_sum_decimal;
+    const float pdf0 = lum_s(color) / totalSum;
+    emsPdf = a.env.size_x * a.env.size_y * pdf0;
+    envMisDir = normalize(mul_dir_left(envMisDir, a.cam.camera_matrix_world));
+    emsProbability = dot(envMisDir, viewNormal);
+    emsProbability *= m.roughness;
+    emsProbability = fminf(SSGI_ONE_MINUS_EPSILON, emsProbability);
+    emsIsEnvSample = random.w < emsProbability;
+    if (emsIsEnvSample) {
+      emsPdf /= 1.0f - emsProbability;
+      l = envMisDir;
+      calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+    } else {
+      emsPdf = 1.0f - emsProbability;
+    }
+  }
+  const v3 diffuseRay = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs(viewNormal, random.x, sc.x, sc.y);
+  const v3 specularRay = emsIsEnvSample ? envMisDir : l;
+
+  v3 diffuseGI = mk3(0.0f), specularGI = mk3(0.0f), hitPos = mk3(0.0f);
+  float brdf, pdf;
+  bool haveDiffuse = false;
+  if (MODE == RFX_MODE_SSGI && isDiffuseSample) {  // :222-242
+    l = diffuseRay;
+    calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+    v3 gi = doSample(a, c, m, viewPos, viewNormal, roughnessSq, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    gi = gi * brdf;
+    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * (aa / (aa + bb)); } else gi = gi / pdf;
+    gi = gi / emsPdf;
+    diffuseGI = mix(diffuseGI, gi, 1.0f / 1.0f);  // diffuseSamples == 1
+    haveDiffuse = true;
+  }
+  l = specularRay;  // :246-265
+  calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+  {
+    v3 gi = doSample(a, c, m, viewPos, viewNormal, roughnessSq, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    gi = gi * brdf;
+    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * (aa / (aa + bb)); } else gi = gi / pdf;
+    gi = gi / emsPdf;
+    specularGI = mix(specularGI, gi, 1.0f / 1.0f);
+  }
+  const v3 specularHitPos = hitPos;
+  if (a.flags & RFX_SSGI_USE_DIRECT_LIGHT) {  // :267-272
+    v3 dl = mk3(0.0f);
+    if (a.direct.p) dl = xyz(tex_h4_linear(a.direct, vUv));
+    diffuseGI = diffuseGI + dl;
+    specularGI = specularGI + dl;
+  }
+  float rayLength = 0.0f;
+  if (!(hitPos.x > 10.0e8f)) {  // :288-296
+    const v3 cameraPosWS = mk3(a.cam.camera_matrix_world.m[12], a.cam.camera_matrix_world.m[13], a.cam.camera_matrix_world.m[14]);
+    const v3 hitPosWS = xyz(mul(a.cam.camera_matrix_world, mk4(specularHitPos, 1.0f)));
+    rayLength = length(cameraPosWS - hitPosWS);
+  }
+  if (MODE == RFX_MODE_SSGI) {
+    if (!haveDiffuse) diffuseGI = mk3(-1.0f);
+    st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(mk4(diffuseGI, m.roughness), mk4(specularGI, rayLength)));
+  } else {
+    const float al = __uint_as_float(packHalf2x16(rayLength, m.roughness));
+    st_f4(a.out.p, a.out.pitch, x, y, make_float4(specularGI.x, specularGI.y, specularGI.z, al));
+  }
+}
+
+cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {
+  const int rb = a.row0 & ~1;
+  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  const bool is = (a.flags & RFX_SSGI_IMPORTANCE_SAMPLING) != 0;
+  if (a.mode == RFX_MODE_SSGI) {
+    if (is) ssgi_kernel<RFX_MODE_SSGI, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<RFX_MODE_SSGI, false><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (is) ssgi_kernel<RFX_MODE_SSR, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<RFX_MODE_SSR, false><<<grid, kThreads, 0, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace rfx

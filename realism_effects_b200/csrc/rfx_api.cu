@@ -1,0 +1,689 @@
+// rfx_api.cu — implementation of the C ABI declared in include/rfx.h.
+//
+// Host-side responsibilities: argument validation, plane bookkeeping, the small per-context
+// tables the kernels index by 8-bit blue-noise values, the env-map mip chain, and the native
+// SSGI chain (the mirror of SSGIEffect.update / Denoiser.render frame logic).  No torch types, no
+// exceptions across the boundary, no CPU fallback: every compute entry point launches a kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rfx_kernels.h"
+
+using namespace rfx;
+
+struct rfx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  // blue noise
+  uchar4* blue = nullptr;
+  int blue_size = 0;
+  // tables
+  float2* rot_table = nullptr;  // [256]
+  float* step_table = nullptr;  // [steps-1][256]
+  int step_table_steps = 0;
+  // env
+  bool env_set = false;
+  EnvD env{};
+  std::vector<void*> env_allocs;
+};
+
+static rfx_status fail(rfx_ctx* c, rfx_status st, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return st;
+}
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(ctx, RFX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static const float kPi = 3.1415926535897932384626433832795f;
+
+extern "C" {
+
+int rfx_version(void) { return RFX_VERSION; }
+uint32_t rfx_format_bytes(int32_t f) { return f == RFX_FMT_R32F ? 4u : f == RFX_FMT_RGBA32F ? 16u : f == RFX_FMT_RGBA16F ? 8u : f == RFX_FMT_RGBA8 ? 4u : 0u; }
+
+rfx_status rfx_ctx_create(int device, rfx_ctx** out) {
+  if (!out) return RFX_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return RFX_ERR_CUDA;
+  rfx_ctx* ctx = new rfx_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return RFX_ERR_CUDA;
+  }
+  // (sin, cos) of the fp32 angle (k/255)*2*pi, correctly rounded: the 256 values blueNoise().r/.g can take
+  float2 rot[256];
+  for (int k = 0; k < 256; k++) {
+    volatile float r = (float)k / 255.0f;
+    volatile float r2 = r * 2.0f;
+    volatile float ang = r2 * kPi;
+    rot[k].x = (float)std::sin((double)ang);
+    rot[k].y = (float)std::cos((double)ang);
+  }
+  if (cudaMalloc(&ctx->rot_table, sizeof rot) != cudaSuccess || cudaMemcpy(ctx->rot_table, rot, sizeof rot, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RFX_ERR_CUDA;
+  }
+  *out = ctx;
+  return RFX_OK;
+}
+
+static void free_env(rfx_ctx* ctx) {
+  for (void* p : ctx->env_allocs) cudaFree(p);
+  ctx->env_allocs.clear();
+  ctx->env_set = false;
+  ctx->env = EnvD{};
+}
+
+void rfx_ctx_destroy(rfx_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_env(ctx);
+  cudaFree(ctx->blue);
+  cudaFree(ctx->rot_table);
+  cudaFree(ctx->step_table);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+const char* rfx_last_error(const rfx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* rfx_ctx_stream(rfx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+rfx_status rfx_ctx_sync(rfx_ctx* ctx) {
+  if (!ctx) return RFX_ERR_INVALID_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RFX_OK;
+}
+uint64_t rfx_launch_count(const rfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+rfx_status rfx_blue_noise_set(rfx_ctx* ctx, const uint8_t* rgba8, uint32_t w, uint32_t h) {
+  if (!ctx || !rgba8 || w != h || w == 0) return fail(ctx, RFX_ERR_INVALID_ARG, "blue noise must be a square RGBA8 image");
+  CU(cudaSetDevice(ctx->device));
+  cudaFree(ctx->blue);
+  ctx->blue = nullptr;
+  CU(cudaMalloc(&ctx->blue, (size_t)w * h * 4));
+  CU(cudaMemcpy(ctx->blue, rgba8, (size_t)w * h * 4, cudaMemcpyHostToDevice));
+  ctx->blue_size = (int)w;
+  return RFX_OK;
+}
+
+// ---- planes -----------------------------------------------------------------------------
+rfx_status rfx_plane_alloc(rfx_ctx* ctx, int32_t format, uint32_t w, uint32_t h, rfx_plane* out) {
+  if (!ctx || !out || w == 0 || h == 0 || rfx_format_bytes(format) == 0) return fail(ctx, RFX_ERR_INVALID_ARG, "plane_alloc: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  size_t pitch = ((size_t)w * rfx_format_bytes(format) + 255) & ~(size_t)255;
+  void* p = nullptr;
+  CU(cudaMalloc(&p, pitch * h));
+  CU(cudaMemsetAsync(p, 0, pitch * h, ctx->stream));  // targets are zero after allocation
+  CU(cudaStreamSynchronize(ctx->stream));
+  out->ptr = p; out->width = w; out->height = h; out->pitch = pitch; out->format = format; out->_reserved = 0;
+  return RFX_OK;
+}
+rfx_status rfx_plane_free(rfx_ctx* ctx, rfx_plane* p) {
+  if (!ctx || !p) return RFX_ERR_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaFree(p->ptr));
+  p->ptr = nullptr;
+  return RFX_OK;
+}
+static cudaStream_t pick(rfx_ctx* ctx, void* s) { return s ? (cudaStream_t)s : ctx->stream; }
+rfx_status rfx_plane_clear(rfx_ctx* ctx, void* stream, const rfx_plane* p) {
+  if (!ctx || !p || !p->ptr) return RFX_ERR_INVALID_ARG;
+  CU(cudaMemsetAsync(p->ptr, 0, p->pitch * p->height, pick(ctx, stream)));
+  return RFX_OK;
+}
+rfx_status rfx_plane_upload(rfx_ctx* ctx, void* stream, const rfx_plane* dst, const void* host, uint64_t host_pitch) {
+  if (!ctx || !dst || !dst->ptr || !host) return RFX_ERR_INVALID_ARG;
+  size_t row = (size_t)dst->width * rfx_format_bytes(dst->format);
+  if (host_pitch == 0) host_pitch = row;
+  CU(cudaMemcpy2DAsync(dst->ptr, dst->pitch, host, host_pitch, row, dst->height, cudaMemcpyHostToDevice, pick(ctx, stream)));
+  return RFX_OK;
+}
+rfx_status rfx_plane_download(rfx_ctx* ctx, void* stream, const rfx_plane* src, void* host, uint64_t host_pitch) {
+  if (!ctx || !src || !src->ptr || !host) return RFX_ERR_INVALID_ARG;
+  size_t row = (size_t)src->width * rfx_format_bytes(src->format);
+  if (host_pitch == 0) host_pitch = row;
+  CU(cudaMemcpy2DAsync(host, host_pitch, src->ptr, src->pitch, row, src->height, cudaMemcpyDeviceToHost, pick(ctx, stream)));
+  return RFX_OK;
+}
+rfx_status rfx_host_alloc(rfx_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return RFX_ERR_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return RFX_OK;
+}
+rfx_status rfx_host_free(rfx_ctx* ctx, void* p) {
+  if (!ctx) return RFX_ERR_INVALID_ARG;
+  CU(cudaFreeHost(p));
+  return RFX_OK;
+}
+
+// ---- env map ----------------------------------------------------------------------------
+rfx_status rfx_env_clear(rfx_ctx* ctx) {
+  if (!ctx) return RFX_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_env(ctx);
+  return RFX_OK;
+}
+rfx_status rfx_env_set(rfx_ctx* ctx, const rfx_env_desc* e) {
+  if (!ctx || !e || !e->map_rgba16f || e->width == 0 || e->height == 0) return fail(ctx, RFX_ERR_INVALID_ARG, "env_set: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_env(ctx);
+  int w = (int)e->width, h = (int)e->height, l = 0;
+  EnvD d{};
+  for (;;) {
+    if (l >= 16) return fail(ctx, RFX_ERR_UNSUPPORTED, "env map too large");
+    size_t pitch = ((size_t)w * 8 + 255) & ~(size_t)255;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, pitch * h));
+    ctx->env_allocs.push_back(p);
+    d.mip[l] = PV{(const unsigned char*)p, w, h, (long long)pitch};
+    if (l == 0) {
+      CU(cudaMemcpy2DAsync(p, pitch, e->map_rgba16f, (size_t)w * 8, (size_t)w * 8, h, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      cudaError_t ce = launch_env_downsample(d.mip[l - 1], OutV{(unsigned char*)p, (long long)pitch}, w, h, ctx->stream);
+      if (ce != cudaSuccess) return fail(ctx, RFX_ERR_CUDA, "env downsample: %s", cudaGetErrorString(ce));
+      ctx->launches++;
+    }
+    l++;
+    if (w == 1 && h == 1) break;
+    w = w > 1 ? w >> 1 : 1;
+    h = h > 1 ? h >> 1 : 1;
+  }
+  d.levels = l;
+  d.size_x = (float)e->width;
+  d.size_y = (float)e->height;
+  d.total_sum_whole = e->total_sum_whole;
+  d.total_sum_decimal = e->total_sum_decimal;
+  if (e->marginal && e->conditional) {
+    float *m = nullptr, *c = nullptr;
+    CU(cudaMalloc(&m, (size_t)e->height * 4));
+    ctx->env_allocs.push_back(m);
+    CU(cudaMalloc(&c, (size_t)e->width * e->height * 4));
+    ctx->env_allocs.push_back(c);
+    CU(cudaMemcpyAsync(m, e->marginal, (size_t)e->height * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(c, e->conditional, (size_t)e->width * e->height * 4, cudaMemcpyHostToDevice, ctx->stream));
+    d.marginal = PV{(const unsigned char*)m, (int)e->height, 1, (long long)e->height * 4};  // image {width: height, height: 1}
+    d.conditional = PV{(const unsigned char*)c, (int)e->width, (int)e->height, (long long)e->width * 4};
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->env = d;
+  ctx->env_set = true;
+  return RFX_OK;
+}
+
+}  // extern "C"
+
+// ---- helpers ------------------------------------------------------------------------------
+static bool pv(const rfx_plane* p, int fmt, PV& out) {
+  if (!p || !p->ptr || p->format != fmt) return false;
+  out = PV{(const unsigned char*)p->ptr, (int)p->width, (int)p->height, (long long)p->pitch};
+  return true;
+}
+static bool ov(const rfx_plane* p, int fmt, OutV& out) {
+  if (!p || !p->ptr || p->format != fmt) return false;
+  out = OutV{(unsigned char*)p->ptr, (long long)p->pitch};
+  return true;
+}
+static void cam_to_dev(const rfx_camera& c, CamD& d) {
+  memcpy(d.projection.m, c.projection, 64);
+  memcpy(d.projection_inverse.m, c.projection_inverse, 64);
+  memcpy(d.camera_matrix_world.m, c.camera_matrix_world, 64);
+  memcpy(d.view_matrix.m, c.view_matrix, 64);
+  d.near_plane = c.near_plane;
+  d.far_plane = c.far_plane;
+  d.perspective = c.perspective;
+}
+// pcg4d  (reference src/utils/shader/blue_noise.glsl:17-28), integer, bit-exact
+static void pcg4d(uint32_t v[4]) {
+  for (int i = 0; i < 4; i++) v[i] = v[i] * 1664525u + 1013904223u;
+  v[0] += v[1] * v[3]; v[1] += v[2] * v[0]; v[2] += v[0] * v[1]; v[3] += v[1] * v[2];
+  for (int i = 0; i < 4; i++) v[i] ^= v[i] >> 16;
+  v[0] += v[1] * v[3]; v[1] += v[2] * v[0]; v[2] += v[0] * v[1]; v[3] += v[1] * v[2];
+}
+static rfx_status blue_for(rfx_ctx* ctx, int index, BlueD& b) {
+  if (!ctx->blue) return fail(ctx, RFX_ERR_NOT_READY, "blue noise texture not set (rfx_blue_noise_set)");
+  uint32_t ui = (uint32_t)index;
+  uint32_t s1[4] = {ui, ui * 15843u, ui * 31u + 4566u, ui * 2345u + 58585u};  // rng_initialize :13
+  pcg4d(s1);
+  b.tex = ctx->blue;
+  b.size = ctx->blue_size;
+  b.shift.sx = (int)((s1[0] % 0x0fffffffu) % (uint32_t)ctx->blue_size);  // shift2 :31-34
+  b.shift.sy = (int)((s1[1] % 0x0fffffffu) % (uint32_t)ctx->blue_size);
+  b.index = index;
+  return RFX_OK;
+}
+static void rows(uint32_t row0, uint32_t row1, uint32_t H, int& r0, int& r1) {
+  if (row0 == 0 && row1 == 0) { r0 = 0; r1 = (int)H; }
+  else { r0 = (int)row0; r1 = (int)(row1 > H ? H : row1); }
+}
+// mat4 * mat4 with the oracle's lowering: s = ((a0*b0 + a1*b1) + a2*b2) + a3*b3, no contraction
+static void matmul(const float* A, const float* B, float* R) {
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) {
+      volatile float s = 0.0f;
+      for (int k = 0; k < 4; k++) {
+        volatile float p = A[k * 4 + r] * B[c * 4 + k];
+        s = s + p;
+      }
+      R[c * 4 + r] = s;
+    }
+}
+static rfx_status ensure_step_table(rfx_ctx* ctx, int steps) {
+  if (ctx->step_table && ctx->step_table_steps == steps) return RFX_OK;
+  if (steps < 1 || steps > 4096) return fail(ctx, RFX_ERR_INVALID_ARG, "steps out of range");
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->step_table);
+  ctx->step_table = nullptr;
+  int rows_n = steps > 1 ? steps - 1 : 1;
+  std::vector<float> t((size_t)rows_n * 256, 0.0f);
+  for (int i = 1; i < steps; i++)
+    for (int k = 0; k < 256; k++) {  // ssgi.frag:453   cs = 1. - exp(-0.25 * pow(float(i) + random.b - 0.5, 2.))
+      volatile float b = (float)k / 255.0f;
+      volatile float u = (float)i + b;
+      volatile float v = u - 0.5f;
+      volatile float p = (float)std::pow((double)v, 2.0);
+      volatile float q = -0.25f * p;
+      volatile float e = (float)std::exp((double)q);
+      t[(size_t)(i - 1) * 256 + k] = 1.0f - e;
+    }
+  CU(cudaMalloc(&ctx->step_table, t.size() * 4));
+  CU(cudaMemcpy(ctx->step_table, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+  ctx->step_table_steps = steps;
+  return RFX_OK;
+}
+#define LAUNCHED(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, RFX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));      \
+    ctx->launches++;                                                                                     \
+  } while (0)
+
+extern "C" {
+
+rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_params* p, const rfx_plane* depth, const rfx_plane* gbuffer,
+                                 const rfx_plane* velocity, const rfx_plane* direct_light, const rfx_plane* accumulated, const rfx_plane* out,
+                                 uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "ssgi_trace: null argument");
+  SsgiArgs a{};
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gbuffer, RFX_FMT_RGBA32F, a.gb) || !ov(out, RFX_FMT_RGBA32F, a.out))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_trace: depth must be R32F, gbuffer/out RGBA32F");
+  if (velocity && !pv(velocity, RFX_FMT_RGBA32F, a.velocity)) return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_trace: velocity must be RGBA32F");
+  if (direct_light && !pv(direct_light, RFX_FMT_RGBA16F, a.direct)) return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_trace: direct light must be RGBA16F");
+  if (accumulated && !pv(accumulated, RFX_FMT_RGBA32F, a.accumulated)) return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_trace: accumulated must be RGBA32F");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.gb.h != a.H || (a.velocity.p && (a.velocity.w != a.W || a.velocity.h != a.H)) ||
+      (a.direct.p && (a.direct.w != a.W || a.direct.h != a.H)) || (a.accumulated.p && (a.accumulated.w != a.W || a.accumulated.h != a.H)))
+    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_trace: all planes must match the output size (resolutionScale != 1 is not supported)");
+  if (p->steps < 1 || p->refine_steps < 0 || (p->mode != RFX_MODE_SSGI && p->mode != RFX_MODE_SSR)) return fail(ctx, RFX_ERR_INVALID_ARG, "ssgi_trace: bad steps/mode");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  cam_to_dev(p->cam, a.cam);
+  a.ray_distance = p->ray_distance; a.thickness = p->thickness; a.env_blur = p->env_blur; a.max_env_mip = p->max_env_map_mip_level;
+  a.near_minus_far = p->cam.near_plane - p->cam.far_plane;  // SSGIPass.js:85-87
+  a.far_minus_near = p->cam.far_plane - p->cam.near_plane;
+  a.near_mul_far = p->cam.near_plane * p->cam.far_plane;
+  a.steps = p->steps; a.refine_steps = p->refine_steps; a.mode = p->mode; a.flags = p->flags;
+  if (p->flags & (RFX_SSGI_USE_ENVMAP | RFX_SSGI_IMPORTANCE_SAMPLING)) {
+    if (!ctx->env_set) return fail(ctx, RFX_ERR_NOT_READY, "ssgi_trace: env map requested but rfx_env_set was not called");
+    if ((p->flags & RFX_SSGI_IMPORTANCE_SAMPLING) && !ctx->env.marginal.p) return fail(ctx, RFX_ERR_NOT_READY, "ssgi_trace: importance sampling needs CDF tables");
+    a.env = ctx->env;
+  }
+  rfx_status st = blue_for(ctx, p->blue_noise_index, a.blue);
+  if (st != RFX_OK) return st;
+  if (p->blue_noise_index == 0) return fail(ctx, RFX_ERR_UNSUPPORTED, "ssgi_trace: blue_noise_index 0 (tiled lookup) is not used by this pass");
+  st = ensure_step_table(ctx, p->steps);
+  if (st != RFX_OK) return st;
+  a.rot_table = ctx->rot_table;
+  a.step_table = ctx->step_table;
+  LAUNCHED(launch_ssgi(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_temporal_reproject_launch(rfx_ctx* ctx, void* stream, const rfx_temporal_params* p, const rfx_plane* input, const rfx_plane* velocity,
+                                         const rfx_plane* history0, const rfx_plane* history1, const rfx_plane* out0, const rfx_plane* out1,
+                                         uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !input || !out0) return fail(ctx, RFX_ERR_INVALID_ARG, "temporal: null argument");
+  TemporalArgs a{};
+  if (p->texture_count != 1 && p->texture_count != 2) return fail(ctx, RFX_ERR_INVALID_ARG, "temporal: texture_count must be 1 or 2");
+  a.input_half = input->format == RFX_FMT_RGBA16F;
+  if (!pv(input, a.input_half ? RFX_FMT_RGBA16F : RFX_FMT_RGBA32F, a.input)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: input must be RGBA32F or RGBA16F");
+  if (p->input_type != RFX_INPUT_DIFFUSE && a.input_half) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: packed inputs must be RGBA32F");
+  if (!pv(velocity, RFX_FMT_RGBA32F, a.velocity)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: velocity must be RGBA32F");
+  if (!pv(history0, RFX_FMT_RGBA16F, a.hist0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: history must be RGBA16F");
+  a.out_half = out0->format == RFX_FMT_RGBA16F;
+  if (!ov(out0, a.out_half ? RFX_FMT_RGBA16F : RFX_FMT_RGBA32F, a.out0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: out must be RGBA32F or RGBA16F");
+  if (p->texture_count == 2) {
+    if (!pv(history1, RFX_FMT_RGBA16F, a.hist1) || !ov(out1, out0->format, a.out1)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: second plane missing / wrong format");
+  }
+  a.W = (int)out0->width; a.H = (int)out0->height;
+  if (a.input.w != a.W || a.input.h != a.H || a.velocity.w != a.W || a.velocity.h != a.H || a.hist0.w != a.W || a.hist0.h != a.H)
+    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "temporal: plane sizes differ");
+  rows(row0, row1, out0->height, a.row0, a.row1);
+  cam_to_dev(p->cam, a.cam);
+  memcpy(a.prev_view.m, p->prev_view_matrix, 64);
+  memcpy(a.prev_world.m, p->prev_camera_matrix_world, 64);
+  memcpy(a.prev_proj.m, p->prev_projection, 64);
+  memcpy(a.prev_proj_inv.m, p->prev_projection_inverse, 64);
+  matmul(p->prev_projection, p->prev_view_matrix, a.prev_proj_view.m);
+  memcpy(a.camera_pos, p->camera_pos, 12);
+  a.max_blend = p->max_blend; a.clamp_intensity = p->neighborhood_clamp_intensity; a.keep_data = p->keep_data; a.confidence_power = p->confidence_power;
+  a.inv_w = (float)(1.0 / (double)a.W);  // TemporalReprojectPass.js:135: JS doubles, uploaded as float32
+  a.inv_h = (float)(1.0 / (double)a.H);
+  a.full_accumulate = p->full_accumulate; a.texture_count = p->texture_count; a.input_type = p->input_type; a.log_transform = p->log_transform;
+  a.rs0 = p->reproject_specular[0]; a.rs1 = p->reproject_specular[1]; a.history_linear = p->history_linear;
+  LAUNCHED(launch_temporal(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_poisson_params* p, const rfx_plane* depth, const rfx_plane* gb,
+                                      const rfx_plane* in0, const rfx_plane* in1, const rfx_plane* out0, const rfx_plane* out1, uint32_t row0,
+                                      uint32_t row1) {
+  if (!ctx || !p || !in0 || !out0) return fail(ctx, RFX_ERR_INVALID_ARG, "poisson: null argument");
+  if (p->texture_count != 1 && p->texture_count != 2) return fail(ctx, RFX_ERR_INVALID_ARG, "poisson: texture_count must be 1 or 2");
+  PoissonArgs a{};
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gb, RFX_FMT_RGBA32F, a.gb)) return fail(ctx, RFX_ERR_BAD_FORMAT, "poisson: depth R32F + gbuffer/normal RGBA32F required");
+  a.in_half = in0->format == RFX_FMT_RGBA16F;
+  if (!pv(in0, a.in_half ? RFX_FMT_RGBA16F : RFX_FMT_RGBA32F, a.in0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "poisson: in0 must be RGBA32F or RGBA16F");
+  if (!ov(out0, RFX_FMT_RGBA16F, a.out0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "poisson: out must be RGBA16F");
+  if (p->texture_count == 2) {
+    if (!pv(in1, in0->format, a.in1) || !ov(out1, RFX_FMT_RGBA16F, a.out1)) return fail(ctx, RFX_ERR_BAD_FORMAT, "poisson: second plane missing / wrong format");
+  } else {
+    a.in1 = a.in0;
+  }
+  if (p->input_linear && !a.in_half) return fail(ctx, RFX_ERR_UNSUPPORTED, "poisson: LINEAR inputs must be RGBA16F");
+  a.W = (int)out0->width; a.H = (int)out0->height;
+  if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.gb.h != a.H || a.in0.w != a.W || a.in0.h != a.H)
+    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "poisson: plane sizes differ");
+  if (out0->ptr == in0->ptr || (out1 && in1 && out1->ptr == in1->ptr)) return fail(ctx, RFX_ERR_INVALID_ARG, "poisson: in-place filtering is not allowed");
+  rows(row0, row1, out0->height, a.row0, a.row1);
+  a.radius = p->radius; a.phi = p->phi; a.luma_phi = p->luma_phi; a.depth_phi = p->depth_phi; a.normal_phi = p->normal_phi;
+  a.roughness_phi = p->roughness_phi; a.specular_phi = p->specular_phi;
+  a.texture_count = p->texture_count; a.spec0 = p->is_texture_specular[0]; a.spec1 = p->is_texture_specular[1];
+  a.gbuffer_texture = p->gbuffer_texture; a.input_linear = p->input_linear;
+  rfx_status st = blue_for(ctx, p->blue_noise_index, a.blue);
+  if (st != RFX_OK) return st;
+  if (p->blue_noise_index == 0) return fail(ctx, RFX_ERR_UNSUPPORTED, "poisson: blue_noise_index 0 is not used by this pass");
+  a.rot_table = ctx->rot_table;
+  LAUNCHED(launch_poisson(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_params* p, const rfx_plane* depth, const rfx_plane* gb,
+                                 const rfx_plane* dgi, const rfx_plane* sgi, const rfx_plane* out, uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "gi_compose: null argument");
+  ComposeArgs a{};
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gb, RFX_FMT_RGBA32F, a.gb) || !pv(dgi, RFX_FMT_RGBA16F, a.diffuse) || !pv(sgi, RFX_FMT_RGBA16F, a.specular) ||
+      !ov(out, RFX_FMT_RGBA32F, a.out))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: depth R32F, gbuffer RGBA32F, gi RGBA16F, out RGBA32F required");
+  if (p->input_type != RFX_INPUT_DIFFUSE_SPECULAR) return fail(ctx, RFX_ERR_UNSUPPORTED, "gi_compose: only inputType diffuseSpecular is implemented");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.diffuse.w != a.W || a.specular.w != a.W || a.diffuse.h != a.H)
+    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "gi_compose: plane sizes differ");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  cam_to_dev(p->cam, a.cam);
+  a.input_type = p->input_type;
+  LAUNCHED(launch_gi_compose(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* depth, const rfx_plane* gi, const rfx_plane* scene, const rfx_plane* out,
+                                   uint32_t row0, uint32_t row1) {
+  if (!ctx || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "ssgi_compose: null argument");
+  SsgiComposeArgs a{};
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gi, RFX_FMT_RGBA32F, a.gi) || !pv(scene, RFX_FMT_RGBA16F, a.scene) || !ov(out, RFX_FMT_RGBA16F, a.out))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_compose: depth R32F, gi RGBA32F, scene/out RGBA16F required");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.depth.w != a.W || a.depth.h != a.H || a.gi.w != a.W || a.scene.w != a.W) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_compose: plane sizes differ");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  LAUNCHED(launch_ssgi_compose(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_hbao_launch(rfx_ctx* ctx, void* stream, const rfx_hbao_params* p, const rfx_plane* depth, const rfx_plane* out, uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "hbao: null argument");
+  HbaoArgs a{};
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !ov(out, RFX_FMT_RGBA16F, a.out)) return fail(ctx, RFX_ERR_BAD_FORMAT, "hbao: depth R32F, out RGBA16F required");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.depth.w != a.W || a.depth.h != a.H) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "hbao: plane sizes differ");
+  if (p->spp < 0) return fail(ctx, RFX_ERR_INVALID_ARG, "hbao: spp < 0");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  memcpy(a.projection_view.m, p->projection_view, 64);
+  memcpy(a.projection_inverse.m, p->projection_inverse, 64);
+  memcpy(a.camera_matrix_world.m, p->camera_matrix_world, 64);
+  a.ao_distance = p->ao_distance; a.distance_power = p->distance_power; a.bias = p->bias; a.thickness = p->thickness; a.spp = p->spp;
+  rfx_status st = blue_for(ctx, p->blue_noise_index, a.blue);
+  if (st != RFX_OK) return st;
+  if (p->blue_noise_index == 0) return fail(ctx, RFX_ERR_UNSUPPORTED, "hbao: blue_noise_index 0 is not used by this pass");
+  a.rot_table = ctx->rot_table;
+  LAUNCHED(launch_hbao(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_ao_compose_launch(rfx_ctx* ctx, void* stream, const rfx_ao_compose_params* p, const rfx_plane* depth, const rfx_plane* ao,
+                                 const rfx_plane* input, const rfx_plane* out, uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "ao_compose: null argument");
+  AoComposeArgs a{};
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(ao, RFX_FMT_RGBA16F, a.ao) || !pv(input, RFX_FMT_RGBA16F, a.input) || !ov(out, RFX_FMT_RGBA16F, a.out))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "ao_compose: depth R32F, ao/input/out RGBA16F required");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.depth.w != a.W || a.depth.h != a.H || a.ao.w != a.W || a.input.w != a.W) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ao_compose: plane sizes differ");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  a.power = p->power;
+  memcpy(a.color, p->color, 12);
+  LAUNCHED(launch_ao_compose(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_motion_blur_launch(rfx_ctx* ctx, void* stream, const rfx_motion_blur_params* p, const rfx_plane* velocity, const rfx_plane* input,
+                                  const rfx_plane* out, uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "motion_blur: null argument");
+  MotionBlurArgs a{};
+  if (!pv(velocity, RFX_FMT_RGBA32F, a.velocity) || !pv(input, RFX_FMT_RGBA16F, a.input) || !ov(out, RFX_FMT_RGBA16F, a.out))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "motion_blur: velocity RGBA32F, input/out RGBA16F required");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.velocity.w != a.W || a.velocity.h != a.H || a.input.w != a.W || a.input.h != a.H) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "motion_blur: plane sizes differ");
+  if (input->ptr == out->ptr) return fail(ctx, RFX_ERR_INVALID_ARG, "motion_blur: in-place is not allowed");
+  if (p->samples < 1) return fail(ctx, RFX_ERR_INVALID_ARG, "motion_blur: samples < 1");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  a.intensity = p->intensity; a.jitter = p->jitter; a.delta_time = p->delta_time; a.res_x = p->resolution[0]; a.res_y = p->resolution[1];
+  a.samples = p->samples;
+  rfx_status st = blue_for(ctx, p->frame, a.blue);
+  if (st != RFX_OK) return st;
+  LAUNCHED(launch_motion_blur(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* acc, const rfx_plane* out, uint32_t row0, uint32_t row1) {
+  if (!ctx || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "traa_compose: null argument");
+  TraaComposeArgs a{};
+  if (!pv(acc, RFX_FMT_RGBA16F, a.acc) || !ov(out, RFX_FMT_RGBA16F, a.out)) return fail(ctx, RFX_ERR_BAD_FORMAT, "traa_compose: RGBA16F planes required");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.acc.w != a.W || a.acc.h != a.H) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "traa_compose: plane sizes differ");
+  rows(row0, row1, out->height, a.row0, a.row1);
+  LAUNCHED(launch_traa_compose(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// native SSGI chain
+// ==========================================================================================
+struct rfx_ssgi_chain {
+  rfx_ctx* ctx;
+  rfx_ssgi_chain_options opt;
+  rfx_plane ssgi_out{}, tr[2]{}, dnA[2]{}, dnB[2]{}, composed{};
+  rfx_plane in_depth{}, in_gb{}, in_vel{}, in_direct{};  // staging for the host-buffer entry point
+  bool have_staging = false;
+  // cross-frame state (TemporalReprojectPass.js:203-213)
+  bool have_prev = false;
+  float prev_view[16], prev_world[16], prev_proj[16], prev_proj_inv[16], prev_pos[3];
+  float keep_data = 0.0f;  // SSGIEffect's constructor resets the denoiser (makeOptionsReactive -> reset())
+  // blue-noise counters: one closure per material (BlueNoiseUtils.js:17-33)
+  int32_t bn_trace = 0, bn_poisson = 0;
+};
+
+static int32_t next_blue(int32_t start, int32_t& counter) {  // BlueNoiseUtils.js:25-28
+  const int64_t highest = 0x7fffffff;
+  counter = (int32_t)(((int64_t)start + (int64_t)counter + 1) % highest);
+  return counter;
+}
+
+extern "C" {
+
+rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt, rfx_ssgi_chain** out) {
+  if (!ctx || !opt || !out || opt->width == 0 || opt->height == 0 || opt->denoise_iterations < 0) return fail(ctx, RFX_ERR_INVALID_ARG, "chain_create: bad arguments");
+  rfx_ssgi_chain* ch = new rfx_ssgi_chain();
+  ch->ctx = ctx;
+  ch->opt = *opt;
+  rfx_status st = RFX_OK;
+  auto alloc = [&](int fmt, rfx_plane* p) { if (st == RFX_OK) st = rfx_plane_alloc(ctx, fmt, opt->width, opt->height, p); };
+  alloc(RFX_FMT_RGBA32F, &ch->ssgi_out);
+  for (int i = 0; i < 2; i++) { alloc(RFX_FMT_RGBA32F, &ch->tr[i]); alloc(RFX_FMT_RGBA16F, &ch->dnA[i]); alloc(RFX_FMT_RGBA16F, &ch->dnB[i]); }
+  alloc(RFX_FMT_RGBA32F, &ch->composed);
+  if (st != RFX_OK) { rfx_ssgi_chain_destroy(ch); return st; }
+  *out = ch;
+  return RFX_OK;
+}
+
+void rfx_ssgi_chain_destroy(rfx_ssgi_chain* ch) {
+  if (!ch) return;
+  rfx_ctx* ctx = ch->ctx;
+  cudaStreamSynchronize(ctx->stream);
+  rfx_plane* all[] = {&ch->ssgi_out, &ch->tr[0], &ch->tr[1], &ch->dnA[0], &ch->dnA[1], &ch->dnB[0], &ch->dnB[1], &ch->composed,
+                      &ch->in_depth, &ch->in_gb, &ch->in_vel, &ch->in_direct};
+  for (rfx_plane* p : all) if (p->ptr) rfx_plane_free(ctx, p);
+  delete ch;
+}
+
+rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* ch) {
+  if (!ch) return RFX_ERR_INVALID_ARG;
+  ch->keep_data = 0.0f;  // TemporalReprojectPass.reset()  :158-160
+  return RFX_OK;
+}
+
+rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* ch, int32_t which, rfx_plane* out) {
+  if (!ch || !out) return RFX_ERR_INVALID_ARG;
+  switch (which) {
+    case 0: *out = ch->composed; break;
+    case 1: *out = ch->ssgi_out; break;
+    case 2: *out = ch->tr[0]; break;
+    case 3: *out = ch->tr[1]; break;
+    case 4: *out = ch->dnB[0]; break;
+    case 5: *out = ch->dnB[1]; break;
+    default: return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_output: which must be 0..5");
+  }
+  return RFX_OK;
+}
+
+rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f) {
+  if (!ch || !f) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = ch->ctx;
+  const rfx_ssgi_chain_options& o = ch->opt;
+  rfx_status st;
+  // ---- K1  SSGIPass.render (src/ssgi/pass/SSGIPass.js:68-95)
+  rfx_ssgi_params sp{};
+  sp.cam = f->cam;
+  sp.ray_distance = o.distance; sp.thickness = o.thickness; sp.env_blur = o.env_blur;
+  sp.max_env_map_mip_level = ctx->env_set ? (float)((int)std::floor(std::log2((double)std::max(ctx->env.size_x, ctx->env.size_y))) + 1) : 0.0f;  // Utils.js:30-34
+  sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
+  sp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_trace);
+  // velocityTexture is a null sampler in the shipped wiring
+  st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, 0, 0);
+  if (st != RFX_OK) return st;
+  // ---- K2  TemporalReprojectPass.render (TemporalReprojectPass.js:162-214), options from Denoiser.js:26-43 + SSGIEffect.js:74-77
+  rfx_temporal_params tp{};
+  tp.cam = f->cam;
+  if (!ch->have_prev) {  // the constructor clones the current camera matrices (TemporalReprojectPass.js:94-97)
+    memcpy(ch->prev_view, f->cam.view_matrix, 64); memcpy(ch->prev_world, f->cam.camera_matrix_world, 64);
+    memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
+    memcpy(ch->prev_pos, f->camera_pos, 12);
+    ch->have_prev = true;
+  }
+  memcpy(tp.prev_view_matrix, ch->prev_view, 64); memcpy(tp.prev_camera_matrix_world, ch->prev_world, 64);
+  memcpy(tp.prev_projection, ch->prev_proj, 64); memcpy(tp.prev_projection_inverse, ch->prev_proj_inv, 64);
+  memcpy(tp.camera_pos, f->camera_pos, 12); memcpy(tp.prev_camera_pos, ch->prev_pos, 12);
+  tp.max_blend = 1.0f; tp.neighborhood_clamp_intensity = 0.5f; tp.keep_data = ch->keep_data; tp.confidence_power = 0.75f;
+  tp.full_accumulate = f->camera_moved ? 0 : 1;  // options.fullAccumulate && !didCameraMove
+  tp.log_transform = 1; tp.history_linear = 1;
+  if (o.mode == RFX_MODE_SSGI) { tp.texture_count = 2; tp.input_type = RFX_INPUT_DIFFUSE_SPECULAR; tp.reproject_specular[0] = 0; tp.reproject_specular[1] = 1; }
+  else { tp.texture_count = 1; tp.input_type = RFX_INPUT_SPECULAR; tp.reproject_specular[0] = 1; tp.reproject_specular[1] = 1; }
+  const int tc = tp.texture_count;
+  st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
+                                     tc == 2 ? &ch->tr[1] : nullptr, 0, 0);
+  if (st != RFX_OK) return st;
+  ch->keep_data = 1.0f;  // :195
+  memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
+  memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
+  memcpy(ch->prev_pos, f->camera_pos, 12);
+  // ---- K3  PoissonDenoisePass.render (PoissonDenoisePass.js:135-149)
+  rfx_poisson_params pp{};
+  pp.radius = o.radius; pp.phi = o.phi; pp.luma_phi = o.luma_phi; pp.depth_phi = o.depth_phi; pp.normal_phi = o.normal_phi;
+  pp.roughness_phi = o.roughness_phi; pp.specular_phi = o.specular_phi;
+  pp.texture_count = tc; pp.gbuffer_texture = 1;
+  if (o.mode == RFX_MODE_SSGI) { pp.is_texture_specular[0] = 0; pp.is_texture_specular[1] = 1; } else { pp.is_texture_specular[0] = 1; pp.is_texture_specular[1] = 1; }
+  for (int i = 0; i < 2 * o.denoise_iterations; i++) {
+    const bool horizontal = (i % 2) == 0;
+    rfx_plane* inp = i == 0 ? ch->tr : (horizontal ? ch->dnB : ch->dnA);
+    rfx_plane* outp = horizontal ? ch->dnA : ch->dnB;
+    pp.input_linear = i == 0 ? 0 : 1;
+    pp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_poisson);
+    st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, 0, 0);
+    if (st != RFX_OK) return st;
+  }
+  // ---- K4  DenoiserComposePass.render
+  if (o.mode == RFX_MODE_SSGI) {
+    rfx_compose_params cp{};
+    cp.cam = f->cam;
+    cp.input_type = RFX_INPUT_DIFFUSE_SPECULAR;
+    st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, 0, 0);
+    if (st != RFX_OK) return st;
+  }
+  return RFX_OK;
+}
+
+rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_frame* hf) {
+  if (!ch || !hf || !hf->depth || !hf->gbuffer || !hf->velocity || !hf->out_composed) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = ch->ctx;
+  rfx_status st = RFX_OK;
+  if (!ch->have_staging) {
+    auto alloc = [&](int fmt, rfx_plane* p) { if (st == RFX_OK) st = rfx_plane_alloc(ctx, fmt, ch->opt.width, ch->opt.height, p); };
+    alloc(RFX_FMT_R32F, &ch->in_depth); alloc(RFX_FMT_RGBA32F, &ch->in_gb); alloc(RFX_FMT_RGBA32F, &ch->in_vel); alloc(RFX_FMT_RGBA16F, &ch->in_direct);
+    if (st != RFX_OK) return st;
+    ch->have_staging = true;
+  }
+  if ((st = rfx_plane_upload(ctx, nullptr, &ch->in_depth, hf->depth, 0)) != RFX_OK) return st;
+  if ((st = rfx_plane_upload(ctx, nullptr, &ch->in_gb, hf->gbuffer, 0)) != RFX_OK) return st;
+  if ((st = rfx_plane_upload(ctx, nullptr, &ch->in_vel, hf->velocity, 0)) != RFX_OK) return st;
+  if (hf->direct_light && (st = rfx_plane_upload(ctx, nullptr, &ch->in_direct, hf->direct_light, 0)) != RFX_OK) return st;
+  rfx_ssgi_frame f{};
+  f.cam = hf->cam;
+  f.depth = &ch->in_depth; f.gbuffer = &ch->in_gb; f.velocity = &ch->in_vel; f.direct_light = hf->direct_light ? &ch->in_direct : nullptr;
+  memcpy(f.camera_pos, hf->camera_pos, 12);
+  f.camera_moved = hf->camera_moved;
+  if ((st = rfx_ssgi_chain_render(ch, nullptr, &f)) != RFX_OK) return st;
+  if ((st = rfx_plane_download(ctx, nullptr, &ch->composed, hf->out_composed, 0)) != RFX_OK) return st;
+  return rfx_ctx_sync(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// rfx_kernels.h — internal launch interface between the C-ABI layer (rfx_api.cu) and the
+// sm_100a kernels (k_*.cu).  Everything here is plain structs of device pointers + uniforms.
+#pragma once
+#include "rfx_device.cuh"
+#include "../../include/rfx.h"
+
+namespace rfx {
+
+struct OutV {  // writable plane view
+  unsigned char* p;
+  long long pitch;
+};
+
+struct CamD {  // device copy of rfx_camera
+  M4 projection, projection_inverse, camera_matrix_world, view_matrix;
+  float near_plane, far_plane;
+  int perspective;
+};
+
+struct BlueD {
+  const uchar4* tex;  // size x size RGBA8, GL texel order
+  int size;
+  BlueShift shift;    // (pcg4d(seed(index)).xy % 0x0fffffff) % size, computed on the host
+  int index;          // raw index (0 selects the tiled lookup of blue_noise.glsl:38-39)
+};
+
+struct EnvD {
+  PV mip[16];  // RGBA16F levels
+  int levels;
+  PV marginal, conditional;  // R32F
+  float size_x, size_y, total_sum_whole, total_sum_decimal;
+};
+
+// ---- K3 ----------------------------------------------------------------------------------
+struct PoissonArgs {
+  PV depth, gb, in0, in1;
+  OutV out0, out1;
+  int W, H, row0, row1;
+  float radius, phi, luma_phi, depth_phi, normal_phi, roughness_phi, specular_phi;
+  int texture_count, spec0, spec1, gbuffer_texture, input_linear, in_half;
+  BlueD blue;
+  const float2* rot_table;  // [256] (sin, cos) of (k/255)*2*pi, correctly rounded
+};
+cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s);
+
+// ---- K4 / K5 -------------------------------------------------------------------------------
+struct ComposeArgs {
+  PV depth, gb, diffuse, specular;
+  OutV out;
+  int W, H, row0, row1;
+  CamD cam;
+  int input_type;
+};
+cudaError_t launch_gi_compose(const ComposeArgs& a, cudaStream_t s);
+
+struct SsgiComposeArgs {
+  PV depth, gi, scene;
+  OutV out;
+  int W, H, row0, row1;
+};
+cudaError_t launch_ssgi_compose(const SsgiComposeArgs& a, cudaStream_t s);
+
+// ---- K2 ----------------------------------------------------------------------------------
+struct TemporalArgs {
+  PV input, velocity, hist0, hist1;
+  OutV out0, out1;
+  int W, H, row0, row1;
+  CamD cam;
+  M4 prev_view, prev_world, prev_proj, prev_proj_inv;
+  M4 prev_proj_view;  // prevProjectionMatrix * prevViewMatrix (reproject.frag:183), fma-lowered on the host
+  float camera_pos[3];
+  float max_blend, clamp_intensity, keep_data, confidence_power;
+  float inv_w, inv_h;  // invTexSize
+  int full_accumulate, texture_count, input_type, log_transform, rs0, rs1, history_linear;
+  int input_half, out_half;
+};
+cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t s);
+
+// ---- K1 ----------------------------------------------------------------------------------
+struct SsgiArgs {
+  PV depth, gb, velocity, direct, accumulated;  // velocity/direct/accumulated may have p == nullptr
+  OutV out;
+  int W, H, row0, row1;
+  CamD cam;
+  float ray_distance, thickness, env_blur, max_env_mip;
+  float near_minus_far, near_mul_far, far_minus_near;
+  int steps, refine_steps, mode;
+  unsigned flags;
+  BlueD blue;
+  EnvD env;
+  const float2* rot_table;   // [256] (sin, cos)
+  const float* step_table;   // [steps][256]  cs(i, b) = 1 - exp(-0.25 (i + b - 0.5)^2), row i-1 for step i
+};
+cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);
+
+// ---- K6 / K7 / K8 / K9 -----------------------------------------------------------------------
+struct HbaoArgs {
+  PV depth;
+  OutV out;
+  int W, H, row0, row1;
+  M4 projection_view, projection_inverse, camera_matrix_world;
+  float ao_distance, distance_power, bias, thickness;
+  int spp;
+  BlueD blue;
+  const float2* rot_table;
+};
+cudaError_t launch_hbao(const HbaoArgs& a, cudaStream_t s);
+
+struct AoComposeArgs {
+  PV depth, ao, input;
+  OutV out;
+  int W, H, row0, row1;
+  float power, color[3];
+};
+cudaError_t launch_ao_compose(const AoComposeArgs& a, cudaStream_t s);
+
+struct MotionBlurArgs {
+  PV velocity, input;
+  OutV out;
+  int W, H, row0, row1;
+  float intensity, jitter, delta_time, res_x, res_y;
+  int samples;
+  BlueD blue;
+};
+cudaError_t launch_motion_blur(const MotionBlurArgs& a, cudaStream_t s);
+
+struct TraaComposeArgs {
+  PV acc;
+  OutV out;
+  int W, H, row0, row1;
+};
+cudaError_t launch_traa_compose(const TraaComposeArgs& a, cudaStream_t s);
+
+// env mip chain: dst (w1 x h1) = box filter of src (w0 x h0), RGBA16F
+cudaError_t launch_env_downsample(PV src, OutV dst, int w1, int h1, cudaStream_t s);
+
+// common launch geometry: 256-thread blocks, 8 warps as 2 x 4 warp tiles of 8x4 pixels => 16x16 pixel tile
+constexpr int kTileW = 16, kTileH = 16, kThreads = 256;
+RFX_D void block_pixel(int& x, int& y, int row_base) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lx, ly;
+  lane_to_pixel(lane, lx, ly);
+  x = blockIdx.x * kTileW + ((warp & 1) << 3) + lx;
+  y = row_base + blockIdx.y * kTileH + ((warp >> 1) << 2) + ly;
+}
+
+}  // namespace rfx

@@ -1,0 +1,230 @@
+"""Thin Python host layer over the C ABI (include/rfx.h): context, device planes, pass launches.
+
+This is plumbing, not the product: every method forwards to one `rfx_*` entry point of
+csrc/librfx.so and raises RfxError on a non-zero status (like the JS wrapper of INTEGRATION.md
+would throw).  There is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import (FMT_R32F, FMT_RGBA8, FMT_RGBA16F, FMT_RGBA32F, Plane, RfxError)
+
+
+def _fmt_of(a: np.ndarray) -> int:
+    if a.ndim == 2 and a.dtype == np.float32:
+        return FMT_R32F
+    if a.ndim == 3 and a.shape[2] == 4:
+        if a.dtype == np.float32:
+            return FMT_RGBA32F
+        if a.dtype in (np.float16, np.uint16):
+            return FMT_RGBA16F
+        if a.dtype == np.uint8:
+            return FMT_RGBA8
+    raise RfxError(f"no plane format for array {a.shape} {a.dtype}")
+
+
+_NP_OF = {FMT_R32F: (np.float32, 1), FMT_RGBA32F: (np.float32, 4), FMT_RGBA16F: (np.float16, 4), FMT_RGBA8: (np.uint8, 4)}
+
+
+class DevPlane:
+    """An rfx_plane owned by a Context."""
+
+    def __init__(self, ctx: "Context", fmt: int, width: int, height: int):
+        self.ctx = ctx
+        self.p = Plane()
+        ctx._chk(ctx.lib.rfx_plane_alloc(ctx.h, fmt, width, height, C.byref(self.p)))
+        self.owned = True
+
+    @property
+    def width(self):
+        return self.p.width
+
+    @property
+    def height(self):
+        return self.p.height
+
+    @property
+    def format(self):
+        return self.p.format
+
+    def ref(self):
+        return C.byref(self.p)
+
+    def upload(self, a: np.ndarray, stream=None):
+        a = np.ascontiguousarray(a)
+        assert _fmt_of(a) == self.p.format and a.shape[0] == self.p.height and a.shape[1] == self.p.width, (a.shape, a.dtype)
+        self.ctx._chk(self.ctx.lib.rfx_plane_upload(self.ctx.h, stream, self.ref(), a.ctypes.data_as(C.c_void_p), 0))
+        self.ctx.sync()
+        return self
+
+    def download(self) -> np.ndarray:
+        dt, ch = _NP_OF[self.p.format]
+        shape = (self.p.height, self.p.width) if ch == 1 else (self.p.height, self.p.width, ch)
+        out = np.empty(shape, dt)
+        self.ctx.sync()
+        self.ctx._chk(self.ctx.lib.rfx_plane_download(self.ctx.h, None, self.ref(), out.ctypes.data_as(C.c_void_p), 0))
+        self.ctx.sync()
+        return out
+
+    def clear(self):
+        self.ctx._chk(self.ctx.lib.rfx_plane_clear(self.ctx.h, None, self.ref()))
+
+    def free(self):
+        if self.owned and self.p.ptr:
+            self.ctx.lib.rfx_plane_free(self.ctx.h, self.ref())
+            self.owned = False
+
+
+def _r(p):
+    return None if p is None else (p.ref() if isinstance(p, DevPlane) else C.byref(p))
+
+
+class Context:
+    def __init__(self, device: int = 0, blue_noise: np.ndarray | None = None):
+        self.lib = abi.lib()
+        h = C.c_void_p()
+        st = self.lib.rfx_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise RfxError(f"rfx_ctx_create(device={device}) failed with status {st} (is a CUDA device visible?)")
+        self.h = h
+        self.device = device
+        self._keep = []
+        if blue_noise is None:
+            from .synth import load_blue_noise
+
+            blue_noise = load_blue_noise()
+        self.set_blue_noise(blue_noise)
+
+    def _chk(self, st: int):
+        if st != 0:
+            raise RfxError(f"rfx status {st}: {self.lib.rfx_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.rfx_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self._chk(self.lib.rfx_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.rfx_ctx_stream(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rfx_launch_count(self.h))
+
+    def set_blue_noise(self, rgba8: np.ndarray):
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        self._chk(self.lib.rfx_blue_noise_set(self.h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))
+
+    def set_env(self, map_f16: np.ndarray, marginal: np.ndarray | None, conditional: np.ndarray | None, total_sum: float):
+        m = np.ascontiguousarray(map_f16)
+        assert m.dtype in (np.float16, np.uint16) and m.ndim == 3 and m.shape[2] == 4
+        d = abi.EnvDesc()
+        d.map_rgba16f = m.ctypes.data
+        d.width, d.height = m.shape[1], m.shape[0]
+        keep = [m]
+        if marginal is not None:
+            mg = np.ascontiguousarray(marginal, np.float32)
+            cd = np.ascontiguousarray(conditional, np.float32)
+            d.marginal, d.conditional = mg.ctypes.data, cd.ctypes.data
+            keep += [mg, cd]
+        whole = float(int(total_sum))  # ~~totalSumValue (EquirectHdrInfoUniform.js:346-349)
+        d.total_sum_whole = float(np.float32(whole))
+        d.total_sum_decimal = float(np.float32(total_sum - whole))
+        self._chk(self.lib.rfx_env_set(self.h, C.byref(d)))
+
+    def clear_env(self):
+        self._chk(self.lib.rfx_env_clear(self.h))
+
+    def alloc(self, fmt: int, width: int, height: int) -> DevPlane:
+        return DevPlane(self, fmt, width, height)
+
+    def upload(self, a: np.ndarray) -> DevPlane:
+        a = np.ascontiguousarray(a)
+        return DevPlane(self, _fmt_of(a), a.shape[1], a.shape[0]).upload(a)
+
+    # ---- pass launches (one per reference fullscreen draw) -----------------------------------
+    def ssgi_trace(self, p, depth, gbuffer, velocity, direct_light, accumulated, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_ssgi_trace_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer), _r(velocity), _r(direct_light),
+                                                 _r(accumulated), _r(out), rows[0], rows[1]))
+
+    def temporal_reproject(self, p, inp, velocity, hist0, hist1, out0, out1, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_temporal_reproject_launch(self.h, stream, C.byref(p), _r(inp), _r(velocity), _r(hist0), _r(hist1), _r(out0),
+                                                         _r(out1), rows[0], rows[1]))
+
+    def poisson_denoise(self, p, depth, gbuffer_or_normal, in0, in1, out0, out1, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_poisson_denoise_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer_or_normal), _r(in0), _r(in1), _r(out0),
+                                                      _r(out1), rows[0], rows[1]))
+
+    def gi_compose(self, p, depth, gbuffer, diffuse_gi, specular_gi, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_gi_compose_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer), _r(diffuse_gi), _r(specular_gi), _r(out),
+                                                 rows[0], rows[1]))
+
+    def ssgi_compose(self, depth, gi, scene, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_ssgi_compose_launch(self.h, stream, _r(depth), _r(gi), _r(scene), _r(out), rows[0], rows[1]))
+
+    def hbao(self, p, depth, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_hbao_launch(self.h, stream, C.byref(p), _r(depth), _r(out), rows[0], rows[1]))
+
+    def ao_compose(self, p, depth, ao, inp, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_ao_compose_launch(self.h, stream, C.byref(p), _r(depth), _r(ao), _r(inp), _r(out), rows[0], rows[1]))
+
+    def motion_blur(self, p, velocity, inp, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_motion_blur_launch(self.h, stream, C.byref(p), _r(velocity), _r(inp), _r(out), rows[0], rows[1]))
+
+    def traa_compose(self, acc, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_traa_compose_launch(self.h, stream, _r(acc), _r(out), rows[0], rows[1]))
+
+
+class SsgiChain:
+    """Native SSGI chain (rfx_ssgi_chain): K1 -> K2 -> K3 x 2*iterations -> K4 with history."""
+
+    def __init__(self, ctx: Context, opt: abi.ChainOptions):
+        self.ctx = ctx
+        self.opt = opt
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.rfx_ssgi_chain_create(ctx.h, C.byref(opt), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.rfx_ssgi_chain_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_reset(self.h))
+
+    def render(self, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None):
+        f = abi.SsgiFrame()
+        f.cam = cam
+        f.depth = C.pointer(depth.p)
+        f.gbuffer = C.pointer(gbuffer.p)
+        f.velocity = C.pointer(velocity.p)
+        f.direct_light = C.pointer(direct_light.p) if direct_light is not None else None
+        f.camera_pos[:] = [float(x) for x in camera_pos]
+        f.camera_moved = int(camera_moved)
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render(self.h, stream, C.byref(f)))
+
+    def output(self, which: int = 0) -> Plane:
+        p = Plane()
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_output(self.h, which, C.byref(p)))
+        return p
+
+    def download(self, which: int = 0) -> np.ndarray:
+        p = self.output(which)
+        dt, ch = _NP_OF[p.format]
+        out = np.empty((p.height, p.width, ch), dt)
+        self.ctx.sync()
+        self.ctx._chk(self.ctx.lib.rfx_plane_download(self.ctx.h, None, C.byref(p), out.ctypes.data_as(C.c_void_p), 0))
+        self.ctx.sync()
+        return out
+
+    def render_host(self, hf: abi.SsgiHostFrame):
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_host(self.h, C.byref(hf)))

@@ -1,0 +1,276 @@
+"""Drives the same synthetic frames through (a) the CUDA engine via the C ABI and (b) the CPU
+oracle, pass by pass, following the reference's frame logic (SSGIEffect.update ->
+SSGIPass.render -> Denoiser.render).  TEST INFRASTRUCTURE (imports tests/orc.py).
+
+The oracle chain below is written in Python straight from the reference JS
+(src/ssgi/pass/SSGIPass.js:68-95, src/temporal-reproject/TemporalReprojectPass.js:162-214,
+src/denoise/pass/PoissonDenoisePass.js:135-149, src/denoise/Denoiser.js:97-107,
+src/utils/BlueNoiseUtils.js:17-33) independently of the native chain in csrc/rfx_api.cu, so a
+chain-level comparison also checks the native frame-state logic.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+from dataclasses import dataclass
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from realism_effects_b200 import abi, synth  # noqa: E402
+
+RTOL, ATOL = 1e-3, 1e-5  # north_star: within 1e-3 relative per channel (ATOL guards exact zeros)
+
+
+@dataclass
+class Opts:
+    """SSGI options (defaults = src/ssgi/SSGIOptions.js:26-48)."""
+
+    distance: float = 10.0
+    thickness: float = 10.0
+    denoise_iterations: int = 1
+    radius: float = 3.0
+    phi: float = 0.5
+    luma_phi: float = 5.0
+    depth_phi: float = 2.0
+    normal_phi: float = 50.0
+    roughness_phi: float = 50.0
+    specular_phi: float = 50.0
+    env_blur: float = 0.5
+    importance_sampling: bool = True
+    steps: int = 20
+    refine_steps: int = 5
+    missed_rays: bool = False
+    use_direct_light: bool = True
+    use_envmap: bool = True
+    mode: int = abi.MODE_SSGI
+    blue_noise_start: int = 1234567
+
+    @property
+    def flags(self) -> int:
+        f = 0
+        if self.importance_sampling and self.use_envmap:
+            f |= abi.SSGI_IMPORTANCE_SAMPLING
+        if self.missed_rays:
+            f |= abi.SSGI_MISSED_RAYS
+        if self.use_direct_light:
+            f |= abi.SSGI_USE_DIRECT_LIGHT
+        if self.use_envmap:
+            f |= abi.SSGI_USE_ENVMAP
+        return f
+
+
+@dataclass
+class Inputs:
+    width: int
+    height: int
+    frames: list  # of dicts of numpy planes + camera uniforms
+    env_map: np.ndarray
+    env_marginal: np.ndarray
+    env_conditional: np.ndarray
+    env_total: float
+    blue: np.ndarray
+
+
+def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_size=(128, 64), device="cpu") -> Inputs:
+    frames = []
+    for t in range(n_frames):
+        fr = synth.render_frame(width, height, t, device=device, static=static)
+        u = fr.cam.uniforms()
+        moved = (t > 0) and not static
+        frames.append(dict(depth=fr.depth.cpu().numpy(), gbuffer=fr.gbuffer.cpu().numpy(), velocity=fr.velocity.cpu().numpy(),
+                           direct=fr.direct_light.cpu().numpy(), cam=u, moved=moved))
+    env = synth.synthetic_env(*env_size)
+    marg, cond, total = synth.build_env_cdf(env.astype(np.float32), flip_y=False)
+    return Inputs(width, height, frames, env, marg, cond, total, synth.load_blue_noise())
+
+
+def next_blue(start: int, counter: int) -> int:
+    """BlueNoiseUtils.js:25-28"""
+    return (start + counter + 1) % 0x7FFFFFFF
+
+
+def max_mip_level(w: int, h: int) -> float:
+    return float(math.floor(math.log2(max(w, h))) + 1)  # Utils.js:30-34
+
+
+def ssgi_params(o: Opts, cam: abi.CameraS, index: int, env_wh) -> abi.SsgiParams:
+    p = abi.SsgiParams()
+    p.cam = cam
+    p.ray_distance, p.thickness, p.env_blur = o.distance, o.thickness, o.env_blur
+    p.max_env_map_mip_level = max_mip_level(*env_wh) if o.use_envmap else 0.0
+    p.steps, p.refine_steps, p.mode, p.flags, p.blue_noise_index = o.steps, o.refine_steps, o.mode, o.flags, index
+    return p
+
+
+def temporal_params(o: Opts, cam: abi.CameraS, cam_pos, prev: dict, keep_data: float, moved: bool) -> abi.TemporalParams:
+    p = abi.TemporalParams()
+    p.cam = cam
+    abi.set_f16(p.prev_view_matrix, prev["view_matrix"])
+    abi.set_f16(p.prev_camera_matrix_world, prev["camera_matrix_world"])
+    abi.set_f16(p.prev_projection, prev["projection"])
+    abi.set_f16(p.prev_projection_inverse, prev["projection_inverse"])
+    p.camera_pos[:] = [float(x) for x in cam_pos]
+    p.prev_camera_pos[:] = [float(x) for x in prev["position"]]
+    p.max_blend, p.neighborhood_clamp_intensity, p.keep_data, p.confidence_power = 1.0, 0.5, keep_data, 0.75
+    p.full_accumulate = 0 if moved else 1
+    p.log_transform, p.history_linear = 1, 1
+    if o.mode == abi.MODE_SSGI:
+        p.texture_count, p.input_type = 2, abi.INPUT_DIFFUSE_SPECULAR
+        p.reproject_specular[:] = [0, 1]
+    else:
+        p.texture_count, p.input_type = 1, abi.INPUT_SPECULAR
+        p.reproject_specular[:] = [1, 1]
+    return p
+
+
+def poisson_params(o: Opts, index: int, first: bool) -> abi.PoissonParams:
+    p = abi.PoissonParams()
+    p.radius, p.phi, p.luma_phi, p.depth_phi, p.normal_phi = o.radius, o.phi, o.luma_phi, o.depth_phi, o.normal_phi
+    p.roughness_phi, p.specular_phi = o.roughness_phi, o.specular_phi
+    p.texture_count = 2 if o.mode == abi.MODE_SSGI else 1
+    p.is_texture_specular[:] = [0, 1] if o.mode == abi.MODE_SSGI else [1, 1]
+    p.gbuffer_texture, p.input_linear, p.blue_noise_index = 1, 0 if first else 1, index
+    return p
+
+
+def compose_params(cam: abi.CameraS) -> abi.ComposeParams:
+    p = abi.ComposeParams()
+    p.cam = cam
+    p.input_type = abi.INPUT_DIFFUSE_SPECULAR
+    return p
+
+
+def chain_options(inp: Inputs, o: Opts) -> abi.ChainOptions:
+    c = abi.ChainOptions()
+    c.width, c.height = inp.width, inp.height
+    c.denoise_iterations, c.steps, c.refine_steps = o.denoise_iterations, o.steps, o.refine_steps
+    c.distance, c.thickness, c.env_blur = o.distance, o.thickness, o.env_blur
+    c.radius, c.phi, c.luma_phi, c.depth_phi, c.normal_phi = o.radius, o.phi, o.luma_phi, o.depth_phi, o.normal_phi
+    c.roughness_phi, c.specular_phi = o.roughness_phi, o.specular_phi
+    c.ssgi_flags, c.mode, c.blue_noise_start, c.use_cuda_graph = o.flags, o.mode, o.blue_noise_start, 0
+    return c
+
+
+# ----------------------------------------------------------------------------------------------
+def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed")):
+    """Returns a list (one dict per frame) of the planes named in `capture` (+ the per-pass inputs
+    needed for isolated kernel tests under keys starting with '_')."""
+    import orc
+
+    H, W = inp.height, inp.width
+    env = orc.Env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total) if o.use_envmap else None
+    z32 = lambda: np.zeros((H, W, 4), np.float32)  # noqa: E731
+    z16 = lambda: np.zeros((H, W, 4), np.float16)  # noqa: E731
+    tr = [z32(), z32()]
+    dnA, dnB = [z16(), z16()], [z16(), z16()]
+    composed = z32()
+    keep_data, prev = 0.0, None
+    bn_trace = bn_poisson = 0
+    out = []
+    for fr in inp.frames:
+        cam = abi.make_camera(fr["cam"])
+        rec = {}
+        # K1
+        bn_trace = next_blue(o.blue_noise_start, bn_trace)
+        sp = ssgi_params(o, cam, bn_trace, (inp.env_map.shape[1], inp.env_map.shape[0]))
+        rec["_k1_accumulated"] = composed.copy()
+        rec["_k1_params"] = sp
+        ssgi = orc.ssgi_trace(sp, fr["depth"], fr["gbuffer"], None, fr["direct"], composed, env, inp.blue)
+        # K2
+        if prev is None:
+            prev = fr["cam"]
+        tp = temporal_params(o, cam, fr["cam"]["position"], prev, keep_data, fr["moved"])
+        rec["_k2_params"], rec["_k2_hist"], rec["_k2_prev_out"] = tp, [dnB[0].copy(), dnB[1].copy()], [tr[0].copy(), tr[1].copy()]
+        tr0, tr1 = orc.temporal_reproject(tp, ssgi, fr["velocity"], dnB[0], dnB[1], tr[0], tr[1])
+        tr = [tr0, tr1]
+        keep_data, prev = 1.0, fr["cam"]
+        # K3
+        rec["_k3"] = []
+        for i in range(2 * o.denoise_iterations):
+            horizontal = i % 2 == 0
+            src = tr if i == 0 else (dnB if horizontal else dnA)
+            dst = dnA if horizontal else dnB
+            bn_poisson = next_blue(o.blue_noise_start, bn_poisson)
+            pp = poisson_params(o, bn_poisson, i == 0)
+            rec["_k3"].append(dict(params=pp, in0=src[0].copy(), in1=src[1].copy(), prev0=dst[0].copy(), prev1=dst[1].copy()))
+            o0, o1 = orc.poisson_denoise(pp, fr["depth"], fr["gbuffer"], src[0], src[1], inp.blue, dst[0], dst[1])
+            rec["_k3"][-1].update(out0=o0, out1=o1)
+            if horizontal:
+                dnA = [o0, o1]
+            else:
+                dnB = [o0, o1]
+        # K4
+        cp = compose_params(cam)
+        rec["_k4_params"], rec["_k4_prev"] = cp, composed.copy()
+        composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed)
+        full = dict(ssgi=ssgi, tr0=tr[0], tr1=tr[1], dn0=dnB[0], dn1=dnB[1], composed=composed)
+        rec.update({k: full[k].copy() for k in capture})
+        out.append(rec)
+    return out
+
+
+def run_cuda_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed")):
+    from realism_effects_b200 import engine
+
+    ctx = engine.Context(0, inp.blue)
+    try:
+        if o.use_envmap:
+            ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+        chain = engine.SsgiChain(ctx, chain_options(inp, o))
+        which = dict(composed=0, ssgi=1, tr0=2, tr1=3, dn0=4, dn1=5)
+        out = []
+        for fr in inp.frames:
+            d, g, v, dl = ctx.upload(fr["depth"]), ctx.upload(fr["gbuffer"]), ctx.upload(fr["velocity"]), ctx.upload(fr["direct"])
+            chain.render(abi.make_camera(fr["cam"]), d, g, v, dl, fr["cam"]["position"], fr["moved"])
+            out.append({k: chain.download(which[k]) for k in capture})
+            for p in (d, g, v, dl):
+                p.free()
+        launches = ctx.launch_count
+        chain.close()
+        return out, launches
+    finally:
+        ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+def unpack_halves(a: np.ndarray) -> np.ndarray:
+    """RGBA32F plane of packed half pairs -> (H,W,8) float32"""
+    return a.view(np.uint32).view(np.float16).astype(np.float32).reshape(a.shape[0], a.shape[1], 8)
+
+
+def compare(a: np.ndarray, b: np.ndarray, packed: bool = False) -> dict:
+    """Per-channel |a-b| <= RTOL*max(|a|,|b|) + ATOL; returns max relative error over the
+    conforming elements, the fraction of PIXELS with any non-conforming channel, and bit-equality."""
+    if packed:
+        a, b = unpack_halves(a), unpack_halves(b)
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    fin = np.isfinite(a) & np.isfinite(b)
+    same_nonfinite = (~fin) & ((a == b) | (np.isnan(a) & np.isnan(b)))
+    diff = np.where(fin, np.abs(a - b), 0.0)
+    scale = np.where(fin, np.maximum(np.abs(a), np.abs(b)), 0.0)
+    bad = (diff > RTOL * scale + ATOL) | ((~fin) & ~same_nonfinite)
+    rel = np.where(scale > 0, diff / np.maximum(scale, 1e-30), 0.0)
+    ok_rel = np.where(bad, 0.0, rel)
+    bad_px = bad.reshape(bad.shape[0], bad.shape[1], -1).any(-1)
+    return dict(frac_bad=float(bad_px.mean()), n_bad=int(bad_px.sum()), max_rel_ok=float(ok_rel.max()), max_abs=float(diff.max()),
+                bit_equal=float(((a == b) | (np.isnan(a) & np.isnan(b))).mean()))
+
+
+def run_chain_parity(width=192, height=108, frames=2, max_frac=2e-3, **opt_kw) -> dict:
+    o = Opts(**opt_kw)
+    inp = make_inputs(width, height, frames)
+    ref = run_oracle_chain(inp, o)
+    got, launches = run_cuda_chain(inp, o)
+    worst, lines = 0.0, []
+    for t, (r, g) in enumerate(zip(ref, got)):
+        for k in ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"):
+            c = compare(r[k], g[k], packed=(k == "ssgi"))
+            worst = max(worst, c["frac_bad"])
+            lines.append(f"f{t}.{k}: bad={c['frac_bad']:.2e} maxrel_ok={c['max_rel_ok']:.1e} biteq={c['bit_equal']:.4f}")
+    return dict(ok=worst <= max_frac, worst=worst, launches=launches, summary=f"worst bad-pixel fraction {worst:.2e} (limit {max_frac:.0e}); " + "; ".join(lines))
