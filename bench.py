@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — SSGI+denoise Mpixels/s at 3840x2160 on N B200s (BASELINE.json metric, config C3).
+
+One "step" = one frame of the SSGI chain over one batch of synthetic G-buffer planes:
+  K1 SSGI trace (steps 20 / refine 5) -> K2 temporal reprojection (2 planes) ->
+  K3 Poisson denoise x4 (denoiseIterations = 2) -> K4 GI compose          (432 B/px algorithmic)
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+value   : whole-job Mpixels/s with the input planes resident in HBM (CUDA events on the launching
+          stream, max over ranks).
+e2e     : the same metric through the host-buffer C-ABI call rfx_ssgi_chain_render_host (pinned host
+          planes -> H2D -> chain -> D2H of `composed`), copies inside the timed region.
+roofline: the dominant kernel's algorithmic bytes / its mean CUDA-event duration over the timed frames,
+          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: the CPU restatement in oracle/ (the reference itself is WebGL-only and
+          cannot run here: no GL, no JS engine) on the box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT = 3840, 2160
+DENOISE_ITERATIONS = 2
+ALGO_BYTES = {  # algorithmic bytes per output pixel
+    "K1_ssgi_trace": 76, "K2_temporal_reproject": 80, "K3_poisson_pass0": 68, "K3_poisson_pass1plus": 52, "K4_gi_compose": 52,
+}
+CHAIN_BYTES_PER_PX = 76 + 80 + (68 + 3 * 52) + 52  # = 432 (C3)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def opts_for_bench():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import chain_harness as ch  # parameter builders only (no oracle import at module level)
+
+    return ch, ch.Opts(denoise_iterations=DENOISE_ITERATIONS)
+
+
+# ------------------------------------------------------------------------------------------------
+def make_gpu_frames(width, height, n, device):
+    """Synthetic planes generated on the device with torch (plumbing); returns list of dicts of tensors."""
+    import torch
+
+    from realism_effects_b200 import synth
+
+    frames = []
+    for t in range(n):
+        fr = synth.render_frame(width, height, t + 1, device=device)
+        frames.append(dict(depth=fr.depth, gbuffer=fr.gbuffer, velocity=fr.velocity, direct=fr.direct_light, cam=fr.cam.uniforms(), moved=True))
+    torch.cuda.synchronize()
+    return frames
+
+
+def tensor_plane(t, fmt):
+    from realism_effects_b200 import abi
+
+    p = abi.Plane()
+    p.ptr = t.data_ptr()
+    p.height, p.width = t.shape[0], t.shape[1]
+    p.pitch = t.shape[1] * abi.FMT_BYTES[fmt]
+    p.format = fmt
+    return p
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from realism_effects_b200 import abi, engine, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU oracle timing)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ch, o = opts_for_bench()
+    W, H = args.width, args.height
+    K, Wm = args.steps, args.warmup
+
+    ctx = engine.Context(local)
+    env = synth.synthetic_env(1024, 512)
+    marg, cond, total = synth.build_env_cdf(env.astype(np.float32))
+    ctx.set_env(env, marg, cond, total)
+
+    class _I:  # minimal Inputs for chain_options
+        width, height = W, H
+
+    chain = engine.SsgiChain(ctx, ch.chain_options(_I, o))
+    frames = make_gpu_frames(W, H, 2, dev)
+    planes = [dict(depth=tensor_plane(f["depth"], abi.FMT_R32F), gbuffer=tensor_plane(f["gbuffer"], abi.FMT_RGBA32F),
+                   velocity=tensor_plane(f["velocity"], abi.FMT_RGBA32F), direct=tensor_plane(f["direct"], abi.FMT_RGBA16F)) for f in frames]
+    cams = [abi.make_camera(f["cam"]) for f in frames]
+
+    class _PW:  # adapter so SsgiChain.render can take raw planes
+        def __init__(self, p):
+            self.p = p
+
+    def render(i, stream=None):
+        j = i % len(frames)
+        pl = planes[j]
+        chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True, stream=stream)
+
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for i in range(Wm):
+        render(i)
+    ctx.sync()
+    launches0 = ctx.launch_count
+    chain.set_profiling(True)
+    chain.get_profile()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(K):
+        render(Wm + i)
+    e1.record(ext)
+    barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    prof = chain.get_profile()
+    chain.set_profiling(False)
+    launches = ctx.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    mpx = W * H * world / 1e6
+    value = mpx / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peak, peak_src = measured_peak()
+    per_kernel = {}
+    for k, (ms, n) in prof.items():
+        if n:
+            per_kernel[k] = {"ms_per_launch": ms / n, "launches": n, "share_of_step": ms / max(ms_total, 1e-9),
+                             "algo_GBps": ALGO_BYTES[k] * W * H / (ms / n * 1e-3) / 1e9}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"]) if per_kernel else None
+    roof = None
+    if dom:
+        ach = per_kernel[dom]["algo_GBps"]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                "peak_source": peak_src, "chain_achieved": round(CHAIN_BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9, 1),
+                "chain_frac": round(CHAIN_BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                "per_kernel": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in per_kernel.items()}}
+
+    # ---- e2e through the host-buffer C-ABI call ---------------------------------------------------
+    host = []
+    for f in frames[:2]:
+        host.append({k: f[k].cpu().pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")})
+    out_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
+    d2h = out_host.numel() * 4
+    hfs = []
+    for j, hb in enumerate(host):
+        hf = abi.SsgiHostFrame()
+        hf.cam = cams[j]
+        hf.depth, hf.gbuffer, hf.velocity, hf.direct_light = hb["depth"].data_ptr(), hb["gbuffer"].data_ptr(), hb["velocity"].data_ptr(), hb["direct"].data_ptr()
+        hf.camera_pos[:] = [float(x) for x in frames[j]["cam"]["position"]]
+        hf.camera_moved = 1
+        hf.out_composed = out_host.data_ptr()
+        hfs.append(hf)
+    ke = max(3, min(K, 10))
+    for i in range(2):
+        chain.render_host(hfs[i % 2])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(ke):
+        chain.render_host(hfs[i % 2])  # synchronous: returns after the D2H copy completed
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / ke
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(out_host[::97, ::89, :3].double().sum())
+    e2e = {"value": round(mpx / e2e_s, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": round(e2e_s * 1e3, 3), "steps": ke, "result_checksum": checksum}
+
+    # ---- CPU baseline (rank 0, N=1 only): one full-resolution frame through the oracle ------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if (args.cpu_width, args.cpu_height) == (W, H):  # reuse the planes already generated on the device
+            f0 = frames[0]
+            fr = dict(depth=f0["depth"].cpu().numpy(), gbuffer=f0["gbuffer"].cpu().numpy(), velocity=f0["velocity"].cpu().numpy(),
+                      direct=f0["direct"].cpu().numpy(), cam=f0["cam"], moved=True)
+            cpu_inp = ch.Inputs(W, H, [fr], env, marg, cond, total, synth.load_blue_noise())
+        else:
+            cpu_inp = ch.make_inputs(args.cpu_width, args.cpu_height, 1, env_size=(1024, 512))
+        cpu = cpu_baseline_sample(ch, o, cpu_inp)
+
+    if rank == 0:
+        line = {
+            "metric": "SSGI+denoise Mpixels/s at 4K", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 accumulate planes)",
+            "data": "synthetic", "impl": "ours",
+            "config": {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS} => {2 * DENOISE_ITERATIONS} passes)+compose {W}x{H} per GPU, steps=20 refineSteps=5",
+                       "inputs": "2 alternating synthetic G-buffer frames (365 MB/frame of input planes > 126 MB L2), moving camera",
+                       "l2": "inputs larger than L2; no explicit flush", "multi_gpu": "replicas" if world > 1 else "single"},
+            "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line))
+    chain.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(ch, o, inp):
+    """Times the CPU oracle chain on the frames of `inp` (all host threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+
+    width, height, frames_n = inp.width, inp.height, len(inp.frames)
+    orc.lib()
+    t0 = time.perf_counter()
+    ch.run_oracle_chain(inp, o, capture=("composed",))
+    dt = time.perf_counter() - t0
+    cores = int(orc.lib().orc_num_threads())
+    return {"value": round(width * height * frames_n / 1e6 / dt, 4), "unit": "Mpixels/s", "cores": cores, "kind": "port",
+            "sample": f"{frames_n} frame(s) of the same chain at {width}x{height} ({dt:.1f} s of CPU work; first frame => empty history)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation is WebGL-only (no GL / JS engine here), so the
+    arm times the CPU restatement in oracle/ with all host threads, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ch, o = opts_for_bench()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+
+    sw, sh = args.cpu_width, args.cpu_height
+    if args.cpu_width == WIDTH:  # default: 1/16 of the 4K frame per step
+        sw, sh = 960, 540
+    K, Wm = args.steps, args.warmup
+    inp = ch.make_inputs(sw, sh, 2, env_size=(1024, 512))
+    frames = inp.frames
+    cores = int(orc.lib().orc_num_threads())
+
+    def step_block(n):
+        inp.frames = [frames[i % 2] for i in range(n)]
+        ch.run_oracle_chain(inp, o, capture=("composed",))
+
+    step_block(Wm)
+    t0 = time.perf_counter()
+    step_block(K)
+    dt = (time.perf_counter() - t0) / K
+    v = round(sw * sh / 1e6 / dt, 4)
+    line = {"metric": "SSGI+denoise Mpixels/s at 4K", "value": v, "unit": "Mpixels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K,
+            "warmup": Wm, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS})+compose, CPU restatement (oracle/), bounded sample {sw}x{sh} per step"},
+            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": f"{K} steps x one {sw}x{sh} frame (1/16 of the 4K frame)"},
+            "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--cpu-width", type=int, default=WIDTH)
+    ap.add_argument("--cpu-height", type=int, default=HEIGHT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

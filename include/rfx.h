@@ -331,6 +331,14 @@ typedef struct rfx_ssgi_host_frame {
 } rfx_ssgi_host_frame;
 rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* chain, const rfx_ssgi_host_frame* frame);
 
+/* Per-pass device timing (CUDA events recorded on the launching stream around every kernel of
+ * the chain).  Slots: 0 K1 trace, 1 K2 temporal, 2 K3 pass 0, 3 K3 passes >= 1, 4 K4 compose.
+ * get_profile synchronises the stream, adds the elapsed milliseconds / launch counts of all
+ * frames rendered since the last call into ms[5] / launches[5] and clears the record. */
+#define RFX_CHAIN_PROFILE_SLOTS 5
+rfx_status rfx_ssgi_chain_set_profiling(rfx_ssgi_chain* chain, int32_t enable);
+rfx_status rfx_ssgi_chain_get_profile(rfx_ssgi_chain* chain, double* ms, uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -541,6 +541,23 @@ struct rfx_ssgi_chain {
   float keep_data = 0.0f;  // SSGIEffect's constructor resets the denoiser (makeOptionsReactive -> reset())
   // blue-noise counters: one closure per material (BlueNoiseUtils.js:17-33)
   int32_t bn_trace = 0, bn_poisson = 0;
+  // optional per-pass event timing
+  bool profiling = false;
+  struct Span { cudaEvent_t a, b; int slot; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+static cudaEvent_t chain_event(rfx_ssgi_chain* ch) {
+  if (!ch->event_pool.empty()) { cudaEvent_t e = ch->event_pool.back(); ch->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct SpanGuard {  // records an event pair around one launch when profiling is on
+  rfx_ssgi_chain* ch; cudaStream_t s; cudaEvent_t a = nullptr; int slot;
+  SpanGuard(rfx_ssgi_chain* c, cudaStream_t st, int sl) : ch(c), s(st), slot(sl) { if (ch->profiling) { a = chain_event(ch); cudaEventRecord(a, s); } }
+  ~SpanGuard() { if (a) { cudaEvent_t b = chain_event(ch); cudaEventRecord(b, s); ch->spans.push_back({a, b, slot}); } }
 };
 
 static int32_t next_blue(int32_t start, int32_t& counter) {  // BlueNoiseUtils.js:25-28
@@ -573,7 +590,30 @@ void rfx_ssgi_chain_destroy(rfx_ssgi_chain* ch) {
   rfx_plane* all[] = {&ch->ssgi_out, &ch->tr[0], &ch->tr[1], &ch->dnA[0], &ch->dnA[1], &ch->dnB[0], &ch->dnB[1], &ch->composed,
                       &ch->in_depth, &ch->in_gb, &ch->in_vel, &ch->in_direct};
   for (rfx_plane* p : all) if (p->ptr) rfx_plane_free(ctx, p);
+  for (auto& sp : ch->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (cudaEvent_t e : ch->event_pool) cudaEventDestroy(e);
   delete ch;
+}
+
+rfx_status rfx_ssgi_chain_set_profiling(rfx_ssgi_chain* ch, int32_t enable) {
+  if (!ch) return RFX_ERR_INVALID_ARG;
+  ch->profiling = enable != 0;
+  return RFX_OK;
+}
+rfx_status rfx_ssgi_chain_get_profile(rfx_ssgi_chain* ch, double* ms, uint64_t* launches) {
+  if (!ch || !ms || !launches) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = ch->ctx;
+  CU(cudaDeviceSynchronize());
+  for (auto& sp : ch->spans) {
+    float t = 0.0f;
+    CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms[sp.slot] += (double)t;
+    launches[sp.slot] += 1;
+    ch->event_pool.push_back(sp.a);
+    ch->event_pool.push_back(sp.b);
+  }
+  ch->spans.clear();
+  return RFX_OK;
 }
 
 rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* ch) {
@@ -609,7 +649,9 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
   sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
   sp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_trace);
   // velocityTexture is a null sampler in the shipped wiring
-  st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, 0, 0);
+  const cudaStream_t cs = stream ? (cudaStream_t)stream : ctx->stream;
+  { SpanGuard g(ch, cs, 0);
+    st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, 0, 0); }
   if (st != RFX_OK) return st;
   // ---- K2  TemporalReprojectPass.render (TemporalReprojectPass.js:162-214), options from Denoiser.js:26-43 + SSGIEffect.js:74-77
   rfx_temporal_params tp{};
@@ -629,8 +671,9 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
   if (o.mode == RFX_MODE_SSGI) { tp.texture_count = 2; tp.input_type = RFX_INPUT_DIFFUSE_SPECULAR; tp.reproject_specular[0] = 0; tp.reproject_specular[1] = 1; }
   else { tp.texture_count = 1; tp.input_type = RFX_INPUT_SPECULAR; tp.reproject_specular[0] = 1; tp.reproject_specular[1] = 1; }
   const int tc = tp.texture_count;
-  st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
-                                     tc == 2 ? &ch->tr[1] : nullptr, 0, 0);
+  { SpanGuard g(ch, cs, 1);
+    st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
+                                       tc == 2 ? &ch->tr[1] : nullptr, 0, 0); }
   if (st != RFX_OK) return st;
   ch->keep_data = 1.0f;  // :195
   memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
@@ -648,7 +691,8 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
     rfx_plane* outp = horizontal ? ch->dnA : ch->dnB;
     pp.input_linear = i == 0 ? 0 : 1;
     pp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_poisson);
-    st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, 0, 0);
+    { SpanGuard g(ch, cs, i == 0 ? 2 : 3);
+      st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, 0, 0); }
     if (st != RFX_OK) return st;
   }
   // ---- K4  DenoiserComposePass.render
@@ -656,7 +700,8 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
     rfx_compose_params cp{};
     cp.cam = f->cam;
     cp.input_type = RFX_INPUT_DIFFUSE_SPECULAR;
-    st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, 0, 0);
+    { SpanGuard g(ch, cs, 4);
+      st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, 0, 0); }
     if (st != RFX_OK) return st;
   }
   return RFX_OK;

@@ -226,5 +226,17 @@ class SsgiChain:
         self.ctx.sync()
         return out
 
+    PROFILE_SLOTS = ("K1_ssgi_trace", "K2_temporal_reproject", "K3_poisson_pass0", "K3_poisson_pass1plus", "K4_gi_compose")
+
+    def set_profiling(self, enable: bool):
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_set_profiling(self.h, int(enable)))
+
+    def get_profile(self) -> dict:
+        """{slot: (total_ms, launches)} for the frames rendered since the last call."""
+        ms = (C.c_double * 5)()
+        n = (C.c_uint64 * 5)()
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_get_profile(self.h, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_SLOTS)}
+
     def render_host(self, hf: abi.SsgiHostFrame):
         self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_host(self.h, C.byref(hf)))
