@@ -274,3 +274,62 @@ def run_chain_parity(width=192, height=108, frames=2, max_frac=2e-3, **opt_kw) -
             worst = max(worst, c["frac_bad"])
             lines.append(f"f{t}.{k}: bad={c['frac_bad']:.2e} maxrel_ok={c['max_rel_ok']:.1e} biteq={c['bit_equal']:.4f}")
     return dict(ok=worst <= max_frac, worst=worst, launches=launches, summary=f"worst bad-pixel fraction {worst:.2e} (limit {max_frac:.0e}); " + "; ".join(lines))
+
+
+# ----------------------------------------------------------------------------------------------
+# other passes: HBAO (C4), AO compose, motion blur (C1), TRAA
+# ----------------------------------------------------------------------------------------------
+def hbao_params(cam_u: dict, index: int, spp: int = 8) -> abi.HbaoParams:
+    """defaults src/ao/AOEffect.js:8-21; projectionViewMatrix = projectionMatrix * matrixWorldInverse (AOPass.js:93-96),
+    multiplied in float64 like three.js' Matrix4 (JS numbers) and uploaded as float32."""
+    p = abi.HbaoParams()
+    P = np.asarray(cam_u["projection"], np.float64).reshape(4, 4).T
+    V = np.asarray(cam_u["view_matrix"], np.float64).reshape(4, 4).T
+    abi.set_f16(p.projection_view, np.ascontiguousarray((P @ V).T.reshape(16)).astype(np.float32))
+    abi.set_f16(p.projection_inverse, cam_u["projection_inverse"])
+    abi.set_f16(p.camera_matrix_world, cam_u["camera_matrix_world"])
+    p.ao_distance, p.distance_power, p.bias, p.thickness, p.spp, p.blue_noise_index = 2.0, 1.0, 40.0, 0.075, spp, index
+    return p
+
+
+def ao_compose_params(power: float = 2.0, color=(0.0, 0.0, 0.0)) -> abi.AoComposeParams:
+    p = abi.AoComposeParams()
+    p.power = power
+    p.color[:] = list(color)
+    return p
+
+
+def motion_blur_params(width: int, height: int, frame: int = 7, samples: int = 16, delta_time: float = 1 / 60, resolution=None) -> abi.MotionBlurParams:
+    """defaults src/motion-blur/MotionBlurEffect.js:14; `resolution` is the window size (may differ from the buffer size)."""
+    p = abi.MotionBlurParams()
+    p.intensity, p.jitter, p.delta_time = 1.0, 1.0, max(1 / 1000, delta_time)
+    p.resolution[:] = list(resolution or (width, height))
+    p.frame, p.samples = frame, samples
+    return p
+
+
+def rotation_velocity_field(width: int, height: int, depth: np.ndarray, vmax: float = 0.05) -> np.ndarray:
+    """C1: rigid rotation about the image centre, |v| up to vmax in uv units; velocity-plane layout."""
+    ys, xs = np.meshgrid((np.arange(height) + 0.5) / height - 0.5, (np.arange(width) + 0.5) / width - 0.5, indexing="ij")
+    k = vmax / 0.5
+    vel = np.zeros((height, width, 4), np.float32)
+    vel[..., 0], vel[..., 1] = (-ys * k).astype(np.float32), (xs * k).astype(np.float32)
+    vel[..., 3] = depth
+    vel[:8, :8, :2] = 0.0  # a patch that did not move (early-out branch)
+    return vel
+
+
+def traa_temporal_params(cam: abi.CameraS, cam_pos, prev: dict, keep_data: float) -> abi.TemporalParams:
+    """TRAAEffect forced options (src/traa/TRAAEffect.js:21-31) over the TemporalReprojectPass defaults (:17-32)."""
+    p = abi.TemporalParams()
+    p.cam = cam
+    abi.set_f16(p.prev_view_matrix, prev["view_matrix"])
+    abi.set_f16(p.prev_camera_matrix_world, prev["camera_matrix_world"])
+    abi.set_f16(p.prev_projection, prev["projection"])
+    abi.set_f16(p.prev_projection_inverse, prev["projection_inverse"])
+    p.camera_pos[:] = [float(x) for x in cam_pos]
+    p.prev_camera_pos[:] = [float(x) for x in prev["position"]]
+    p.max_blend, p.neighborhood_clamp_intensity, p.keep_data, p.confidence_power = 0.9, 1.0, keep_data, 4.0
+    p.full_accumulate, p.texture_count, p.input_type, p.log_transform, p.history_linear = 0, 1, abi.INPUT_DIFFUSE, 1, 1
+    p.reproject_specular[:] = [0, 0]
+    return p
