@@ -204,6 +204,10 @@ int rfx_version(void);
 void* rfx_ctx_stream(rfx_ctx* ctx);      /* the context's cudaStream_t             */
 rfx_status rfx_ctx_sync(rfx_ctx* ctx);   /* cudaStreamSynchronize(ctx stream)      */
 uint64_t rfx_launch_count(const rfx_ctx* ctx); /* kernels launched so far by this ctx */
+/* Kernel variants: 1 (default) = transcendentals on the SFU pipe (lg2/ex2.approx, ~2^-22 relative
+ * error, well inside the 1e-3 parity budget); 0 = exact-libm variants whose non-transcendental
+ * arithmetic is bit-identical to the parity oracle.  Both are CUDA kernels; neither is a CPU path. */
+rfx_status rfx_ctx_set_fast_math(rfx_ctx* ctx, int32_t enable);
 
 /* blue noise: 128x128 RGBA8 in GL texel order (flipY already applied)
  * (src/utils/BlueNoiseUtils.js:6-15) */

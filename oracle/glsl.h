@@ -69,9 +69,19 @@ struct vec4 {
   inline vec4 operator op(vec4 a, vec4 b) { return vec4(a.x op b.x, a.y op b.y, a.z op b.z, a.w op b.w); }    \
   inline vec4 operator op(vec4 a, float s) { return vec4(a.x op s, a.y op s, a.z op s, a.w op s); }           \
   inline vec4 operator op(float s, vec4 a) { return vec4(s op a.x, s op a.y, s op a.z, s op a.w); }
-GL_DEF2(+) GL_DEF2(-) GL_DEF2(*) GL_DEF2(/)
-GL_DEF3(+) GL_DEF3(-) GL_DEF3(*) GL_DEF3(/)
-GL_DEF4(+) GL_DEF4(-) GL_DEF4(*) GL_DEF4(/)
+GL_DEF2(+) GL_DEF2(-) GL_DEF2(*)
+GL_DEF3(+) GL_DEF3(-) GL_DEF3(*)
+GL_DEF4(+) GL_DEF4(-) GL_DEF4(*)
+// division: vector / vector and scalar / vector are component-wise IEEE divisions; vector / SCALAR is lowered the
+// way GLSL compilers lower it — one IEEE reciprocal, then a multiply per component.
+inline vec2 operator/(vec2 a, vec2 b) { return vec2(a.x / b.x, a.y / b.y); }
+inline vec3 operator/(vec3 a, vec3 b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
+inline vec4 operator/(vec4 a, vec4 b) { return vec4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w); }
+inline vec2 operator/(float s, vec2 a) { return vec2(s / a.x, s / a.y); }
+inline vec3 operator/(float s, vec3 a) { return vec3(s / a.x, s / a.y, s / a.z); }
+inline vec2 operator/(vec2 a, float s) { float r = 1.0f / s; return vec2(a.x * r, a.y * r); }
+inline vec3 operator/(vec3 a, float s) { float r = 1.0f / s; return vec3(a.x * r, a.y * r, a.z * r); }
+inline vec4 operator/(vec4 a, float s) { float r = 1.0f / s; return vec4(a.x * r, a.y * r, a.z * r, a.w * r); }
 inline vec2 operator-(vec2 a) { return vec2(-a.x, -a.y); }
 inline vec3 operator-(vec3 a) { return vec3(-a.x, -a.y, -a.z); }
 inline vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }

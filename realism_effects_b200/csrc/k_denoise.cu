@@ -111,6 +111,164 @@ __global__ void __launch_bounds__(kThreads) poisson_kernel(const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K0  per-frame G-buffer decode prepass: (world normal xyz, roughness) as one float4 per pixel.
+// K3 decodes the packed G-buffer 9x per pixel per pass (centre + 8 taps) and runs 2*iterations passes;
+// decoding once per frame with the *same* arithmetic (bit-identical values) removes ~1.6k instructions
+// per pixel per frame.  For the velocity-layout variant (no GBUFFER_TEXTURE) roughness decodes the
+// null-sampler texel (0,0,0,1) => 0 and the normal comes from .b.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gbuffer_decode_kernel(PV gb, OutV nrd, int W, int H, int gbuffer_texture) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const float4 g = ld_f4(gb, x, y);
+  const v3 n = unpackNormal(gbuffer_texture ? g.y : g.z);
+  const float r = gbuffer_texture ? gb_roughness(g.z) : gb_roughness(0.0f);
+  st_f4(nrd.p, nrd.pitch, x, y, make_float4(n.x, n.y, n.z, r));
+}
+cudaError_t launch_gbuffer_decode(PV gb, OutV nrd, int W, int H, int gbuffer_texture, cudaStream_t s) {
+  dim3 grid((W + 31) / 32, (H + 7) / 8);
+  gbuffer_decode_kernel<<<grid, 256, 0, s>>>(gb, nrd, W, H, gbuffer_texture);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 fast variant.  Same algorithm and the same tap geometry (the tap coordinates, nearest texel
+// choices and bilinear weights are computed with exactly the arithmetic of poisson_kernel above),
+// but the transcendental work is restructured for the SFU pipe (MUFU.LG2 / MUFU.EX2):
+//   log(c+1)                   -> lg2(c+1) * ln2
+//   luminance = pow(d, 0.125)  -> ex2(0.125 * lg2(d))
+//   wBasic = exp(A), w*specularFactor = exp(A + S), pow(w, 0.1) = exp(0.1*(A [+ S])),
+//   w * lumaFactor = exp(A [+ S] - lumaDiff*lumaPhi)     (one ex2 each, no pow)
+//   age = ex2(-1.2*phi*lg2(a + 1)),  exp(x) - 1 -> ex2(x*log2e) - 1
+// The approximate lg2/ex2 have ~2^-22 relative error, far inside the 1e-3 parity budget (the outputs are
+// rounded to fp16 anyway); the exact variant above stays available (rfx_ctx_set_fast_math(ctx, 0)).
+// ------------------------------------------------------------------------------------------
+RFX_D float lg2a(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D float ex2a(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define RFX_LN2 0.69314718055994530942f
+#define RFX_LOG2E 1.44269504088896340736f
+RFX_D v3 flog1p3(v3 c) { return mk3(lg2a(c.x + 1.0f) * RFX_LN2, lg2a(c.y + 1.0f) * RFX_LN2, lg2a(c.z + 1.0f) * RFX_LN2); }
+RFX_D float flum(v3 c) { return ex2a(0.125f * lg2a(dot(mk3(0.2125f, 0.7154f, 0.0721f), c))); }
+
+template <bool LINEAR>
+RFX_D void fetch2(const PoissonArgs& a, v2 uv, bool two, v3& c0, v3& c1, float* alpha0 = nullptr, float* alpha1 = nullptr) {
+  if (LINEAR) {  // RGBA16F + LinearFilter: one bilinear setup shared by both planes
+    const Bilin b = bilin_setup(uv, a.W, a.H);
+    {
+      const v4 t00 = ld_h4(a.in0, b.x0, b.y0), t10 = ld_h4(a.in0, b.x1, b.y0), t01 = ld_h4(a.in0, b.x0, b.y1), t11 = ld_h4(a.in0, b.x1, b.y1);
+      c0 = mk3(bilin_blend(b, t00.x, t10.x, t01.x, t11.x), bilin_blend(b, t00.y, t10.y, t01.y, t11.y), bilin_blend(b, t00.z, t10.z, t01.z, t11.z));
+      if (alpha0) *alpha0 = bilin_blend(b, t00.w, t10.w, t01.w, t11.w);
+    }
+    if (two) {
+      const v4 t00 = ld_h4(a.in1, b.x0, b.y0), t10 = ld_h4(a.in1, b.x1, b.y0), t01 = ld_h4(a.in1, b.x0, b.y1), t11 = ld_h4(a.in1, b.x1, b.y1);
+      c1 = mk3(bilin_blend(b, t00.x, t10.x, t01.x, t11.x), bilin_blend(b, t00.y, t10.y, t01.y, t11.y), bilin_blend(b, t00.z, t10.z, t01.z, t11.z));
+      if (alpha1) *alpha1 = bilin_blend(b, t00.w, t10.w, t01.w, t11.w);
+    }
+  } else {  // pass 0: NEAREST fp32 temporal targets
+    const int nx = nearest_i(uv.x, a.W), ny = nearest_i(uv.y, a.H);
+    const float4 t = ld_f4(a.in0, nx, ny);
+    c0 = mk3(t.x, t.y, t.z);
+    if (alpha0) *alpha0 = t.w;
+    if (two) {
+      const float4 u = ld_f4(a.in1, nx, ny);
+      c1 = mk3(u.x, u.y, u.z);
+      if (alpha1) *alpha1 = u.w;
+    }
+  }
+}
+
+// TC planes; plane j is "specular" per a.spec0/spec1; with TC == 2 plane 1 reads in1, with TC == 1 the single plane reads in0.
+template <int TC, bool LINEAR>
+__global__ void __launch_bounds__(kThreads) poisson_fast_kernel(const __grid_constant__ PoissonArgs a) {
+  int x, y;
+  block_pixel(x, y, a.row0 & ~1);
+  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
+  const v2 vUv = pixel_uv(x, y, a.W, a.H);
+  const float depth = ld_r32f(a.depth, xc, yc);
+  const float fwd = fwidth_f(depth);
+  const float4 nc = ld_f4(a.nrd, xc, yc);
+  const v3 normal = mk3(nc.x, nc.y, nc.z);
+  const float fwn = length(fwidth_3(normal));
+  if (!active) return;
+  if (depth == 1.0f && fwd == 0.0f) return;
+  const float roughness = nc.w;
+
+  v3 rgb[2];
+  float alpha[2], lumc[2], age[2], tw[2];
+  {
+    v3 c[2];
+    fetch2<LINEAR>(a, vUv, TC == 2, c[0], c[1], &alpha[0], &alpha[1]);
+#pragma unroll
+    for (int i = 0; i < TC; i++) {
+      age[i] = ex2a(-1.2f * a.phi * lg2a(alpha[i] + 1.0f));
+      rgb[i] = flog1p3(c[i] * 1.0003f);
+      lumc[i] = flum(rgb[i]);
+      tw[i] = 1.0f;
+    }
+  }
+  const float glossiness = fmaxf(0.0f, 4.0f * (1.0f - roughness / 0.25f));
+  // exponent (natural-log units) added for specular planes: w *= exp(-glossiness * specularPhi)
+  const float specArg = -glossiness * a.specular_phi;
+  const float sarg[2] = {a.spec0 ? specArg : 0.0f, a.spec1 ? specArg : 0.0f};
+  float flatness = 1.0f - fminf(fwn, 1.0f);
+  flatness = flatness * flatness * 0.75f + 0.25f;
+  const uchar4 bn = __ldg(a.blue.tex + ((y + a.blue.shift.sy) % a.blue.size) * a.blue.size + ((x + a.blue.shift.sx) % a.blue.size));
+  const float2 sc = __ldg(a.rot_table + bn.x);
+  const float k = a.radius * flatness;
+  const float m00 = k * sc.y, m01 = k * -sc.x, m10 = k * sc.x, m11 = k * sc.y;
+
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float ox = a.tap_ox[i], oy = a.tap_oy[i];  // POISSON[i] / resolution, divided on the host (IEEE, same value)
+    const v2 nuv = mk2(vUv.x + (m00 * ox + m10 * oy), vUv.y + (m01 * ox + m11 * oy));
+    const int nx = nearest_i(nuv.x, a.W), ny = nearest_i(nuv.y, a.H);
+    const float ndepth = ld_r32f(a.depth, nx, ny);
+    if (ndepth == 1.0f) continue;  // wBasic = 0 => w = 0 for every plane: the tap contributes nothing
+    const float4 nn = ld_f4(a.nrd, nx, ny);
+    const float normalDiff = 1.0f - fmaxf(dot(normal, mk3(nn.x, nn.y, nn.z)), 0.0f);
+    const float depthDiff = 10000.0f * fabsf(depth - ndepth);
+    const float roughnessDiff = fabsf(roughness - nn.w);
+    const float A = -normalDiff * a.normal_phi - depthDiff * a.depth_phi - roughnessDiff * a.roughness_phi;
+    v3 c[2];
+    fetch2<LINEAR>(a, nuv, TC == 2, c[0], c[1]);
+#pragma unroll
+    for (int j = 0; j < TC; j++) {
+      const float Aj = A + sarg[j];
+      const v3 lc = flog1p3(c[j]);
+      const float lumaDiff = fminf(fabsf(lumc[j] - flum(lc)), 0.5f);
+      const float wl = ex2a((Aj - lumaDiff * a.luma_phi) * RFX_LOG2E);  // w * lumaFactor
+      const float wd = ex2a(Aj * (0.1f * RFX_LOG2E));                    // pow(w, 0.1)
+      float w = mixf(wl, wd, age[j]) * age[j];
+      w = (w < 0.0001f) ? 0.0f : w;
+      rgb[j] = mk3(fma_(w, lc.x, rgb[j].x), fma_(w, lc.y, rgb[j].y), fma_(w, lc.z, rgb[j].z));
+      tw[j] += w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TC; j++) {
+    const float inv = __frcp_rn(tw[j]);
+    const v3 m = rgb[j] * inv;
+    const v3 c = mk3(ex2a(m.x * RFX_LOG2E) - 1.0f, ex2a(m.y * RFX_LOG2E) - 1.0f, ex2a(m.z * RFX_LOG2E) - 1.0f);
+    const OutV& o = j == 0 ? a.out0 : a.out1;
+    st_h4(o.p, o.pitch, x, y, mk4(c, alpha[j]));
+  }
+}
+
+cudaError_t launch_poisson_fast(const PoissonArgs& a, cudaStream_t s) {
+  const int rb = a.row0 & ~1;
+  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  if (a.input_linear && !a.in_half) return cudaErrorInvalidValue;
+  if (!a.input_linear && a.in_half) return cudaErrorNotSupported;
+  if (a.texture_count == 2) {
+    if (a.input_linear) poisson_fast_kernel<2, true><<<grid, kThreads, 0, s>>>(a); else poisson_fast_kernel<2, false><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (a.input_linear) poisson_fast_kernel<1, true><<<grid, kThreads, 0, s>>>(a); else poisson_fast_kernel<1, false><<<grid, kThreads, 0, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s) {
   const int rb = a.row0 & ~1;
   dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);

@@ -12,7 +12,7 @@ RFX_D v3 hbao_world_pos(const HbaoArgs& a, float depth, v2 coord) {  // hbao_uti
   const v4 clip = mk4(coord.x * 2.0f - 1.0f, coord.y * 2.0f - 1.0f, z, 1.0f);
   const v4 vs = mul(a.projection_inverse, clip);
   const v4 ws = mul(a.camera_matrix_world, vs);
-  return mk3(ws.x / ws.w, ws.y / ws.w, ws.z / ws.w);
+  return xyz(ws) / ws.w;
 }
 
 __global__ void __launch_bounds__(256) hbao_kernel(const __grid_constant__ HbaoArgs a) {
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) hbao_kernel(const __grid_constant__ HbaoA
   }
   const v3 sampleWorldPos = worldPos + a.ao_distance * powf(bz, a.distance_power + 1.0f) * sampleWorldDir;
   const v4 suv4 = mul(a.projection_view, mk4(sampleWorldPos, 1.0f));
-  const v2 suv = mk2(suv4.x / suv4.w * 0.5f + 0.5f, suv4.y / suv4.w * 0.5f + 0.5f);
+  const v2 sq = mk2(suv4.x, suv4.y) / suv4.w;
+  const v2 suv = mk2(sq.x * 0.5f + 0.5f, sq.y * 0.5f + 0.5f);
   const float sampleDepth = tex_r32f_nearest(a.depth, suv);
   float deltaDepth = depth - sampleDepth;
   const float d = length(sampleWorldPos - cameraPosition);

@@ -5,11 +5,18 @@
 //
 // Blackwell mapping: one thread per pixel, a warp owns an 8x4 pixel tile laid out in 2x2 quads so
 // the implicit-LOD env fetch (ssgi_utils.frag:218) gets its quad derivatives from two shuffles.
-// The march is a data-dependent gather over the (L2-resident) depth plane; the ray positions do not
-// depend on the fetched depths, so the taps of a batch of RFX_MARCH_BATCH steps are issued together
-// (memory-level parallelism instead of a 19-deep dependent chain) and tested in order afterwards.
+// The march is a data-dependent gather over an L2-resident plane.  Three things keep the per-tap
+// instruction count low without changing a single bit of the tap positions:
+//   * a per-frame prepass turns the depth plane into a view-space-z plane with the shader's own
+//     getViewZ() arithmetic, so a tap is one 4-byte load + two compares (no divide per tap);
+//   * when the projection matrix has the perspective sparsity pattern (detected on the host) the
+//     fma chain of `projectionMatrix * vec4(p, 1)` drops its exact-zero terms: x' = fma(P00,x,P20*z),
+//     y' = fma(P11,y,P21*z), w' = -z — bit-identical to the full chain;
+//   * the ray positions do not depend on the fetched depths, so the taps of a batch of
+//     RFX_MARCH_BATCH steps are issued together (memory-level parallelism) and tested in order.
 // All blue-noise driven transcendentals (sin/cos of 2*pi*k/255, the march step profile
 // 1-exp(-0.25 (i+b-0.5)^2)) come from small host-built tables indexed by the 8-bit noise value.
+// FAST = true additionally moves the remaining continuous transcendentals to the SFU pipe.
 #include "rfx_kernels.h"
 
 #ifndef RFX_MARCH_BATCH
@@ -23,19 +30,54 @@ namespace rfx {
 #define PI_F 3.1415926535897932384626433832795f
 
 RFX_D float lum_s(v3 a) { return dot(mk3(0.2125f, 0.7154f, 0.0721f), a); }  // ssgi_utils.frag:3
+RFX_D float lg2a_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-struct SsgiCtx {
-  const SsgiArgs& a;
-  __device__ SsgiCtx(const SsgiArgs& a_) : a(a_) {}
-  RFX_D float getViewZ(float depth) const {  // ssgi_utils.frag:7-13
-    if (a.cam.perspective) return a.near_mul_far / (a.far_minus_near * depth - a.cam.far_plane);
-    return depth * a.near_minus_far - a.cam.near_plane;
+// getViewZ  ssgi_utils.frag:7-13
+RFX_D float ssgi_view_z(const SsgiArgs& a, float depth) {
+  if (a.cam.perspective) return a.near_mul_far / (a.far_minus_near * depth - a.cam.far_plane);
+  return depth * a.near_minus_far - a.cam.near_plane;
+}
+
+// prepass: viewZ plane = getViewZ(depth), same arithmetic as the shader => bit-identical taps
+__global__ void __launch_bounds__(256) viewz_kernel(PV depth, OutV vz, int W, int H, float near_mul_far, float far_minus_near, float near_minus_far,
+                                                    float near_plane, float far_plane, int perspective) {
+  const int x = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y;
+  if (x >= W) return;
+  const float* src = (const float*)(depth.p + (long long)y * depth.pitch) + x;
+  float* dst = (float*)(vz.p + (long long)y * vz.pitch) + x;
+  float d[4];
+  if (x + 3 < W) { const float4 t = __ldg((const float4*)src); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
+  else { for (int i = 0; i < 4; i++) d[i] = x + i < W ? __ldg(src + i) : 0.0f; }
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) o[i] = perspective ? near_mul_far / (far_minus_near * d[i] - far_plane) : d[i] * near_minus_far - near_plane;
+  if (x + 3 < W) *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+  else { for (int i = 0; i < 4 && x + i < W; i++) dst[i] = o[i]; }
+}
+cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) {
+  dim3 grid((a.W / 4 + 255) / 256 + 1, a.H);
+  viewz_kernel<<<grid, 256, 0, s>>>(a.depth, vz, a.W, a.H, a.near_mul_far, a.far_minus_near, a.near_minus_far, a.cam.near_plane, a.cam.far_plane,
+                                    a.cam.perspective);
+  return cudaGetLastError();
+}
+
+// viewSpaceToScreenSpace  ssgi_utils.frag:26-33  (vector / scalar = reciprocal + multiplies, see rfx_device.cuh)
+template <bool SPARSE>
+RFX_D v2 view_to_screen(const SsgiArgs& a, v3 p) {
+  float cx, cy, cw;
+  const float* M = a.cam.projection.m;
+  if (SPARSE) {
+    cx = fma_(M[0], p.x, M[8] * p.z);
+    cy = fma_(M[5], p.y, M[9] * p.z);
+    cw = -p.z;
+  } else {
+    cx = fma_(M[0], p.x, fma_(M[4], p.y, fma_(M[8], p.z, M[12])));
+    cy = fma_(M[1], p.x, fma_(M[5], p.y, fma_(M[9], p.z, M[13])));
+    cw = fma_(M[3], p.x, fma_(M[7], p.y, fma_(M[11], p.z, M[15])));
   }
-  RFX_D v2 viewSpaceToScreenSpace(v3 p) const {  // :26-33
-    v4 pc = mul(a.cam.projection, mk4(p, 1.0f));
-    return mk2(pc.x / pc.w * 0.5f + 0.5f, pc.y / pc.w * 0.5f + 0.5f);
-  }
-};
+  const float r = 1.0f / cw;
+  return mk2((cx * r) * 0.5f + 0.5f, (cy * r) * 0.5f + 0.5f);
+}
 
 RFX_D v2 equirectDirectionToUv(v3 d) {  // ssgi_utils.frag:64-74
   v2 uv = mk2(atan2f(d.z, d.x), acosf(d.y));
@@ -44,52 +86,66 @@ RFX_D v2 equirectDirectionToUv(v3 d) {  // ssgi_utils.frag:64-74
   uv.y = 1.0f - uv.y;
   return uv;
 }
+template <bool FAST>
 RFX_D v3 equirectUvToDirection(v2 uv) {  // :77-86
   uv.x -= 0.5f;
   uv.y = 1.0f - uv.y;
-  float theta = uv.x * 2.0f * PI_F;
-  float phi = uv.y * PI_F;
-  float sinPhi = sinf(phi);
+  const float theta = uv.x * 2.0f * PI_F;
+  const float phi = uv.y * PI_F;
+  if (FAST) {
+    float st, ct, sp, cp;
+    __sincosf(theta, &st, &ct);
+    __sincosf(phi, &sp, &cp);
+    return mk3(sp * ct, cp, sp * st);
+  }
+  const float sinPhi = sinf(phi);
   return mk3(sinPhi * cosf(theta), cosf(phi), sinPhi * sinf(theta));
 }
-RFX_D float F_Schlick1(float f0, float f90, float theta) { return f0 + (f90 - f0) * powf(1.0f - theta, 5.0f); }
+template <bool FAST>
+RFX_D float pow5(float x) {
+  if (FAST) { const float x2 = x * x; return x2 * x2 * x; }
+  return powf(x, 5.0f);
+}
+template <bool FAST>
+RFX_D float F_Schlick1(float f0, float f90, float theta) { return f0 + (f90 - f0) * pow5<FAST>(1.0f - theta); }
 RFX_D float D_GTR2(float roughness, float NoH) {  // D_GTR(roughness, NoH, 2.)
-  float a2 = roughness * roughness;
-  float t = (NoH * NoH) * (a2 * a2 - 1.0f) + 1.0f;
+  const float a2 = roughness * roughness;
+  const float t = (NoH * NoH) * (a2 * a2 - 1.0f) + 1.0f;
   return a2 / (PI_F * (t * t));
 }
 RFX_D float SmithG(float NDotV, float alphaG) {
-  float a = alphaG * alphaG;
-  float b = NDotV * NDotV;
+  const float a = alphaG * alphaG;
+  const float b = NDotV * NDotV;
   return (2.0f * NDotV) / (NDotV + sqrtf(a + b - a * b));
 }
 RFX_D float GGXVNDFPdf(float NoH, float NoV, float roughness) {
-  float D = D_GTR2(roughness, NoH);
-  float G1 = SmithG(NoV, roughness * roughness);
+  const float D = D_GTR2(roughness, NoH);
+  const float G1 = SmithG(NoV, roughness * roughness);
   return (D * G1) / fmaxf(0.00001f, 4.0f * NoV);
 }
+template <bool FAST>
 RFX_D float evalDisneyDiffuse(float NoL, float NoV, float LoH, float roughness, float metalness) {
-  float FD90 = 0.5f + 2.0f * roughness * (LoH * LoH);
-  float a = F_Schlick1(1.0f, FD90, NoL);
-  float b = F_Schlick1(1.0f, FD90, NoV);
+  const float FD90 = 0.5f + 2.0f * roughness * (LoH * LoH);
+  const float a = F_Schlick1<FAST>(1.0f, FD90, NoL);
+  const float b = F_Schlick1<FAST>(1.0f, FD90, NoV);
   return (a * b / PI_F) * (1.0f - metalness);
 }
 RFX_D float evalDisneySpecular(float roughness, float NoH, float NoV, float NoL) {
-  float D = D_GTR2(roughness, NoH);
+  const float D = D_GTR2(roughness, NoH);
   float ag = 0.5f + roughness * 0.5f;
   ag = ag * ag;
-  float a2 = ag * ag;  // GeometryTerm: a2 = roughness * roughness with roughness := pow(.5 + r*.5, 2.)
-  float G = SmithG(NoV, a2) * SmithG(NoL, a2);
+  const float a2 = ag * ag;  // GeometryTerm: a2 = roughness * roughness with roughness := pow(.5 + r*.5, 2.)
+  const float G = SmithG(NoV, a2) * SmithG(NoL, a2);
   return D * G / (4.0f * NoL * NoV);
 }
 RFX_D v3 cosineSampleHemisphere_cs(v3 n, float ux, float sth, float cth) {  // ssgi_utils.frag:183-191
-  float r = sqrtf(ux);
-  v3 b = normalize(cross(n, mk3(0.0f, 1.0f, 1.0f)));
-  v3 t = cross(b, n);
+  const float r = sqrtf(ux);
+  const v3 b = normalize(cross(n, mk3(0.0f, 1.0f, 1.0f)));
+  const v3 t = cross(b, n);
   return normalize(r * sth * b + sqrtf(1.0f - ux) * n + r * cth * t);
 }
 RFX_D void calculateAngles(v3 l, v3 v, v3 n, float& NoL, float& NoH, float& LoH, float& VoH) {  // ssgi.frag:93-100
-  v3 h = normalize(v + l);
+  const v3 h = normalize(v + l);
   NoL = clampf(dot(n, l), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
   NoH = clampf(dot(n, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
   LoH = clampf(dot(l, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
@@ -98,38 +154,39 @@ RFX_D void calculateAngles(v3 l, v3 v, v3 n, float& NoL, float& NoH, float& LoH,
 
 // textureLod(map, uv, lod) with linear-mipmap-linear / clamp
 RFX_D v3 env_trilinear(const EnvD& e, v2 uv, float lod) {
-  float l = clampf(lod, 0.0f, (float)(e.levels - 1));
-  int l0 = (int)floorf(l);
-  int l1 = min(l0 + 1, e.levels - 1);
-  float f = l - (float)l0;
-  v4 A = tex_h4_linear(e.mip[l0], uv);
+  const float l = clampf(lod, 0.0f, (float)(e.levels - 1));
+  const int l0 = (int)floorf(l);
+  const int l1 = min(l0 + 1, e.levels - 1);
+  const float f = l - (float)l0;
+  const v4 A = tex_h4_linear(e.mip[l0], uv);
   if (f == 0.0f || l1 == l0) return xyz(A);
-  v4 B = tex_h4_linear(e.mip[l1], uv);
+  const v4 B = tex_h4_linear(e.mip[l1], uv);
   return mk3(mixf(A.x, B.x, f), mixf(A.y, B.y, f), mixf(A.z, B.z, f));
 }
 
 // getEnvColor  ssgi.frag:311-346
 RFX_D v3 getEnvColor(const SsgiArgs& a, v3 l, float roughness, bool isDiffuseSample, bool isEnvSample) {
   if (!(a.flags & RFX_SSGI_USE_ENVMAP)) return mk3(0.0f);
-  v3 reflectedWS = normalize(mul_dir_left(l, a.cam.view_matrix));
+  const v3 reflectedWS = normalize(mul_dir_left(l, a.cam.view_matrix));
   float mip = a.env_blur * a.max_env_mip;
   if (!isDiffuseSample && roughness < 0.15f) mip *= roughness / 0.15f;
   v3 s = env_trilinear(a.env, equirectDirectionToUv(reflectedWS), mip);
-  float maxEnvLum = isEnvSample ? 100.0f : 25.0f;
-  float envLum = lum_s(s);
+  const float maxEnvLum = isEnvSample ? 100.0f : 25.0f;
+  const float envLum = lum_s(s);
   if (envLum > maxEnvLum) s = s * (maxEnvLum / envLum);
   return s;
 }
 
 RFX_D float getSaturation(v3 c) {  // :348-360
-  float mx = fmaxf(fmaxf(c.x, c.y), c.z), mn = fminf(fminf(c.x, c.y), c.z);
+  const float mx = fmaxf(fmaxf(c.x, c.y), c.z), mn = fminf(fminf(c.x, c.y), c.z);
   if (mx == mn) return 0.0f;
   return (mx - mn) / mx;
 }
 
 // RayMarch + BinarySearch  ssgi.frag:441-503.  `dir` is l scaled in place like the shader's inout.
 // Returns the hit uv; sets hit=false and hitPos=(10e9) on a miss.
-RFX_D v2 rayMarch(const SsgiArgs& a, const SsgiCtx& c, v3& dir, v3& hitPos, int noiseB, bool& hit) {
+template <bool SPARSE>
+RFX_D v2 rayMarch(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit) {
   dir = dir * (a.ray_distance / (float)a.steps);
   v2 uv = mk2(0.0f, 0.0f);
   hit = false;
@@ -138,22 +195,21 @@ RFX_D v2 rayMarch(const SsgiArgs& a, const SsgiCtx& c, v3& dir, v3& hitPos, int 
   while (i < a.steps && !hit) {
     v3 pos[RFX_MARCH_BATCH];
     v2 uvs[RFX_MARCH_BATCH];
-    float dep[RFX_MARCH_BATCH];
+    float vzs[RFX_MARCH_BATCH];
     v3 p = hitPos;
 #pragma unroll
-    for (int k = 0; k < RFX_MARCH_BATCH; k++) {  // issue the whole batch of depth taps before testing any
+    for (int k = 0; k < RFX_MARCH_BATCH; k++) {  // issue the whole batch of taps before testing any
       const int ii = min(i + k, a.steps - 1);
       const float cs = __ldg(cs_row + (ii - 1) * 256);
       p = p + dir * cs;
       pos[k] = p;
-      uvs[k] = c.viewSpaceToScreenSpace(p);
-      dep[k] = tex_r32f_nearest(a.depth, uvs[k]);
+      uvs[k] = view_to_screen<SPARSE>(a, p);
+      vzs[k] = tex_r32f_nearest(a.viewz, uvs[k]);
     }
 #pragma unroll
     for (int k = 0; k < RFX_MARCH_BATCH; k++) {
       if (!hit && i + k < a.steps) {
-        const float z = c.getViewZ(dep[k]);
-        const float diff = z - pos[k].z;
+        const float diff = vzs[k] - pos[k].z;
         hitPos = pos[k];
         uv = uvs[k];
         if (diff >= 0.0f && diff < a.thickness) hit = true;
@@ -170,13 +226,12 @@ RFX_D v2 rayMarch(const SsgiArgs& a, const SsgiCtx& c, v3& dir, v3& hitPos, int 
   dir = dir * 0.5f;
   hitPos = hitPos - dir;
   for (int r = 0; r < a.refine_steps; r++) {
-    v2 u = c.viewSpaceToScreenSpace(hitPos);
-    const float z = c.getViewZ(tex_r32f_nearest(a.depth, u));
-    const float diff = z - hitPos.z;
+    const v2 u = view_to_screen<SPARSE>(a, hitPos);
+    const float diff = tex_r32f_nearest(a.viewz, u) - hitPos.z;
     dir = dir * 0.5f;
     if (diff >= 0.0f) hitPos = hitPos - dir; else hitPos = hitPos + dir;
   }
-  return c.viewSpaceToScreenSpace(hitPos);
+  return view_to_screen<SPARSE>(a, hitPos);
 }
 
 struct PixelMat {
@@ -185,11 +240,12 @@ struct PixelMat {
 };
 
 // doSample  ssgi.frag:362-439
-RFX_D v3 doSample(const SsgiArgs& a, const SsgiCtx& c, const PixelMat& m, v3 viewPos, v3 viewNormal, float roughnessSq, bool isDiffuseSample,
-                  bool isEnvSample, float NoV, float NoL, float NoH, float LoH, int noiseB, v3& l, v3& hitPos, float& brdf, float& pdf) {
+template <bool SPARSE, bool FAST>
+RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNormal, float roughnessSq, bool isDiffuseSample, bool isEnvSample,
+                  float NoV, float NoL, float NoH, float LoH, int noiseB, v3& l, v3& hitPos, float& brdf, float& pdf) {
   const float cosTheta = fmaxf(0.0f, dot(viewNormal, l));
   if (isDiffuseSample) {
-    brdf = evalDisneyDiffuse(NoL, NoV, LoH, roughnessSq, m.metalness);
+    brdf = evalDisneyDiffuse<FAST>(NoL, NoV, LoH, roughnessSq, m.metalness);
     pdf = NoL / PI_F;
   } else {
     brdf = evalDisneySpecular(roughnessSq, NoH, NoV, NoL);
@@ -199,11 +255,11 @@ RFX_D v3 doSample(const SsgiArgs& a, const SsgiCtx& c, const PixelMat& m, v3 vie
   pdf = fmaxf(SSGI_EPSILON, pdf);
   hitPos = viewPos;
   bool hit;
-  const v2 coords = rayMarch(a, c, l, hitPos, noiseB, hit);
+  const v2 coords = rayMarch<SPARSE>(a, l, hitPos, noiseB, hit);
   const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
   if (!hit && !allowMissedRays) return getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v2 vel = mk2(0.0f, 0.0f);
-  if (a.velocity.p) { float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }  // :400 (null sampler => 0)
+  if (a.velocity.p) { const float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }  // :400 (null sampler => 0)
   const v2 ruv = coords - vel;
   const v3 envColor = getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v3 SSGI;
@@ -226,12 +282,11 @@ RFX_D v3 doSample(const SsgiArgs& a, const SsgiCtx& c, const PixelMat& m, v3 vie
   return SSGI;
 }
 
-template <int MODE, bool IS>
+template <int MODE, bool IS, bool SPARSE, bool FAST>
 __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
   int x, y;
   block_pixel(x, y, a.row0 & ~1);
   const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
-  const SsgiCtx c(a);
   const uchar4 bn = __ldg(a.blue.tex + ((y + a.blue.shift.sy) % a.blue.size) * a.blue.size + ((x + a.blue.shift.sx) % a.blue.size));
   const v4 random = mk4((float)bn.x / 255.0f, (float)bn.y / 255.0f, (float)bn.z / 255.0f, (float)bn.w / 255.0f);
 
@@ -239,7 +294,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
   v2 cdfUv = mk2(0.0f, 0.0f);
   float lambda = 0.0f;
   if (IS) {
-    const float v = ld_r32f(a.env.marginal, nearest_i(random.x, a.env.marginal.w), 0);                                     // ssgi_utils.frag:212
+    const float v = ld_r32f(a.env.marginal, nearest_i(random.x, a.env.marginal.w), 0);                                        // ssgi_utils.frag:212
     const float u = ld_r32f(a.env.conditional, nearest_i(random.y, a.env.conditional.w), nearest_i(v, a.env.conditional.h));  // :213
     cdfUv = mk2(u, v);
     const unsigned full = 0xffffffffu;
@@ -248,7 +303,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
     const v2 sz = mk2(a.env.size_x, a.env.size_y);
     const v2 ddx = (ux - cdfUv) * sz, ddy = (uy - cdfUv) * sz;
     const float rho = fmaxf(length(ddx), length(ddy));
-    lambda = rho > 0.0f ? log2f(rho) : -1000.0f;
+    lambda = rho > 0.0f ? (FAST ? lg2a_(rho) : log2f(rho)) : -1000.0f;
   }
   if (!active) return;
 
@@ -268,7 +323,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
   m.metalness = gb_metalness(g.z);
   const float roughnessSq = clampf(m.roughness * m.roughness, 0.000001f, 1.0f);
 
-  const float viewZ = c.getViewZ(unpackedDepth);
+  const float viewZ = ssgi_view_z(a, unpackedDepth);
   // getViewPosition  ssgi_utils.frag:17-24
   v3 viewPos;
   {
@@ -302,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
 
   bool isDiffuseSample = false;
   if (MODE == RFX_MODE_SSGI) {
-    const v3 F = f0 + (mk3(1.0f) - f0) * powf(1.0f - VoH, 5.0f);
+    const v3 F = f0 + (mk3(1.0f) - f0) * pow5<FAST>(1.0f - VoH);
     float diffW = (1.0f - m.metalness) * lum_s(m.diffuse);
     float specW = lum_s(F);
     diffW = fmaxf(diffW, SSGI_EPSILON);
@@ -316,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
   bool emsIsEnvSample = false;
   v3 envMisDir = mk3(0.0f);
   if (IS) {  // ssgi.frag:197-215, ssgi_utils.frag:210-225
-    envMisDir = equirectUvToDirection(cdfUv);
+    envMisDir = equirectUvToDirection<FAST>(cdfUv);
     const v3 color = env_trilinear(a.env, cdfUv, lambda);
     const float totalSum = a.env.total_sum_whole + a.env.total_sum_decimal;
     const float pdf0 = lum_s(color) / totalSum;
@@ -343,7 +398,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
   if (MODE == RFX_MODE_SSGI && isDiffuseSample) {  // :222-242
     l = diffuseRay;
     calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
-    v3 gi = doSample(a, c, m, viewPos, viewNormal, roughnessSq, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    v3 gi = doSample<SPARSE, FAST>(a, m, viewPos, viewNormal, roughnessSq, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * (aa / (aa + bb)); } else gi = gi / pdf;
     gi = gi / emsPdf;
@@ -353,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
   l = specularRay;  // :246-265
   calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
   {
-    v3 gi = doSample(a, c, m, viewPos, viewNormal, roughnessSq, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    v3 gi = doSample<SPARSE, FAST>(a, m, viewPos, viewNormal, roughnessSq, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * (aa / (aa + bb)); } else gi = gi / pdf;
     gi = gi / emsPdf;
@@ -381,14 +436,23 @@ __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ 
   }
 }
 
+template <int MODE, bool IS>
+static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
+  if (a.proj_sparse) {
+    if (a.fast) ssgi_kernel<MODE, IS, true, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, true, false><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (a.fast) ssgi_kernel<MODE, IS, false, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, false, false><<<grid, kThreads, 0, s>>>(a);
+  }
+}
+
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {
   const int rb = a.row0 & ~1;
   dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
   const bool is = (a.flags & RFX_SSGI_IMPORTANCE_SAMPLING) != 0;
   if (a.mode == RFX_MODE_SSGI) {
-    if (is) ssgi_kernel<RFX_MODE_SSGI, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<RFX_MODE_SSGI, false><<<grid, kThreads, 0, s>>>(a);
+    if (is) launch_ssgi_t<RFX_MODE_SSGI, true>(a, grid, s); else launch_ssgi_t<RFX_MODE_SSGI, false>(a, grid, s);
   } else {
-    if (is) ssgi_kernel<RFX_MODE_SSR, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<RFX_MODE_SSR, false><<<grid, kThreads, 0, s>>>(a);
+    if (is) launch_ssgi_t<RFX_MODE_SSR, true>(a, grid, s); else launch_ssgi_t<RFX_MODE_SSR, false>(a, grid, s);
   }
   return cudaGetLastError();
 }

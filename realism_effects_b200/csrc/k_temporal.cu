@@ -3,9 +3,19 @@
 // Replaces the fullscreen draw of reference src/temporal-reproject/TemporalReprojectPass.js:192-193
 // (shader src/temporal-reproject/shader/temporal_reproject.frag:178-208 + reproject.frag).
 // Used with 2 planes (SSGI: diffuse + specular, packed fp16x8 input) and with 1 plane (TRAA).
+//
+// Structure vs the shader: the two per-plane neighbourhood-AABB loops (reproject.frag:53-81) read the
+// same packed texels, so they are merged into ONE 5x5 sweep that unpacks each texel once and feeds both
+// planes' min/max (the specular plane only inside its 3x3 / 5x5 radius) — same values, half the loads.
+// FAST = true moves log/exp/pow to the SFU pipe (lg2/ex2.approx).
 #include "rfx_kernels.h"
 
 namespace rfx {
+
+RFX_D float t_lg2a(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D float t_ex2a(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define T_LN2 0.69314718055994530942f
+#define T_LOG2E 1.44269504088896340736f
 
 struct TState {  // the shader's invocation globals (reproject.frag:3-7)
   v2 vUv, velocity;
@@ -14,39 +24,53 @@ struct TState {  // the shader's invocation globals (reproject.frag:3-7)
 };
 
 RFX_D v3 screenSpaceToWorldSpace(v2 uv, float depth, const M4& world, const M4& projInv) {  // reproject.frag:21-28
-  v4 ndc = mk4((uv.x - 0.5f) * 2.0f, (uv.y - 0.5f) * 2.0f, (depth - 0.5f) * 2.0f, 1.0f);
-  v4 clip = mul(projInv, ndc);
-  v4 view = mul(world, mk4(clip.x / clip.w, clip.y / clip.w, clip.z / clip.w, clip.w / clip.w));
+  const v4 ndc = mk4((uv.x - 0.5f) * 2.0f, (uv.y - 0.5f) * 2.0f, (depth - 0.5f) * 2.0f, 1.0f);
+  const v4 clip = mul(projInv, ndc);
+  const v4 view = mul(world, clip / clip.w);
   return xyz(view);
 }
 
-template <bool LOG>
-RFX_D v3 transformColor(v3 c) { return LOG ? vlog1p_(c) : c; }
-template <bool LOG>
-RFX_D v3 undoColorTransform(v3 c) { return LOG ? vexpm1_(c) : c; }
+template <bool LOG, bool FAST>
+RFX_D v3 transformColor(v3 c) {  // reproject.frag:42
+  if (!LOG) return c;
+  if (FAST) return mk3(t_lg2a(c.x + 1.0f) * T_LN2, t_lg2a(c.y + 1.0f) * T_LN2, t_lg2a(c.z + 1.0f) * T_LN2);
+  return vlog1p_(c);
+}
+template <bool LOG, bool FAST>
+RFX_D v3 undoColorTransform(v3 c) {  // :43
+  if (!LOG) return c;
+  if (FAST) return mk3(t_ex2a(c.x * T_LOG2E) - 1.0f, t_ex2a(c.y * T_LOG2E) - 1.0f, t_ex2a(c.z * T_LOG2E) - 1.0f);
+  return vexpm1_(c);
+}
+template <bool FAST>
+RFX_D float tpow(float x, float p) { return FAST ? t_ex2a(p * t_lg2a(x)) : powf(x, p); }
 
 RFX_D float getViewZ(const TemporalArgs& a, float d) {
   return a.cam.perspective ? perspectiveDepthToViewZ(d, a.cam.near_plane, a.cam.far_plane) : orthographicDepthToViewZ(d, a.cam.near_plane, a.cam.far_plane);
 }
 
 // validateReprojectedUV  reproject.frag:130-167
-RFX_D float validateReprojectedUV(const TemporalArgs& a, const TState& s, v2 ruv) {
+template <bool FAST>
+RFX_D float validateReprojectedUV(const TemporalArgs& a, const TState& s, v2 ruv, float distFactor) {
   if (ruv.x > 1.0f || ruv.x < 0.0f || ruv.y > 1.0f || ruv.y < 0.0f) return 0.0f;
   const float4 t = tex_f4_nearest(a.velocity, ruv);
   const v3 lastWorldNormal = unpackNormal(t.z);
   const float lastDepth = t.w;
   const v3 lastWorldPos = screenSpaceToWorldSpace(ruv, lastDepth, a.prev_world, a.prev_proj_inv);
   // (lastViewAngle / angleMix are computed by the shader but never used)
-  const float viewZ = fabsf(getViewZ(a, s.depth));
-  const float distFactor = 1.0f + 1.0f / (viewZ + 1.0f);
   const v3 dpos = s.worldPos - lastWorldPos;
   float disoccl = 0.0f;
-  disoccl += length(dpos) / 10.0f * distFactor;
-  disoccl += fabsf(dot(dpos, s.worldNormal)) / 20.0f * distFactor;
+  if (FAST) {
+    disoccl += length(dpos) * 0.1f * distFactor;
+    disoccl += fabsf(dot(dpos, s.worldNormal)) * 0.05f * distFactor;
+  } else {
+    disoccl += length(dpos) / 10.0f * distFactor;
+    disoccl += fabsf(dot(dpos, s.worldNormal)) / 20.0f * distFactor;
+  }
   disoccl += fminf(1.0f - dot(s.worldNormal, lastWorldNormal), 1.0f) / 1.0f * distFactor;
   float confidence = 1.0f - fminf(disoccl, 1.0f);
   confidence = fmaxf(confidence, 0.0f);
-  return powf(confidence, a.confidence_power);
+  return tpow<FAST>(confidence, a.confidence_power);
 }
 
 // reprojectHitPoint  reproject.frag:169-193
@@ -56,7 +80,8 @@ RFX_D v2 reprojectHitPoint(const TemporalArgs& a, const TState& s) {
   const v3 cameraRay = normalize(s.worldPos - cameraPos);
   const v3 hit = cameraPos + cameraRay * s.rayLength;
   const v4 rh = mul(a.prev_proj_view, mk4(hit, 1.0f));
-  return mk2(rh.x / rh.w * 0.5f + 0.5f, rh.y / rh.w * 0.5f + 0.5f);
+  const v2 q = mk2(rh.x, rh.y) / rh.w;
+  return mk2(q.x * 0.5f + 0.5f, q.y * 0.5f + 0.5f);
 }
 
 template <bool HLIN>
@@ -89,7 +114,7 @@ RFX_D v4 catmull5(const TemporalArgs& a, const PV& tex, v2 P) {
   return r;
 }
 
-template <int TC, int ITYPE, bool LOG, bool HLIN>
+template <int TC, int ITYPE, bool LOG, bool HLIN, bool FAST>
 __global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constant__ TemporalArgs a) {
   int x, y;
   block_pixel(x, y, a.row0 & ~1);
@@ -122,84 +147,95 @@ __global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constan
 #pragma unroll
   for (int i = 0; i < NIN; i++) {
     sampled[i] = inp[i].x >= 0.0f;
-    v3 c = transformColor<LOG>(vmax(xyz(inp[i]), mk3(0.0f)));
+    const v3 c = transformColor<LOG, FAST>(vmax(xyz(inp[i]), mk3(0.0f)));
     inp[i] = mk4(c, inp[i].w);
   }
   if (ITYPE != RFX_INPUT_DIFFUSE) {
     if (s.depth == 1.0f && fwd == 0.0f) return;  // discard :188-193
   }
-  // computeGVariables :147-153
+  // computeGVariables :147-153 (viewDir / viewAngle only feed the unused angleMix)
   s.worldPos = screenSpaceToWorldSpace(s.vUv, s.depth, a.cam.camera_matrix_world, a.cam.projection_inverse);
-  {
-    const v3 viewPos = xyz(mul(a.cam.view_matrix, mk4(s.worldPos, 1.0f)));
-    const v3 viewDir = normalize(viewPos);
-    const v3 viewNormal = mul_dir_left(s.worldNormal, a.cam.view_matrix);
-    s.viewAngle = dot(-viewDir, viewNormal);
-  }
   // getRoughnessRayLength :167-176
   if (ITYPE == RFX_INPUT_DIFFUSE_SPECULAR) {
     s.rayLength = inp[1].w;
     s.roughness = clampf(inp[0].w, 0.0f, 1.0f);
   } else if (ITYPE == RFX_INPUT_SPECULAR) {
-    v2 d = unpackHalf2x16(__float_as_uint(inp[0].w));
+    const v2 d = unpackHalf2x16(__float_as_uint(inp[0].w));
     s.rayLength = d.x;
     s.roughness = clampf(d.y, 0.0f, 1.0f);
   }
   // computeReprojectedUv :155-165
   v3 ruvD, ruvS;
   {
-    v2 r = s.vUv - s.velocity;
-    ruvD = mk3(r.x, r.y, validateReprojectedUV(a, s, r));
+    const float viewZ = fabsf(getViewZ(a, s.depth));
+    const float distFactor = 1.0f + 1.0f / (viewZ + 1.0f);
+    const v2 r = s.vUv - s.velocity;
+    ruvD = mk3(r.x, r.y, validateReprojectedUV<FAST>(a, s, r, distFactor));
     ruvS = mk3(-1.0f);
     if (ITYPE != RFX_INPUT_DIFFUSE) {
-      v2 h = reprojectHitPoint(a, s);
-      ruvS = mk3(h.x, h.y, validateReprojectedUV(a, s, h));
+      const v2 h = reprojectHitPoint(a, s);
+      ruvS = mk3(h.x, h.y, validateReprojectedUV<FAST>(a, s, h, distFactor));
       if (ruvS.x == -1.0f) ruvS = ruvD;
     }
   }
   s.moveFactor = fminf(dot(s.velocity, s.velocity) * 10000.0f, 1.0f);
 
   const int rs[2] = {a.rs0, a.rs1};
+  // ---- neighbourhood AABBs (clampNeighborhood / getNeighborhoodAABB, reproject.frag:53-95), one merged sweep
+  v3 mn[2], mx[2];
+  int radius[2];
+  bool need_sweep = false;
+#pragma unroll
+  for (int i = 0; i < TC; i++) {
+    const v3 inLin = undoColorTransform<LOG, FAST>(xyz(inp[i]));
+    mn[i] = inLin; mx[i] = inLin;
+    radius[i] = (rs[i] != 0 && s.roughness < 0.25f) ? 1 : 2;
+    need_sweep = need_sweep || sampled[i];
+  }
+  if (need_sweep) {
+    if (ITYPE == RFX_INPUT_DIFFUSE_SPECULAR) {
+      // neighborUv = vUv + (dx,dy)*invTexSize lands on texel (x+dx, y+dy) (clamped): direct addressing, each texel unpacked once
+      for (int dy = -2; dy <= 2; dy++) {
+        const int ty = clampi(y + dy, a.H);
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx++) {
+          const int tx = clampi(x + dx, a.W);
+          v4 t[2];
+          unpackTwoVec4(ld_f4(a.input, tx, ty), t[0], t[1]);
+#pragma unroll
+          for (int i = 0; i < TC; i++) {
+            const v4 nt = rs[i] != 0 ? t[1] : t[0];
+            const bool inside = abs(dx) <= radius[i] && abs(dy) <= radius[i];
+            if (inside && nt.x >= 0.0f) { mn[i] = vmin(xyz(nt), mn[i]); mx[i] = vmax(xyz(nt), mx[i]); }
+          }
+        }
+      }
+    } else {
+      for (int dx = -radius[0]; dx <= radius[0]; dx++)
+        for (int dy = -radius[0]; dy <= radius[0]; dy++) {
+          const v2 nuv = mk2(s.vUv.x + (float)dx * a.inv_w, s.vUv.y + (float)dy * a.inv_h);
+          const v4 nt = a.input_half ? tex_h4_linear(a.input, nuv) : f4v(tex_f4_nearest(a.input, nuv));
+          if (nt.x >= 0.0f) { mn[0] = vmin(xyz(nt), mn[0]); mx[0] = vmax(xyz(nt), mx[0]); }
+        }
+    }
+  }
+
 #pragma unroll
   for (int i = 0; i < TC; i++) {
     const bool spec = rs[i] != 0;
     const v3 uvc = spec ? ruvS : ruvD;
     const PV& hist = i == 0 ? a.hist0 : a.hist1;
     // reproject()  temporal_reproject.frag:83-122
-    v4 acc = catmull5<HLIN>(a, hist, mk2(uvc.x, uvc.y));
-    v3 accRgb = transformColor<LOG>(xyz(acc));
+    const v4 acc = catmull5<HLIN>(a, hist, mk2(uvc.x, uvc.y));
+    v3 accRgb = transformColor<LOG, FAST>(xyz(acc));
     float accA = acc.w;
     v3 inRgb = xyz(inp[i]);
     if (!sampled[i]) {
       inRgb = accRgb;
     } else {
       accA += 1.0f;
-      const int clampRadius = (spec && s.roughness < 0.25f) ? 1 : 2;
-      // clampNeighborhood  reproject.frag:53-95
-      v3 inLin = undoColorTransform<LOG>(inRgb);
-      v3 mn = inLin, mx = inLin;
-      for (int dx = -clampRadius; dx <= clampRadius; dx++) {
-        for (int dy = -clampRadius; dy <= clampRadius; dy++) {
-          const v2 nuv = mk2(s.vUv.x + (float)dx * a.inv_w, s.vUv.y + (float)dy * a.inv_h);
-          v4 nt;
-          if (ITYPE == RFX_INPUT_DIFFUSE_SPECULAR) {
-            v4 t1, t2;
-            unpackTwoVec4(tex_f4_nearest(a.input, nuv), t1, t2);
-            nt = spec ? t2 : t1;
-          } else if (a.input_half) {
-            nt = tex_h4_linear(a.input, nuv);
-          } else {
-            nt = f4v(tex_f4_nearest(a.input, nuv));
-          }
-          if (nt.x >= 0.0f) {
-            mn = vmin(xyz(nt), mn);
-            mx = vmax(xyz(nt), mx);
-          }
-        }
-      }
-      mn = transformColor<LOG>(mn);
-      mx = transformColor<LOG>(mx);
-      const v3 clamped = mk3(clampf(accRgb.x, mn.x, mx.x), clampf(accRgb.y, mn.y, mx.y), clampf(accRgb.z, mn.z, mx.z));
+      const v3 lo = transformColor<LOG, FAST>(mn[i]), hi = transformColor<LOG, FAST>(mx[i]);
+      const v3 clamped = mk3(clampf(accRgb.x, lo.x, hi.x), clampf(accRgb.y, lo.y, hi.y), clampf(accRgb.z, lo.z, hi.z));
       const float r = spec ? s.roughness : 1.0f;
       const float clampAggressiveness = fminf(1.0f, uvc.z * r);
       const float clampIntensity = mixf(0.0f, fminf(1.0f, s.moveFactor * 50.0f + a.clamp_intensity), clampAggressiveness);
@@ -209,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constan
       accRgb = newColor;
     }
     // accumulate()  temporal_reproject.frag:42-79
-    const float confidence = powf(uvc.z, a.confidence_power);
+    const float confidence = tpow<FAST>(uvc.z, a.confidence_power);
     float accumBlend = 1.0f - 1.0f / (accA + 1.0f);
     accumBlend = mixf(0.0f, accumBlend, confidence);
     float maxValue = (a.full_accumulate ? 1.0f : a.max_blend) * a.keep_data;
@@ -222,21 +258,28 @@ __global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constan
     const float tmix = fminf(accumBlend, maxValue);
     float oa = 1.0f / (1.0f - tmix) - 1.0f;
     oa = fminf(65536.0f, oa);
-    const v3 orgb = undoColorTransform<LOG>(mix(inRgb, accRgb, tmix));
+    const v3 orgb = undoColorTransform<LOG, FAST>(mix(inRgb, accRgb, tmix));
     const OutV& o = i == 0 ? a.out0 : a.out1;
     if (a.out_half) st_h4(o.p, o.pitch, x, y, mk4(orgb, oa));
     else st_f4(o.p, o.pitch, x, y, make_float4(orgb.x, orgb.y, orgb.z, oa));
   }
 }
 
+template <int TC, int IT, bool FAST>
+static void launch_temporal_t(const TemporalArgs& a, dim3 grid, cudaStream_t s) {
+  if (a.log_transform) {
+    if (a.history_linear) temporal_kernel<TC, IT, true, true, FAST><<<grid, kThreads, 0, s>>>(a);
+    else temporal_kernel<TC, IT, true, false, FAST><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (a.history_linear) temporal_kernel<TC, IT, false, true, FAST><<<grid, kThreads, 0, s>>>(a);
+    else temporal_kernel<TC, IT, false, false, FAST><<<grid, kThreads, 0, s>>>(a);
+  }
+}
+
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t s) {
   const int rb = a.row0 & ~1;
   dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
-#define RFX_LT(TC, IT) \
-  do { if (a.log_transform) { if (a.history_linear) temporal_kernel<TC, IT, true, true><<<grid, kThreads, 0, s>>>(a); \
-                              else temporal_kernel<TC, IT, true, false><<<grid, kThreads, 0, s>>>(a); } \
-       else { if (a.history_linear) temporal_kernel<TC, IT, false, true><<<grid, kThreads, 0, s>>>(a); \
-              else temporal_kernel<TC, IT, false, false><<<grid, kThreads, 0, s>>>(a); } } while (0)
+#define RFX_LT(TC, IT) do { if (a.fast) launch_temporal_t<TC, IT, true>(a, grid, s); else launch_temporal_t<TC, IT, false>(a, grid, s); } while (0)
   if (a.input_type == RFX_INPUT_DIFFUSE_SPECULAR && a.texture_count == 2) RFX_LT(2, RFX_INPUT_DIFFUSE_SPECULAR);
   else if (a.input_type == RFX_INPUT_DIFFUSE && a.texture_count == 1) RFX_LT(1, RFX_INPUT_DIFFUSE);
   else if (a.input_type == RFX_INPUT_SPECULAR && a.texture_count == 1) RFX_LT(1, RFX_INPUT_SPECULAR);

@@ -32,6 +32,17 @@ struct rfx_ctx {
   bool env_set = false;
   EnvD env{};
   std::vector<void*> env_allocs;
+  // fast-math kernel variants (SFU lg2/ex2 instead of libm polynomials); 0 selects the exact-libm variants
+  int fast_math = 1;
+  // scratch: decoded G-buffer (float4 normal.xyz + roughness) for the fast Poisson kernel
+  void* nrd = nullptr;
+  int nrd_w = 0, nrd_h = 0;
+  size_t nrd_pitch = 0;
+  bool nrd_reuse = false;  // set by the native chain: the scratch already holds this frame's decode
+  // scratch: view-space z plane for the SSGI march
+  void* viewz = nullptr;
+  int viewz_w = 0, viewz_h = 0;
+  size_t viewz_pitch = 0;
 };
 
 static rfx_status fail(rfx_ctx* c, rfx_status st, const char* fmt, ...) {
@@ -102,8 +113,15 @@ void rfx_ctx_destroy(rfx_ctx* ctx) {
   cudaFree(ctx->blue);
   cudaFree(ctx->rot_table);
   cudaFree(ctx->step_table);
+  cudaFree(ctx->nrd);
+  cudaFree(ctx->viewz);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+rfx_status rfx_ctx_set_fast_math(rfx_ctx* ctx, int32_t enable) {
+  if (!ctx) return RFX_ERR_INVALID_ARG;
+  ctx->fast_math = enable ? 1 : 0;
+  return RFX_OK;
 }
 const char* rfx_last_error(const rfx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void* rfx_ctx_stream(rfx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -355,6 +373,23 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
   if (st != RFX_OK) return st;
   a.rot_table = ctx->rot_table;
   a.step_table = ctx->step_table;
+  a.fast = ctx->fast_math;
+  {  // perspective sparsity pattern: [P00 0 P20 0; 0 P11 P21 0; 0 0 P22 P32; 0 0 -1 0] (column-major m[col*4+row])
+    const float* M = p->cam.projection;
+    a.proj_sparse = M[1] == 0.0f && M[2] == 0.0f && M[3] == 0.0f && M[4] == 0.0f && M[6] == 0.0f && M[7] == 0.0f && M[11] == -1.0f &&
+                    M[12] == 0.0f && M[13] == 0.0f && M[15] == 0.0f;
+  }
+  // view-space z plane (scratch): the march taps read it instead of converting depth -> viewZ per tap
+  if (!ctx->viewz || ctx->viewz_w != a.W || ctx->viewz_h != a.H) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->viewz);
+    ctx->viewz = nullptr;
+    ctx->viewz_pitch = ((size_t)a.W * 4 + 255) & ~(size_t)255;
+    CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * a.H));
+    ctx->viewz_w = a.W; ctx->viewz_h = a.H;
+  }
+  LAUNCHED(launch_viewz(a, OutV{(unsigned char*)ctx->viewz, (long long)ctx->viewz_pitch}, pick(ctx, stream)));
+  a.viewz = PV{(const unsigned char*)ctx->viewz, a.W, a.H, (long long)ctx->viewz_pitch};
   LAUNCHED(launch_ssgi(a, pick(ctx, stream)));
   return RFX_OK;
 }
@@ -391,6 +426,7 @@ rfx_status rfx_temporal_reproject_launch(rfx_ctx* ctx, void* stream, const rfx_t
   a.inv_h = (float)(1.0 / (double)a.H);
   a.full_accumulate = p->full_accumulate; a.texture_count = p->texture_count; a.input_type = p->input_type; a.log_transform = p->log_transform;
   a.rs0 = p->reproject_specular[0]; a.rs1 = p->reproject_specular[1]; a.history_linear = p->history_linear;
+  a.fast = ctx->fast_math;
   LAUNCHED(launch_temporal(a, pick(ctx, stream)));
   return RFX_OK;
 }
@@ -424,7 +460,30 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
   if (st != RFX_OK) return st;
   if (p->blue_noise_index == 0) return fail(ctx, RFX_ERR_UNSUPPORTED, "poisson: blue_noise_index 0 is not used by this pass");
   a.rot_table = ctx->rot_table;
-  LAUNCHED(launch_poisson(a, pick(ctx, stream)));
+  const bool fast = ctx->fast_math && p->gbuffer_texture && ((p->input_linear && a.in_half) || (!p->input_linear && !a.in_half));
+  if (!fast) {
+    LAUNCHED(launch_poisson(a, pick(ctx, stream)));
+    return RFX_OK;
+  }
+  // fast variant: decode the G-buffer once into the context scratch (the native chain reuses it across the passes of a frame)
+  if (!ctx->nrd || ctx->nrd_w != a.W || ctx->nrd_h != a.H) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->nrd);
+    ctx->nrd = nullptr;
+    ctx->nrd_pitch = ((size_t)a.W * 16 + 255) & ~(size_t)255;
+    CU(cudaMalloc(&ctx->nrd, ctx->nrd_pitch * a.H));
+    ctx->nrd_w = a.W; ctx->nrd_h = a.H;
+    ctx->nrd_reuse = false;
+  }
+  if (!ctx->nrd_reuse) LAUNCHED(launch_gbuffer_decode(a.gb, OutV{(unsigned char*)ctx->nrd, (long long)ctx->nrd_pitch}, a.W, a.H, 1, pick(ctx, stream)));
+  a.nrd = PV{(const unsigned char*)ctx->nrd, a.W, a.H, (long long)ctx->nrd_pitch};
+  {
+    const float SQ = 1.41421356237f;
+    const float px[8] = {-1.0f, 0.0f, 1.0f, 0.0f, -0.25f * SQ, 0.25f * SQ, 0.25f * SQ, -0.25f * SQ};
+    const float py[8] = {0.0f, -1.0f, 0.0f, 1.0f, -0.25f * SQ, -0.25f * SQ, 0.25f * SQ, 0.25f * SQ};
+    for (int i = 0; i < 8; i++) { a.tap_ox[i] = px[i] / (float)a.W; a.tap_oy[i] = py[i] / (float)a.H; }  // offset / resolution
+  }
+  LAUNCHED(launch_poisson_fast(a, pick(ctx, stream)));
   return RFX_OK;
 }
 
@@ -691,10 +750,12 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
     rfx_plane* outp = horizontal ? ch->dnA : ch->dnB;
     pp.input_linear = i == 0 ? 0 : 1;
     pp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_poisson);
+    ctx->nrd_reuse = i > 0;  // the G-buffer does not change within a frame: decode it once (pass 0), reuse it afterwards
     { SpanGuard g(ch, cs, i == 0 ? 2 : 3);
       st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, 0, 0); }
     if (st != RFX_OK) return st;
   }
+  ctx->nrd_reuse = false;
   // ---- K4  DenoiserComposePass.render
   if (o.mode == RFX_MODE_SSGI) {
     rfx_compose_params cp{};

@@ -42,9 +42,15 @@ RFX_D v3 xyz(v4 a) { return mk3(a.x, a.y, a.z); }
 #define RFX_OP4(op)                                                                              \
   RFX_D v4 operator op(v4 a, v4 b) { return mk4(a.x op b.x, a.y op b.y, a.z op b.z, a.w op b.w); } \
   RFX_D v4 operator op(v4 a, float s) { return mk4(a.x op s, a.y op s, a.z op s, a.w op s); }
-RFX_OP2(+) RFX_OP2(-) RFX_OP2(*) RFX_OP2(/)
-RFX_OP3(+) RFX_OP3(-) RFX_OP3(*) RFX_OP3(/)
-RFX_OP4(+) RFX_OP4(-) RFX_OP4(*) RFX_OP4(/)
+RFX_OP2(+) RFX_OP2(-) RFX_OP2(*)
+RFX_OP3(+) RFX_OP3(-) RFX_OP3(*)
+RFX_OP4(+) RFX_OP4(-) RFX_OP4(*)
+// division: vector / vector is component-wise IEEE; vector / SCALAR = one IEEE reciprocal + multiplies (oracle/glsl.h rule)
+RFX_D v2 operator/(v2 a, v2 b) { return mk2(a.x / b.x, a.y / b.y); }
+RFX_D v3 operator/(v3 a, v3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+RFX_D v2 operator/(v2 a, float s) { const float r = 1.0f / s; return mk2(a.x * r, a.y * r); }
+RFX_D v3 operator/(v3 a, float s) { const float r = 1.0f / s; return mk3(a.x * r, a.y * r, a.z * r); }
+RFX_D v4 operator/(v4 a, float s) { const float r = 1.0f / s; return mk4(a.x * r, a.y * r, a.z * r, a.w * r); }
 RFX_D v3 operator-(v3 a) { return mk3(-a.x, -a.y, -a.z); }
 
 RFX_D float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }

@@ -40,8 +40,13 @@ struct PoissonArgs {
   int texture_count, spec0, spec1, gbuffer_texture, input_linear, in_half;
   BlueD blue;
   const float2* rot_table;  // [256] (sin, cos) of (k/255)*2*pi, correctly rounded
+  // fast variant only:
+  PV nrd;                       // float4 (normal.xyz, roughness) from the decode prepass
+  float tap_ox[8], tap_oy[8];   // POISSON[i] / resolution
 };
-cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s);
+cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s);       // exact-libm variant (any configuration)
+cudaError_t launch_poisson_fast(const PoissonArgs& a, cudaStream_t s);  // SFU variant (GBUFFER_TEXTURE configurations)
+cudaError_t launch_gbuffer_decode(PV gb, OutV nrd, int W, int H, int gbuffer_texture, cudaStream_t s);
 
 // ---- K4 / K5 -------------------------------------------------------------------------------
 struct ComposeArgs {
@@ -73,6 +78,7 @@ struct TemporalArgs {
   float inv_w, inv_h;  // invTexSize
   int full_accumulate, texture_count, input_type, log_transform, rs0, rs1, history_linear;
   int input_half, out_half;
+  int fast;  // SFU variants of log/exp/pow
 };
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t s);
 
@@ -90,8 +96,12 @@ struct SsgiArgs {
   EnvD env;
   const float2* rot_table;   // [256] (sin, cos)
   const float* step_table;   // [steps][256]  cs(i, b) = 1 - exp(-0.25 (i + b - 0.5)^2), row i-1 for step i
+  PV viewz;                  // R32F: getViewZ(depth) per texel (launch_viewz prepass)
+  int proj_sparse;           // projection matrix has the perspective sparsity pattern (exact-zero terms dropped)
+  int fast;                  // SFU variants of the continuous transcendentals
 };
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);
+cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s);
 
 // ---- K6 / K7 / K8 / K9 -----------------------------------------------------------------------
 struct HbaoArgs {

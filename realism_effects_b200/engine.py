@@ -119,6 +119,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.rfx_launch_count(self.h))
 
+    def set_fast_math(self, enable: bool):
+        """True (default): SFU-pipe kernel variants; False: exact-libm variants (bit-level parity with the oracle)."""
+        self._chk(self.lib.rfx_ctx_set_fast_math(self.h, int(enable)))
+
     def set_blue_noise(self, rgba8: np.ndarray):
         a = np.ascontiguousarray(rgba8, dtype=np.uint8)
         self._chk(self.lib.rfx_blue_noise_set(self.h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0]))

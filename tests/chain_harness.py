@@ -214,10 +214,11 @@ def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0",
     return out
 
 
-def run_cuda_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed")):
+def run_cuda_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"), fast_math: bool = True):
     from realism_effects_b200 import engine
 
     ctx = engine.Context(0, inp.blue)
+    ctx.set_fast_math(fast_math)
     try:
         if o.use_envmap:
             ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
@@ -262,11 +263,11 @@ def compare(a: np.ndarray, b: np.ndarray, packed: bool = False) -> dict:
                 bit_equal=float(((a == b) | (np.isnan(a) & np.isnan(b))).mean()))
 
 
-def run_chain_parity(width=192, height=108, frames=2, max_frac=2e-3, **opt_kw) -> dict:
+def run_chain_parity(width=192, height=108, frames=2, max_frac=2e-3, fast_math=True, **opt_kw) -> dict:
     o = Opts(**opt_kw)
     inp = make_inputs(width, height, frames)
     ref = run_oracle_chain(inp, o)
-    got, launches = run_cuda_chain(inp, o)
+    got, launches = run_cuda_chain(inp, o, fast_math=fast_math)
     worst, lines = 0.0, []
     for t, (r, g) in enumerate(zip(ref, got)):
         for k in ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"):

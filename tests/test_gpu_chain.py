@@ -1,21 +1,37 @@
-"""GPU parity of the whole SSGI chain (K1 -> K2 -> K3 x n -> K4) through the C ABI vs the oracle."""
-import numpy as np
+"""GPU parity of the whole SSGI chain (K1 -> K2 -> K3 x n -> K4) through the C ABI vs the oracle, for both kernel
+variants: fast_math=True (SFU lg2/ex2; the default, what bench.py times) and fast_math=False (exact libm, bit-level)."""
 import pytest
 
 import chain_harness as ch
 
 pytestmark = pytest.mark.gpu
 
-
-@pytest.mark.parametrize("kw", [
+CASES = [
     dict(width=192, height=108, frames=3),
     dict(width=161, height=91, frames=2, denoise_iterations=2),            # odd sizes: helper lanes beyond the edge
     dict(width=128, height=72, frames=2, importance_sampling=False),
     dict(width=128, height=72, frames=2, use_envmap=False, use_direct_light=False, steps=8, refine_steps=0),
     dict(width=128, height=72, frames=2, missed_rays=True),
-])
-def test_chain_parity(built, kw):
-    res = ch.run_chain_parity(**kw)
+]
+
+
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("kw", CASES)
+def test_chain_parity(built, kw, fast):
+    res = ch.run_chain_parity(fast_math=fast, **kw)
     print(res["summary"])
     assert res["ok"], res["summary"]
     assert res["launches"] > 0
+
+
+def test_static_camera_full_accumulate(built):
+    """static camera => fullAccumulate path (TemporalReprojectPass.js:178-180), history length grows every frame"""
+    o = ch.Opts()
+    inp = ch.make_inputs(160, 90, 4, static=True)
+    ref = ch.run_oracle_chain(inp, o)
+    got, _ = ch.run_cuda_chain(inp, o)
+    for t in range(4):
+        for k in ("tr0", "tr1", "composed"):
+            c = ch.compare(ref[t][k], got[t][k])
+            assert c["frac_bad"] <= 2e-3, (t, k, c)
+    assert got[3]["tr0"][..., 3].max() > got[1]["tr0"][..., 3].max()
