@@ -253,13 +253,16 @@ rfx_status rfx_env_set(rfx_ctx* ctx, const rfx_env_desc* e) {
 }  // extern "C"
 
 // ---- helpers ------------------------------------------------------------------------------
+static bool plane_ok(const rfx_plane* p, int fmt) {  // kernels address planes with 32-bit byte offsets
+  return p && p->ptr && p->format == fmt && p->pitch * (uint64_t)p->height < (1ull << 32) && (p->pitch % rfx_format_bytes(fmt)) == 0;
+}
 static bool pv(const rfx_plane* p, int fmt, PV& out) {
-  if (!p || !p->ptr || p->format != fmt) return false;
+  if (!plane_ok(p, fmt)) return false;
   out = PV{(const unsigned char*)p->ptr, (int)p->width, (int)p->height, (long long)p->pitch};
   return true;
 }
 static bool ov(const rfx_plane* p, int fmt, OutV& out) {
-  if (!p || !p->ptr || p->format != fmt) return false;
+  if (!plane_ok(p, fmt)) return false;
   out = OutV{(unsigned char*)p->ptr, (long long)p->pitch};
   return true;
 }

@@ -166,23 +166,25 @@ struct PV {  // device view of an rfx_plane
   long long pitch;
 };
 RFX_D int clampi(int i, int n) { return min(max(i, 0), n - 1); }
-RFX_D float ld_r32f(const PV& t, int x, int y) { return __ldg((const float*)(t.p + (long long)y * t.pitch) + x); }
-RFX_D float4 ld_f4(const PV& t, int x, int y) { return __ldg((const float4*)(t.p + (long long)y * t.pitch) + x); }
+// byte offsets are computed in 32 bits (planes are < 4 GiB; the C ABI rejects larger ones): one IMAD instead of a 64-bit chain
+RFX_D unsigned pv_off(const PV& t, int x, int y, int bytes) { return (unsigned)y * (unsigned)t.pitch + (unsigned)x * (unsigned)bytes; }
+RFX_D float ld_r32f(const PV& t, int x, int y) { return __ldg((const float*)(t.p + pv_off(t, x, y, 4))); }
+RFX_D float4 ld_f4(const PV& t, int x, int y) { return __ldg((const float4*)(t.p + pv_off(t, x, y, 16))); }
 RFX_D v4 half4_to_v4(uint2 u) {
   v2 a = unpackHalf2x16(u.x), b = unpackHalf2x16(u.y);
   return mk4(a.x, a.y, b.x, b.y);
 }
-RFX_D v4 ld_h4(const PV& t, int x, int y) { return half4_to_v4(__ldg((const uint2*)(t.p + (long long)y * t.pitch) + x)); }
+RFX_D v4 ld_h4(const PV& t, int x, int y) { return half4_to_v4(__ldg((const uint2*)(t.p + pv_off(t, x, y, 8)))); }
 RFX_D void st_h4(unsigned char* base, long long pitch, int x, int y, v4 v) {
   uint2 u;
   u.x = packHalf2x16(v.x, v.y);
   u.y = packHalf2x16(v.z, v.w);
-  *((uint2*)(base + (long long)y * pitch) + x) = u;
+  *((uint2*)(base + ((unsigned)y * (unsigned)pitch + (unsigned)x * 8u))) = u;
 }
-RFX_D void st_f4(unsigned char* base, long long pitch, int x, int y, float4 v) { *((float4*)(base + (long long)y * pitch) + x) = v; }
+RFX_D void st_f4(unsigned char* base, long long pitch, int x, int y, float4 v) { *((float4*)(base + ((unsigned)y * (unsigned)pitch + (unsigned)x * 16u))) = v; }
 
-// NEAREST texel index for coordinate u in a texture of n texels (clamp-to-edge)
-RFX_D int nearest_i(float u, int n) { return clampi((int)floorf(u * (float)n), n); }
+// NEAREST texel index for coordinate u in a texture of n texels (clamp-to-edge): floor + convert in one F2I.FLOOR
+RFX_D int nearest_i(float u, int n) { return clampi(__float2int_rd(u * (float)n), n); }
 RFX_D float tex_r32f_nearest(const PV& t, v2 uv) { return ld_r32f(t, nearest_i(uv.x, t.w), nearest_i(uv.y, t.h)); }
 RFX_D float4 tex_f4_nearest(const PV& t, v2 uv) { return ld_f4(t, nearest_i(uv.x, t.w), nearest_i(uv.y, t.h)); }
 RFX_D v4 f4v(float4 a) { return mk4(a.x, a.y, a.z, a.w); }
