@@ -255,8 +255,13 @@ def test_full_size_4k_properties(built):
     assert fg_written.all(), "every non-discarded pixel is written with alpha 1"
     assert np.isfinite(comp[~bg]).all()
     assert (comp[~bg][:, :3] >= -1e-6).all()  # exp(x)-1 of a ~0 log-average may round a hair below 0
-    interior_bg = bg & np.roll(bg, 1, 0) & np.roll(bg, -1, 0) & np.roll(bg, 1, 1) & np.roll(bg, -1, 1)
-    assert (comp[interior_bg] == 0).all()                       # discarded => the zero-initialised target is untouched
+    def interior(b):
+        return b & np.roll(b, 1, 0) & np.roll(b, -1, 0) & np.roll(b, 1, 1) & np.roll(b, -1, 1)
+
+    bg_prev = frames[0].depth.cpu().numpy() == 1.0
+    never_written = interior(bg) & interior(bg_prev)            # discarded in both frames => the zero-initialised target is untouched;
+    assert (comp[never_written] == 0).all()                     # pixels that were foreground last frame keep their stale texel
+    assert never_written.any()
     assert np.allclose(ssgi[bg][:, :4], ssgi[bg][:, 4:], atol=0)  # background = packTwoVec4(directLight, directLight)
     torch.cuda.synchronize()
 
