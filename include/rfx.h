@@ -318,6 +318,9 @@ typedef struct rfx_ssgi_frame {
 rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt, rfx_ssgi_chain** out);
 void rfx_ssgi_chain_destroy(rfx_ssgi_chain* chain);
 rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* chain);
+/* reactive options (SSGIEffect.makeOptionsReactive, src/ssgi/SSGIEffect.js:157-268): replaces every option except
+ * width/height (use a new chain to resize) and resets the temporal history like the reference's setters do. */
+rfx_status rfx_ssgi_chain_set_options(rfx_ssgi_chain* chain, const rfx_ssgi_chain_options* opt);
 rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
 /* which: 0 composed (RGBA32F), 1 ssgiOut, 2/3 trOut[0/1], 4/5 dnB[0/1] */
 rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* chain, int32_t which, rfx_plane* out);

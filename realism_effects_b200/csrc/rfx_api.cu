@@ -678,6 +678,17 @@ rfx_status rfx_ssgi_chain_get_profile(rfx_ssgi_chain* ch, double* ms, uint64_t* 
   return RFX_OK;
 }
 
+rfx_status rfx_ssgi_chain_set_options(rfx_ssgi_chain* ch, const rfx_ssgi_chain_options* opt) {
+  if (!ch || !opt) return RFX_ERR_INVALID_ARG;
+  if (opt->width != ch->opt.width || opt->height != ch->opt.height) return fail(ch->ctx, RFX_ERR_SIZE_MISMATCH, "chain_set_options: size change needs a new chain");
+  if (opt->denoise_iterations < 0 || opt->steps < 1 || opt->refine_steps < 0) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_set_options: bad option value");
+  const int32_t start = ch->opt.blue_noise_start;
+  ch->opt = *opt;
+  ch->opt.blue_noise_start = start;  // the blue-noise closures keep their start index for the life of the material
+  ch->keep_data = 0.0f;              // every reference setter ends with this.reset()
+  return RFX_OK;
+}
+
 rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* ch) {
   if (!ch) return RFX_ERR_INVALID_ARG;
   ch->keep_data = 0.0f;  // TemporalReprojectPass.reset()  :158-160

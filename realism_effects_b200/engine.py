@@ -205,6 +205,10 @@ class SsgiChain:
     def reset(self):
         self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_reset(self.h))
 
+    def set_options(self, opt: abi.ChainOptions):
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_set_options(self.h, C.byref(opt)))
+        self.opt = opt
+
     def render(self, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None):
         f = abi.SsgiFrame()
         f.cam = cam

@@ -1,0 +1,139 @@
+"""GPU tests of the plugin-surface mirror (realism_effects_b200/effects.py): the classes a reference user instantiates
+(SSGIEffect / TRAAEffect / MotionBlurEffect / HBAOEffect / VelocityDepthNormalPass) produce what the oracle produces
+when driven like the reference's frame loop."""
+import numpy as np
+import pytest
+
+import chain_harness as ch
+from realism_effects_b200 import abi, effects, engine, synth
+
+pytestmark = pytest.mark.gpu
+
+
+class Scene:  # what stands in for the rasterised G-buffer / velocity render targets
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.depth = self.gbuffer = self.velocity = None
+
+    def load(self, fr):
+        for p in (self.depth, self.gbuffer, self.velocity):
+            if p is not None:
+                p.free()
+        self.depth, self.gbuffer, self.velocity = self.ctx.upload(fr["depth"]), self.ctx.upload(fr["gbuffer"]), self.ctx.upload(fr["velocity"])
+
+
+class Composer:
+    def __init__(self, ctx, w, h):
+        self.ctx, self.width, self.height = ctx, w, h
+        self.inputBuffer = ctx.alloc(abi.FMT_RGBA16F, w, h)
+        self.outputBuffer = ctx.alloc(abi.FMT_RGBA16F, w, h)
+
+
+class Cam:
+    def __init__(self):
+        self.u = None
+
+    def uniforms(self):
+        return self.u
+
+
+def test_ssgi_effect_matches_oracle_chain(built):
+    import orc
+
+    inp = ch.make_inputs(160, 90, 3)
+    o = ch.Opts()
+    ref = ch.run_oracle_chain(inp, o)
+    ctx = engine.Context(0, inp.blue)
+    try:
+        scene, comp, cam = Scene(ctx), Composer(ctx, 160, 90), Cam()
+        cam.u = inp.frames[0]["cam"]
+        fx = effects.SSGIEffect(comp, scene, cam, {"blueNoiseStart": o.blue_noise_start})
+        assert fx.steps == 20 and fx.refineSteps == 5 and fx.denoiseIterations == 1 and effects.SSGIEffect.DefaultOptions["normalPhi"] == 50
+        fx.setEnvironment(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+        for t, fr in enumerate(inp.frames):
+            scene.load(fr)
+            comp.inputBuffer.upload(fr["direct"])
+            cam.u = fr["cam"]
+            fx.update(None, comp.inputBuffer)
+            got = fx._chain.download(0)
+            c = ch.compare(ref[t]["composed"], got)
+            assert c["frac_bad"] <= 1e-2 and ch.compare(ref[t]["composed"], got, rtol=4e-3)["frac_bad"] <= 2e-3, (t, c)
+            want5 = orc.ssgi_compose(fr["depth"], got, fr["direct"])  # K5 on the engine's own GI plane
+            assert ch.compare(want5, comp.outputBuffer.download())["n_bad"] == 0
+        # reactive option: the setter reconfigures the native chain and resets the history (SSGIEffect.js:203-209)
+        fx.steps = 8
+        assert fx.steps == 8 and fx._chain.opt.steps == 8
+        fx.update(None, comp.inputBuffer)
+        tr_alpha = fx._chain.download(2)[..., 3]
+        assert tr_alpha.max() == 0.0  # keepData = 0 => no accumulated history on the frame after a reset
+        fx.dispose()
+    finally:
+        ctx.close()
+
+
+def test_hbao_effect_traa_effect_motion_blur_effect(built):
+    import orc
+
+    inp = ch.make_inputs(128, 72, 2)
+    f0, f1 = inp.frames
+    W, H = 128, 72
+    ctx = engine.Context(0, inp.blue)
+    try:
+        scene, comp, cam = Scene(ctx), Composer(ctx, W, H), Cam()
+        scene.load(f1)
+        cam.u = f1["cam"]
+        comp.inputBuffer.upload(f1["direct"])
+        # ---- HBAOEffect: K6 -> 2 Poisson passes (1 plane, velocity-layout normals) -> K7
+        hb = effects.HBAOEffect(comp, cam, scene, {"blueNoiseStart": 777})
+        assert hb.spp == 8 and hb.distance == 2 and hb.bias == 40 and hb.power == 2
+        hb.update(None, comp.inputBuffer)
+        bi = effects.BlueNoiseIndex(777)
+        z = np.zeros((H, W, 4), np.float16)
+        ao = orc.hbao(ch.hbao_params(f1["cam"], bi.value), f1["depth"], inp.blue, z)
+        pbi = effects.BlueNoiseIndex(1234567)
+        cur, tgtA, tgtB = ao, z.copy(), z.copy()
+        for i in range(2):
+            p = ch.poisson_params(ch.Opts(), pbi.value, False)
+            p.texture_count, p.gbuffer_texture, p.input_linear = 1, 0, 1
+            p.is_texture_specular[:] = [0, 0]
+            p.normal_phi, p.depth_phi, p.roughness_phi, p.specular_phi = 3.25, 2.0, 0.0, 0.0
+            src = cur if i == 0 else tgtA
+            out, _ = orc.poisson_denoise(p, f1["depth"], f1["velocity"], src, None, inp.blue, tgtA if i == 0 else tgtB, None)
+            if i == 0:
+                tgtA = out
+            else:
+                tgtB = out
+        assert ch.compare(tgtB, hb.texture.download())["frac_bad"] <= 2e-3
+        want7 = orc.ao_compose(ch.ao_compose_params(), f1["depth"], hb.texture.download(), f1["direct"])
+        assert ch.compare(want7, comp.outputBuffer.download())["frac_bad"] <= 2e-3
+        hb.dispose()
+        # ---- TRAAEffect: frame 0 seeds the history, frame 1 reprojects it
+        vdn = effects.VelocityDepthNormalPass(scene, cam)
+        traa = effects.TRAAEffect(scene, cam, vdn)
+        assert traa.options["maxBlend"] == 0.9 and traa.options["confidencePower"] == 4 and traa.options["logTransform"] is True
+        scene.load(f0)
+        cam.u = f0["cam"]
+        comp.inputBuffer.upload(f0["direct"])
+        traa.update(None, comp.inputBuffer)
+        hist = traa.temporalReprojectPass.accumulated.download()
+        scene.load(f1)
+        cam.u = f1["cam"]
+        comp.inputBuffer.upload(f1["direct"])
+        traa.update(None, comp.inputBuffer)
+        p = ch.traa_temporal_params(abi.make_camera(f1["cam"]), f1["cam"]["position"], f0["cam"], 1.0)
+        want, _ = orc.temporal_reproject(p, f1["direct"], f1["velocity"], hist, None, z, None, out_half=True)
+        assert ch.compare(want, traa.temporalReprojectPass.accumulated.download())["frac_bad"] <= 2e-3
+        traa.compose(comp.outputBuffer)
+        assert (comp.outputBuffer.download()[..., 3] == 1).all()
+        traa.dispose()
+        # ---- MotionBlurEffect
+        mb = effects.MotionBlurEffect(vdn)
+        assert (mb.intensity, mb.jitter, mb.samples) == (1, 1, 16)
+        vel = ch.rotation_velocity_field(W, H, f1["depth"])
+        scene.velocity.upload(vel)
+        mb._frame = 7
+        mb.update(None, comp.inputBuffer, 1 / 60, comp.outputBuffer)
+        want = orc.motion_blur(ch.motion_blur_params(W, H, frame=7), vel, f1["direct"], inp.blue)
+        assert ch.compare(want, comp.outputBuffer.download())["frac_bad"] <= 2e-3
+    finally:
+        ctx.close()
