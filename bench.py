@@ -7,19 +7,21 @@ One "step" = one frame of the SSGI chain over one batch of synthetic G-buffer pl
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-value   : whole-job Mpixels/s with the input planes resident in HBM (CUDA events on the launching
-          stream, max over ranks).
-e2e     : the same metric through the host-buffer C-ABI call rfx_ssgi_chain_render_host (pinned host
-          planes -> H2D -> chain -> D2H of `composed`), copies inside the timed region.
-roofline: the dominant kernel's algorithmic bytes / its mean CUDA-event duration over the timed frames,
-          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-cpu_baseline / --impl reference: the CPU restatement in oracle/ (the reference itself is WebGL-only and
-          cannot run here: no GL, no JS engine) on the box's host cores, bounded sample.
+N = 1 : one 3840x2160 frame per step on one GPU (the configuration the metric is quoted on).
+N > 1 : weak scaling — a 3840 x (2160*N) frame, row-block sharded: each rank renders its own 2160 rows (halo rows
+        recomputed locally, realism_effects_b200/parallel.py) and the ranks all-gather the produced planes the next frame
+        samples at arbitrary uv (composed + dnB[0..1], 32 B/px) over NCCL once per frame.
+value   : whole-job Mpixels/s with the input planes resident in HBM (CUDA events on the launching stream, max over ranks).
+e2e     : the same metric through host buffers (pinned host planes -> H2D -> chain -> D2H of `composed`), copies inside
+          the timed region; at N = 1 this is the single C-ABI call rfx_ssgi_chain_render_host.
+roofline: the dominant kernel's algorithmic bytes / its mean CUDA-event duration over the timed frames, against the
+          measured HBM copy bandwidth in MEASURED_PEAKS.json (+ the chain-level figure).
+cpu_baseline / --impl reference: the CPU restatement in oracle/ (the reference itself is WebGL-only and cannot run
+          here: no GL, no JS engine) on the box's host cores, bounded sample.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -55,9 +57,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.rows = []
-        self.p = None
+        self.gpu, self.rows, self.p = gpu_index, [], None
 
     def start(self):
         try:
@@ -96,21 +96,20 @@ class ClockSampler:
 
 def opts_for_bench():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import chain_harness as ch  # parameter builders only (no oracle import at module level)
+    import chain_harness as ch  # parameter builders only (the oracle is imported lazily by the CPU legs)
 
     return ch, ch.Opts(denoise_iterations=DENOISE_ITERATIONS)
 
 
-# ------------------------------------------------------------------------------------------------
-def make_gpu_frames(width, height, n, device):
-    """Synthetic planes generated on the device with torch (plumbing); returns list of dicts of tensors."""
+def make_gpu_frames(width, height, n, device, fov):
+    """Synthetic planes generated on the device with torch (plumbing)."""
     import torch
 
     from realism_effects_b200 import synth
 
     frames = []
     for t in range(n):
-        fr = synth.render_frame(width, height, t + 1, device=device)
+        fr = synth.render_frame(width, height, t + 1, device=device, fov=fov)
         frames.append(dict(depth=fr.depth, gbuffer=fr.gbuffer, velocity=fr.velocity, direct=fr.direct_light, cam=fr.cam.uniforms(), moved=True))
     torch.cuda.synchronize()
     return frames
@@ -127,11 +126,18 @@ def tensor_plane(t, fmt):
     return p
 
 
+class _PW:  # adapter so SsgiChain.render can take raw planes
+    def __init__(self, p):
+        self.p = p
+
+
 def run_ours(args):
+    import math
+
     import torch
     import torch.distributed as dist
 
-    from realism_effects_b200 import abi, engine, synth
+    from realism_effects_b200 import abi, engine, parallel, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -143,8 +149,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ch, o = opts_for_bench()
-    W, H = args.width, args.height
+    W, Hr = args.width, args.height          # per-rank block
+    H = Hr * world                           # global frame height (weak scaling)
     K, Wm = args.steps, args.warmup
+    # keep the horizontal framing of the 4K view when the frame gets taller
+    fov = 2.0 * math.degrees(math.atan(math.tan(math.radians(20.0)) * world))
 
     ctx = engine.Context(local)
     env = synth.synthetic_env(1024, 512)
@@ -154,105 +163,128 @@ def run_ours(args):
     class _I:  # minimal Inputs for chain_options
         width, height = W, H
 
-    chain = engine.SsgiChain(ctx, ch.chain_options(_I, o))
-    frames = make_gpu_frames(W, H, 2, dev)
+    copt = ch.chain_options(_I, o)
+    frames = make_gpu_frames(W, H, 2, dev, fov)
     planes = [dict(depth=tensor_plane(f["depth"], abi.FMT_R32F), gbuffer=tensor_plane(f["gbuffer"], abi.FMT_RGBA32F),
                    velocity=tensor_plane(f["velocity"], abi.FMT_RGBA32F), direct=tensor_plane(f["direct"], abi.FMT_RGBA16F)) for f in frames]
     cams = [abi.make_camera(f["cam"]) for f in frames]
 
-    class _PW:  # adapter so SsgiChain.render can take raw planes
-        def __init__(self, p):
-            self.p = p
+    if world == 1:
+        chain = engine.SsgiChain(ctx, copt)
+        native = chain
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
-    def render(i, stream=None):
-        j = i % len(frames)
-        pl = planes[j]
-        chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True, stream=stream)
+        def render(i):
+            j = i % len(frames)
+            pl = planes[j]
+            chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True)
+    else:
+        chain = parallel.ShardedSsgiChain(ctx, copt)
+        native = chain.chain
+        stream = torch.cuda.current_stream()
 
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        def render(i):
+            j = i % len(frames)
+            pl = planes[j]
+            chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident timing ------------------------------------------------------------
     for i in range(Wm):
         render(i)
-    ctx.sync()
+    barrier()
     launches0 = ctx.launch_count
-    chain.set_profiling(True)
-    chain.get_profile()
+    native.set_profiling(True)
+    native.get_profile()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
+    e0.record(stream)
     for i in range(K):
         render(Wm + i)
-    e1.record(ext)
+    e1.record(stream)
     barrier()
     clk = clocks.stop()
-    ms_total = e0.elapsed_time(e1)
-    prof = chain.get_profile()
-    chain.set_profiling(False)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = native.get_profile()
+    native.set_profiling(False)
     launches = ctx.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_per_step = ms_total / K
-    mpx = W * H * world / 1e6
+    mpx = W * H / 1e6
     value = mpx / (ms_per_step / 1e3)
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------
+    # ---- roofline of the dominant kernel (this rank's owned pixels / its event-timed duration) -------
     peak, peak_src = measured_peak()
     per_kernel = {}
     for k, (ms, n) in prof.items():
         if n:
             per_kernel[k] = {"ms_per_launch": ms / n, "launches": n, "share_of_step": ms / max(ms_total, 1e-9),
-                             "algo_GBps": ALGO_BYTES[k] * W * H / (ms / n * 1e-3) / 1e9}
+                             "algo_GBps": ALGO_BYTES[k] * W * Hr / (ms / n * 1e-3) / 1e9}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"]) if per_kernel else None
     roof = None
     if dom:
         ach = per_kernel[dom]["algo_GBps"]
+        chain_ach = CHAIN_BYTES_PER_PX * W * Hr / (ms_per_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
-                "peak_source": peak_src, "chain_achieved": round(CHAIN_BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9, 1),
-                "chain_frac": round(CHAIN_BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                "peak_source": peak_src, "chain_achieved": round(chain_ach, 1), "chain_frac": round(chain_ach / peak, 4),
+                "note": "per GPU; this path is instruction/SFU-bound, not HBM-bound (DESIGN.md §4): ncu DRAM traffic is at or below the algorithmic bytes",
                 "per_kernel": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in per_kernel.items()}}
 
-    # ---- e2e through the host-buffer C-ABI call ---------------------------------------------------
-    host = []
-    for f in frames[:2]:
-        host.append({k: f[k].cpu().pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")})
-    out_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    # ---- e2e through host buffers --------------------------------------------------------------------
+    host = [{k: f[k].cpu().pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")} for f in frames[:2]]
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
-    d2h = out_host.numel() * 4
-    hfs = []
-    for j, hb in enumerate(host):
-        hf = abi.SsgiHostFrame()
-        hf.cam = cams[j]
-        hf.depth, hf.gbuffer, hf.velocity, hf.direct_light = hb["depth"].data_ptr(), hb["gbuffer"].data_ptr(), hb["velocity"].data_ptr(), hb["direct"].data_ptr()
-        hf.camera_pos[:] = [float(x) for x in frames[j]["cam"]["position"]]
-        hf.camera_moved = 1
-        hf.out_composed = out_host.data_ptr()
-        hfs.append(hf)
     ke = max(3, min(K, 10))
+    if world == 1:
+        out_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        hfs = []
+        for j, hb in enumerate(host):
+            hf = abi.SsgiHostFrame()
+            hf.cam = cams[j]
+            hf.depth, hf.gbuffer, hf.velocity, hf.direct_light = hb["depth"].data_ptr(), hb["gbuffer"].data_ptr(), hb["velocity"].data_ptr(), hb["direct"].data_ptr()
+            hf.camera_pos[:] = [float(x) for x in frames[j]["cam"]["position"]]
+            hf.camera_moved = 1
+            hf.out_composed = out_host.data_ptr()
+            hfs.append(hf)
+
+        def e2e_step(i):
+            chain.render_host(hfs[i % 2])  # one C-ABI call; returns after the D2H copy completed
+    else:
+        plan = chain.plan
+        out_host = torch.empty((Hr, W, 4), dtype=torch.float32).pin_memory()
+        comp = chain.chain.output(0)
+        comp_t = torch.as_tensor(parallel._CudaBytes(comp.ptr, int(comp.pitch) * int(comp.height)), device=dev).view(torch.float32).view(H, -1)[:, :W * 4].view(H, W, 4)
+
+        def e2e_step(i):
+            j = i % 2
+            for k in ("depth", "gbuffer", "velocity", "direct"):
+                frames[j][k].copy_(host[j][k], non_blocking=True)  # every rank needs the full input planes (K1 taps anywhere)
+            render(i)
+            out_host.copy_(comp_t[plan.r0:plan.r1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    d2h = out_host.numel() * 4
     for i in range(2):
-        chain.render_host(hfs[i % 2])
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(ke):
-        chain.render_host(hfs[i % 2])  # synchronous: returns after the D2H copy completed
+        e2e_step(i)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / ke
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / ke)
     checksum = float(out_host[::97, ::89, :3].double().sum())
     e2e = {"value": round(mpx / e2e_s, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": round(e2e_s * 1e3, 3), "steps": ke, "result_checksum": checksum}
+           "ms_per_step": round(e2e_s * 1e3, 3), "steps": ke, "result_checksum": checksum, "bytes_are": "per rank"}
 
     # ---- CPU baseline (rank 0, N=1 only): one full-resolution frame through the oracle ------------
     cpu = None
@@ -267,14 +299,18 @@ def run_ours(args):
         cpu = cpu_baseline_sample(ch, o, cpu_inp)
 
     if rank == 0:
+        cfg = {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS} => {2 * DENOISE_ITERATIONS} passes)+compose, steps=20 refineSteps=5, "
+                           f"{W}x{Hr} per GPU" + (f" (frame {W}x{H} row-sharded over {world} GPUs)" if world > 1 else ""),
+               "inputs": f"2 alternating synthetic G-buffer frames ({h2d / 1e6:.0f} MB of input planes per frame > 126 MB L2), moving camera",
+               "l2": "inputs larger than L2; no explicit flush", "fast_math": True}
+        if world > 1:
+            cfg["multi_gpu"] = {"sharding": "row blocks, halo rows recomputed locally", "recompute_overhead": round(chain.plan.recompute_overhead, 4),
+                                "exchange": "NCCL all-gather of composed + dnB[0..1] once per frame",
+                                "exchange_recv_bytes_per_rank_per_frame": chain.exchange_bytes_per_frame}
         line = {
             "metric": "SSGI+denoise Mpixels/s at 4K", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 accumulate planes)",
-            "data": "synthetic", "impl": "ours",
-            "config": {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS} => {2 * DENOISE_ITERATIONS} passes)+compose {W}x{H} per GPU, steps=20 refineSteps=5",
-                       "inputs": "2 alternating synthetic G-buffer frames (365 MB/frame of input planes > 126 MB L2), moving camera",
-                       "l2": "inputs larger than L2; no explicit flush", "multi_gpu": "replicas" if world > 1 else "single"},
-            "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "data": "synthetic", "impl": "ours", "config": cfg, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
         }
         print(json.dumps(line))
     chain.close()
@@ -342,7 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--height", type=int, default=HEIGHT, help="rows per GPU")
     ap.add_argument("--cpu-width", type=int, default=WIDTH)
     ap.add_argument("--cpu-height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -322,6 +322,12 @@ rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* chain);
  * width/height (use a new chain to resize) and resets the temporal history like the reference's setters do. */
 rfx_status rfx_ssgi_chain_set_options(rfx_ssgi_chain* chain, const rfx_ssgi_chain_options* opt);
 rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
+/* Row-block sharded frame: ranges[2k], ranges[2k+1] = output rows [a,b) of launch k in chain order
+ * (K1, K2, K3 pass 0..2*denoiseIterations-1, K4 when mode == SSGI).  The caller (realism_effects_b200/parallel.py) sizes
+ * the ranges so that every pass finds valid halo rows produced locally by the previous pass, then all-gathers the
+ * produced-then-gathered planes (composed, dnB[0..1]) across ranks.  Results are bit-identical to rfx_ssgi_chain_render. */
+rfx_status rfx_ssgi_chain_render_ranges(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame, const uint32_t* ranges,
+                                        uint32_t n_launches);
 /* which: 0 composed (RGBA32F), 1 ssgiOut, 2/3 trOut[0/1], 4/5 dnB[0/1] */
 rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* chain, int32_t which, rfx_plane* out);
 /* host-buffer frame: uploads the four input planes from (pinned) host memory, renders,

@@ -709,11 +709,15 @@ rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* ch, int32_t which, rfx_plane* o
   return RFX_OK;
 }
 
-rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f) {
-  if (!ch || !f) return RFX_ERR_INVALID_ARG;
+// ranges == nullptr: whole planes.  Otherwise ranges[2k], ranges[2k+1] = output rows [a,b) of launch k in chain order
+// (K1, K2, K3 pass 0 .. 2*iterations-1, K4): row-block sharding with locally recomputed halos (realism_effects_b200/parallel.py).
+static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges) {
   rfx_ctx* ctx = ch->ctx;
   const rfx_ssgi_chain_options& o = ch->opt;
   rfx_status st;
+  int launch_k = 0;
+  auto R0 = [&]() -> uint32_t { return ranges ? ranges[2 * launch_k] : 0u; };
+  auto R1 = [&]() -> uint32_t { return ranges ? ranges[2 * launch_k + 1] : 0u; };
   // ---- K1  SSGIPass.render (src/ssgi/pass/SSGIPass.js:68-95)
   rfx_ssgi_params sp{};
   sp.cam = f->cam;
@@ -724,7 +728,8 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
   // velocityTexture is a null sampler in the shipped wiring
   const cudaStream_t cs = stream ? (cudaStream_t)stream : ctx->stream;
   { SpanGuard g(ch, cs, 0);
-    st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, 0, 0); }
+    st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, R0(), R1()); }
+  launch_k++;
   if (st != RFX_OK) return st;
   // ---- K2  TemporalReprojectPass.render (TemporalReprojectPass.js:162-214), options from Denoiser.js:26-43 + SSGIEffect.js:74-77
   rfx_temporal_params tp{};
@@ -746,7 +751,8 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
   const int tc = tp.texture_count;
   { SpanGuard g(ch, cs, 1);
     st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
-                                       tc == 2 ? &ch->tr[1] : nullptr, 0, 0); }
+                                       tc == 2 ? &ch->tr[1] : nullptr, R0(), R1()); }
+  launch_k++;
   if (st != RFX_OK) return st;
   ch->keep_data = 1.0f;  // :195
   memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
@@ -766,7 +772,8 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
     pp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_poisson);
     ctx->nrd_reuse = i > 0;  // the G-buffer does not change within a frame: decode it once (pass 0), reuse it afterwards
     { SpanGuard g(ch, cs, i == 0 ? 2 : 3);
-      st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, 0, 0); }
+      st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, R0(), R1()); }
+    launch_k++;
     if (st != RFX_OK) return st;
   }
   ctx->nrd_reuse = false;
@@ -776,10 +783,23 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
     cp.cam = f->cam;
     cp.input_type = RFX_INPUT_DIFFUSE_SPECULAR;
     { SpanGuard g(ch, cs, 4);
-      st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, 0, 0); }
+      st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, R0(), R1()); }
     if (st != RFX_OK) return st;
   }
   return RFX_OK;
+}
+
+rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f) {
+  if (!ch || !f) return RFX_ERR_INVALID_ARG;
+  return chain_render_impl(ch, stream, f, nullptr);
+}
+rfx_status rfx_ssgi_chain_render_ranges(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_launches) {
+  if (!ch || !f || !ranges) return RFX_ERR_INVALID_ARG;
+  const uint32_t expect = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
+  if (n_launches != expect) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_render_ranges: expected %u row ranges, got %u", expect, n_launches);
+  for (uint32_t k = 0; k < n_launches; k++)
+    if (ranges[2 * k] >= ranges[2 * k + 1] || ranges[2 * k + 1] > ch->opt.height) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_render_ranges: bad range %u", k);
+  return chain_render_impl(ch, stream, f, ranges);
 }
 
 rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_frame* hf) {

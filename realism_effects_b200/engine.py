@@ -209,7 +209,8 @@ class SsgiChain:
         self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_set_options(self.h, C.byref(opt)))
         self.opt = opt
 
-    def render(self, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None):
+    def render(self, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None, ranges=None):
+        """ranges: optional list of (row0, row1) per launch (K1, K2, K3 passes..., K4) for row-block sharding."""
         f = abi.SsgiFrame()
         f.cam = cam
         f.depth = C.pointer(depth.p)
@@ -218,7 +219,11 @@ class SsgiChain:
         f.direct_light = C.pointer(direct_light.p) if direct_light is not None else None
         f.camera_pos[:] = [float(x) for x in camera_pos]
         f.camera_moved = int(camera_moved)
-        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render(self.h, stream, C.byref(f)))
+        if ranges is None:
+            self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render(self.h, stream, C.byref(f)))
+        else:
+            flat = (C.c_uint32 * (2 * len(ranges)))(*[int(v) for r in ranges for v in r])
+            self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_ranges(self.h, stream, C.byref(f), flat, len(ranges)))
 
     def output(self, which: int = 0) -> Plane:
         p = Plane()

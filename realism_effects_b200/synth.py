@@ -225,15 +225,15 @@ class Frame:
     background: torch.Tensor    # (H,W) bool
 
 
-def render_frame(width: int, height: int, t: int = 0, *, device="cpu", cam_step=(0.02, 0.0, 0.0), static=False) -> Frame:
+def render_frame(width: int, height: int, t: int = 0, *, device="cpu", cam_step=(0.02, 0.0, 0.0), static=False, fov: float = 40.0) -> Frame:
     """Ray-cast frame `t`.  The camera translates by `cam_step` per frame; with
-    `static=True` it does not move (exercises fullAccumulate)."""
+    `static=True` it does not move (exercises fullAccumulate).  `fov` = vertical field of view in degrees."""
     aspect = width / height
     step = (0.0, 0.0, 0.0) if static else cam_step
 
     def cam_at(k):
         off = tuple(s * k for s in step)
-        return Camera(aspect=aspect, position=(0.0 + off[0], 8.75 + off[1], 25.0 + off[2]), target=(0.0 + off[0], 8.75 + off[1], 0.0 + off[2]))
+        return Camera(fov=fov, aspect=aspect, position=(0.0 + off[0], 8.75 + off[1], 25.0 + off[2]), target=(0.0 + off[0], 8.75 + off[1], 0.0 + off[2]))
 
     cam, prev = cam_at(t), cam_at(max(t - 1, 0))
     dev = torch.device(device)

@@ -1,0 +1,73 @@
+"""Multi-GPU test (needs >= 2 GPUs on the box; skipped otherwise): the row-sharded chain over NCCL must equal the
+single-GPU chain bit for bit on every rank (gathered planes: whole frame; other planes: the rank's own rows)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import chain_harness as ch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from realism_effects_b200 import abi, engine, parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        o = ch.Opts(denoise_iterations=2)
+        inp = ch.make_inputs(256, 128, 3)
+        ctx = engine.Context(rank, inp.blue)
+        ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o))
+        for fr in inp.frames:
+            pl = [ctx.upload(fr[k]) for k in ("depth", "gbuffer", "velocity", "direct")]
+            chain.render(abi.make_camera(fr["cam"]), *pl, fr["cam"]["position"], fr["moved"])
+            torch.cuda.synchronize()
+            for p in pl:
+                p.free()
+        out = {k: chain.chain.download(w).tobytes() for k, w in (("composed", 0), ("ssgi", 1), ("tr0", 2), ("dn0", 4), ("dn1", 5))}
+        q.put((rank, out, (chain.plan.r0, chain.plan.r1)))
+        chain.close()
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
+def test_sharded_chain_equals_single_gpu_bit_exact(built):
+    import torch.multiprocessing as mp
+
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in procs:
+        rank, out, own = q.get(timeout=600)
+        res[rank] = (out, own)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = ch.Opts(denoise_iterations=2)
+    inp = ch.make_inputs(256, 128, 3)
+    single, _ = ch.run_cuda_chain(inp, o)
+    ref = single[-1]
+    for rank, (out, (r0, r1)) in res.items():
+        for k in ("composed", "dn0", "dn1"):
+            assert out[k] == ref[k].tobytes(), (rank, k)
+        for k in ("ssgi", "tr0"):
+            got = np.frombuffer(out[k], ref[k].dtype).reshape(ref[k].shape)
+            assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)

@@ -1,0 +1,124 @@
+"""CPU tests of the multi-GPU host logic: the row-block ShardPlan (halo recompute ranges) and the per-frame all-gather,
+exercised with world_size = 2 over gloo with the ORACLE standing in for the kernels (each "launch" commits only its row
+range, like a row-sharded kernel).  The sharded result must equal the single-process chain bit for bit — if a halo were
+one row short, a pass would read a stale row and the comparison would fail."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import chain_harness as ch
+from realism_effects_b200 import abi
+from realism_effects_b200.parallel import ShardPlan
+
+
+def test_shard_plan_ranges():
+    p = ShardPlan(2160, 8, 3, 4, 3.0)
+    own = (810, 1080)
+    k1, k2, p0, p1, p2, p3, k4 = p.ranges
+    assert k4 == own and p3 == (809, 1081) and p2 == (805, 1085) and p1 == (801, 1089) and p0 == (797, 1093)
+    assert k2 == (793, 1097) and k1 == (791, 1099)
+    assert 0 < p.recompute_overhead < 0.15
+    first, last = ShardPlan(2160, 8, 0, 4, 3.0), ShardPlan(2160, 8, 7, 4, 3.0)
+    assert first.ranges[0][0] == 0 and last.ranges[0][1] == 2160                 # clipped at the frame border
+    assert ShardPlan(2160, 1, 0, 4, 3.0).ranges == [(0, 2160)] * 7               # one GPU: whole planes
+    assert ShardPlan(64, 2, 1, 0, 3.0).ranges == [(30, 64), (32, 64), (32, 64)]   # denoiseIterations = 0: K1, K2, K4 only
+    assert len(ShardPlan(64, 2, 0, 2, 3.0, ssgi_mode=False).ranges) == 4          # SSR: no K4
+    with pytest.raises(ValueError):
+        ShardPlan(2161, 8, 0, 4, 3.0)
+    assert ShardPlan(2160, 8, 0, 4, 11.0).poisson_halo == 12                      # demo radius 11
+
+
+def sharded_oracle_chain(inp, o, rank, world, all_gather_rows):
+    """The chain of chain_harness.run_oracle_chain, but every pass commits only plan.ranges[k] rows into this rank's planes."""
+    import orc
+
+    H, W = inp.height, inp.width
+    plan = ShardPlan(H, world, rank, 2 * o.denoise_iterations, o.radius)
+    env = orc.Env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+    z32, z16 = (lambda: np.zeros((H, W, 4), np.float32)), (lambda: np.zeros((H, W, 4), np.float16))
+    ssgi, tr, dnA, dnB, composed = z32(), [z32(), z32()], [z16(), z16()], [z16(), z16()], z32()
+    keep_data, prev, bn_t, bn_p = 0.0, None, 0, 0
+
+    def commit(dst, new, rng):
+        dst[rng[0]:rng[1]] = new[rng[0]:rng[1]]
+
+    for fr in inp.frames:
+        rngs = iter(plan.ranges)
+        cam = abi.make_camera(fr["cam"])
+        bn_t = ch.next_blue(o.blue_noise_start, bn_t)
+        sp = ch.ssgi_params(o, cam, bn_t, (inp.env_map.shape[1], inp.env_map.shape[0]))
+        commit(ssgi, orc.ssgi_trace(sp, fr["depth"], fr["gbuffer"], None, fr["direct"], composed, env, inp.blue), next(rngs))
+        prev = prev or fr["cam"]
+        tp = ch.temporal_params(o, cam, fr["cam"]["position"], prev, keep_data, fr["moved"])
+        t0, t1 = orc.temporal_reproject(tp, ssgi, fr["velocity"], dnB[0], dnB[1], tr[0], tr[1])
+        r = next(rngs)
+        commit(tr[0], t0, r)
+        commit(tr[1], t1, r)
+        keep_data, prev = 1.0, fr["cam"]
+        for i in range(2 * o.denoise_iterations):
+            horizontal = i % 2 == 0
+            src = tr if i == 0 else (dnB if horizontal else dnA)
+            dst = dnA if horizontal else dnB
+            bn_p = ch.next_blue(o.blue_noise_start, bn_p)
+            o0, o1 = orc.poisson_denoise(ch.poisson_params(o, bn_p, i == 0), fr["depth"], fr["gbuffer"], src[0], src[1], inp.blue, dst[0], dst[1])
+            r = next(rngs)
+            commit(dst[0], o0, r)
+            commit(dst[1], o1, r)
+        commit(composed, orc.gi_compose(ch.compose_params(cam), fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed), next(rngs))
+        for plane in (composed, dnB[0], dnB[1]):
+            all_gather_rows(plane, plan.r0, plan.r1)
+    return dict(composed=composed, dn0=dnB[0], dn1=dnB[1], tr0=tr[0], ssgi=ssgi, plan=plan)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        o = ch.Opts(steps=8, refine_steps=2, denoise_iterations=1)
+        inp = ch.make_inputs(96, 64, 2)
+
+        def all_gather_rows(plane, r0, r1):
+            mine = torch.from_numpy(np.ascontiguousarray(plane[r0:r1]).view(np.uint8).reshape(-1))
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            rows = plane.shape[0] // world
+            for g, t in enumerate(parts):
+                plane[g * rows:(g + 1) * rows] = t.numpy().view(plane.dtype).reshape(rows, *plane.shape[1:])
+
+        out = sharded_oracle_chain(inp, o, rank, world, all_gather_rows)
+        q.put((rank, {k: v.tobytes() for k, v in out.items() if k != "plan"}, (out["plan"].r0, out["plan"].r1)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_chain_equals_single_process_bit_exact():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict()
+    for _ in procs:
+        rank, planes, own = q.get(timeout=300)
+        results[rank] = (planes, own)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = ch.Opts(steps=8, refine_steps=2, denoise_iterations=1)
+    inp = ch.make_inputs(96, 64, 2)
+    ref = ch.run_oracle_chain(inp, o)[-1]
+    for rank, (planes, (r0, r1)) in results.items():
+        for k in ("composed", "dn0", "dn1"):                       # gathered planes: the whole frame must match on every rank
+            assert planes[k] == ref[k].tobytes(), (rank, k)
+        for k in ("tr0", "ssgi"):                                  # not gathered: this rank's own rows must match
+            got = np.frombuffer(planes[k], ref[k].dtype).reshape(ref[k].shape)
+            assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
