@@ -181,7 +181,7 @@ def run_ours(args):
     else:
         chain = parallel.ShardedSsgiChain(ctx, copt)
         native = chain.chain
-        stream = torch.cuda.current_stream()
+        stream = chain.stream  # kernels + NCCL all-gathers are ordered on this stream
 
         def render(i):
             j = i % len(frames)
@@ -268,11 +268,13 @@ def run_ours(args):
 
         def e2e_step(i):
             j = i % 2
-            for k in ("depth", "gbuffer", "velocity", "direct"):
-                frames[j][k].copy_(host[j][k], non_blocking=True)  # every rank needs the full input planes (K1 taps anywhere)
+            with torch.cuda.stream(chain.stream):
+                for k in ("depth", "gbuffer", "velocity", "direct"):
+                    frames[j][k].copy_(host[j][k], non_blocking=True)  # every rank needs the full input planes (K1 taps anywhere)
             render(i)
-            out_host.copy_(comp_t[plan.r0:plan.r1], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(chain.stream):
+                out_host.copy_(comp_t[plan.r0:plan.r1], non_blocking=True)
+            chain.stream.synchronize()
     d2h = out_host.numel() * 4
     for i in range(2):
         e2e_step(i)

@@ -98,6 +98,9 @@ class ShardedSsgiChain:
         self.ctx = ctx
         self.plan = ShardPlan(chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
                               chain_options.mode == abi.MODE_SSGI)
+        # a dedicated torch stream: the kernels and the NCCL collectives are ordered on it.  (A NULL stream handle means "the
+        # context's own stream" to the C ABI, so torch's default stream cannot be used here.)
+        self.stream = torch.cuda.Stream(device=torch.device("cuda", ctx.device))
         self._tensors = {}
         for which in self.plan.gathered_planes:
             p = self.chain.output(which)
@@ -106,15 +109,16 @@ class ShardedSsgiChain:
             self._tensors[which] = (t, int(p.pitch))
 
     def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool):
-        """Enqueues the frame on torch's current stream, then the all-gathers (stream-ordered by torch's NCCL wrapper)."""
+        """Enqueues the frame on self.stream, then the all-gathers (torch's NCCL wrapper orders them after the kernels on that
+        stream and makes the stream wait for their completion)."""
         torch = self.torch
-        stream = torch.cuda.current_stream().cuda_stream
-        self.chain.render(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved, stream=stream,
-                          ranges=self.plan.ranges if self.world > 1 else None)
-        if self.world > 1:
-            for which, (t, pitch) in self._tensors.items():
-                own = t[self.plan.r0 * pitch:self.plan.r1 * pitch]
-                self.dist.all_gather_into_tensor(t, own, group=self.group)  # in place: block g lands at rows [g*H/N, (g+1)*H/N)
+        with torch.cuda.stream(self.stream):
+            self.chain.render(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved, stream=self.stream.cuda_stream,
+                              ranges=self.plan.ranges if self.world > 1 else None)
+            if self.world > 1:
+                for which, (t, pitch) in self._tensors.items():
+                    own = t[self.plan.r0 * pitch:self.plan.r1 * pitch]
+                    self.dist.all_gather_into_tensor(t, own, group=self.group)  # in place: block g lands at rows [g*H/N, (g+1)*H/N)
 
     @property
     def exchange_bytes_per_frame(self) -> int:
