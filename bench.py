@@ -179,7 +179,7 @@ def run_ours(args):
             pl = planes[j]
             chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True)
     else:
-        chain = parallel.ShardedSsgiChain(ctx, copt)
+        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap)
         native = chain.chain
         stream = chain.stream  # kernels + NCCL all-gathers are ordered on this stream
 
@@ -214,6 +214,8 @@ def run_ours(args):
     e0.record(stream)
     for i in range(K):
         render(Wm + i)
+    if world > 1:
+        chain.finish()  # the last frame's all-gathers belong to the timed region
     e1.record(stream)
     barrier()
     clk = clocks.stop()
@@ -273,8 +275,11 @@ def run_ours(args):
                     frames[j][k].copy_(host[j][k], non_blocking=True)  # every rank needs the full input planes (K1 taps anywhere)
             render(i)
             with torch.cuda.stream(chain.stream):
-                out_host.copy_(comp_t[plan.r0:plan.r1], non_blocking=True)
-            chain.stream.synchronize()
+                off = 0
+                for b0, b1 in plan.blocks:  # this rank's rows of `composed`
+                    out_host[off:off + (b1 - b0)].copy_(comp_t[b0:b1], non_blocking=True)
+                    off += b1 - b0
+            chain.finish()
     d2h = out_host.numel() * 4
     for i in range(2):
         e2e_step(i)
@@ -306,8 +311,9 @@ def run_ours(args):
                "inputs": f"2 alternating synthetic G-buffer frames ({h2d / 1e6:.0f} MB of input planes per frame > 126 MB L2), moving camera",
                "l2": "inputs larger than L2; no explicit flush", "fast_math": True}
         if world > 1:
-            cfg["multi_gpu"] = {"sharding": "row blocks, halo rows recomputed locally", "recompute_overhead": round(chain.plan.recompute_overhead, 4),
-                                "exchange": "NCCL all-gather of composed + dnB[0..1] once per frame",
+            cfg["multi_gpu"] = {"sharding": f"block-cyclic row blocks ({chain.plan.blocks_per_rank} x {chain.plan.block_rows} rows per rank), halo rows recomputed locally",
+                                "recompute_overhead": round(chain.plan.recompute_overhead, 4),
+                                "exchange": "NCCL all-gather of composed + dnB[0..1] once per frame" + ("" if args.no_overlap else "; dnB gathers overlap the next frame's K1"),
                                 "exchange_recv_bytes_per_rank_per_frame": chain.exchange_bytes_per_frame}
         line = {
             "metric": "SSGI+denoise Mpixels/s at 4K", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -384,6 +390,8 @@ def main():
     ap.add_argument("--cpu-width", type=int, default=WIDTH)
     ap.add_argument("--cpu-height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocks-per-rank", type=int, default=4, help="N > 1: block-cyclic row blocks per rank (content balance)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for all all-gathers at the end of every frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

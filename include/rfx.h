@@ -328,6 +328,12 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* chain, void* stream, const rfx_
  * produced-then-gathered planes (composed, dnB[0..1]) across ranks.  Results are bit-identical to rfx_ssgi_chain_render. */
 rfx_status rfx_ssgi_chain_render_ranges(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame, const uint32_t* ranges,
                                         uint32_t n_launches);
+/* General form: this rank owns `n_blocks` row blocks (block-cyclic assignment balances sky / floor content across ranks);
+ * ranges[(blk*n_launches + k)*2 + {0,1}] = rows of launch k for block blk.  Only launches k in [k_begin, k_end) are issued,
+ * which lets the caller split a frame into phases — K1 (needs last frame's `composed` gathered) | K2..K4 (need `dnB`
+ * gathered) — so the dnB all-gather overlaps K1.  Per-frame state advances with the launch that consumes it. */
+rfx_status rfx_ssgi_chain_render_blocks(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame, const uint32_t* ranges,
+                                        uint32_t n_launches, uint32_t n_blocks, uint32_t k_begin, uint32_t k_end);
 /* which: 0 composed (RGBA32F), 1 ssgiOut, 2/3 trOut[0/1], 4/5 dnB[0/1] */
 rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* chain, int32_t which, rfx_plane* out);
 /* host-buffer frame: uploads the four input planes from (pinned) host memory, renders,

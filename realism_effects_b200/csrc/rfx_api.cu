@@ -43,6 +43,7 @@ struct rfx_ctx {
   void* viewz = nullptr;
   int viewz_w = 0, viewz_h = 0;
   size_t viewz_pitch = 0;
+  bool viewz_reuse = false;  // set by the native chain for the 2nd.. row block of a frame
 };
 
 static rfx_status fail(rfx_ctx* c, rfx_status st, const char* fmt, ...) {
@@ -391,7 +392,7 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * a.H));
     ctx->viewz_w = a.W; ctx->viewz_h = a.H;
   }
-  LAUNCHED(launch_viewz(a, OutV{(unsigned char*)ctx->viewz, (long long)ctx->viewz_pitch}, pick(ctx, stream)));
+  if (!ctx->viewz_reuse) LAUNCHED(launch_viewz(a, OutV{(unsigned char*)ctx->viewz, (long long)ctx->viewz_pitch}, pick(ctx, stream)));
   a.viewz = PV{(const unsigned char*)ctx->viewz, a.W, a.H, (long long)ctx->viewz_pitch};
   LAUNCHED(launch_ssgi(a, pick(ctx, stream)));
   return RFX_OK;
@@ -709,81 +710,105 @@ rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* ch, int32_t which, rfx_plane* o
   return RFX_OK;
 }
 
-// ranges == nullptr: whole planes.  Otherwise ranges[2k], ranges[2k+1] = output rows [a,b) of launch k in chain order
-// (K1, K2, K3 pass 0 .. 2*iterations-1, K4): row-block sharding with locally recomputed halos (realism_effects_b200/parallel.py).
-static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges) {
+// One frame of the chain.  `ranges` == nullptr: whole planes, one block.  Otherwise ranges[(blk*n_launches + k)*2 + {0,1}] =
+// output rows [a,b) of launch k (chain order: K1, K2, K3 pass 0..2*iterations-1, K4) for row block `blk` of this rank
+// (row-block sharding with locally recomputed halos, realism_effects_b200/parallel.py).  Only launches k in
+// [k_begin, k_end) are issued, so a frame can be split into phases (K1 | the rest) between which the caller waits for a
+// different all-gather; per-frame state advances with the launch that consumes it.
+static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_blocks,
+                                    uint32_t k_begin, uint32_t k_end) {
   rfx_ctx* ctx = ch->ctx;
   const rfx_ssgi_chain_options& o = ch->opt;
-  rfx_status st;
-  int launch_k = 0;
-  auto R0 = [&]() -> uint32_t { return ranges ? ranges[2 * launch_k] : 0u; };
-  auto R1 = [&]() -> uint32_t { return ranges ? ranges[2 * launch_k + 1] : 0u; };
-  // ---- K1  SSGIPass.render (src/ssgi/pass/SSGIPass.js:68-95)
-  rfx_ssgi_params sp{};
-  sp.cam = f->cam;
-  sp.ray_distance = o.distance; sp.thickness = o.thickness; sp.env_blur = o.env_blur;
-  sp.max_env_map_mip_level = ctx->env_set ? (float)((int)std::floor(std::log2((double)std::max(ctx->env.size_x, ctx->env.size_y))) + 1) : 0.0f;  // Utils.js:30-34
-  sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
-  sp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_trace);
-  // velocityTexture is a null sampler in the shipped wiring
+  rfx_status st = RFX_OK;
+  const uint32_t n_launches = 2u + 2u * (uint32_t)o.denoise_iterations + (o.mode == RFX_MODE_SSGI ? 1u : 0u);
+  if (!ranges) n_blocks = 1;
+  auto R0 = [&](uint32_t blk, uint32_t k) -> uint32_t { return ranges ? ranges[(blk * n_launches + k) * 2] : 0u; };
+  auto R1 = [&](uint32_t blk, uint32_t k) -> uint32_t { return ranges ? ranges[(blk * n_launches + k) * 2 + 1] : 0u; };
+  auto on = [&](uint32_t k) { return k >= k_begin && k < k_end; };
   const cudaStream_t cs = stream ? (cudaStream_t)stream : ctx->stream;
-  { SpanGuard g(ch, cs, 0);
-    st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, R0(), R1()); }
-  launch_k++;
-  if (st != RFX_OK) return st;
+  uint32_t k = 0;
+  // ---- K1  SSGIPass.render (src/ssgi/pass/SSGIPass.js:68-95)
+  if (on(k)) {
+    rfx_ssgi_params sp{};
+    sp.cam = f->cam;
+    sp.ray_distance = o.distance; sp.thickness = o.thickness; sp.env_blur = o.env_blur;
+    sp.max_env_map_mip_level = ctx->env_set ? (float)((int)std::floor(std::log2((double)std::max(ctx->env.size_x, ctx->env.size_y))) + 1) : 0.0f;  // Utils.js:30-34
+    sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
+    sp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_trace);
+    // velocityTexture is a null sampler in the shipped wiring
+    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+      ctx->viewz_reuse = blk > 0;  // the view-z plane depends on the depth plane only: one prepass per frame
+      SpanGuard g(ch, cs, 0);
+      st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, R0(blk, k), R1(blk, k));
+    }
+    ctx->viewz_reuse = false;
+    if (st != RFX_OK) return st;
+  }
+  k++;
   // ---- K2  TemporalReprojectPass.render (TemporalReprojectPass.js:162-214), options from Denoiser.js:26-43 + SSGIEffect.js:74-77
-  rfx_temporal_params tp{};
-  tp.cam = f->cam;
-  if (!ch->have_prev) {  // the constructor clones the current camera matrices (TemporalReprojectPass.js:94-97)
-    memcpy(ch->prev_view, f->cam.view_matrix, 64); memcpy(ch->prev_world, f->cam.camera_matrix_world, 64);
+  const int tc = o.mode == RFX_MODE_SSGI ? 2 : 1;
+  if (on(k)) {
+    rfx_temporal_params tp{};
+    tp.cam = f->cam;
+    if (!ch->have_prev) {  // the constructor clones the current camera matrices (TemporalReprojectPass.js:94-97)
+      memcpy(ch->prev_view, f->cam.view_matrix, 64); memcpy(ch->prev_world, f->cam.camera_matrix_world, 64);
+      memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
+      memcpy(ch->prev_pos, f->camera_pos, 12);
+      ch->have_prev = true;
+    }
+    memcpy(tp.prev_view_matrix, ch->prev_view, 64); memcpy(tp.prev_camera_matrix_world, ch->prev_world, 64);
+    memcpy(tp.prev_projection, ch->prev_proj, 64); memcpy(tp.prev_projection_inverse, ch->prev_proj_inv, 64);
+    memcpy(tp.camera_pos, f->camera_pos, 12); memcpy(tp.prev_camera_pos, ch->prev_pos, 12);
+    tp.max_blend = 1.0f; tp.neighborhood_clamp_intensity = 0.5f; tp.keep_data = ch->keep_data; tp.confidence_power = 0.75f;
+    tp.full_accumulate = f->camera_moved ? 0 : 1;  // options.fullAccumulate && !didCameraMove
+    tp.log_transform = 1; tp.history_linear = 1;
+    if (o.mode == RFX_MODE_SSGI) { tp.texture_count = 2; tp.input_type = RFX_INPUT_DIFFUSE_SPECULAR; tp.reproject_specular[0] = 0; tp.reproject_specular[1] = 1; }
+    else { tp.texture_count = 1; tp.input_type = RFX_INPUT_SPECULAR; tp.reproject_specular[0] = 1; tp.reproject_specular[1] = 1; }
+    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+      SpanGuard g(ch, cs, 1);
+      st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
+                                         tc == 2 ? &ch->tr[1] : nullptr, R0(blk, k), R1(blk, k));
+    }
+    if (st != RFX_OK) return st;
+    ch->keep_data = 1.0f;  // :195
+    memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
     memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
     memcpy(ch->prev_pos, f->camera_pos, 12);
-    ch->have_prev = true;
   }
-  memcpy(tp.prev_view_matrix, ch->prev_view, 64); memcpy(tp.prev_camera_matrix_world, ch->prev_world, 64);
-  memcpy(tp.prev_projection, ch->prev_proj, 64); memcpy(tp.prev_projection_inverse, ch->prev_proj_inv, 64);
-  memcpy(tp.camera_pos, f->camera_pos, 12); memcpy(tp.prev_camera_pos, ch->prev_pos, 12);
-  tp.max_blend = 1.0f; tp.neighborhood_clamp_intensity = 0.5f; tp.keep_data = ch->keep_data; tp.confidence_power = 0.75f;
-  tp.full_accumulate = f->camera_moved ? 0 : 1;  // options.fullAccumulate && !didCameraMove
-  tp.log_transform = 1; tp.history_linear = 1;
-  if (o.mode == RFX_MODE_SSGI) { tp.texture_count = 2; tp.input_type = RFX_INPUT_DIFFUSE_SPECULAR; tp.reproject_specular[0] = 0; tp.reproject_specular[1] = 1; }
-  else { tp.texture_count = 1; tp.input_type = RFX_INPUT_SPECULAR; tp.reproject_specular[0] = 1; tp.reproject_specular[1] = 1; }
-  const int tc = tp.texture_count;
-  { SpanGuard g(ch, cs, 1);
-    st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
-                                       tc == 2 ? &ch->tr[1] : nullptr, R0(), R1()); }
-  launch_k++;
-  if (st != RFX_OK) return st;
-  ch->keep_data = 1.0f;  // :195
-  memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
-  memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
-  memcpy(ch->prev_pos, f->camera_pos, 12);
+  k++;
   // ---- K3  PoissonDenoisePass.render (PoissonDenoisePass.js:135-149)
   rfx_poisson_params pp{};
   pp.radius = o.radius; pp.phi = o.phi; pp.luma_phi = o.luma_phi; pp.depth_phi = o.depth_phi; pp.normal_phi = o.normal_phi;
   pp.roughness_phi = o.roughness_phi; pp.specular_phi = o.specular_phi;
   pp.texture_count = tc; pp.gbuffer_texture = 1;
   if (o.mode == RFX_MODE_SSGI) { pp.is_texture_specular[0] = 0; pp.is_texture_specular[1] = 1; } else { pp.is_texture_specular[0] = 1; pp.is_texture_specular[1] = 1; }
-  for (int i = 0; i < 2 * o.denoise_iterations; i++) {
+  bool decoded = false;
+  for (int i = 0; i < 2 * o.denoise_iterations; i++, k++) {
+    if (!on(k)) continue;
     const bool horizontal = (i % 2) == 0;
     rfx_plane* inp = i == 0 ? ch->tr : (horizontal ? ch->dnB : ch->dnA);
     rfx_plane* outp = horizontal ? ch->dnA : ch->dnB;
     pp.input_linear = i == 0 ? 0 : 1;
     pp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_poisson);
-    ctx->nrd_reuse = i > 0;  // the G-buffer does not change within a frame: decode it once (pass 0), reuse it afterwards
-    { SpanGuard g(ch, cs, i == 0 ? 2 : 3);
-      st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr, R0(), R1()); }
-    launch_k++;
+    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+      ctx->nrd_reuse = decoded;  // the G-buffer does not change within a frame: decode it once, reuse it afterwards
+      SpanGuard g(ch, cs, i == 0 ? 2 : 3);
+      st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr,
+                                      R0(blk, k), R1(blk, k));
+      decoded = true;
+    }
+    ctx->nrd_reuse = false;
     if (st != RFX_OK) return st;
   }
-  ctx->nrd_reuse = false;
   // ---- K4  DenoiserComposePass.render
-  if (o.mode == RFX_MODE_SSGI) {
+  if (o.mode == RFX_MODE_SSGI && on(k)) {
     rfx_compose_params cp{};
     cp.cam = f->cam;
     cp.input_type = RFX_INPUT_DIFFUSE_SPECULAR;
-    { SpanGuard g(ch, cs, 4);
-      st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, R0(), R1()); }
+    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+      SpanGuard g(ch, cs, 4);
+      st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, R0(blk, k), R1(blk, k));
+    }
     if (st != RFX_OK) return st;
   }
   return RFX_OK;
@@ -791,15 +816,25 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
 
 rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f) {
   if (!ch || !f) return RFX_ERR_INVALID_ARG;
-  return chain_render_impl(ch, stream, f, nullptr);
+  return chain_render_impl(ch, stream, f, nullptr, 1, 0, 0xffffffffu);
+}
+static rfx_status check_ranges(rfx_ssgi_chain* ch, const uint32_t* ranges, uint32_t n_launches, uint32_t n_blocks) {
+  const uint32_t expect = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
+  if (n_launches != expect || n_blocks == 0) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: expected %u launches per block, got %u (blocks %u)", expect, n_launches, n_blocks);
+  for (uint32_t i = 0; i < n_launches * n_blocks; i++)
+    if (ranges[2 * i] >= ranges[2 * i + 1] || ranges[2 * i + 1] > ch->opt.height) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: bad range %u", i);
+  return RFX_OK;
 }
 rfx_status rfx_ssgi_chain_render_ranges(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_launches) {
   if (!ch || !f || !ranges) return RFX_ERR_INVALID_ARG;
-  const uint32_t expect = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
-  if (n_launches != expect) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_render_ranges: expected %u row ranges, got %u", expect, n_launches);
-  for (uint32_t k = 0; k < n_launches; k++)
-    if (ranges[2 * k] >= ranges[2 * k + 1] || ranges[2 * k + 1] > ch->opt.height) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_render_ranges: bad range %u", k);
-  return chain_render_impl(ch, stream, f, ranges);
+  rfx_status st = check_ranges(ch, ranges, n_launches, 1);
+  return st != RFX_OK ? st : chain_render_impl(ch, stream, f, ranges, 1, 0, 0xffffffffu);
+}
+rfx_status rfx_ssgi_chain_render_blocks(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_launches,
+                                        uint32_t n_blocks, uint32_t k_begin, uint32_t k_end) {
+  if (!ch || !f || !ranges) return RFX_ERR_INVALID_ARG;
+  rfx_status st = check_ranges(ch, ranges, n_launches, n_blocks);
+  return st != RFX_OK ? st : chain_render_impl(ch, stream, f, ranges, n_blocks, k_begin, k_end);
 }
 
 rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_frame* hf) {

@@ -1,16 +1,25 @@
 """Row-block sharding of the SSGI chain across N GPUs (one process per GPU, torch.distributed / NCCL over NVLink).
 
-Every kernel of the path writes disjoint output rows, so GPU g of N owns rows [g*H/N, (g+1)*H/N) of every produced
-plane.  Two kinds of inputs cross row-block borders:
+Every kernel of the path writes disjoint output rows, so the produced planes are partitioned by row block
+(SURVEY.md §8e).  Two kinds of inputs cross row-block borders:
 
   * bounded stencils — K2's 5x5 neighbourhood of ssgiOut (2 rows), K3's Poisson taps (ceil(radius)+1 rows per pass,
     bilinear footprint included), K4's pixel-centre bilinear fetch of dnB (1 row).  Instead of one halo exchange per
     pass, each rank RECOMPUTES the halo rows itself: pass k is launched on a row range widened by the halos of all the
     passes after it (`ShardPlan`).  Kernels are bit-identical under row sharding, so the recomputed rows equal the
-    owner's rows bit for bit, and no per-pass NCCL latency is paid.
+    owner's rows bit for bit, and no per-pass NCCL latency is paid (cost: ~1 % extra rows per block at 4K).
   * arbitrary-uv gathers — K1 samples `composed` at ray hit points and K2 samples the history `dnB[0..1]` at
     reprojected uvs anywhere on screen, so these three produced planes are all-gathered once per frame (32 B/px of each
     rank's rows).  The static inputs (depth, gBuffer, velocity, directLight) are given to every rank in full.
+
+Load balance: sky rows are nearly free (background pixels are discarded) while floor rows are the most expensive, so
+contiguous bands would leave the max-over-ranks time ~1/3 above the mean.  Rows are therefore assigned BLOCK-CYCLICALLY:
+with B blocks per rank the frame is cut into N*B blocks and rank r owns blocks r, r+N, r+2N, ...; super-block j (blocks
+j*N .. j*N+N-1) is contiguous and in rank order, so each plane is all-gathered in place with B collectives.
+
+Overlap: a frame is issued in two phases.  K1 only needs last frame's `composed`; K2..K4 need `dnB`.  The all-gathers
+are launched asynchronously after K4 (composed first); the next frame waits for the composed gather before K1 and for the
+dnB gathers only before K2, so the dnB transfer hides behind K1.
 
 The result on N GPUs is bit-identical to the single-GPU result (tests/test_sharding_cpu.py with gloo + the oracle as
 compute; tests/test_gpu_multi.py on >= 2 GPUs).
@@ -23,7 +32,8 @@ from dataclasses import dataclass
 
 @dataclass
 class ShardPlan:
-    """Row ranges [a, b) per launch of one frame, in chain order: K1, K2, K3 pass 0..n-1, K4 (SSGI mode only)."""
+    """Row ranges [a, b) per launch of one frame, in chain order: K1, K2, K3 pass 0..n-1, K4 (SSGI mode only),
+    for every row block this rank owns."""
 
     height: int
     world: int
@@ -31,23 +41,26 @@ class ShardPlan:
     n_poisson_passes: int  # 2 * denoiseIterations
     radius: float
     ssgi_mode: bool = True
+    blocks_per_rank: int = 1
 
     K2_NEIGHBOURHOOD_ROWS = 2  # 5x5 clamp window (reproject.frag:57-59)
     K4_INPUT_ROWS = 1          # literal bilinear fetch of the LINEAR Poisson targets at the pixel centre
 
     def __post_init__(self):
-        if self.height % self.world:
-            raise ValueError(f"height {self.height} is not divisible by world size {self.world}")
-        self.rows_per_rank = self.height // self.world
-        self.r0, self.r1 = self.rank * self.rows_per_rank, (self.rank + 1) * self.rows_per_rank
+        nb = self.world * self.blocks_per_rank
+        if self.height % nb:
+            raise ValueError(f"height {self.height} is not divisible by world size x blocks per rank = {nb}")
+        self.block_rows = self.height // nb
+        self.rows_per_rank = self.block_rows * self.blocks_per_rank
+        self.blocks = [((j * self.world + self.rank) * self.block_rows, (j * self.world + self.rank + 1) * self.block_rows)
+                       for j in range(self.blocks_per_rank)]
+        self.r0, self.r1 = self.blocks[0]  # (single-block plans: the contiguous band)
         self.poisson_halo = int(math.ceil(self.radius)) + 1  # taps reach ceil(radius) rows, +1 for the bilinear footprint
 
     def _expand(self, rng, rows):
         return (max(0, rng[0] - rows), min(self.height, rng[1] + rows))
 
-    @property
-    def ranges(self) -> list:
-        own = (self.r0, self.r1)
+    def ranges_for(self, own) -> list:
         n = self.n_poisson_passes
         k3 = [None] * n
         nxt = own
@@ -64,14 +77,32 @@ class ShardPlan:
         return out
 
     @property
+    def ranges(self) -> list:
+        """single-block plans: the per-launch ranges of the band"""
+        return self.ranges_for(self.blocks[0])
+
+    @property
+    def block_ranges(self) -> list:
+        """[block][launch] -> (row0, row1)"""
+        return [self.ranges_for(b) for b in self.blocks]
+
+    @property
+    def n_launches(self) -> int:
+        return 2 + self.n_poisson_passes + (1 if self.ssgi_mode else 0)
+
+    def super_block(self, j: int):
+        """rows of super-block j: N consecutive blocks, one per rank, in rank order (an in-place all-gather unit)"""
+        return (j * self.world * self.block_rows, (j + 1) * self.world * self.block_rows)
+
+    @property
     def recompute_overhead(self) -> float:
         """extra rows launched / rows owned (the price of exchanging nothing per pass)"""
-        rs = self.ranges
-        return sum((b - a) for a, b in rs) / (len(rs) * self.rows_per_rank) - 1.0
+        tot = sum((b - a) for rs in self.block_ranges for a, b in rs)
+        return tot / (self.n_launches * self.rows_per_rank) - 1.0
 
     @property
     def gathered_planes(self):
-        """chain outputs (`rfx_ssgi_chain_output` index) that are all-gathered after the frame"""
+        """chain outputs (`rfx_ssgi_chain_output` index) that are all-gathered after the frame; `composed` first"""
         return (0, 4, 5) if self.ssgi_mode else (4,)
 
 
@@ -83,9 +114,9 @@ class _CudaBytes:
 
 
 class ShardedSsgiChain:
-    """The native SSGI chain on this rank's row block of a W x H frame + the per-frame all-gather of the produced planes."""
+    """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
 
-    def __init__(self, ctx, chain_options, group=None):
+    def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 1, overlap: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -96,8 +127,9 @@ class ShardedSsgiChain:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.chain = engine.SsgiChain(ctx, chain_options)
         self.ctx = ctx
+        self.overlap = overlap
         self.plan = ShardPlan(chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
-                              chain_options.mode == abi.MODE_SSGI)
+                              chain_options.mode == abi.MODE_SSGI, blocks_per_rank)
         # a dedicated torch stream: the kernels and the NCCL collectives are ordered on it.  (A NULL stream handle means "the
         # context's own stream" to the C ABI, so torch's default stream cannot be used here.)
         self.stream = torch.cuda.Stream(device=torch.device("cuda", ctx.device))
@@ -107,18 +139,51 @@ class ShardedSsgiChain:
             nbytes = int(p.pitch) * int(p.height)
             t = torch.as_tensor(_CudaBytes(p.ptr, nbytes), device=torch.device("cuda", ctx.device))
             self._tensors[which] = (t, int(p.pitch))
+        self._pending = {}  # plane index -> [Work]: all-gathers of the previous frame not yet waited for
+
+    def _wait(self, planes):
+        for which in planes:
+            for w in self._pending.pop(which, []):
+                w.wait()  # makes self.stream wait for the collective
+
+    def _gather(self, which):
+        t, pitch = self._tensors[which]
+        works = []
+        for j, (b0, b1) in enumerate(self.plan.blocks):
+            s0, s1 = self.plan.super_block(j)
+            out = t[s0 * pitch:s1 * pitch]
+            own = t[b0 * pitch:b1 * pitch]  # in place: rank g's block lands at its own rows inside the super-block
+            works.append(self.dist.all_gather_into_tensor(out, own, group=self.group, async_op=True))
+        self._pending[which] = works
 
     def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool):
-        """Enqueues the frame on self.stream, then the all-gathers (torch's NCCL wrapper orders them after the kernels on that
-        stream and makes the stream wait for their completion)."""
-        torch = self.torch
+        """Enqueues one frame on self.stream (two phases) and the asynchronous all-gathers of its outputs."""
+        torch, plan = self.torch, self.plan
+        args = (cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
         with torch.cuda.stream(self.stream):
-            self.chain.render(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved, stream=self.stream.cuda_stream,
-                              ranges=self.plan.ranges if self.world > 1 else None)
-            if self.world > 1:
-                for which, (t, pitch) in self._tensors.items():
-                    own = t[self.plan.r0 * pitch:self.plan.r1 * pitch]
-                    self.dist.all_gather_into_tensor(t, own, group=self.group)  # in place: block g lands at rows [g*H/N, (g+1)*H/N)
+            if self.world == 1:
+                self.chain.render(*args, stream=self.stream.cuda_stream)
+                return
+            br, nl = plan.block_ranges, plan.n_launches
+            first = plan.gathered_planes[0]
+            if self.overlap and plan.ssgi_mode:
+                self._wait([first])                                   # K1 samples last frame's `composed`
+                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(0, 1))
+                self._wait(plan.gathered_planes[1:])                  # K2 samples last frame's dnB history
+                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(1, nl))
+            else:
+                self._wait(plan.gathered_planes)
+                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(0, nl))
+            for which in plan.gathered_planes:                        # `composed` first: the next frame needs it first
+                self._gather(which)
+            if not self.overlap:
+                self._wait(plan.gathered_planes)
+
+    def finish(self):
+        """wait for the outstanding all-gathers (before reading the planes or tearing down)"""
+        with self.torch.cuda.stream(self.stream):
+            self._wait(list(self._pending))
+        self.stream.synchronize()
 
     @property
     def exchange_bytes_per_frame(self) -> int:
@@ -126,4 +191,6 @@ class ShardedSsgiChain:
         return sum((len(t) // self.world) * (self.world - 1) for t, _ in self._tensors.values())
 
     def close(self):
+        if self.world > 1:
+            self.finish()
         self.chain.close()

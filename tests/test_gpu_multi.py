@@ -1,5 +1,6 @@
 """Multi-GPU test (needs >= 2 GPUs on the box; skipped otherwise): the row-sharded chain over NCCL must equal the
-single-GPU chain bit for bit on every rank (gathered planes: whole frame; other planes: the rank's own rows)."""
+single-GPU chain bit for bit on every rank (gathered planes: whole frame; other planes: the rank's own rows) — for
+contiguous bands and for block-cyclic blocks with the overlapped two-phase frame."""
 import os
 import socket
 
@@ -12,7 +13,7 @@ import chain_harness as ch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, bpr, overlap):
     import torch.distributed as dist
 
     from realism_effects_b200 import abi, engine, parallel
@@ -25,15 +26,15 @@ def _worker(rank, world, port, q):
         inp = ch.make_inputs(256, 128, 3)
         ctx = engine.Context(rank, inp.blue)
         ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
-        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o))
+        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), blocks_per_rank=bpr, overlap=overlap)
+        keep = []
         for fr in inp.frames:
             pl = [ctx.upload(fr[k]) for k in ("depth", "gbuffer", "velocity", "direct")]
+            keep.append(pl)  # inputs must outlive the asynchronously enqueued frame
             chain.render(abi.make_camera(fr["cam"]), *pl, fr["cam"]["position"], fr["moved"])
-            torch.cuda.synchronize()
-            for p in pl:
-                p.free()
+        chain.finish()
         out = {k: chain.chain.download(w).tobytes() for k, w in (("composed", 0), ("ssgi", 1), ("tr0", 2), ("dn0", 4), ("dn1", 5))}
-        q.put((rank, out, (chain.plan.r0, chain.plan.r1)))
+        q.put((rank, out, chain.plan.blocks))
         chain.close()
         ctx.close()
     finally:
@@ -41,7 +42,8 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
-def test_sharded_chain_equals_single_gpu_bit_exact(built):
+@pytest.mark.parametrize("bpr,overlap", [(1, False), (2, True)])
+def test_sharded_chain_equals_single_gpu_bit_exact(built, bpr, overlap):
     import torch.multiprocessing as mp
 
     world = 2
@@ -51,13 +53,13 @@ def test_sharded_chain_equals_single_gpu_bit_exact(built):
     s.close()
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, q, bpr, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict()
     for _ in procs:
-        rank, out, own = q.get(timeout=600)
-        res[rank] = (out, own)
+        rank, out, blocks = q.get(timeout=600)
+        res[rank] = (out, blocks)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -65,9 +67,10 @@ def test_sharded_chain_equals_single_gpu_bit_exact(built):
     inp = ch.make_inputs(256, 128, 3)
     single, _ = ch.run_cuda_chain(inp, o)
     ref = single[-1]
-    for rank, (out, (r0, r1)) in res.items():
+    for rank, (out, blocks) in res.items():
         for k in ("composed", "dn0", "dn1"):
             assert out[k] == ref[k].tobytes(), (rank, k)
         for k in ("ssgi", "tr0"):
             got = np.frombuffer(out[k], ref[k].dtype).reshape(ref[k].shape)
-            assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
+            for r0, r1 in blocks:
+                assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)

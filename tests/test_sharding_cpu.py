@@ -28,27 +28,31 @@ def test_shard_plan_ranges():
     assert ShardPlan(2160, 1, 0, 4, 3.0).ranges == [(0, 2160)] * 7               # one GPU: whole planes
     assert ShardPlan(64, 2, 1, 0, 3.0).ranges == [(30, 64), (32, 64), (32, 64)]   # denoiseIterations = 0: K1, K2, K4 only
     assert len(ShardPlan(64, 2, 0, 2, 3.0, ssgi_mode=False).ranges) == 4          # SSR: no K4
+    cyc = ShardPlan(2160, 2, 1, 4, 3.0, True, 4)                                  # block-cyclic: rank 1 of 2, 4 blocks each of 270 rows
+    assert cyc.blocks == [(270, 540), (810, 1080), (1350, 1620), (1890, 2160)] and cyc.super_block(2) == (1080, 1620)
+    assert cyc.rows_per_rank == 1080 and len(cyc.block_ranges) == 4 and cyc.block_ranges[3][-1] == (1890, 2160)
     with pytest.raises(ValueError):
         ShardPlan(2161, 8, 0, 4, 3.0)
     assert ShardPlan(2160, 8, 0, 4, 11.0).poisson_halo == 12                      # demo radius 11
 
 
-def sharded_oracle_chain(inp, o, rank, world, all_gather_rows):
-    """The chain of chain_harness.run_oracle_chain, but every pass commits only plan.ranges[k] rows into this rank's planes."""
+def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1):
+    """The chain of chain_harness.run_oracle_chain, but every pass commits only its planned rows (all owned blocks) into this rank's planes."""
     import orc
 
     H, W = inp.height, inp.width
-    plan = ShardPlan(H, world, rank, 2 * o.denoise_iterations, o.radius)
+    plan = ShardPlan(H, world, rank, 2 * o.denoise_iterations, o.radius, True, blocks_per_rank)
     env = orc.Env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
     z32, z16 = (lambda: np.zeros((H, W, 4), np.float32)), (lambda: np.zeros((H, W, 4), np.float16))
     ssgi, tr, dnA, dnB, composed = z32(), [z32(), z32()], [z16(), z16()], [z16(), z16()], z32()
     keep_data, prev, bn_t, bn_p = 0.0, None, 0, 0
 
-    def commit(dst, new, rng):
-        dst[rng[0]:rng[1]] = new[rng[0]:rng[1]]
+    def commit(dst, new, rngs_of_blocks):
+        for rng in rngs_of_blocks:
+            dst[rng[0]:rng[1]] = new[rng[0]:rng[1]]
 
     for fr in inp.frames:
-        rngs = iter(plan.ranges)
+        rngs = iter(list(zip(*plan.block_ranges)))  # per launch: the ranges of every owned block
         cam = abi.make_camera(fr["cam"])
         bn_t = ch.next_blue(o.blue_noise_start, bn_t)
         sp = ch.ssgi_params(o, cam, bn_t, (inp.env_map.shape[1], inp.env_map.shape[0]))
@@ -71,39 +75,41 @@ def sharded_oracle_chain(inp, o, rank, world, all_gather_rows):
             commit(dst[1], o1, r)
         commit(composed, orc.gi_compose(ch.compose_params(cam), fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed), next(rngs))
         for plane in (composed, dnB[0], dnB[1]):
-            all_gather_rows(plane, plan.r0, plan.r1)
+            all_gather_rows(plane, plan)
     return dict(composed=composed, dn0=dnB[0], dn1=dnB[1], tr0=tr[0], ssgi=ssgi, plan=plan)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, bpr):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         o = ch.Opts(steps=8, refine_steps=2, denoise_iterations=1)
         inp = ch.make_inputs(96, 64, 2)
 
-        def all_gather_rows(plane, r0, r1):
-            mine = torch.from_numpy(np.ascontiguousarray(plane[r0:r1]).view(np.uint8).reshape(-1))
-            parts = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(parts, mine)
-            rows = plane.shape[0] // world
-            for g, t in enumerate(parts):
-                plane[g * rows:(g + 1) * rows] = t.numpy().view(plane.dtype).reshape(rows, *plane.shape[1:])
+        def all_gather_rows(plane, plan):
+            for j, (b0, b1) in enumerate(plan.blocks):  # one collective per super-block, like ShardedSsgiChain._gather
+                mine = torch.from_numpy(np.ascontiguousarray(plane[b0:b1]).view(np.uint8).reshape(-1))
+                parts = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine)
+                s0, _ = plan.super_block(j)
+                for g, t in enumerate(parts):
+                    plane[s0 + g * plan.block_rows:s0 + (g + 1) * plan.block_rows] = t.numpy().view(plane.dtype).reshape(plan.block_rows, *plane.shape[1:])
 
-        out = sharded_oracle_chain(inp, o, rank, world, all_gather_rows)
-        q.put((rank, {k: v.tobytes() for k, v in out.items() if k != "plan"}, (out["plan"].r0, out["plan"].r1)))
+        out = sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=bpr)
+        q.put((rank, {k: v.tobytes() for k, v in out.items() if k != "plan"}, out["plan"].blocks))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_sharded_chain_equals_single_process_bit_exact():
+@pytest.mark.parametrize("bpr", [1, 2])
+def test_two_rank_sharded_chain_equals_single_process_bit_exact(bpr):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, bpr)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict()
@@ -116,9 +122,10 @@ def test_two_rank_sharded_chain_equals_single_process_bit_exact():
     o = ch.Opts(steps=8, refine_steps=2, denoise_iterations=1)
     inp = ch.make_inputs(96, 64, 2)
     ref = ch.run_oracle_chain(inp, o)[-1]
-    for rank, (planes, (r0, r1)) in results.items():
+    for rank, (planes, blocks) in results.items():
         for k in ("composed", "dn0", "dn1"):                       # gathered planes: the whole frame must match on every rank
             assert planes[k] == ref[k].tobytes(), (rank, k)
         for k in ("tr0", "ssgi"):                                  # not gathered: this rank's own rows must match
             got = np.frombuffer(planes[k], ref[k].dtype).reshape(ref[k].shape)
-            assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
+            for r0, r1 in blocks:
+                assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
