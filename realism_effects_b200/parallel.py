@@ -128,6 +128,7 @@ class ShardedSsgiChain:
         self.chain = engine.SsgiChain(ctx, chain_options)
         self.ctx = ctx
         self.overlap = overlap
+        self.coalesce = True
         self.plan = ShardPlan(chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
                               chain_options.mode == abi.MODE_SSGI, blocks_per_rank)
         # a dedicated torch stream: the kernels and the NCCL collectives are ordered on it.  (A NULL stream handle means "the
@@ -146,15 +147,29 @@ class ShardedSsgiChain:
             for w in self._pending.pop(which, []):
                 w.wait()  # makes self.stream wait for the collective
 
-    def _gather(self, which):
-        t, pitch = self._tensors[which]
-        works = []
-        for j, (b0, b1) in enumerate(self.plan.blocks):
-            s0, s1 = self.plan.super_block(j)
-            out = t[s0 * pitch:s1 * pitch]
-            own = t[b0 * pitch:b1 * pitch]  # in place: rank g's block lands at its own rows inside the super-block
-            works.append(self.dist.all_gather_into_tensor(out, own, group=self.group, async_op=True))
-        self._pending[which] = works
+    def _gather(self, planes):
+        """Launches the in-place all-gathers of `planes` as ONE coalesced NCCL group (ncclGroupStart/End: a single launch
+        instead of len(planes) x blocks_per_rank); falls back to one async collective per super-block."""
+        def calls():
+            for which in planes:
+                t, pitch = self._tensors[which]
+                for j, (b0, b1) in enumerate(self.plan.blocks):
+                    s0, s1 = self.plan.super_block(j)
+                    yield t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]  # in place: rank g's block lands at its own rows
+
+        works = None
+        cm_fn = getattr(self.dist, "_coalescing_manager", None)
+        if self.coalesce and cm_fn is not None:
+            try:
+                with cm_fn(group=self.group, device=self.torch.device("cuda", self.ctx.device), async_ops=True) as cm:
+                    for out, own in calls():
+                        self.dist.all_gather_into_tensor(out, own, group=self.group)
+                works = [cm]
+            except Exception:  # private API: keep working if its signature changes
+                self.coalesce = False
+        if works is None:
+            works = [self.dist.all_gather_into_tensor(out, own, group=self.group, async_op=True) for out, own in calls()]
+        self._pending[planes[0]] = works
 
     def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool):
         """Enqueues one frame on self.stream (two phases) and the asynchronous all-gathers of its outputs."""
@@ -174,8 +189,9 @@ class ShardedSsgiChain:
             else:
                 self._wait(plan.gathered_planes)
                 self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(0, nl))
-            for which in plan.gathered_planes:                        # `composed` first: the next frame needs it first
-                self._gather(which)
+            self._gather(plan.gathered_planes[:1])                    # `composed` first: the next frame needs it first
+            if len(plan.gathered_planes) > 1:
+                self._gather(plan.gathered_planes[1:])                # dnB[0..1]: pending under key gathered_planes[1]
             if not self.overlap:
                 self._wait(plan.gathered_planes)
 

@@ -225,10 +225,12 @@ class Frame:
     background: torch.Tensor    # (H,W) bool
 
 
-def render_frame(width: int, height: int, t: int = 0, *, device="cpu", cam_step=(0.02, 0.0, 0.0), static=False, fov: float = 40.0) -> Frame:
+def render_frame(width: int, height: int, t: int = 0, *, device="cpu", cam_step=(0.02, 0.0, 0.0), static=False, fov: float = 40.0,
+                 aspect: float | None = None) -> Frame:
     """Ray-cast frame `t`.  The camera translates by `cam_step` per frame; with
-    `static=True` it does not move (exercises fullAccumulate).  `fov` = vertical field of view in degrees."""
-    aspect = width / height
+    `static=True` it does not move (exercises fullAccumulate).  `fov` = vertical field of view in degrees; `aspect`
+    overrides width/height (non-square pixels: the same view sampled with more rows, used for weak scaling)."""
+    aspect = width / height if aspect is None else aspect
     step = (0.0, 0.0, 0.0) if static else cam_step
 
     def cam_at(k):
