@@ -154,7 +154,7 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
     # weak scaling keeps the 4K VIEW (same camera, same content mix) and samples it with N x more rows (non-square pixels), so
     # the per-pixel work statistics are those of the N = 1 frame
-    aspect = W / Hr
+    aspect = W / (args.view_height or Hr)
 
     ctx = engine.Context(local)
     env = synth.synthetic_env(1024, 512)
@@ -175,10 +175,15 @@ def run_ours(args):
         native = chain
         stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
+        force_ranges = None
+        if args.force_blocks:  # experiment: issue the frame as B row blocks (with their recomputed halos) on one GPU
+            force_ranges = parallel.ShardPlan(H, 1, 0, 2 * o.denoise_iterations, o.radius, True, args.force_blocks).block_ranges
+
         def render(i):
             j = i % len(frames)
             pl = planes[j]
-            chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True)
+            chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True,
+                         ranges=force_ranges)
     else:
         chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap)
         native = chain.chain
@@ -391,6 +396,8 @@ def main():
     ap.add_argument("--cpu-width", type=int, default=WIDTH)
     ap.add_argument("--cpu-height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-blocks", type=int, default=0, help="experiment (N = 1): issue each pass as this many row-block launches")
+    ap.add_argument("--view-height", type=int, default=0, help="experiment: rows of the VIEW (aspect = width / view_height) when --height differs")
     ap.add_argument("--blocks-per-rank", type=int, default=4, help="N > 1: block-cyclic row blocks per rank (content balance)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for all all-gathers at the end of every frame")
     args = ap.parse_args()

@@ -21,8 +21,8 @@ RFX_D v4 fetch_in(const PV& t, v2 uv) {
 template <int TC, bool GB, bool LINEAR, bool HALF>
 __global__ void __launch_bounds__(kThreads) poisson_kernel(const __grid_constant__ PoissonArgs a) {
   int x, y;
-  block_pixel(x, y, a.row0 & ~1);
-  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
   // helper pixels beyond the edge evaluate at the clamped texel (clamp-to-edge sampling)
   const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
   const v2 vUv = pixel_uv(x, y, a.W, a.H);
@@ -182,8 +182,8 @@ RFX_D void fetch2(const PoissonArgs& a, v2 uv, bool two, v3& c0, v3& c1, float* 
 template <int TC, bool LINEAR>
 __global__ void __launch_bounds__(kThreads) poisson_fast_kernel(const __grid_constant__ PoissonArgs a) {
   int x, y;
-  block_pixel(x, y, a.row0 & ~1);
-  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
   const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
   const v2 vUv = pixel_uv(x, y, a.W, a.H);
   const float depth = ld_r32f(a.depth, xc, yc);
@@ -257,8 +257,7 @@ __global__ void __launch_bounds__(kThreads) poisson_fast_kernel(const __grid_con
 }
 
 cudaError_t launch_poisson_fast(const PoissonArgs& a, cudaStream_t s) {
-  const int rb = a.row0 & ~1;
-  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   if (a.input_linear && !a.in_half) return cudaErrorInvalidValue;
   if (!a.input_linear && a.in_half) return cudaErrorNotSupported;
   if (a.texture_count == 2) {
@@ -270,8 +269,7 @@ cudaError_t launch_poisson_fast(const PoissonArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s) {
-  const int rb = a.row0 & ~1;
-  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
 #define RFX_LP(TC, GB, LIN, HALF) poisson_kernel<TC, GB, LIN, HALF><<<grid, kThreads, 0, s>>>(a)
   const bool lin = a.input_linear, half = a.in_half, gb = a.gbuffer_texture;
   if (lin && !half) return cudaErrorInvalidValue;
@@ -288,8 +286,8 @@ cudaError_t launch_poisson(const PoissonArgs& a, cudaStream_t s) {
 
 __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_constant__ ComposeArgs a) {
   int x, y;
-  block_pixel(x, y, a.row0 & ~1);
-  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
   const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
   const float depth = ld_r32f(a.depth, xc, yc);
   const float fwd = fwidth_f(depth);
@@ -350,8 +348,7 @@ __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_const
 
 cudaError_t launch_gi_compose(const ComposeArgs& a, cudaStream_t s) {
   if (a.input_type != RFX_INPUT_DIFFUSE_SPECULAR) return cudaErrorNotSupported;
-  const int rb = a.row0 & ~1;
-  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   gi_compose_kernel<<<grid, kThreads, 0, s>>>(a);
   return cudaGetLastError();
 }

@@ -285,8 +285,8 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
 template <int MODE, bool IS, bool SPARSE, bool FAST>
 __global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
   int x, y;
-  block_pixel(x, y, a.row0 & ~1);
-  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
   const uchar4 bn = __ldg(a.blue.tex + ((y + a.blue.shift.sy) % a.blue.size) * a.blue.size + ((x + a.blue.shift.sx) % a.blue.size));
   const v4 random = mk4((float)bn.x / 255.0f, (float)bn.y / 255.0f, (float)bn.z / 255.0f, (float)bn.w / 255.0f);
 
@@ -446,8 +446,7 @@ static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
 }
 
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {
-  const int rb = a.row0 & ~1;
-  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   const bool is = (a.flags & RFX_SSGI_IMPORTANCE_SAMPLING) != 0;
   if (a.mode == RFX_MODE_SSGI) {
     if (is) launch_ssgi_t<RFX_MODE_SSGI, true>(a, grid, s); else launch_ssgi_t<RFX_MODE_SSGI, false>(a, grid, s);

@@ -117,8 +117,8 @@ RFX_D v4 catmull5(const TemporalArgs& a, const PV& tex, v2 P) {
 template <int TC, int ITYPE, bool LOG, bool HLIN, bool FAST>
 __global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constant__ TemporalArgs a) {
   int x, y;
-  block_pixel(x, y, a.row0 & ~1);
-  const bool active = x < a.W && y < a.H && y >= a.row0 && y < a.row1;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
   const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
   TState s;
   s.vUv = pixel_uv(x, y, a.W, a.H);
@@ -277,8 +277,7 @@ static void launch_temporal_t(const TemporalArgs& a, dim3 grid, cudaStream_t s) 
 }
 
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t s) {
-  const int rb = a.row0 & ~1;
-  dim3 grid((a.W + kTileW - 1) / kTileW, (a.row1 - rb + kTileH - 1) / kTileH);
+  dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
 #define RFX_LT(TC, IT) do { if (a.fast) launch_temporal_t<TC, IT, true>(a, grid, s); else launch_temporal_t<TC, IT, false>(a, grid, s); } while (0)
   if (a.input_type == RFX_INPUT_DIFFUSE_SPECULAR && a.texture_count == 2) RFX_LT(2, RFX_INPUT_DIFFUSE_SPECULAR);
   else if (a.input_type == RFX_INPUT_DIFFUSE && a.texture_count == 1) RFX_LT(1, RFX_INPUT_DIFFUSE);

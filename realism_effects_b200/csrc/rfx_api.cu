@@ -44,6 +44,7 @@ struct rfx_ctx {
   int viewz_w = 0, viewz_h = 0;
   size_t viewz_pitch = 0;
   bool viewz_reuse = false;  // set by the native chain for the 2nd.. row block of a frame
+  const RowSegs* segs_override = nullptr;  // set by the native chain: all owned row blocks in ONE launch
 };
 
 static rfx_status fail(rfx_ctx* c, rfx_status st, const char* fmt, ...) {
@@ -299,6 +300,11 @@ static void rows(uint32_t row0, uint32_t row1, uint32_t H, int& r0, int& r1) {
   if (row0 == 0 && row1 == 0) { r0 = 0; r1 = (int)H; }
   else { r0 = (int)row0; r1 = (int)(row1 > H ? H : row1); }
 }
+// the row segments of a launch: [r0,r1) of the call, or the multi-block table the native chain installed for this launch
+static void set_segs(rfx_ctx* ctx, int r0, int r1, RowSegs& s) {
+  if (ctx->segs_override) s = *ctx->segs_override;
+  else s = make_segs(&r0, &r1, 1);
+}
 // mat4 * mat4 with the oracle's lowering: s = ((a0*b0 + a1*b1) + a2*b2) + a3*b3, no contraction
 static void matmul(const float* A, const float* B, float* R) {
   for (int c = 0; c < 4; c++)
@@ -359,6 +365,7 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_trace: all planes must match the output size (resolutionScale != 1 is not supported)");
   if (p->steps < 1 || p->refine_steps < 0 || (p->mode != RFX_MODE_SSGI && p->mode != RFX_MODE_SSR)) return fail(ctx, RFX_ERR_INVALID_ARG, "ssgi_trace: bad steps/mode");
   rows(row0, row1, out->height, a.row0, a.row1);
+  set_segs(ctx, a.row0, a.row1, a.segs);
   cam_to_dev(p->cam, a.cam);
   a.ray_distance = p->ray_distance; a.thickness = p->thickness; a.env_blur = p->env_blur; a.max_env_mip = p->max_env_map_mip_level;
   a.near_minus_far = p->cam.near_plane - p->cam.far_plane;  // SSGIPass.js:85-87
@@ -418,6 +425,7 @@ rfx_status rfx_temporal_reproject_launch(rfx_ctx* ctx, void* stream, const rfx_t
   if (a.input.w != a.W || a.input.h != a.H || a.velocity.w != a.W || a.velocity.h != a.H || a.hist0.w != a.W || a.hist0.h != a.H)
     return fail(ctx, RFX_ERR_SIZE_MISMATCH, "temporal: plane sizes differ");
   rows(row0, row1, out0->height, a.row0, a.row1);
+  set_segs(ctx, a.row0, a.row1, a.segs);
   cam_to_dev(p->cam, a.cam);
   memcpy(a.prev_view.m, p->prev_view_matrix, 64);
   memcpy(a.prev_world.m, p->prev_camera_matrix_world, 64);
@@ -456,6 +464,7 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
     return fail(ctx, RFX_ERR_SIZE_MISMATCH, "poisson: plane sizes differ");
   if (out0->ptr == in0->ptr || (out1 && in1 && out1->ptr == in1->ptr)) return fail(ctx, RFX_ERR_INVALID_ARG, "poisson: in-place filtering is not allowed");
   rows(row0, row1, out0->height, a.row0, a.row1);
+  set_segs(ctx, a.row0, a.row1, a.segs);
   a.radius = p->radius; a.phi = p->phi; a.luma_phi = p->luma_phi; a.depth_phi = p->depth_phi; a.normal_phi = p->normal_phi;
   a.roughness_phi = p->roughness_phi; a.specular_phi = p->specular_phi;
   a.texture_count = p->texture_count; a.spec0 = p->is_texture_specular[0]; a.spec1 = p->is_texture_specular[1];
@@ -503,6 +512,7 @@ rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_p
   if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.diffuse.w != a.W || a.specular.w != a.W || a.diffuse.h != a.H)
     return fail(ctx, RFX_ERR_SIZE_MISMATCH, "gi_compose: plane sizes differ");
   rows(row0, row1, out->height, a.row0, a.row1);
+  set_segs(ctx, a.row0, a.row1, a.segs);
   cam_to_dev(p->cam, a.cam);
   a.input_type = p->input_type;
   LAUNCHED(launch_gi_compose(a, pick(ctx, stream)));
@@ -710,6 +720,20 @@ rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* ch, int32_t which, rfx_plane* o
   return RFX_OK;
 }
 
+// installs the row-segment table of launch k (all owned blocks) for the duration of one launch call
+struct SegScope {
+  rfx_ctx* ctx;
+  RowSegs segs;
+  SegScope(rfx_ctx* c, const uint32_t* ranges, uint32_t n_blocks, uint32_t n_launches, uint32_t k) : ctx(c) {
+    if (!ranges || n_blocks <= 1) return;
+    int r0[RFX_MAX_SEGS], r1[RFX_MAX_SEGS];
+    for (uint32_t b = 0; b < n_blocks; b++) { r0[b] = (int)ranges[(b * n_launches + k) * 2]; r1[b] = (int)ranges[(b * n_launches + k) * 2 + 1]; }
+    segs = make_segs(r0, r1, (int)n_blocks);
+    ctx->segs_override = &segs;
+  }
+  ~SegScope() { ctx->segs_override = nullptr; }
+};
+
 // One frame of the chain.  `ranges` == nullptr: whole planes, one block.  Otherwise ranges[(blk*n_launches + k)*2 + {0,1}] =
 // output rows [a,b) of launch k (chain order: K1, K2, K3 pass 0..2*iterations-1, K4) for row block `blk` of this rank
 // (row-block sharding with locally recomputed halos, realism_effects_b200/parallel.py).  Only launches k in
@@ -736,7 +760,8 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
     sp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_trace);
     // velocityTexture is a null sampler in the shipped wiring
-    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+    for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
+      SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       ctx->viewz_reuse = blk > 0;  // the view-z plane depends on the depth plane only: one prepass per frame
       SpanGuard g(ch, cs, 0);
       st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, R0(blk, k), R1(blk, k));
@@ -764,7 +789,8 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     tp.log_transform = 1; tp.history_linear = 1;
     if (o.mode == RFX_MODE_SSGI) { tp.texture_count = 2; tp.input_type = RFX_INPUT_DIFFUSE_SPECULAR; tp.reproject_specular[0] = 0; tp.reproject_specular[1] = 1; }
     else { tp.texture_count = 1; tp.input_type = RFX_INPUT_SPECULAR; tp.reproject_specular[0] = 1; tp.reproject_specular[1] = 1; }
-    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+    for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
+      SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       SpanGuard g(ch, cs, 1);
       st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
                                          tc == 2 ? &ch->tr[1] : nullptr, R0(blk, k), R1(blk, k));
@@ -790,7 +816,8 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     rfx_plane* outp = horizontal ? ch->dnA : ch->dnB;
     pp.input_linear = i == 0 ? 0 : 1;
     pp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_poisson);
-    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+    for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
+      SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       ctx->nrd_reuse = decoded;  // the G-buffer does not change within a frame: decode it once, reuse it afterwards
       SpanGuard g(ch, cs, i == 0 ? 2 : 3);
       st = rfx_poisson_denoise_launch(ctx, stream, &pp, f->depth, f->gbuffer, &inp[0], tc == 2 ? &inp[1] : nullptr, &outp[0], tc == 2 ? &outp[1] : nullptr,
@@ -805,7 +832,8 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     rfx_compose_params cp{};
     cp.cam = f->cam;
     cp.input_type = RFX_INPUT_DIFFUSE_SPECULAR;
-    for (uint32_t blk = 0; blk < n_blocks && st == RFX_OK; blk++) {
+    for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
+      SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       SpanGuard g(ch, cs, 4);
       st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, R0(blk, k), R1(blk, k));
     }
@@ -820,7 +848,7 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
 }
 static rfx_status check_ranges(rfx_ssgi_chain* ch, const uint32_t* ranges, uint32_t n_launches, uint32_t n_blocks) {
   const uint32_t expect = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
-  if (n_launches != expect || n_blocks == 0) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: expected %u launches per block, got %u (blocks %u)", expect, n_launches, n_blocks);
+  if (n_launches != expect || n_blocks == 0 || n_blocks > RFX_MAX_SEGS) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: expected %u launches per block, got %u (blocks %u)", expect, n_launches, n_blocks);
   for (uint32_t i = 0; i < n_launches * n_blocks; i++)
     if (ranges[2 * i] >= ranges[2 * i + 1] || ranges[2 * i + 1] > ch->opt.height) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: bad range %u", i);
   return RFX_OK;

@@ -11,6 +11,16 @@ struct OutV {  // writable plane view
   long long pitch;
 };
 
+// Output rows of one launch: up to RFX_MAX_SEGS disjoint row segments [r0,r1) (one per row block this rank owns), covered by a
+// single grid: blockIdx.y walks the 16-row tiles of segment 0, then segment 1, ...  One launch per pass regardless of how
+// many row blocks a rank owns (a launch per block costs ~10 % in launch gaps and partial last waves).
+#define RFX_MAX_SEGS 16
+struct RowSegs {
+  int n, tiles;                  // segments, total 16-row tiles (= gridDim.y)
+  int r0[RFX_MAX_SEGS], r1[RFX_MAX_SEGS];
+  int tile0[RFX_MAX_SEGS + 1];   // first tile index of each segment
+};
+
 struct CamD {  // device copy of rfx_camera
   M4 projection, projection_inverse, camera_matrix_world, view_matrix;
   float near_plane, far_plane;
@@ -36,6 +46,7 @@ struct PoissonArgs {
   PV depth, gb, in0, in1;
   OutV out0, out1;
   int W, H, row0, row1;
+  RowSegs segs;
   float radius, phi, luma_phi, depth_phi, normal_phi, roughness_phi, specular_phi;
   int texture_count, spec0, spec1, gbuffer_texture, input_linear, in_half;
   BlueD blue;
@@ -53,6 +64,7 @@ struct ComposeArgs {
   PV depth, gb, diffuse, specular;
   OutV out;
   int W, H, row0, row1;
+  RowSegs segs;
   CamD cam;
   int input_type;
 };
@@ -70,6 +82,7 @@ struct TemporalArgs {
   PV input, velocity, hist0, hist1;
   OutV out0, out1;
   int W, H, row0, row1;
+  RowSegs segs;
   CamD cam;
   M4 prev_view, prev_world, prev_proj, prev_proj_inv;
   M4 prev_proj_view;  // prevProjectionMatrix * prevViewMatrix (reproject.frag:183), fma-lowered on the host
@@ -87,6 +100,7 @@ struct SsgiArgs {
   PV depth, gb, velocity, direct, accumulated;  // velocity/direct/accumulated may have p == nullptr
   OutV out;
   int W, H, row0, row1;
+  RowSegs segs;
   CamD cam;
   float ray_distance, thickness, env_blur, max_env_mip;
   float near_minus_far, near_mul_far, far_minus_near;
@@ -151,6 +165,31 @@ RFX_D void block_pixel(int& x, int& y, int row_base) {
   lane_to_pixel(lane, lx, ly);
   x = blockIdx.x * kTileW + ((warp & 1) << 3) + lx;
   y = row_base + blockIdx.y * kTileH + ((warp >> 1) << 2) + ly;
+}
+// pixel of this thread for a multi-segment launch; returns whether its row lies inside the segment (quads stay aligned to
+// even rows because every segment's tiles start at r0 & ~1)
+RFX_D bool seg_pixel(const RowSegs& s, int& x, int& y) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lx, ly;
+  lane_to_pixel(lane, lx, ly);
+  int k = 0;
+  const int ty = blockIdx.y;
+  while (k + 1 < s.n && ty >= s.tile0[k + 1]) k++;
+  x = blockIdx.x * kTileW + ((warp & 1) << 3) + lx;
+  y = (s.r0[k] & ~1) + (ty - s.tile0[k]) * kTileH + ((warp >> 1) << 2) + ly;
+  return y >= s.r0[k] && y < s.r1[k];
+}
+// host: build the segment table
+inline RowSegs make_segs(const int* r0, const int* r1, int n) {
+  RowSegs s{};
+  s.n = n;
+  int t = 0;
+  for (int i = 0; i < n; i++) {
+    s.r0[i] = r0[i]; s.r1[i] = r1[i]; s.tile0[i] = t;
+    t += (r1[i] - (r0[i] & ~1) + kTileH - 1) / kTileH;
+  }
+  s.tile0[n] = t;
+  s.tiles = t;
+  return s;
 }
 
 }  // namespace rfx
