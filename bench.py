@@ -150,7 +150,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ch, o = opts_for_bench()
     W, Hr = args.width, args.height          # per-rank block
-    H = Hr * world                           # global frame height (weak scaling)
+    emu = max(1, args.emulate_world) if world == 1 else 1   # experiment: one process plays rank 0 of `emu` (no exchange)
+    H = Hr * world * emu                     # global frame height (weak scaling)
     K, Wm = args.steps, args.warmup
     # weak scaling keeps the 4K VIEW (same camera, same content mix) and samples it with N x more rows (non-square pixels), so
     # the per-pixel work statistics are those of the N = 1 frame
@@ -177,7 +178,7 @@ def run_ours(args):
 
         force_ranges = None
         if args.force_blocks:  # experiment: issue the frame as B row blocks (with their recomputed halos) on one GPU
-            force_ranges = parallel.ShardPlan(H, 1, 0, 2 * o.denoise_iterations, o.radius, True, args.force_blocks).block_ranges
+            force_ranges = parallel.ShardPlan(H, emu, 0, 2 * o.denoise_iterations, o.radius, True, args.force_blocks).block_ranges
 
         def render(i):
             j = i % len(frames)
@@ -230,7 +231,7 @@ def run_ours(args):
     native.set_profiling(False)
     launches = ctx.launch_count - launches0
     ms_per_step = ms_total / K
-    mpx = W * H / 1e6
+    mpx = W * H / emu / 1e6
     value = mpx / (ms_per_step / 1e3)
 
     # ---- roofline of the dominant kernel (this rank's owned pixels / its event-timed duration) -------
@@ -396,6 +397,7 @@ def main():
     ap.add_argument("--cpu-width", type=int, default=WIDTH)
     ap.add_argument("--cpu-height", type=int, default=HEIGHT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=1, help="experiment (N = 1, with --force-blocks): play rank 0 of this many ranks")
     ap.add_argument("--force-blocks", type=int, default=0, help="experiment (N = 1): issue each pass as this many row-block launches")
     ap.add_argument("--view-height", type=int, default=0, help="experiment: rows of the VIEW (aspect = width / view_height) when --height differs")
     ap.add_argument("--blocks-per-rank", type=int, default=4, help="N > 1: block-cyclic row blocks per rank (content balance)")

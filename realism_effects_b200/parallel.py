@@ -42,9 +42,21 @@ class ShardPlan:
     radius: float
     ssgi_mode: bool = True
     blocks_per_rank: int = 1
+    mirror: bool = False  # True: odd super-blocks are assigned in REVERSE rank order (boustrophedon), see block_of()
 
     K2_NEIGHBOURHOOD_ROWS = 2  # 5x5 clamp window (reproject.frag:57-59)
     K4_INPUT_ROWS = 1          # literal bilinear fetch of the LINEAR Poisson targets at the pixel centre
+
+    def block_of(self, rank: int, j: int):
+        """rows of the block `rank` owns inside super-block j.  With `mirror`, odd super-blocks run in reverse rank order, so a
+        rank that gets the cheapest end of one super-block (sky) gets the most expensive end of the next (floor): 2 blocks per
+        rank already balance a vertical cost gradient, at half the halo recompute of a 4-block cyclic assignment."""
+        pos = (self.world - 1 - rank) if (self.mirror and j % 2 == 1) else rank
+        b = j * self.world + pos
+        return (b * self.block_rows, (b + 1) * self.block_rows)
+
+    def reversed_order(self, j: int) -> bool:
+        return self.mirror and j % 2 == 1
 
     def __post_init__(self):
         nb = self.world * self.blocks_per_rank
@@ -52,8 +64,7 @@ class ShardPlan:
             raise ValueError(f"height {self.height} is not divisible by world size x blocks per rank = {nb}")
         self.block_rows = self.height // nb
         self.rows_per_rank = self.block_rows * self.blocks_per_rank
-        self.blocks = [((j * self.world + self.rank) * self.block_rows, (j * self.world + self.rank + 1) * self.block_rows)
-                       for j in range(self.blocks_per_rank)]
+        self.blocks = [self.block_of(self.rank, j) for j in range(self.blocks_per_rank)]
         self.r0, self.r1 = self.blocks[0]  # (single-block plans: the contiguous band)
         self.poisson_halo = int(math.ceil(self.radius)) + 1  # taps reach ceil(radius) rows, +1 for the bilinear footprint
 
@@ -116,7 +127,7 @@ class _CudaBytes:
 class ShardedSsgiChain:
     """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
 
-    def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 1, overlap: bool = True):
+    def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 4, overlap: bool = True, mirror: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -130,7 +141,13 @@ class ShardedSsgiChain:
         self.overlap = overlap
         self.coalesce = True
         self.plan = ShardPlan(chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
-                              chain_options.mode == abi.MODE_SSGI, blocks_per_rank)
+                              chain_options.mode == abi.MODE_SSGI, blocks_per_rank, mirror)
+        # A mirrored (boustrophedon) assignment needs an all-gather whose output order is the reverse rank order; torch.distributed
+        # sorts the ranks of every new_group(), so that order is not expressible with NCCL collectives here.  The plan supports it
+        # (ShardPlan.block_of) for the planned peer-store exchange; the NCCL path uses the forward cyclic order.
+        self.group_rev = None
+        if self.world > 1 and mirror and blocks_per_rank > 1:
+            raise ValueError("mirror=True needs a reverse-rank-order gather, which torch.distributed process groups cannot express")
         # a dedicated torch stream: the kernels and the NCCL collectives are ordered on it.  (A NULL stream handle means "the
         # context's own stream" to the C ABI, so torch's default stream cannot be used here.)
         self.stream = torch.cuda.Stream(device=torch.device("cuda", ctx.device))
@@ -150,25 +167,33 @@ class ShardedSsgiChain:
     def _gather(self, planes):
         """Launches the in-place all-gathers of `planes` as ONE coalesced NCCL group (ncclGroupStart/End: a single launch
         instead of len(planes) x blocks_per_rank); falls back to one async collective per super-block."""
-        def calls():
+        def calls(rev):
             for which in planes:
                 t, pitch = self._tensors[which]
                 for j, (b0, b1) in enumerate(self.plan.blocks):
+                    if self.plan.reversed_order(j) != rev:
+                        continue
                     s0, s1 = self.plan.super_block(j)
-                    yield t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]  # in place: rank g's block lands at its own rows
+                    yield t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]  # in place: every rank's block lands at its own rows
 
-        works = None
+        works = []
         cm_fn = getattr(self.dist, "_coalescing_manager", None)
-        if self.coalesce and cm_fn is not None:
-            try:
-                with cm_fn(group=self.group, device=self.torch.device("cuda", self.ctx.device), async_ops=True) as cm:
-                    for out, own in calls():
-                        self.dist.all_gather_into_tensor(out, own, group=self.group)
-                works = [cm]
-            except Exception:  # private API: keep working if its signature changes
-                self.coalesce = False
-        if works is None:
-            works = [self.dist.all_gather_into_tensor(out, own, group=self.group, async_op=True) for out, own in calls()]
+        for rev, group in ((False, self.group), (True, self.group_rev)):  # reversed super-blocks gather over the reversed group
+            todo = list(calls(rev))
+            if not todo:
+                continue
+            done = False
+            if self.coalesce and cm_fn is not None:
+                try:
+                    with cm_fn(group=group, device=self.torch.device("cuda", self.ctx.device), async_ops=True) as cm:
+                        for out, own in todo:
+                            self.dist.all_gather_into_tensor(out, own, group=group)
+                    works.append(cm)
+                    done = True
+                except Exception:  # private API: keep working if its signature changes
+                    self.coalesce = False
+            if not done:
+                works += [self.dist.all_gather_into_tensor(out, own, group=group, async_op=True) for out, own in todo]
         self._pending[planes[0]] = works
 
     def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool):

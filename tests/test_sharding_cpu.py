@@ -31,6 +31,12 @@ def test_shard_plan_ranges():
     cyc = ShardPlan(2160, 2, 1, 4, 3.0, True, 4)                                  # block-cyclic: rank 1 of 2, 4 blocks each of 270 rows
     assert cyc.blocks == [(270, 540), (810, 1080), (1350, 1620), (1890, 2160)] and cyc.super_block(2) == (1080, 1620)
     assert cyc.rows_per_rank == 1080 and len(cyc.block_ranges) == 4 and cyc.block_ranges[3][-1] == (1890, 2160)
+    # every assignment (cyclic, mirrored) is a partition of the rows
+    for mirror in (False, True):
+        owned = sorted(b for r in range(4) for b in ShardPlan(2160, 4, r, 4, 3.0, True, 3, mirror).blocks)
+        assert owned[0][0] == 0 and owned[-1][1] == 2160 and all(a[1] == b[0] for a, b in zip(owned, owned[1:]))
+    m = ShardPlan(2160, 4, 0, 4, 3.0, True, 2, True)
+    assert m.blocks == [(0, 270), (1890, 2160)]                                   # mirrored: bottom-most + top-most block
     with pytest.raises(ValueError):
         ShardPlan(2161, 8, 0, 4, 3.0)
     assert ShardPlan(2160, 8, 0, 4, 11.0).poisson_halo == 12                      # demo radius 11
