@@ -148,8 +148,12 @@ RFX_D float lg2a(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) 
 RFX_D float ex2a(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #define RFX_LN2 0.69314718055994530942f
 #define RFX_LOG2E 1.44269504088896340736f
-RFX_D v3 flog1p3(v3 c) { return mk3(lg2a(c.x + 1.0f) * RFX_LN2, lg2a(c.y + 1.0f) * RFX_LN2, lg2a(c.z + 1.0f) * RFX_LN2); }
-RFX_D float flum(v3 c) { return ex2a(0.125f * lg2a(dot(mk3(0.2125f, 0.7154f, 0.0721f), c))); }
+// The colours are carried in LOG2 units: lc2 = lg2(c + 1) = log(c + 1) / ln2.  The weighted average is linear, so the final
+// exp(avg_ln) - 1 is ex2(avg_lg2) - 1 and the ln2 factor never has to be applied; the luminance pow(dot(w, ln-values), 0.125)
+// becomes ex2(0.125 * lg2(dot(w, lc2)) + 0.125 * lg2(ln2)).
+RFX_D v3 flog1p3(v3 c) { return mk3(lg2a(c.x + 1.0f), lg2a(c.y + 1.0f), lg2a(c.z + 1.0f)); }
+#define RFX_LUM_C (-0.06609580f)  /* 0.125 * log2(ln 2) */
+RFX_D float flum(v3 c2) { return ex2a(fma_(0.125f, lg2a(dot(mk3(0.2125f, 0.7154f, 0.0721f), c2)), RFX_LUM_C)); }
 
 template <bool LINEAR>
 RFX_D void fetch2(const PoissonArgs& a, v2 uv, bool two, v3& c0, v3& c1, float* alpha0 = nullptr, float* alpha1 = nullptr) {
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) poisson_fast_kernel(const __grid_con
   for (int j = 0; j < TC; j++) {
     const float inv = __frcp_rn(tw[j]);
     const v3 m = rgb[j] * inv;
-    const v3 c = mk3(ex2a(m.x * RFX_LOG2E) - 1.0f, ex2a(m.y * RFX_LOG2E) - 1.0f, ex2a(m.z * RFX_LOG2E) - 1.0f);
+    const v3 c = mk3(ex2a(m.x) - 1.0f, ex2a(m.y) - 1.0f, ex2a(m.z) - 1.0f);  // m is in log2 units
     const OutV& o = j == 0 ? a.out0 : a.out1;
     st_h4(o.p, o.pitch, x, y, mk4(c, alpha[j]));
   }
@@ -312,8 +316,10 @@ __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_const
   viewPos.z = -viewZ;
   const v3 viewDir = normalize(viewPos);
   // pixel-centre fetch of the LINEAR Poisson targets (literal bilinear, like the GL sampler)
-  const v4 dgi = tex_h4_linear(a.diffuse, vUv);
-  const v4 sgi = tex_h4_linear(a.specular, vUv);
+  // exact variant: the literal bilinear fetch a GL sampler performs at the pixel centre; fast variant: the centre texel itself
+  // (the literal weights are (1,0,0,0) up to one ulp of u*W, i.e. the two differ by <= 1.2e-4 x the neighbour contrast)
+  const v4 dgi = a.fast ? ld_h4(a.diffuse, x, y) : tex_h4_linear(a.diffuse, vUv);
+  const v4 sgi = a.fast ? ld_h4(a.specular, x, y) : tex_h4_linear(a.specular, vUv);
 
   // constructGlobalIllumination :53-107
   const float roughness = rough0 * rough0;
@@ -339,7 +345,8 @@ __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_const
   const v3 h = normalize(v + l);
   const float VoH = fmaxf(1e-6f, dot(v, h));
   const v3 f0 = mix(mk3(0.04f), diffuse, metalness);
-  const v3 F = f0 + (mk3(1.0f) - f0) * powf(1.0f - VoH, 5.0f);
+  const float omv = 1.0f - VoH, omv2 = omv * omv;
+  const v3 F = f0 + (mk3(1.0f) - f0) * (a.fast ? omv2 * omv2 * omv : powf(omv, 5.0f));
   const v3 diffuseComponent = diffuse * (1.0f - metalness) * (mk3(1.0f) - F) * xyz(dgi);
   const v3 specularComponent = xyz(sgi) * F;
   const v3 gi = diffuseComponent + specularComponent + emissive;

@@ -283,7 +283,10 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
 }
 
 template <int MODE, bool IS, bool SPARSE, bool FAST>
-__global__ void __launch_bounds__(kThreads) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
+#ifndef RFX_K1_MIN_BLOCKS
+#define RFX_K1_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
   int x, y;
   const bool in_rows = seg_pixel(a.segs, x, y);
   const bool active = x < a.W && y < a.H && in_rows;

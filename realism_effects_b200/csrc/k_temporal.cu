@@ -194,21 +194,35 @@ __global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constan
   }
   if (need_sweep) {
     if (ITYPE == RFX_INPUT_DIFFUSE_SPECULAR) {
-      // neighborUv = vUv + (dx,dy)*invTexSize lands on texel (x+dx, y+dy) (clamped): direct addressing, each texel unpacked once
+      // neighborUv = vUv + (dx,dy)*invTexSize lands on texel (x+dx, y+dy) (clamped): direct addressing.  The packed texel holds
+      // fp16 pairs and x -> fl(x - 1e-4) is monotonic, so min/max run on the packed halves (HMNMX2) and the offset is removed
+      // once at the end — same values as unpacking every texel to fp32 first, a third of the instructions.
+      const __half2 pinf = __floats2half2_rn(INFINITY, INFINITY), ninf = __floats2half2_rn(-INFINITY, -INFINITY);
+      __half2 mn_rg[2] = {pinf, pinf}, mn_ba[2] = {pinf, pinf}, mx_rg[2] = {ninf, ninf}, mx_ba[2] = {ninf, ninf};
       for (int dy = -2; dy <= 2; dy++) {
         const int ty = clampi(y + dy, a.H);
 #pragma unroll
         for (int dx = -2; dx <= 2; dx++) {
           const int tx = clampi(x + dx, a.W);
-          v4 t[2];
-          unpackTwoVec4(ld_f4(a.input, tx, ty), t[0], t[1]);
+          const float4 e = ld_f4(a.input, tx, ty);
 #pragma unroll
           for (int i = 0; i < TC; i++) {
-            const v4 nt = rs[i] != 0 ? t[1] : t[0];
+            const unsigned urg = __float_as_uint(rs[i] != 0 ? e.z : e.x), uba = __float_as_uint(rs[i] != 0 ? e.w : e.y);
+            const __half2 rg = *reinterpret_cast<const __half2*>(&urg), ba = *reinterpret_cast<const __half2*>(&uba);
             const bool inside = abs(dx) <= radius[i] && abs(dy) <= radius[i];
-            if (inside && nt.x >= 0.0f) { mn[i] = vmin(xyz(nt), mn[i]); mx[i] = vmax(xyz(nt), mx[i]); }
+            if (inside && (__low2float(rg) - RFX_NON_ZERO_OFFSET) >= 0.0f) {  // neighborTexel.r >= 0.
+              mn_rg[i] = __hmin2(mn_rg[i], rg); mx_rg[i] = __hmax2(mx_rg[i], rg);
+              mn_ba[i] = __hmin2(mn_ba[i], ba); mx_ba[i] = __hmax2(mx_ba[i], ba);
+            }
           }
         }
+      }
+#pragma unroll
+      for (int i = 0; i < TC; i++) {
+        const v3 lo = mk3(__low2float(mn_rg[i]) - RFX_NON_ZERO_OFFSET, __high2float(mn_rg[i]) - RFX_NON_ZERO_OFFSET, __low2float(mn_ba[i]) - RFX_NON_ZERO_OFFSET);
+        const v3 hi = mk3(__low2float(mx_rg[i]) - RFX_NON_ZERO_OFFSET, __high2float(mx_rg[i]) - RFX_NON_ZERO_OFFSET, __low2float(mx_ba[i]) - RFX_NON_ZERO_OFFSET);
+        mn[i] = vmin(lo, mn[i]);
+        mx[i] = vmax(hi, mx[i]);
       }
     } else {
       for (int dx = -radius[0]; dx <= radius[0]; dx++)

@@ -515,6 +515,7 @@ rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_p
   set_segs(ctx, a.row0, a.row1, a.segs);
   cam_to_dev(p->cam, a.cam);
   a.input_type = p->input_type;
+  a.fast = ctx->fast_math;
   LAUNCHED(launch_gi_compose(a, pick(ctx, stream)));
   return RFX_OK;
 }

@@ -67,6 +67,7 @@ struct ComposeArgs {
   RowSegs segs;
   CamD cam;
   int input_type;
+  int fast;
 };
 cudaError_t launch_gi_compose(const ComposeArgs& a, cudaStream_t s);
 
