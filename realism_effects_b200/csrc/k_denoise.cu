@@ -184,7 +184,10 @@ RFX_D void fetch2(const PoissonArgs& a, v2 uv, bool two, v3& c0, v3& c1, float* 
 
 // TC planes; plane j is "specular" per a.spec0/spec1; with TC == 2 plane 1 reads in1, with TC == 1 the single plane reads in0.
 template <int TC, bool LINEAR>
-__global__ void __launch_bounds__(kThreads) poisson_fast_kernel(const __grid_constant__ PoissonArgs a) {
+#ifndef RFX_K3_MIN_BLOCKS
+#define RFX_K3_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kThreads, RFX_K3_MIN_BLOCKS) poisson_fast_kernel(const __grid_constant__ PoissonArgs a) {
   int x, y;
   const bool in_rows = seg_pixel(a.segs, x, y);
   const bool active = x < a.W && y < a.H && in_rows;

@@ -12,18 +12,34 @@
 //   * when the projection matrix has the perspective sparsity pattern (detected on the host) the
 //     fma chain of `projectionMatrix * vec4(p, 1)` drops its exact-zero terms: x' = fma(P00,x,P20*z),
 //     y' = fma(P11,y,P21*z), w' = -z — bit-identical to the full chain;
-//   * the ray positions do not depend on the fetched depths, so the taps of a batch of
-//     RFX_MARCH_BATCH steps are issued together (memory-level parallelism) and tested in order.
+//   * the ray positions do not depend on the fetched depths, so the taps of a batch of RFX_MARCH_BATCH steps can be
+//     issued together and tested in order (tunable; see the sweep note at the macro).
 // All blue-noise driven transcendentals (sin/cos of 2*pi*k/255, the march step profile
 // 1-exp(-0.25 (i+b-0.5)^2)) come from small host-built tables indexed by the 8-bit noise value.
 // FAST = true additionally moves the remaining continuous transcendentals to the SFU pipe.
 #include "rfx_kernels.h"
 
+// Taps issued per march batch.  Batching trades wasted speculative taps after the first hit (plus registers) against
+// memory-level parallelism; measured on B200 at 4K (tools/sweep_k1.sh): 1 -> 1.54 ms, 2 -> 1.55, 3 -> 1.63, 4 -> 1.67, 8 -> 2.07
+// (at 4 resident blocks per SM the other warps already hide the L2 latency), so the default is a plain dependent loop.
 #ifndef RFX_MARCH_BATCH
-#define RFX_MARCH_BATCH 4
+#define RFX_MARCH_BATCH 1
+#endif
+
+// This file is compiled twice (see __graft_entry__.py): once with the IEEE contract flags (exact variant, bit-equal to the
+// oracle) and once with -DRFX_SSGI_FAST_TU -prec-div=false -prec-sqrt=false, which turns every division, reciprocal and square
+// root of the FAST instantiations into the SFU approximations (rcp/sqrt/rsqrt.approx).  The kernels live in a per-TU inner
+// namespace so the two sets of template instantiations cannot be merged by the linker.
+#ifdef RFX_SSGI_FAST_TU
+#define RFX_K1_NS k1_fast
+#define RFX_K1_FAST true
+#else
+#define RFX_K1_NS k1_exact
+#define RFX_K1_FAST false
 #endif
 
 namespace rfx {
+namespace RFX_K1_NS {
 
 #define SSGI_EPSILON 0.00001f
 #define SSGI_ONE_MINUS_EPSILON (1.0f - 0.00001f)
@@ -38,6 +54,7 @@ RFX_D float ssgi_view_z(const SsgiArgs& a, float depth) {
   return depth * a.near_minus_far - a.cam.near_plane;
 }
 
+#ifndef RFX_SSGI_FAST_TU
 // prepass: viewZ plane = getViewZ(depth), same arithmetic as the shader => bit-identical taps
 __global__ void __launch_bounds__(256) viewz_kernel(PV depth, OutV vz, int W, int H, float near_mul_far, float far_minus_near, float near_minus_far,
                                                     float near_plane, float far_plane, int perspective) {
@@ -60,6 +77,7 @@ cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) {
                                     a.cam.perspective);
   return cudaGetLastError();
 }
+#endif
 
 // viewSpaceToScreenSpace  ssgi_utils.frag:26-33  (vector / scalar = reciprocal + multiplies, see rfx_device.cuh)
 template <bool SPARSE>
@@ -261,9 +279,14 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
   v2 vel = mk2(0.0f, 0.0f);
   if (a.velocity.p) { const float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }  // :400 (null sampler => 0)
   const v2 ruv = coords - vel;
-  const v3 envColor = getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  const bool reproj_ok = ruv.x >= 0.0f && ruv.x <= 1.0f && ruv.y >= 0.0f && ruv.y <= 1.0f;
+  // FAST: a hit whose borderFactor is exactly 1 (the inner 70 % x 70 % of the screen) resolves to mix(env, rgi, 1) = env*0 + rgi = rgi
+  // for any finite env texel, so the env fetch (equirect mapping + mip select + bilinear taps) is only done when it can matter.
+  const bool inner = FAST && reproj_ok && coords.x >= 0.15f && coords.x <= 1.0f - 0.15f && coords.y >= 0.15f && coords.y <= 1.0f - 0.15f;
+  v3 envColor = mk3(0.0f);
+  if (!inner) envColor = getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v3 SSGI;
-  if (ruv.x >= 0.0f && ruv.x <= 1.0f && ruv.y >= 0.0f && ruv.y <= 1.0f) {
+  if (reproj_ok) {
     v3 rgi = mk3(0.0f);
     if (a.accumulated.p) rgi = xyz(f4v(tex_f4_nearest(a.accumulated, ruv)));
     const float saturation = getSaturation(m.diffuse);
@@ -284,7 +307,7 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
 
 template <int MODE, bool IS, bool SPARSE, bool FAST>
 #ifndef RFX_K1_MIN_BLOCKS
-#define RFX_K1_MIN_BLOCKS 3
+#define RFX_K1_MIN_BLOCKS 4  // 64 registers/thread, 4 blocks (32 warps) per SM: best of the 3..6 sweep
 #endif
 __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
   int x, y;
@@ -441,14 +464,11 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
 
 template <int MODE, bool IS>
 static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
-  if (a.proj_sparse) {
-    if (a.fast) ssgi_kernel<MODE, IS, true, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, true, false><<<grid, kThreads, 0, s>>>(a);
-  } else {
-    if (a.fast) ssgi_kernel<MODE, IS, false, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, false, false><<<grid, kThreads, 0, s>>>(a);
-  }
+  if (a.proj_sparse) ssgi_kernel<MODE, IS, true, RFX_K1_FAST><<<grid, kThreads, 0, s>>>(a);
+  else ssgi_kernel<MODE, IS, false, RFX_K1_FAST><<<grid, kThreads, 0, s>>>(a);
 }
 
-cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {
+static cudaError_t launch_ssgi_variant(const SsgiArgs& a, cudaStream_t s) {
   dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   const bool is = (a.flags & RFX_SSGI_IMPORTANCE_SAMPLING) != 0;
   if (a.mode == RFX_MODE_SSGI) {
@@ -458,5 +478,14 @@ cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {
   }
   return cudaGetLastError();
 }
+
+}  // namespace RFX_K1_NS
+
+#ifdef RFX_SSGI_FAST_TU
+cudaError_t launch_ssgi_fast(const SsgiArgs& a, cudaStream_t s) { return k1_fast::launch_ssgi_variant(a, s); }
+#else
+cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) { return k1_exact::launch_viewz(a, vz, s); }
+cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) { return a.fast ? launch_ssgi_fast(a, s) : k1_exact::launch_ssgi_variant(a, s); }
+#endif
 
 }  // namespace rfx

@@ -115,7 +115,10 @@ RFX_D v4 catmull5(const TemporalArgs& a, const PV& tex, v2 P) {
 }
 
 template <int TC, int ITYPE, bool LOG, bool HLIN, bool FAST>
-__global__ void __launch_bounds__(kThreads) temporal_kernel(const __grid_constant__ TemporalArgs a) {
+#ifndef RFX_K2_MIN_BLOCKS
+#define RFX_K2_MIN_BLOCKS 4  // tools/sweep_occupancy.sh: 2 -> 0.90 ms, 3 -> 0.71, 4 -> 0.67 at 4K
+#endif
+__global__ void __launch_bounds__(kThreads, RFX_K2_MIN_BLOCKS) temporal_kernel(const __grid_constant__ TemporalArgs a) {
   int x, y;
   const bool in_rows = seg_pixel(a.segs, x, y);
   const bool active = x < a.W && y < a.H && in_rows;
