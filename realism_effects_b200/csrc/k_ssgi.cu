@@ -26,20 +26,7 @@
 #define RFX_MARCH_BATCH 1
 #endif
 
-// This file is compiled twice (see __graft_entry__.py): once with the IEEE contract flags (exact variant, bit-equal to the
-// oracle) and once with -DRFX_SSGI_FAST_TU -prec-div=false -prec-sqrt=false, which turns every division, reciprocal and square
-// root of the FAST instantiations into the SFU approximations (rcp/sqrt/rsqrt.approx).  The kernels live in a per-TU inner
-// namespace so the two sets of template instantiations cannot be merged by the linker.
-#ifdef RFX_SSGI_FAST_TU
-#define RFX_K1_NS k1_fast
-#define RFX_K1_FAST true
-#else
-#define RFX_K1_NS k1_exact
-#define RFX_K1_FAST false
-#endif
-
 namespace rfx {
-namespace RFX_K1_NS {
 
 #define SSGI_EPSILON 0.00001f
 #define SSGI_ONE_MINUS_EPSILON (1.0f - 0.00001f)
@@ -48,13 +35,29 @@ namespace RFX_K1_NS {
 RFX_D float lum_s(v3 a) { return dot(mk3(0.2125f, 0.7154f, 0.0721f), a); }  // ssgi_utils.frag:3
 RFX_D float lg2a_(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// FAST-variant arithmetic (AP = true) for everything downstream of the per-pixel DECISIONS (diffuse/specular lottery, env-sample
+// choice): SFU reciprocal / sqrt / rsqrt, 1-2 ulp.  The decision chain itself (view position, normals, VNDF sample, Fresnel
+// weights, env-sample probability) stays IEEE in both variants: its thresholds are compared with 8-bit blue-noise values, and a
+// one-ulp change there flips the lottery for ~1e-4 of the pixels - a different ray, not a rounding difference.
+template <bool AP> RFX_D float rcp_(float x) { if (AP) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } return 1.0f / x; }
+template <bool AP> RFX_D float div_(float a, float b) { return AP ? a * rcp_<true>(b) : a / b; }
+template <bool AP> RFX_D float sqrt_(float x) { if (AP) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; } return sqrtf(x); }
+template <bool AP> RFX_D v3 normalize_(v3 a) {
+  if (AP) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dot(a, a))); return a * r; }
+  return normalize(a);
+}
+template <bool AP> RFX_D v3 vdiv_(v3 a, float s) { return a * rcp_<AP>(s); }  // vector / scalar = one reciprocal + multiplies
+template <bool AP> RFX_D float smoothstep_(float e0, float e1, float x) {
+  const float t = clampf(div_<AP>(x - e0, e1 - e0), 0.0f, 1.0f);
+  return t * t * (3.0f - 2.0f * t);
+}
+
 // getViewZ  ssgi_utils.frag:7-13
 RFX_D float ssgi_view_z(const SsgiArgs& a, float depth) {
   if (a.cam.perspective) return a.near_mul_far / (a.far_minus_near * depth - a.cam.far_plane);
   return depth * a.near_minus_far - a.cam.near_plane;
 }
 
-#ifndef RFX_SSGI_FAST_TU
 // prepass: viewZ plane = getViewZ(depth), same arithmetic as the shader => bit-identical taps
 __global__ void __launch_bounds__(256) viewz_kernel(PV depth, OutV vz, int W, int H, float near_mul_far, float far_minus_near, float near_minus_far,
                                                     float near_plane, float far_plane, int perspective) {
@@ -77,10 +80,9 @@ cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) {
                                     a.cam.perspective);
   return cudaGetLastError();
 }
-#endif
 
 // viewSpaceToScreenSpace  ssgi_utils.frag:26-33  (vector / scalar = reciprocal + multiplies, see rfx_device.cuh)
-template <bool SPARSE>
+template <bool SPARSE, bool AP>
 RFX_D v2 view_to_screen(const SsgiArgs& a, v3 p) {
   float cx, cy, cw;
   const float* M = a.cam.projection.m;
@@ -93,13 +95,14 @@ RFX_D v2 view_to_screen(const SsgiArgs& a, v3 p) {
     cy = fma_(M[1], p.x, fma_(M[5], p.y, fma_(M[9], p.z, M[13])));
     cw = fma_(M[3], p.x, fma_(M[7], p.y, fma_(M[11], p.z, M[15])));
   }
-  const float r = 1.0f / cw;
+  const float r = rcp_<AP>(cw);
   return mk2((cx * r) * 0.5f + 0.5f, (cy * r) * 0.5f + 0.5f);
 }
 
+template <bool AP>
 RFX_D v2 equirectDirectionToUv(v3 d) {  // ssgi_utils.frag:64-74
   v2 uv = mk2(atan2f(d.z, d.x), acosf(d.y));
-  uv = mk2(uv.x / (2.0f * PI_F), uv.y / PI_F);
+  uv = mk2(div_<AP>(uv.x, 2.0f * PI_F), div_<AP>(uv.y, PI_F));
   uv.x += 0.5f;
   uv.y = 1.0f - uv.y;
   return uv;
@@ -126,44 +129,50 @@ RFX_D float pow5(float x) {
 }
 template <bool FAST>
 RFX_D float F_Schlick1(float f0, float f90, float theta) { return f0 + (f90 - f0) * pow5<FAST>(1.0f - theta); }
+template <bool AP>
 RFX_D float D_GTR2(float roughness, float NoH) {  // D_GTR(roughness, NoH, 2.)
   const float a2 = roughness * roughness;
   const float t = (NoH * NoH) * (a2 * a2 - 1.0f) + 1.0f;
-  return a2 / (PI_F * (t * t));
+  return div_<AP>(a2, PI_F * (t * t));
 }
+template <bool AP>
 RFX_D float SmithG(float NDotV, float alphaG) {
   const float a = alphaG * alphaG;
   const float b = NDotV * NDotV;
-  return (2.0f * NDotV) / (NDotV + sqrtf(a + b - a * b));
+  return div_<AP>(2.0f * NDotV, NDotV + sqrt_<AP>(a + b - a * b));
 }
+template <bool AP>
 RFX_D float GGXVNDFPdf(float NoH, float NoV, float roughness) {
-  const float D = D_GTR2(roughness, NoH);
-  const float G1 = SmithG(NoV, roughness * roughness);
-  return (D * G1) / fmaxf(0.00001f, 4.0f * NoV);
+  const float D = D_GTR2<AP>(roughness, NoH);
+  const float G1 = SmithG<AP>(NoV, roughness * roughness);
+  return div_<AP>(D * G1, fmaxf(0.00001f, 4.0f * NoV));
 }
 template <bool FAST>
 RFX_D float evalDisneyDiffuse(float NoL, float NoV, float LoH, float roughness, float metalness) {
   const float FD90 = 0.5f + 2.0f * roughness * (LoH * LoH);
   const float a = F_Schlick1<FAST>(1.0f, FD90, NoL);
   const float b = F_Schlick1<FAST>(1.0f, FD90, NoV);
-  return (a * b / PI_F) * (1.0f - metalness);
+  return div_<FAST>(a * b, PI_F) * (1.0f - metalness);
 }
+template <bool AP>
 RFX_D float evalDisneySpecular(float roughness, float NoH, float NoV, float NoL) {
-  const float D = D_GTR2(roughness, NoH);
+  const float D = D_GTR2<AP>(roughness, NoH);
   float ag = 0.5f + roughness * 0.5f;
   ag = ag * ag;
   const float a2 = ag * ag;  // GeometryTerm: a2 = roughness * roughness with roughness := pow(.5 + r*.5, 2.)
-  const float G = SmithG(NoV, a2) * SmithG(NoL, a2);
-  return D * G / (4.0f * NoL * NoV);
+  const float G = SmithG<AP>(NoV, a2) * SmithG<AP>(NoL, a2);
+  return div_<AP>(D * G, 4.0f * NoL * NoV);
 }
+template <bool AP>
 RFX_D v3 cosineSampleHemisphere_cs(v3 n, float ux, float sth, float cth) {  // ssgi_utils.frag:183-191
-  const float r = sqrtf(ux);
-  const v3 b = normalize(cross(n, mk3(0.0f, 1.0f, 1.0f)));
+  const float r = sqrt_<AP>(ux);
+  const v3 b = normalize_<AP>(cross(n, mk3(0.0f, 1.0f, 1.0f)));
   const v3 t = cross(b, n);
-  return normalize(r * sth * b + sqrtf(1.0f - ux) * n + r * cth * t);
+  return normalize_<AP>(r * sth * b + sqrt_<AP>(1.0f - ux) * n + r * cth * t);
 }
+template <bool AP>
 RFX_D void calculateAngles(v3 l, v3 v, v3 n, float& NoL, float& NoH, float& LoH, float& VoH) {  // ssgi.frag:93-100
-  const v3 h = normalize(v + l);
+  const v3 h = normalize_<AP>(v + l);
   NoL = clampf(dot(n, l), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
   NoH = clampf(dot(n, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
   LoH = clampf(dot(l, h), SSGI_EPSILON, SSGI_ONE_MINUS_EPSILON);
@@ -183,27 +192,29 @@ RFX_D v3 env_trilinear(const EnvD& e, v2 uv, float lod) {
 }
 
 // getEnvColor  ssgi.frag:311-346
+template <bool AP>
 RFX_D v3 getEnvColor(const SsgiArgs& a, v3 l, float roughness, bool isDiffuseSample, bool isEnvSample) {
   if (!(a.flags & RFX_SSGI_USE_ENVMAP)) return mk3(0.0f);
-  const v3 reflectedWS = normalize(mul_dir_left(l, a.cam.view_matrix));
+  const v3 reflectedWS = normalize_<AP>(mul_dir_left(l, a.cam.view_matrix));
   float mip = a.env_blur * a.max_env_mip;
-  if (!isDiffuseSample && roughness < 0.15f) mip *= roughness / 0.15f;
-  v3 s = env_trilinear(a.env, equirectDirectionToUv(reflectedWS), mip);
+  if (!isDiffuseSample && roughness < 0.15f) mip *= div_<AP>(roughness, 0.15f);
+  v3 s = env_trilinear(a.env, equirectDirectionToUv<AP>(reflectedWS), mip);
   const float maxEnvLum = isEnvSample ? 100.0f : 25.0f;
   const float envLum = lum_s(s);
-  if (envLum > maxEnvLum) s = s * (maxEnvLum / envLum);
+  if (envLum > maxEnvLum) s = s * div_<AP>(maxEnvLum, envLum);
   return s;
 }
 
+template <bool AP>
 RFX_D float getSaturation(v3 c) {  // :348-360
   const float mx = fmaxf(fmaxf(c.x, c.y), c.z), mn = fminf(fminf(c.x, c.y), c.z);
   if (mx == mn) return 0.0f;
-  return (mx - mn) / mx;
+  return div_<AP>(mx - mn, mx);
 }
 
 // RayMarch + BinarySearch  ssgi.frag:441-503.  `dir` is l scaled in place like the shader's inout.
 // Returns the hit uv; sets hit=false and hitPos=(10e9) on a miss.
-template <bool SPARSE>
+template <bool SPARSE, bool AP>
 RFX_D v2 rayMarch(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit) {
   dir = dir * (a.ray_distance / (float)a.steps);
   v2 uv = mk2(0.0f, 0.0f);
@@ -221,7 +232,7 @@ RFX_D v2 rayMarch(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit)
       const float cs = __ldg(cs_row + (ii - 1) * 256);
       p = p + dir * cs;
       pos[k] = p;
-      uvs[k] = view_to_screen<SPARSE>(a, p);
+      uvs[k] = view_to_screen<SPARSE, AP>(a, p);
       vzs[k] = tex_r32f_nearest(a.viewz, uvs[k]);
     }
 #pragma unroll
@@ -244,12 +255,12 @@ RFX_D v2 rayMarch(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit)
   dir = dir * 0.5f;
   hitPos = hitPos - dir;
   for (int r = 0; r < a.refine_steps; r++) {
-    const v2 u = view_to_screen<SPARSE>(a, hitPos);
+    const v2 u = view_to_screen<SPARSE, AP>(a, hitPos);
     const float diff = tex_r32f_nearest(a.viewz, u) - hitPos.z;
     dir = dir * 0.5f;
     if (diff >= 0.0f) hitPos = hitPos - dir; else hitPos = hitPos + dir;
   }
-  return view_to_screen<SPARSE>(a, hitPos);
+  return view_to_screen<SPARSE, AP>(a, hitPos);
 }
 
 struct PixelMat {
@@ -264,18 +275,18 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
   const float cosTheta = fmaxf(0.0f, dot(viewNormal, l));
   if (isDiffuseSample) {
     brdf = evalDisneyDiffuse<FAST>(NoL, NoV, LoH, roughnessSq, m.metalness);
-    pdf = NoL / PI_F;
+    pdf = div_<FAST>(NoL, PI_F);
   } else {
-    brdf = evalDisneySpecular(roughnessSq, NoH, NoV, NoL);
-    pdf = GGXVNDFPdf(NoH, NoV, roughnessSq);
+    brdf = evalDisneySpecular<FAST>(roughnessSq, NoH, NoV, NoL);
+    pdf = GGXVNDFPdf<FAST>(NoH, NoV, roughnessSq);
   }
   brdf *= cosTheta;
   pdf = fmaxf(SSGI_EPSILON, pdf);
   hitPos = viewPos;
   bool hit;
-  const v2 coords = rayMarch<SPARSE>(a, l, hitPos, noiseB, hit);
+  const v2 coords = rayMarch<SPARSE, FAST>(a, l, hitPos, noiseB, hit);
   const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
-  if (!hit && !allowMissedRays) return getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  if (!hit && !allowMissedRays) return getEnvColor<FAST>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v2 vel = mk2(0.0f, 0.0f);
   if (a.velocity.p) { const float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }  // :400 (null sampler => 0)
   const v2 ruv = coords - vel;
@@ -284,17 +295,17 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
   // for any finite env texel, so the env fetch (equirect mapping + mip select + bilinear taps) is only done when it can matter.
   const bool inner = FAST && reproj_ok && coords.x >= 0.15f && coords.x <= 1.0f - 0.15f && coords.y >= 0.15f && coords.y <= 1.0f - 0.15f;
   v3 envColor = mk3(0.0f);
-  if (!inner) envColor = getEnvColor(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  if (!inner) envColor = getEnvColor<FAST>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v3 SSGI;
   if (reproj_ok) {
     v3 rgi = mk3(0.0f);
     if (a.accumulated.p) rgi = xyz(f4v(tex_f4_nearest(a.accumulated, ruv)));
-    const float saturation = getSaturation(m.diffuse);
+    const float saturation = getSaturation<FAST>(m.diffuse);
     rgi = mix(rgi, mk3(lum_s(rgi)), (1.0f - roughnessSq) * saturation * 0.4f);
     const float border = 0.15f;
-    float bf = smoothstepf(0.0f, border, coords.x) * smoothstepf(1.0f, 1.0f - border, coords.x) * smoothstepf(0.0f, border, coords.y) *
-               smoothstepf(1.0f, 1.0f - border, coords.y);
-    bf = sqrtf(bf);
+    float bf = smoothstep_<FAST>(0.0f, border, coords.x) * smoothstep_<FAST>(1.0f, 1.0f - border, coords.x) *
+               smoothstep_<FAST>(0.0f, border, coords.y) * smoothstep_<FAST>(1.0f, 1.0f - border, coords.y);
+    bf = sqrt_<FAST>(bf);
     SSGI = mix(envColor, rgi, bf);
   } else {
     return envColor;
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
   l = mul_dir_left(l, a.cam.camera_matrix_world);
   l = normalize(l);
   float NoL, NoH, LoH, VoH;
-  calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+  calculateAngles<false>(l, v, n, NoL, NoH, LoH, VoH);  // VoH feeds the lottery threshold: IEEE in both variants
 
   bool isDiffuseSample = false;
   if (MODE == RFX_MODE_SSGI) {
@@ -410,12 +421,12 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
     if (emsIsEnvSample) {
       emsPdf /= 1.0f - emsProbability;
       l = envMisDir;
-      calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+      calculateAngles<FAST>(l, v, n, NoL, NoH, LoH, VoH);
     } else {
       emsPdf = 1.0f - emsProbability;
     }
   }
-  const v3 diffuseRay = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs(viewNormal, random.x, sc.x, sc.y);
+  const v3 diffuseRay = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs<FAST>(viewNormal, random.x, sc.x, sc.y);
   const v3 specularRay = emsIsEnvSample ? envMisDir : l;
 
   v3 diffuseGI = mk3(0.0f), specularGI = mk3(0.0f), hitPos = mk3(0.0f);
@@ -423,21 +434,21 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
   bool haveDiffuse = false;
   if (MODE == RFX_MODE_SSGI && isDiffuseSample) {  // :222-242
     l = diffuseRay;
-    calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+    calculateAngles<FAST>(l, v, n, NoL, NoH, LoH, VoH);
     v3 gi = doSample<SPARSE, FAST>(a, m, viewPos, viewNormal, roughnessSq, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
     gi = gi * brdf;
-    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * (aa / (aa + bb)); } else gi = gi / pdf;
-    gi = gi / emsPdf;
+    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<FAST>(aa, aa + bb); } else gi = vdiv_<FAST>(gi, pdf);
+    gi = vdiv_<FAST>(gi, emsPdf);
     diffuseGI = mix(diffuseGI, gi, 1.0f / 1.0f);  // diffuseSamples == 1
     haveDiffuse = true;
   }
   l = specularRay;  // :246-265
-  calculateAngles(l, v, n, NoL, NoH, LoH, VoH);
+  calculateAngles<FAST>(l, v, n, NoL, NoH, LoH, VoH);
   {
     v3 gi = doSample<SPARSE, FAST>(a, m, viewPos, viewNormal, roughnessSq, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
     gi = gi * brdf;
-    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * (aa / (aa + bb)); } else gi = gi / pdf;
-    gi = gi / emsPdf;
+    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<FAST>(aa, aa + bb); } else gi = vdiv_<FAST>(gi, pdf);
+    gi = vdiv_<FAST>(gi, emsPdf);
     specularGI = mix(specularGI, gi, 1.0f / 1.0f);
   }
   const v3 specularHitPos = hitPos;
@@ -451,7 +462,8 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
   if (!(hitPos.x > 10.0e8f)) {  // :288-296
     const v3 cameraPosWS = mk3(a.cam.camera_matrix_world.m[12], a.cam.camera_matrix_world.m[13], a.cam.camera_matrix_world.m[14]);
     const v3 hitPosWS = xyz(mul(a.cam.camera_matrix_world, mk4(specularHitPos, 1.0f)));
-    rayLength = length(cameraPosWS - hitPosWS);
+    const v3 dWS = cameraPosWS - hitPosWS;
+    rayLength = sqrt_<FAST>(dot(dWS, dWS));
   }
   if (MODE == RFX_MODE_SSGI) {
     if (!haveDiffuse) diffuseGI = mk3(-1.0f);
@@ -464,11 +476,14 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
 
 template <int MODE, bool IS>
 static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
-  if (a.proj_sparse) ssgi_kernel<MODE, IS, true, RFX_K1_FAST><<<grid, kThreads, 0, s>>>(a);
-  else ssgi_kernel<MODE, IS, false, RFX_K1_FAST><<<grid, kThreads, 0, s>>>(a);
+  if (a.proj_sparse) {
+    if (a.fast) ssgi_kernel<MODE, IS, true, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, true, false><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (a.fast) ssgi_kernel<MODE, IS, false, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, false, false><<<grid, kThreads, 0, s>>>(a);
+  }
 }
 
-static cudaError_t launch_ssgi_variant(const SsgiArgs& a, cudaStream_t s) {
+cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {
   dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   const bool is = (a.flags & RFX_SSGI_IMPORTANCE_SAMPLING) != 0;
   if (a.mode == RFX_MODE_SSGI) {
@@ -478,14 +493,5 @@ static cudaError_t launch_ssgi_variant(const SsgiArgs& a, cudaStream_t s) {
   }
   return cudaGetLastError();
 }
-
-}  // namespace RFX_K1_NS
-
-#ifdef RFX_SSGI_FAST_TU
-cudaError_t launch_ssgi_fast(const SsgiArgs& a, cudaStream_t s) { return k1_fast::launch_ssgi_variant(a, s); }
-#else
-cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) { return k1_exact::launch_viewz(a, vz, s); }
-cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) { return a.fast ? launch_ssgi_fast(a, s) : k1_exact::launch_ssgi_variant(a, s); }
-#endif
 
 }  // namespace rfx

@@ -132,10 +132,12 @@ RFX_D v4 floatToVec4(float f) {  // :151-164
   r.z = fmaxf(r.z - RFX_NON_ZERO_OFFSET, 0.0f); r.w = fmaxf(r.w - RFX_NON_ZERO_OFFSET, 0.0f);
   return r;
 }
-RFX_D float mod_gl(float x, float y) { return x - y * floorf(x / y); }
+// The byte-field decodes feed floor(): they keep IEEE division (__fdiv_rn) even in a TU built with -prec-div=false, where an
+// approximate quotient one ulp below an integer would land in the wrong field.
+RFX_D float mod_gl(float x, float y) { return x - y * floorf(__fdiv_rn(x, y)); }
 // float2color(...).r / .g  = roughness / metalness  (:24-34,189-191)
 RFX_D float gb_roughness(float b) { return fmaxf(mod_gl(b, 257.0f) / 256.0f - RFX_NON_ZERO_OFFSET, 0.0f); }
-RFX_D float gb_metalness(float b) { return fmaxf(floorf(b / (257.0f * 257.0f)) / 256.0f - RFX_NON_ZERO_OFFSET, 0.0f); }
+RFX_D float gb_metalness(float b) { return fmaxf(floorf(__fdiv_rn(b, 257.0f * 257.0f)) / 256.0f - RFX_NON_ZERO_OFFSET, 0.0f); }
 RFX_D v3 decodeRGBE8(v4 rgbe) {  // :136-141
   float fExp = rgbe.w * 255.0f - 128.0f;
   return xyz(rgbe) * exp2f(fExp);

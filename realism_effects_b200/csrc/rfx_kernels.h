@@ -115,8 +115,7 @@ struct SsgiArgs {
   int proj_sparse;           // projection matrix has the perspective sparsity pattern (exact-zero terms dropped)
   int fast;                  // SFU variants of the continuous transcendentals
 };
-cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);       // dispatches on a.fast
-cudaError_t launch_ssgi_fast(const SsgiArgs& a, cudaStream_t s);  // k_ssgi.cu compiled as the fast TU (approx div/sqrt)
+cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);
 cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s);
 
 // ---- K6 / K7 / K8 / K9 -----------------------------------------------------------------------
