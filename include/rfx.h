@@ -349,6 +349,15 @@ typedef struct rfx_ssgi_host_frame {
   float* out_composed;            /* W*H*4    fp32 */
 } rfx_ssgi_host_frame;
 rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* chain, const rfx_ssgi_host_frame* frame);
+/* Pipelined form of the same path (what a per-frame caller such as EffectComposer.render would drive): submit enqueues the
+ * frame's H2D copies (copy stream, staging set frame&1), its kernels (context stream) and the D2H of `composed` (third stream),
+ * ordered by events only, and returns without waiting; frame i+1 uploads while frame i renders and frame i-1 downloads.
+ * wait_host blocks until at most max_in_flight (0 or 1) submitted frames are incomplete.  A frame's host input buffers and
+ * out_composed must stay untouched until it is complete, so a caller alternates two host buffer sets:
+ *     submit(frame i, set i&1);  wait_host(chain, 1);   // frame i-1 is complete, its set is free for frame i+1
+ * render_host(f) == submit_host(f) + wait_host(chain, 0).  Results are bit-identical to rfx_ssgi_chain_render. */
+rfx_status rfx_ssgi_chain_submit_host(rfx_ssgi_chain* chain, const rfx_ssgi_host_frame* frame);
+rfx_status rfx_ssgi_chain_wait_host(rfx_ssgi_chain* chain, int32_t max_in_flight);
 
 /* Per-pass device timing (CUDA events recorded on the launching stream around every kernel of
  * the chain).  Slots: 0 K1 trace, 1 K2 temporal, 2 K3 pass 0, 3 K3 passes >= 1, 4 K4 compose.

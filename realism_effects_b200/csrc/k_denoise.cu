@@ -219,6 +219,11 @@ __global__ void __launch_bounds__(kThreads, RFX_K3_MIN_BLOCKS) poisson_fast_kern
   // exponent (natural-log units) added for specular planes: w *= exp(-glossiness * specularPhi)
   const float specArg = -glossiness * a.specular_phi;
   const float sarg[2] = {a.spec0 ? specArg : 0.0f, a.spec1 ? specArg : 0.0f};
+  // per-pixel constants of the two per-tap exponentials, in log2 units: w*lumaFactor = ex2(A2 + sarg2 - lumaDiff*lphi2) and
+  // pow(w, 0.1) = ex2(0.1*A2) * ex2(0.1*sarg2) - the second factor does not depend on the tap, so the planes share one ex2
+  const float sarg2[2] = {sarg[0] * RFX_LOG2E, sarg[1] * RFX_LOG2E};
+  const float swd[2] = {a.spec0 ? ex2a(sarg2[0] * 0.1f) : 1.0f, a.spec1 ? ex2a(sarg2[1] * 0.1f) : 1.0f};
+  const float lphi2 = a.luma_phi * RFX_LOG2E;
   float flatness = 1.0f - fminf(fwn, 1.0f);
   flatness = flatness * flatness * 0.75f + 0.25f;
   const uchar4 bn = __ldg(a.blue.tex + ((y + a.blue.shift.sy) % a.blue.size) * a.blue.size + ((x + a.blue.shift.sx) % a.blue.size));
@@ -238,15 +243,16 @@ __global__ void __launch_bounds__(kThreads, RFX_K3_MIN_BLOCKS) poisson_fast_kern
     const float depthDiff = 10000.0f * fabsf(depth - ndepth);
     const float roughnessDiff = fabsf(roughness - nn.w);
     const float A = -normalDiff * a.normal_phi - depthDiff * a.depth_phi - roughnessDiff * a.roughness_phi;
+    const float A2 = A * RFX_LOG2E;
+    const float wdA = ex2a(A2 * 0.1f);
     v3 c[2];
     fetch2<LINEAR>(a, nuv, TC == 2, c[0], c[1]);
 #pragma unroll
     for (int j = 0; j < TC; j++) {
-      const float Aj = A + sarg[j];
       const v3 lc = flog1p3(c[j]);
       const float lumaDiff = fminf(fabsf(lumc[j] - flum(lc)), 0.5f);
-      const float wl = ex2a((Aj - lumaDiff * a.luma_phi) * RFX_LOG2E);  // w * lumaFactor
-      const float wd = ex2a(Aj * (0.1f * RFX_LOG2E));                    // pow(w, 0.1)
+      const float wl = ex2a(fma_(-lumaDiff, lphi2, A2 + sarg2[j]));  // w * lumaFactor
+      const float wd = wdA * swd[j];                                  // pow(w, 0.1)
       float w = mixf(wl, wd, age[j]) * age[j];
       w = (w < 0.0001f) ? 0.0f : w;
       rgb[j] = mk3(fma_(w, lc.x, rgb[j].x), fma_(w, lc.y, rgb[j].y), fma_(w, lc.z, rgb[j].z));

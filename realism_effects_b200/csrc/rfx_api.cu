@@ -174,14 +174,16 @@ rfx_status rfx_plane_upload(rfx_ctx* ctx, void* stream, const rfx_plane* dst, co
   if (!ctx || !dst || !dst->ptr || !host) return RFX_ERR_INVALID_ARG;
   size_t row = (size_t)dst->width * rfx_format_bytes(dst->format);
   if (host_pitch == 0) host_pitch = row;
-  CU(cudaMemcpy2DAsync(dst->ptr, dst->pitch, host, host_pitch, row, dst->height, cudaMemcpyHostToDevice, pick(ctx, stream)));
+  if (host_pitch == row && dst->pitch == row) CU(cudaMemcpyAsync(dst->ptr, host, row * dst->height, cudaMemcpyHostToDevice, pick(ctx, stream)));  // one contiguous DMA
+  else CU(cudaMemcpy2DAsync(dst->ptr, dst->pitch, host, host_pitch, row, dst->height, cudaMemcpyHostToDevice, pick(ctx, stream)));
   return RFX_OK;
 }
 rfx_status rfx_plane_download(rfx_ctx* ctx, void* stream, const rfx_plane* src, void* host, uint64_t host_pitch) {
   if (!ctx || !src || !src->ptr || !host) return RFX_ERR_INVALID_ARG;
   size_t row = (size_t)src->width * rfx_format_bytes(src->format);
   if (host_pitch == 0) host_pitch = row;
-  CU(cudaMemcpy2DAsync(host, host_pitch, src->ptr, src->pitch, row, src->height, cudaMemcpyDeviceToHost, pick(ctx, stream)));
+  if (host_pitch == row && src->pitch == row) CU(cudaMemcpyAsync(host, src->ptr, row * src->height, cudaMemcpyDeviceToHost, pick(ctx, stream)));
+  else CU(cudaMemcpy2DAsync(host, host_pitch, src->ptr, src->pitch, row, src->height, cudaMemcpyDeviceToHost, pick(ctx, stream)));
   return RFX_OK;
 }
 rfx_status rfx_host_alloc(rfx_ctx* ctx, uint64_t bytes, void** out) {
@@ -607,8 +609,13 @@ struct rfx_ssgi_chain {
   rfx_ctx* ctx;
   rfx_ssgi_chain_options opt;
   rfx_plane ssgi_out{}, tr[2]{}, dnA[2]{}, dnB[2]{}, composed{};
-  rfx_plane in_depth{}, in_gb{}, in_vel{}, in_direct{};  // staging for the host-buffer entry point
+  // host-buffer entry points: two staging sets so frame i+1 uploads while frame i renders; H2D, kernels and D2H each get
+  // their own stream and are ordered by events only (see rfx_ssgi_chain_submit_host)
+  rfx_plane in_depth[2]{}, in_gb[2]{}, in_vel[2]{}, in_direct[2]{};
   bool have_staging = false;
+  cudaStream_t s_up = nullptr, s_dn = nullptr;
+  cudaEvent_t ev_up[2]{}, ev_rendered[2]{}, ev_dn[2]{};
+  uint64_t host_submitted = 0;
   // cross-frame state (TemporalReprojectPass.js:203-213)
   bool have_prev = false;
   float prev_view[16], prev_world[16], prev_proj[16], prev_proj_inv[16], prev_pos[3];
@@ -661,9 +668,14 @@ void rfx_ssgi_chain_destroy(rfx_ssgi_chain* ch) {
   if (!ch) return;
   rfx_ctx* ctx = ch->ctx;
   cudaStreamSynchronize(ctx->stream);
+  if (ch->s_up) cudaStreamSynchronize(ch->s_up);
+  if (ch->s_dn) cudaStreamSynchronize(ch->s_dn);
   rfx_plane* all[] = {&ch->ssgi_out, &ch->tr[0], &ch->tr[1], &ch->dnA[0], &ch->dnA[1], &ch->dnB[0], &ch->dnB[1], &ch->composed,
-                      &ch->in_depth, &ch->in_gb, &ch->in_vel, &ch->in_direct};
+                      &ch->in_depth[0], &ch->in_gb[0], &ch->in_vel[0], &ch->in_direct[0], &ch->in_depth[1], &ch->in_gb[1], &ch->in_vel[1], &ch->in_direct[1]};
   for (rfx_plane* p : all) if (p->ptr) rfx_plane_free(ctx, p);
+  for (int i = 0; i < 2; i++) for (cudaEvent_t e : {ch->ev_up[i], ch->ev_rendered[i], ch->ev_dn[i]}) if (e) cudaEventDestroy(e);
+  if (ch->s_up) cudaStreamDestroy(ch->s_up);
+  if (ch->s_dn) cudaStreamDestroy(ch->s_dn);
   for (auto& sp : ch->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (cudaEvent_t e : ch->event_pool) cudaEventDestroy(e);
   delete ch;
@@ -866,28 +878,72 @@ rfx_status rfx_ssgi_chain_render_blocks(rfx_ssgi_chain* ch, void* stream, const 
   return st != RFX_OK ? st : chain_render_impl(ch, stream, f, ranges, n_blocks, k_begin, k_end);
 }
 
-rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_frame* hf) {
+// Host-buffer path.  submit enqueues one frame and returns: the four input planes go H2D on a copy stream into staging set
+// (frame & 1), the chain runs on the context stream once that upload's event fires, and `composed` goes D2H on a third stream once
+// the frame's last kernel is done.  Frame i+1 therefore uploads (and frame i-1 downloads) while frame i renders; PCIe is full
+// duplex, so steady-state time per frame is max(H2D, kernels, D2H) instead of their sum.  Hazards, all resolved on the device:
+//   staging set reuse   - the upload of frame i+2 waits for frame i's kernels (ev_rendered);
+//   `composed` reuse    - K4 of frame i+1 (the only writer) waits for frame i's D2H (ev_dn); K1 of frame i+1 only reads it.
+rfx_status rfx_ssgi_chain_submit_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_frame* hf) {
   if (!ch || !hf || !hf->depth || !hf->gbuffer || !hf->velocity || !hf->out_composed) return RFX_ERR_INVALID_ARG;
   rfx_ctx* ctx = ch->ctx;
   rfx_status st = RFX_OK;
   if (!ch->have_staging) {
     auto alloc = [&](int fmt, rfx_plane* p) { if (st == RFX_OK) st = rfx_plane_alloc(ctx, fmt, ch->opt.width, ch->opt.height, p); };
-    alloc(RFX_FMT_R32F, &ch->in_depth); alloc(RFX_FMT_RGBA32F, &ch->in_gb); alloc(RFX_FMT_RGBA32F, &ch->in_vel); alloc(RFX_FMT_RGBA16F, &ch->in_direct);
+    for (int i = 0; i < 2; i++) {
+      alloc(RFX_FMT_R32F, &ch->in_depth[i]); alloc(RFX_FMT_RGBA32F, &ch->in_gb[i]); alloc(RFX_FMT_RGBA32F, &ch->in_vel[i]); alloc(RFX_FMT_RGBA16F, &ch->in_direct[i]);
+    }
     if (st != RFX_OK) return st;
+    CU(cudaStreamCreateWithFlags(&ch->s_up, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ch->s_dn, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&ch->ev_up[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ch->ev_rendered[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ch->ev_dn[i], cudaEventDisableTiming));
+    }
     ch->have_staging = true;
   }
-  if ((st = rfx_plane_upload(ctx, nullptr, &ch->in_depth, hf->depth, 0)) != RFX_OK) return st;
-  if ((st = rfx_plane_upload(ctx, nullptr, &ch->in_gb, hf->gbuffer, 0)) != RFX_OK) return st;
-  if ((st = rfx_plane_upload(ctx, nullptr, &ch->in_vel, hf->velocity, 0)) != RFX_OK) return st;
-  if (hf->direct_light && (st = rfx_plane_upload(ctx, nullptr, &ch->in_direct, hf->direct_light, 0)) != RFX_OK) return st;
+  const int set = (int)(ch->host_submitted & 1);
+  if (ch->host_submitted >= 2) CU(cudaStreamWaitEvent(ch->s_up, ch->ev_rendered[set], 0));
+  if ((st = rfx_plane_upload(ctx, ch->s_up, &ch->in_depth[set], hf->depth, 0)) != RFX_OK) return st;
+  if ((st = rfx_plane_upload(ctx, ch->s_up, &ch->in_gb[set], hf->gbuffer, 0)) != RFX_OK) return st;
+  if (hf->direct_light && (st = rfx_plane_upload(ctx, ch->s_up, &ch->in_direct[set], hf->direct_light, 0)) != RFX_OK) return st;
+  if ((st = rfx_plane_upload(ctx, ch->s_up, &ch->in_vel[set], hf->velocity, 0)) != RFX_OK) return st;
+  CU(cudaEventRecord(ch->ev_up[set], ch->s_up));
+  CU(cudaStreamWaitEvent(ctx->stream, ch->ev_up[set], 0));
   rfx_ssgi_frame f{};
   f.cam = hf->cam;
-  f.depth = &ch->in_depth; f.gbuffer = &ch->in_gb; f.velocity = &ch->in_vel; f.direct_light = hf->direct_light ? &ch->in_direct : nullptr;
+  f.depth = &ch->in_depth[set]; f.gbuffer = &ch->in_gb[set]; f.velocity = &ch->in_vel[set]; f.direct_light = hf->direct_light ? &ch->in_direct[set] : nullptr;
   memcpy(f.camera_pos, hf->camera_pos, 12);
   f.camera_moved = hf->camera_moved;
-  if ((st = rfx_ssgi_chain_render(ch, nullptr, &f)) != RFX_OK) return st;
-  if ((st = rfx_plane_download(ctx, nullptr, &ch->composed, hf->out_composed, 0)) != RFX_OK) return st;
-  return rfx_ctx_sync(ctx);
+  const uint32_t n_launches = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
+  const uint32_t split = ch->opt.mode == RFX_MODE_SSGI ? n_launches - 1 : 0;  // K4 is the only launch that writes `composed`
+  if (split && (st = chain_render_impl(ch, nullptr, &f, nullptr, 1, 0, split)) != RFX_OK) return st;
+  if (ch->host_submitted >= 1) CU(cudaStreamWaitEvent(ctx->stream, ch->ev_dn[set ^ 1], 0));
+  if ((st = chain_render_impl(ch, nullptr, &f, nullptr, 1, split, 0xffffffffu)) != RFX_OK) return st;
+  CU(cudaEventRecord(ch->ev_rendered[set], ctx->stream));
+  CU(cudaStreamWaitEvent(ch->s_dn, ch->ev_rendered[set], 0));
+  if ((st = rfx_plane_download(ctx, ch->s_dn, &ch->composed, hf->out_composed, 0)) != RFX_OK) return st;
+  CU(cudaEventRecord(ch->ev_dn[set], ch->s_dn));
+  ch->host_submitted++;
+  return RFX_OK;
+}
+
+// Blocks until at most `max_in_flight` (0 or 1) of the submitted frames are still incomplete.  A complete frame's out_composed is
+// filled and its input buffers may be overwritten.  Frames complete in submission order.
+rfx_status rfx_ssgi_chain_wait_host(rfx_ssgi_chain* ch, int32_t max_in_flight) {
+  if (!ch || max_in_flight < 0) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = ch->ctx;
+  if (ch->host_submitted == 0 || !ch->have_staging) return RFX_OK;
+  if (max_in_flight == 0) { CU(cudaEventSynchronize(ch->ev_dn[(ch->host_submitted - 1) & 1])); }
+  else if (max_in_flight == 1 && ch->host_submitted >= 2) { CU(cudaEventSynchronize(ch->ev_dn[(ch->host_submitted - 2) & 1])); }
+  return RFX_OK;
+}
+
+// synchronous form: one frame in, its result out
+rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_frame* hf) {
+  rfx_status st = rfx_ssgi_chain_submit_host(ch, hf);
+  return st != RFX_OK ? st : rfx_ssgi_chain_wait_host(ch, 0);
 }
 
 }  // extern "C"

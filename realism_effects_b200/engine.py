@@ -259,3 +259,10 @@ class SsgiChain:
 
     def render_host(self, hf: abi.SsgiHostFrame):
         self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_host(self.h, C.byref(hf)))
+
+    def submit_host(self, hf: abi.SsgiHostFrame):
+        """Pipelined host path: enqueue H2D -> chain -> D2H for one frame and return (include/rfx.h: rfx_ssgi_chain_submit_host)."""
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_submit_host(self.h, C.byref(hf)))
+
+    def wait_host(self, max_in_flight: int = 0):
+        self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_wait_host(self.h, int(max_in_flight)))

@@ -1,5 +1,6 @@
 """GPU parity of the whole SSGI chain (K1 -> K2 -> K3 x n -> K4) through the C ABI vs the oracle, for both kernel
 variants: fast_math=True (SFU lg2/ex2; the default, what bench.py times) and fast_math=False (exact libm, bit-level)."""
+import numpy as np
 import pytest
 
 import chain_harness as ch
@@ -35,3 +36,42 @@ def test_static_camera_full_accumulate(built):
             c = ch.compare(ref[t][k], got[t][k])
             assert c["frac_bad"] <= 1e-2 and ch.compare(ref[t][k], got[t][k], rtol=4e-3)["frac_bad"] <= 2e-3, (t, k, c)  # chain-level bar, see chain_harness
     assert got[3]["tr0"][..., 3].max() > got[1]["tr0"][..., 3].max()
+
+
+def test_host_buffer_paths_match_device_path(built):
+    """rfx_ssgi_chain_render_host and the pipelined submit_host / wait_host pair give, frame for frame, the bytes of the
+    device-plane path (same kernels, only the copies and the stream/event ordering differ)."""
+    import ctypes as C
+
+    from realism_effects_b200 import abi, engine
+
+    o = ch.Opts(denoise_iterations=1)
+    inp = ch.make_inputs(160, 96, 5)
+    want, _ = ch.run_cuda_chain(inp, o, capture=("composed",))
+    for pipelined in (False, True):
+        ctx = engine.Context(0, inp.blue)
+        try:
+            ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+            chain = engine.SsgiChain(ctx, ch.chain_options(inp, o))
+            outs = [np.zeros((inp.height, inp.width, 4), np.float32) for _ in inp.frames]
+            keep = []
+            for i, fr in enumerate(inp.frames):
+                hf = abi.SsgiHostFrame()
+                hf.cam = abi.make_camera(fr["cam"])
+                bufs = [np.ascontiguousarray(fr[k]) for k in ("depth", "gbuffer", "velocity", "direct")]
+                keep.append(bufs)  # pageable host memory is fine (slower, still ordered); buffers stay alive until the frame completed
+                hf.depth, hf.gbuffer, hf.velocity, hf.direct_light = (b.ctypes.data_as(C.c_void_p).value for b in bufs)
+                hf.camera_pos[:] = [float(x) for x in fr["cam"]["position"]]
+                hf.camera_moved = int(fr["moved"])
+                hf.out_composed = outs[i].ctypes.data_as(C.c_void_p).value
+                if pipelined:
+                    chain.submit_host(hf)
+                    chain.wait_host(1)
+                else:
+                    chain.render_host(hf)
+            chain.wait_host(0)
+            for i in range(len(inp.frames)):
+                assert outs[i].tobytes() == want[i]["composed"].tobytes(), f"frame {i} pipelined={pipelined}"
+            chain.close()
+        finally:
+            ctx.close()
