@@ -277,26 +277,21 @@ def run_ours(args):
         def e2e_drain():
             chain.wait_host(0)
     else:
-        plan = chain.plan
-        out_host = torch.empty((Hr, W, 4), dtype=torch.float32).pin_memory()
-        comp = chain.chain.output(0)
-        comp_t = torch.as_tensor(parallel._CudaBytes(comp.ptr, int(comp.pitch) * int(comp.height)), device=dev).view(torch.float32).view(H, -1)[:, :W * 4].view(H, W, 4)
+        # sharded host path (parallel.ShardedSsgiChain.submit_host): each rank uploads its own rows of depth / velocity and the
+        # K1-range rows of gbuffer / direct light, the two sampled-anywhere planes are all-gathered over NVLink, and the rank
+        # reads back its own rows of `composed`; two frames in flight
+        outs = [torch.empty((Hr, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        out_host = outs[0]
+        h2d = chain.host_bytes_per_frame[0]
 
         def e2e_step(i):
             j = i % 2
-            with torch.cuda.stream(chain.stream):
-                for k in ("depth", "gbuffer", "velocity", "direct"):
-                    frames[j][k].copy_(host[j][k], non_blocking=True)  # every rank needs the full input planes (K1 taps anywhere)
-            render(i)
-            with torch.cuda.stream(chain.stream):
-                off = 0
-                for b0, b1 in plan.blocks:  # this rank's rows of `composed`
-                    out_host[off:off + (b1 - b0)].copy_(comp_t[b0:b1], non_blocking=True)
-                    off += b1 - b0
-            chain.finish()
+            chain.submit_host(cams[j], host[j], frames[j]["cam"]["position"], True, outs[j])
+            chain.wait_host(1)
 
         def e2e_drain():
-            pass
+            chain.wait_host(0)
+            chain.finish()
     d2h = out_host.numel() * 4
     for i in range(3):
         e2e_step(i)

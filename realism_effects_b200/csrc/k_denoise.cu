@@ -118,17 +118,25 @@ __global__ void __launch_bounds__(kThreads) poisson_kernel(const __grid_constant
 // per pixel per frame.  For the velocity-layout variant (no GBUFFER_TEXTURE) roughness decodes the
 // null-sampler texel (0,0,0,1) => 0 and the normal comes from .b.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gbuffer_decode_kernel(PV gb, OutV nrd, int W, int H, int gbuffer_texture) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= W || y >= H) return;
+__global__ void __launch_bounds__(256) gbuffer_decode_kernel(PV gb, OutV nrd, int W, int row0, int row1, int gbuffer_texture) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= row1) return;
   const float4 g = ld_f4(gb, x, y);
   const v3 n = unpackNormal(gbuffer_texture ? g.y : g.z);
   const float r = gbuffer_texture ? gb_roughness(g.z) : gb_roughness(0.0f);
   st_f4(nrd.p, nrd.pitch, x, y, make_float4(n.x, n.y, n.z, r));
 }
-cudaError_t launch_gbuffer_decode(PV gb, OutV nrd, int W, int H, int gbuffer_texture, cudaStream_t s) {
-  dim3 grid((W + 31) / 32, (H + 7) / 8);
-  gbuffer_decode_kernel<<<grid, 256, 0, s>>>(gb, nrd, W, H, gbuffer_texture);
+// Decodes the rows the Poisson taps of `segs` can reach: every output segment widened by `halo` rows (ceil(radius) + 1: tap offsets
+// are at most `radius` pixels, + 1 for the quad-derivative helper row).  A rank that owns a few row blocks of a tall frame decodes
+// those bands only, not the whole plane.
+cudaError_t launch_gbuffer_decode(PV gb, OutV nrd, int W, int H, int gbuffer_texture, const RowSegs& segs, int halo, cudaStream_t s) {
+  for (int k = 0; k < segs.n; k++) {
+    int r0 = max(0, segs.r0[k] - halo), r1 = min(H, segs.r1[k] + halo);
+    if (k > 0) r0 = max(r0, min(H, segs.r1[k - 1] + halo));  // segments are ascending: skip rows the previous band already covered
+    if (r0 >= r1) continue;
+    dim3 grid((W + 31) / 32, (r1 - r0 + 7) / 8);
+    gbuffer_decode_kernel<<<grid, 256, 0, s>>>(gb, nrd, W, r0, r1, gbuffer_texture);
+  }
   return cudaGetLastError();
 }
 

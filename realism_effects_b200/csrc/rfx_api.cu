@@ -490,7 +490,8 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
     ctx->nrd_w = a.W; ctx->nrd_h = a.H;
     ctx->nrd_reuse = false;
   }
-  if (!ctx->nrd_reuse) LAUNCHED(launch_gbuffer_decode(a.gb, OutV{(unsigned char*)ctx->nrd, (long long)ctx->nrd_pitch}, a.W, a.H, 1, pick(ctx, stream)));
+  if (!ctx->nrd_reuse)  // (the chain's first pass of a frame has the widest rows of all its passes, so its decode serves the later ones)
+    LAUNCHED(launch_gbuffer_decode(a.gb, OutV{(unsigned char*)ctx->nrd, (long long)ctx->nrd_pitch}, a.W, a.H, 1, a.segs, (int)std::ceil(p->radius) + 1, pick(ctx, stream)));
   a.nrd = PV{(const unsigned char*)ctx->nrd, a.W, a.H, (long long)ctx->nrd_pitch};
   {
     const float SQ = 1.41421356237f;

@@ -112,6 +112,13 @@ class ShardPlan:
         return tot / (self.n_launches * self.rows_per_rank) - 1.0
 
     @property
+    def local_input_rows(self) -> list:
+        """Rows of the PER-PIXEL input planes (G-buffer, direct light) this rank reads: the K1 range of each block, which contains
+        every later launch's range and the rows its Poisson taps reach.  The planes sampled at arbitrary screen positions (depth:
+        ray-march taps; velocity: reprojected uv) are needed whole and are all-gathered from the ranks' own rows instead."""
+        return [rs[0] for rs in self.block_ranges]
+
+    @property
     def gathered_planes(self):
         """chain outputs (`rfx_ssgi_chain_output` index) that are all-gathered after the frame; `composed` first"""
         return (0, 4, 5) if self.ssgi_mode else (4,)
@@ -124,6 +131,13 @@ class _CudaBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+class _PlaneRef:
+    """adapter: SsgiChain.render takes objects with a `.p` rfx_plane"""
+
+    def __init__(self, p):
+        self.p = p
+
+
 class ShardedSsgiChain:
     """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
 
@@ -134,6 +148,7 @@ class ShardedSsgiChain:
         from . import abi, engine
 
         self.dist, self.torch, self.group = dist, torch, group
+        self._abi = abi
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.chain = engine.SsgiChain(ctx, chain_options)
@@ -225,6 +240,127 @@ class ShardedSsgiChain:
         with self.torch.cuda.stream(self.stream):
             self._wait(list(self._pending))
         self.stream.synchronize()
+
+    # ---- host-buffer path ------------------------------------------------------------------------------------------------
+    # Every rank holds (or maps) the frame's host planes but moves only its share over PCIe: its own rows of depth and velocity -
+    # the two planes sampled anywhere on screen - which are then all-gathered over NVLink (own communicator, so the gather of
+    # frame i+1 is not queued behind frame i's output gathers), and the K1-range rows of the G-buffer and direct light.  H2D,
+    # kernels and D2H run on three streams with two staging sets, like rfx_ssgi_chain_submit_host on one GPU.
+    INPUTS = (("depth", 4, True), ("gbuffer", 16, False), ("velocity", 16, True), ("direct", 8, False))  # name, bytes/px, gathered
+
+    def _host_init(self):
+        torch, abi = self.torch, self._abi
+        dev = torch.device("cuda", self.ctx.device)
+        W, H = self.chain.opt.width, self.chain.opt.height
+        fmts = dict(depth=abi.FMT_R32F, gbuffer=abi.FMT_RGBA32F, velocity=abi.FMT_RGBA32F, direct=abi.FMT_RGBA16F)
+        self._in = []
+        for _ in range(2):
+            st = {}
+            for name, bpp, _g in self.INPUTS:
+                t = torch.zeros(H * W * bpp, dtype=torch.uint8, device=dev)
+                pl = abi.Plane()
+                pl.ptr, pl.width, pl.height, pl.pitch, pl.format = t.data_ptr(), W, H, W * bpp, fmts[name]
+                st[name] = (t, pl, W * bpp)
+            self._in.append(st)
+        self._out_dev = [torch.empty(self.plan.rows_per_rank * W * 16, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.up_stream, self.dn_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._ev_up = [torch.cuda.Event() for _ in range(2)]
+        self._ev_rendered = [torch.cuda.Event() for _ in range(2)]
+        self._ev_dn = [torch.cuda.Event() for _ in range(2)]
+        self.in_group = self.dist.new_group(ranks=list(range(self.world))) if self.world > 1 else None
+        self._host_frames = 0
+
+    def submit_host(self, cam, host: dict, camera_pos, camera_moved: bool, out_host):
+        """One frame from host planes (dict name -> CPU tensor of the FULL frame, pinned for asynchronous copies) to this rank's
+        rows of `composed` in out_host (CPU float32 tensor (rows_per_rank, W, 4), blocks in plan order).  Returns after enqueueing."""
+        torch, plan = self.torch, self.plan
+        if not hasattr(self, "_in"):
+            self._host_init()
+        W, H = self.chain.opt.width, self.chain.opt.height
+        k = self._host_frames & 1
+        st = self._in[k]
+        works = []
+        with torch.cuda.stream(self.up_stream):
+            if self._host_frames >= 2:
+                self.up_stream.wait_event(self._ev_rendered[k])   # frame i-2 no longer reads this staging set
+            for name, bpp, gathered in self.INPUTS:
+                if name not in host or host[name] is None:
+                    continue
+                t, _pl, pitch = st[name]
+                dev2d, host2d = t.view(H, pitch), host[name].view(torch.uint8).view(H, pitch)
+                for a, b in (plan.blocks if (gathered and self.world > 1) else plan.local_input_rows if self.world > 1 else [(0, H)]):
+                    dev2d[a:b].copy_(host2d[a:b], non_blocking=True)
+            self._ev_up[k].record(self.up_stream)
+            if self.world > 1:
+                todo = []
+                for name, bpp, gathered in self.INPUTS:
+                    if gathered and host.get(name) is not None:
+                        t, _pl, pitch = st[name]
+                        for j, (b0, b1) in enumerate(plan.blocks):
+                            s0, s1 = plan.super_block(j)
+                            todo.append((t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]))
+                works = self._all_gather(todo, self.in_group)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._ev_up[k])
+            for w in works:
+                w.wait()
+        pw = lambda n: _PlaneRef(st[n][1]) if host.get(n) is not None else None  # noqa: E731
+        self.render(cam, pw("depth"), pw("gbuffer"), pw("velocity"), pw("direct"), camera_pos, camera_moved)
+        comp, cpitch = self._composed()
+        with torch.cuda.stream(self.stream):
+            # snapshot this rank's rows of `composed`, so the next frame's K4 may overwrite them while the D2H copy still runs
+            out2d, off = self._out_dev[k].view(plan.rows_per_rank, W * 16), 0
+            for b0, b1 in plan.blocks:
+                out2d[off:off + (b1 - b0)].copy_(comp.view(H, cpitch)[b0:b1, :W * 16], non_blocking=True)
+                off += b1 - b0
+            self._ev_rendered[k].record(self.stream)
+        with torch.cuda.stream(self.dn_stream):
+            self.dn_stream.wait_event(self._ev_rendered[k])
+            out_host.view(torch.uint8).view(-1).copy_(self._out_dev[k], non_blocking=True)
+            self._ev_dn[k].record(self.dn_stream)
+        self._host_frames += 1
+
+    def wait_host(self, max_in_flight: int = 0):
+        """Blocks until at most max_in_flight (0 or 1) submitted frames are incomplete (their out_host rows not yet written)."""
+        n = getattr(self, "_host_frames", 0)
+        if n == 0:
+            return
+        if max_in_flight <= 0:
+            self._ev_dn[(n - 1) & 1].synchronize()
+        elif n >= 2:
+            self._ev_dn[(n - 2) & 1].synchronize()
+
+    def _composed(self):
+        if 0 in self._tensors:
+            return self._tensors[0]
+        p = self.chain.output(0)
+        t = self.torch.as_tensor(_CudaBytes(p.ptr, int(p.pitch) * int(p.height)), device=self.torch.device("cuda", self.ctx.device))
+        self._tensors[0] = (t, int(p.pitch))
+        return self._tensors[0]
+
+    def _all_gather(self, todo, group):
+        """in-place all-gathers [(out, own)] as one coalesced NCCL group when the private coalescing API is usable"""
+        if not todo:
+            return []
+        cm_fn = getattr(self.dist, "_coalescing_manager", None)
+        if self.coalesce and cm_fn is not None:
+            try:
+                with cm_fn(group=group, device=self.torch.device("cuda", self.ctx.device), async_ops=True) as cm:
+                    for out, own in todo:
+                        self.dist.all_gather_into_tensor(out, own, group=group)
+                return [cm]
+            except Exception:
+                self.coalesce = False
+        return [self.dist.all_gather_into_tensor(out, own, group=group, async_op=True) for out, own in todo]
+
+    @property
+    def host_bytes_per_frame(self):
+        """(H2D, D2H) bytes this rank moves per frame on the host path"""
+        W = self.chain.opt.width
+        own = self.plan.rows_per_rank if self.world > 1 else self.chain.opt.height
+        loc = sum(b - a for a, b in self.plan.local_input_rows) if self.world > 1 else self.chain.opt.height
+        h2d = sum((own if g else loc) * W * bpp for _n, bpp, g in self.INPUTS)
+        return h2d, own * W * 16
 
     @property
     def exchange_bytes_per_frame(self) -> int:

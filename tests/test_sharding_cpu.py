@@ -135,3 +135,21 @@ def test_two_rank_sharded_chain_equals_single_process_bit_exact(bpr):
             got = np.frombuffer(planes[k], ref[k].dtype).reshape(ref[k].shape)
             for r0, r1 in blocks:
                 assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
+
+
+def test_host_path_row_sets_cover_what_each_launch_reads():
+    """ShardPlan.local_input_rows (G-buffer / direct-light rows a rank uploads) contains every launch's output rows plus the
+    rows its Poisson taps and quad helpers reach; the ranks' own blocks (uploaded + all-gathered depth / velocity) tile the frame."""
+    from realism_effects_b200.parallel import ShardPlan
+
+    for world, bpr, H, radius, iters in ((2, 1, 128, 3.0, 1), (2, 4, 4320, 8.0, 2), (8, 4, 17280, 8.0, 2), (4, 2, 960, 12.5, 3)):
+        covered = np.zeros(H, np.int32)
+        for rank in range(world):
+            p = ShardPlan(H, world, rank, 2 * iters, radius, True, bpr)
+            for (a, b), launches, (la, lb) in zip(p.blocks, p.block_ranges, p.local_input_rows):
+                covered[a:b] += 1
+                assert la <= a and lb >= b
+                for k, (r0, r1) in enumerate(launches):
+                    reach = p.poisson_halo if 2 <= k < 2 + p.n_poisson_passes else 0   # K3 passes read G-buffer rows around their output
+                    assert la <= max(0, r0 - reach) and lb >= min(H, r1 + reach), (world, rank, k)
+        assert (covered == 1).all()
