@@ -186,7 +186,7 @@ def run_ours(args):
             chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True,
                          ranges=force_ranges)
     else:
-        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap)
+        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=args.balance)
         native = chain.chain
         stream = chain.stream  # kernels + NCCL all-gathers are ordered on this stream
 
@@ -208,7 +208,8 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------------------
-    for i in range(Wm):
+    calib = 24 if (world > 1 and chain.balance == "adaptive") else 0  # untimed frames in which the band borders settle (on top of --warmup)
+    for i in range(calib + Wm):
         render(i)
     barrier()
     launches0 = ctx.launch_count
@@ -231,16 +232,21 @@ def run_ours(args):
     native.set_profiling(False)
     launches = ctx.launch_count - launches0
     ms_per_step = ms_total / K
+    rank_kernel_ms = [{k: round(ms / K, 3) for k, (ms, n) in prof.items() if n}]  # per-frame kernel time of every rank (load balance)
+    if world > 1:
+        rank_kernel_ms = [None] * world
+        dist.all_gather_object(rank_kernel_ms, {k: round(ms / K, 3) for k, (ms, n) in prof.items() if n})
     mpx = W * H / emu / 1e6
     value = mpx / (ms_per_step / 1e3)
 
     # ---- roofline of the dominant kernel (this rank's owned pixels / its event-timed duration) -------
     peak, peak_src = measured_peak()
     per_kernel = {}
+    own_rows = chain.plan.rows_per_rank if world > 1 else Hr  # (adaptive bands: this rank's band at the end of the run)
     for k, (ms, n) in prof.items():
         if n:
             per_kernel[k] = {"ms_per_launch": ms / n, "launches": n, "share_of_step": ms / max(ms_total, 1e-9),
-                             "algo_GBps": ALGO_BYTES[k] * W * Hr / (ms / n * 1e-3) / 1e9}
+                             "algo_GBps": ALGO_BYTES[k] * W * own_rows / (ms / n * 1e-3) / 1e9}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"]) if per_kernel else None
     roof = None
     if dom:
@@ -280,9 +286,8 @@ def run_ours(args):
         # sharded host path (parallel.ShardedSsgiChain.submit_host): each rank uploads its own rows of depth / velocity and the
         # K1-range rows of gbuffer / direct light, the two sampled-anywhere planes are all-gathered over NVLink, and the rank
         # reads back its own rows of `composed`; two frames in flight
-        outs = [torch.empty((Hr, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+        outs = [torch.empty((min(H, int(chain.MAX_SHARE * Hr) + 16), W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]  # tallest adaptive band
         out_host = outs[0]
-        h2d = chain.host_bytes_per_frame[0]
 
         def e2e_step(i):
             j = i % 2
@@ -293,7 +298,8 @@ def run_ours(args):
             chain.wait_host(0)
             chain.finish()
     d2h = out_host.numel() * 4
-    for i in range(3):
+    input_planes_bytes = h2d  # size of one frame's input planes (the working set the L2 note in `config` refers to)
+    for i in range(3 + calib):  # (adaptive bands re-settle for the host path: upload time grows with the band as well)
         e2e_step(i)
     e2e_drain()
     barrier()
@@ -304,6 +310,8 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / ke)
     checksum = float(out_host[::97, ::89, :3].double().sum())
+    if world > 1:
+        h2d, d2h = chain.host_bytes_per_frame  # this rank's share (own rows + K1-range rows), after the bands settled
     e2e = {"value": round(mpx / e2e_s, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": round(e2e_s * 1e3, 3), "steps": ke, "result_checksum": checksum, "bytes_are": "per rank"}
     if world == 1:  # latency of one frame through the synchronous call (no overlap between frames)
@@ -328,13 +336,21 @@ def run_ours(args):
     if rank == 0:
         cfg = {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS} => {2 * DENOISE_ITERATIONS} passes)+compose, steps=20 refineSteps=5, "
                            f"{W}x{Hr} per GPU" + (f" (frame {W}x{H} = the 4K view sampled with {world}x the rows, row-sharded over {world} GPUs)" if world > 1 else ""),
-               "inputs": f"2 alternating synthetic G-buffer frames ({h2d / 1e6:.0f} MB of input planes per frame > 126 MB L2), moving camera",
+               "inputs": f"2 alternating synthetic G-buffer frames ({input_planes_bytes / 1e6:.0f} MB of input planes per frame > 126 MB L2), moving camera",
                "l2": "inputs larger than L2; no explicit flush", "fast_math": True}
         if world > 1:
-            cfg["multi_gpu"] = {"sharding": f"block-cyclic row blocks ({chain.plan.blocks_per_rank} x {chain.plan.block_rows} rows per rank), halo rows recomputed locally",
-                                "recompute_overhead": round(chain.plan.recompute_overhead, 4),
-                                "exchange": "NCCL all-gather of composed + dnB[0..1] once per frame" + ("" if args.no_overlap else "; dnB gathers overlap the next frame's K1"),
-                                "exchange_recv_bytes_per_rank_per_frame": chain.exchange_bytes_per_frame}
+            if chain.balance == "adaptive":
+                shard = (f"one contiguous band per rank, borders rebalanced every {chain.rebalance_every} frames from the ranks' event-timed kernel time; "
+                         f"borders at the end of the run {list(chain.plan.bounds)}, halo rows recomputed locally")
+            else:
+                shard = ("mirrored (boustrophedon) " if chain.plan.mirror else "block-cyclic ") + \
+                    f"row blocks ({chain.plan.blocks_per_rank} x {chain.plan.block_rows} rows per rank), halo rows recomputed locally"
+            cfg["multi_gpu"] = {"sharding": shard,
+                                "recompute_overhead": round(chain.plan.recompute_overhead, 4), "calibration_frames": calib,
+                                "exchange": ("NCCL grouped send/recv" if chain.plan.p2p else "NCCL all-gather") + " of composed + dnB[0..1] once per frame" + ("" if args.no_overlap else "; dnB gathers overlap the next frame's K1"),
+                                "exchange_recv_bytes_per_rank_per_frame": chain.exchange_bytes_per_frame,
+                                "per_rank_kernel_ms_per_frame": [round(sum(d.values()), 3) for d in rank_kernel_ms],
+                                "per_rank_K1_ms": [d.get("K1_ssgi_trace") for d in rank_kernel_ms]}
         line = {
             "metric": "SSGI+denoise Mpixels/s at 4K", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 accumulate planes)",
@@ -414,6 +430,9 @@ def main():
     ap.add_argument("--force-blocks", type=int, default=0, help="experiment (N = 1): issue each pass as this many row-block launches")
     ap.add_argument("--view-height", type=int, default=0, help="experiment: rows of the VIEW (aspect = width / view_height) when --height differs")
     ap.add_argument("--blocks-per-rank", type=int, default=4, help="N > 1: block-cyclic row blocks per rank (content balance)")
+    ap.add_argument("--balance", default="adaptive", choices=("adaptive", "static"),
+                    help="N > 1: adaptive = one band per rank, borders follow the measured kernel time; static = block-cyclic / mirrored blocks")
+    ap.add_argument("--mirror", type=int, default=0, help="N > 1: 1 = boustrophedon block assignment (odd super-blocks in reverse rank order), P2P exchange")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for all all-gathers at the end of every frame")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -21,6 +21,14 @@ Overlap: a frame is issued in two phases.  K1 only needs last frame's `composed`
 are launched asynchronously after K4 (composed first); the next frame waits for the composed gather before K1 and for the
 dnB gathers only before K2, so the dnB transfer hides behind K1.
 
+Adaptive bands (`balance="adaptive"`, the default of bench.py): one CONTIGUOUS band per rank whose height follows the measured
+kernel time.  Every rank times its own kernels with CUDA events; every few frames the ranks exchange those times (a few floats
+over a gloo control group), model the cost per row as piecewise constant over the bands and move the band borders towards equal
+cost (`rebalance`, damped, 16-row aligned).  All cross-frame state lives in the exchanged planes, so the split may change from
+frame to frame without copying anything, and the result stays bit-identical.  Against block-cyclic assignment this keeps the
+K1 tap working set of a rank local (one band + ray reach instead of the whole frame), halves the halo rows and removes the
+partial-tile waste of many small blocks; the bands have different heights, so the exchange is a grouped send/recv.
+
 The result on N GPUs is bit-identical to the single-GPU result (tests/test_sharding_cpu.py with gloo + the oracle as
 compute; tests/test_gpu_multi.py on >= 2 GPUs).
 """
@@ -43,6 +51,7 @@ class ShardPlan:
     ssgi_mode: bool = True
     blocks_per_rank: int = 1
     mirror: bool = False  # True: odd super-blocks are assigned in REVERSE rank order (boustrophedon), see block_of()
+    bounds: tuple | None = None  # explicit band borders (world + 1 ascending rows, 0 .. height): one contiguous band per rank
 
     K2_NEIGHBOURHOOD_ROWS = 2  # 5x5 clamp window (reproject.frag:57-59)
     K4_INPUT_ROWS = 1          # literal bilinear fetch of the LINEAR Poisson targets at the pixel centre
@@ -51,6 +60,8 @@ class ShardPlan:
         """rows of the block `rank` owns inside super-block j.  With `mirror`, odd super-blocks run in reverse rank order, so a
         rank that gets the cheapest end of one super-block (sky) gets the most expensive end of the next (floor): 2 blocks per
         rank already balance a vertical cost gradient, at half the halo recompute of a 4-block cyclic assignment."""
+        if self.bounds is not None:
+            return (self.bounds[rank], self.bounds[rank + 1])
         pos = (self.world - 1 - rank) if (self.mirror and j % 2 == 1) else rank
         b = j * self.world + pos
         return (b * self.block_rows, (b + 1) * self.block_rows)
@@ -58,7 +69,22 @@ class ShardPlan:
     def reversed_order(self, j: int) -> bool:
         return self.mirror and j % 2 == 1
 
+    @property
+    def p2p(self) -> bool:
+        """the exchange cannot be a rank-ordered in-place all-gather (mirrored order or unequal bands)"""
+        return self.mirror or self.bounds is not None
+
     def __post_init__(self):
+        if self.bounds is not None:
+            b = tuple(int(x) for x in self.bounds)
+            if len(b) != self.world + 1 or b[0] != 0 or b[-1] != self.height or any(b[i] >= b[i + 1] for i in range(self.world)):
+                raise ValueError(f"bounds {b} are not {self.world + 1} ascending rows from 0 to {self.height}")
+            self.bounds, self.blocks_per_rank, self.block_rows = b, 1, None
+            self.blocks = [self.block_of(self.rank, 0)]
+            self.rows_per_rank = self.blocks[0][1] - self.blocks[0][0]
+            self.r0, self.r1 = self.blocks[0]
+            self.poisson_halo = int(math.ceil(self.radius)) + 1
+            return
         nb = self.world * self.blocks_per_rank
         if self.height % nb:
             raise ValueError(f"height {self.height} is not divisible by world size x blocks per rank = {nb}")
@@ -124,6 +150,39 @@ class ShardPlan:
         return (0, 4, 5) if self.ssgi_mode else (4,)
 
 
+def rebalance(bounds, costs, measured_bounds=None, align: int = 16, min_rows: int = 64, max_share: float = 4.0, damping: float = 0.6):
+    """New band borders from per-rank costs (any unit) measured with `measured_bounds` (default: `bounds`).
+
+    The cost per row is modelled as constant inside each measured band; the ideal border k is the row where the cumulative
+    cost reaches k/N of the total.  The borders move `damping` of the way from `bounds` to the ideal ones (the model is coarse:
+    damping avoids overshoot), are rounded to `align` rows (the kernels' tile height, so no band ends in a partial tile) and
+    kept at least `min_rows` and at most max_share x the mean height apart.  Pure and deterministic: every rank computes the
+    same borders from the same gathered costs."""
+    mb = list(measured_bounds if measured_bounds is not None else bounds)
+    n, H = len(costs), bounds[-1]
+    costs = [max(float(c), 1e-9) for c in costs]
+    total = sum(costs)
+    ideal, k, acc = [0], 0, 0.0
+    for i in range(1, n):  # invert the piecewise-linear cumulative cost at i/n of the total
+        want = total * i / n
+        while k < n - 1 and acc + costs[k] < want:
+            acc += costs[k]
+            k += 1
+        ideal.append(mb[k] + (want - acc) / costs[k] * (mb[k + 1] - mb[k]))
+    ideal.append(H)
+    lo_h, hi_h = min_rows, max(min_rows, int(max_share * H / n))
+    out = [0]
+    for i in range(1, n):
+        b = bounds[i] + damping * (ideal[i] - bounds[i])
+        b = int(round(b / align)) * align
+        b = max(b, out[-1] + lo_h)                    # not thinner than min_rows ...
+        b = min(b, out[-1] + hi_h)                    # ... nor taller than max_share x the mean
+        b = min(b, H - (n - i) * lo_h)                # leave room for the bands below
+        out.append(b)
+    out.append(H)
+    return tuple(out)
+
+
 class _CudaBytes:
     """__cuda_array_interface__ view of a raw device allocation (an rfx_plane) so torch/NCCL can address it."""
 
@@ -141,7 +200,8 @@ class _PlaneRef:
 class ShardedSsgiChain:
     """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
 
-    def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 4, overlap: bool = True, mirror: bool = False):
+    def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 4, overlap: bool = True, mirror: bool = False,
+                 balance: str = "static", rebalance_every: int = 4, rebalance_lag: int = 2):
         import torch
         import torch.distributed as dist
 
@@ -155,14 +215,27 @@ class ShardedSsgiChain:
         self.ctx = ctx
         self.overlap = overlap
         self.coalesce = True
-        self.plan = ShardPlan(chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
-                              chain_options.mode == abi.MODE_SSGI, blocks_per_rank, mirror)
-        # A mirrored (boustrophedon) assignment needs an all-gather whose output order is the reverse rank order; torch.distributed
-        # sorts the ranks of every new_group(), so that order is not expressible with NCCL collectives here.  The plan supports it
-        # (ShardPlan.block_of) for the planned peer-store exchange; the NCCL path uses the forward cyclic order.
-        self.group_rev = None
-        if self.world > 1 and mirror and blocks_per_rank > 1:
-            raise ValueError("mirror=True needs a reverse-rank-order gather, which torch.distributed process groups cannot express")
+        self._plan_args = (chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
+                           chain_options.mode == abi.MODE_SSGI)
+        if balance not in ("static", "adaptive"):
+            raise ValueError("balance must be 'static' (block-cyclic / mirrored blocks) or 'adaptive' (one cost-balanced band per rank)")
+        self.balance = balance if self.world > 1 else "static"
+        self.rebalance_every, self.rebalance_lag = max(1, rebalance_every), max(1, rebalance_lag)
+        self._frame, self._timing, self._ev_pool, self.last_costs, self._host_span = 0, [], [], None, None
+        if self.balance == "adaptive":
+            H, n = chain_options.height, self.world
+            if H < n * 64:
+                raise ValueError("adaptive bands need at least 64 rows per rank")
+            eq = tuple(int(round(H * i / n / 16.0)) * 16 for i in range(n)) + (H,)
+            self.plan = ShardPlan(*self._plan_args, bounds=eq)
+            # host-side control plane: a few floats per rebalance, over gloo (no device sync, no NCCL stream involved)
+            self.ctl_group = dist.new_group(ranks=[self._global_rank(r) for r in range(self.world)], backend="gloo")
+        else:
+            self.plan = ShardPlan(*self._plan_args, blocks_per_rank, mirror)
+        # A mirrored (boustrophedon) assignment puts the ranks of odd super-blocks in reverse order, which a rank-ordered
+        # all_gather_into_tensor cannot write in place (torch.distributed sorts the ranks of every new_group()).  Mirrored plans
+        # therefore exchange with grouped point-to-point transfers (one ncclGroup of send/recv pairs per exchange, every block
+        # landing directly at its rows); plain cyclic plans keep the in-place all-gather.
         # a dedicated torch stream: the kernels and the NCCL collectives are ordered on it.  (A NULL stream handle means "the
         # context's own stream" to the C ABI, so torch's default stream cannot be used here.)
         self.stream = torch.cuda.Stream(device=torch.device("cuda", ctx.device))
@@ -179,61 +252,108 @@ class ShardedSsgiChain:
             for w in self._pending.pop(which, []):
                 w.wait()  # makes self.stream wait for the collective
 
+    def _exchange(self, items, group):
+        """Every rank's blocks of the planes `items` = [(flat byte tensor, pitch)] to every other rank, in place, as ONE NCCL group:
+        in-place all-gathers per super-block for cyclic plans, send/recv pairs for mirrored plans and unequal bands.  Returns the Work handles."""
+        plan = self.plan
+        if plan.p2p:
+            ops = []
+            for t, pitch in items:
+                for j, (b0, b1) in enumerate(plan.blocks):
+                    for peer in range(self.world):  # both sides walk (plane, block) in the same order, so the k-th send to a peer meets its k-th recv
+                        if peer == self.rank:
+                            continue
+                        p0, p1 = plan.block_of(peer, j)
+                        ops.append(self.dist.P2POp(self.dist.isend, t[b0 * pitch:b1 * pitch], self._global_rank(peer), group))
+                        ops.append(self.dist.P2POp(self.dist.irecv, t[p0 * pitch:p1 * pitch], self._global_rank(peer), group))
+            return list(self.dist.batch_isend_irecv(ops)) if ops else []
+        todo = []
+        for t, pitch in items:
+            for j, (b0, b1) in enumerate(plan.blocks):
+                s0, s1 = plan.super_block(j)
+                todo.append((t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]))  # in place: every rank's block lands at its own rows
+        return self._all_gather(todo, group)
+
     def _gather(self, planes):
-        """Launches the in-place all-gathers of `planes` as ONE coalesced NCCL group (ncclGroupStart/End: a single launch
-        instead of len(planes) x blocks_per_rank); falls back to one async collective per super-block."""
-        def calls(rev):
-            for which in planes:
-                t, pitch = self._tensors[which]
-                for j, (b0, b1) in enumerate(self.plan.blocks):
-                    if self.plan.reversed_order(j) != rev:
-                        continue
-                    s0, s1 = self.plan.super_block(j)
-                    yield t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]  # in place: every rank's block lands at its own rows
+        """launches the exchange of the chain outputs `planes`; the handles wait under the first plane's key"""
+        self._pending[planes[0]] = self._exchange([self._tensors[w] for w in planes], self.group)
 
-        works = []
-        cm_fn = getattr(self.dist, "_coalescing_manager", None)
-        for rev, group in ((False, self.group), (True, self.group_rev)):  # reversed super-blocks gather over the reversed group
-            todo = list(calls(rev))
-            if not todo:
-                continue
-            done = False
-            if self.coalesce and cm_fn is not None:
-                try:
-                    with cm_fn(group=group, device=self.torch.device("cuda", self.ctx.device), async_ops=True) as cm:
-                        for out, own in todo:
-                            self.dist.all_gather_into_tensor(out, own, group=group)
-                    works.append(cm)
-                    done = True
-                except Exception:  # private API: keep working if its signature changes
-                    self.coalesce = False
-            if not done:
-                works += [self.dist.all_gather_into_tensor(out, own, group=group, async_op=True) for out, own in todo]
-        self._pending[planes[0]] = works
+    def _global_rank(self, r: int) -> int:
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
-    def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool):
-        """Enqueues one frame on self.stream (two phases) and the asynchronous all-gathers of its outputs."""
-        torch, plan = self.torch, self.plan
+    def _event(self):
+        return self._ev_pool.pop() if self._ev_pool else self.torch.cuda.Event(enable_timing=True)
+
+    def _maybe_rebalance(self):
+        """adaptive bands: every `rebalance_every` frames move the band borders towards equal measured kernel time.  Uses the
+        newest measurement that is at least `rebalance_lag` frames old (long finished, so the event wait is immediate); the ranks
+        hold identical frame counters and gather identical costs, so they all derive the same borders."""
+        if self.balance != "adaptive":
+            return
+        f = self._frame
+        if f % self.rebalance_every == 0:
+            cand = [t for t in self._timing if t[0] <= f - self.rebalance_lag]
+            if cand:
+                _fr, mb, spans, hspan = cand[-1]
+                spans[-1][1].synchronize()
+                cost = sum(a.elapsed_time(b) for a, b in spans)
+                if hspan is not None:  # host path: a rank is as slow as the slower of its kernels and its PCIe upload (both grow with the band)
+                    hspan[1].synchronize()
+                    cost = max(cost, hspan[0].elapsed_time(hspan[1]))
+                mine = self.torch.tensor([cost], dtype=self.torch.float64)
+                allc = [self.torch.zeros(1, dtype=self.torch.float64) for _ in range(self.world)]
+                self.dist.all_gather(allc, mine, group=self.ctl_group)
+                self.last_costs = [float(c) for c in allc]
+                nb = rebalance(self.plan.bounds, self.last_costs, mb, max_share=self.MAX_SHARE)
+                if nb != self.plan.bounds:
+                    self.plan = ShardPlan(*self._plan_args, bounds=nb)
+        keep = []
+        for t in self._timing:  # recycle the events of measurements that can no longer be chosen
+            if t[0] > f - self.rebalance_lag - self.rebalance_every - 1:
+                keep.append(t)
+            else:
+                for a, b in t[2] + ([t[3]] if t[3] is not None else []):
+                    self._ev_pool += [a, b]
+        self._timing = keep
+
+    def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, _rebalanced: bool = False):
+        """Enqueues one frame on self.stream (two phases) and the asynchronous exchange of its outputs."""
+        torch = self.torch
         args = (cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
         with torch.cuda.stream(self.stream):
             if self.world == 1:
                 self.chain.render(*args, stream=self.stream.cuda_stream)
                 return
+            if not _rebalanced:
+                self._maybe_rebalance()
+            plan = self.plan
             br, nl = plan.block_ranges, plan.n_launches
             first = plan.gathered_planes[0]
+            spans = []
+
+            def timed(launches):  # kernels only: the waits for the exchanges stay outside the measured spans
+                a, b = self._event(), self._event()
+                a.record(self.stream)
+                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=launches)
+                b.record(self.stream)
+                spans.append((a, b))
+
             if self.overlap and plan.ssgi_mode:
                 self._wait([first])                                   # K1 samples last frame's `composed`
-                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(0, 1))
+                timed((0, 1))
                 self._wait(plan.gathered_planes[1:])                  # K2 samples last frame's dnB history
-                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(1, nl))
+                timed((1, nl))
             else:
                 self._wait(plan.gathered_planes)
-                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=(0, nl))
+                timed((0, nl))
             self._gather(plan.gathered_planes[:1])                    # `composed` first: the next frame needs it first
             if len(plan.gathered_planes) > 1:
                 self._gather(plan.gathered_planes[1:])                # dnB[0..1]: pending under key gathered_planes[1]
             if not self.overlap:
                 self._wait(plan.gathered_planes)
+            self._timing.append((self._frame, plan.bounds, spans, self._host_span))
+            self._host_span = None
+            self._frame += 1
 
     def finish(self):
         """wait for the outstanding all-gathers (before reading the planes or tearing down)"""
@@ -246,6 +366,7 @@ class ShardedSsgiChain:
     # the two planes sampled anywhere on screen - which are then all-gathered over NVLink (own communicator, so the gather of
     # frame i+1 is not queued behind frame i's output gathers), and the K1-range rows of the G-buffer and direct light.  H2D,
     # kernels and D2H run on three streams with two staging sets, like rfx_ssgi_chain_submit_host on one GPU.
+    MAX_SHARE = 4.0  # tallest adaptive band, in units of the mean band height (sizes the read-back staging)
     INPUTS = (("depth", 4, True), ("gbuffer", 16, False), ("velocity", 16, True), ("direct", 8, False))  # name, bytes/px, gathered
 
     def _host_init(self):
@@ -262,20 +383,26 @@ class ShardedSsgiChain:
                 pl.ptr, pl.width, pl.height, pl.pitch, pl.format = t.data_ptr(), W, H, W * bpp, fmts[name]
                 st[name] = (t, pl, W * bpp)
             self._in.append(st)
-        self._out_dev = [torch.empty(self.plan.rows_per_rank * W * 16, dtype=torch.uint8, device=dev) for _ in range(2)]
+        cap = H if self.world == 1 else min(H, int(self.MAX_SHARE * H / self.world) + 16)   # adaptive bands stay below MAX_SHARE x the mean height
+        self._out_dev = [torch.empty(cap * W * 16, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.up_stream, self.dn_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self._ev_up = [torch.cuda.Event() for _ in range(2)]
         self._ev_rendered = [torch.cuda.Event() for _ in range(2)]
         self._ev_dn = [torch.cuda.Event() for _ in range(2)]
-        self.in_group = self.dist.new_group(ranks=list(range(self.world))) if self.world > 1 else None
+        self.in_group = self.dist.new_group(ranks=[self._global_rank(r) for r in range(self.world)]) if self.world > 1 else None
         self._host_frames = 0
 
     def submit_host(self, cam, host: dict, camera_pos, camera_moved: bool, out_host):
         """One frame from host planes (dict name -> CPU tensor of the FULL frame, pinned for asynchronous copies) to this rank's
-        rows of `composed` in out_host (CPU float32 tensor (rows_per_rank, W, 4), blocks in plan order).  Returns after enqueueing."""
-        torch, plan = self.torch, self.plan
+        rows of `composed`, written to the start of out_host (CPU float32 tensor of at least rows_per_rank x W x 4; with adaptive
+        bands up to MAX_SHARE x the mean band height).  Returns the row blocks [(r0, r1), ...] the frame's rows belong to, after enqueueing."""
+        torch = self.torch
         if not hasattr(self, "_in"):
             self._host_init()
+        if self.world > 1:
+            with torch.cuda.stream(self.stream):
+                self._maybe_rebalance()   # before the uploads: they follow this frame's bands
+        plan = self.plan
         W, H = self.chain.opt.width, self.chain.opt.height
         k = self._host_frames & 1
         st = self._in[k]
@@ -283,6 +410,8 @@ class ShardedSsgiChain:
         with torch.cuda.stream(self.up_stream):
             if self._host_frames >= 2:
                 self.up_stream.wait_event(self._ev_rendered[k])   # frame i-2 no longer reads this staging set
+            eu0, eu1 = self._event(), self._event()
+            eu0.record(self.up_stream)
             for name, bpp, gathered in self.INPUTS:
                 if name not in host or host[name] is None:
                     continue
@@ -291,34 +420,31 @@ class ShardedSsgiChain:
                 for a, b in (plan.blocks if (gathered and self.world > 1) else plan.local_input_rows if self.world > 1 else [(0, H)]):
                     dev2d[a:b].copy_(host2d[a:b], non_blocking=True)
             self._ev_up[k].record(self.up_stream)
+            eu1.record(self.up_stream)
+            self._host_span = (eu0, eu1)
             if self.world > 1:
-                todo = []
-                for name, bpp, gathered in self.INPUTS:
-                    if gathered and host.get(name) is not None:
-                        t, _pl, pitch = st[name]
-                        for j, (b0, b1) in enumerate(plan.blocks):
-                            s0, s1 = plan.super_block(j)
-                            todo.append((t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]))
-                works = self._all_gather(todo, self.in_group)
+                works = self._exchange([(st[n][0], st[n][2]) for n, _b, g in self.INPUTS if g and host.get(n) is not None], self.in_group)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self._ev_up[k])
             for w in works:
                 w.wait()
         pw = lambda n: _PlaneRef(st[n][1]) if host.get(n) is not None else None  # noqa: E731
-        self.render(cam, pw("depth"), pw("gbuffer"), pw("velocity"), pw("direct"), camera_pos, camera_moved)
+        self.render(cam, pw("depth"), pw("gbuffer"), pw("velocity"), pw("direct"), camera_pos, camera_moved, _rebalanced=True)
         comp, cpitch = self._composed()
         with torch.cuda.stream(self.stream):
             # snapshot this rank's rows of `composed`, so the next frame's K4 may overwrite them while the D2H copy still runs
-            out2d, off = self._out_dev[k].view(plan.rows_per_rank, W * 16), 0
+            nbytes = plan.rows_per_rank * W * 16
+            out2d, off = self._out_dev[k][:nbytes].view(plan.rows_per_rank, W * 16), 0
             for b0, b1 in plan.blocks:
                 out2d[off:off + (b1 - b0)].copy_(comp.view(H, cpitch)[b0:b1, :W * 16], non_blocking=True)
                 off += b1 - b0
             self._ev_rendered[k].record(self.stream)
         with torch.cuda.stream(self.dn_stream):
             self.dn_stream.wait_event(self._ev_rendered[k])
-            out_host.view(torch.uint8).view(-1).copy_(self._out_dev[k], non_blocking=True)
+            out_host.view(torch.uint8).view(-1)[:nbytes].copy_(self._out_dev[k][:nbytes], non_blocking=True)
             self._ev_dn[k].record(self.dn_stream)
         self._host_frames += 1
+        return list(plan.blocks)
 
     def wait_host(self, max_in_flight: int = 0):
         """Blocks until at most max_in_flight (0 or 1) submitted frames are incomplete (their out_host rows not yet written)."""
@@ -365,7 +491,8 @@ class ShardedSsgiChain:
     @property
     def exchange_bytes_per_frame(self) -> int:
         """bytes this rank RECEIVES per frame"""
-        return sum((len(t) // self.world) * (self.world - 1) for t, _ in self._tensors.values())
+        H = self.chain.opt.height
+        return sum((H - self.plan.rows_per_rank) * pitch for _t, pitch in self._tensors.values())
 
     def close(self):
         if self.world > 1:

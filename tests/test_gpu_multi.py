@@ -13,7 +13,7 @@ import chain_harness as ch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q, bpr, overlap):
+def _worker(rank, world, port, q, bpr, overlap, mirror=False, balance="static"):
     import torch.distributed as dist
 
     from realism_effects_b200 import abi, engine, parallel
@@ -23,10 +23,10 @@ def _worker(rank, world, port, q, bpr, overlap):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         o = ch.Opts(denoise_iterations=2)
-        inp = ch.make_inputs(256, 128, 3)
+        inp = ch.make_inputs(256, 256 if balance == "adaptive" else 128, 3)
         ctx = engine.Context(rank, inp.blue)
         ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
-        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), blocks_per_rank=bpr, overlap=overlap)
+        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), blocks_per_rank=bpr, overlap=overlap, mirror=mirror, balance=balance, rebalance_every=1, rebalance_lag=1)
         keep = []
         for fr in inp.frames:
             pl = [ctx.upload(fr[k]) for k in ("depth", "gbuffer", "velocity", "direct")]
@@ -42,8 +42,9 @@ def _worker(rank, world, port, q, bpr, overlap):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
-@pytest.mark.parametrize("bpr,overlap", [(1, False), (2, True)])
-def test_sharded_chain_equals_single_gpu_bit_exact(built, bpr, overlap):
+@pytest.mark.parametrize("bpr,overlap,mirror,balance", [(1, False, False, "static"), (2, True, False, "static"), (2, True, True, "static"),
+                                                        (1, True, False, "adaptive")])
+def test_sharded_chain_equals_single_gpu_bit_exact(built, bpr, overlap, mirror, balance):
     import torch.multiprocessing as mp
 
     world = 2
@@ -53,7 +54,7 @@ def test_sharded_chain_equals_single_gpu_bit_exact(built, bpr, overlap):
     s.close()
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, q, bpr, overlap)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, q, bpr, overlap, mirror, balance)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict()
@@ -64,7 +65,7 @@ def test_sharded_chain_equals_single_gpu_bit_exact(built, bpr, overlap):
         p.join(timeout=60)
         assert p.exitcode == 0
     o = ch.Opts(denoise_iterations=2)
-    inp = ch.make_inputs(256, 128, 3)
+    inp = ch.make_inputs(256, 256 if balance == "adaptive" else 128, 3)
     single, _ = ch.run_cuda_chain(inp, o)
     ref = single[-1]
     for rank, (out, blocks) in res.items():
@@ -76,7 +77,7 @@ def test_sharded_chain_equals_single_gpu_bit_exact(built, bpr, overlap):
                 assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
 
 
-def _host_worker(rank, world, port, q):
+def _host_worker(rank, world, port, q, mirror):
     import torch.distributed as dist
 
     from realism_effects_b200 import abi, engine, parallel
@@ -89,7 +90,7 @@ def _host_worker(rank, world, port, q):
         inp = ch.make_inputs(256, 128, 4)
         ctx = engine.Context(rank, inp.blue)
         ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
-        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), blocks_per_rank=2, overlap=True)
+        chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), blocks_per_rank=2, overlap=True, mirror=mirror)
         rows = chain.plan.rows_per_rank
         outs = [torch.zeros((rows, inp.width, 4), dtype=torch.float32).pin_memory() for _ in inp.frames]
         hosts = [{k: torch.from_numpy(np.ascontiguousarray(fr[k])).pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")} for fr in inp.frames]
@@ -106,7 +107,8 @@ def _host_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
-def test_sharded_host_path_equals_single_gpu_bit_exact(built):
+@pytest.mark.parametrize("mirror", [False, True])
+def test_sharded_host_path_equals_single_gpu_bit_exact(built, mirror):
     """submit_host / wait_host on 2 ranks: each rank uploads its share, depth + velocity are all-gathered, and the rows of
     `composed` it reads back are, for every frame, the single-GPU chain's rows."""
     import torch.multiprocessing as mp
@@ -118,7 +120,7 @@ def test_sharded_host_path_equals_single_gpu_bit_exact(built):
     s.close()
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
-    procs = [mpc.Process(target=_host_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [mpc.Process(target=_host_worker, args=(r, world, port, q, mirror)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict()

@@ -42,8 +42,9 @@ def test_shard_plan_ranges():
     assert ShardPlan(2160, 8, 0, 4, 11.0).poisson_halo == 12                      # demo radius 11
 
 
-def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1):
-    """The chain of chain_harness.run_oracle_chain, but every pass commits only its planned rows (all owned blocks) into this rank's planes."""
+def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1, bounds_per_frame=None):
+    """The chain of chain_harness.run_oracle_chain, but every pass commits only its planned rows (all owned blocks) into this rank's
+    planes.  bounds_per_frame: explicit (unequal) band borders, one tuple per frame - the adaptive-band mode moves them between frames."""
     import orc
 
     H, W = inp.height, inp.width
@@ -57,7 +58,9 @@ def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1
         for rng in rngs_of_blocks:
             dst[rng[0]:rng[1]] = new[rng[0]:rng[1]]
 
-    for fr in inp.frames:
+    for t, fr in enumerate(inp.frames):
+        if bounds_per_frame is not None:
+            plan = ShardPlan(H, world, rank, 2 * o.denoise_iterations, o.radius, True, bounds=bounds_per_frame[t])
         rngs = iter(list(zip(*plan.block_ranges)))  # per launch: the ranges of every owned block
         cam = abi.make_camera(fr["cam"])
         bn_t = ch.next_blue(o.blue_noise_start, bn_t)
@@ -85,7 +88,7 @@ def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1
     return dict(composed=composed, dn0=dnB[0], dn1=dnB[1], tr0=tr[0], ssgi=ssgi, plan=plan)
 
 
-def _worker(rank, world, port, q, bpr):
+def _worker(rank, world, port, q, bpr, bounds_per_frame=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -93,6 +96,19 @@ def _worker(rank, world, port, q, bpr):
         inp = ch.make_inputs(96, 64, 2)
 
         def all_gather_rows(plane, plan):
+            if plan.p2p:  # unequal bands: every rank's band to every other rank, like ShardedSsgiChain._exchange's send/recv group
+                b0, b1 = plan.blocks[0]
+                mine = torch.from_numpy(np.ascontiguousarray(plane[b0:b1]).view(np.uint8).reshape(-1))
+                for peer in range(world):
+                    if peer == rank:
+                        continue
+                    p0, p1 = plan.block_of(peer, 0)
+                    theirs = torch.empty((p1 - p0) * plane[0].nbytes, dtype=torch.uint8)
+                    reqs = [dist.isend(mine, peer), dist.irecv(theirs, peer)]
+                    for r in reqs:
+                        r.wait()
+                    plane[p0:p1] = theirs.numpy().view(plane.dtype).reshape(p1 - p0, *plane.shape[1:])
+                return
             for j, (b0, b1) in enumerate(plan.blocks):  # one collective per super-block, like ShardedSsgiChain._gather
                 mine = torch.from_numpy(np.ascontiguousarray(plane[b0:b1]).view(np.uint8).reshape(-1))
                 parts = [torch.empty_like(mine) for _ in range(world)]
@@ -101,21 +117,24 @@ def _worker(rank, world, port, q, bpr):
                 for g, t in enumerate(parts):
                     plane[s0 + g * plan.block_rows:s0 + (g + 1) * plan.block_rows] = t.numpy().view(plane.dtype).reshape(plan.block_rows, *plane.shape[1:])
 
-        out = sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=bpr)
+        out = sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=bpr, bounds_per_frame=bounds_per_frame)
         q.put((rank, {k: v.tobytes() for k, v in out.items() if k != "plan"}, out["plan"].blocks))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("bpr", [1, 2])
+@pytest.mark.parametrize("bpr", [1, 2, "moving-bands"])
 def test_two_rank_sharded_chain_equals_single_process_bit_exact(bpr):
+    bounds = None
+    if bpr == "moving-bands":  # adaptive mode: unequal bands whose border moves between the frames
+        bpr, bounds = 1, [(0, 16, 64), (0, 48, 64)]
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, bpr)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, bpr, bounds)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict()
@@ -153,3 +172,28 @@ def test_host_path_row_sets_cover_what_each_launch_reads():
                     reach = p.poisson_halo if 2 <= k < 2 + p.n_poisson_passes else 0   # K3 passes read G-buffer rows around their output
                     assert la <= max(0, r0 - reach) and lb >= min(H, r1 + reach), (world, rank, k)
         assert (covered == 1).all()
+
+
+def test_rebalance_moves_borders_towards_equal_cost():
+    from realism_effects_b200.parallel import ShardPlan, rebalance
+
+    H, n = 17280, 8
+    density = lambda r: 0.2 + 2.0 * np.exp(-((r / H - 0.55) ** 2) / 0.02) + 0.8 * (r > 0.7 * H)  # noqa: E731  cheap sky, expensive horizon, floor
+    rows = density(np.arange(H))
+    cost = lambda b: [float(rows[b[i]:b[i + 1]].sum()) for i in range(n)]  # noqa: E731
+    b = tuple(H * i // n for i in range(n + 1))
+    spread0 = max(cost(b)) / (sum(cost(b)) / n)
+    for _ in range(12):
+        nb = rebalance(b, cost(b))
+        assert nb[0] == 0 and nb[-1] == H and all(x % 16 == 0 for x in nb) and all(nb[i + 1] - nb[i] >= 64 for i in range(n))
+        assert nb == rebalance(b, cost(b))                                   # deterministic
+        ShardPlan(H, n, 3, 4, 8.0, True, bounds=nb)                           # always a valid plan
+        b = nb
+    spread = max(cost(b)) / (sum(cost(b)) / n)
+    assert spread0 > 1.5 and spread < 1.06, (spread0, spread)                  # max-over-ranks within 6 % of the mean
+    # measurements taken with older borders are interpreted on those borders
+    assert rebalance((0, 1000, 2000), [3.0, 1.0], measured_bounds=(0, 1200, 2000), align=8, damping=1.0) == (0, 800, 2000)
+    # a rank that reports (almost) nothing cannot collapse to less than min_rows, nor can a band exceed max_share x the mean
+    assert rebalance((0, 1024, 2048), [1e-12, 5.0], min_rows=64, damping=1.0)[1] <= 2048 - 64
+    with pytest.raises(ValueError):
+        ShardPlan(128, 2, 0, 2, 3.0, True, bounds=(0, 64, 100))
