@@ -183,10 +183,14 @@ def run_ours(args):
         def render(i):
             j = i % len(frames)
             pl = planes[j]
-            chain.render(cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True,
-                         ranges=force_ranges)
+            a = (cams[j], _PW(pl["depth"]), _PW(pl["gbuffer"]), _PW(pl["velocity"]), _PW(pl["direct"]), frames[j]["cam"]["position"], True)
+            if args.split_parts:  # experiment: the three-part frame of the sharded path on one GPU (cost of splitting K1)
+                for part in (0, 1, 2):
+                    chain.render_part(part, *a, ranges=force_ranges)
+            else:
+                chain.render(*a, ranges=force_ranges)
     else:
-        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=args.balance)
+        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=args.balance, split_k1=bool(args.split_k1))
         native = chain.chain
         stream = chain.stream  # kernels + NCCL all-gathers are ordered on this stream
 
@@ -232,6 +236,7 @@ def run_ours(args):
     native.set_profiling(False)
     launches = ctx.launch_count - launches0
     ms_per_step = ms_total / K
+    bounds_dev = list(chain.plan.bounds) if (world > 1 and chain.plan.bounds is not None) else None  # band borders of the timed region
     rank_kernel_ms = [{k: round(ms / K, 3) for k, (ms, n) in prof.items() if n}]  # per-frame kernel time of every rank (load balance)
     if world > 1:
         rank_kernel_ms = [None] * world
@@ -341,13 +346,13 @@ def run_ours(args):
         if world > 1:
             if chain.balance == "adaptive":
                 shard = (f"one contiguous band per rank, borders rebalanced every {chain.rebalance_every} frames from the ranks' event-timed kernel time; "
-                         f"borders at the end of the run {list(chain.plan.bounds)}, halo rows recomputed locally")
+                         f"borders during the timed frames {bounds_dev}, halo rows recomputed locally")
             else:
                 shard = ("mirrored (boustrophedon) " if chain.plan.mirror else "block-cyclic ") + \
                     f"row blocks ({chain.plan.blocks_per_rank} x {chain.plan.block_rows} rows per rank), halo rows recomputed locally"
             cfg["multi_gpu"] = {"sharding": shard,
                                 "recompute_overhead": round(chain.plan.recompute_overhead, 4), "calibration_frames": calib,
-                                "exchange": ("NCCL grouped send/recv" if chain.plan.p2p else "NCCL all-gather") + " of composed + dnB[0..1] once per frame" + ("" if args.no_overlap else "; dnB gathers overlap the next frame's K1"),
+                                "exchange": ("NCCL grouped send/recv" if chain.plan.p2p else "NCCL all-gather") + " of composed + dnB[0..1] once per frame" + ("" if args.no_overlap else ("; the composed exchange overlaps the next frame's K1 ray march, the dnB exchange its K1 shading" if args.split_k1 else "; dnB exchange overlaps the next frame's K1")),
                                 "exchange_recv_bytes_per_rank_per_frame": chain.exchange_bytes_per_frame,
                                 "per_rank_kernel_ms_per_frame": [round(sum(d.values()), 3) for d in rank_kernel_ms],
                                 "per_rank_K1_ms": [d.get("K1_ssgi_trace") for d in rank_kernel_ms]}
@@ -432,6 +437,8 @@ def main():
     ap.add_argument("--blocks-per-rank", type=int, default=4, help="N > 1: block-cyclic row blocks per rank (content balance)")
     ap.add_argument("--balance", default="adaptive", choices=("adaptive", "static"),
                     help="N > 1: adaptive = one band per rank, borders follow the measured kernel time; static = block-cyclic / mirrored blocks")
+    ap.add_argument("--split-parts", action="store_true", help="experiment (N = 1): issue every frame as K1 march / K1 shading / K2..K4")
+    ap.add_argument("--split-k1", type=int, default=1, help="N > 1: 1 = K1 as ray march + shading so the `composed` exchange hides behind the march")
     ap.add_argument("--mirror", type=int, default=0, help="N > 1: 1 = boustrophedon block assignment (odd super-blocks in reverse rank order), P2P exchange")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for all all-gathers at the end of every frame")
     args = ap.parse_args()

@@ -334,6 +334,12 @@ rfx_status rfx_ssgi_chain_render_ranges(rfx_ssgi_chain* chain, void* stream, con
  * gathered) — so the dnB all-gather overlaps K1.  Per-frame state advances with the launch that consumes it. */
 rfx_status rfx_ssgi_chain_render_blocks(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame, const uint32_t* ranges,
                                         uint32_t n_launches, uint32_t n_blocks, uint32_t k_begin, uint32_t k_end);
+/* One frame in three parts (for row-sharded callers that overlap the plane exchange with the ray march): part 0 = K1 ray march
+ * only (reads depth / gbuffer; writes a context scratch record per ray), part 1 = K1 shading from those records (the only
+ * reader of last frame's `composed`), part 2 = K2..K4.  Parts 0 and 1 together produce the bytes of the fused K1; issue them
+ * in order 0, 1, 2 with the same frame and ranges.  ranges == NULL: whole planes (n_launches / n_blocks ignored). */
+rfx_status rfx_ssgi_chain_render_part(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame, const uint32_t* ranges,
+                                      uint32_t n_launches, uint32_t n_blocks, uint32_t part);
 /* which: 0 composed (RGBA32F), 1 ssgiOut, 2/3 trOut[0/1], 4/5 dnB[0/1] */
 rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* chain, int32_t which, rfx_plane* out);
 /* host-buffer frame: uploads the four input planes from (pinned) host memory, renders,

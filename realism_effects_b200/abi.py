@@ -168,6 +168,7 @@ def _sig(lib):
     lib.rfx_ssgi_chain_output.argtypes = [vp, C.c_int32, PP]
     lib.rfx_ssgi_chain_render_ranges.argtypes = [vp, vp, _P(SsgiFrame), _P(C.c_uint32), C.c_uint32]
     lib.rfx_ssgi_chain_render_blocks.argtypes = [vp, vp, _P(SsgiFrame), _P(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.rfx_ssgi_chain_render_part.argtypes = [vp, vp, _P(SsgiFrame), _P(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32]
     lib.rfx_ssgi_chain_render_host.argtypes = [vp, _P(SsgiHostFrame)]
     lib.rfx_ssgi_chain_submit_host.argtypes = [vp, _P(SsgiHostFrame)]
     lib.rfx_ssgi_chain_wait_host.argtypes = [vp, C.c_int32]
@@ -183,7 +184,7 @@ EXPORTS = [
     "rfx_temporal_reproject_launch", "rfx_poisson_denoise_launch", "rfx_gi_compose_launch", "rfx_ssgi_compose_launch", "rfx_hbao_launch",
     "rfx_ao_compose_launch", "rfx_motion_blur_launch", "rfx_traa_compose_launch", "rfx_ssgi_chain_create", "rfx_ssgi_chain_destroy",
     "rfx_ssgi_chain_reset", "rfx_ssgi_chain_render", "rfx_ssgi_chain_output", "rfx_ssgi_chain_render_host",
-    "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host",
+    "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host", "rfx_ssgi_chain_render_part",
     "rfx_ssgi_chain_set_profiling", "rfx_ssgi_chain_get_profile", "rfx_ssgi_chain_set_options", "rfx_ssgi_chain_render_ranges", "rfx_ssgi_chain_render_blocks",
 ]
 

@@ -268,10 +268,16 @@ struct PixelMat {
   float roughness, metalness;
 };
 
+// Split-phase K1 (row-sharded multi-GPU frames): PHASE 1 marches the rays - it needs the depth plane only - and stores one
+// float4 per ray; PHASE 2 repeats the (deterministic) per-pixel prologue, takes the march result from the record instead of
+// marching and does everything that samples last frame's `composed`.  The exchange of `composed` between the GPUs runs under
+// PHASE 1 of the next frame.  PHASE 0 is the fused kernel.  Record: hit -> (hitPos.xyz, 1); miss -> (10e9, uv.x, uv.y, 0).
+RFX_D float4 march_record(bool hit, v3 hitPos, v2 uv) { return hit ? make_float4(hitPos.x, hitPos.y, hitPos.z, 1.0f) : make_float4(10.0e9f, uv.x, uv.y, 0.0f); }
+
 // doSample  ssgi.frag:362-439
-template <bool SPARSE, bool FAST>
+template <bool SPARSE, bool FAST, int PHASE>
 RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNormal, float roughnessSq, bool isDiffuseSample, bool isEnvSample,
-                  float NoV, float NoL, float NoH, float LoH, int noiseB, v3& l, v3& hitPos, float& brdf, float& pdf) {
+                  float NoV, float NoL, float NoH, float LoH, int noiseB, v3& l, v3& hitPos, float& brdf, float& pdf, const float4* rec) {
   const float cosTheta = fmaxf(0.0f, dot(viewNormal, l));
   if (isDiffuseSample) {
     brdf = evalDisneyDiffuse<FAST>(NoL, NoV, LoH, roughnessSq, m.metalness);
@@ -284,7 +290,22 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
   pdf = fmaxf(SSGI_EPSILON, pdf);
   hitPos = viewPos;
   bool hit;
-  const v2 coords = rayMarch<SPARSE, FAST>(a, l, hitPos, noiseB, hit);
+  v2 coords;
+  if (PHASE == 2) {  // the march ran in the PHASE 1 launch; replay its effect on hitPos, the hit uv and the in-place scaled direction
+    const float4 r = *rec;
+    hit = r.w != 0.0f;
+    l = l * (a.ray_distance / (float)a.steps);
+    if (hit) {
+      hitPos = mk3(r.x, r.y, r.z);
+      coords = view_to_screen<SPARSE, FAST>(a, hitPos);  // what rayMarch returns for a hit, with or without refinement
+      if (a.refine_steps > 0) { l = l * 0.5f; for (int k = 0; k < a.refine_steps; k++) l = l * 0.5f; }
+    } else {
+      hitPos = mk3(10.0e9f);
+      coords = mk2(r.y, r.z);
+    }
+  } else {
+    coords = rayMarch<SPARSE, FAST>(a, l, hitPos, noiseB, hit);
+  }
   const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
   if (!hit && !allowMissedRays) return getEnvColor<FAST>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v2 vel = mk2(0.0f, 0.0f);
@@ -316,11 +337,14 @@ RFX_D v3 doSample(const SsgiArgs& a, const PixelMat& m, v3 viewPos, v3 viewNorma
   return SSGI;
 }
 
-template <int MODE, bool IS, bool SPARSE, bool FAST>
+template <int MODE, bool IS, bool SPARSE, bool FAST, int PHASE>
 #ifndef RFX_K1_MIN_BLOCKS
 #define RFX_K1_MIN_BLOCKS 4  // 64 registers/thread, 4 blocks (32 warps) per SM: best of the 3..6 sweep
 #endif
-__global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
+#ifndef RFX_K1_MARCH_MIN_BLOCKS
+#define RFX_K1_MARCH_MIN_BLOCKS 8  // march-only phase: L2-latency bound, so occupancy wins over the spills of its prologue (tools/sweep_k1_split.sh, split K1 per frame at 4K: 4 -> 1.65 ms, 5 -> 1.54, 6 -> 1.48, 7 -> 1.45, 8 -> 1.45)
+#endif
+__global__ void __launch_bounds__(kThreads, PHASE == 1 ? RFX_K1_MARCH_MIN_BLOCKS : RFX_K1_MIN_BLOCKS) ssgi_kernel(const __grid_constant__ SsgiArgs a) {
   int x, y;
   const bool in_rows = seg_pixel(a.segs, x, y);
   const bool active = x < a.W && y < a.H && in_rows;
@@ -347,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
   const v2 vUv = pixel_uv(x, y, a.W, a.H);
   const float unpackedDepth = ld_r32f(a.depth, x, y);
   if (unpackedDepth == 1.0f) {  // background :109-113
+    if (PHASE == 1) return;
     v4 dl = mk4(0.0f, 0.0f, 0.0f, 1.0f);
     if (a.direct.p) dl = tex_h4_linear(a.direct, vUv);
     st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(dl, dl));
@@ -429,13 +454,29 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
   const v3 diffuseRay = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs<FAST>(viewNormal, random.x, sc.x, sc.y);
   const v3 specularRay = emsIsEnvSample ? envMisDir : l;
 
+  float4* rec = PHASE != 0 ? (float4*)(a.rec + (long long)y * a.rec_pitch) + 2 * x : nullptr;
+  if (PHASE == 1) {  // march only
+    float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (MODE == RFX_MODE_SSGI && isDiffuseSample) {
+      v3 d = diffuseRay, hp = viewPos;
+      bool hit;
+      const v2 uv = rayMarch<SPARSE, FAST>(a, d, hp, bn.z, hit);
+      r0 = march_record(hit, hp, uv);
+    }
+    v3 d = specularRay, hp = viewPos;
+    bool hit;
+    const v2 uv = rayMarch<SPARSE, FAST>(a, d, hp, bn.z, hit);
+    rec[0] = r0;
+    rec[1] = march_record(hit, hp, uv);
+    return;
+  }
   v3 diffuseGI = mk3(0.0f), specularGI = mk3(0.0f), hitPos = mk3(0.0f);
   float brdf, pdf;
   bool haveDiffuse = false;
   if (MODE == RFX_MODE_SSGI && isDiffuseSample) {  // :222-242
     l = diffuseRay;
     calculateAngles<FAST>(l, v, n, NoL, NoH, LoH, VoH);
-    v3 gi = doSample<SPARSE, FAST>(a, m, viewPos, viewNormal, roughnessSq, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    v3 gi = doSample<SPARSE, FAST, PHASE>(a, m, viewPos, viewNormal, roughnessSq, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf, rec);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<FAST>(aa, aa + bb); } else gi = vdiv_<FAST>(gi, pdf);
     gi = vdiv_<FAST>(gi, emsPdf);
@@ -445,7 +486,8 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
   l = specularRay;  // :246-265
   calculateAngles<FAST>(l, v, n, NoL, NoH, LoH, VoH);
   {
-    v3 gi = doSample<SPARSE, FAST>(a, m, viewPos, viewNormal, roughnessSq, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    v3 gi = doSample<SPARSE, FAST, PHASE>(a, m, viewPos, viewNormal, roughnessSq, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf,
+                                          rec + 1);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<FAST>(aa, aa + bb); } else gi = vdiv_<FAST>(gi, pdf);
     gi = vdiv_<FAST>(gi, emsPdf);
@@ -476,11 +518,16 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_kernel(const
 
 template <int MODE, bool IS>
 static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
-  if (a.proj_sparse) {
-    if (a.fast) ssgi_kernel<MODE, IS, true, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, true, false><<<grid, kThreads, 0, s>>>(a);
+#define RFX_K1_LAUNCH(SP, F, PH) ssgi_kernel<MODE, IS, SP, F, PH><<<grid, kThreads, 0, s>>>(a)
+  if (a.phase == 0) {
+    if (a.proj_sparse) { if (a.fast) RFX_K1_LAUNCH(true, true, 0); else RFX_K1_LAUNCH(true, false, 0); }
+    else { if (a.fast) RFX_K1_LAUNCH(false, true, 0); else RFX_K1_LAUNCH(false, false, 0); }
+  } else if (a.phase == 1) {  // split phases exist for the fast variant only (rfx_api.cu falls back to the fused kernel otherwise)
+    if (a.proj_sparse) RFX_K1_LAUNCH(true, true, 1); else RFX_K1_LAUNCH(false, true, 1);
   } else {
-    if (a.fast) ssgi_kernel<MODE, IS, false, true><<<grid, kThreads, 0, s>>>(a); else ssgi_kernel<MODE, IS, false, false><<<grid, kThreads, 0, s>>>(a);
+    if (a.proj_sparse) RFX_K1_LAUNCH(true, true, 2); else RFX_K1_LAUNCH(false, true, 2);
   }
+#undef RFX_K1_LAUNCH
 }
 
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s) {

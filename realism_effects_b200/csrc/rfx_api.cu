@@ -44,6 +44,10 @@ struct rfx_ctx {
   int viewz_w = 0, viewz_h = 0;
   size_t viewz_pitch = 0;
   bool viewz_reuse = false;  // set by the native chain for the 2nd.. row block of a frame
+  int k1_phase = 0;          // set by the native chain: 0 fused K1, 1 ray march only, 2 shading from the march records
+  void* k1rec = nullptr;     // march records, 2 x float4 per pixel
+  size_t k1rec_pitch = 0;
+  int k1rec_w = 0, k1rec_h = 0;
   const RowSegs* segs_override = nullptr;  // set by the native chain: all owned row blocks in ONE launch
 };
 
@@ -117,6 +121,7 @@ void rfx_ctx_destroy(rfx_ctx* ctx) {
   cudaFree(ctx->step_table);
   cudaFree(ctx->nrd);
   cudaFree(ctx->viewz);
+  cudaFree(ctx->k1rec);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -401,7 +406,24 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * a.H));
     ctx->viewz_w = a.W; ctx->viewz_h = a.H;
   }
-  if (!ctx->viewz_reuse) LAUNCHED(launch_viewz(a, OutV{(unsigned char*)ctx->viewz, (long long)ctx->viewz_pitch}, pick(ctx, stream)));
+  a.phase = ctx->k1_phase;
+  if (a.phase != 0 && !a.fast) {  // the split phases exist for the fast variant: otherwise phase 1 is empty and phase 2 is the fused kernel
+    if (a.phase == 1) return RFX_OK;
+    a.phase = 0;
+  }
+  if (a.phase != 0) {
+    if (!ctx->k1rec || ctx->k1rec_w != a.W || ctx->k1rec_h != a.H) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->k1rec);
+      ctx->k1rec = nullptr;
+      ctx->k1rec_pitch = (size_t)a.W * 32;
+      CU(cudaMalloc(&ctx->k1rec, ctx->k1rec_pitch * a.H));
+      ctx->k1rec_w = a.W; ctx->k1rec_h = a.H;
+    }
+    a.rec = (unsigned char*)ctx->k1rec;
+    a.rec_pitch = (long long)ctx->k1rec_pitch;
+  }
+  if (!ctx->viewz_reuse && a.phase != 2) LAUNCHED(launch_viewz(a, OutV{(unsigned char*)ctx->viewz, (long long)ctx->viewz_pitch}, pick(ctx, stream)));
   a.viewz = PV{(const unsigned char*)ctx->viewz, a.W, a.H, (long long)ctx->viewz_pitch};
   LAUNCHED(launch_ssgi(a, pick(ctx, stream)));
   return RFX_OK;
@@ -754,7 +776,7 @@ struct SegScope {
 // [k_begin, k_end) are issued, so a frame can be split into phases (K1 | the rest) between which the caller waits for a
 // different all-gather; per-frame state advances with the launch that consumes it.
 static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_blocks,
-                                    uint32_t k_begin, uint32_t k_end) {
+                                    uint32_t k_begin, uint32_t k_end, int k1_phase = 0) {
   rfx_ctx* ctx = ch->ctx;
   const rfx_ssgi_chain_options& o = ch->opt;
   rfx_status st = RFX_OK;
@@ -772,15 +794,17 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     sp.ray_distance = o.distance; sp.thickness = o.thickness; sp.env_blur = o.env_blur;
     sp.max_env_map_mip_level = ctx->env_set ? (float)((int)std::floor(std::log2((double)std::max(ctx->env.size_x, ctx->env.size_y))) + 1) : 0.0f;  // Utils.js:30-34
     sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
-    sp.blue_noise_index = next_blue(o.blue_noise_start, ch->bn_trace);
+    sp.blue_noise_index = k1_phase == 2 ? ch->bn_trace : next_blue(o.blue_noise_start, ch->bn_trace);  // the shading phase reuses the march phase's index
     // velocityTexture is a null sampler in the shipped wiring
     for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
       SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       ctx->viewz_reuse = blk > 0;  // the view-z plane depends on the depth plane only: one prepass per frame
+      ctx->k1_phase = k1_phase;
       SpanGuard g(ch, cs, 0);
       st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, R0(blk, k), R1(blk, k));
     }
     ctx->viewz_reuse = false;
+    ctx->k1_phase = 0;
     if (st != RFX_OK) return st;
   }
   k++;
@@ -877,6 +901,20 @@ rfx_status rfx_ssgi_chain_render_blocks(rfx_ssgi_chain* ch, void* stream, const 
   if (!ch || !f || !ranges) return RFX_ERR_INVALID_ARG;
   rfx_status st = check_ranges(ch, ranges, n_launches, n_blocks);
   return st != RFX_OK ? st : chain_render_impl(ch, stream, f, ranges, n_blocks, k_begin, k_end);
+}
+
+// A frame in three parts, so a row-sharded caller can put its waits for the exchanged planes exactly where the data is needed:
+// part 0 = K1 ray march (reads depth / G-buffer only), part 1 = K1 shading (samples last frame's `composed`), part 2 = K2..K4
+// (K2 samples last frame's dnB history).  Parts 0+1 together write the same bytes as the fused K1.  ranges may be NULL.
+rfx_status rfx_ssgi_chain_render_part(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_launches,
+                                      uint32_t n_blocks, uint32_t part) {
+  if (!ch || !f || part > 2) return RFX_ERR_INVALID_ARG;
+  if (ranges) {
+    rfx_status st = check_ranges(ch, ranges, n_launches, n_blocks);
+    if (st != RFX_OK) return st;
+  }
+  if (part == 2) return chain_render_impl(ch, stream, f, ranges, ranges ? n_blocks : 1, 1, 0xffffffffu);
+  return chain_render_impl(ch, stream, f, ranges, ranges ? n_blocks : 1, 0, 1, part == 0 ? 1 : 2);
 }
 
 // Host-buffer path.  submit enqueues one frame and returns: the four input planes go H2D on a copy stream into staging set

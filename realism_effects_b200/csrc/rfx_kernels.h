@@ -114,6 +114,9 @@ struct SsgiArgs {
   PV viewz;                  // R32F: getViewZ(depth) per texel (launch_viewz prepass)
   int proj_sparse;           // projection matrix has the perspective sparsity pattern (exact-zero terms dropped)
   int fast;                  // SFU variants of the continuous transcendentals
+  int phase;                 // 0 fused; 1 ray march only -> rec; 2 shading from rec (k_ssgi.cu "Split-phase K1")
+  unsigned char* rec;        // 2 x float4 per pixel (diffuse ray, specular ray)
+  long long rec_pitch;
 };
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);
 cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s);

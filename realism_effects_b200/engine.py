@@ -209,9 +209,8 @@ class SsgiChain:
         self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_set_options(self.h, C.byref(opt)))
         self.opt = opt
 
-    def render(self, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None, ranges=None, launches=None):
-        """ranges: optional list of (row0, row1) per launch (K1, K2, K3 passes..., K4) for row-block sharding, or a list of such
-        lists (one per owned row block); launches = (k_begin, k_end) restricts the call to a window of launches (frame phases)."""
+    @staticmethod
+    def _frame(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved) -> abi.SsgiFrame:
         f = abi.SsgiFrame()
         f.cam = cam
         f.depth = C.pointer(depth.p)
@@ -220,6 +219,12 @@ class SsgiChain:
         f.direct_light = C.pointer(direct_light.p) if direct_light is not None else None
         f.camera_pos[:] = [float(x) for x in camera_pos]
         f.camera_moved = int(camera_moved)
+        return f
+
+    def render(self, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None, ranges=None, launches=None):
+        """ranges: optional list of (row0, row1) per launch (K1, K2, K3 passes..., K4) for row-block sharding, or a list of such
+        lists (one per owned row block); launches = (k_begin, k_end) restricts the call to a window of launches (frame phases)."""
+        f = self._frame(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
         if ranges is None:
             self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render(self.h, stream, C.byref(f)))
         elif ranges and isinstance(ranges[0][0], (tuple, list)):  # [block][launch] -> (row0, row1), optional launch window
@@ -230,6 +235,17 @@ class SsgiChain:
         else:
             flat = (C.c_uint32 * (2 * len(ranges)))(*[int(v) for r in ranges for v in r])
             self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_ranges(self.h, stream, C.byref(f), flat, len(ranges)))
+
+    def render_part(self, part: int, cam: abi.CameraS, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None, ranges=None):
+        """One of the three parts of a frame (include/rfx.h: rfx_ssgi_chain_render_part): 0 = K1 ray march, 1 = K1 shading,
+        2 = K2..K4.  ranges: None (whole planes) or [block][launch] -> (row0, row1)."""
+        f = self._frame(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
+        if ranges is None:
+            self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_part(self.h, stream, C.byref(f), None, 0, 0, part))
+        else:
+            nb, nl = len(ranges), len(ranges[0])
+            flat = (C.c_uint32 * (2 * nb * nl))(*[int(v) for blk in ranges for r in blk for v in r])
+            self.ctx._chk(self.ctx.lib.rfx_ssgi_chain_render_part(self.h, stream, C.byref(f), flat, nl, nb, part))
 
     def output(self, which: int = 0) -> Plane:
         p = Plane()

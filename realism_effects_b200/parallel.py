@@ -17,9 +17,10 @@ contiguous bands would leave the max-over-ranks time ~1/3 above the mean.  Rows 
 with B blocks per rank the frame is cut into N*B blocks and rank r owns blocks r, r+N, r+2N, ...; super-block j (blocks
 j*N .. j*N+N-1) is contiguous and in rank order, so each plane is all-gathered in place with B collectives.
 
-Overlap: a frame is issued in two phases.  K1 only needs last frame's `composed`; K2..K4 need `dnB`.  The all-gathers
-are launched asynchronously after K4 (composed first); the next frame waits for the composed gather before K1 and for the
-dnB gathers only before K2, so the dnB transfer hides behind K1.
+Overlap: a frame is issued in three parts (rfx_ssgi_chain_render_part).  K1's ray march reads the depth plane only; K1's
+shading samples last frame's `composed`; K2..K4 need the `dnB` history.  The exchanges are launched asynchronously after K4
+(composed first); the next frame marches its rays immediately, waits for `composed` only before the K1 shading part and for
+`dnB` only before K2 - so the `composed` transfer hides behind the march and the `dnB` transfer behind the whole of K1.
 
 Adaptive bands (`balance="adaptive"`, the default of bench.py): one CONTIGUOUS band per rank whose height follows the measured
 kernel time.  Every rank times its own kernels with CUDA events; every few frames the ranks exchange those times (a few floats
@@ -201,7 +202,7 @@ class ShardedSsgiChain:
     """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
 
     def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 4, overlap: bool = True, mirror: bool = False,
-                 balance: str = "static", rebalance_every: int = 4, rebalance_lag: int = 2):
+                 balance: str = "static", rebalance_every: int = 4, rebalance_lag: int = 2, split_k1: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -214,6 +215,7 @@ class ShardedSsgiChain:
         self.chain = engine.SsgiChain(ctx, chain_options)
         self.ctx = ctx
         self.overlap = overlap
+        self.split_k1 = split_k1  # overlap mode: K1 as ray march + shading, so only the shading waits for the `composed` exchange
         self.coalesce = True
         self._plan_args = (chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
                            chain_options.mode == abi.MODE_SSGI)
@@ -331,14 +333,23 @@ class ShardedSsgiChain:
             first = plan.gathered_planes[0]
             spans = []
 
-            def timed(launches):  # kernels only: the waits for the exchanges stay outside the measured spans
+            def timed(launches=None, part=None):  # kernels only: the waits for the exchanges stay outside the measured spans
                 a, b = self._event(), self._event()
                 a.record(self.stream)
-                self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=launches)
+                if part is None:
+                    self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=launches)
+                else:
+                    self.chain.render_part(part, *args, stream=self.stream.cuda_stream, ranges=br)
                 b.record(self.stream)
                 spans.append((a, b))
 
-            if self.overlap and plan.ssgi_mode:
+            if self.overlap and plan.ssgi_mode and self.split_k1:
+                timed(part=0)                                         # K1 ray march: depth only - runs under the exchange of `composed`
+                self._wait([first])                                   # K1 shading samples last frame's `composed`
+                timed(part=1)
+                self._wait(plan.gathered_planes[1:])                  # K2 samples last frame's dnB history
+                timed(part=2)
+            elif self.overlap and plan.ssgi_mode:
                 self._wait([first])                                   # K1 samples last frame's `composed`
                 timed((0, 1))
                 self._wait(plan.gathered_planes[1:])                  # K2 samples last frame's dnB history
