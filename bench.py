@@ -261,6 +261,13 @@ def run_ours(args):
                 "peak_source": peak_src, "chain_achieved": round(chain_ach, 1), "chain_frac": round(chain_ach / peak, 4),
                 "note": "per GPU; this path is instruction/SFU-bound, not HBM-bound (DESIGN.md §4): ncu DRAM traffic is at or below the algorithmic bytes",
                 "per_kernel": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in per_kernel.items()}}
+        tf = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+        if world == 1 and (W, Hr) == (3840, 2160) and os.path.exists(tf):  # measured once per round under ncu (tools/ncu_traffic.py), quoted here
+            t = json.load(open(tf))
+            if dom in t.get("bytes_per_launch", {}):
+                roof["traffic"] = t["bytes_per_launch"][dom]
+                roof["algorithmic_bytes_per_launch"] = ALGO_BYTES[dom] * W * Hr
+                roof["traffic_source"] = t.get("source")
 
     # ---- e2e through host buffers --------------------------------------------------------------------
     host = [{k: f[k].cpu().pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")} for f in frames[:2]]
