@@ -88,9 +88,9 @@ napi_value ChainCreate(napi_env env, napi_callback_info info) {
   return st == RFX_OK ? external(env, ch) : throw_status(env, ctx, st, "rfx_ssgi_chain_create");
 }
 // chainRenderHost(ctx, chain, camera, depth:Float32Array, gbuffer:Float32Array, velocity:Float32Array, direct:Uint16Array|null,
-//                 cameraPos:Float32Array(3), cameraMoved:boolean, out:Float32Array)
+//                 cameraPos:Float32Array(3), cameraMoved:boolean, out:Float32Array[, sync:boolean = true])
 napi_value ChainRenderHost(napi_env env, napi_callback_info info) {
-  size_t argc = 10; napi_value argv[10]; NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  size_t argc = 11; napi_value argv[11]; NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
   rfx_ctx* ctx = unwrap<rfx_ctx>(env, argv[0]);
   rfx_ssgi_chain* ch = unwrap<rfx_ssgi_chain>(env, argv[1]);
   rfx_ssgi_host_frame f{};
@@ -103,8 +103,20 @@ napi_value ChainRenderHost(napi_env env, napi_callback_info info) {
   read_f32(env, argv[7], f.camera_pos, 3);
   bool moved = true; napi_get_value_bool(env, argv[8], &moved); f.camera_moved = moved;
   f.out_composed = (float*)ptr(argv[9]);
-  rfx_status st = rfx_ssgi_chain_render_host(ch, &f);
-  return st == RFX_OK ? nullptr : throw_status(env, ctx, st, "rfx_ssgi_chain_render_host");
+  // `sync` selects the synchronous call; otherwise the frame is only enqueued (pipelined H2D / kernels / D2H) and the caller
+  // pairs it with chainWaitHost(chain, 1) - the typed arrays of a frame must stay alive and untouched until it completed.
+  bool sync = true;
+  if (argc > 10) napi_get_value_bool(env, argv[10], &sync);
+  rfx_status st = sync ? rfx_ssgi_chain_render_host(ch, &f) : rfx_ssgi_chain_submit_host(ch, &f);
+  return st == RFX_OK ? nullptr : throw_status(env, ctx, st, sync ? "rfx_ssgi_chain_render_host" : "rfx_ssgi_chain_submit_host");
+}
+// chainWaitHost(ctx, chain, maxInFlight)
+napi_value ChainWaitHost(napi_env env, napi_callback_info info) {
+  size_t argc = 3; napi_value argv[3]; NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rfx_ctx* ctx = unwrap<rfx_ctx>(env, argv[0]);
+  int32_t n = 0; napi_get_value_int32(env, argv[2], &n);
+  rfx_status st = rfx_ssgi_chain_wait_host(unwrap<rfx_ssgi_chain>(env, argv[1]), n);
+  return st == RFX_OK ? nullptr : throw_status(env, ctx, st, "rfx_ssgi_chain_wait_host");
 }
 napi_value ChainReset(napi_env env, napi_callback_info info) {
   size_t argc = 1; napi_value argv[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
@@ -124,6 +136,7 @@ napi_value Init(napi_env env, napi_value exports) {
       {"blueNoiseSet", nullptr, BlueNoiseSet, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"chainCreate", nullptr, ChainCreate, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"chainRenderHost", nullptr, ChainRenderHost, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"chainWaitHost", nullptr, ChainWaitHost, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"chainReset", nullptr, ChainReset, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"chainDestroy", nullptr, ChainDestroy, nullptr, nullptr, nullptr, napi_default, nullptr},
   };
