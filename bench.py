@@ -270,7 +270,10 @@ def run_ours(args):
                 roof["traffic_source"] = t.get("source")
 
     # ---- e2e through host buffers --------------------------------------------------------------------
-    host = [{k: f[k].cpu().pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")} for f in frames[:2]]
+    # pinned host copies of the input frames (N > 1: one frame serves both parities - at N = 8 a frame is 2.9 GB per rank)
+    host = [{k: f[k].cpu().pin_memory() for k in ("depth", "gbuffer", "velocity", "direct")} for f in frames[:(2 if world == 1 else 1)]]
+    if world > 1:
+        host.append(host[0])
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
     ke = max(3, min(K, 10))
     if world == 1:
