@@ -190,7 +190,8 @@ def run_ours(args):
             else:
                 chain.render(*a, ranges=force_ranges)
     else:
-        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=args.balance, split_k1=bool(args.split_k1))
+        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=args.balance, split_k1=bool(args.split_k1),
+                                            dual_comm=bool(args.dual_comm))
         native = chain.chain
         stream = chain.stream  # kernels + NCCL all-gathers are ordered on this stream
 
@@ -448,6 +449,7 @@ def main():
     ap.add_argument("--balance", default="adaptive", choices=("adaptive", "static"),
                     help="N > 1: adaptive = one band per rank, borders follow the measured kernel time; static = block-cyclic / mirrored blocks")
     ap.add_argument("--split-parts", action="store_true", help="experiment (N = 1): issue every frame as K1 march / K1 shading / K2..K4")
+    ap.add_argument("--dual-comm", type=int, default=0, help="experiment (N > 1): 1 = dnB exchange on a second NCCL communicator, concurrent with composed")
     ap.add_argument("--split-k1", type=int, default=1, help="N > 1: 1 = K1 as ray march + shading so the `composed` exchange hides behind the march")
     ap.add_argument("--mirror", type=int, default=0, help="N > 1: 1 = boustrophedon block assignment (odd super-blocks in reverse rank order), P2P exchange")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for all all-gathers at the end of every frame")

@@ -25,6 +25,12 @@
 #ifndef RFX_MARCH_BATCH
 #define RFX_MARCH_BATCH 1
 #endif
+// 1: the march as the shader's plain loop + fma(x, 0.5, 0.5) for the screen uv (bit-identical by construction, ~100 fewer
+// instructions per pixel).  Written at the end of round 1 with no GPU time left to re-run parity, so it ships disabled;
+// tools/next_round_sweeps.sh measures it.
+#ifndef RFX_K1_SIMPLE_MARCH
+#define RFX_K1_SIMPLE_MARCH 0
+#endif
 
 namespace rfx {
 
@@ -96,7 +102,12 @@ RFX_D v2 view_to_screen(const SsgiArgs& a, v3 p) {
     cw = fma_(M[3], p.x, fma_(M[7], p.y, fma_(M[11], p.z, M[15])));
   }
   const float r = rcp_<AP>(cw);
+#if RFX_K1_SIMPLE_MARCH
+  // x * 0.5 is exact, so fma(x, 0.5, 0.5) rounds exactly like the shader's (x * 0.5) + 0.5: one instruction instead of two
+  return mk2(fma_(cx * r, 0.5f, 0.5f), fma_(cy * r, 0.5f, 0.5f));
+#else
   return mk2((cx * r) * 0.5f + 0.5f, (cy * r) * 0.5f + 0.5f);
+#endif
 }
 
 template <bool AP>
@@ -220,6 +231,14 @@ RFX_D v2 rayMarch(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit)
   v2 uv = mk2(0.0f, 0.0f);
   hit = false;
   const float* cs_row = a.step_table + noiseB;  // cs(i, b) at [(i-1)*256 + b]
+#if RFX_K1_SIMPLE_MARCH && RFX_MARCH_BATCH == 1
+  for (int i = 1; i < a.steps; i++, cs_row += 256) {  // the shader's loop as it stands: no batch scaffolding
+    hitPos = hitPos + dir * __ldg(cs_row);
+    uv = view_to_screen<SPARSE, AP>(a, hitPos);
+    const float diff = tex_r32f_nearest(a.viewz, uv) - hitPos.z;
+    if (diff >= 0.0f && diff < a.thickness) { hit = true; break; }
+  }
+#else
   int i = 1;
   while (i < a.steps && !hit) {
     v3 pos[RFX_MARCH_BATCH];
@@ -246,6 +265,7 @@ RFX_D v2 rayMarch(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit)
     }
     i += RFX_MARCH_BATCH;
   }
+#endif
   if (!hit) {
     hitPos = mk3(10.0e9f);
     return uv;

@@ -202,7 +202,7 @@ class ShardedSsgiChain:
     """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
 
     def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 4, overlap: bool = True, mirror: bool = False,
-                 balance: str = "static", rebalance_every: int = 4, rebalance_lag: int = 2, split_k1: bool = True):
+                 balance: str = "static", rebalance_every: int = 4, rebalance_lag: int = 2, split_k1: bool = True, dual_comm: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -248,6 +248,11 @@ class ShardedSsgiChain:
             t = torch.as_tensor(_CudaBytes(p.ptr, nbytes), device=torch.device("cuda", ctx.device))
             self._tensors[which] = (t, int(p.pitch))
         self._pending = {}  # plane index -> [Work]: all-gathers of the previous frame not yet waited for
+        # dual_comm (experiment, unmeasured in round 1): the dnB exchange runs on a second communicator so it moves concurrently with
+        # the `composed` exchange instead of queueing behind it on one NCCL stream.  Every rank issues both in the same order.
+        self.group2 = None
+        if dual_comm and self.world > 1:
+            self.group2 = dist.new_group(ranks=[self._global_rank(r) for r in range(self.world)])
 
     def _wait(self, planes):
         for which in planes:
@@ -276,9 +281,9 @@ class ShardedSsgiChain:
                 todo.append((t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]))  # in place: every rank's block lands at its own rows
         return self._all_gather(todo, group)
 
-    def _gather(self, planes):
+    def _gather(self, planes, group=None):
         """launches the exchange of the chain outputs `planes`; the handles wait under the first plane's key"""
-        self._pending[planes[0]] = self._exchange([self._tensors[w] for w in planes], self.group)
+        self._pending[planes[0]] = self._exchange([self._tensors[w] for w in planes], group if group is not None else self.group)
 
     def _global_rank(self, r: int) -> int:
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
@@ -358,8 +363,8 @@ class ShardedSsgiChain:
                 self._wait(plan.gathered_planes)
                 timed((0, nl))
             self._gather(plan.gathered_planes[:1])                    # `composed` first: the next frame needs it first
-            if len(plan.gathered_planes) > 1:
-                self._gather(plan.gathered_planes[1:])                # dnB[0..1]: pending under key gathered_planes[1]
+            if len(plan.gathered_planes) > 1:                         # dnB[0..1]: pending under key gathered_planes[1]
+                self._gather(plan.gathered_planes[1:], self.group2)   # (dual_comm: on its own communicator, concurrent with `composed`)
             if not self.overlap:
                 self._wait(plan.gathered_planes)
             self._timing.append((self._frame, plan.bounds, spans, self._host_span))
