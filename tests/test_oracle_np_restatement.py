@@ -1,0 +1,323 @@
+"""A second, independently written restatement of whole passes - vectorised numpy in float64, derived from the GLSL, sharing
+no code with oracle/rfx_oracle.cpp - checked against the C++ oracle on the frames of the chain harness.
+
+The reference ships nothing to pin the oracle to (parity unpinned).  Two restatements written at different
+times, in different languages and styles (scalar C++ with fp32 lowering rules vs whole-image numpy in fp64) agreeing to the
+fp16 quantisation of the targets is the strongest check this environment allows that the oracle follows the shader text and
+not a transcription slip.  Covered: K3 Poisson denoise (poisson_denoise.frag:52-208, both the NEAREST fp32 first pass and the
+LINEAR fp16 later passes, two planes, G-buffer variant), the G-buffer material decode it uses (gbuffer_packing.glsl:24-63,
+151-196), the blue-noise lookup (blue_noise.glsl:9-48), K4 GI compose (DenoiserComposePass.js:58-85 +
+denoiser_compose_functions.glsl:13-107), K7 ao_compose.frag:6-16 and K9 traa_compose.frag:3-6.
+
+What the exercise found: the two restatements disagreed twice, both times on a documented reference quirk that only one of
+them had modelled - GLSL's fp32 `mod` on packed values above 2^24 (metalness = 1) and `max(EPSILON, NaN)` returning EPSILON -
+and never on the algorithm.
+"""
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore", message="invalid value encountered", category=RuntimeWarning)
+
+import chain_harness as ch
+import orc
+from realism_effects_b200 import abi
+
+
+# ---- leaf restatements -----------------------------------------------------------------------------------------------------
+def np_unpack_half2x16(bits_f32):
+    u = bits_f32.view(np.uint32)
+    lo = (u & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+    hi = (u >> 16).astype(np.uint16).view(np.float16).astype(np.float64)
+    return lo, hi
+
+
+def np_unpack_normal(packed_f32):
+    """unpackNormal = decodeOctWrap(unpackHalf2x16(bits))  gbuffer_packing.glsl:52-63"""
+    fx, fy = np_unpack_half2x16(packed_f32)
+    fx, fy = fx * 2.0 - 1.0, fy * 2.0 - 1.0
+    nz = 1.0 - np.abs(fx) - np.abs(fy)
+    t = np.maximum(-nz, 0.0)
+    nx = fx + np.where(fx >= 0.0, -t, t)
+    ny = fy + np.where(fy >= 0.0, -t, t)
+    n = np.stack([nx, ny, nz], -1)
+    return n / np.linalg.norm(n, axis=-1, keepdims=True)
+
+
+def np_roughness(b_f32):
+    """float2color(value).r - NON_ZERO_OFFSET, clamped at 0   gbuffer_packing.glsl:24-34"""
+    # GLSL mod(x, y) = x - y * floor(x / y) evaluated in fp32: with metalness = 1 the packed value exceeds 2^24 and the fp32
+    # product y * floor(x / y) rounds, so the shader's result is NOT the mathematical remainder (a reference quirk, kept)
+    v = b_f32.astype(np.float32)
+    y = np.float32(257.0)
+    r = v - y * np.floor(v / y)
+    return np.maximum(r.astype(np.float64) / 256.0 - 1e-4, 0.0)
+
+
+def np_pcg4d_shift(index: int, size: int = 128):
+    """(pcg4d(seed(index)).xy % 0x0fffffff) % size  blue_noise.glsl:12-35, uint32 wraparound done with Python ints"""
+    M = 0xFFFFFFFF
+    i32 = lambda v: v & M  # noqa: E731   (int -> uvec4 conversion wraps)
+    v = [i32(index), i32(index * 15843), i32(index * 31 + 4566), i32(index * 2345 + 58585)]
+    v = [(x * 1664525 + 1013904223) & M for x in v]
+
+    def rounds(v):
+        v[0] = (v[0] + v[1] * v[3]) & M
+        v[1] = (v[1] + v[2] * v[0]) & M
+        v[2] = (v[2] + v[0] * v[1]) & M
+        v[3] = (v[3] + v[1] * v[2]) & M
+        return v
+
+    v = rounds(v)
+    v = [x ^ (x >> 16) for x in v]
+    v = rounds(v)
+    return (v[0] % 0x0FFFFFFF), (v[1] % 0x0FFFFFFF)
+
+
+def np_blue_noise(blue_rgba8, index, W, H):
+    sx, sy = np_pcg4d_shift(index)
+    ys, xs = np.mgrid[0:H, 0:W]
+    return blue_rgba8[(ys + sy) % 128, (xs + sx) % 128].astype(np.float64) / 255.0
+
+
+def np_fwidth(a):
+    """fine 2x2-quad derivatives: |right - left| + |lower - upper| of the pixel's quad (even image sizes)"""
+    H, W = a.shape[:2]
+    q = a.reshape(H // 2, 2, W // 2, 2, *a.shape[2:])
+    dx = np.abs(q[:, :, :, 1] - q[:, :, :, 0])[:, :, :, None]
+    dy = np.abs(q[:, 1] - q[:, 0])[:, None]
+    return (np.broadcast_to(dx, q.shape) + np.broadcast_to(dy, q.shape)).reshape(a.shape)
+
+
+def np_nearest(plane, u, v):
+    H, W = plane.shape[:2]
+    ix = np.clip(np.floor(u * W).astype(np.int64), 0, W - 1)
+    iy = np.clip(np.floor(v * H).astype(np.int64), 0, H - 1)
+    return plane[iy, ix]
+
+
+def np_bilinear(plane, u, v):
+    H, W = plane.shape[:2]
+    fx, fy = u * W - 0.5, v * H - 0.5
+    x0, y0 = np.floor(fx), np.floor(fy)
+    ax, ay = (fx - x0)[..., None], (fy - y0)[..., None]
+    cx = lambda x: np.clip(x.astype(np.int64), 0, W - 1)  # noqa: E731
+    cy = lambda y: np.clip(y.astype(np.int64), 0, H - 1)  # noqa: E731
+    p = plane.astype(np.float64)
+    return ((p[cy(y0), cx(x0)] * (1 - ax) + p[cy(y0), cx(x0 + 1)] * ax) * (1 - ay) +
+            (p[cy(y0 + 1), cx(x0)] * (1 - ax) + p[cy(y0 + 1), cx(x0 + 1)] * ax) * ay)
+
+
+# ---- K3 --------------------------------------------------------------------------------------------------------------------
+def np_poisson(p: abi.PoissonParams, depth, gbuffer, in0, in1, blue, prev0, prev1):
+    H, W = depth.shape
+    ys, xs = np.mgrid[0:H, 0:W]
+    u, v = (xs + 0.5) / W, (ys + 0.5) / H
+    d = depth.astype(np.float64)
+    discard = (depth == 1.0) & (np_fwidth(d) == 0.0)
+    fetch = np_bilinear if p.input_linear else (lambda pl, uu, vv: np_nearest(pl, uu, vv).astype(np.float64))
+    lum = lambda c: np.power(np.maximum(c @ np.array([0.2125, 0.7154, 0.0721]), 0.0), 0.125)  # noqa: E731
+    planes = [in0, in1]
+    rgb, alpha, lumc, age, tw = [], [], [], [], []
+    for i in range(2):
+        t = fetch(planes[i], u, v)
+        alpha.append(t[..., 3])
+        age.append(1.0 / np.power(t[..., 3] + 1.0, 1.2 * p.phi))
+        c = np.log(t[..., :3] * 1.0003 + 1.0)
+        rgb.append(c.copy())
+        lumc.append(lum(c))
+        tw.append(np.ones((H, W)))
+    normal = np_unpack_normal(gbuffer[..., 1])
+    rough = np_roughness(gbuffer[..., 2])
+    gloss = np.maximum(0.0, 4.0 * (1.0 - rough / 0.25))
+    spec_factor = np.exp(-gloss * p.specular_phi)
+    flat = 1.0 - np.minimum(np.linalg.norm(np_fwidth(normal), axis=-1), 1.0)
+    flat = flat ** 2 * 0.75 + 0.25
+    bn = np_blue_noise(blue, p.blue_noise_index, W, H)
+    ang = bn[..., 0] * 2.0 * np.pi
+    s, c = np.sin(ang), np.cos(ang)
+    k = p.radius * flat
+    S2 = 1.41421356237
+    POISSON = [(-1, 0), (0, -1), (1, 0), (0, 1), (-.25 * S2, -.25 * S2), (.25 * S2, -.25 * S2), (.25 * S2, .25 * S2), (-.25 * S2, .25 * S2)]
+    for ox, oy in POISSON:
+        ox, oy = ox / W, oy / H
+        nu, nv = u + k * (c * ox + s * oy), v + k * (-s * ox + c * oy)   # mat2(c, -s, s, c) is column-major
+        nd = np_nearest(depth, nu, nv).astype(np.float64)
+        ng = np_nearest(gbuffer, nu, nv)
+        nn, nr = np_unpack_normal(ng[..., 1]), np_roughness(ng[..., 2])
+        ndiff = 1.0 - np.maximum((normal * nn).sum(-1), 0.0)
+        w_basic = np.exp(-ndiff * p.normal_phi - 10000.0 * np.abs(d - nd) * p.depth_phi - np.abs(rough - nr) * p.roughness_phi)
+        w_basic = np.where(nd == 1.0, 0.0, w_basic)
+        for i in range(2):
+            w = w_basic * (spec_factor if p.is_texture_specular[i] else 1.0)
+            t = np.log(fetch(planes[i], nu, nv)[..., :3] + 1.0)
+            disoccl = np.power(w, 0.1)
+            ldiff = np.minimum(np.abs(lumc[i] - lum(t)), 0.5)
+            w = (w * np.exp(-ldiff * p.luma_phi) * (1 - age[i]) + disoccl * age[i]) * age[i]
+            w = np.where(w >= 0.0001, w, 0.0)
+            rgb[i] += w[..., None] * t
+            tw[i] += w
+    outs = []
+    for i, prev in enumerate((prev0, prev1)):
+        o = np.concatenate([np.exp(rgb[i] / tw[i][..., None]) - 1.0, alpha[i][..., None]], -1)
+        outs.append(np.where(discard[..., None], prev.astype(np.float64), o))
+    return outs
+
+
+def _agree(want, got, rtol, atol, max_bad):
+    want, got = want.astype(np.float64), got.astype(np.float64)
+    bad = np.abs(want - got) > rtol * np.maximum(np.abs(want), np.abs(got)) + atol
+    frac = bad.any(-1).mean() if bad.ndim == 3 else bad.mean()
+    assert frac <= max_bad, f"{frac:.2e} of the pixels differ (limit {max_bad:.0e}); worst abs {np.abs(want - got).max():.3e}"
+    return frac
+
+
+def test_poisson_pass_oracle_matches_numpy_restatement():
+    o = ch.Opts(denoise_iterations=1, steps=8, refine_steps=2)
+    inp = ch.make_inputs(96, 64, 2)
+    rec = ch.run_oracle_chain(inp, o)[1]
+    fr = inp.frames[1]
+    seen_modes = set()
+    for k3 in rec["_k3"]:
+        p = k3["params"]
+        seen_modes.add(int(p.input_linear))
+        w0, w1 = np_poisson(p, fr["depth"], fr["gbuffer"], k3["in0"], k3["in1"], inp.blue, k3["prev0"], k3["prev1"])
+        # the oracle's targets are fp16 (2^-11 relative); its arithmetic is fp32 with fixed lowering, the restatement's fp64:
+        # branch flips (w >= 1e-4, nearest-texel choice on an exact half) may differ for a handful of pixels
+        _agree(w0, k3["out0"], 2e-3, 1e-4, 5e-3)
+        _agree(w1, k3["out1"], 2e-3, 1e-4, 5e-3)
+        assert np.isfinite(w0).all() and (k3["out0"].astype(np.float64) != k3["prev0"].astype(np.float64)).any()
+    assert seen_modes == {0, 1}  # the NEAREST fp32 first pass and a LINEAR fp16 pass were both exercised
+
+
+def test_material_decode_matches_oracle_unpack():
+    import ctypes as C
+
+    L = orc.lib()
+    inp = ch.make_inputs(64, 32, 1)
+    g = inp.frames[0]["gbuffer"].reshape(-1, 4)
+    geo = inp.frames[0]["depth"].reshape(-1) < 1.0
+    n_np, r_np = np_unpack_normal(g[:, 1].copy()), np_roughness(g[:, 2].copy())
+    out = np.zeros(12, np.float32)
+    for i in np.flatnonzero(geo)[::7]:
+        tex = np.ascontiguousarray(g[i])
+        L.orc_unpack_gbuffer(tex.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))  # diffuse4, normal3, roughness, metalness, emissive3
+        assert np.allclose(out[4:7], n_np[i], atol=2e-6) and abs(out[7] - r_np[i]) < 2e-6
+
+
+def test_blue_noise_shift_matches_oracle():
+    import ctypes as C
+
+    L = orc.lib()
+    for index in (1, 2, 77, 991, 123456, 2 ** 31 - 2):
+        sx, sy = np_pcg4d_shift(index)
+        ox, oy = C.c_int(), C.c_int()
+        L.orc_blue_noise_coord(5, 9, index, 128, C.byref(ox), C.byref(oy))
+        assert (ox.value, oy.value) == ((5 + sx) % 128, (9 + sy) % 128)
+
+
+def test_ao_and_traa_compose_match_numpy_restatement():
+    rng = np.random.default_rng(3)
+    H, W = 24, 40
+    depth = rng.random((H, W)).astype(np.float32)
+    depth[rng.random((H, W)) < 0.2] = 1.0
+    ao = rng.random((H, W, 4)).astype(np.float16)
+    col = (rng.random((H, W, 4)) * 3).astype(np.float16)
+    # ao_compose.frag:6-16: mix(color, 1, pow(depth > .9999 ? 1 : ao, power)) * input
+    got = orc.ao_compose(ch.ao_compose_params(power=2.0, color=(0.1, 0.2, 0.3)), depth, ao, col).astype(np.float64)
+    a = np.where(depth > 0.9999, 1.0, ao[..., 3].astype(np.float64)) ** 2.0
+    want_rgb = (np.array([0.1, 0.2, 0.3])[None, None] * (1 - a[..., None]) + a[..., None]) * col[..., :3].astype(np.float64)
+    _agree(want_rgb, got[..., :3], 2e-3, 1e-4, 0.0)
+    acc = (rng.random((H, W, 4)) * 2).astype(np.float16)  # traa_compose.frag:3-6 copies the accumulated colour with alpha 1
+    got = orc.traa_compose(acc).astype(np.float64)
+    _agree(acc[..., :3].astype(np.float64), got[..., :3], 1e-3, 1e-6, 0.0)
+
+
+# ---- K4 --------------------------------------------------------------------------------------------------------------------
+def np_float_to_vec4(f32):
+    """floatToVec4  gbuffer_packing.glsl:151-164: bytes / 255 - 1e-4, clamped at 0"""
+    u = f32.view(np.uint32)
+    v = np.stack([(u >> s) & 0xFF for s in (0, 8, 16, 24)], -1).astype(np.float64) / 255.0
+    return np.maximum(v - 1e-4, 0.0)
+
+
+def np_metalness(b_f32):
+    v = b_f32.astype(np.float32)  # fp32 like the shader (see np_roughness)
+    return np.maximum(np.floor(v / np.float32(257.0 * 257.0)).astype(np.float64) / 256.0 - 1e-4, 0.0)
+
+
+def np_normalize(a):
+    return a / np.linalg.norm(a, axis=-1, keepdims=True)
+
+
+def np_gi_compose(cam: dict, depth, gbuffer, dgi, sgi, prev):
+    """DenoiserComposePass.js:58-85 + constructGlobalIllumination (denoiser_compose_functions.glsl:53-107), inputType DIFFUSE_SPECULAR.
+    cam: synth camera uniforms (column-major 4x4 arrays)."""
+    H, W = depth.shape
+    M = lambda k: np.asarray(cam[k], np.float64).reshape(4, 4).T  # noqa: E731  column-major -> numpy row-major
+    P, Pinv, Mw, V = M("projection"), M("projection_inverse"), M("camera_matrix_world"), M("view_matrix")
+    near, far = float(cam["near"]), float(cam["far"])
+    ys, xs = np.mgrid[0:H, 0:W]
+    u, v = (xs + 0.5) / W, (ys + 0.5) / H
+    d = depth.astype(np.float64)
+    discard = (depth == 1.0) & (np_fwidth(d) == 0.0)
+    diffuse = np_float_to_vec4(gbuffer[..., 0].copy())[..., :3]
+    normal = np_unpack_normal(gbuffer[..., 1].copy())
+    rough, metal = np_roughness(gbuffer[..., 2]), np_metalness(gbuffer[..., 2])
+    rgbe = np_float_to_vec4(gbuffer[..., 3].copy())
+    emissive = rgbe[..., :3] * np.exp2(rgbe[..., 3:4] * 255.0 - 128.0)
+    rot_left = lambda vec, A: vec @ A[:3, :3]          # noqa: E731  (vec4(v, 0) * A).xyz = A^T v, i.e. row-vector times A
+    view_normal = rot_left(normal, Mw)
+    view_z = -(near * far / ((far - near) * d - far))   # -perspectiveDepthToViewZ
+    clip_w = P[3, 2] * view_z + P[3, 3]                 # projectionMatrix[2][3] is column 2, row 3
+    clip = np.stack([(u - 0.5) * 2.0, (v - 0.5) * 2.0, (view_z - 0.5) * 2.0, np.ones_like(u)], -1) * clip_w[..., None]
+    pos = clip @ Pinv.T
+    view_pos = np.stack([pos[..., 0], pos[..., 1], -view_z], -1)
+    view_dir = np_normalize(view_pos)
+    a = (rough * rough)[..., None]
+    N = rot_left(view_normal, V)
+    vv = -view_dir
+    Vw = rot_left(vv, V)
+    up = np.where((np.abs(N[..., 2:3]) < 0.9999999), np.array([0.0, 0.0, 1.0]), np.array([1.0, 0.0, 0.0]))
+    T = np_normalize(np.cross(up, N))
+    B = np.cross(N, T)
+    Vl = np.stack([(Vw * T).sum(-1), (Vw * B).sum(-1), (Vw * N).sum(-1)], -1)
+    # SampleGGXVNDF(V, a, a, 0.25, 0.25)
+    Vh = np_normalize(np.concatenate([a * Vl[..., :2], Vl[..., 2:3]], -1))
+    lensq = Vh[..., 0] ** 2 + Vh[..., 1] ** 2
+    T1 = np.where((lensq > 0.0)[..., None], np.stack([-Vh[..., 1], Vh[..., 0], np.zeros_like(lensq)], -1) / np.sqrt(np.maximum(lensq, 1e-300))[..., None],
+                  np.array([1.0, 0.0, 0.0]))
+    T2 = np.cross(Vh, T1)
+    r, phi = np.sqrt(0.25), 2.0 * np.pi * 0.25
+    t1, t2 = r * np.cos(phi), r * np.sin(phi)
+    s = 0.5 * (1.0 + Vh[..., 2])
+    t2 = (1.0 - s) * np.sqrt(1.0 - t1 * t1) + s * t2
+    Nh = t1 * T1 + t2[..., None] * T2 + np.sqrt(np.maximum(0.0, 1.0 - t1 * t1 - t2 * t2))[..., None] * Vh
+    Hh = np_normalize(np.concatenate([a * Nh[..., :2], np.maximum(0.0, Nh[..., 2:3])], -1))
+    Hh = np.where(Hh[..., 2:3] < 0.0, -Hh, Hh)
+    inc = -Vl
+    l = np_normalize(inc - 2.0 * (Hh * inc).sum(-1, keepdims=True) * Hh)   # reflect(-V, H)
+    l = l[..., 0:1] * T + l[..., 1:2] * B + l[..., 2:3] * N
+    l = np_normalize(rot_left(l, Mw))  # (vec4(l, 1.) * cameraMatrixWorld).xyz: the translation row only feeds .w
+    l = np.where(((view_normal * l).sum(-1) < 0.0)[..., None], -l, l)
+    h = np_normalize(vv + l)
+    # GLSL max(x, y) = (x < y) ? y : x.  With roughness 0 on a back-facing texel H = normalize(0) is NaN, the comparison with
+    # NaN is false and max(EPSILON, NaN) returns EPSILON - the shader's output there is finite (F ~ 1), and so is the oracle's.
+    dvh = (vv * h).sum(-1)
+    VoH = np.where(1e-6 < dvh, dvh, 1e-6)[..., None]
+    f0 = 0.04 * (1.0 - metal[..., None]) + diffuse * metal[..., None]
+    F = f0 + (1.0 - f0) * np.power(1.0 - VoH, 5.0)
+    gi = diffuse * (1.0 - metal[..., None]) * (1.0 - F) * dgi[..., :3].astype(np.float64) + sgi[..., :3].astype(np.float64) * F + emissive
+    out = np.concatenate([gi, np.ones((H, W, 1))], -1)
+    return np.where(discard[..., None], prev.astype(np.float64), out)
+
+
+def test_gi_compose_oracle_matches_numpy_restatement():
+    o = ch.Opts(denoise_iterations=1, steps=8, refine_steps=2)
+    inp = ch.make_inputs(96, 64, 2)
+    recs = ch.run_oracle_chain(inp, o)
+    for t in (0, 1):
+        fr, rec = inp.frames[t], recs[t]
+        want = np_gi_compose(fr["cam"], fr["depth"], fr["gbuffer"], rec["dn0"], rec["dn1"], rec["_k4_prev"])
+        frac = _agree(want, rec["composed"], 1e-3, 1e-5, 0.0)    # fp32 oracle vs fp64 restatement, through pow(1 - VoH, 5)
+        assert _agree(want, rec["composed"], 3e-4, 1e-5, 3e-3) < 3e-3 and np.isfinite(want).all() and frac == 0.0
