@@ -6,7 +6,9 @@ times, in different languages and styles (scalar C++ with fp32 lowering rules vs
 fp16 quantisation of the targets is the strongest check this environment allows that the oracle follows the shader text and
 not a transcription slip.  Covered: K1 SSGI trace without environment map / importance sampling (ssgi.frag:105-503 +
 ssgi_utils.frag: view position, TBN, VNDF sample, diffuse/specular lottery, both BRDFs and pdfs, the ray march with binary
-refinement, hit shading with saturation and border fade, ray length, packTwoVec4), K3 Poisson denoise (poisson_denoise.frag:52-208, both the NEAREST fp32 first pass and the
+refinement, hit shading with saturation and border fade, ray length, packTwoVec4), K2 temporal reprojection in its SSGI form
+(temporal_reproject.frag:42-208 + reproject.frag: both reprojection modes, the confidence checks, Catmull-Rom history fetch,
+neighbourhood clamp, accumulation), K3 Poisson denoise (poisson_denoise.frag:52-208, both the NEAREST fp32 first pass and the
 LINEAR fp16 later passes, two planes, G-buffer variant), the G-buffer material decode it uses (gbuffer_packing.glsl:24-63,
 151-196), the blue-noise lookup (blue_noise.glsl:9-48), K4 GI compose (DenoiserComposePass.js:58-85 +
 denoiser_compose_functions.glsl:13-107), K7 ao_compose.frag:6-16 and K9 traa_compose.frag:3-6.
@@ -500,3 +502,127 @@ def test_ssgi_trace_oracle_matches_numpy_restatement():
         frac = _agree(want, got, 3e-3, 3e-4, 1.5e-2)
         geo = fr["depth"] < 1.0
         assert frac < 1.5e-2 and (want[geo][:, 0] < -0.9).any() and (want[geo][:, 0] >= 0.0).any() and (want[geo][:, 7] > 1.0).any()
+
+
+# ---- K2 (SSGI form: two planes, packed K1 input, log transform, LINEAR fp16 history) -----------------------------------------
+def np_temporal(p: abi.TemporalParams, ssgi_packed, velocity, hist, prev_out):
+    """temporal_reproject.frag:42-208 + reproject.frag (inputType DIFFUSE_SPECULAR, textureCount 2, logTransform)."""
+    assert p.input_type == abi.INPUT_DIFFUSE_SPECULAR and p.texture_count == 2 and p.log_transform and p.history_linear
+    H, W = velocity.shape[:2]
+    M = lambda arr: np.asarray(list(arr), np.float64).reshape(4, 4).T  # noqa: E731
+    cam = p.cam
+    Pinv, Mw = M(cam.projection_inverse), M(cam.camera_matrix_world)
+    pV, pMw, pP, pPinv = M(p.prev_view_matrix), M(p.prev_camera_matrix_world), M(p.prev_projection), M(p.prev_projection_inverse)
+    near, far = float(cam.near_plane), float(cam.far_plane)
+    cam_pos = np.array(list(p.camera_pos), np.float64)
+    ys, xs = np.mgrid[0:H, 0:W]
+    u, v = (xs + 0.5) / W, (ys + 0.5) / H
+    hom = lambda a: np.concatenate([a, np.ones_like(a[..., :1])], -1)  # noqa: E731
+
+    def to_world(uu, vv_, dd, world, proj_inv):  # screenSpaceToWorldSpace  reproject.frag:21-28
+        ndc = np.stack([(uu - 0.5) * 2.0, (vv_ - 0.5) * 2.0, (dd - 0.5) * 2.0, np.ones_like(uu)], -1)
+        clip = ndc @ proj_inv.T
+        return ((clip / clip[..., 3:4]) @ world.T)[..., :3]
+
+    vel = velocity[..., :2].astype(np.float64)
+    wnormal = np_unpack_normal(velocity[..., 2].copy())
+    depth = velocity[..., 3].astype(np.float64)
+    halves = ch.unpack_halves(ssgi_packed).astype(np.float64) - 1e-4          # unpackTwoVec4
+    inp = [halves[..., 0:4].copy(), halves[..., 4:8].copy()]
+    sampled = [t[..., 0] >= 0.0 for t in inp]
+    for t in inp:
+        t[..., :3] = np.log(np.maximum(t[..., :3], 0.0) + 1.0)
+    discard = (velocity[..., 3] == 1.0) & (np_fwidth(depth) == 0.0)
+    curvature = np.linalg.norm(np_fwidth(wnormal), axis=-1)
+    wpos = to_world(u, v, depth, Mw, Pinv)
+    ray_len, rough = inp[1][..., 3], np.clip(inp[0][..., 3], 0.0, 1.0)
+    view_z = np.abs(near * far / ((far - near) * depth - far))
+    dist_factor = 1.0 + 1.0 / (view_z + 1.0)
+
+    def validate(ru, rv):  # validateReprojectedUV :130-167 (confidence already raised to confidencePower once here)
+        outside = (ru > 1.0) | (ru < 0.0) | (rv > 1.0) | (rv < 0.0)
+        t = np_nearest(velocity, ru, rv)
+        ln, ld = np_unpack_normal(np.ascontiguousarray(t[..., 2])), t[..., 3].astype(np.float64)
+        lpos = to_world(ru, rv, ld, pMw, pPinv)
+        dpos = wpos - lpos
+        dis = (np.linalg.norm(dpos, axis=-1) / 10.0 + np.abs(_dot(dpos, wnormal)) / 20.0 + np.minimum(1.0 - _dot(wnormal, ln), 1.0)) * dist_factor
+        conf = np.power(np.maximum(1.0 - np.minimum(dis, 1.0), 0.0), p.confidence_power)
+        return np.where(outside, 0.0, conf)
+
+    du, dv = u - vel[..., 0], v - vel[..., 1]
+    uvc_d = (du, dv, validate(du, dv))
+    ray = np_normalize(wpos - cam_pos)
+    hitp = hom(cam_pos + ray * ray_len[..., None]) @ (pP @ pV).T
+    su, sv = hitp[..., 0] / hitp[..., 3] * 0.5 + 0.5, hitp[..., 1] / hitp[..., 3] * 0.5 + 0.5
+    no_hit = (curvature > 0.05) | (ray_len < 0.01)
+    su, sv = np.where(no_hit, -1.0, su), np.where(no_hit, -1.0, sv)
+    sc = validate(su, sv)
+    fall = su == -1.0
+    uvc_s = (np.where(fall, uvc_d[0], su), np.where(fall, uvc_d[1], sv), np.where(fall, uvc_d[2], sc))
+    move = np.minimum(_dot(vel, vel) * 10000.0, 1.0)
+
+    def catmull(plane, pu, pv):  # BiCubicCatmullRom5Tap :212-255 over a LINEAR fp16 plane
+        inv = np.array([1.0 / W, 1.0 / H])
+        UV = np.stack([pu, pv], -1) / inv
+        tc = np.floor(UV - 0.5) + 0.5
+        f = UV - tc
+        f2, f3 = f * f, f * f * f
+        w0, w1, w3 = f2 - 0.5 * (f3 + f), 1.5 * f3 - 2.5 * f2 + 1.0, 0.5 * (f3 - f2)
+        w2 = 1.0 - w0 - w1 - w3
+        W0, W1, W2 = w0, w1 + w2, w3
+        S0, S1, S2 = (tc - 1.0) * inv, (tc + w2 / W1) * inv, (tc + 2.0) * inv
+        taps = [(S1[..., 0], S0[..., 1], W1[..., 0] * W0[..., 1]), (S0[..., 0], S1[..., 1], W0[..., 0] * W1[..., 1]), (S1[..., 0], S1[..., 1], W1[..., 0] * W1[..., 1]),
+                (S2[..., 0], S1[..., 1], W2[..., 0] * W1[..., 1]), (S1[..., 0], S2[..., 1], W1[..., 0] * W2[..., 1])]
+        acc = sum(np_bilinear(plane, a, b) * w[..., None] for a, b, w in taps)
+        return np.maximum(acc / sum(w for _a, _b, w in taps)[..., None], 0.0)
+
+    lin = [np.exp(t[..., :3]) - 1.0 for t in inp]  # undoColorTransform(inputColor) for the clamp box
+    outs = []
+    for i in range(2):
+        spec = bool(p.reproject_specular[i])
+        uvc = uvc_s if spec else uvc_d
+        acc = catmull(hist[i], uvc[0], uvc[1])
+        acc_rgb, acc_a = np.log(acc[..., :3] + 1.0), acc[..., 3] + 1.0
+        radius = np.where(spec & (rough < 0.25), 1, 2)
+        mn, mx = lin[i].copy(), lin[i].copy()
+        for dy in range(-2, 3):
+            for dx in range(-2, 3):
+                t = halves[np.clip(ys + dy, 0, H - 1), np.clip(xs + dx, 0, W - 1)][..., 4 * i:4 * i + 3]
+                use = ((np.abs(dx) <= radius) & (np.abs(dy) <= radius) & (t[..., 0] >= 0.0))[..., None]
+                mn, mx = np.where(use, np.minimum(t, mn), mn), np.where(use, np.maximum(t, mx), mx)
+        clamped = np.clip(acc_rgb, np.log(mn + 1.0), np.log(mx + 1.0))
+        r = rough if spec else 1.0
+        intensity = np.minimum(1.0, move * 50.0 + p.neighborhood_clamp_intensity) * np.minimum(1.0, uvc[2] * r)
+        new = acc_rgb * (1.0 - intensity[..., None]) + clamped * intensity[..., None]
+        acc_a2 = acc_a * (1.0 - np.minimum(np.linalg.norm(new - acc_rgb, axis=-1), 1.0))
+        # not sampled this frame: the input is replaced by the history and the history is used as fetched (no clamp, no age + 1)
+        in_rgb = np.where(sampled[i][..., None], inp[i][..., :3], acc_rgb)
+        acc_rgb = np.where(sampled[i][..., None], new, acc_rgb)
+        acc_a = np.where(sampled[i], acc_a2, acc[..., 3])
+        conf = np.power(uvc[2], p.confidence_power)          # raised a second time in accumulate() :49
+        blend = (1.0 - 1.0 / (acc_a + 1.0)) * conf
+        max_v = np.full((H, W), (1.0 if p.full_accumulate else p.max_blend) * p.keep_data)
+        if spec:
+            low = (rough >= 0.0) & (rough < 0.1)
+            mrv = max_v * (rough / 0.1)
+            k = np.minimum(100.0 * move, 1.0)
+            max_v = np.where(low, max_v * (1.0 - k) + mrv * k, max_v)
+        tmix = np.minimum(blend, max_v)
+        oa = np.minimum(65536.0, 1.0 / (1.0 - tmix) - 1.0)
+        rgb = np.exp(in_rgb * (1.0 - tmix[..., None]) + acc_rgb * tmix[..., None]) - 1.0
+        o = np.concatenate([rgb, oa[..., None]], -1)
+        outs.append(np.where(discard[..., None], prev_out[i].astype(np.float64), o))
+    return outs
+
+
+def test_temporal_reproject_oracle_matches_numpy_restatement():
+    o = ch.Opts(denoise_iterations=1, steps=8, refine_steps=2)
+    inp = ch.make_inputs(96, 64, 3)
+    recs = ch.run_oracle_chain(inp, o)
+    for t in (1, 2):  # frames with a history and a moving camera
+        fr, rec = inp.frames[t], recs[t]
+        w0, w1 = np_temporal(rec["_k2_params"], rec["ssgi"], fr["velocity"], rec["_k2_hist"], rec["_k2_prev_out"])
+        # fp32 targets; confidence / clamp branches and nearest-texel choices may flip for a few pixels between fp32 and fp64
+        assert _agree(w0, rec["tr0"], 2e-4, 1e-5, 2e-3) < 2e-3   # (measured: 0 pixels outside 1e-4)
+        assert _agree(w1, rec["tr1"], 2e-4, 1e-5, 2e-3) < 2e-3
+        assert (rec["tr0"][..., 3] > 0.5).any()  # some history was actually accumulated
