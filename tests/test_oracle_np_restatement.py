@@ -4,9 +4,10 @@ no code with oracle/rfx_oracle.cpp - checked against the C++ oracle on the frame
 The reference ships nothing to pin the oracle to (parity unpinned).  Two restatements written at different
 times, in different languages and styles (scalar C++ with fp32 lowering rules vs whole-image numpy in fp64) agreeing to the
 fp16 quantisation of the targets is the strongest check this environment allows that the oracle follows the shader text and
-not a transcription slip.  Covered: K1 SSGI trace without environment map / importance sampling (ssgi.frag:105-503 +
-ssgi_utils.frag: view position, TBN, VNDF sample, diffuse/specular lottery, both BRDFs and pdfs, the ray march with binary
-refinement, hit shading with saturation and border fade, ray length, packTwoVec4), K2 temporal reprojection in its SSGI form
+not a transcription slip.  Covered: K1 SSGI trace (ssgi.frag:105-503 + ssgi_utils.frag: view position, TBN, VNDF sample,
+diffuse/specular lottery, both BRDFs and pdfs, the ray march with binary refinement, hit shading with saturation and border
+fade, ray length, packTwoVec4; with and without the environment map - inverse-CDF importance sample with its implicit-LOD
+colour fetch, MIS weights, equirect lookup with the roughness-scaled mip and the luminance cap), K2 temporal reprojection in its SSGI form
 (temporal_reproject.frag:42-208 + reproject.frag: both reprojection modes, the confidence checks, Catmull-Rom history fetch,
 neighbourhood clamp, accumulation), K3 Poisson denoise (poisson_denoise.frag:52-208, both the NEAREST fp32 first pass and the
 LINEAR fp16 later passes, two planes, G-buffer variant), the G-buffer material decode it uses (gbuffer_packing.glsl:24-63,
@@ -355,10 +356,45 @@ def np_sample_ggx_vndf(V, a, r1, r2):
     return np_normalize(np.concatenate([a * Nh[..., :2], np.maximum(0.0, Nh[..., 2:3])], -1))
 
 
-def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue):
-    """ssgi.frag:105-503 + ssgi_utils.frag with USE_ENVMAP and importanceSampling undefined, missedRays undefined, MODE_SSGI; the
-    velocity sampler is the null sampler of the shipped wiring.  Returns the 8 unpacked fp16 channels as float64."""
-    assert not (p.flags & (abi.SSGI_USE_ENVMAP | abi.SSGI_IMPORTANCE_SAMPLING | abi.SSGI_MISSED_RAYS)) and p.mode == abi.MODE_SSGI
+def np_env_mips(env_f16):
+    """box-filtered mip chain of a power-of-two equirect map, every level rounded to fp16 (GL generateMipmap)"""
+    levels = [env_f16.astype(np.float64)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        a = levels[-1]
+        h, w = a.shape[:2]
+        y0, y1 = np.minimum(2 * np.arange(max(1, h // 2)), h - 1), np.minimum(2 * np.arange(max(1, h // 2)) + 1, h - 1)
+        x0, x1 = np.minimum(2 * np.arange(max(1, w // 2)), w - 1), np.minimum(2 * np.arange(max(1, w // 2)) + 1, w - 1)
+        b = (a[y0][:, x0] + a[y0][:, x1] + a[y1][:, x0] + a[y1][:, x1]) * 0.25
+        levels.append(b.astype(np.float16).astype(np.float64))
+    return levels
+
+
+def np_trilinear(mips, eu, ev, lod):
+    """textureLod(map, uv, lod), LINEAR_MIPMAP_LINEAR, clamp to edge"""
+    n = len(mips)
+    l = np.clip(lod, 0.0, n - 1.0)
+    l0 = np.floor(l).astype(np.int64)
+    l1 = np.minimum(l0 + 1, n - 1)
+    f = (l - l0)[..., None]
+    A, B = np.zeros(eu.shape + (4,)), np.zeros(eu.shape + (4,))
+    for k in range(n):
+        if (l0 == k).any() or (l1 == k).any():
+            s = np_bilinear(mips[k], eu, ev)
+            A, B = np.where((l0 == k)[..., None], s, A), np.where((l1 == k)[..., None], s, B)
+    return A * (1.0 - f) + B * f
+
+
+def np_equirect_uv(dirs):
+    """equirectDirectionToUv  ssgi_utils.frag:64-74"""
+    return np.arctan2(dirs[..., 2], dirs[..., 0]) / (2.0 * np.pi) + 0.5, 1.0 - np.arccos(np.clip(dirs[..., 1], -1.0, 1.0)) / np.pi
+
+
+def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue, env=None):
+    """ssgi.frag:105-503 + ssgi_utils.frag, MODE_SSGI, missedRays undefined, with or without USE_ENVMAP + importanceSampling (env =
+    (map fp16 (h, w, 4), marginal, conditional, total_sum)); the velocity sampler is the null sampler of the shipped wiring
+    (SURVEY.md D4).  Returns the 8 stored fp16 channels as float64."""
+    use_env, use_is = bool(p.flags & abi.SSGI_USE_ENVMAP), bool(p.flags & abi.SSGI_IMPORTANCE_SAMPLING)
+    assert not (p.flags & abi.SSGI_MISSED_RAYS) and p.mode == abi.MODE_SSGI and (env is not None or not (use_env or use_is))
     H, W = depth.shape
     cam = p.cam
     M = lambda arr: np.asarray(list(arr), np.float64).reshape(4, 4).T  # noqa: E731
@@ -416,6 +452,43 @@ def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue):
     b_ = np_normalize(np.cross(n, np.broadcast_to(np.array([0.0, 1.0, 1.0]), n.shape)))
     t_ = np.cross(b_, n)
     diffuse_ray = np_normalize((r_ * np.sin(th))[..., None] * b_ + np.sqrt(1.0 - rnd[..., 0])[..., None] * n + (r_ * np.cos(th))[..., None] * t_)
+    spec_ray = l
+    ems_pdf, is_env = np.ones((H, W)), np.zeros((H, W), bool)
+    if use_env or use_is:
+        mips = np_env_mips(env[0])
+        eh, ew = env[0].shape[:2]
+    if use_is:  # sampleEquirectProbability  ssgi_utils.frag:210-225 and ssgi.frag:197-215
+        marg, cond = np.asarray(env[1], np.float64), np.asarray(env[2], np.float64)
+        cv = marg[np.clip(np.floor(rnd[..., 0] * len(marg)).astype(np.int64), 0, len(marg) - 1)]
+        cu = cond[np.clip(np.floor(cv * eh).astype(np.int64), 0, eh - 1), np.clip(np.floor(rnd[..., 1] * ew).astype(np.int64), 0, ew - 1)]
+        theta, phi = (cu - 0.5) * 2.0 * np.pi, (1.0 - cv) * np.pi
+        edir = np.stack([np.sin(phi) * np.cos(theta), np.cos(phi), np.sin(phi) * np.sin(theta)], -1)
+        # texture(info.map, uv): implicit LOD from the quad derivatives of the (random) uv, in texels
+        q = np.stack([cu * ew, cv * eh], -1).reshape(H // 2, 2, W // 2, 2, 2)
+        ddx = np.linalg.norm(q[:, :, :, 1] - q[:, :, :, 0], axis=-1)[:, :, :, None]
+        ddy = np.linalg.norm(q[:, 1] - q[:, 0], axis=-1)[:, None]
+        rho = np.maximum(np.broadcast_to(ddx, (H // 2, 2, W // 2, 2)), np.broadcast_to(ddy, (H // 2, 2, W // 2, 2))).reshape(H, W)
+        lam = np.where(rho > 0.0, np.log2(np.maximum(rho, 1e-300)), -1000.0)
+        ecol = np_trilinear(mips, cu, cv, lam)[..., :3]
+        ems_pdf = ew * eh * lum(ecol) / float(env[3])
+        edir = np_normalize(rot_left(edir, Mw))
+        prob = np.minimum(1.0 - EPS, _dot(edir, view_normal) * rough)
+        is_env = rnd[..., 3] < prob
+        ems_pdf = np.where(is_env, ems_pdf / (1.0 - prob), 1.0 - prob)
+        diffuse_ray = np.where(is_env[..., None], edir, diffuse_ray)
+        spec_ray = np.where(is_env[..., None], edir, spec_ray)
+
+    def env_color(ll, diffuse_sample):  # getEnvColor  ssgi.frag:311-346
+        if not use_env:
+            return np.zeros((H, W, 3))
+        eu, ev = np_equirect_uv(np_normalize(rot_left(ll, V_)))
+        mip = np.full((H, W), p.env_blur * p.max_env_map_mip_level)
+        if not diffuse_sample:
+            mip = np.where(rsq < 0.15, mip * (rsq / 0.15), mip)
+        s = np_trilinear(mips, eu, ev, mip)[..., :3]
+        cap = np.where(is_env, 100.0, 25.0)
+        el = lum(s)
+        return np.where((el > cap)[..., None], s * (cap / np.where(el == 0.0, 1.0, el))[..., None], s)
 
     def d_gtr2(a, NoH):
         a2 = a * a
@@ -467,15 +540,18 @@ def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue):
         k = ((1.0 - rsq) * sat * 0.4)[..., None]
         rgi = rgi * (1.0 - k) + lum(rgi)[..., None] * k
         sm = lambda e0, e1, x: (lambda t: t * t * (3.0 - 2.0 * t))(np.clip((x - e0) / (e1 - e0), 0.0, 1.0))  # noqa: E731
-        bf = np.sqrt(sm(0.0, 0.15, cu) * sm(1.0, 0.85, cu) * sm(0.0, 0.15, cv) * sm(1.0, 0.85, cv))
-        gi = np.where((hit & inside)[..., None], rgi * bf[..., None], 0.0)   # env colour is 0 without USE_ENVMAP
-        gi = gi * brdf[..., None] / pdf[..., None]
+        bf = np.sqrt(sm(0.0, 0.15, cu) * sm(1.0, 0.85, cu) * sm(0.0, 0.15, cv) * sm(1.0, 0.85, cv))[..., None]
+        ec = env_color(ll, diffuse_sample)   # (the shader passes the march-scaled l; it is normalised inside, so the scale drops out)
+        gi = np.where((hit & inside)[..., None], ec * (1.0 - bf) + rgi * bf, ec)   # miss or off-screen reprojection: the env colour alone
+        gi = gi * brdf[..., None]
+        aa, bb = ems_pdf * ems_pdf, pdf * pdf                               # misHeuristic for env samples, plain 1/pdf otherwise
+        gi = np.where(is_env[..., None], gi * (aa / (aa + bb))[..., None], gi / pdf[..., None]) / ems_pdf[..., None]
         return gi, np.where(hit[..., None], pos, 10.0e9)
 
     gi_d, _ = do_sample(diffuse_ray, True)
     # the specular sample evaluates the diffuse BRDF when the pixel drew the diffuse lottery (isDiffuseSample is passed through :246-249)
-    gi_s_spec, hit_pos = do_sample(l, False)
-    gi_s_diff, _ = do_sample(l, True)
+    gi_s_spec, hit_pos = do_sample(spec_ray, False)
+    gi_s_diff, _ = do_sample(spec_ray, True)
     gi_s = np.where(is_diffuse[..., None], gi_s_diff, gi_s_spec)
     dl = direct.astype(np.float64)
     if p.flags & abi.SSGI_USE_DIRECT_LIGHT:
@@ -490,13 +566,18 @@ def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue):
     return (out + 1e-4).astype(np.float16).astype(np.float64)   # packTwoVec4: the stored fp16 values carry the +1e-4 offset
 
 
-def test_ssgi_trace_oracle_matches_numpy_restatement():
-    o = ch.Opts(use_envmap=False, importance_sampling=False, use_direct_light=True, steps=10, refine_steps=3, denoise_iterations=1)
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("env_on", [False, True])
+def test_ssgi_trace_oracle_matches_numpy_restatement(env_on):
+    o = ch.Opts(use_envmap=env_on, importance_sampling=env_on, use_direct_light=True, steps=10, refine_steps=3, denoise_iterations=1)
     inp = ch.make_inputs(96, 64, 2)
     recs = ch.run_oracle_chain(inp, o)
+    env = (inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total) if env_on else None
     for t in (0, 1):
         fr, rec = inp.frames[t], recs[t]
-        want = np_ssgi_trace(rec["_k1_params"], fr["depth"], fr["gbuffer"], fr["direct"], rec["_k1_accumulated"], inp.blue)
+        want = np_ssgi_trace(rec["_k1_params"], fr["depth"], fr["gbuffer"], fr["direct"], rec["_k1_accumulated"], inp.blue, env)
         got = ch.unpack_halves(rec["ssgi"]).astype(np.float64)
         # discrete choices (lottery vs an 8-bit noise value, hit tests, nearest texels) can flip between fp32 and fp64 for a few rays
         frac = _agree(want, got, 3e-3, 3e-4, 1.5e-2)
