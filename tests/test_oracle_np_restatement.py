@@ -12,7 +12,9 @@ colour fetch, MIS weights, equirect lookup with the roughness-scaled mip and the
 neighbourhood clamp, accumulation), K3 Poisson denoise (poisson_denoise.frag:52-208, both the NEAREST fp32 first pass and the
 LINEAR fp16 later passes, two planes, G-buffer variant), the G-buffer material decode it uses (gbuffer_packing.glsl:24-63,
 151-196), the blue-noise lookup (blue_noise.glsl:9-48), K4 GI compose (DenoiserComposePass.js:58-85 +
-denoiser_compose_functions.glsl:13-107), K7 ao_compose.frag:6-16 and K9 traa_compose.frag:3-6.
+denoiser_compose_functions.glsl:13-107), K5 ssgi_compose.frag:20-44, K6 HBAO (hbao.frag:21-96 + hbao_utils.glsl), K7
+ao_compose.frag:6-16, K8 motion blur (motion_blur.frag:11-44, incl. the tiled frame-0 lookup and a window size that differs
+from the buffer size) and K9 traa_compose.frag:3-6.  Not covered: the TRAA (one-plane) form of K2 and the SSR mode of K1.
 
 What the exercise found: the two restatements disagreed twice, both times on a documented reference quirk that only one of
 them had modelled - GLSL's fp32 `mod` on packed values above 2^24 (metalness = 1) and `max(EPSILON, NaN)` returning EPSILON -
@@ -707,3 +709,118 @@ def test_temporal_reproject_oracle_matches_numpy_restatement():
         assert _agree(w0, rec["tr0"], 2e-4, 1e-5, 2e-3) < 2e-3   # (measured: 0 pixels outside 1e-4)
         assert _agree(w1, rec["tr1"], 2e-4, 1e-5, 2e-3) < 2e-3
         assert (rec["tr0"][..., 3] > 0.5).any()  # some history was actually accumulated
+
+
+# ---- K8 motion blur, K5 ssgi compose -----------------------------------------------------------------------------------------
+def np_motion_blur(p: abi.MotionBlurParams, velocity, inp_f16, blue):
+    """motion_blur.frag:11-44; blueNoise(vUv, frame) with pixel = ivec2(vUv * resolution) where `resolution` is the WINDOW size"""
+    H, W = velocity.shape[:2]
+    ys, xs = np.mgrid[0:H, 0:W]
+    u, v = (xs + 0.5) / W, (ys + 0.5) / H
+    vel = velocity[..., :2].astype(np.float64)
+    moved = _dot(vel, vel) > 0.000000001
+    vel = vel * p.intensity
+    rx, ry = float(p.resolution[0]), float(p.resolution[1])
+    if p.frame == 0:   # tiled lookup: textureLod(blueNoise, uv * resolution / blueNoiseSize), NEAREST + REPEAT
+        bx, by = np.floor(u * rx / 128.0 * 128.0).astype(np.int64) % 128, np.floor(v * ry / 128.0 * 128.0).astype(np.int64) % 128
+    else:
+        sx, sy = np_pcg4d_shift(p.frame)
+        bx, by = (np.floor(u * rx).astype(np.int64) + sx) % 128, (np.floor(v * ry).astype(np.int64) + sy) % 128
+    bn = blue[by, bx].astype(np.float64) / 255.0
+    jit = p.jitter * vel * bn[..., :2]
+    speed = (1.0 / 100.0) / p.delta_time
+    start = np.maximum(0.0, np.stack([u, v], -1) + (jit - vel * 0.5) * speed)
+    end = np.minimum(1.0, np.stack([u, v], -1) + (jit + vel * 0.5) * speed)
+    col = inp_f16.astype(np.float64)
+    acc = col[..., :3].copy()
+    n = float(p.samples)
+    for i in range(p.samples + 1):
+        uv = start * (1.0 - i / n) + end * (i / n)
+        acc += np_bilinear(inp_f16, uv[..., 0], uv[..., 1])[..., :3]
+    out = np.concatenate([acc / (n + 2.0), col[..., 3:4]], -1)
+    return np.where(moved[..., None], out, col)
+
+
+@pytest.mark.parametrize("frame,res", [(7, None), (0, None), (33, (130, 70))])
+def test_motion_blur_oracle_matches_numpy_restatement(frame, res):
+    H, W = 48, 80
+    rng = np.random.default_rng(5)
+    depth = rng.random((H, W)).astype(np.float32)
+    vel = ch.rotation_velocity_field(W, H, depth)
+    col = (rng.random((H, W, 4)) * 2.0).astype(np.float16)
+    p = ch.motion_blur_params(W, H, frame=frame, resolution=res)
+    inp = ch.make_inputs(32, 16, 1)
+    got = orc.motion_blur(p, vel, col, inp.blue).astype(np.float64)
+    want = np_motion_blur(p, vel, col, inp.blue)
+    assert _agree(want, got, 2e-3, 1e-4, 2e-3) < 2e-3 and (got[:8, :8] == col[:8, :8].astype(np.float64)).all()
+
+
+def np_hbao(p: abi.HbaoParams, depth, blue, prev):
+    """hbao.frag:21-96 + hbao_utils.glsl (normal from depth, the spp-sample form: blueNoise() returns the same texel for every sample)"""
+    H, W = depth.shape
+    M = lambda arr: np.asarray(list(arr), np.float64).reshape(4, 4).T  # noqa: E731
+    PV, Pinv, Mw = M(p.projection_view), M(p.projection_inverse), M(p.camera_matrix_world)
+    ys, xs = np.mgrid[0:H, 0:W]
+    u, v = (xs + 0.5) / W, (ys + 0.5) / H
+    d = depth.astype(np.float64)
+
+    def world(dd, uu, vv):  # getWorldPos  hbao_utils.glsl:19-29
+        clip = np.stack([uu * 2.0 - 1.0, vv * 2.0 - 1.0, dd * 2.0 - 1.0, np.ones_like(dd)], -1)
+        w = (clip @ Pinv.T) @ Mw.T
+        return w[..., :3] / w[..., 3:4]
+
+    tap = lambda dx, dy: d[np.clip(ys + dy, 0, H - 1), np.clip(xs + dx, 0, W - 1)]  # noqa: E731  texelFetch, clamped
+    c0, l2, l1, r1, r2, b2, b1, t1, t2 = tap(0, 0), tap(-2, 0), tap(-1, 0), tap(1, 0), tap(2, 0), tap(0, -2), tap(0, -1), tap(0, 1), tap(0, 2)
+    dl, dr, db, dt = np.abs((2 * l1 - l2) - c0), np.abs((2 * r1 - r2) - c0), np.abs((2 * b1 - b2) - c0), np.abs((2 * t1 - t2) - c0)
+    ce = world(c0, u, v)
+    dpdx = np.where((dl < dr)[..., None], ce - world(l1, u - 1.0 / W, v), -ce + world(r1, u + 1.0 / W, v))
+    dpdy = np.where((db < dt)[..., None], ce - world(b1, u, v - 1.0 / H), -ce + world(t1, u, v + 1.0 / H))
+    n = np_normalize(np.cross(dpdx, dpdy))
+    cam = Mw[:3, 3]
+    bn = np_blue_noise(blue, p.blue_noise_index, W, H)
+    r_, th_ = np.sqrt(bn[..., 0]), 2.0 * np.pi * bn[..., 1]
+    b_ = np_normalize(np.cross(n, np.broadcast_to(np.array([0.0, 1.0, 1.0]), n.shape)))
+    t_ = np.cross(b_, n)
+    sdir = np_normalize((r_ * np.sin(th_))[..., None] * b_ + np.sqrt(1.0 - bn[..., 0])[..., None] * n + (r_ * np.cos(th_))[..., None] * t_)
+    spos = ce + (p.ao_distance * np.power(bn[..., 2], p.distance_power + 1.0))[..., None] * sdir
+    suv = np.concatenate([spos, np.ones((H, W, 1))], -1) @ PV.T
+    su, sv = suv[..., 0] / suv[..., 3] * 0.5 + 0.5, suv[..., 1] / suv[..., 3] * 0.5 + 0.5
+    sdepth = np_nearest(depth, su, sv).astype(np.float64)
+    dist = np.linalg.norm(spos - cam, axis=-1)
+    delta = (d - sdepth) * 0.001 * dist * dist
+    th = p.thickness * 0.01
+    theta = _dot(n, sdir)
+    occ = np.sqrt(10.0 * np.maximum(0.0, sdepth + delta * p.bias * 1000.0 - d) * theta * np.maximum(0.0, 1.0 - delta / th) / dist)
+    occ = np.where(delta < th, occ, 0.0)
+    total = p.spp * theta
+    ao = p.spp * occ
+    ao = np.where(total > 0.0, ao / np.where(total == 0.0, 1.0, total), ao)
+    out = np.concatenate([n, np.clip(1.0 - ao, 0.0, 1.0)[..., None]], -1)
+    return np.where((depth == 1.0)[..., None], prev.astype(np.float64), out)
+
+
+def test_hbao_oracle_matches_numpy_restatement():
+    inp = ch.make_inputs(96, 64, 2)
+    fr = inp.frames[1]
+    p = ch.hbao_params(fr["cam"], 4242)
+    prev = np.zeros((64, 96, 4), np.float16)
+    got = orc.hbao(p, fr["depth"], inp.blue, prev).astype(np.float64)
+    want = np_hbao(p, fr["depth"], inp.blue, prev)
+    # fp16 target; the normal reconstruction picks the smoother side by comparing depth differences (dl < dr), which can flip at
+    # silhouettes between fp32 and fp64, and so can the nearest depth tap of the sample
+    assert _agree(want, got, 1e-3, 1e-3, 5e-3) < 5e-3   # (measured: 1 pixel of 6144)
+    geo = fr["depth"] < 1.0
+    assert (got[geo][:, 3] < 0.99).any() and (got[~geo] == 0.0).all()
+
+
+def test_ssgi_compose_oracle_matches_numpy_restatement():
+    rng = np.random.default_rng(6)
+    H, W = 20, 36
+    depth = rng.random((H, W)).astype(np.float32)
+    depth[rng.random((H, W)) < 0.3] = 1.0
+    gi = (rng.random((H, W, 4)) * 4).astype(np.float32)
+    scene = (rng.random((H, W, 4)) * 4).astype(np.float16)
+    got = orc.ssgi_compose(depth, gi, scene).astype(np.float64)   # ssgi_compose.frag:20-44 without fog: background -> scene colour, else the GI
+    want = np.where((depth == 1.0)[..., None], scene[..., :3].astype(np.float64), gi[..., :3].astype(np.float64))
+    _agree(want, got[..., :3], 1e-3, 1e-6, 0.0)
+    assert (got[..., 3] == 1.0).all()
