@@ -11,7 +11,8 @@
 //  and its GLSL cannot be executed in this environment (no GL, no JS
 // engine).  This oracle is therefore a restatement checked by inspection against the GLSL,
 // by self-consistency properties and by independent numpy restatements of its leaf
-// functions (tests/test_oracle_*.py) — not against output of a real WebGL run.
+// functions and of every whole pass K1-K9 (tests/test_oracle_leaf.py,
+// tests/test_oracle_np_restatement.py) — not against output of a real WebGL run.
 //
 // Implementation-defined GL behaviour is fixed as documented in oracle/glsl.h.
 #include "glsl.h"
