@@ -14,7 +14,7 @@ LINEAR fp16 later passes, two planes, G-buffer variant), the G-buffer material d
 151-196), the blue-noise lookup (blue_noise.glsl:9-48), K4 GI compose (DenoiserComposePass.js:58-85 +
 denoiser_compose_functions.glsl:13-107), K5 ssgi_compose.frag:20-44, K6 HBAO (hbao.frag:21-96 + hbao_utils.glsl), K7
 ao_compose.frag:6-16, K8 motion blur (motion_blur.frag:11-44, incl. the tiled frame-0 lookup and a window size that differs
-from the buffer size) and K9 traa_compose.frag:3-6.  Not covered: the TRAA (one-plane) form of K2 and the SSR mode of K1.
+from the buffer size) and K9 traa_compose.frag:3-6; K1 also in MODE_SSR and K2 also in the one-plane form TRAAEffect drives.
 
 What the exercise found: the two restatements disagreed twice, both times on a documented reference quirk that only one of
 them had modelled - GLSL's fp32 `mod` on packed values above 2^24 (metalness = 1) and `max(EPSILON, NaN)` returning EPSILON -
@@ -396,7 +396,8 @@ def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue, 
     (map fp16 (h, w, 4), marginal, conditional, total_sum)); the velocity sampler is the null sampler of the shipped wiring
     (SURVEY.md D4).  Returns the 8 stored fp16 channels as float64."""
     use_env, use_is = bool(p.flags & abi.SSGI_USE_ENVMAP), bool(p.flags & abi.SSGI_IMPORTANCE_SAMPLING)
-    assert not (p.flags & abi.SSGI_MISSED_RAYS) and p.mode == abi.MODE_SSGI and (env is not None or not (use_env or use_is))
+    assert not (p.flags & abi.SSGI_MISSED_RAYS) and (env is not None or not (use_env or use_is))
+    ssr = p.mode == abi.MODE_SSR
     H, W = depth.shape
     cam = p.cam
     M = lambda arr: np.asarray(list(arr), np.float64).reshape(4, 4).T  # noqa: E731
@@ -448,7 +449,7 @@ def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue, 
     diffW = np.maximum((1.0 - metal) * lum(diffuse), EPS)
     specW = np.maximum(lum(F), EPS)
     diffW = diffW * (1.0 / (diffW + specW))
-    is_diffuse = rnd[..., 2] < diffW
+    is_diffuse = (rnd[..., 2] < diffW) & (not ssr)   # MODE_SSR never takes a diffuse sample (:188-190)
     # cosineSampleHemisphere(viewNormal, random.rg)  ssgi_utils.frag:183-191
     r_, th = np.sqrt(rnd[..., 0]), 2.0 * np.pi * rnd[..., 1]
     b_ = np_normalize(np.cross(n, np.broadcast_to(np.array([0.0, 1.0, 1.0]), n.shape)))
@@ -562,10 +563,14 @@ def np_ssgi_trace(p: abi.SsgiParams, depth, gbuffer, direct, accumulated, blue, 
     cam_pos = Mw[:3, 3]
     hp_ws = np.concatenate([hit_pos, np.ones((H, W, 1))], -1) @ Mw.T
     ray_len = np.where(hit_pos[..., 0] > 10.0e8, 0.0, np.linalg.norm(cam_pos - hp_ws[..., :3], axis=-1))
+    bg = (np.concatenate([dl, dl], -1) + 1e-4).astype(np.float16)   # the background branch packs two vec4 in BOTH modes (:109-113)
+    if ssr:  # MODE_SSR: plain RGBA32F texel (specularGI, bits of packHalf2x16(rayLength, roughness))  :298-308
+        alpha = np.stack([ray_len, rough], -1).astype(np.float16)
+        out = np.concatenate([gi_s.astype(np.float32), alpha.view(np.float32).reshape(H, W, 1)], -1)
+        return np.where((depth == 1.0)[..., None], bg.view(np.float32).reshape(H, W, 4), out)
     out = np.concatenate([gi_d, rough[..., None], gi_s, ray_len[..., None]], -1)
-    bg = np.concatenate([dl, dl], -1)
-    out = np.where((depth == 1.0)[..., None], bg, out)
-    return (out + 1e-4).astype(np.float16).astype(np.float64)   # packTwoVec4: the stored fp16 values carry the +1e-4 offset
+    out = (out + 1e-4).astype(np.float16)                           # packTwoVec4: the stored fp16 values carry the +1e-4 offset
+    return np.where((depth == 1.0)[..., None], bg, out).astype(np.float64)
 
 
 import pytest  # noqa: E402
@@ -587,10 +592,30 @@ def test_ssgi_trace_oracle_matches_numpy_restatement(env_on):
         assert frac < 1.5e-2 and (want[geo][:, 0] < -0.9).any() and (want[geo][:, 0] >= 0.0).any() and (want[geo][:, 7] > 1.0).any()
 
 
+def test_ssr_mode_trace_oracle_matches_numpy_restatement():
+    o = ch.Opts(mode=abi.MODE_SSR, steps=10, refine_steps=3, denoise_iterations=1)
+    inp = ch.make_inputs(96, 64, 2)
+    recs = ch.run_oracle_chain(inp, o)
+    env = (inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+    for t in (0, 1):
+        fr, rec = inp.frames[t], recs[t]
+        want = np_ssgi_trace(rec["_k1_params"], fr["depth"], fr["gbuffer"], fr["direct"], rec["_k1_accumulated"], inp.blue, env)
+        got, geo = rec["ssgi"], fr["depth"] < 1.0
+        assert _agree(want[..., :3][geo].astype(np.float64), got[..., :3][geo].astype(np.float64), 1e-3, 1e-5, 1.5e-2) < 1.5e-2
+        wa = np.ascontiguousarray(want[..., 3]).view(np.uint32)[geo]     # packed (rayLength, roughness) halves
+        ga = np.ascontiguousarray(got[..., 3]).view(np.uint32)[geo]
+        assert ((wa >> 16) == (ga >> 16)).all()                           # roughness: exact
+        rl = lambda a: (a & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)  # noqa: E731
+        assert _agree(rl(wa), rl(ga), 2e-3, 1e-3, 1.5e-2) < 1.5e-2        # ray length: to fp16, a few rays flip hit / miss
+        assert (want[~geo].view(np.uint32) == got[~geo].view(np.uint32)).all()   # background texels: bit-equal packing of the direct light
+
+
 # ---- K2 (SSGI form: two planes, packed K1 input, log transform, LINEAR fp16 history) -----------------------------------------
 def np_temporal(p: abi.TemporalParams, ssgi_packed, velocity, hist, prev_out):
     """temporal_reproject.frag:42-208 + reproject.frag (inputType DIFFUSE_SPECULAR, textureCount 2, logTransform)."""
-    assert p.input_type == abi.INPUT_DIFFUSE_SPECULAR and p.texture_count == 2 and p.log_transform and p.history_linear
+    traa = p.input_type == abi.INPUT_DIFFUSE   # the one-plane form TRAAEffect drives: RGBA16F composer input, no discard, no hit-point reprojection
+    assert (traa and p.texture_count == 1) or (p.input_type == abi.INPUT_DIFFUSE_SPECULAR and p.texture_count == 2)
+    assert p.log_transform and p.history_linear
     H, W = velocity.shape[:2]
     M = lambda arr: np.asarray(list(arr), np.float64).reshape(4, 4).T  # noqa: E731
     cam = p.cam
@@ -610,15 +635,19 @@ def np_temporal(p: abi.TemporalParams, ssgi_packed, velocity, hist, prev_out):
     vel = velocity[..., :2].astype(np.float64)
     wnormal = np_unpack_normal(velocity[..., 2].copy())
     depth = velocity[..., 3].astype(np.float64)
-    halves = ch.unpack_halves(ssgi_packed).astype(np.float64) - 1e-4          # unpackTwoVec4
-    inp = [halves[..., 0:4].copy(), halves[..., 4:8].copy()]
+    if traa:
+        halves = ssgi_packed.astype(np.float64)                                # LINEAR fetch at the pixel centre = the texel
+        inp = [halves.copy()]
+    else:
+        halves = ch.unpack_halves(ssgi_packed).astype(np.float64) - 1e-4      # unpackTwoVec4
+        inp = [halves[..., 0:4].copy(), halves[..., 4:8].copy()]
     sampled = [t[..., 0] >= 0.0 for t in inp]
     for t in inp:
         t[..., :3] = np.log(np.maximum(t[..., :3], 0.0) + 1.0)
-    discard = (velocity[..., 3] == 1.0) & (np_fwidth(depth) == 0.0)
+    discard = (velocity[..., 3] == 1.0) & (np_fwidth(depth) == 0.0) & (not traa)
     curvature = np.linalg.norm(np_fwidth(wnormal), axis=-1)
     wpos = to_world(u, v, depth, Mw, Pinv)
-    ray_len, rough = inp[1][..., 3], np.clip(inp[0][..., 3], 0.0, 1.0)
+    ray_len, rough = (np.zeros((H, W)), np.ones((H, W))) if traa else (inp[1][..., 3], np.clip(inp[0][..., 3], 0.0, 1.0))
     view_z = np.abs(near * far / ((far - near) * depth - far))
     dist_factor = 1.0 + 1.0 / (view_z + 1.0)
 
@@ -661,7 +690,7 @@ def np_temporal(p: abi.TemporalParams, ssgi_packed, velocity, hist, prev_out):
 
     lin = [np.exp(t[..., :3]) - 1.0 for t in inp]  # undoColorTransform(inputColor) for the clamp box
     outs = []
-    for i in range(2):
+    for i in range(p.texture_count):
         spec = bool(p.reproject_specular[i])
         uvc = uvc_s if spec else uvc_d
         acc = catmull(hist[i], uvc[0], uvc[1])
@@ -824,3 +853,18 @@ def test_ssgi_compose_oracle_matches_numpy_restatement():
     want = np.where((depth == 1.0)[..., None], scene[..., :3].astype(np.float64), gi[..., :3].astype(np.float64))
     _agree(want, got[..., :3], 1e-3, 1e-6, 0.0)
     assert (got[..., 3] == 1.0).all()
+
+
+def test_traa_form_of_temporal_reproject_matches_numpy_restatement():
+    """K2 as TRAAEffect drives it (src/traa/TRAAEffect.js:21-31): one RGBA16F plane, inputType DIFFUSE, no discard, maxBlend 0.9,
+    neighborhoodClampIntensity 1, confidencePower 4; the history here is last frame's colour buffer with alpha = a history length."""
+    inp = ch.make_inputs(96, 64, 3)
+    f0, f1 = inp.frames[1], inp.frames[2]
+    p = ch.traa_temporal_params(abi.make_camera(f1["cam"]), f1["cam"]["position"], f0["cam"], 1.0)
+    hist = f0["direct"].copy()
+    hist[..., 3] = np.float16(3.0)
+    z = np.zeros((64, 96, 4), np.float16)
+    got, _ = orc.temporal_reproject(p, f1["direct"], f1["velocity"], hist, None, z, None, out_half=True)
+    (want,) = np_temporal(p, f1["direct"], f1["velocity"], [hist], [z])
+    assert _agree(want, got.astype(np.float64), 2e-3, 1e-4, 5e-3) < 5e-3
+    assert (got[..., 3].astype(np.float64) > 0.5).mean() > 0.3   # history was blended in on a good part of the frame
