@@ -16,6 +16,10 @@ k1)
   python -m pytest tests -m gpu -x -q 2>&1 | tail -2          # parity with the rewritten loop (expected: bit-identical K1)
   python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | line "simple march             "
   python bench.py --steps 8 --warmup 3 --no-cpu-baseline --split-parts 2>/dev/null | tail -1 | line "simple march, split K1   "
+  rm -f realism_effects_b200/csrc/build/k_ssgi.o
+  RFX_NVCC_EXTRA="-DRFX_K1_SIMPLE_MARCH=1 -DRFX_K1_FAST_TRIG=1" python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
+  python -m pytest tests -m gpu -x -q 2>&1 | tail -2          # polynomial atan2 / acos in the fast env lookup: within the 1e-3 bars?
+  python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | line "simple march + poly trig "
   rm -f realism_effects_b200/csrc/build/k_ssgi.o; python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
   ;;
 n8)
