@@ -855,6 +855,50 @@ def test_ssgi_compose_oracle_matches_numpy_restatement():
     assert (got[..., 3] == 1.0).all()
 
 
+def test_env_cdf_tables_match_a_loop_for_loop_restatement():
+    """synth.build_env_cdf (vectorised; it feeds rfx_env_set) against a statement-by-statement Python walk of gatherData
+    (src/ssgi/utils/EquirectHdrInfoUniform.js:149-245): Float32Array stores, double accumulators, the lower-bound binary search."""
+    from realism_effects_b200 import synth
+
+    rng = np.random.default_rng(11)
+    h, w = 8, 16
+    data = (rng.random((h, w, 4)) ** 4 * 20.0).astype(np.float32)
+    data[3] = 0.0                      # an all-black row: its conditional CDF stays unnormalised (all zeros)
+    f32 = np.float32
+    pdf_c, cdf_c, cdf_m = np.zeros(h * w, f32), np.zeros(h * w, f32), np.zeros(h, f32)
+    total, cum_m = 0.0, 0.0
+    for y in range(h):
+        cum = 0.0
+        for x in range(w):
+            wgt = 0.2126 * float(data[y, x, 0]) + 0.7152 * float(data[y, x, 1]) + 0.0722 * float(data[y, x, 2])
+            cum += wgt
+            total += wgt
+            pdf_c[y * w + x], cdf_c[y * w + x] = f32(wgt), f32(cum)
+        if cum != 0:
+            for i in range(y * w, y * w + w):
+                cdf_c[i] = f32(float(cdf_c[i]) / cum)
+        cum_m += cum
+        cdf_m[y] = f32(cum_m)
+    if cum_m != 0:
+        for i in range(h):
+            cdf_m[i] = f32(float(cdf_m[i]) / cum_m)
+
+    def closest(arr, target, offset, count):
+        lower, upper = offset, offset + count - 1
+        while lower < upper:
+            mid = (lower + upper) >> 1
+            if float(arr[mid]) < target:
+                lower = mid + 1
+            else:
+                upper = mid
+        return lower - offset
+
+    marg = np.array([(closest(cdf_m, (i + 1) / h, 0, h) + 0.5) / h for i in range(h)], f32)
+    cond = np.array([[(closest(cdf_c, (x + 1) / w, y * w, w) + 0.5) / w for x in range(w)] for y in range(h)], f32)
+    m2, c2, t2 = synth.build_env_cdf(data)
+    assert np.array_equal(m2, marg) and np.array_equal(c2, cond) and abs(t2 - total) <= 1e-9 * total
+
+
 def test_traa_form_of_temporal_reproject_matches_numpy_restatement():
     """K2 as TRAAEffect drives it (src/traa/TRAAEffect.js:21-31): one RGBA16F plane, inputType DIFFUSE, no discard, maxBlend 0.9,
     neighborhoodClampIntensity 1, confidencePower 4; the history here is last frame's colour buffer with alpha = a history length."""
