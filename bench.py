@@ -190,8 +190,14 @@ def run_ours(args):
             else:
                 chain.render(*a, ranges=force_ranges)
     else:
-        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=args.balance, split_k1=bool(args.split_k1),
-                                            dual_comm=bool(args.dual_comm))
+        # auto: measured up to 4 GPUs, adaptive bands win (N = 2: 4.70 vs 5.14 ms, N = 4: 6.02 vs 7.04 ms against cyclic blocks).  At 8
+        # GPUs the frame is exchange-bound and the grouped send/recv of unequal bands sustains only ~211 GB/s per rank with 7 peers
+        # (the overlap model reproduces the measured 11.8 ms), so from 8 GPUs on the block-cyclic assignment is used:
+        # equal blocks can be exchanged with NCCL's in-place all-gather (a real collective, not 7 point-to-point pairs per rank).
+        # This choice is model-based - round 1 had no GPU time left to measure it; tools/next_round_sweeps.sh n8 does.
+        balance = args.balance if args.balance != "auto" else ("adaptive" if world <= 4 else "static")
+        chain = parallel.ShardedSsgiChain(ctx, copt, blocks_per_rank=args.blocks_per_rank, overlap=not args.no_overlap, mirror=args.mirror, balance=balance,
+                                            split_k1=bool(args.split_k1), dual_comm=bool(args.dual_comm))
         native = chain.chain
         stream = chain.stream  # kernels + NCCL all-gathers are ordered on this stream
 
@@ -446,8 +452,9 @@ def main():
     ap.add_argument("--force-blocks", type=int, default=0, help="experiment (N = 1): issue each pass as this many row-block launches")
     ap.add_argument("--view-height", type=int, default=0, help="experiment: rows of the VIEW (aspect = width / view_height) when --height differs")
     ap.add_argument("--blocks-per-rank", type=int, default=4, help="N > 1: block-cyclic row blocks per rank (content balance)")
-    ap.add_argument("--balance", default="adaptive", choices=("adaptive", "static"),
-                    help="N > 1: adaptive = one band per rank, borders follow the measured kernel time; static = block-cyclic / mirrored blocks")
+    ap.add_argument("--balance", default="auto", choices=("auto", "adaptive", "static"),
+                    help="N > 1: adaptive = one band per rank, borders follow the measured kernel time (grouped send/recv exchange); static = "
+                         "block-cyclic / mirrored blocks (in-place all-gather); auto = adaptive up to 4 GPUs, static from 8 (see run_ours)")
     ap.add_argument("--split-parts", action="store_true", help="experiment (N = 1): issue every frame as K1 march / K1 shading / K2..K4")
     ap.add_argument("--dual-comm", type=int, default=0, help="experiment (N > 1): 1 = dnB exchange on a second NCCL communicator, concurrent with composed")
     ap.add_argument("--split-k1", type=int, default=1, help="N > 1: 1 = K1 as ray march + shading so the `composed` exchange hides behind the march")
