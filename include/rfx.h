@@ -302,7 +302,7 @@ typedef struct rfx_ssgi_chain_options {
   uint32_t ssgi_flags;         /* RFX_SSGI_* */
   int32_t mode;                /* RFX_MODE_* */
   int32_t blue_noise_start;    /* startIndex of BlueNoiseUtils.js:19 (pinned)          */
-  int32_t use_cuda_graph;      /* capture the frame into a CUDA graph                   */
+  int32_t _reserved;           /* (was use_cuda_graph: never implemented, removed)      */
 } rfx_ssgi_chain_options;
 
 typedef struct rfx_ssgi_frame {
@@ -364,6 +364,37 @@ rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* chain, const rfx_ssgi_host
  * render_host(f) == submit_host(f) + wait_host(chain, 0).  Results are bit-identical to rfx_ssgi_chain_render. */
 rfx_status rfx_ssgi_chain_submit_host(rfx_ssgi_chain* chain, const rfx_ssgi_host_frame* frame);
 rfx_status rfx_ssgi_chain_wait_host(rfx_ssgi_chain* chain, int32_t max_in_flight);
+
+/* ---- row-sharded multi-GPU groups (one process per GPU) ------------------------------------------------
+ * The path shards by output row band.  Bounded stencils (K2's 5x5 window, the Poisson taps, K4) are RECOMPUTED on row ranges
+ * widened by rfx_shard_ranges, so no pass exchanges a halo; the two produced planes the next frame samples at arbitrary uv
+ * (`composed` for K1's hit colour, `dn` for K2's history — src/ssgi/pass/SSGIPass.js:88, src/denoise/Denoiser.js:51) are read
+ * IN PLACE on the rank that owns the row, through CUDA-IPC peer mappings over NVLink, instead of being replicated.  The group
+ * owns an NCCL communicator for its one collective per frame (an all-gather of every rank's device-timed kernel cost, which is
+ * also the frame barrier) and the band table with its cost-driven rebalancing.  Results are bit-identical to the single-GPU
+ * chain.  NCCL is loaded at run time (libnccl.so.2); without it every entry below returns RFX_ERR_NCCL. */
+typedef struct rfx_group rfx_group;
+#define RFX_GROUP_ID_BYTES 128
+rfx_status rfx_group_get_unique_id(void* id128);   /* rank 0; hand the 128 bytes to the other ranks by any means */
+rfx_status rfx_group_create(rfx_ctx* ctx, const void* id128, int32_t rank, int32_t world, rfx_group** out);  /* collective */
+void rfx_group_destroy(rfx_group* group);
+int32_t rfx_group_rank(const rfx_group* group);
+int32_t rfx_group_world(const rfx_group* group);
+/* collective: maps every rank's history planes of `chain` (a fast SSGI chain with the same options on every rank) */
+rfx_status rfx_group_attach_chain(rfx_group* group, rfx_ssgi_chain* chain);
+/* band borders: world + 1 ascending rows, bounds[0] = 0, bounds[world] = height; rank r owns rows [bounds[r], bounds[r+1]) */
+rfx_status rfx_group_get_bounds(const rfx_group* group, uint32_t* bounds);
+rfx_status rfx_group_set_bounds(rfx_group* group, const uint32_t* bounds);   /* same values on every rank; next frame on */
+/* every > 0: move the borders towards equal device-timed kernel cost every `every` frames, from times `lag` frames old */
+rfx_status rfx_group_set_rebalance(rfx_group* group, int32_t every, int32_t lag);
+rfx_status rfx_group_last_costs(const rfx_group* group, float* ms_per_rank);  /* the times the last rebalance used */
+/* collective: one frame; this rank renders its band from full-frame input planes and joins the frame's collective on `stream` */
+rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
+/* pure host arithmetic, exported for hosts that drive the per-launch ranges themselves (and for the CPU tests):
+ * rows [ranges[2k], ranges[2k+1]) of launch k (K1, K2, K3 pass 0.., K4 in SSGI mode) for the band [own0, own1) */
+rfx_status rfx_shard_ranges(uint32_t width, uint32_t height, uint32_t own0, uint32_t own1, int32_t n_poisson_passes, float radius,
+                            int32_t ssgi_mode, uint32_t* ranges, uint32_t n_launches);
+rfx_status rfx_shard_rebalance(const uint32_t* bounds, const uint32_t* measured_bounds, const float* costs, int32_t n, uint32_t* out);
 
 /* Per-pass device timing (CUDA events recorded on the launching stream around every kernel of
  * the chain).  Slots: 0 K1 trace, 1 K2 temporal, 2 K3 pass 0, 3 K3 passes >= 1, 4 K4 compose.

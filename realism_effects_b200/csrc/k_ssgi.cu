@@ -566,10 +566,303 @@ __global__ void __launch_bounds__(kThreads, PHASE == 1 ? RFX_K1_MARCH_MIN_BLOCKS
   }
 }
 
+// ==========================================================================================================================
+// K1, fast variant (fast_math on, fused phase): same shader, restructured for what bounds it on B200 (profiles/r01_v4: issue
+// 68 %, 22.5 of 32 lanes active, 58 instructions per march tap):
+//   * the diffuse rays of a 16x16 block — only the pixels that win the diffuse / specular lottery cast one — are compacted
+//     through shared memory and traced by FULL warps, instead of every warp running its diffuse phase with ~45 % of its lanes;
+//   * the march tap is ~25 instructions: projection rows pre-scaled to texel units on the host, packed fp32x2 arithmetic
+//     (FFMA2), one-instruction index clamps, 32-bit word indexing of the viewZ plane;
+//   * in a row-sharded group (PEER) last frame's `composed` is sampled in place on the rank that owns the row (NVLink loads).
+// The per-pixel DECISIONS (lottery, env-sample choice) keep the IEEE arithmetic of the exact variant; the march positions may
+// differ from the oracle's by an ulp (measured at 4K: ~1e-5 of the rays resolve differently, tools/parity_at_size.py).
+// ==========================================================================================================================
+template <bool SPARSE>
+RFX_D float tap_viewz(const SsgiArgs& a, v3 p) {
+  f2 t;
+  if (SPARSE) {
+    const f2 c = f2fma(mkf2(p.x, p.y), mkf2(a.ps_x0, a.ps_y1), f2mul(mkf2(p.z), mkf2(a.ps_x2, a.ps_y2)));
+    t = f2fma(c, mkf2(fx_rcp(-p.z)), mkf2(a.ps_hw, a.ps_hh));
+  } else {
+    const v2 uv = view_to_screen<false, true>(a, p);
+    t = mkf2(uv.x * (float)a.W, uv.y * (float)a.H);
+  }
+  const int ix = clamp_idx(__float2int_rd(f2lo(t)), a.W - 1), iy = clamp_idx(__float2int_rd(f2hi(t)), a.H - 1);
+  return __ldg((const float*)a.viewz.p + (iy * a.vz_pitchw + ix));
+}
+RFX_D v3 fma3(v3 d, float s, v3 p) {
+  const f2 xy = f2fma(mkf2(d.x, d.y), mkf2(s), mkf2(p.x, p.y));
+  return mk3(f2lo(xy), f2hi(xy), fma_(d.z, s, p.z));
+}
+// RayMarch + BinarySearch  ssgi.frag:441-503
+template <bool SPARSE>
+RFX_D v2 march_fast(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit) {
+  dir = dir * (a.ray_distance / (float)a.steps);
+  hit = false;
+  const float* cs_row = a.step_table + noiseB;
+  v3 p = hitPos;
+  for (int i = 1; i < a.steps; i++, cs_row += 256) {
+    p = fma3(dir, __ldg(cs_row), p);
+    const float diff = tap_viewz<SPARSE>(a, p) - p.z;
+    if (diff >= 0.0f && diff < a.thickness) { hit = true; break; }
+  }
+  if (!hit) {
+    hitPos = mk3(10.0e9f);
+    return view_to_screen<SPARSE, true>(a, p);
+  }
+  if (a.refine_steps > 0) {
+    dir = dir * 0.5f;
+    p = p - dir;
+    for (int r = 0; r < a.refine_steps; r++) {
+      const float diff = tap_viewz<SPARSE>(a, p) - p.z;
+      dir = dir * 0.5f;
+      p = diff >= 0.0f ? p - dir : p + dir;
+    }
+  }
+  hitPos = p;
+  return view_to_screen<SPARSE, true>(a, p);
+}
+
+// doSample  ssgi.frag:362-439 (SFU arithmetic; `desat` = (1 - roughnessSq) * saturation(diffuse) * 0.4)
+template <bool SPARSE, bool PEER>
+RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughnessSq, float metalness, float desat, bool isDiffuseSample, bool isEnvSample, float NoV,
+                     float NoL, float NoH, float LoH, int noiseB, v3 l, v3& hitPos, float& brdf, float& pdf) {
+  const float cosTheta = fmaxf(0.0f, dot(viewNormal, l));
+  if (isDiffuseSample) {
+    brdf = evalDisneyDiffuse<true>(NoL, NoV, LoH, roughnessSq, metalness);
+    pdf = NoL * (1.0f / PI_F);
+  } else {
+    brdf = evalDisneySpecular<true>(roughnessSq, NoH, NoV, NoL);
+    pdf = GGXVNDFPdf<true>(NoH, NoV, roughnessSq);
+  }
+  brdf *= cosTheta;
+  pdf = fmaxf(SSGI_EPSILON, pdf);
+  hitPos = viewPos;
+  bool hit;
+  const v2 coords = march_fast<SPARSE>(a, l, hitPos, noiseB, hit);
+  const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
+  if (!hit && !allowMissedRays) return getEnvColor<true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  v2 vel = mk2(0.0f, 0.0f);
+  if (a.velocity.p) { const float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }
+  const v2 ruv = coords - vel;
+  const bool reproj_ok = ruv.x >= 0.0f && ruv.x <= 1.0f && ruv.y >= 0.0f && ruv.y <= 1.0f;
+  // a hit whose borderFactor is exactly 1 (the inner 70 % x 70 % of the screen) resolves to mix(env, rgi, 1) = rgi: no env fetch
+  const bool inner = reproj_ok && coords.x >= 0.15f && coords.x <= 1.0f - 0.15f && coords.y >= 0.15f && coords.y <= 1.0f - 0.15f;
+  v3 envColor = mk3(0.0f);
+  if (!inner) envColor = getEnvColor<true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  if (!reproj_ok) return envColor;
+  v3 rgi = mk3(0.0f);
+  if (a.accumulated.p) {
+    const int ix = nearest_i(ruv.x, a.W), iy = nearest_i(ruv.y, a.H);
+    const unsigned char* base = PEER ? peer_row_base(a.acc_peer, iy) : a.accumulated.p;
+    const float4 t = __ldg((const float4*)(base + ((unsigned)iy * (unsigned)a.accumulated.pitch + (unsigned)ix * 16u)));
+    rgi = mk3(t.x, t.y, t.z);
+  }
+  rgi = mix(rgi, mk3(lum_s(rgi)), desat);
+  v3 SSGI = rgi;
+  if (!inner) {
+    const float border = 0.15f;
+    float bf = smoothstep_<true>(0.0f, border, coords.x) * smoothstep_<true>(1.0f, 1.0f - border, coords.x) * smoothstep_<true>(0.0f, border, coords.y) *
+               smoothstep_<true>(1.0f, 1.0f - border, coords.y);
+    bf = sqrt_<true>(bf);
+    SSGI = mix(envColor, rgi, bf);
+  }
+  if (allowMissedRays && 0.0f > lum_s(SSGI)) SSGI = mk3(0.0f);
+  return SSGI;
+}
+
+#define K1Q_FIELDS 15
+template <int MODE, bool IS, bool SPARSE, bool PEER>
+__global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_fast_kernel(const __grid_constant__ SsgiArgs a) {
+  __shared__ float q[K1Q_FIELDS][kThreads];  // compacted diffuse-ray tasks of this block (structure of arrays)
+  __shared__ float dres[3][kThreads];        // their results, by the pixel's thread index
+  __shared__ int nq;
+  if (MODE == RFX_MODE_SSGI) {
+    if (threadIdx.x == 0) nq = 0;
+    __syncthreads();
+  }
+  int x, y;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
+  const uchar4 bn = __ldg(a.blue.tex + blue_index(a.blue, x, y));
+  const v4 random = mk4((float)bn.x / 255.0f, (float)bn.y / 255.0f, (float)bn.z / 255.0f, (float)bn.w / 255.0f);
+  const unsigned full = 0xffffffffu;
+  v2 cdfUv = mk2(0.0f, 0.0f);
+  float lambda = 0.0f;
+  if (IS) {  // env importance sample: the implicit-LOD colour fetch needs all four quad lanes
+    const float v = ld_r32f(a.env.marginal, nearest_i(random.x, a.env.marginal.w), 0);
+    const float u = ld_r32f(a.env.conditional, nearest_i(random.y, a.env.conditional.w), nearest_i(v, a.env.conditional.h));
+    cdfUv = mk2(u, v);
+    const v2 ux = mk2(__shfl_xor_sync(full, u, 1), __shfl_xor_sync(full, v, 1));
+    const v2 uy = mk2(__shfl_xor_sync(full, u, 2), __shfl_xor_sync(full, v, 2));
+    const v2 sz = mk2(a.env.size_x, a.env.size_y);
+    const v2 ddx = (ux - cdfUv) * sz, ddy = (uy - cdfUv) * sz;
+    const float rho = fmaxf(length(ddx), length(ddy));
+    lambda = rho > 0.0f ? lg2a_(rho) : -1000.0f;
+  }
+  const v2 vUv = pixel_uv(x, y, a.W, a.H);
+  const float unpackedDepth = active ? ld_r32f(a.depth, x, y) : 1.0f;
+  const bool live = active && unpackedDepth != 1.0f;
+  if (active && !live) {  // background :109-113
+    v4 dl = mk4(0.0f, 0.0f, 0.0f, 1.0f);
+    if (a.direct.p) dl = tex_h4_linear(a.direct, vUv);
+    st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(dl, dl));
+  }
+  // state that survives until the pixel's result is packed
+  v3 specularGI = mk3(0.0f);
+  float rayLength = 0.0f, roughness0 = 0.0f;
+  bool isDiffuseSample = false;
+  if (live) {
+    const float4 g = ld_f4(a.gb, x, y);
+    PixelMat m;
+    m.diffuse = xyz(floatToVec4(g.x));
+    const v3 worldNormal = unpackNormal(g.y);
+    m.roughness = gb_roughness(g.z);
+    m.metalness = gb_metalness(g.z);
+    roughness0 = m.roughness;
+    const float roughnessSq = clampf(m.roughness * m.roughness, 0.000001f, 1.0f);
+    const float viewZ = ssgi_view_z(a, unpackedDepth);
+    v3 viewPos;
+    {
+      const float clipW = a.cam.projection.m[2 * 4 + 3] * viewZ + a.cam.projection.m[3 * 4 + 3];
+      v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
+      clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
+      viewPos = xyz(mul(a.cam.projection_inverse, clip));
+      viewPos.z = viewZ;
+    }
+    const v3 viewDir = normalize(viewPos);
+    const v3 viewNormal = normalize(mul_dir_left(worldNormal, a.cam.camera_matrix_world));
+    const v3 n = viewNormal;
+    const v3 v = -viewDir;
+    const float NoV = fmaxf(SSGI_EPSILON, dot(n, v));
+    v3 V = mul_dir_left(v, a.cam.view_matrix);
+    const v3 N = worldNormal;
+    v3 T, B;
+    Onb(N, T, B);
+    V = ToLocal(T, B, N, V);
+    const v3 f0 = mix(mk3(0.04f), m.diffuse, m.metalness);
+    const float2 sc = __ldg(a.rot_table + bn.y);
+    v3 Hh = SampleGGXVNDF_cs(V, roughnessSq, roughnessSq, random.x, sc.y, sc.x);
+    if (Hh.z < 0.0f) Hh = -Hh;
+    v3 l = normalize(reflect(-V, Hh));
+    l = ToWorld(T, B, N, l);
+    l = mul_dir_left(l, a.cam.camera_matrix_world);
+    l = normalize(l);
+    float NoL, NoH, LoH, VoH;
+    calculateAngles<false>(l, v, n, NoL, NoH, LoH, VoH);  // VoH feeds the lottery threshold: IEEE
+    if (MODE == RFX_MODE_SSGI) {
+      const v3 F = f0 + (mk3(1.0f) - f0) * pow5<true>(1.0f - VoH);
+      float diffW = (1.0f - m.metalness) * lum_s(m.diffuse);
+      float specW = lum_s(F);
+      diffW = fmaxf(diffW, SSGI_EPSILON);
+      specW = fmaxf(specW, SSGI_EPSILON);
+      const float invW = 1.0f / (diffW + specW);
+      diffW *= invW;
+      isDiffuseSample = random.z < diffW;
+    }
+    float emsPdf = 1.0f, emsProbability = 0.0f;
+    bool emsIsEnvSample = false;
+    v3 envMisDir = mk3(0.0f);
+    if (IS) {  // ssgi.frag:197-215, ssgi_utils.frag:210-225
+      envMisDir = equirectUvToDirection<true>(cdfUv);
+      const v3 color = env_trilinear(a.env, cdfUv, lambda);
+      const float totalSum = a.env.total_sum_whole + a.env.total_sum_decimal;
+      const float pdf0 = lum_s(color) / totalSum;
+      emsPdf = a.env.size_x * a.env.size_y * pdf0;
+      envMisDir = normalize(mul_dir_left(envMisDir, a.cam.camera_matrix_world));
+      emsProbability = dot(envMisDir, viewNormal);
+      emsProbability *= m.roughness;
+      emsProbability = fminf(SSGI_ONE_MINUS_EPSILON, emsProbability);
+      emsIsEnvSample = random.w < emsProbability;
+      if (emsIsEnvSample) {
+        emsPdf /= 1.0f - emsProbability;
+        l = envMisDir;
+      } else {
+        emsPdf = 1.0f - emsProbability;
+      }
+    }
+    const float desat = (1.0f - roughnessSq) * getSaturation<true>(m.diffuse) * 0.4f;
+    if (MODE == RFX_MODE_SSGI) {  // queue the diffuse ray :222-242
+      const unsigned want = __ballot_sync(__activemask(), isDiffuseSample);
+      if (isDiffuseSample) {
+        const unsigned lane = threadIdx.x & 31;
+        const int leader = __ffs(want) - 1;
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(&nq, __popc(want));
+        base = __shfl_sync(want, base, leader);
+        const int slot = base + __popc(want & ((1u << lane) - 1u));
+        const v3 dray = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs<true>(viewNormal, random.x, sc.x, sc.y);
+        q[0][slot] = viewPos.x; q[1][slot] = viewPos.y; q[2][slot] = viewPos.z;
+        q[3][slot] = viewNormal.x; q[4][slot] = viewNormal.y; q[5][slot] = viewNormal.z;
+        q[6][slot] = dray.x; q[7][slot] = dray.y; q[8][slot] = dray.z;
+        q[9][slot] = roughnessSq; q[10][slot] = m.metalness; q[11][slot] = desat; q[12][slot] = NoV; q[13][slot] = emsPdf;
+        q[14][slot] = __uint_as_float((unsigned)threadIdx.x | ((unsigned)bn.z << 8) | (emsIsEnvSample ? 0x10000u : 0u));
+      }
+    }
+    // the specular ray :246-265
+    calculateAngles<true>(l, v, n, NoL, NoH, LoH, VoH);
+    v3 hitPos;
+    float brdf, pdf;
+    v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    gi = gi * brdf;
+    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
+    specularGI = vdiv_<true>(gi, emsPdf);
+    if (!(hitPos.x > 10.0e8f)) {  // :288-296
+      const v3 cameraPosWS = mk3(a.cam.camera_matrix_world.m[12], a.cam.camera_matrix_world.m[13], a.cam.camera_matrix_world.m[14]);
+      const v3 hitPosWS = xyz(mul(a.cam.camera_matrix_world, mk4(hitPos, 1.0f)));
+      const v3 dWS = cameraPosWS - hitPosWS;
+      rayLength = sqrt_<true>(dot(dWS, dWS));
+    }
+  }
+  if (MODE == RFX_MODE_SSGI) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < nq) {  // one compacted diffuse ray per thread: full warps
+      const v3 viewPos = mk3(q[0][t], q[1][t], q[2][t]), viewNormal = mk3(q[3][t], q[4][t], q[5][t]);
+      v3 l = mk3(q[6][t], q[7][t], q[8][t]);
+      const float roughnessSq = q[9][t], metalness = q[10][t], desat = q[11][t], NoV = q[12][t], emsPdf = q[13][t];
+      const unsigned w = __float_as_uint(q[14][t]);
+      const bool isEnv = (w & 0x10000u) != 0;
+      const v3 v = -normalize_<true>(viewPos);
+      float NoL, NoH, LoH, VoH;
+      calculateAngles<true>(l, v, viewNormal, NoL, NoH, LoH, VoH);
+      v3 hitPos;
+      float brdf, pdf;
+      v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, metalness, desat, true, isEnv, NoV, NoL, NoH, LoH, (int)((w >> 8) & 0xffu), l, hitPos, brdf, pdf);
+      gi = gi * brdf;
+      if (isEnv) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
+      gi = vdiv_<true>(gi, emsPdf);
+      const int o = (int)(w & 0xffu);
+      dres[0][o] = gi.x; dres[1][o] = gi.y; dres[2][o] = gi.z;
+    }
+    __syncthreads();
+  }
+  if (!live) return;
+  v3 diffuseGI = mk3(0.0f);
+  if (MODE == RFX_MODE_SSGI && isDiffuseSample) diffuseGI = mk3(dres[0][threadIdx.x], dres[1][threadIdx.x], dres[2][threadIdx.x]);
+  if (a.flags & RFX_SSGI_USE_DIRECT_LIGHT) {  // :267-272
+    v3 dl = mk3(0.0f);
+    if (a.direct.p) dl = xyz(tex_h4_linear(a.direct, vUv));
+    diffuseGI = diffuseGI + dl;
+    specularGI = specularGI + dl;
+  }
+  if (MODE == RFX_MODE_SSGI) {
+    if (!isDiffuseSample) diffuseGI = mk3(-1.0f);
+    st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(mk4(diffuseGI, roughness0), mk4(specularGI, rayLength)));
+  } else {
+    const float al = __uint_as_float(packHalf2x16(rayLength, roughness0));
+    st_f4(a.out.p, a.out.pitch, x, y, make_float4(specularGI.x, specularGI.y, specularGI.z, al));
+  }
+}
+
 template <int MODE, bool IS>
 static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
 #define RFX_K1_LAUNCH(SP, F, PH) ssgi_kernel<MODE, IS, SP, F, PH><<<grid, kThreads, 0, s>>>(a)
-  if (a.phase == 0) {
+  if (a.phase == 0 && a.fast && !a.legacy_fast) {
+    const bool peer = a.acc_peer.n > 1;
+    if (a.proj_sparse) { if (peer) ssgi_fast_kernel<MODE, IS, true, true><<<grid, kThreads, 0, s>>>(a); else ssgi_fast_kernel<MODE, IS, true, false><<<grid, kThreads, 0, s>>>(a); }
+    else { if (peer) ssgi_fast_kernel<MODE, IS, false, true><<<grid, kThreads, 0, s>>>(a); else ssgi_fast_kernel<MODE, IS, false, false><<<grid, kThreads, 0, s>>>(a); }
+  } else if (a.phase == 0) {
     if (a.proj_sparse) { if (a.fast) RFX_K1_LAUNCH(true, true, 0); else RFX_K1_LAUNCH(true, false, 0); }
     else { if (a.fast) RFX_K1_LAUNCH(false, true, 0); else RFX_K1_LAUNCH(false, false, 0); }
   } else if (a.phase == 1) {  // split phases exist for the fast variant only (rfx_api.cu falls back to the fused kernel otherwise)

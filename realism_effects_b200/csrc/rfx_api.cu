@@ -49,6 +49,8 @@ struct rfx_ctx {
   size_t k1rec_pitch = 0;
   int k1rec_w = 0, k1rec_h = 0;
   const RowSegs* segs_override = nullptr;  // set by the native chain: all owned row blocks in ONE launch
+  int legacy_k1 = 0;  // RFX_LEGACY_K1=1 in the environment: the round-1 fast K1 kernel (A/B timing)
+  const PeerPV* peer_accumulated = nullptr;  // set by the native chain in a row-sharded group: K1's `accumulated` rows live on their owners
 };
 
 static rfx_status fail(rfx_ctx* c, rfx_status st, const char* fmt, ...) {
@@ -82,6 +84,7 @@ rfx_status rfx_ctx_create(int device, rfx_ctx** out) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return RFX_ERR_CUDA;
   rfx_ctx* ctx = new rfx_ctx();
   ctx->device = device;
+  if (const char* e = getenv("RFX_LEGACY_K1")) ctx->legacy_k1 = atoi(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return RFX_ERR_CUDA;
@@ -301,6 +304,7 @@ static rfx_status blue_for(rfx_ctx* ctx, int index, BlueD& b) {
   b.shift.sx = (int)((s1[0] % 0x0fffffffu) % (uint32_t)ctx->blue_size);  // shift2 :31-34
   b.shift.sy = (int)((s1[1] % 0x0fffffffu) % (uint32_t)ctx->blue_size);
   b.index = index;
+  b.mask = (ctx->blue_size & (ctx->blue_size - 1)) == 0 ? ctx->blue_size - 1 : 0;
   return RFX_OK;
 }
 static void rows(uint32_t row0, uint32_t row1, uint32_t H, int& r0, int& r1) {
@@ -405,6 +409,14 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     ctx->viewz_pitch = ((size_t)a.W * 4 + 255) & ~(size_t)255;
     CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * a.H));
     ctx->viewz_w = a.W; ctx->viewz_h = a.H;
+  }
+  {  // fast fused kernel: projection rows in texel units (0.5 W P00, 0.5 W P20, 0.5 H P11, 0.5 H P21), word pitch of the viewZ plane
+    const float* M = p->cam.projection;
+    const float hw = 0.5f * (float)a.W, hh = 0.5f * (float)a.H;
+    a.ps_x0 = hw * M[0]; a.ps_x2 = hw * M[8]; a.ps_y1 = hh * M[5]; a.ps_y2 = hh * M[9]; a.ps_hw = hw; a.ps_hh = hh;
+    a.vz_pitchw = (int)(ctx->viewz_pitch / 4);
+    a.legacy_fast = ctx->legacy_k1;
+    if (ctx->peer_accumulated) a.acc_peer = *ctx->peer_accumulated;
   }
   a.phase = ctx->k1_phase;
   if (a.phase != 0 && !a.fast) {  // the split phases exist for the fast variant: otherwise phase 1 is empty and phase 2 is the fused kernel
@@ -628,10 +640,23 @@ rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* 
 // ==========================================================================================
 // native SSGI chain
 // ==========================================================================================
+struct IPlane {  // chain-internal plane (formats of k_chain.cu): raw pitched allocation
+  void* p = nullptr;
+  size_t pitch = 0;
+};
 struct rfx_ssgi_chain {
   rfx_ctx* ctx;
   rfx_ssgi_chain_options opt;
   rfx_plane ssgi_out{}, tr[2]{}, dnA[2]{}, dnB[2]{}, composed{};
+  // fast chain (fast_math on at creation, mode SSGI): interleaved internal planes; history planes are double-buffered by frame
+  // parity so that, in a row-sharded group, no rank overwrites rows a peer may still be reading (see rfx_group_*)
+  bool fastpath = false;
+  IPlane nrdz, tr32, dnA16, dnB16[2];
+  rfx_plane composed2[2]{};  // fast chain: composed of frame parity 0 / 1 (composed2[cur] is output 0)
+  struct rfx_group* group = nullptr;  // row-sharded group this chain is attached to (rfx_group_attach_chain)
+  PeerPV peer_composed[2]{}, peer_dn[2]{};
+  uint64_t frame_idx = 0;    // frames completed (advances with the frame's last launch)
+  bool views_valid = false;  // tr[]/dnB[] hold the split views of the current frame's interleaved planes
   // host-buffer entry points: two staging sets so frame i+1 uploads while frame i renders; H2D, kernels and D2H each get
   // their own stream and are ordered by events only (see rfx_ssgi_chain_submit_host)
   rfx_plane in_depth[2]{}, in_gb[2]{}, in_vel[2]{}, in_direct[2]{};
@@ -639,6 +664,7 @@ struct rfx_ssgi_chain {
   cudaStream_t s_up = nullptr, s_dn = nullptr;
   cudaEvent_t ev_up[2]{}, ev_rendered[2]{}, ev_dn[2]{};
   uint64_t host_submitted = 0;
+  int dn_buf[2] = {-1, -1};  // fast chain: which composed2[] buffer the D2H of staging set 0 / 1 reads
   // cross-frame state (TemporalReprojectPass.js:203-213)
   bool have_prev = false;
   float prev_view[16], prev_world[16], prev_proj[16], prev_proj_inv[16], prev_pos[3];
@@ -679,9 +705,22 @@ rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt
   ch->opt = *opt;
   rfx_status st = RFX_OK;
   auto alloc = [&](int fmt, rfx_plane* p) { if (st == RFX_OK) st = rfx_plane_alloc(ctx, fmt, opt->width, opt->height, p); };
+  auto ialloc = [&](size_t texel, IPlane* p) {
+    if (st != RFX_OK) return;
+    p->pitch = ((size_t)opt->width * texel + 255) & ~(size_t)255;
+    if (p->pitch * opt->height >= (1ull << 32)) { st = fail(ctx, RFX_ERR_UNSUPPORTED, "chain_create: internal plane exceeds 4 GiB"); return; }
+    if (cudaMalloc(&p->p, p->pitch * opt->height) != cudaSuccess || cudaMemset(p->p, 0, p->pitch * opt->height) != cudaSuccess) st = fail(ctx, RFX_ERR_CUDA, "chain_create: cudaMalloc failed");
+  };
+  CU(cudaSetDevice(ctx->device));
+  ch->fastpath = ctx->fast_math && opt->mode == RFX_MODE_SSGI;  // latched: the history formats differ between the two paths
   alloc(RFX_FMT_RGBA32F, &ch->ssgi_out);
-  for (int i = 0; i < 2; i++) { alloc(RFX_FMT_RGBA32F, &ch->tr[i]); alloc(RFX_FMT_RGBA16F, &ch->dnA[i]); alloc(RFX_FMT_RGBA16F, &ch->dnB[i]); }
-  alloc(RFX_FMT_RGBA32F, &ch->composed);
+  if (ch->fastpath) {
+    ialloc(16, &ch->nrdz); ialloc(32, &ch->tr32); ialloc(16, &ch->dnA16); ialloc(16, &ch->dnB16[0]); ialloc(16, &ch->dnB16[1]);
+    alloc(RFX_FMT_RGBA32F, &ch->composed2[0]); alloc(RFX_FMT_RGBA32F, &ch->composed2[1]);
+  } else {
+    for (int i = 0; i < 2; i++) { alloc(RFX_FMT_RGBA32F, &ch->tr[i]); alloc(RFX_FMT_RGBA16F, &ch->dnA[i]); alloc(RFX_FMT_RGBA16F, &ch->dnB[i]); }
+    alloc(RFX_FMT_RGBA32F, &ch->composed);
+  }
   if (st != RFX_OK) { rfx_ssgi_chain_destroy(ch); return st; }
   *out = ch;
   return RFX_OK;
@@ -696,6 +735,8 @@ void rfx_ssgi_chain_destroy(rfx_ssgi_chain* ch) {
   rfx_plane* all[] = {&ch->ssgi_out, &ch->tr[0], &ch->tr[1], &ch->dnA[0], &ch->dnA[1], &ch->dnB[0], &ch->dnB[1], &ch->composed,
                       &ch->in_depth[0], &ch->in_gb[0], &ch->in_vel[0], &ch->in_direct[0], &ch->in_depth[1], &ch->in_gb[1], &ch->in_vel[1], &ch->in_direct[1]};
   for (rfx_plane* p : all) if (p->ptr) rfx_plane_free(ctx, p);
+  for (rfx_plane* p : {&ch->composed2[0], &ch->composed2[1]}) if (p->ptr) rfx_plane_free(ctx, p);
+  for (IPlane* p : {&ch->nrdz, &ch->tr32, &ch->dnA16, &ch->dnB16[0], &ch->dnB16[1]}) if (p->p) cudaFree(p->p);
   for (int i = 0; i < 2; i++) for (cudaEvent_t e : {ch->ev_up[i], ch->ev_rendered[i], ch->ev_dn[i]}) if (e) cudaEventDestroy(e);
   if (ch->s_up) cudaStreamDestroy(ch->s_up);
   if (ch->s_dn) cudaStreamDestroy(ch->s_dn);
@@ -744,14 +785,39 @@ rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* ch) {
 
 rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* ch, int32_t which, rfx_plane* out) {
   if (!ch || !out) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = ch->ctx;
+  if (which < 0 || which > 5) return fail(ctx, RFX_ERR_INVALID_ARG, "chain_output: which must be 0..5");
+  if (ch->fastpath) {
+    const int last = (int)((ch->frame_idx + 1) & 1);  // parity of the most recently completed frame
+    if (which == 0) { *out = ch->composed2[last]; return RFX_OK; }
+    if (which == 1) { *out = ch->ssgi_out; return RFX_OK; }
+    // views of the interleaved planes in the reference's formats, refreshed on the context stream
+    if (!ch->tr[0].ptr) {
+      rfx_status st = RFX_OK;
+      for (int i = 0; i < 2 && st == RFX_OK; i++) {
+        st = rfx_plane_alloc(ctx, RFX_FMT_RGBA32F, ch->opt.width, ch->opt.height, &ch->tr[i]);
+        if (st == RFX_OK) st = rfx_plane_alloc(ctx, RFX_FMT_RGBA16F, ch->opt.width, ch->opt.height, &ch->dnB[i]);
+      }
+      if (st != RFX_OK) return st;
+    }
+    if (!ch->views_valid) {
+      const int W = (int)ch->opt.width, H = (int)ch->opt.height;
+      LAUNCHED(launch_split_tr(PV{(const unsigned char*)ch->tr32.p, W, H, (long long)ch->tr32.pitch}, OutV{(unsigned char*)ch->tr[0].ptr, (long long)ch->tr[0].pitch},
+                               OutV{(unsigned char*)ch->tr[1].ptr, (long long)ch->tr[1].pitch}, W, H, ctx->stream));
+      LAUNCHED(launch_split_dn(PV{(const unsigned char*)ch->dnB16[last].p, W, H, (long long)ch->dnB16[last].pitch}, OutV{(unsigned char*)ch->dnB[0].ptr, (long long)ch->dnB[0].pitch},
+                               OutV{(unsigned char*)ch->dnB[1].ptr, (long long)ch->dnB[1].pitch}, W, H, ctx->stream));
+      ch->views_valid = true;
+    }
+    *out = which == 2 ? ch->tr[0] : which == 3 ? ch->tr[1] : which == 4 ? ch->dnB[0] : ch->dnB[1];
+    return RFX_OK;
+  }
   switch (which) {
     case 0: *out = ch->composed; break;
     case 1: *out = ch->ssgi_out; break;
     case 2: *out = ch->tr[0]; break;
     case 3: *out = ch->tr[1]; break;
     case 4: *out = ch->dnB[0]; break;
-    case 5: *out = ch->dnB[1]; break;
-    default: return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_output: which must be 0..5");
+    default: *out = ch->dnB[1]; break;
   }
   return RFX_OK;
 }
@@ -770,6 +836,162 @@ struct SegScope {
   ~SegScope() { ctx->segs_override = nullptr; }
 };
 
+// ------------------------------------------------------------------------------------------
+// fast chain (k_chain.cu): same frame logic as chain_render_impl below, interleaved internal planes, compose fused into the
+// last Poisson pass.  Launch indices k (for `ranges` and [k_begin, k_end)) are those of the reference chain — K1, K2, K3 pass
+// 0..2n-1, K4 — the K4 range selects the rows the last pass composes.
+// ------------------------------------------------------------------------------------------
+static PV ipv(const IPlane& p, int w, int h) { return PV{(const unsigned char*)p.p, w, h, (long long)p.pitch}; }
+static OutV iov(const IPlane& p) { return OutV{(unsigned char*)p.p, (long long)p.pitch}; }
+static PV rpv(const rfx_plane& p) { return PV{(const unsigned char*)p.ptr, (int)p.width, (int)p.height, (long long)p.pitch}; }
+static RowSegs segs_for(const uint32_t* ranges, uint32_t n_blocks, uint32_t n_launches, uint32_t k, int H) {
+  int r0[RFX_MAX_SEGS], r1[RFX_MAX_SEGS];
+  if (!ranges) { r0[0] = 0; r1[0] = H; return make_segs(r0, r1, 1); }
+  for (uint32_t b = 0; b < n_blocks; b++) { r0[b] = (int)ranges[(b * n_launches + k) * 2]; r1[b] = (int)ranges[(b * n_launches + k) * 2 + 1]; }
+  return make_segs(r0, r1, (int)n_blocks);
+}
+static void peer_single(PeerPV& pp, PV local) {
+  pp = PeerPV{};
+  pp.local = local;
+  pp.n = 1;
+  pp.own0 = 0; pp.own1 = local.h;
+}
+
+static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_blocks,
+                                    uint32_t k_begin, uint32_t k_end, int k1_phase) {
+  rfx_ctx* ctx = ch->ctx;
+  const rfx_ssgi_chain_options& o = ch->opt;
+  const int W = (int)o.width, H = (int)o.height;
+  const uint32_t n_launches = 3u + 2u * (uint32_t)o.denoise_iterations;
+  if (!ranges) n_blocks = 1;
+  auto on = [&](uint32_t k) { return k >= k_begin && k < k_end; };
+  const cudaStream_t cs = stream ? (cudaStream_t)stream : ctx->stream;
+  const int cur = (int)(ch->frame_idx & 1), prev = cur ^ 1;
+  rfx_status st = RFX_OK;
+  PV depth, gb, vel;
+  if (!pv(f->depth, RFX_FMT_R32F, depth) || !pv(f->gbuffer, RFX_FMT_RGBA32F, gb) || !pv(f->velocity, RFX_FMT_RGBA32F, vel))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "chain: depth must be R32F, gbuffer / velocity RGBA32F");
+  if (depth.w != W || depth.h != H || gb.w != W || gb.h != H || vel.w != W || vel.h != H) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "chain: input planes must match the chain size");
+  CamD cam;
+  cam_to_dev(f->cam, cam);
+  uint32_t k = 0;
+  ch->views_valid = false;
+  // ---- K1
+  if (on(k)) {
+    rfx_ssgi_params sp{};
+    sp.cam = f->cam;
+    sp.ray_distance = o.distance; sp.thickness = o.thickness; sp.env_blur = o.env_blur;
+    sp.max_env_map_mip_level = ctx->env_set ? (float)((int)std::floor(std::log2((double)std::max(ctx->env.size_x, ctx->env.size_y))) + 1) : 0.0f;
+    sp.steps = o.steps; sp.refine_steps = o.refine_steps; sp.mode = o.mode; sp.flags = o.ssgi_flags;
+    sp.blue_noise_index = k1_phase == 2 ? ch->bn_trace : next_blue(o.blue_noise_start, ch->bn_trace);
+    SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
+    ctx->k1_phase = k1_phase;
+    ctx->peer_accumulated = ch->group ? &ch->peer_composed[prev] : nullptr;
+    {
+      SpanGuard g(ch, cs, 0);
+      st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed2[prev], &ch->ssgi_out, ranges ? ranges[k * 2] : 0u,
+                                 ranges ? ranges[k * 2 + 1] : 0u);
+    }
+    ctx->k1_phase = 0;
+    ctx->peer_accumulated = nullptr;
+    if (st != RFX_OK) return st;
+  }
+  k++;
+  // ---- K2
+  if (on(k)) {
+    CTemporalArgs a{};
+    a.input = rpv(ch->ssgi_out); a.velocity = vel;
+    if (ch->group) a.hist = ch->peer_dn[prev]; else peer_single(a.hist, ipv(ch->dnB16[prev], W, H));
+    a.out = iov(ch->tr32);
+    a.W = W; a.H = H;
+    a.segs = segs_for(ranges, n_blocks, n_launches, k, H);
+    a.cam = cam;
+    if (!ch->have_prev) {
+      memcpy(ch->prev_view, f->cam.view_matrix, 64); memcpy(ch->prev_world, f->cam.camera_matrix_world, 64);
+      memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
+      memcpy(ch->prev_pos, f->camera_pos, 12);
+      ch->have_prev = true;
+    }
+    memcpy(a.prev_world.m, ch->prev_world, 64); memcpy(a.prev_proj_inv.m, ch->prev_proj_inv, 64);
+    matmul(ch->prev_proj, ch->prev_view, a.prev_proj_view.m);
+    memcpy(a.camera_pos, f->camera_pos, 12);
+    a.max_blend = 1.0f; a.clamp_intensity = 0.5f; a.keep_data = ch->keep_data; a.confidence_power = 0.75f;  // Denoiser.js:26-43, TemporalReprojectPass.js:17-32
+    a.inv_w = (float)(1.0 / (double)W); a.inv_h = (float)(1.0 / (double)H);
+    a.full_accumulate = f->camera_moved ? 0 : 1;
+    {
+      SpanGuard g(ch, cs, 1);
+      LAUNCHED(launch_ctemporal(a, cs));
+    }
+    ch->keep_data = 1.0f;
+    memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
+    memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
+    memcpy(ch->prev_pos, f->camera_pos, 12);
+  }
+  k++;
+  // ---- K3 (+ fused K4)
+  const int n_pass = 2 * o.denoise_iterations;
+  const int halo = (int)std::ceil(o.radius * std::max(1.0f, (float)H / (float)W)) + 1;  // rows a Poisson tap can reach (the offset is rotated AFTER the division by the resolution)
+  bool decoded = false;
+  auto decode = [&](const RowSegs& segs) -> rfx_status {
+    if (decoded) return RFX_OK;
+    CDecodeArgs d{gb, depth, iov(ch->nrdz), W, H};
+    LAUNCHED(launch_cdecode(d, segs, halo, cs));
+    decoded = true;
+    return RFX_OK;
+  };
+  const uint32_t k_compose = 2u + (uint32_t)n_pass;
+  for (int i = 0; i < n_pass; i++, k++) {
+    if (!on(k)) continue;
+    const bool horizontal = (i % 2) == 0, last = i == n_pass - 1;
+    CPoissonArgs a{};
+    a.segs = segs_for(ranges, n_blocks, n_launches, k, H);
+    if ((st = decode(a.segs)) != RFX_OK) return st;  // the first pass of a frame has the widest rows of all its passes
+    a.nrdz = ipv(ch->nrdz, W, H);
+    a.first = i == 0;
+    a.in = i == 0 ? ipv(ch->tr32, W, H) : ipv(horizontal ? ch->dnB16[cur] : ch->dnA16, W, H);
+    a.out = iov(horizontal ? ch->dnA16 : ch->dnB16[cur]);
+    if (!horizontal) { if (ch->group) a.carry = ch->peer_dn[prev]; else peer_single(a.carry, ipv(ch->dnB16[prev], W, H)); }
+    a.W = W; a.H = H;
+    a.radius = o.radius; a.phi = o.phi; a.luma_phi = o.luma_phi; a.depth_phi = o.depth_phi; a.normal_phi = o.normal_phi;
+    a.roughness_phi = o.roughness_phi; a.specular_phi = o.specular_phi;
+    if ((st = blue_for(ctx, next_blue(o.blue_noise_start, ch->bn_poisson), a.blue)) != RFX_OK) return st;
+    a.rot_table = ctx->rot_table;
+    a.reach_x = (int)std::ceil(o.radius * std::max(1.0f, (float)W / (float)H)) + 2;
+    a.reach_y = (int)std::ceil(o.radius * std::max(1.0f, (float)H / (float)W)) + 2;
+    {
+      const float SQ = 1.41421356237f;
+      const float px[8] = {-1.0f, 0.0f, 1.0f, 0.0f, -0.25f * SQ, 0.25f * SQ, 0.25f * SQ, -0.25f * SQ};
+      const float py[8] = {0.0f, -1.0f, 0.0f, 1.0f, -0.25f * SQ, -0.25f * SQ, 0.25f * SQ, 0.25f * SQ};
+      for (int t = 0; t < 8; t++) { a.tap_ox[t] = px[t] / (float)W; a.tap_oy[t] = py[t] / (float)H; }
+    }
+    if (last && on(k_compose)) {
+      a.compose = 1;
+      a.csegs = segs_for(ranges, n_blocks, n_launches, k_compose, H);
+      a.gb = gb;
+      a.composed = OutV{(unsigned char*)ch->composed2[cur].ptr, (long long)ch->composed2[cur].pitch};
+      if (ch->group) a.composed_carry = ch->peer_composed[prev]; else peer_single(a.composed_carry, rpv(ch->composed2[prev]));
+      a.cam = cam;
+    }
+    SpanGuard g(ch, cs, i == 0 ? 2 : 3);
+    LAUNCHED(launch_cpoisson(a, cs));
+  }
+  // ---- K4 stand-alone (no Poisson pass to ride on, or the caller split the frame between the last pass and K4)
+  k = k_compose;
+  if (on(k) && (n_pass == 0 || !on(k - 1))) {
+    CComposeArgs a{};
+    a.segs = segs_for(ranges, n_blocks, n_launches, k, H);
+    if ((st = decode(a.segs)) != RFX_OK) return st;
+    a.nrdz = ipv(ch->nrdz, W, H); a.gb = gb; a.dn = ipv(ch->dnB16[cur], W, H);
+    a.composed = OutV{(unsigned char*)ch->composed2[cur].ptr, (long long)ch->composed2[cur].pitch};
+    if (ch->group) a.composed_carry = ch->peer_composed[prev]; else peer_single(a.composed_carry, rpv(ch->composed2[prev]));
+    a.W = W; a.H = H; a.cam = cam;
+    SpanGuard g(ch, cs, 4);
+    LAUNCHED(launch_ccompose(a, cs));
+  }
+  if (on(k_compose)) ch->frame_idx++;  // the frame is complete: its planes become `prev`
+  return RFX_OK;
+}
+
 // One frame of the chain.  `ranges` == nullptr: whole planes, one block.  Otherwise ranges[(blk*n_launches + k)*2 + {0,1}] =
 // output rows [a,b) of launch k (chain order: K1, K2, K3 pass 0..2*iterations-1, K4) for row block `blk` of this rank
 // (row-block sharding with locally recomputed halos, realism_effects_b200/parallel.py).  Only launches k in
@@ -777,6 +999,7 @@ struct SegScope {
 // different all-gather; per-frame state advances with the launch that consumes it.
 static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_blocks,
                                     uint32_t k_begin, uint32_t k_end, int k1_phase = 0) {
+  if (ch->fastpath) return chain_render_fast(ch, stream, f, ranges, n_blocks, k_begin, k_end, k1_phase);
   rfx_ctx* ctx = ch->ctx;
   const rfx_ssgi_chain_options& o = ch->opt;
   rfx_status st = RFX_OK;
@@ -914,6 +1137,10 @@ rfx_status rfx_ssgi_chain_render_part(rfx_ssgi_chain* ch, void* stream, const rf
     if (st != RFX_OK) return st;
   }
   if (part == 2) return chain_render_impl(ch, stream, f, ranges, ranges ? n_blocks : 1, 1, 0xffffffffu);
+  if (ch->fastpath) {  // the fast K1 is one fused kernel (its diffuse rays are compacted inside the block): part 0 is empty, part 1 is K1
+    if (part == 0) return RFX_OK;
+    return chain_render_impl(ch, stream, f, ranges, ranges ? n_blocks : 1, 0, 1, 0);
+  }
   return chain_render_impl(ch, stream, f, ranges, ranges ? n_blocks : 1, 0, 1, part == 0 ? 1 : 2);
 }
 
@@ -955,14 +1182,26 @@ rfx_status rfx_ssgi_chain_submit_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_fr
   f.depth = &ch->in_depth[set]; f.gbuffer = &ch->in_gb[set]; f.velocity = &ch->in_vel[set]; f.direct_light = hf->direct_light ? &ch->in_direct[set] : nullptr;
   memcpy(f.camera_pos, hf->camera_pos, 12);
   f.camera_moved = hf->camera_moved;
-  const uint32_t n_launches = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
-  const uint32_t split = ch->opt.mode == RFX_MODE_SSGI ? n_launches - 1 : 0;  // K4 is the only launch that writes `composed`
-  if (split && (st = chain_render_impl(ch, nullptr, &f, nullptr, 1, 0, split)) != RFX_OK) return st;
-  if (ch->host_submitted >= 1) CU(cudaStreamWaitEvent(ctx->stream, ch->ev_dn[set ^ 1], 0));
-  if ((st = chain_render_impl(ch, nullptr, &f, nullptr, 1, split, 0xffffffffu)) != RFX_OK) return st;
+  const rfx_plane* result = &ch->composed;
+  if (ch->fastpath) {
+    // `composed` is double-buffered by frame parity: this frame writes composed2[cur], whose previous reader is the D2H of two
+    // frames ago (long finished in steady state); frame i-1's D2H keeps running under this frame's kernels
+    const int cur = (int)(ch->frame_idx & 1);
+    for (int q = 0; q < 2; q++)
+      if (ch->dn_buf[q] == cur) CU(cudaStreamWaitEvent(ctx->stream, ch->ev_dn[q], 0));
+    if ((st = chain_render_impl(ch, nullptr, &f, nullptr, 1, 0, 0xffffffffu)) != RFX_OK) return st;
+    result = &ch->composed2[cur];
+    ch->dn_buf[set] = cur;
+  } else {
+    const uint32_t n_launches = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
+    const uint32_t split = ch->opt.mode == RFX_MODE_SSGI ? n_launches - 1 : 0;  // K4 is the only launch that writes `composed`
+    if (split && (st = chain_render_impl(ch, nullptr, &f, nullptr, 1, 0, split)) != RFX_OK) return st;
+    if (ch->host_submitted >= 1) CU(cudaStreamWaitEvent(ctx->stream, ch->ev_dn[set ^ 1], 0));
+    if ((st = chain_render_impl(ch, nullptr, &f, nullptr, 1, split, 0xffffffffu)) != RFX_OK) return st;
+  }
   CU(cudaEventRecord(ch->ev_rendered[set], ctx->stream));
   CU(cudaStreamWaitEvent(ch->s_dn, ch->ev_rendered[set], 0));
-  if ((st = rfx_plane_download(ctx, ch->s_dn, &ch->composed, hf->out_composed, 0)) != RFX_OK) return st;
+  if ((st = rfx_plane_download(ctx, ch->s_dn, result, hf->out_composed, 0)) != RFX_OK) return st;
   CU(cudaEventRecord(ch->ev_dn[set], ch->s_dn));
   ch->host_submitted++;
   return RFX_OK;
@@ -986,3 +1225,5 @@ rfx_status rfx_ssgi_chain_render_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_fr
 }
 
 }  // extern "C"
+
+#include "rfx_group.inl"

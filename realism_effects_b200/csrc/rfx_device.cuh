@@ -264,5 +264,48 @@ RFX_D v3 SampleGGXVNDF_cs(v3 V, float ax, float ay, float r1, float cphi, float 
   return normalize(mk3(ax * Nh.x, ay * Nh.y, fmaxf(0.0f, Nh.z)));
 }
 
+// ---- SFU arithmetic for the fast kernel variants (values downstream of every per-pixel DECISION; 1-2 ulp) -----------
+RFX_D float fx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D float fx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D float fx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D float fx_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D float fx_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RFX_D v3 fx_normalize(v3 a) { return a * fx_rsqrt(dot(a, a)); }
+RFX_D float fx_length(v3 a) { return fx_sqrt(dot(a, a)); }
+// clamp an integer texel index to [0, n-1] in two VIMNMX (max(min(i, n-1), 0))
+RFX_D int clamp_idx(int i, int nm1) { return max(min(i, nm1), 0); }
+RFX_D uint32_t pack_h2(float a, float b) {  // packHalf2x16 in one F2FP
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+RFX_D float h_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+RFX_D float h_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two IEEE fp32 operations per issue slot).  The fast chain is
+// issue-bound, and its value arithmetic is the same expression for the diffuse and the specular plane, so the two planes ride in
+// the two halves of a 64-bit register pair.
+struct f2 { unsigned long long v; };
+RFX_D f2 mkf2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+RFX_D f2 mkf2(float s) { return mkf2(s, s); }
+RFX_D float f2lo(f2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+RFX_D float f2hi(f2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
+RFX_D f2 f2fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+RFX_D f2 f2mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+RFX_D f2 f2add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+RFX_D f2 f2sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+RFX_D f2 f2lg2(f2 a) { return mkf2(fx_lg2(f2lo(a)), fx_lg2(f2hi(a))); }
+RFX_D f2 f2ex2(f2 a) { return mkf2(fx_ex2(f2lo(a)), fx_ex2(f2hi(a))); }
+
+// ---- chain-internal plane formats (fast chain, k_chain.cu) -----------------------------------------------------------
+// nrdz: float4 (n.x, n.y, n.z, depth); the 9-bit roughness code k = mod(gBuffer.b, 257) rides in the low mantissa bits of
+//       n.x (5 bits) and n.y (4 bits): |dn| <= 2^-19 relative.  roughness = max(k/256 - 1e-4, 0)  (gbuffer_packing.glsl:24-34,189)
+RFX_D float nrdz_roughness(float4 t) {
+  const uint32_t k = (__float_as_uint(t.x) & 31u) | ((__float_as_uint(t.y) & 15u) << 5);
+  return fmaxf((float)k / 256.0f - RFX_NON_ZERO_OFFSET, 0.0f);
+}
+RFX_D float4 nrdz_pack(v3 n, float rough_code, float depth) {
+  const uint32_t k = (uint32_t)rough_code;
+  return make_float4(__uint_as_float((__float_as_uint(n.x) & ~31u) | (k & 31u)), __uint_as_float((__float_as_uint(n.y) & ~15u) | ((k >> 5) & 15u)), n.z, depth);
+}
 
 }  // namespace rfx

@@ -21,6 +21,22 @@ struct RowSegs {
   int tile0[RFX_MAX_SEGS + 1];   // first tile index of each segment
 };
 
+#define RFX_MAX_PEERS 8
+struct PeerPV {
+  PV local;                                    // this rank's allocation (full-frame sized); rows [own0, own1) are valid here
+  const unsigned char* base[RFX_MAX_PEERS];    // every rank's allocation of the same plane (peer-mapped), same pitch
+  int bound[RFX_MAX_PEERS + 1];                // rank k owns rows [bound[k], bound[k+1]) of the data being read
+  int n;                                       // ranks; <= 1: single GPU (local only)
+  int own0, own1;
+};
+RFX_D const unsigned char* peer_row_base(const PeerPV& p, int y) {
+  if (p.n <= 1 || (y >= p.own0 && y < p.own1)) return p.local.p;
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < RFX_MAX_PEERS; i++) k += (i < p.n && y >= p.bound[i]) ? 1 : 0;
+  return p.base[k];
+}
+
 struct CamD {  // device copy of rfx_camera
   M4 projection, projection_inverse, camera_matrix_world, view_matrix;
   float near_plane, far_plane;
@@ -32,7 +48,12 @@ struct BlueD {
   int size;
   BlueShift shift;    // (pcg4d(seed(index)).xy % 0x0fffffff) % size, computed on the host
   int index;          // raw index (0 selects the tiled lookup of blue_noise.glsl:38-39)
+  int mask;           // size - 1 when size is a power of two (the shipped 128 x 128 texture), else 0
 };
+RFX_D int blue_index(const BlueD& b, int x, int y) {
+  if (b.mask) return ((y + b.shift.sy) & b.mask) * b.size + ((x + b.shift.sx) & b.mask);
+  return ((y + b.shift.sy) % b.size) * b.size + ((x + b.shift.sx) % b.size);
+}
 
 struct EnvD {
   PV mip[16];  // RGBA16F levels
@@ -117,6 +138,11 @@ struct SsgiArgs {
   int phase;                 // 0 fused; 1 ray march only -> rec; 2 shading from rec (k_ssgi.cu "Split-phase K1")
   unsigned char* rec;        // 2 x float4 per pixel (diffuse ray, specular ray)
   long long rec_pitch;
+  // fast fused kernel (ssgi_fast_kernel)
+  float ps_x0, ps_x2, ps_y1, ps_y2, ps_hw, ps_hh;  // projection rows scaled to texel units: tx = (ps_x0*x + ps_x2*z) / -z + ps_hw
+  int vz_pitchw;             // viewZ pitch in 4-byte words
+  int legacy_fast;           // 1: use the round-1 fast kernel (tools/ A/B comparisons)
+  PeerPV acc_peer;           // `accumulated` in a row-sharded group (n > 1): rows live on their owners
 };
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);
 cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s);
@@ -161,6 +187,72 @@ cudaError_t launch_traa_compose(const TraaComposeArgs& a, cudaStream_t s);
 
 // env mip chain: dst (w1 x h1) = box filter of src (w0 x h0), RGBA16F
 cudaError_t launch_env_downsample(PV src, OutV dst, int w1, int h1, cudaStream_t s);
+
+
+// ==========================================================================================
+// fast chain (k_chain.cu): the SSGI-mode chain of rfx_ssgi_chain_* with fast_math on.  Same passes, same tap geometry and
+// decisions as the per-pass kernels above, but chain-internal plane formats chosen for the tap loops:
+//   nrdz  16 B  (n.xyz, depth) + roughness code in the low mantissa bits          (decode prepass, once per frame)
+//   tr    32 B  {diffuse rgba fp32, specular rgba fp32}                            K2 -> K3 pass 0 (NEAREST)
+//   dn    16 B  {diffuse rgba fp16, specular rgba fp16}                            K3 ping-pong (LINEAR), K2 history, K4 input
+// and the last Poisson pass also does the GI compose for its pixel (K4 has no neighbourhood in the fast variant).
+// Row-sharded multi-GPU frames read last frame's `composed` / `dn` rows owned by other ranks in place over NVLink (PeerPV).
+// ==========================================================================================
+struct CDecodeArgs { PV gb, depth; OutV nrdz; int W, H; };
+cudaError_t launch_cdecode(const CDecodeArgs& a, const RowSegs& segs, int halo, cudaStream_t s);
+
+struct CTemporalArgs {
+  PV input, velocity;   // K1 output (packed), velocity plane
+  PeerPV hist;          // dn of the previous frame
+  OutV out;             // tr
+  int W, H;
+  RowSegs segs;
+  CamD cam;
+  M4 prev_world, prev_proj_inv, prev_proj_view;
+  float camera_pos[3];
+  float max_blend, clamp_intensity, keep_data, confidence_power;
+  float inv_w, inv_h;
+  int full_accumulate;
+};
+cudaError_t launch_ctemporal(const CTemporalArgs& a, cudaStream_t s);
+
+struct CPoissonArgs {
+  PV nrdz, in;          // in: tr (pass 0) or dn (passes >= 1)
+  OutV out;             // dn
+  int W, H;
+  RowSegs segs;
+  float radius, phi, luma_phi, depth_phi, normal_phi, roughness_phi, specular_phi;
+  BlueD blue;
+  const float2* rot_table;
+  float tap_ox[8], tap_oy[8];
+  int first;            // pass 0: `in` is tr, NEAREST
+  int reach_x, reach_y; // pixels a tap (incl. its bilinear footprint) can lie from its pixel: blocks further than that from every border skip all clamping
+  // `out` is double-buffered by frame parity when it is the history plane: a discarded pixel (the reference's "target keeps its
+  // texel") then copies last frame's texel forward.  carry.local.p == nullptr: single-buffered target, no write.
+  PeerPV carry;
+  // fused GI compose (last pass): rows of `csegs` also write `composed` (discarded pixels carry last frame's texel forward)
+  int compose;
+  RowSegs csegs;
+  PV gb;
+  OutV composed;
+  PeerPV composed_carry;
+  CamD cam;
+};
+cudaError_t launch_cpoisson(const CPoissonArgs& a, cudaStream_t s);
+
+struct CComposeArgs {   // stand-alone K4 over dn (denoiseIterations == 0)
+  PV nrdz, gb, dn;
+  OutV composed;
+  PeerPV composed_carry;
+  int W, H;
+  RowSegs segs;
+  CamD cam;
+};
+cudaError_t launch_ccompose(const CComposeArgs& a, cudaStream_t s);
+
+// chain_output() views of the interleaved planes in the reference's formats
+cudaError_t launch_split_tr(PV tr, OutV o0, OutV o1, int W, int H, cudaStream_t s);   // 32 B -> 2 x RGBA32F
+cudaError_t launch_split_dn(PV dn, OutV o0, OutV o1, int W, int H, cudaStream_t s);   // 16 B -> 2 x RGBA16F
 
 // common launch geometry: 256-thread blocks, 8 warps as 2 x 4 warp tiles of 8x4 pixels => 16x16 pixel tile
 constexpr int kTileW = 16, kTileH = 16, kThreads = 256;

@@ -166,7 +166,7 @@ class SSGIEffect(_Reactive):
             flags |= abi.SSGI_USE_DIRECT_LIGHT
         c.ssgi_flags = flags
         c.mode = abi.MODE_SSR if o["mode"] == "ssr" else abi.MODE_SSGI
-        c.blue_noise_start, c.use_cuda_graph = self._blue_start, 0
+        c.blue_noise_start = self._blue_start
         return c
 
     def setSize(self, width, height, force=False):

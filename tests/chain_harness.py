@@ -152,14 +152,15 @@ def chain_options(inp: Inputs, o: Opts) -> abi.ChainOptions:
     c.distance, c.thickness, c.env_blur = o.distance, o.thickness, o.env_blur
     c.radius, c.phi, c.luma_phi, c.depth_phi, c.normal_phi = o.radius, o.phi, o.luma_phi, o.depth_phi, o.normal_phi
     c.roughness_phi, c.specular_phi = o.roughness_phi, o.specular_phi
-    c.ssgi_flags, c.mode, c.blue_noise_start, c.use_cuda_graph = o.flags, o.mode, o.blue_noise_start, 0
+    c.ssgi_flags, c.mode, c.blue_noise_start = o.flags, o.mode, o.blue_noise_start
     return c
 
 
 # ----------------------------------------------------------------------------------------------
-def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed")):
+def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"), lean: bool = False):
     """Returns a list (one dict per frame) of the planes named in `capture` (+ the per-pass inputs
-    needed for isolated kernel tests under keys starting with '_')."""
+    needed for isolated kernel tests under keys starting with '_'; lean=True drops those copies: at 4K they are
+    ~2.5 GB per frame)."""
     import orc
 
     H, W = inp.height, inp.width
@@ -209,6 +210,8 @@ def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0",
         rec["_k4_params"], rec["_k4_prev"] = cp, composed.copy()
         composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed)
         full = dict(ssgi=ssgi, tr0=tr[0], tr1=tr[1], dn0=dnB[0], dn1=dnB[1], composed=composed)
+        if lean:
+            rec = {}
         rec.update({k: full[k].copy() for k in capture})
         out.append(rec)
     return out
