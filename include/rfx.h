@@ -224,6 +224,8 @@ rfx_status rfx_plane_clear(rfx_ctx* ctx, void* stream, const rfx_plane* plane);
 /* host <-> device, asynchronous on `stream` when the host memory is pinned */
 rfx_status rfx_plane_upload(rfx_ctx* ctx, void* stream, const rfx_plane* dst, const void* host, uint64_t host_pitch);
 rfx_status rfx_plane_download(rfx_ctx* ctx, void* stream, const rfx_plane* src, void* host, uint64_t host_pitch);
+/* rows [row0, row1) of a plane to tightly packed host memory (a row-sharded rank reads back only its own band) */
+rfx_status rfx_plane_download_rows(rfx_ctx* ctx, void* stream, const rfx_plane* src, void* host, uint32_t row0, uint32_t row1);
 rfx_status rfx_host_alloc(rfx_ctx* ctx, uint64_t bytes, void** out); /* pinned */
 rfx_status rfx_host_free(rfx_ctx* ctx, void* p);
 uint32_t rfx_format_bytes(int32_t format);
@@ -388,6 +390,13 @@ rfx_status rfx_group_set_bounds(rfx_group* group, const uint32_t* bounds);   /* 
 /* every > 0: move the borders towards equal device-timed kernel cost every `every` frames, from times `lag` frames old */
 rfx_status rfx_group_set_rebalance(rfx_group* group, int32_t every, int32_t lag);
 rfx_status rfx_group_last_costs(const rfx_group* group, float* ms_per_rank);  /* the times the last rebalance used */
+/* in lockstep on every rank, no communication: applies the border move that is due and returns the borders of the NEXT frame
+ * (render_sharded calls it implicitly; a host path calls it first to size its uploads) */
+rfx_status rfx_group_begin_frame(rfx_group* group, uint32_t* bounds_out);
+rfx_status rfx_group_get_last_bounds(const rfx_group* group, uint32_t* bounds);  /* borders of the most recent frame */
+/* collective: completes a full-frame INPUT plane of which every rank uploaded only rows [bounds[r], bounds[r+1]) — one NCCL
+ * group of per-rank broadcasts over NVLink (depth / velocity are sampled at arbitrary screen positions by every rank) */
+rfx_status rfx_group_allgather_rows(rfx_group* group, void* stream, const rfx_plane* plane, const uint32_t* bounds);
 /* collective: one frame; this rank renders its band from full-frame input planes and joins the frame's collective on `stream` */
 rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
 /* pure host arithmetic, exported for hosts that drive the per-launch ranges themselves (and for the CPU tests):

@@ -18,6 +18,8 @@ FMT_R32F, FMT_RGBA32F, FMT_RGBA16F, FMT_RGBA8 = 0, 1, 2, 3
 FMT_BYTES = {FMT_R32F: 4, FMT_RGBA32F: 16, FMT_RGBA16F: 8, FMT_RGBA8: 4}
 SSGI_IMPORTANCE_SAMPLING, SSGI_MISSED_RAYS, SSGI_USE_DIRECT_LIGHT, SSGI_USE_ENVMAP = 1, 2, 4, 8
 MODE_SSGI, MODE_SSR = 0, 1
+GROUP_ID_BYTES = 128
+ERR_NCCL = 7
 INPUT_DIFFUSE_SPECULAR, INPUT_DIFFUSE, INPUT_SPECULAR = 0, 1, 2
 
 F16 = C.c_float * 16
@@ -174,6 +176,26 @@ def _sig(lib):
     lib.rfx_ssgi_chain_wait_host.argtypes = [vp, C.c_int32]
     lib.rfx_ssgi_chain_set_profiling.argtypes = [vp, C.c_int32]
     lib.rfx_ssgi_chain_get_profile.argtypes = [vp, _P(C.c_double), _P(C.c_uint64)]
+    lib.rfx_plane_download_rows.argtypes = [vp, vp, PP, vp, u32, u32]
+    # row-sharded multi-GPU groups
+    U32P = _P(C.c_uint32)
+    lib.rfx_group_get_unique_id.argtypes = [vp]
+    lib.rfx_group_create.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, _P(vp)]
+    lib.rfx_group_destroy.argtypes = [vp]
+    lib.rfx_group_destroy.restype = None
+    lib.rfx_group_rank.argtypes = [vp]
+    lib.rfx_group_world.argtypes = [vp]
+    lib.rfx_group_attach_chain.argtypes = [vp, vp]
+    lib.rfx_group_get_bounds.argtypes = [vp, U32P]
+    lib.rfx_group_set_bounds.argtypes = [vp, U32P]
+    lib.rfx_group_set_rebalance.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.rfx_group_last_costs.argtypes = [vp, _P(C.c_float)]
+    lib.rfx_group_begin_frame.argtypes = [vp, U32P]
+    lib.rfx_group_get_last_bounds.argtypes = [vp, U32P]
+    lib.rfx_group_allgather_rows.argtypes = [vp, vp, PP, U32P]
+    lib.rfx_ssgi_chain_render_sharded.argtypes = [vp, vp, _P(SsgiFrame)]
+    lib.rfx_shard_ranges.argtypes = [u32, u32, u32, u32, C.c_int32, C.c_float, C.c_int32, U32P, u32]
+    lib.rfx_shard_rebalance.argtypes = [U32P, U32P, _P(C.c_float), C.c_int32, U32P]
 
 
 EXPORTS = [
@@ -186,6 +208,10 @@ EXPORTS = [
     "rfx_ssgi_chain_reset", "rfx_ssgi_chain_render", "rfx_ssgi_chain_output", "rfx_ssgi_chain_render_host",
     "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host", "rfx_ssgi_chain_render_part",
     "rfx_ssgi_chain_set_profiling", "rfx_ssgi_chain_get_profile", "rfx_ssgi_chain_set_options", "rfx_ssgi_chain_render_ranges", "rfx_ssgi_chain_render_blocks",
+    "rfx_plane_download_rows", "rfx_group_get_unique_id", "rfx_group_create", "rfx_group_destroy", "rfx_group_rank", "rfx_group_world",
+    "rfx_group_attach_chain", "rfx_group_get_bounds", "rfx_group_set_bounds", "rfx_group_set_rebalance", "rfx_group_last_costs",
+    "rfx_group_begin_frame", "rfx_group_get_last_bounds", "rfx_group_allgather_rows", "rfx_ssgi_chain_render_sharded", "rfx_shard_ranges",
+    "rfx_shard_rebalance",
 ]
 
 

@@ -266,64 +266,41 @@ cudaError_t launch_ctemporal(const CTemporalArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// K4 as a device function: constructGlobalIllumination (denoiser_compose_functions.glsl:53-107), SFU arithmetic
+// K4 as a device function: constructGlobalIllumination (denoiser_compose_functions.glsl:53-107)
 // ------------------------------------------------------------------------------------------------------------------
-RFX_D v3 c_sample_ggx_vndf(v3 V, float ax, float ay, float r1, float cphi, float sphi) {
-  const v3 Vh = fx_normalize(mk3(ax * V.x, ay * V.y, V.z));
-  const float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
-  const v3 T1 = lensq > 0.0f ? mk3(-Vh.y, Vh.x, 0.0f) * fx_rsqrt(lensq) : mk3(1.0f, 0.0f, 0.0f);
-  const v3 T2 = cross(Vh, T1);
-  const float r = fx_sqrt(r1);
-  const float t1 = r * cphi;
-  float t2 = r * sphi;
-  const float sv = 0.5f * (1.0f + Vh.z);
-  t2 = (1.0f - sv) * fx_sqrt(1.0f - t1 * t1) + sv * t2;
-  const v3 Nh = t1 * T1 + t2 * T2 + fx_sqrt(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
-  return fx_normalize(mk3(ax * Nh.x, ay * Nh.y, fmaxf(0.0f, Nh.z)));
-}
+// The arithmetic is the exact K4's (IEEE division / sqrt, k_denoise.cu: gi_compose_kernel) — measured at 4K (tools/parity_at_size.py): with SFU
+// reciprocals here another 2.4e-4 of the pixels leave the 1e-3 band, because the two fp16 inputs already sit up to one fp16 ulp
+// (9.8e-4) from the oracle's; the pixel-centre fetch is the centre texel and pow(x, 5) is multiplies, as in the round-1 fast K4.
 RFX_D float4 c_compose(const CamD& cam, int x, int y, int W, int H, float4 g, float rough0, float depth, v3 dgi, v3 sgi) {
   const v2 vUv = pixel_uv(x, y, W, H);
-  // the exact normal (the nrdz copy carries the roughness code in its low mantissa bits: 2^-19 is harmless inside an exponent
-  // scaled by normalPhi, but the Fresnel term at grazing angles amplifies it to ~1e-4 of the composed colour)
+  const v3 diffuse = xyz(floatToVec4(g.x));
   const v3 wn = unpackNormal(g.y);
-  const uint32_t dv = __float_as_uint(g.x);
-  const v3 diffuse = mk3(fmaxf((float)(dv & 0xFFu) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f), fmaxf((float)((dv >> 8) & 0xFFu) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f),
-                         fmaxf((float)((dv >> 16) & 0xFFu) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f));
   const float metalness = gb_metalness(g.z);
-  const uint32_t ev = __float_as_uint(g.w);
-  const float eexp = fmaxf((float)(ev >> 24) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f) * 255.0f - 128.0f;
-  const float es = fx_ex2(eexp);
-  const v3 emissive = mk3(fmaxf((float)(ev & 0xFFu) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f), fmaxf((float)((ev >> 8) & 0xFFu) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f),
-                          fmaxf((float)((ev >> 16) & 0xFFu) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f)) * es;
-
+  const v3 emissive = decodeRGBE8(floatToVec4(g.w));
   const v3 viewNormal = mul_dir_left(wn, cam.camera_matrix_world);
-  const float gz = cam.perspective ? (cam.near_plane * cam.far_plane) * fx_rcp((cam.far_plane - cam.near_plane) * depth - cam.far_plane)
-                                   : orthographicDepthToViewZ(depth, cam.near_plane, cam.far_plane);
+  const float gz = cam.perspective ? perspectiveDepthToViewZ(depth, cam.near_plane, cam.far_plane) : orthographicDepthToViewZ(depth, cam.near_plane, cam.far_plane);
   const float viewZ = -gz;
   const float clipW = cam.projection.m[2 * 4 + 3] * viewZ + cam.projection.m[3 * 4 + 3];
-  const v4 clip = mk4((vUv.x - 0.5f) * 2.0f * clipW, (vUv.y - 0.5f) * 2.0f * clipW, (viewZ - 0.5f) * 2.0f * clipW, clipW);
+  v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
+  clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
   v3 viewPos = xyz(mul(cam.projection_inverse, clip));
   viewPos.z = -viewZ;
-  const v3 viewDir = fx_normalize(viewPos);
+  const v3 viewDir = normalize(viewPos);
   const float roughness = rough0 * rough0;
   const v3 N = mul_dir_left(viewNormal, cam.view_matrix);
+  v3 T, B;
   const v3 v = -viewDir;
   v3 V = mul_dir_left(v, cam.view_matrix);
-  v3 T, B;
-  {  // Onb
-    const v3 up = fabsf(N.z) < 0.9999999f ? mk3(0, 0, 1) : mk3(1, 0, 0);
-    T = fx_normalize(cross(up, N));
-    B = cross(N, T);
-  }
+  Onb(N, T, B);
   V = ToLocal(T, B, N, V);
-  v3 Hh = c_sample_ggx_vndf(V, roughness, roughness, 0.25f, -4.37113883e-08f, 1.0f);  // r2 = 0.25: (cos, sin) of fp32(pi/2)
+  v3 Hh = SampleGGXVNDF_cs(V, roughness, roughness, 0.25f, -4.37113883e-08f, 1.0f);  // r2 = 0.25: (cos, sin) of fp32(pi/2)
   if (Hh.z < 0.0f) Hh = -Hh;
-  v3 l = fx_normalize(reflect(-V, Hh));
+  v3 l = normalize(reflect(-V, Hh));
   l = ToWorld(T, B, N, l);
   l = xyz(mul(mk4(l, 1.0f), cam.camera_matrix_world));
-  l = fx_normalize(l);
+  l = normalize(l);
   if (dot(viewNormal, l) < 0.0f) l = -l;
-  const v3 h = fx_normalize(v + l);
+  const v3 h = normalize(v + l);
   const float VoH = fmaxf(1e-6f, dot(v, h));
   const v3 f0 = mix(mk3(0.04f), diffuse, metalness);
   const float omv = 1.0f - VoH, omv2 = omv * omv;
@@ -360,9 +337,9 @@ RFX_D CTexel2 cp_fetch(const CPoissonArgs& a, float fxn, float fyn, int nx, int 
     if (ALPHA) t.a = mkf2(u0.w, u1.w);
   } else {      // LINEAR fp16 pair: one bilinear setup, one LDG.128 per corner (fxn = uv.x * W, the product bilin_setup forms)
     const float fx = fxn - 0.5f, fy = fyn - 0.5f;
-    const float x0f = floorf(fx), y0f = floorf(fy);
+    float x0f, y0f;
+    const int ix = floor_i(fx, x0f), iy = floor_i(fy, y0f);
     const float ax = fx - x0f, ay = fy - y0f;
-    const int ix = (int)x0f, iy = (int)y0f;
     const float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
     uint4 t00, t10, t01, t11;
     if (INTERIOR) {
@@ -422,7 +399,7 @@ RFX_D void cpoisson_body(const CPoissonArgs& a, int x, int y, float4 nc, float f
     const float ox = a.tap_ox[i], oy = a.tap_oy[i];
     const v2 nuv = mk2(vUv.x + (m00 * ox + m10 * oy), vUv.y + (m01 * ox + m11 * oy));  // tap position: the oracle's arithmetic, op for op
     const float fxn = nuv.x * resx, fyn = nuv.y * resy;
-    int nx = __float2int_rd(fxn), ny = __float2int_rd(fyn);
+    int nx = floor_i(fxn), ny = floor_i(fyn);
     if (!INTERIOR) { nx = clamp_idx(nx, a.W - 1); ny = clamp_idx(ny, a.H - 1); }
     const float4 nn = ld_f4(a.nrdz, nx, ny);
     if (nn.w == 1.0f) continue;  // background tap: wBasic = 0

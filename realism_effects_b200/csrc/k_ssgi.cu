@@ -113,7 +113,7 @@ RFX_D v2 view_to_screen(const SsgiArgs& a, v3 p) {
 // 1: polynomial atan2 / acos (Abramowitz-Stegun 4.4.49 / 4.4.46 evaluated in fp32: 3e-7 / 1.3e-5 rad, i.e. < 0.003 texel of a
 // 512-row env map) for the fast variant's env lookup, ~45 instructions per fetch fewer than libm.  Unmeasured in round 1, so off.
 #ifndef RFX_K1_FAST_TRIG
-#define RFX_K1_FAST_TRIG 0
+#define RFX_K1_FAST_TRIG 0  /* round-1 kernels; the round-2 fast kernel always uses the polynomials (env_uv_fast) */
 #endif
 RFX_D float acos_poly(float x) {
   const float ax = fabsf(x);
@@ -140,9 +140,9 @@ RFX_D float atan2_poly(float y, float x) {
   return y < 0.0f ? -r : r;
 }
 
-template <bool AP>
+template <bool AP, bool POLY = false>
 RFX_D v2 equirectDirectionToUv(v3 d) {  // ssgi_utils.frag:64-74
-  v2 uv = (AP && RFX_K1_FAST_TRIG) ? mk2(atan2_poly(d.z, d.x), acos_poly(d.y)) : mk2(atan2f(d.z, d.x), acosf(d.y));
+  v2 uv = (AP && (POLY || RFX_K1_FAST_TRIG)) ? mk2(atan2_poly(d.z, d.x), acos_poly(d.y)) : mk2(atan2f(d.z, d.x), acosf(d.y));
   uv = mk2(div_<AP>(uv.x, 2.0f * PI_F), div_<AP>(uv.y, PI_F));
   uv.x += 0.5f;
   uv.y = 1.0f - uv.y;
@@ -233,13 +233,13 @@ RFX_D v3 env_trilinear(const EnvD& e, v2 uv, float lod) {
 }
 
 // getEnvColor  ssgi.frag:311-346
-template <bool AP>
+template <bool AP, bool POLY = false>
 RFX_D v3 getEnvColor(const SsgiArgs& a, v3 l, float roughness, bool isDiffuseSample, bool isEnvSample) {
   if (!(a.flags & RFX_SSGI_USE_ENVMAP)) return mk3(0.0f);
   const v3 reflectedWS = normalize_<AP>(mul_dir_left(l, a.cam.view_matrix));
   float mip = a.env_blur * a.max_env_mip;
   if (!isDiffuseSample && roughness < 0.15f) mip *= div_<AP>(roughness, 0.15f);
-  v3 s = env_trilinear(a.env, equirectDirectionToUv<AP>(reflectedWS), mip);
+  v3 s = env_trilinear(a.env, equirectDirectionToUv<AP, POLY>(reflectedWS), mip);
   const float maxEnvLum = isEnvSample ? 100.0f : 25.0f;
   const float envLum = lum_s(s);
   if (envLum > maxEnvLum) s = s * div_<AP>(maxEnvLum, envLum);
@@ -568,9 +568,9 @@ __global__ void __launch_bounds__(kThreads, PHASE == 1 ? RFX_K1_MARCH_MIN_BLOCKS
 
 // ==========================================================================================================================
 // K1, fast variant (fast_math on, fused phase): same shader, restructured for what bounds it on B200 (profiles/r01_v4: issue
-// 68 %, 22.5 of 32 lanes active, 58 instructions per march tap):
-//   * the diffuse rays of a 16x16 block — only the pixels that win the diffuse / specular lottery cast one — are compacted
-//     through shared memory and traced by FULL warps, instead of every warp running its diffuse phase with ~45 % of its lanes;
+// 68 %, 22.5 of 32 lanes active, 58 instructions per march tap).  Measured and dropped (profiles/r02_s2_ncu_summary.txt): compacting the
+// diffuse rays of a block through shared memory so that full warps trace them — lane use stayed at 22 / 32 (the waste is rays
+// leaving the loop at different steps, not the lottery) while the two block barriers cost 0.1 ms.
 //   * the march tap is ~25 instructions: projection rows pre-scaled to texel units on the host, packed fp32x2 arithmetic
 //     (FFMA2), one-instruction index clamps, 32-bit word indexing of the viewZ plane;
 //   * in a row-sharded group (PEER) last frame's `composed` is sampled in place on the rank that owns the row (NVLink loads).
@@ -594,17 +594,27 @@ RFX_D v3 fma3(v3 d, float s, v3 p) {
   const f2 xy = f2fma(mkf2(d.x, d.y), mkf2(s), mkf2(p.x, p.y));
   return mk3(f2lo(xy), f2hi(xy), fma_(d.z, s, p.z));
 }
-// RayMarch + BinarySearch  ssgi.frag:441-503
+// RayMarch + BinarySearch  ssgi.frag:441-503.  The ray positions do not depend on the fetched depths, so two steps are projected
+// and fetched together and tested in order: the march is a chain of dependent L2-latency gathers (L1 hit ~50 %), and at ~25
+// instructions per tap the other resident warps no longer hide that latency on their own (one wasted tap per hit at most).
 template <bool SPARSE>
 RFX_D v2 march_fast(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit) {
   dir = dir * (a.ray_distance / (float)a.steps);
   hit = false;
-  const float* cs_row = a.step_table + noiseB;
+  const float* cs_row = a.step_table + noiseB;  // row i-1 holds cs(i, b); the table carries one spare row for the speculative read
   v3 p = hitPos;
-  for (int i = 1; i < a.steps; i++, cs_row += 256) {
-    p = fma3(dir, __ldg(cs_row), p);
-    const float diff = tap_viewz<SPARSE>(a, p) - p.z;
-    if (diff >= 0.0f && diff < a.thickness) { hit = true; break; }
+  for (int i = 1; i < a.steps; i += 2, cs_row += 512) {
+    const v3 p1 = fma3(dir, __ldg(cs_row), p);
+    const v3 p2 = fma3(dir, __ldg(cs_row + 256), p1);
+    const float z1 = tap_viewz<SPARSE>(a, p1), z2 = tap_viewz<SPARSE>(a, p2);
+    const float d1 = z1 - p1.z, d2 = z2 - p2.z;
+    if (d1 >= 0.0f && d1 < a.thickness) { hit = true; p = p1; break; }
+    if (i + 1 < a.steps) {
+      p = p2;
+      if (d2 >= 0.0f && d2 < a.thickness) { hit = true; break; }
+    } else {
+      p = p1;
+    }
   }
   if (!hit) {
     hitPos = mk3(10.0e9f);
@@ -641,7 +651,7 @@ RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughne
   bool hit;
   const v2 coords = march_fast<SPARSE>(a, l, hitPos, noiseB, hit);
   const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
-  if (!hit && !allowMissedRays) return getEnvColor<true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  if (!hit && !allowMissedRays) return getEnvColor<true, true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v2 vel = mk2(0.0f, 0.0f);
   if (a.velocity.p) { const float4 t = tex_f4_nearest(a.velocity, coords); vel = mk2(t.x, t.y); }
   const v2 ruv = coords - vel;
@@ -649,7 +659,7 @@ RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughne
   // a hit whose borderFactor is exactly 1 (the inner 70 % x 70 % of the screen) resolves to mix(env, rgi, 1) = rgi: no env fetch
   const bool inner = reproj_ok && coords.x >= 0.15f && coords.x <= 1.0f - 0.15f && coords.y >= 0.15f && coords.y <= 1.0f - 0.15f;
   v3 envColor = mk3(0.0f);
-  if (!inner) envColor = getEnvColor<true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
+  if (!inner) envColor = getEnvColor<true, true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   if (!reproj_ok) return envColor;
   v3 rgi = mk3(0.0f);
   if (a.accumulated.p) {
@@ -671,16 +681,8 @@ RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughne
   return SSGI;
 }
 
-#define K1Q_FIELDS 15
 template <int MODE, bool IS, bool SPARSE, bool PEER>
 __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_fast_kernel(const __grid_constant__ SsgiArgs a) {
-  __shared__ float q[K1Q_FIELDS][kThreads];  // compacted diffuse-ray tasks of this block (structure of arrays)
-  __shared__ float dres[3][kThreads];        // their results, by the pixel's thread index
-  __shared__ int nq;
-  if (MODE == RFX_MODE_SSGI) {
-    if (threadIdx.x == 0) nq = 0;
-    __syncthreads();
-  }
   int x, y;
   const bool in_rows = seg_pixel(a.segs, x, y);
   const bool active = x < a.W && y < a.H && in_rows;
@@ -700,146 +702,109 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_fast_kernel(
     const float rho = fmaxf(length(ddx), length(ddy));
     lambda = rho > 0.0f ? lg2a_(rho) : -1000.0f;
   }
+  if (!active) return;
   const v2 vUv = pixel_uv(x, y, a.W, a.H);
-  const float unpackedDepth = active ? ld_r32f(a.depth, x, y) : 1.0f;
-  const bool live = active && unpackedDepth != 1.0f;
-  if (active && !live) {  // background :109-113
+  const float unpackedDepth = ld_r32f(a.depth, x, y);
+  if (unpackedDepth == 1.0f) {  // background :109-113
     v4 dl = mk4(0.0f, 0.0f, 0.0f, 1.0f);
     if (a.direct.p) dl = tex_h4_linear(a.direct, vUv);
     st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(dl, dl));
+    return;
   }
-  // state that survives until the pixel's result is packed
-  v3 specularGI = mk3(0.0f);
-  float rayLength = 0.0f, roughness0 = 0.0f;
+  const float4 g = ld_f4(a.gb, x, y);
+  PixelMat m;
+  m.diffuse = xyz(floatToVec4(g.x));
+  const v3 worldNormal = unpackNormal(g.y);
+  m.roughness = gb_roughness(g.z);
+  m.metalness = gb_metalness(g.z);
+  const float roughnessSq = clampf(m.roughness * m.roughness, 0.000001f, 1.0f);
+  const float viewZ = ssgi_view_z(a, unpackedDepth);
+  v3 viewPos;
+  {
+    const float clipW = a.cam.projection.m[2 * 4 + 3] * viewZ + a.cam.projection.m[3 * 4 + 3];
+    v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
+    clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
+    viewPos = xyz(mul(a.cam.projection_inverse, clip));
+    viewPos.z = viewZ;
+  }
+  const v3 viewDir = normalize(viewPos);
+  const v3 viewNormal = normalize(mul_dir_left(worldNormal, a.cam.camera_matrix_world));
+  const v3 n = viewNormal;
+  const v3 v = -viewDir;
+  const float NoV = fmaxf(SSGI_EPSILON, dot(n, v));
+  v3 V = mul_dir_left(v, a.cam.view_matrix);
+  const v3 N = worldNormal;
+  v3 T, B;
+  Onb(N, T, B);
+  V = ToLocal(T, B, N, V);
+  const v3 f0 = mix(mk3(0.04f), m.diffuse, m.metalness);
+  const float2 sc = __ldg(a.rot_table + bn.y);
+  v3 Hh = SampleGGXVNDF_cs(V, roughnessSq, roughnessSq, random.x, sc.y, sc.x);
+  if (Hh.z < 0.0f) Hh = -Hh;
+  v3 l = normalize(reflect(-V, Hh));
+  l = ToWorld(T, B, N, l);
+  l = mul_dir_left(l, a.cam.camera_matrix_world);
+  l = normalize(l);
+  float NoL, NoH, LoH, VoH;
+  calculateAngles<false>(l, v, n, NoL, NoH, LoH, VoH);  // VoH feeds the lottery threshold: IEEE
   bool isDiffuseSample = false;
-  if (live) {
-    const float4 g = ld_f4(a.gb, x, y);
-    PixelMat m;
-    m.diffuse = xyz(floatToVec4(g.x));
-    const v3 worldNormal = unpackNormal(g.y);
-    m.roughness = gb_roughness(g.z);
-    m.metalness = gb_metalness(g.z);
-    roughness0 = m.roughness;
-    const float roughnessSq = clampf(m.roughness * m.roughness, 0.000001f, 1.0f);
-    const float viewZ = ssgi_view_z(a, unpackedDepth);
-    v3 viewPos;
-    {
-      const float clipW = a.cam.projection.m[2 * 4 + 3] * viewZ + a.cam.projection.m[3 * 4 + 3];
-      v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
-      clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
-      viewPos = xyz(mul(a.cam.projection_inverse, clip));
-      viewPos.z = viewZ;
+  if (MODE == RFX_MODE_SSGI) {
+    const v3 F = f0 + (mk3(1.0f) - f0) * pow5<true>(1.0f - VoH);
+    float diffW = (1.0f - m.metalness) * lum_s(m.diffuse);
+    float specW = lum_s(F);
+    diffW = fmaxf(diffW, SSGI_EPSILON);
+    specW = fmaxf(specW, SSGI_EPSILON);
+    const float invW = 1.0f / (diffW + specW);
+    diffW *= invW;
+    isDiffuseSample = random.z < diffW;
+  }
+  float emsPdf = 1.0f, emsProbability = 0.0f;
+  bool emsIsEnvSample = false;
+  v3 envMisDir = mk3(0.0f);
+  if (IS) {  // ssgi.frag:197-215, ssgi_utils.frag:210-225
+    envMisDir = equirectUvToDirection<true>(cdfUv);
+    const v3 color = env_trilinear(a.env, cdfUv, lambda);
+    const float totalSum = a.env.total_sum_whole + a.env.total_sum_decimal;
+    const float pdf0 = lum_s(color) / totalSum;
+    emsPdf = a.env.size_x * a.env.size_y * pdf0;
+    envMisDir = normalize(mul_dir_left(envMisDir, a.cam.camera_matrix_world));
+    emsProbability = dot(envMisDir, viewNormal);
+    emsProbability *= m.roughness;
+    emsProbability = fminf(SSGI_ONE_MINUS_EPSILON, emsProbability);
+    emsIsEnvSample = random.w < emsProbability;
+    if (emsIsEnvSample) {
+      emsPdf /= 1.0f - emsProbability;
+      l = envMisDir;
+    } else {
+      emsPdf = 1.0f - emsProbability;
     }
-    const v3 viewDir = normalize(viewPos);
-    const v3 viewNormal = normalize(mul_dir_left(worldNormal, a.cam.camera_matrix_world));
-    const v3 n = viewNormal;
-    const v3 v = -viewDir;
-    const float NoV = fmaxf(SSGI_EPSILON, dot(n, v));
-    v3 V = mul_dir_left(v, a.cam.view_matrix);
-    const v3 N = worldNormal;
-    v3 T, B;
-    Onb(N, T, B);
-    V = ToLocal(T, B, N, V);
-    const v3 f0 = mix(mk3(0.04f), m.diffuse, m.metalness);
-    const float2 sc = __ldg(a.rot_table + bn.y);
-    v3 Hh = SampleGGXVNDF_cs(V, roughnessSq, roughnessSq, random.x, sc.y, sc.x);
-    if (Hh.z < 0.0f) Hh = -Hh;
-    v3 l = normalize(reflect(-V, Hh));
-    l = ToWorld(T, B, N, l);
-    l = mul_dir_left(l, a.cam.camera_matrix_world);
-    l = normalize(l);
-    float NoL, NoH, LoH, VoH;
-    calculateAngles<false>(l, v, n, NoL, NoH, LoH, VoH);  // VoH feeds the lottery threshold: IEEE
-    if (MODE == RFX_MODE_SSGI) {
-      const v3 F = f0 + (mk3(1.0f) - f0) * pow5<true>(1.0f - VoH);
-      float diffW = (1.0f - m.metalness) * lum_s(m.diffuse);
-      float specW = lum_s(F);
-      diffW = fmaxf(diffW, SSGI_EPSILON);
-      specW = fmaxf(specW, SSGI_EPSILON);
-      const float invW = 1.0f / (diffW + specW);
-      diffW *= invW;
-      isDiffuseSample = random.z < diffW;
-    }
-    float emsPdf = 1.0f, emsProbability = 0.0f;
-    bool emsIsEnvSample = false;
-    v3 envMisDir = mk3(0.0f);
-    if (IS) {  // ssgi.frag:197-215, ssgi_utils.frag:210-225
-      envMisDir = equirectUvToDirection<true>(cdfUv);
-      const v3 color = env_trilinear(a.env, cdfUv, lambda);
-      const float totalSum = a.env.total_sum_whole + a.env.total_sum_decimal;
-      const float pdf0 = lum_s(color) / totalSum;
-      emsPdf = a.env.size_x * a.env.size_y * pdf0;
-      envMisDir = normalize(mul_dir_left(envMisDir, a.cam.camera_matrix_world));
-      emsProbability = dot(envMisDir, viewNormal);
-      emsProbability *= m.roughness;
-      emsProbability = fminf(SSGI_ONE_MINUS_EPSILON, emsProbability);
-      emsIsEnvSample = random.w < emsProbability;
-      if (emsIsEnvSample) {
-        emsPdf /= 1.0f - emsProbability;
-        l = envMisDir;
-      } else {
-        emsPdf = 1.0f - emsProbability;
-      }
-    }
-    const float desat = (1.0f - roughnessSq) * getSaturation<true>(m.diffuse) * 0.4f;
-    if (MODE == RFX_MODE_SSGI) {  // queue the diffuse ray :222-242
-      const unsigned want = __ballot_sync(__activemask(), isDiffuseSample);
-      if (isDiffuseSample) {
-        const unsigned lane = threadIdx.x & 31;
-        const int leader = __ffs(want) - 1;
-        int base = 0;
-        if ((int)lane == leader) base = atomicAdd(&nq, __popc(want));
-        base = __shfl_sync(want, base, leader);
-        const int slot = base + __popc(want & ((1u << lane) - 1u));
-        const v3 dray = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs<true>(viewNormal, random.x, sc.x, sc.y);
-        q[0][slot] = viewPos.x; q[1][slot] = viewPos.y; q[2][slot] = viewPos.z;
-        q[3][slot] = viewNormal.x; q[4][slot] = viewNormal.y; q[5][slot] = viewNormal.z;
-        q[6][slot] = dray.x; q[7][slot] = dray.y; q[8][slot] = dray.z;
-        q[9][slot] = roughnessSq; q[10][slot] = m.metalness; q[11][slot] = desat; q[12][slot] = NoV; q[13][slot] = emsPdf;
-        q[14][slot] = __uint_as_float((unsigned)threadIdx.x | ((unsigned)bn.z << 8) | (emsIsEnvSample ? 0x10000u : 0u));
-      }
-    }
-    // the specular ray :246-265
-    calculateAngles<true>(l, v, n, NoL, NoH, LoH, VoH);
-    v3 hitPos;
-    float brdf, pdf;
+  }
+  const float desat = (1.0f - roughnessSq) * getSaturation<true>(m.diffuse) * 0.4f;
+  const float inv_ems = rcp_<true>(emsPdf);
+  v3 diffuseGI = mk3(0.0f), specularGI, hitPos;
+  float brdf, pdf;
+  if (MODE == RFX_MODE_SSGI && isDiffuseSample) {  // :222-242
+    const v3 dray = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs<true>(viewNormal, random.x, sc.x, sc.y);
+    calculateAngles<true>(dray, v, n, NoL, NoH, LoH, VoH);
+    v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, dray, hitPos, brdf, pdf);
+    gi = gi * brdf;
+    if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
+    diffuseGI = gi * inv_ems;
+  }
+  calculateAngles<true>(l, v, n, NoL, NoH, LoH, VoH);  // the specular ray :246-265
+  {
     v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
-    specularGI = vdiv_<true>(gi, emsPdf);
-    if (!(hitPos.x > 10.0e8f)) {  // :288-296
-      const v3 cameraPosWS = mk3(a.cam.camera_matrix_world.m[12], a.cam.camera_matrix_world.m[13], a.cam.camera_matrix_world.m[14]);
-      const v3 hitPosWS = xyz(mul(a.cam.camera_matrix_world, mk4(hitPos, 1.0f)));
-      const v3 dWS = cameraPosWS - hitPosWS;
-      rayLength = sqrt_<true>(dot(dWS, dWS));
-    }
+    specularGI = gi * inv_ems;
   }
-  if (MODE == RFX_MODE_SSGI) {
-    __syncthreads();
-    const int t = threadIdx.x;
-    if (t < nq) {  // one compacted diffuse ray per thread: full warps
-      const v3 viewPos = mk3(q[0][t], q[1][t], q[2][t]), viewNormal = mk3(q[3][t], q[4][t], q[5][t]);
-      v3 l = mk3(q[6][t], q[7][t], q[8][t]);
-      const float roughnessSq = q[9][t], metalness = q[10][t], desat = q[11][t], NoV = q[12][t], emsPdf = q[13][t];
-      const unsigned w = __float_as_uint(q[14][t]);
-      const bool isEnv = (w & 0x10000u) != 0;
-      const v3 v = -normalize_<true>(viewPos);
-      float NoL, NoH, LoH, VoH;
-      calculateAngles<true>(l, v, viewNormal, NoL, NoH, LoH, VoH);
-      v3 hitPos;
-      float brdf, pdf;
-      v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, metalness, desat, true, isEnv, NoV, NoL, NoH, LoH, (int)((w >> 8) & 0xffu), l, hitPos, brdf, pdf);
-      gi = gi * brdf;
-      if (isEnv) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
-      gi = vdiv_<true>(gi, emsPdf);
-      const int o = (int)(w & 0xffu);
-      dres[0][o] = gi.x; dres[1][o] = gi.y; dres[2][o] = gi.z;
-    }
-    __syncthreads();
+  float rayLength = 0.0f;
+  if (!(hitPos.x > 10.0e8f)) {  // :288-296
+    const v3 cameraPosWS = mk3(a.cam.camera_matrix_world.m[12], a.cam.camera_matrix_world.m[13], a.cam.camera_matrix_world.m[14]);
+    const v3 hitPosWS = xyz(mul(a.cam.camera_matrix_world, mk4(hitPos, 1.0f)));
+    const v3 dWS = cameraPosWS - hitPosWS;
+    rayLength = sqrt_<true>(dot(dWS, dWS));
   }
-  if (!live) return;
-  v3 diffuseGI = mk3(0.0f);
-  if (MODE == RFX_MODE_SSGI && isDiffuseSample) diffuseGI = mk3(dres[0][threadIdx.x], dres[1][threadIdx.x], dres[2][threadIdx.x]);
   if (a.flags & RFX_SSGI_USE_DIRECT_LIGHT) {  // :267-272
     v3 dl = mk3(0.0f);
     if (a.direct.p) dl = xyz(tex_h4_linear(a.direct, vUv));
@@ -848,9 +813,9 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_fast_kernel(
   }
   if (MODE == RFX_MODE_SSGI) {
     if (!isDiffuseSample) diffuseGI = mk3(-1.0f);
-    st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(mk4(diffuseGI, roughness0), mk4(specularGI, rayLength)));
+    st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(mk4(diffuseGI, m.roughness), mk4(specularGI, rayLength)));
   } else {
-    const float al = __uint_as_float(packHalf2x16(rayLength, roughness0));
+    const float al = __uint_as_float(packHalf2x16(rayLength, m.roughness));
     st_f4(a.out.p, a.out.pitch, x, y, make_float4(specularGI.x, specularGI.y, specularGI.z, al));
   }
 }

@@ -194,6 +194,14 @@ rfx_status rfx_plane_download(rfx_ctx* ctx, void* stream, const rfx_plane* src, 
   else CU(cudaMemcpy2DAsync(host, host_pitch, src->ptr, src->pitch, row, src->height, cudaMemcpyDeviceToHost, pick(ctx, stream)));
   return RFX_OK;
 }
+rfx_status rfx_plane_download_rows(rfx_ctx* ctx, void* stream, const rfx_plane* src, void* host, uint32_t row0, uint32_t row1) {
+  if (!ctx || !src || !src->ptr || !host || row0 >= row1 || row1 > src->height) return RFX_ERR_INVALID_ARG;
+  const size_t row = (size_t)src->width * rfx_format_bytes(src->format);
+  const unsigned char* p = (const unsigned char*)src->ptr + (size_t)row0 * src->pitch;
+  if (src->pitch == row) CU(cudaMemcpyAsync(host, p, row * (row1 - row0), cudaMemcpyDeviceToHost, pick(ctx, stream)));
+  else CU(cudaMemcpy2DAsync(host, row, p, src->pitch, row, row1 - row0, cudaMemcpyDeviceToHost, pick(ctx, stream)));
+  return RFX_OK;
+}
 rfx_status rfx_host_alloc(rfx_ctx* ctx, uint64_t bytes, void** out) {
   if (!ctx || !out) return RFX_ERR_INVALID_ARG;
   CU(cudaSetDevice(ctx->device));
@@ -334,7 +342,7 @@ static rfx_status ensure_step_table(rfx_ctx* ctx, int steps) {
   CU(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->step_table);
   ctx->step_table = nullptr;
-  int rows_n = steps > 1 ? steps - 1 : 1;
+  int rows_n = steps + 1;  // rows 0..steps-2 hold cs(1..steps-1, b); two spare zero rows: the fast march reads one step ahead
   std::vector<float> t((size_t)rows_n * 256, 0.0f);
   for (int i = 1; i < steps; i++)
     for (int k = 0; k < 256; k++) {  // ssgi.frag:453   cs = 1. - exp(-0.25 * pow(float(i) + random.b - 0.5, 2.))

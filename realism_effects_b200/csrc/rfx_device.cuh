@@ -300,9 +300,18 @@ RFX_D f2 f2ex2(f2 a) { return mkf2(fx_ex2(f2lo(a)), fx_ex2(f2hi(a))); }
 // nrdz: float4 (n.x, n.y, n.z, depth); the 9-bit roughness code k = mod(gBuffer.b, 257) rides in the low mantissa bits of
 //       n.x (5 bits) and n.y (4 bits): |dn| <= 2^-19 relative.  roughness = max(k/256 - 1e-4, 0)  (gbuffer_packing.glsl:24-34,189)
 RFX_D float nrdz_roughness(float4 t) {
-  const uint32_t k = (__float_as_uint(t.x) & 31u) | ((__float_as_uint(t.y) & 15u) << 5);
-  return fmaxf((float)k / 256.0f - RFX_NON_ZERO_OFFSET, 0.0f);
+  // (float)k through the 2^23 trick (k < 2^9): integer -> float conversions run on the quarter-rate XU pipe, which the Poisson
+  // passes already load to ~60 % with their lg2 / ex2
+  const uint32_t kb = (__float_as_uint(t.x) & 31u) | ((__float_as_uint(t.y) & 15u) << 5) | 0x4B000000u;
+  return fmaxf((__uint_as_float(kb) - 8388608.0f) * 0.00390625f - RFX_NON_ZERO_OFFSET, 0.0f);
 }
+// floor(v) for |v| < 2^22 without the conversion (XU) pipe: FADD.RM against 1.5 * 2^23 leaves floor(v) in the low mantissa bits
+RFX_D int floor_i(float v, float& fl) {
+  const float t = __fadd_rd(v, 12582912.0f);
+  fl = t - 12582912.0f;
+  return __float_as_int(t) - 0x4B400000;
+}
+RFX_D int floor_i(float v) { return __float_as_int(__fadd_rd(v, 12582912.0f)) - 0x4B400000; }
 RFX_D float4 nrdz_pack(v3 n, float rough_code, float depth) {
   const uint32_t k = (uint32_t)rough_code;
   return make_float4(__uint_as_float((__float_as_uint(n.x) & ~31u) | (k & 31u)), __uint_as_float((__float_as_uint(n.y) & ~15u) | ((k >> 5) & 15u)), n.z, depth);

@@ -136,6 +136,7 @@ struct rfx_group {
   std::vector<uint32_t> bounds;              // bands of the frame being rendered (world + 1)
   std::vector<uint32_t> bounds_ring[RFX_GROUP_RING];  // bands each recent frame was rendered with
   uint64_t frame = 0;
+  bool began = false;  // begin_frame already ran for the frame about to be rendered
   // device-timed cost of this rank's kernels, all-gathered every frame (the collective doubles as the frame barrier)
   unsigned long long* d_t0 = nullptr;
   float* d_ms = nullptr;     // [1 + world]: own, then everyone's
@@ -283,6 +284,56 @@ rfx_status rfx_group_last_costs(const rfx_group* g, float* ms) {
   return RFX_OK;
 }
 
+// In lockstep on every rank (no communication): applies the cost-driven border move that is due and returns the borders the next
+// frame will be rendered with.  rfx_ssgi_chain_render_sharded calls it implicitly; a host path calls it first to size its uploads.
+rfx_status rfx_group_begin_frame(rfx_group* g, uint32_t* bounds_out) {
+  if (!g || !g->chain) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = g->ctx;
+  const int n = g->world;
+  if (!g->began) {
+    g->began = true;
+    // cost-driven borders (deterministic on every rank: same gathered times, same arithmetic)
+    if (g->rebalance_every > 0 && g->frame >= (uint64_t)g->rebalance_lag && g->frame % (uint64_t)g->rebalance_every == 0) {
+      const uint64_t src = g->frame - (uint64_t)g->rebalance_lag;
+      const int slot = (int)(src % RFX_GROUP_RING);
+      if (g->ev_valid[slot]) {
+        CU(cudaEventSynchronize(g->ev[slot]));
+        std::vector<uint32_t> nb((size_t)n + 1);
+        memcpy(g->last_costs, g->h_ms + (size_t)slot * n, sizeof(float) * (size_t)n);
+        if (rfx_shard_rebalance(g->bounds.data(), g->bounds_ring[slot].data(), g->last_costs, n, nb.data()) == RFX_OK) g->bounds = nb;
+      }
+    }
+  }
+  if (bounds_out) memcpy(bounds_out, g->bounds.data(), sizeof(uint32_t) * g->bounds.size());
+  return RFX_OK;
+}
+rfx_status rfx_group_get_last_bounds(const rfx_group* g, uint32_t* bounds) {  // the borders the most recent frame was rendered with
+  if (!g || !bounds || g->bounds.empty()) return RFX_ERR_INVALID_ARG;
+  const std::vector<uint32_t>& b = g->frame ? g->bounds_ring[(g->frame - 1) % RFX_GROUP_RING] : g->bounds;
+  memcpy(bounds, b.data(), sizeof(uint32_t) * b.size());
+  return RFX_OK;
+}
+
+// Collective: completes a full-frame INPUT plane of which every rank has uploaded only its own rows [bounds[r], bounds[r+1]):
+// one NCCL group of per-rank broadcasts (an all-gather with unequal counts), in place, over NVLink.  This is the path's one
+// real exchange of the host-buffer route: depth and velocity are sampled at arbitrary screen positions by every rank.
+rfx_status rfx_group_allgather_rows(rfx_group* g, void* stream, const rfx_plane* plane, const uint32_t* bounds) {
+  if (!g || !plane || !plane->ptr || !bounds) return RFX_ERR_INVALID_ARG;
+  rfx_ctx* ctx = g->ctx;
+  const cudaStream_t cs = stream ? (cudaStream_t)stream : ctx->stream;
+  if (bounds[g->world] > plane->height) return fail(ctx, RFX_ERR_INVALID_ARG, "group_allgather_rows: borders exceed the plane");
+  if (g->world == 1) return RFX_OK;
+  NcclApi* n = nccl_api();
+  NC(n->GroupStart());
+  for (int r = 0; r < g->world; r++) {
+    unsigned char* p = (unsigned char*)plane->ptr + (size_t)bounds[r] * plane->pitch;
+    const size_t bytes = (size_t)(bounds[r + 1] - bounds[r]) * plane->pitch;
+    if (bytes) NC(n->Broadcast(p, p, bytes, ncclChar, r, g->comm, cs));
+  }
+  NC(n->GroupEnd());
+  return RFX_OK;
+}
+
 // Collective: one frame, this rank's band.  Inputs are full-frame planes (every rank holds them).  Ends with the group's
 // per-frame collective on `stream`, after which every rank's rows of this frame are visible to its peers.
 rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f) {
@@ -292,17 +343,9 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
   if (!g) return fail(ctx, RFX_ERR_NOT_READY, "render_sharded: the chain is not attached to a group (rfx_group_attach_chain)");
   const int n = g->world;
   const cudaStream_t cs = stream ? (cudaStream_t)stream : ctx->stream;
-  // cost-driven borders (deterministic on every rank: same gathered times, same arithmetic)
-  if (g->rebalance_every > 0 && g->frame >= (uint64_t)g->rebalance_lag && g->frame % (uint64_t)g->rebalance_every == 0) {
-    const uint64_t src = g->frame - (uint64_t)g->rebalance_lag;
-    const int slot = (int)(src % RFX_GROUP_RING);
-    if (g->ev_valid[slot]) {
-      CU(cudaEventSynchronize(g->ev[slot]));
-      std::vector<uint32_t> nb((size_t)n + 1);
-      memcpy(g->last_costs, g->h_ms + (size_t)slot * n, sizeof(float) * (size_t)n);
-      if (rfx_shard_rebalance(g->bounds.data(), g->bounds_ring[slot].data(), g->last_costs, n, nb.data()) == RFX_OK) g->bounds = nb;
-    }
-  }
+  rfx_status st = rfx_group_begin_frame(g, nullptr);
+  if (st != RFX_OK) return st;
+  g->began = false;
   const int cur = (int)(ch->frame_idx & 1), prev = cur ^ 1;
   // owners of the data this frame READS (last frame's bands) and of the rows it carries forward
   const std::vector<uint32_t>& pb = g->bounds_ring[(g->frame + RFX_GROUP_RING - 1) % RFX_GROUP_RING];
@@ -313,7 +356,7 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
   }
   const uint32_t n_launches = 3u + 2u * (uint32_t)ch->opt.denoise_iterations;
   std::vector<uint32_t> ranges((size_t)n_launches * 2);
-  rfx_status st = rfx_shard_ranges(ch->opt.width, ch->opt.height, g->bounds[g->rank], g->bounds[g->rank + 1], 2 * ch->opt.denoise_iterations, ch->opt.radius, 1, ranges.data(), n_launches);
+  st = rfx_shard_ranges(ch->opt.width, ch->opt.height, g->bounds[g->rank], g->bounds[g->rank + 1], 2 * ch->opt.denoise_iterations, ch->opt.radius, 1, ranges.data(), n_launches);
   if (st != RFX_OK) return fail(ctx, st, "render_sharded: bad band");
   stamp_kernel<<<1, 1, 0, cs>>>(g->d_t0);
   if ((st = chain_render_impl(ch, stream, f, ranges.data(), 1, 0, 0xffffffffu)) != RFX_OK) return st;

@@ -1,37 +1,29 @@
-"""Row-block sharding of the SSGI chain across N GPUs (one process per GPU, torch.distributed / NCCL over NVLink).
+"""Row-band sharding of the SSGI chain across N GPUs (one process per GPU).
 
-Every kernel of the path writes disjoint output rows, so the produced planes are partitioned by row block
-(SURVEY.md §8e).  Two kinds of inputs cross row-block borders:
+The product path is native: `rfx_group_*` / `rfx_ssgi_chain_render_sharded` in csrc/rfx_group.inl (C ABI, include/rfx.h).
+This module is the Python host binding of that API (`ShardedSsgiChain`) plus a pure-Python mirror of its host arithmetic
+(`ShardPlan`, `rebalance`) that the CPU tests check against the exported C functions `rfx_shard_ranges` / `rfx_shard_rebalance`
+and drive with the oracle as compute (tests/test_sharding_cpu.py).
 
-  * bounded stencils — K2's 5x5 neighbourhood of ssgiOut (2 rows), K3's Poisson taps (ceil(radius)+1 rows per pass,
-    bilinear footprint included), K4's pixel-centre bilinear fetch of dnB (1 row).  Instead of one halo exchange per
-    pass, each rank RECOMPUTES the halo rows itself: pass k is launched on a row range widened by the halos of all the
-    passes after it (`ShardPlan`).  Kernels are bit-identical under row sharding, so the recomputed rows equal the
-    owner's rows bit for bit, and no per-pass NCCL latency is paid (cost: ~1 % extra rows per block at 4K).
-  * arbitrary-uv gathers — K1 samples `composed` at ray hit points and K2 samples the history `dnB[0..1]` at
-    reprojected uvs anywhere on screen, so these three produced planes are all-gathered once per frame (32 B/px of each
-    rank's rows).  The static inputs (depth, gBuffer, velocity, directLight) are given to every rank in full.
+Every kernel of the path writes disjoint output rows, so the produced planes are partitioned by row band.
+Two kinds of inputs cross band borders:
 
-Load balance: sky rows are nearly free (background pixels are discarded) while floor rows are the most expensive, so
-contiguous bands would leave the max-over-ranks time ~1/3 above the mean.  Rows are therefore assigned BLOCK-CYCLICALLY:
-with B blocks per rank the frame is cut into N*B blocks and rank r owns blocks r, r+N, r+2N, ...; super-block j (blocks
-j*N .. j*N+N-1) is contiguous and in rank order, so each plane is all-gathered in place with B collectives.
+  * bounded stencils — K2's 5x5 neighbourhood of ssgiOut (2 rows), K3's Poisson taps (ceil(radius * max(1, H/W)) + 1 rows per
+    pass: the tap offset is rotated AFTER the division by the resolution, so portrait frames reach further in rows), K4's
+    pixel-centre fetch (1 row).  Instead of one halo exchange per pass, each rank RECOMPUTES the halo rows itself: pass k is
+    launched on a row range widened by the halos of all the passes after it.  Kernels are bit-identical under row sharding,
+    so the recomputed rows equal the owner's rows bit for bit and no per-pass latency is paid (~3 % extra rows at 4K / 8 ranks).
+  * arbitrary-uv gathers — K1 samples last frame's `composed` at ray hit points and K2 samples the `dn` history at reprojected
+    uvs anywhere on screen.  Round 1 replicated those planes with an all-gather (32 B/px x the whole frame per rank per frame,
+    which bounded the 8-GPU frame).  Now every rank keeps only its own rows and the kernels read a row another rank owns IN
+    PLACE over NVLink through CUDA-IPC peer mappings (PeerPV in csrc/rfx_kernels.h); the planes are double-buffered by frame
+    parity so no rank overwrites rows a peer may still read, and the frame ends with ONE tiny NCCL all-gather (each rank's
+    device-timed kernel cost) that is also the frame barrier.
 
-Overlap: a frame is issued in three parts (rfx_ssgi_chain_render_part).  K1's ray march reads the depth plane only; K1's
-shading samples last frame's `composed`; K2..K4 need the `dnB` history.  The exchanges are launched asynchronously after K4
-(composed first); the next frame marches its rays immediately, waits for `composed` only before the K1 shading part and for
-`dnB` only before K2 - so the `composed` transfer hides behind the march and the `dnB` transfer behind the whole of K1.
-
-Adaptive bands (`balance="adaptive"`, the default of bench.py): one CONTIGUOUS band per rank whose height follows the measured
-kernel time.  Every rank times its own kernels with CUDA events; every few frames the ranks exchange those times (a few floats
-over a gloo control group), model the cost per row as piecewise constant over the bands and move the band borders towards equal
-cost (`rebalance`, damped, 16-row aligned).  All cross-frame state lives in the exchanged planes, so the split may change from
-frame to frame without copying anything, and the result stays bit-identical.  Against block-cyclic assignment this keeps the
-K1 tap working set of a rank local (one band + ray reach instead of the whole frame), halves the halo rows and removes the
-partial-tile waste of many small blocks; the bands have different heights, so the exchange is a grouped send/recv.
-
-The result on N GPUs is bit-identical to the single-GPU result (tests/test_sharding_cpu.py with gloo + the oracle as
-compute; tests/test_gpu_multi.py on >= 2 GPUs).
+Adaptive bands: one contiguous band per rank; every few frames the borders move towards equal device-timed cost
+(`rfx_shard_rebalance`: cost per row piecewise constant over the measured bands, damped, 16-row aligned; every rank derives the
+same borders from the same gathered times).  All cross-frame state lives in the peer-readable planes, so borders move freely
+between frames and the result stays bit-identical to the single-GPU chain (tests/test_gpu_multi.py).
 """
 from __future__ import annotations
 
@@ -53,6 +45,7 @@ class ShardPlan:
     blocks_per_rank: int = 1
     mirror: bool = False  # True: odd super-blocks are assigned in REVERSE rank order (boustrophedon), see block_of()
     bounds: tuple | None = None  # explicit band borders (world + 1 ascending rows, 0 .. height): one contiguous band per rank
+    width: int | None = None     # frame width: portrait frames (H > W) stretch the Poisson taps' row reach by H / W
 
     K2_NEIGHBOURHOOD_ROWS = 2  # 5x5 clamp window (reproject.frag:57-59)
     K4_INPUT_ROWS = 1          # literal bilinear fetch of the LINEAR Poisson targets at the pixel centre
@@ -84,7 +77,7 @@ class ShardPlan:
             self.blocks = [self.block_of(self.rank, 0)]
             self.rows_per_rank = self.blocks[0][1] - self.blocks[0][0]
             self.r0, self.r1 = self.blocks[0]
-            self.poisson_halo = int(math.ceil(self.radius)) + 1
+            self.poisson_halo = self._halo()
             return
         nb = self.world * self.blocks_per_rank
         if self.height % nb:
@@ -93,7 +86,13 @@ class ShardPlan:
         self.rows_per_rank = self.block_rows * self.blocks_per_rank
         self.blocks = [self.block_of(self.rank, j) for j in range(self.blocks_per_rank)]
         self.r0, self.r1 = self.blocks[0]  # (single-block plans: the contiguous band)
-        self.poisson_halo = int(math.ceil(self.radius)) + 1  # taps reach ceil(radius) rows, +1 for the bilinear footprint
+        self.poisson_halo = self._halo()
+
+    def _halo(self) -> int:
+        """rows a Poisson tap can reach: the offset is rotated after the division by the resolution (poisson_denoise.frag:183-189),
+        so the row reach is radius * max(1, H / W); + 1 for the bilinear footprint / the quad-derivative helper row"""
+        stretch = max(1.0, self.height / self.width) if self.width else 1.0
+        return int(math.ceil(self.radius * stretch)) + 1
 
     def _expand(self, rng, rows):
         return (max(0, rng[0] - rows), min(self.height, rng[1] + rows))
@@ -140,10 +139,11 @@ class ShardPlan:
 
     @property
     def local_input_rows(self) -> list:
-        """Rows of the PER-PIXEL input planes (G-buffer, direct light) this rank reads: the K1 range of each block, which contains
-        every later launch's range and the rows its Poisson taps reach.  The planes sampled at arbitrary screen positions (depth:
-        ray-march taps; velocity: reprojected uv) are needed whole and are all-gathered from the ranks' own rows instead."""
-        return [rs[0] for rs in self.block_ranges]
+        """Rows of the PER-PIXEL input planes (G-buffer, direct light) this rank reads: the K1 range of each block (it contains
+        every later launch's range and the rows its Poisson taps reach) + 1 row each side, because K1's literal bilinear fetch
+        of the direct-light plane at the pixel centre touches row y +- 1 whenever ((y + .5) / H) * H - .5 is not exactly y.
+        The planes sampled at arbitrary screen positions (depth: ray-march taps; velocity: reprojected uv) are needed whole."""
+        return [self._expand(rs[0], 1) for rs in self.block_ranges]
 
     @property
     def gathered_planes(self):
@@ -181,336 +181,210 @@ def rebalance(bounds, costs, measured_bounds=None, align: int = 16, min_rows: in
         b = min(b, H - (n - i) * lo_h)                # leave room for the bands below
         out.append(b)
     out.append(H)
+    for i in range(n - 1, 0, -1):                     # the cap holds for the last bands too: push borders down where a band exceeds it
+        if out[i + 1] - out[i] > hi_h:
+            out[i] = min(out[i + 1] - lo_h, -(-(out[i + 1] - hi_h) // align) * align)
     return tuple(out)
 
 
-class _CudaBytes:
-    """__cuda_array_interface__ view of a raw device allocation (an rfx_plane) so torch/NCCL can address it."""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
-
-
 class _PlaneRef:
-    """adapter: SsgiChain.render takes objects with a `.p` rfx_plane"""
+    """adapter: objects with a `.p` rfx_plane"""
 
     def __init__(self, p):
         self.p = p
 
 
-class ShardedSsgiChain:
-    """The native SSGI chain on this rank's row blocks of a W x H frame + the per-frame all-gathers of the produced planes."""
+def _raw_plane(abi, ptr: int, width: int, height: int, pitch: int, fmt: int):
+    p = abi.Plane()
+    p.ptr, p.width, p.height, p.pitch, p.format = ptr, width, height, pitch, fmt
+    return p
 
-    def __init__(self, ctx, chain_options, group=None, blocks_per_rank: int = 4, overlap: bool = True, mirror: bool = False,
-                 balance: str = "static", rebalance_every: int = 4, rebalance_lag: int = 2, split_k1: bool = True, dual_comm: bool = False):
-        import torch
-        import torch.distributed as dist
+
+class ShardedSsgiChain:
+    """This rank's member of a row-sharded SSGI chain: Python binding of rfx_group_* + rfx_ssgi_chain_render_sharded.
+
+    The 128-byte NCCL unique id travels over torch.distributed (any backend) when a process group is initialised, or is
+    passed explicitly (`unique_id`, e.g. read from a file by a host without torch)."""
+
+    INPUTS = (("depth", 4, True), ("gbuffer", 16, False), ("velocity", 16, True), ("direct", 8, False))  # name, bytes/px, sampled anywhere
+
+    def __init__(self, ctx, chain_options, rank: int | None = None, world: int | None = None, unique_id: bytes | None = None,
+                 rebalance_every: int = 4, rebalance_lag: int = 2, dist_group=None):
+        import ctypes as C
 
         from . import abi, engine
 
-        self.dist, self.torch, self.group = dist, torch, group
-        self._abi = abi
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._abi, self.ctx, self.lib, self._C = abi, ctx, ctx.lib, C
+        if rank is None or world is None or unique_id is None:
+            import torch.distributed as dist
+
+            rank, world = dist.get_rank(dist_group), dist.get_world_size(dist_group)
+            box = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(abi.GROUP_ID_BYTES)
+                ctx._chk(self.lib.rfx_group_get_unique_id(buf))
+                box[0] = bytes(buf.raw)
+            src = dist.get_global_rank(dist_group, 0) if dist_group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=dist_group)
+            unique_id = box[0]
+        self.rank, self.world = rank, world
         self.chain = engine.SsgiChain(ctx, chain_options)
-        self.ctx = ctx
-        self.overlap = overlap
-        self.split_k1 = split_k1  # overlap mode: K1 as ray march + shading, so only the shading waits for the `composed` exchange
-        self.coalesce = True
-        self._plan_args = (chain_options.height, self.world, self.rank, 2 * chain_options.denoise_iterations, chain_options.radius,
-                           chain_options.mode == abi.MODE_SSGI)
-        if balance not in ("static", "adaptive"):
-            raise ValueError("balance must be 'static' (block-cyclic / mirrored blocks) or 'adaptive' (one cost-balanced band per rank)")
-        self.balance = balance if self.world > 1 else "static"
-        self.rebalance_every, self.rebalance_lag = max(1, rebalance_every), max(1, rebalance_lag)
-        self._frame, self._timing, self._ev_pool, self.last_costs, self._host_span = 0, [], [], None, None
-        if self.balance == "adaptive":
-            H, n = chain_options.height, self.world
-            if H < n * 64:
-                raise ValueError("adaptive bands need at least 64 rows per rank")
-            eq = tuple(int(round(H * i / n / 16.0)) * 16 for i in range(n)) + (H,)
-            self.plan = ShardPlan(*self._plan_args, bounds=eq)
-            # host-side control plane: a few floats per rebalance, over gloo (no device sync, no NCCL stream involved)
-            self.ctl_group = dist.new_group(ranks=[self._global_rank(r) for r in range(self.world)], backend="gloo")
-        else:
-            self.plan = ShardPlan(*self._plan_args, blocks_per_rank, mirror)
-        # A mirrored (boustrophedon) assignment puts the ranks of odd super-blocks in reverse order, which a rank-ordered
-        # all_gather_into_tensor cannot write in place (torch.distributed sorts the ranks of every new_group()).  Mirrored plans
-        # therefore exchange with grouped point-to-point transfers (one ncclGroup of send/recv pairs per exchange, every block
-        # landing directly at its rows); plain cyclic plans keep the in-place all-gather.
-        # a dedicated torch stream: the kernels and the NCCL collectives are ordered on it.  (A NULL stream handle means "the
-        # context's own stream" to the C ABI, so torch's default stream cannot be used here.)
-        self.stream = torch.cuda.Stream(device=torch.device("cuda", ctx.device))
-        self._tensors = {}
-        for which in self.plan.gathered_planes:
-            p = self.chain.output(which)
-            nbytes = int(p.pitch) * int(p.height)
-            t = torch.as_tensor(_CudaBytes(p.ptr, nbytes), device=torch.device("cuda", ctx.device))
-            self._tensors[which] = (t, int(p.pitch))
-        self._pending = {}  # plane index -> [Work]: all-gathers of the previous frame not yet waited for
-        # dual_comm (experiment, unmeasured in round 1): the dnB exchange runs on a second communicator so it moves concurrently with
-        # the `composed` exchange instead of queueing behind it on one NCCL stream.  Every rank issues both in the same order.
-        self.group2 = None
-        if dual_comm and self.world > 1:
-            self.group2 = dist.new_group(ranks=[self._global_rank(r) for r in range(self.world)])
+        g = C.c_void_p()
+        ctx._chk(self.lib.rfx_group_create(ctx.h, unique_id, rank, world, C.byref(g)))
+        self.g = g
+        ctx._chk(self.lib.rfx_group_attach_chain(g, self.chain.h))
+        ctx._chk(self.lib.rfx_group_set_rebalance(g, int(rebalance_every), int(rebalance_lag)))
+        self.rebalance_every = rebalance_every
+        self._host = None
 
-    def _wait(self, planes):
-        for which in planes:
-            for w in self._pending.pop(which, []):
-                w.wait()  # makes self.stream wait for the collective
+    # ---- bands -------------------------------------------------------------------------------------------------------
+    @property
+    def bounds(self) -> tuple:
+        b = (self._C.c_uint32 * (self.world + 1))()
+        self.ctx._chk(self.lib.rfx_group_get_bounds(self.g, b))
+        return tuple(int(x) for x in b)
 
-    def _exchange(self, items, group):
-        """Every rank's blocks of the planes `items` = [(flat byte tensor, pitch)] to every other rank, in place, as ONE NCCL group:
-        in-place all-gathers per super-block for cyclic plans, send/recv pairs for mirrored plans and unequal bands.  Returns the Work handles."""
-        plan = self.plan
-        if plan.p2p:
-            ops = []
-            for t, pitch in items:
-                for j, (b0, b1) in enumerate(plan.blocks):
-                    for peer in range(self.world):  # both sides walk (plane, block) in the same order, so the k-th send to a peer meets its k-th recv
-                        if peer == self.rank:
-                            continue
-                        p0, p1 = plan.block_of(peer, j)
-                        ops.append(self.dist.P2POp(self.dist.isend, t[b0 * pitch:b1 * pitch], self._global_rank(peer), group))
-                        ops.append(self.dist.P2POp(self.dist.irecv, t[p0 * pitch:p1 * pitch], self._global_rank(peer), group))
-            return list(self.dist.batch_isend_irecv(ops)) if ops else []
-        todo = []
-        for t, pitch in items:
-            for j, (b0, b1) in enumerate(plan.blocks):
-                s0, s1 = plan.super_block(j)
-                todo.append((t[s0 * pitch:s1 * pitch], t[b0 * pitch:b1 * pitch]))  # in place: every rank's block lands at its own rows
-        return self._all_gather(todo, group)
+    def set_bounds(self, bounds):
+        b = (self._C.c_uint32 * (self.world + 1))(*[int(x) for x in bounds])
+        self.ctx._chk(self.lib.rfx_group_set_bounds(self.g, b))
 
-    def _gather(self, planes, group=None):
-        """launches the exchange of the chain outputs `planes`; the handles wait under the first plane's key"""
-        self._pending[planes[0]] = self._exchange([self._tensors[w] for w in planes], group if group is not None else self.group)
+    @property
+    def band(self) -> tuple:
+        b = self.bounds
+        return b[self.rank], b[self.rank + 1]
 
-    def _global_rank(self, r: int) -> int:
-        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+    @property
+    def last_costs(self) -> list:
+        c = (self._C.c_float * self.world)()
+        self.ctx._chk(self.lib.rfx_group_last_costs(self.g, c))
+        return [float(x) for x in c]
 
-    def _event(self):
-        return self._ev_pool.pop() if self._ev_pool else self.torch.cuda.Event(enable_timing=True)
+    def begin_frame(self) -> tuple:
+        """Collective in lockstep (no communication): applies the cost-driven border move that is due for the next frame and
+        returns the borders that frame will use.  render() calls it implicitly; the host path calls it before its uploads."""
+        b = (self._C.c_uint32 * (self.world + 1))()
+        self.ctx._chk(self.lib.rfx_group_begin_frame(self.g, b))
+        return tuple(int(x) for x in b)
 
-    def _maybe_rebalance(self):
-        """adaptive bands: every `rebalance_every` frames move the band borders towards equal measured kernel time.  Uses the
-        newest measurement that is at least `rebalance_lag` frames old (long finished, so the event wait is immediate); the ranks
-        hold identical frame counters and gather identical costs, so they all derive the same borders."""
-        if self.balance != "adaptive":
-            return
-        f = self._frame
-        if f % self.rebalance_every == 0:
-            cand = [t for t in self._timing if t[0] <= f - self.rebalance_lag]
-            if cand:
-                _fr, mb, spans, hspan = cand[-1]
-                spans[-1][1].synchronize()
-                cost = sum(a.elapsed_time(b) for a, b in spans)
-                if hspan is not None:  # host path: a rank is as slow as the slower of its kernels and its PCIe upload (both grow with the band)
-                    hspan[1].synchronize()
-                    cost = max(cost, hspan[0].elapsed_time(hspan[1]))
-                mine = self.torch.tensor([cost], dtype=self.torch.float64)
-                allc = [self.torch.zeros(1, dtype=self.torch.float64) for _ in range(self.world)]
-                self.dist.all_gather(allc, mine, group=self.ctl_group)
-                self.last_costs = [float(c) for c in allc]
-                nb = rebalance(self.plan.bounds, self.last_costs, mb, max_share=self.MAX_SHARE)
-                if nb != self.plan.bounds:
-                    self.plan = ShardPlan(*self._plan_args, bounds=nb)
-        keep = []
-        for t in self._timing:  # recycle the events of measurements that can no longer be chosen
-            if t[0] > f - self.rebalance_lag - self.rebalance_every - 1:
-                keep.append(t)
-            else:
-                for a, b in t[2] + ([t[3]] if t[3] is not None else []):
-                    self._ev_pool += [a, b]
-        self._timing = keep
+    # ---- device-resident frame ---------------------------------------------------------------------------------------
+    def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, stream=None):
+        """Collective: one frame from full-frame device planes; this rank renders its band and joins the frame's collective."""
+        f = self.chain._frame(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
+        self.ctx._chk(self.lib.rfx_ssgi_chain_render_sharded(self.chain.h, stream, self._C.byref(f)))
 
-    def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool, _rebalanced: bool = False):
-        """Enqueues one frame on self.stream (two phases) and the asynchronous exchange of its outputs."""
-        torch = self.torch
-        args = (cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
-        with torch.cuda.stream(self.stream):
-            if self.world == 1:
-                self.chain.render(*args, stream=self.stream.cuda_stream)
-                return
-            if not _rebalanced:
-                self._maybe_rebalance()
-            plan = self.plan
-            br, nl = plan.block_ranges, plan.n_launches
-            first = plan.gathered_planes[0]
-            spans = []
+    def download_band(self, which: int = 0):
+        """this rank's rows of chain output `which` of the last frame (numpy)"""
+        b0, b1 = self.band_of_last_frame
+        return self.chain.download(which)[b0:b1]
 
-            def timed(launches=None, part=None):  # kernels only: the waits for the exchanges stay outside the measured spans
-                a, b = self._event(), self._event()
-                a.record(self.stream)
-                if part is None:
-                    self.chain.render(*args, stream=self.stream.cuda_stream, ranges=br, launches=launches)
-                else:
-                    self.chain.render_part(part, *args, stream=self.stream.cuda_stream, ranges=br)
-                b.record(self.stream)
-                spans.append((a, b))
-
-            if self.overlap and plan.ssgi_mode and self.split_k1:
-                timed(part=0)                                         # K1 ray march: depth only - runs under the exchange of `composed`
-                self._wait([first])                                   # K1 shading samples last frame's `composed`
-                timed(part=1)
-                self._wait(plan.gathered_planes[1:])                  # K2 samples last frame's dnB history
-                timed(part=2)
-            elif self.overlap and plan.ssgi_mode:
-                self._wait([first])                                   # K1 samples last frame's `composed`
-                timed((0, 1))
-                self._wait(plan.gathered_planes[1:])                  # K2 samples last frame's dnB history
-                timed((1, nl))
-            else:
-                self._wait(plan.gathered_planes)
-                timed((0, nl))
-            self._gather(plan.gathered_planes[:1])                    # `composed` first: the next frame needs it first
-            if len(plan.gathered_planes) > 1:                         # dnB[0..1]: pending under key gathered_planes[1]
-                self._gather(plan.gathered_planes[1:], self.group2)   # (dual_comm: on its own communicator, concurrent with `composed`)
-            if not self.overlap:
-                self._wait(plan.gathered_planes)
-            self._timing.append((self._frame, plan.bounds, spans, self._host_span))
-            self._host_span = None
-            self._frame += 1
+    @property
+    def band_of_last_frame(self) -> tuple:
+        b = (self._C.c_uint32 * (self.world + 1))()
+        self.ctx._chk(self.lib.rfx_group_get_last_bounds(self.g, b))
+        return int(b[self.rank]), int(b[self.rank + 1])
 
     def finish(self):
-        """wait for the outstanding all-gathers (before reading the planes or tearing down)"""
-        with self.torch.cuda.stream(self.stream):
-            self._wait(list(self._pending))
-        self.stream.synchronize()
+        self.ctx.sync()
 
-    # ---- host-buffer path ------------------------------------------------------------------------------------------------
-    # Every rank holds (or maps) the frame's host planes but moves only its share over PCIe: its own rows of depth and velocity -
-    # the two planes sampled anywhere on screen - which are then all-gathered over NVLink (own communicator, so the gather of
-    # frame i+1 is not queued behind frame i's output gathers), and the K1-range rows of the G-buffer and direct light.  H2D,
-    # kernels and D2H run on three streams with two staging sets, like rfx_ssgi_chain_submit_host on one GPU.
-    MAX_SHARE = 4.0  # tallest adaptive band, in units of the mean band height (sizes the read-back staging)
-    INPUTS = (("depth", 4, True), ("gbuffer", 16, False), ("velocity", 16, True), ("direct", 8, False))  # name, bytes/px, gathered
+    # ---- host-buffer path --------------------------------------------------------------------------------------------
+    # Every rank holds (or maps) the frame's host planes but moves only its share over PCIe: its own rows of depth and velocity —
+    # the two input planes sampled anywhere on screen (ray-march taps, reprojected uv), which are then completed from the other
+    # ranks' uploads with one NCCL exchange over NVLink (rfx_group_allgather_rows: the path's one real input exchange) — and the
+    # K1-range rows (+1) of the G-buffer and the direct light.  H2D, kernels and D2H run on three streams with two staging sets,
+    # like rfx_ssgi_chain_submit_host on one GPU.
+    MAX_SHARE = 4.0
 
     def _host_init(self):
-        torch, abi = self.torch, self._abi
+        import torch
+
+        abi = self._abi
         dev = torch.device("cuda", self.ctx.device)
         W, H = self.chain.opt.width, self.chain.opt.height
         fmts = dict(depth=abi.FMT_R32F, gbuffer=abi.FMT_RGBA32F, velocity=abi.FMT_RGBA32F, direct=abi.FMT_RGBA16F)
-        self._in = []
+        h = dict(torch=torch, W=W, H=H, staging=[], frames=0)
         for _ in range(2):
             st = {}
             for name, bpp, _g in self.INPUTS:
                 t = torch.zeros(H * W * bpp, dtype=torch.uint8, device=dev)
-                pl = abi.Plane()
-                pl.ptr, pl.width, pl.height, pl.pitch, pl.format = t.data_ptr(), W, H, W * bpp, fmts[name]
-                st[name] = (t, pl, W * bpp)
-            self._in.append(st)
-        cap = H if self.world == 1 else min(H, int(self.MAX_SHARE * H / self.world) + 16)   # adaptive bands stay below MAX_SHARE x the mean height
-        self._out_dev = [torch.empty(cap * W * 16, dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.up_stream, self.dn_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        self._ev_up = [torch.cuda.Event() for _ in range(2)]
-        self._ev_rendered = [torch.cuda.Event() for _ in range(2)]
-        self._ev_dn = [torch.cuda.Event() for _ in range(2)]
-        self.in_group = self.dist.new_group(ranks=[self._global_rank(r) for r in range(self.world)]) if self.world > 1 else None
-        self._host_frames = 0
+                st[name] = (t, _raw_plane(abi, t.data_ptr(), W, H, W * bpp, fmts[name]), W * bpp)
+            h["staging"].append(st)
+        cap = H if self.world == 1 else min(H, int(self.MAX_SHARE * H / self.world) + 16)
+        h["out_dev"] = [torch.empty(cap * W * 16, dtype=torch.uint8, device=dev) for _ in range(2)]
+        h["up"], h["dn"] = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        h["main"] = torch.cuda.ExternalStream(self.ctx.stream, device=dev)
+        h["ev_up"] = [torch.cuda.Event() for _ in range(2)]
+        h["ev_rendered"] = [torch.cuda.Event() for _ in range(2)]
+        h["ev_dn"] = [torch.cuda.Event() for _ in range(2)]
+        h["bytes"] = (0, 0)
+        self._host = h
 
     def submit_host(self, cam, host: dict, camera_pos, camera_moved: bool, out_host):
         """One frame from host planes (dict name -> CPU tensor of the FULL frame, pinned for asynchronous copies) to this rank's
-        rows of `composed`, written to the start of out_host (CPU float32 tensor of at least rows_per_rank x W x 4; with adaptive
-        bands up to MAX_SHARE x the mean band height).  Returns the row blocks [(r0, r1), ...] the frame's rows belong to, after enqueueing."""
-        torch = self.torch
-        if not hasattr(self, "_in"):
+        rows of `composed`, written to the start of out_host (CPU float32 tensor of at least MAX_SHARE x the mean band height).
+        Returns the band (row0, row1) the rows belong to, after enqueueing."""
+        if self._host is None:
             self._host_init()
-        if self.world > 1:
-            with torch.cuda.stream(self.stream):
-                self._maybe_rebalance()   # before the uploads: they follow this frame's bands
-        plan = self.plan
-        W, H = self.chain.opt.width, self.chain.opt.height
-        k = self._host_frames & 1
-        st = self._in[k]
-        works = []
-        with torch.cuda.stream(self.up_stream):
-            if self._host_frames >= 2:
-                self.up_stream.wait_event(self._ev_rendered[k])   # frame i-2 no longer reads this staging set
-            eu0, eu1 = self._event(), self._event()
-            eu0.record(self.up_stream)
-            for name, bpp, gathered in self.INPUTS:
-                if name not in host or host[name] is None:
+        h = self._host
+        torch, W, H = h["torch"], h["W"], h["H"]
+        bounds = self.begin_frame()
+        b0, b1 = bounds[self.rank], bounds[self.rank + 1]
+        plan = ShardPlan(H, self.world, self.rank, 2 * self.chain.opt.denoise_iterations, self.chain.opt.radius, True, bounds=bounds, width=W)
+        l0, l1 = plan.local_input_rows[0]
+        k = h["frames"] & 1
+        st = h["staging"][k]
+        h2d = 0
+        with torch.cuda.stream(h["up"]):
+            if h["frames"] >= 2:
+                h["up"].wait_event(h["ev_rendered"][k])   # frame i-2 no longer reads this staging set
+            for name, bpp, anywhere in self.INPUTS:
+                if host.get(name) is None:
                     continue
                 t, _pl, pitch = st[name]
-                dev2d, host2d = t.view(H, pitch), host[name].view(torch.uint8).view(H, pitch)
-                for a, b in (plan.blocks if (gathered and self.world > 1) else plan.local_input_rows if self.world > 1 else [(0, H)]):
-                    dev2d[a:b].copy_(host2d[a:b], non_blocking=True)
-            self._ev_up[k].record(self.up_stream)
-            eu1.record(self.up_stream)
-            self._host_span = (eu0, eu1)
-            if self.world > 1:
-                works = self._exchange([(st[n][0], st[n][2]) for n, _b, g in self.INPUTS if g and host.get(n) is not None], self.in_group)
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(self._ev_up[k])
-            for w in works:
-                w.wait()
+                a, b = ((b0, b1) if anywhere else (l0, l1)) if self.world > 1 else (0, H)
+                t.view(H, pitch)[a:b].copy_(host[name].view(torch.uint8).view(H, pitch)[a:b], non_blocking=True)
+                h2d += (b - a) * pitch
+            h["ev_up"][k].record(h["up"])
+        with torch.cuda.stream(h["main"]):
+            h["main"].wait_event(h["ev_up"][k])
+        if self.world > 1:  # complete depth / velocity from the other ranks' uploads (NVLink), ordered on the context stream
+            bnd = (self._C.c_uint32 * (self.world + 1))(*bounds)
+            for name, _bpp, anywhere in self.INPUTS:
+                if anywhere and host.get(name) is not None:
+                    self.ctx._chk(self.lib.rfx_group_allgather_rows(self.g, None, self._C.byref(st[name][1]), bnd))
         pw = lambda n: _PlaneRef(st[n][1]) if host.get(n) is not None else None  # noqa: E731
-        self.render(cam, pw("depth"), pw("gbuffer"), pw("velocity"), pw("direct"), camera_pos, camera_moved, _rebalanced=True)
-        comp, cpitch = self._composed()
-        with torch.cuda.stream(self.stream):
-            # snapshot this rank's rows of `composed`, so the next frame's K4 may overwrite them while the D2H copy still runs
-            nbytes = plan.rows_per_rank * W * 16
-            out2d, off = self._out_dev[k][:nbytes].view(plan.rows_per_rank, W * 16), 0
-            for b0, b1 in plan.blocks:
-                out2d[off:off + (b1 - b0)].copy_(comp.view(H, cpitch)[b0:b1, :W * 16], non_blocking=True)
-                off += b1 - b0
-            self._ev_rendered[k].record(self.stream)
-        with torch.cuda.stream(self.dn_stream):
-            self.dn_stream.wait_event(self._ev_rendered[k])
-            out_host.view(torch.uint8).view(-1)[:nbytes].copy_(self._out_dev[k][:nbytes], non_blocking=True)
-            self._ev_dn[k].record(self.dn_stream)
-        self._host_frames += 1
-        return list(plan.blocks)
+        self.render(cam, pw("depth"), pw("gbuffer"), pw("velocity"), pw("direct"), camera_pos, camera_moved)
+        p = self.chain.output(0)
+        nbytes = (b1 - b0) * W * 16
+        with torch.cuda.stream(h["main"]):
+            h["ev_rendered"][k].record(h["main"])
+        with torch.cuda.stream(h["dn"]):
+            h["dn"].wait_event(h["ev_rendered"][k])
+            # `composed` is double-buffered by frame parity: the plane of frame i is next written by frame i+2, which waits for this
+            # copy through ev_dn (wait_host is called with at most one frame in flight), so the rows go D2H straight from the plane
+            self.ctx._chk(self.lib.rfx_plane_download_rows(self.ctx.h, h["dn"].cuda_stream, self._C.byref(p), out_host.data_ptr(), b0, b1))
+            h["ev_dn"][k].record(h["dn"])
+        h["frames"] += 1
+        h["bytes"] = (h2d, nbytes)
+        return b0, b1
 
     def wait_host(self, max_in_flight: int = 0):
-        """Blocks until at most max_in_flight (0 or 1) submitted frames are incomplete (their out_host rows not yet written)."""
-        n = getattr(self, "_host_frames", 0)
-        if n == 0:
+        h = self._host
+        if not h or h["frames"] == 0:
             return
+        n = h["frames"]
         if max_in_flight <= 0:
-            self._ev_dn[(n - 1) & 1].synchronize()
+            h["ev_dn"][(n - 1) & 1].synchronize()
         elif n >= 2:
-            self._ev_dn[(n - 2) & 1].synchronize()
-
-    def _composed(self):
-        if 0 in self._tensors:
-            return self._tensors[0]
-        p = self.chain.output(0)
-        t = self.torch.as_tensor(_CudaBytes(p.ptr, int(p.pitch) * int(p.height)), device=self.torch.device("cuda", self.ctx.device))
-        self._tensors[0] = (t, int(p.pitch))
-        return self._tensors[0]
-
-    def _all_gather(self, todo, group):
-        """in-place all-gathers [(out, own)] as one coalesced NCCL group when the private coalescing API is usable"""
-        if not todo:
-            return []
-        cm_fn = getattr(self.dist, "_coalescing_manager", None)
-        if self.coalesce and cm_fn is not None:
-            try:
-                with cm_fn(group=group, device=self.torch.device("cuda", self.ctx.device), async_ops=True) as cm:
-                    for out, own in todo:
-                        self.dist.all_gather_into_tensor(out, own, group=group)
-                return [cm]
-            except Exception:
-                self.coalesce = False
-        return [self.dist.all_gather_into_tensor(out, own, group=group, async_op=True) for out, own in todo]
+            h["ev_dn"][(n - 2) & 1].synchronize()
 
     @property
     def host_bytes_per_frame(self):
-        """(H2D, D2H) bytes this rank moves per frame on the host path"""
-        W = self.chain.opt.width
-        own = self.plan.rows_per_rank if self.world > 1 else self.chain.opt.height
-        loc = sum(b - a for a, b in self.plan.local_input_rows) if self.world > 1 else self.chain.opt.height
-        h2d = sum((own if g else loc) * W * bpp for _n, bpp, g in self.INPUTS)
-        return h2d, own * W * 16
-
-    @property
-    def exchange_bytes_per_frame(self) -> int:
-        """bytes this rank RECEIVES per frame"""
-        H = self.chain.opt.height
-        return sum((H - self.plan.rows_per_rank) * pitch for _t, pitch in self._tensors.values())
+        """(H2D, D2H) bytes this rank moved for the last submitted frame"""
+        return self._host["bytes"] if self._host else (0, 0)
 
     def close(self):
-        if self.world > 1:
-            self.finish()
+        self.ctx.sync()
+        if self.g:
+            self.lib.rfx_group_destroy(self.g)
+            self.g = None
         self.chain.close()

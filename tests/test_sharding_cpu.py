@@ -197,3 +197,72 @@ def test_rebalance_moves_borders_towards_equal_cost():
     assert rebalance((0, 1024, 2048), [1e-12, 5.0], min_rows=64, damping=1.0)[1] <= 2048 - 64
     with pytest.raises(ValueError):
         ShardPlan(128, 2, 0, 2, 3.0, True, bounds=(0, 64, 100))
+
+
+def test_rebalance_caps_every_band_including_the_last():
+    """Cost concentrated in the lower rows (cheap sky on top = the LAST band): no band, the last one included, may exceed
+    max_share x the mean height — the host path sizes its read-back staging by that bound."""
+    from realism_effects_b200.parallel import rebalance
+
+    H, n = 2160, 8
+    rows = np.where(np.arange(H) < 0.35 * H, 10.0, 0.01)
+    cost = lambda b: [float(rows[b[i]:b[i + 1]].sum()) for i in range(n)]  # noqa: E731
+    b = tuple(H * i // n // 16 * 16 for i in range(n)) + (H,)
+    cap = int(4.0 * H / n)
+    for share in (4.0, 1.5):
+        bb = b
+        for _ in range(40):
+            bb = rebalance(bb, cost(bb), max_share=share)
+            assert all(bb[i + 1] - bb[i] <= max(64, int(share * H / n)) for i in range(n)), (share, bb)
+            assert bb[0] == 0 and bb[-1] == H and all(bb[i + 1] - bb[i] >= 64 for i in range(n))
+    assert cap == 1080
+
+
+def test_portrait_frames_reach_further_in_rows():
+    """The Poisson offset is rotated after the division by the resolution, so for H > W a tap reaches radius * H / W rows."""
+    assert ShardPlan(960, 2, 0, 2, 3.0, True, bounds=(0, 480, 960), width=540).poisson_halo == 7   # ceil(3 * 960 / 540) + 1
+    assert ShardPlan(540, 2, 0, 2, 3.0, True, bounds=(0, 272, 540), width=960).poisson_halo == 4   # landscape: unchanged
+    # brute force over the tap geometry of poisson_denoise.frag:177-189 (flatness = 1, any rotation)
+    W, H, radius = 540, 960, 3.0
+    SQ = 2 ** 0.5
+    taps = [(-1, 0), (0, -1), (1, 0), (0, 1), (-.25 * SQ, -.25 * SQ), (.25 * SQ, -.25 * SQ), (.25 * SQ, .25 * SQ), (-.25 * SQ, .25 * SQ)]
+    reach = 0.0
+    for ang in np.linspace(0, 2 * np.pi, 721):
+        s_, c_ = np.sin(ang), np.cos(ang)
+        for px, py in taps:
+            ox, oy = radius * px / W, radius * py / H
+            reach = max(reach, abs((-s_ * ox + c_ * oy) * H))
+    assert 5.0 < reach <= ShardPlan(H, 2, 0, 2, radius, True, bounds=(0, 480, 960), width=W).poisson_halo - 1
+
+
+def test_native_shard_arithmetic_matches_the_python_mirror(built):
+    """rfx_shard_ranges / rfx_shard_rebalance (csrc/rfx_group.inl, what the product path uses) == ShardPlan / rebalance."""
+    import ctypes as C
+
+    from realism_effects_b200.parallel import rebalance
+
+    lib = abi.lib()
+    rng = np.random.default_rng(7)
+    for W, H, world, passes, radius, ssgi in ((3840, 2160, 8, 4, 3.0, True), (540, 960, 2, 2, 3.0, True), (7680, 4320, 8, 4, 11.0, True),
+                                              (256, 128, 2, 0, 3.0, True), (640, 360, 4, 2, 2.5, False)):
+        bounds = tuple(int(round(H * i / world / 16.0)) * 16 for i in range(world)) + (H,)
+        for rank in range(world):
+            p = ShardPlan(H, world, rank, passes, radius, ssgi, bounds=bounds, width=W)
+            n = p.n_launches
+            out = (C.c_uint32 * (2 * n))()
+            assert lib.rfx_shard_ranges(W, H, p.r0, p.r1, passes, radius, int(ssgi), out, n) == 0
+            assert [(out[2 * k], out[2 * k + 1]) for k in range(n)] == p.ranges, (W, H, rank)
+        b = bounds
+        for _ in range(6):
+            costs = [float(x) for x in rng.uniform(0.2, 3.0, world)]
+            cb = (C.c_uint32 * (world + 1))(*b)
+            cc = (C.c_float * world)(*costs)
+            co = (C.c_uint32 * (world + 1))()
+            assert lib.rfx_shard_rebalance(cb, None, cc, world, co) == 0
+            costs32 = [float(np.float32(c)) for c in costs]
+            want = rebalance(b, costs32) if H >= world * 64 else None
+            if want is not None:
+                assert tuple(co) == want, (b, costs, tuple(co), want)
+                b = want
+    assert lib.rfx_shard_ranges(64, 64, 10, 10, 2, 3.0, 1, (C.c_uint32 * 10)(), 5) != 0     # empty band
+    assert lib.rfx_shard_ranges(64, 64, 0, 32, 2, 3.0, 1, (C.c_uint32 * 10)(), 4) != 0      # wrong launch count
