@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RFX_VERSION 1
+#define RFX_VERSION 2
 
 typedef enum rfx_status {
   RFX_OK = 0,
@@ -259,10 +259,12 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
                                       const rfx_plane* out0, const rfx_plane* out1,
                                       uint32_t row0, uint32_t row1);
 
-/* K4. diffuse/specular: RGBA16F Poisson targets; out: RGBA32F. */
+/* K4. diffuse_gi / specular_gi: RGBA16F Poisson targets; out: RGBA32F.  input_type selects the bindings of
+ * DenoiserComposePass.js:23-33: DIFFUSE_SPECULAR both, DIFFUSE only diffuse_gi, SPECULAR (SSR) only specular_gi plus
+ * `scene` = the composer input buffer (RGBA16F, sampled LINEAR; src/denoise/Denoiser.js:100-102); unbound ones are NULL. */
 rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_params* p,
                                  const rfx_plane* depth, const rfx_plane* gbuffer,
-                                 const rfx_plane* diffuse_gi, const rfx_plane* specular_gi,
+                                 const rfx_plane* diffuse_gi, const rfx_plane* specular_gi, const rfx_plane* scene,
                                  const rfx_plane* out, uint32_t row0, uint32_t row1);
 
 /* K5. src/ssgi/shader/ssgi_compose.frag:20-44 (no fog). gi RGBA32F, scene RGBA16F, out RGBA16F */
@@ -325,7 +327,7 @@ rfx_status rfx_ssgi_chain_reset(rfx_ssgi_chain* chain);
 rfx_status rfx_ssgi_chain_set_options(rfx_ssgi_chain* chain, const rfx_ssgi_chain_options* opt);
 rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
 /* Row-block sharded frame: ranges[2k], ranges[2k+1] = output rows [a,b) of launch k in chain order
- * (K1, K2, K3 pass 0..2*denoiseIterations-1, K4 when mode == SSGI).  The caller (realism_effects_b200/parallel.py) sizes
+ * (K1, K2, K3 pass 0..2*denoiseIterations-1, K4).  The caller (realism_effects_b200/parallel.py) sizes
  * the ranges so that every pass finds valid halo rows produced locally by the previous pass, then all-gathers the
  * produced-then-gathered planes (composed, dnB[0..1]) across ranks.  Results are bit-identical to rfx_ssgi_chain_render. */
 rfx_status rfx_ssgi_chain_render_ranges(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame, const uint32_t* ranges,
@@ -400,7 +402,7 @@ rfx_status rfx_group_allgather_rows(rfx_group* group, void* stream, const rfx_pl
 /* collective: one frame; this rank renders its band from full-frame input planes and joins the frame's collective on `stream` */
 rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* chain, void* stream, const rfx_ssgi_frame* frame);
 /* pure host arithmetic, exported for hosts that drive the per-launch ranges themselves (and for the CPU tests):
- * rows [ranges[2k], ranges[2k+1]) of launch k (K1, K2, K3 pass 0.., K4 in SSGI mode) for the band [own0, own1) */
+ * rows [ranges[2k], ranges[2k+1]) of launch k (K1, K2, K3 pass 0.., K4) for the band [own0, own1); n_launches = 3 + n_poisson_passes */
 rfx_status rfx_shard_ranges(uint32_t width, uint32_t height, uint32_t own0, uint32_t own1, int32_t n_poisson_passes, float radius,
                             int32_t ssgi_mode, uint32_t* ranges, uint32_t n_launches);
 rfx_status rfx_shard_rebalance(const uint32_t* bounds, const uint32_t* measured_bounds, const float* costs, int32_t n, uint32_t* out);

@@ -1,43 +1,91 @@
 // js/index.js — the reference's plugin surface (src/index.js:16-31) over the N-API shim (js/napi/shim.cc).
 //
-// NOT RUNNABLE IN THIS IMAGE (no Node, no GL; SURVEY.md D5) — this is the reference-side glue a maintainer would
-// add to drop the CUDA engine under a postprocessing.js EffectComposer: same class names, constructor signatures,
-// option names/defaults and update/setSize/reset/dispose methods as the reference.  The tested host mirror of the
-// same surface is realism_effects_b200/effects.py.
+// NOT RUNNABLE IN THIS IMAGE (no Node, no GL; SURVEY.md D5) — this is the reference-side glue a maintainer adds to drop the
+// CUDA engine under a postprocessing.js EffectComposer: the reference's eight classes with its constructor signatures, option
+// names / defaults, reactive option properties and `update(renderer, inputBuffer, deltaTime)` / `render(renderer)` /
+// `setSize` / `initialize` / `reset` / `dispose` methods.  The tested host mirror of the same surface is
+// realism_effects_b200/effects.py (each method there ends in the same rfx_* entry point this file reaches through the shim).
 //
-// Plane transport in this first binding is host memory: the G-buffer / velocity / scene-colour render targets are
-// read back (renderer.readRenderTargetPixels) into typed arrays and passed to rfx_ssgi_chain_render_host, which
-// uploads, renders and downloads `composed`.  The zero-copy path (cudaGraphicsGLRegisterImage on the WebGL
-// textures) is SURVEY.md §8(f) row 4.
+// Plane transport: three.js keeps rasterising the G-buffer / velocity / scene-colour render targets (SURVEY.md K10/K11: out of
+// scope as compute).  A `PlaneSource` turns them into device planes for the engine; the default one reads the render targets
+// back (renderer.readRenderTargetPixels -> typed arrays -> rfx.planeUpload).  The zero-copy variant (cudaGraphicsGLRegisterImage
+// on the WebGL textures) is SURVEY.md §8(f) row 4 and replaces only this class.
 import { createRequire } from "node:module"
 const rfx = createRequire(import.meta.url)("./napi/rfx_napi.node")
+
+const FMT = { R32F: 0, RGBA32F: 1, RGBA16F: 2, RGBA8: 3 }
+const FLAG = { importanceSampling: 1, missedRays: 2, useDirectLight: 4, useEnvMap: 8 }
+const INPUT = { diffuseSpecular: 0, diffuse: 1, specular: 2 }
+let sharedCtx = null
+export const context = (device = 0) => (sharedCtx ??= rfx.ctxCreate(device))
+
+const f32 = m => new Float32Array(m.elements ?? m)
+const cameraBlock = camera => ({
+	projection: f32(camera.projectionMatrix), projectionInverse: f32(camera.projectionMatrixInverse),
+	matrixWorld: f32(camera.matrixWorld), matrixWorldInverse: f32(camera.matrixWorldInverse), near: camera.near, far: camera.far,
+	perspective: camera.isPerspectiveCamera !== false
+})
+// src/utils/SceneUtils.js:17-27
+const didCameraMove = (camera, lastPos, lastQuat) =>
+	!lastPos || camera.position.distanceToSquared(lastPos) > 1e-6 || 8 * (1 - lastQuat.dot(camera.quaternion)) > 1e-6
+
+// src/utils/BlueNoiseUtils.js:17-33 — one closure per material; the index advances on every uniform READ
+class BlueNoiseIndex {
+	constructor(start = Math.floor(Math.random() * 65536)) { this.start = start; this.index = 0 }
+	get value() { this.index = (this.start + this.index + 1) % 0x7fffffff; return this.index }
+}
+
+const reactive = (self, options, onChange) => {
+	for (const key of Object.keys(options)) {
+		Object.defineProperty(self, key, {
+			get: () => options[key],
+			set: value => { if (options[key] === value) return; options[key] = value; onChange(key, value) },
+			configurable: true
+		})
+	}
+}
+
+// Default PlaneSource: read the three.js render targets back and upload them.  planes: { depth, gbuffer, velocity, directLight }
+export class ReadbackPlaneSource {
+	constructor(ctx, width, height) { this.ctx = ctx; this.resize(width, height) }
+	resize(width, height) {
+		this.dispose()
+		this.width = width; this.height = height
+		const n = width * height
+		this.host = { depth: new Float32Array(n), gbuffer: new Float32Array(4 * n), velocity: new Float32Array(4 * n), directLight: new Uint16Array(4 * n) }
+		this.dev = { depth: rfx.planeAlloc(this.ctx, FMT.R32F, width, height), gbuffer: rfx.planeAlloc(this.ctx, FMT.RGBA32F, width, height),
+			velocity: rfx.planeAlloc(this.ctx, FMT.RGBA32F, width, height), directLight: rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height) }
+	}
+	// targets: { depth: WebGLRenderTarget (R32F copy of the depth texture), gbuffer, velocity, directLight }
+	read(renderer, targets) {
+		for (const k of Object.keys(this.dev)) {
+			if (!targets[k]) continue
+			renderer.readRenderTargetPixels(targets[k], 0, 0, this.width, this.height, this.host[k])
+			rfx.planeUpload(this.ctx, this.dev[k], this.host[k])
+		}
+		return this.dev
+	}
+	dispose() { if (this.dev) for (const p of Object.values(this.dev)) rfx.planeFree(this.ctx, p); this.dev = null }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------
+export class VelocityDepthNormalPass {
+	// new VelocityDepthNormalPass(scene, camera) — src/temporal-reproject/pass/VelocityDepthNormalPass.js:71-91.
+	// Rasterisation stays in three.js (`rasterPass`: the reference's own pass object); this wrapper exposes what others read.
+	constructor(scene, camera, rasterPass) { this._scene = scene; this._camera = camera; this.rasterPass = rasterPass; this.needsSwap = false }
+	get texture() { return this.rasterPass.texture }
+	get renderTarget() { return this.rasterPass.renderTarget }
+	get lastVelocityTexture() { return this.rasterPass.lastVelocityTexture }
+	setSize(w, h) { this.rasterPass.setSize(w, h) }
+	render(renderer) { this.rasterPass.render(renderer) }
+	dispose() { this.rasterPass.dispose() }
+}
 
 // src/ssgi/SSGIOptions.js:26-48
 export const defaultSSGIOptions = {
 	mode: "ssgi", distance: 10, thickness: 10, denoiseIterations: 1, denoiseKernel: 2, denoiseDiffuse: 10, denoiseSpecular: 10,
 	radius: 3, phi: 0.5, lumaPhi: 5, depthPhi: 2, normalPhi: 50, roughnessPhi: 50, specularPhi: 50, envBlur: 0.5,
 	importanceSampling: true, steps: 20, refineSteps: 5, resolutionScale: 1, missedRays: false, outputTexture: null
-}
-
-const FLAG = { importanceSampling: 1, missedRays: 2, useDirectLight: 4, useEnvMap: 8 }
-let sharedCtx = null
-const context = (device = 0) => (sharedCtx ??= rfx.ctxCreate(device))
-
-const f32 = m => new Float32Array(m.elements ?? m)
-const cameraBlock = camera => ({
-	projection: f32(camera.projectionMatrix), projectionInverse: f32(camera.projectionMatrixInverse),
-	matrixWorld: f32(camera.matrixWorld), matrixWorldInverse: f32(camera.matrixWorldInverse), near: camera.near, far: camera.far
-})
-
-export class VelocityDepthNormalPass {
-	// new VelocityDepthNormalPass(scene, camera) — src/temporal-reproject/pass/VelocityDepthNormalPass.js:71-91.
-	// Rasterisation stays in three.js; this wrapper only exposes the planes the CUDA engine consumes.
-	constructor(scene, camera, rasterPass) { this._scene = scene; this._camera = camera; this.rasterPass = rasterPass; this.needsSwap = false }
-	get texture() { return this.rasterPass.texture }
-	get renderTarget() { return this.rasterPass.renderTarget }
-	setSize(w, h) { this.rasterPass.setSize(w, h) }
-	render(renderer) { this.rasterPass.render(renderer) }
-	dispose() { this.rasterPass.dispose() }
 }
 
 export class SSGIEffect {
@@ -48,38 +96,58 @@ export class SSGIEffect {
 		this._options = opts
 		this.ctx = context(options.device ?? 0)
 		this.velocityDepthNormalPass = options.velocityDepthNormalPass
-		this.lastCamera = null
-		for (const key of Object.keys(opts)) {
-			Object.defineProperty(this, key, {
-				get: () => opts[key],
-				set: value => { if (opts[key] === value) return; opts[key] = value; this._rebuild() }   // setters end with reset()
-			})
-		}
-		this.setSize(options.width, options.height)
+		this.gBufferPass = options.gBufferPass                       // three.js GBufferPass: { texture, depthTexture, renderTarget }
+		this.isUsingRenderPass = true
+		this._hasEnv = false
+		this.lastPos = null; this.lastQuat = null
+		reactive(this, opts, key => (key === "resolutionScale" ? this.setSize(this.width, this.height, true) : this._setOptions()))
+		this.setSize(options.width ?? composer?.inputBuffer?.width, options.height ?? composer?.inputBuffer?.height)
 	}
 	_flags() {
 		const o = this._options
 		return (o.importanceSampling && this._hasEnv ? FLAG.importanceSampling : 0) | (o.missedRays ? FLAG.missedRays : 0) |
-			FLAG.useDirectLight | (this._hasEnv ? FLAG.useEnvMap : 0)
+			(this.isUsingRenderPass ? FLAG.useDirectLight : 0) | (this._hasEnv ? FLAG.useEnvMap : 0)
 	}
-	_rebuild() {
+	_chainOptions() { return { ...this._options, width: this.width, height: this.height, flags: this._flags(), mode: this._options.mode === "ssr" ? 1 : 0 } }
+	_setOptions() { if (this.chain) rfx.chainSetOptions(this.ctx, this.chain, this._chainOptions()) }   // setters end with reset() (SSGIEffect.js:203-209)
+	setSize(width, height, force = false) {
+		if (width === undefined || (!force && width === this.width && height === this.height)) return
+		if (this._options.resolutionScale !== 1) throw new Error("resolutionScale != 1 is not supported by the CUDA engine")
+		this.width = width; this.height = height
 		if (this.chain) rfx.chainDestroy(this.chain)
-		this.chain = rfx.chainCreate(this.ctx, { ...this._options, width: this.width, height: this.height, flags: this._flags(), mode: this._options.mode === "ssr" ? 1 : 0 })
-		this.out = new Float32Array(this.width * this.height * 4)
+		this.chain = rfx.chainCreate(this.ctx, this._chainOptions())
+		this.planeSource?.dispose()
+		this.planeSource = new ReadbackPlaneSource(this.ctx, width, height)
+		this.outputPlane = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)
+		this.outputHost = new Uint16Array(width * height * 4)
 	}
-	setSize(width, height) { if (width === undefined || (width === this.width && height === this.height)) return; this.width = width; this.height = height; this._rebuild() }
+	// keepEnvMapUpdated (src/ssgi/SSGIEffect.js:309-366): equirect RGBA16F map; the CDF tables are built on the device
+	setEnvironment(mapF16, width, height) { rfx.envBuild(this.ctx, mapF16, width, height); this._hasEnv = true; this._setOptions() }
+	clearEnvironment() { rfx.envClear(this.ctx); this._hasEnv = false; this._setOptions() }
+	initialize() {}
 	reset() { rfx.chainReset(this.chain) }
-	get outputTexture() { return this.out }
-	// update(renderer, inputBuffer) — src/ssgi/SSGIEffect.js:372-404.  `planes` = typed arrays read back from the
-	// GBufferPass / VelocityDepthNormalPass / input-buffer render targets by the caller's glue.
-	update(renderer, inputBuffer, deltaTime, planes) {
+	get depthTexture() { return this.gBufferPass?.depthTexture }
+	get outputTexture() { return this.outputHost }      // K5 output (RGBA16F), uploaded into the composer's output buffer by the glue
+	// update(renderer, inputBuffer, deltaTime) — src/ssgi/SSGIEffect.js:372-404
+	update(renderer, inputBuffer, deltaTime) {
 		const cam = cameraBlock(this._camera)
-		const moved = !this.lastCamera || cam.matrixWorld.some((v, i) => Math.abs(v - this.lastCamera[i]) > 1e-6)
-		this.lastCamera = cam.matrixWorld
-		rfx.chainRenderHost(this.ctx, this.chain, cam, planes.depth, planes.gbuffer, planes.velocity, planes.directLight ?? null,
-			new Float32Array(this._camera.position.toArray()), moved, this.out)
+		const moved = didCameraMove(this._camera, this.lastPos, this.lastQuat)
+		this.lastPos = this._camera.position.clone(); this.lastQuat = this._camera.quaternion.clone()
+		this.velocityDepthNormalPass?.render(renderer)
+		const planes = this.planeSource.read(renderer, { depth: this.gBufferPass?.depthRenderTarget, gbuffer: this.gBufferPass?.renderTarget,
+			velocity: this.velocityDepthNormalPass?.renderTarget, directLight: inputBuffer })
+		rfx.chainRender(this.ctx, this.chain, cam, planes.depth, planes.gbuffer, planes.velocity, this.isUsingRenderPass ? planes.directLight : null,
+			new Float32Array(this._camera.position.toArray()), moved)
+		// K5: ssgi_compose.frag (mainImage of the effect)
+		rfx.ssgiCompose(this.ctx, planes.depth, rfx.chainOutput(this.ctx, this.chain, 0), planes.directLight, this.outputPlane)
+		rfx.planeDownload(this.ctx, this.outputPlane, this.outputHost)
 	}
-	dispose() { if (this.chain) rfx.chainDestroy(this.chain); this.chain = null }
+	dispose() {
+		if (this.chain) rfx.chainDestroy(this.chain)
+		this.chain = null
+		this.planeSource?.dispose()
+		if (this.outputPlane) rfx.planeFree(this.ctx, this.outputPlane)
+	}
 }
 SSGIEffect.DefaultOptions = defaultSSGIOptions
 
@@ -88,6 +156,227 @@ export class SSREffect extends SSGIEffect {
 	constructor(composer, scene, camera, options = {}) { super(composer, scene, camera, { ...options, mode: "ssr" }) }
 }
 
-// TRAAEffect / MotionBlurEffect / HBAOEffect / TemporalReprojectPass / PoissonDenoisePass bind the per-pass entry points
-// (rfx_temporal_reproject_launch, rfx_motion_blur_launch, rfx_hbao_launch, rfx_ao_compose_launch,
-// rfx_poisson_denoise_launch) the same way; their tested host mirror is realism_effects_b200/effects.py.
+// -------------------------------------------------------------------------------------------------------------------------
+// src/temporal-reproject/TemporalReprojectPass.js:17-32
+export const defaultTemporalReprojectPassOptions = {
+	dilation: false, fullAccumulate: false, neighborhoodClamp: false, neighborhoodClampRadius: 1, neighborhoodClampIntensity: 1, maxBlend: 1,
+	logTransform: false, depthDistance: 2, worldDistance: 4, reprojectSpecular: false, renderTarget: null, copyTextures: true,
+	confidencePower: 0.125, inputType: "diffuse"
+}
+
+// src/temporal-reproject/utils/QuasirandomGenerator.js:11-24, src/taa/TAAUtils.js:3-11
+export const generateR2 = count => {
+	const g = 1.32471795724474602596090885447809, a1 = 1.0 / g, a2 = 1.0 / (g * g), base = 1.1127756842787055
+	return Array.from({ length: count }, (_, n) => [(base + a1 * n) % 1, (base + a2 * n) % 1])
+}
+export const r2Sequence = generateR2(256).map(([a, b]) => [a - 0.5, b - 0.5])
+export function jitter(width, height, camera, frame, jitterScale = 1) {
+	const [x, y] = r2Sequence[frame % r2Sequence.length]
+	if (camera.setViewOffset) camera.setViewOffset(width, height, x * jitterScale, y * jitterScale, width, height)
+}
+
+export class TemporalReprojectPass {
+	// new TemporalReprojectPass(scene, camera, velocityDepthNormalPass, texture, textureCount, options) — TemporalReprojectPass.js:38-225
+	// (stand-alone 1-plane RGBA16F form, as TRAAEffect uses it; the 2-plane SSGI form runs inside the native chain)
+	constructor(scene, camera, velocityDepthNormalPass, texture, textureCount = 1, options = defaultTemporalReprojectPassOptions) {
+		if (textureCount !== 1) throw new Error("stand-alone TemporalReprojectPass: textureCount must be 1")
+		this._scene = scene; this._camera = camera; this.velocityDepthNormalPass = velocityDepthNormalPass
+		this.inputTexture = texture; this.textureCount = textureCount
+		this.options = { ...defaultTemporalReprojectPassOptions, ...options }
+		this.ctx = context(); this.needsSwap = false; this.frame = 0; this.keepData = 1; this.prev = null
+		this.lastPos = null; this.lastQuat = null
+	}
+	setSize(width, height) {
+		this.dispose()
+		this.width = width; this.height = height
+		this.renderTarget = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)
+		this.framebufferTexture = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)   // copyFramebufferToTexture history (:197-200)
+		this.inputPlane = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)
+		this.velocityPlane = rfx.planeAlloc(this.ctx, FMT.RGBA32F, width, height)
+		this.hostIn = new Uint16Array(4 * width * height); this.hostVel = new Float32Array(4 * width * height)
+	}
+	get texture() { return this.renderTarget }   // renderTarget.texture[0]: the plane the most recent render() wrote (:150-156)
+	reset() { this.keepData = 0 }
+	jitter(jitterScale = 1) { this.unjitter(); jitter(this.width, this.height, this._camera, this.frame, jitterScale) }
+	unjitter() { if (this._camera.clearViewOffset) this._camera.clearViewOffset() }
+	render(renderer) {
+		this.frame = (this.frame + 1) % 4096
+		// the pass uploads the UN-jittered projection (:168-186)
+		const proj = this._camera.projectionMatrix.clone(), projInv = this._camera.projectionMatrixInverse.clone()
+		if (this._camera.view) this._camera.view.enabled = false
+		this._camera.updateProjectionMatrix()
+		const cam = cameraBlock(this._camera)
+		if (this._camera.view) this._camera.view.enabled = true
+		this._camera.projectionMatrix.copy(proj); this._camera.projectionMatrixInverse.copy(projInv)
+		const prev = this.prev ?? cam
+		const full = this.options.fullAccumulate && !didCameraMove(this._camera, this.lastPos, this.lastQuat)
+		this.lastPos = this._camera.position.clone(); this.lastQuat = this._camera.quaternion.clone()
+		renderer.readRenderTargetPixels(this.inputTexture, 0, 0, this.width, this.height, this.hostIn)
+		renderer.readRenderTargetPixels(this.velocityDepthNormalPass.renderTarget, 0, 0, this.width, this.height, this.hostVel)
+		rfx.planeUpload(this.ctx, this.inputPlane, this.hostIn); rfx.planeUpload(this.ctx, this.velocityPlane, this.hostVel)
+		;[this.renderTarget, this.framebufferTexture] = [this.framebufferTexture, this.renderTarget]   // the last result becomes the history
+		rfx.temporalReproject(this.ctx, {
+			cam, prev, cameraPos: new Float32Array(this._camera.position.toArray()), maxBlend: this.options.maxBlend,
+			neighborhoodClampIntensity: this.options.neighborhoodClampIntensity, keepData: this.keepData, confidencePower: this.options.confidencePower,
+			fullAccumulate: full, textureCount: 1, inputType: INPUT[this.options.inputType] ?? INPUT.diffuse, logTransform: !!this.options.logTransform,
+			reprojectSpecular: [0, 0], historyLinear: true
+		}, this.inputPlane, this.velocityPlane, this.framebufferTexture, null, this.renderTarget, null)
+		this.keepData = 1
+		this.prev = cam
+	}
+	dispose() { for (const k of ["renderTarget", "framebufferTexture", "inputPlane", "velocityPlane"]) if (this[k]) { rfx.planeFree(this.ctx, this[k]); this[k] = null } }
+}
+
+export class TRAAEffect {
+	// new TRAAEffect(scene, camera, velocityDepthNormalPass, options) — src/traa/TRAAEffect.js:10-76
+	constructor(scene, camera, velocityDepthNormalPass, options = defaultTemporalReprojectPassOptions) {
+		this._scene = scene; this._camera = camera; this.velocityDepthNormalPass = velocityDepthNormalPass
+		this.options = { ...defaultTemporalReprojectPassOptions, ...options,
+			maxBlend: 0.9, neighborhoodClamp: true, neighborhoodClampIntensity: 1, neighborhoodClampRadius: 1, logTransform: true, confidencePower: 4 }   // :21-31
+		this.setSize(options.width, options.height)
+	}
+	setSize(width, height) { this.temporalReprojectPass?.setSize(width, height) }
+	reset() { this.temporalReprojectPass.reset() }
+	update(renderer, inputBuffer) {
+		if (!this.temporalReprojectPass) {
+			this.temporalReprojectPass = new TemporalReprojectPass(this._scene, this._camera, this.velocityDepthNormalPass, inputBuffer, 1, this.options)
+			this.temporalReprojectPass.setSize(inputBuffer.width, inputBuffer.height)
+			this.outputPlane = rfx.planeAlloc(context(), FMT.RGBA16F, inputBuffer.width, inputBuffer.height)
+			this.outputHost = new Uint16Array(4 * inputBuffer.width * inputBuffer.height)
+		}
+		const trp = this.temporalReprojectPass
+		trp.inputTexture = inputBuffer
+		trp.unjitter()                                                        // :67-72
+		this.unjitteredProjectionMatrix = this._camera.projectionMatrix.clone()
+		this._camera.projectionMatrix.copy(this.unjitteredProjectionMatrix)
+		trp.jitter()
+		trp.render(renderer)
+		rfx.traaCompose(trp.ctx, trp.texture, this.outputPlane)               // traa_compose.frag:3-6
+		rfx.planeDownload(trp.ctx, this.outputPlane, this.outputHost)
+	}
+	get outputTexture() { return this.outputHost }
+	dispose() { this.temporalReprojectPass?.dispose(); if (this.outputPlane) rfx.planeFree(context(), this.outputPlane) }
+}
+TRAAEffect.DefaultOptions = defaultTemporalReprojectPassOptions
+
+// -------------------------------------------------------------------------------------------------------------------------
+// src/denoise/pass/PoissonDenoisePass.js:16-24
+export const defaultPoissonBlurOptions = { iterations: 1, radius: 3, phi: 0.5, lumaPhi: 5, depthPhi: 2, normalPhi: 3.25, inputType: "diffuseSpecular" }
+
+export class PoissonDenoisePass {
+	// new PoissonDenoisePass(camera, textures, options) — src/denoise/pass/PoissonDenoisePass.js:26-150 (device planes in, device planes out)
+	constructor(camera, textures, options = defaultPoissonBlurOptions) {
+		this._camera = camera
+		this.textures = Array.isArray(textures) ? textures : [textures]
+		this.options = { ...defaultPoissonBlurOptions, roughnessPhi: 0, specularPhi: 0, ...options }
+		this.ctx = context(); this.iterations = this.options.iterations; this.index = new BlueNoiseIndex(options.blueNoiseStart)
+		reactive(this, { radius: this.options.radius, phi: this.options.phi, lumaPhi: this.options.lumaPhi, depthPhi: this.options.depthPhi,
+			normalPhi: this.options.normalPhi, roughnessPhi: this.options.roughnessPhi, specularPhi: this.options.specularPhi }, () => {})
+	}
+	setGBufferPass(pass) { this.gbufferPlane = pass.texture; this.depthPlane = pass.depthTexture ?? this.depthPlane; this.gbufferTexture = !!pass.isGBufferPass }
+	setSize(width, height) {
+		this.dispose()
+		const n = this.textures.length
+		this.renderTargetA = Array.from({ length: n }, () => rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height))
+		this.renderTargetB = Array.from({ length: n }, () => rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height))
+	}
+	get texture() { return this.renderTargetB }
+	render() {   // :135-149 — 2 * iterations ping-pong passes
+		const n = this.textures.length
+		for (let i = 0; i < 2 * this.iterations; i++) {
+			const horizontal = i % 2 === 0
+			const src = i === 0 ? this.textures : horizontal ? this.renderTargetB : this.renderTargetA
+			const dst = horizontal ? this.renderTargetA : this.renderTargetB
+			rfx.poissonDenoise(this.ctx, { radius: this.radius, phi: this.phi, lumaPhi: this.lumaPhi, depthPhi: this.depthPhi, normalPhi: this.normalPhi,
+				roughnessPhi: this.roughnessPhi, specularPhi: this.specularPhi, textureCount: n, isTextureSpecular: [n === 2 ? 0 : 0, n === 2 ? 1 : 0],
+				gbufferTexture: this.gbufferTexture, inputLinear: i > 0 || !!this.options.inputLinear, blueNoiseIndex: this.index.value },
+			this.depthPlane, this.gbufferPlane, src[0], src[1] ?? null, dst[0], dst[1] ?? null)
+		}
+	}
+	dispose() { for (const t of [...(this.renderTargetA ?? []), ...(this.renderTargetB ?? [])]) rfx.planeFree(this.ctx, t); this.renderTargetA = this.renderTargetB = null }
+}
+PoissonDenoisePass.DefaultOptions = defaultPoissonBlurOptions
+
+// -------------------------------------------------------------------------------------------------------------------------
+// src/ao/AOEffect.js:8-21
+export const defaultAOOptions = { resolutionScale: 1, spp: 8, distance: 2, distancePower: 1, power: 2, bias: 40, thickness: 0.075, color: [0, 0, 0],
+	useNormalPass: false, velocityDepthNormalPass: null, normalTexture: null, ...defaultPoissonBlurOptions }
+
+export class HBAOEffect {
+	// new HBAOEffect(composer, camera, scene, options) — src/hbao/HBAOEffect.js:5-20 + src/ao/AOEffect.js:23-178
+	constructor(composer, camera, scene, options = defaultAOOptions) {
+		this.composer = composer; this._camera = camera; this._scene = scene
+		const opts = { ...defaultAOOptions, ...options }
+		this._options = opts
+		this.ctx = context(); this.index = new BlueNoiseIndex(options.blueNoiseStart)
+		this.velocityDepthNormalPass = opts.velocityDepthNormalPass
+		reactive(this, opts, key => { if (key === "resolutionScale") this.setSize(this.width, this.height) })
+		this.setSize(options.width ?? composer?.inputBuffer?.width, options.height ?? composer?.inputBuffer?.height)
+	}
+	setSize(width, height) {
+		if (width === undefined) return
+		if (this._options.resolutionScale !== 1) throw new Error("resolutionScale != 1 is not supported by the CUDA engine")
+		this.dispose()
+		this.width = width; this.height = height
+		this.aoPlane = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)
+		this.outputPlane = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)
+		this.outputHost = new Uint16Array(4 * width * height)
+		this.planeSource = new ReadbackPlaneSource(this.ctx, width, height)
+		this.denoise = new PoissonDenoisePass(this._camera, [this.aoPlane], { ...this._options, normalPhi: 3.25, depthPhi: 2 })
+		this.denoise.setSize(width, height)
+	}
+	get texture() { return this.denoise.texture[0] }
+	initialize() {}
+	// update(renderer, inputBuffer, deltaTime) — src/ao/AOEffect.js:126-178 + src/ao/AOPass.js:85-110
+	update(renderer, inputBuffer) {
+		const cam = cameraBlock(this._camera)
+		const pv = this._camera.projectionMatrix.clone().multiply(this._camera.matrixWorldInverse)
+		const planes = this.planeSource.read(renderer, { depth: this.composer.depthRenderTarget, velocity: this.velocityDepthNormalPass?.renderTarget, directLight: inputBuffer })
+		rfx.hbao(this.ctx, { projectionView: f32(pv), projectionInverse: cam.projectionInverse, matrixWorld: cam.matrixWorld, aoDistance: this.distance,
+			distancePower: this.distancePower, bias: this.bias, thickness: this.thickness, spp: this.spp, blueNoiseIndex: this.index.value }, planes.depth, this.aoPlane)
+		this.denoise.depthPlane = planes.depth; this.denoise.gbufferPlane = planes.velocity; this.denoise.gbufferTexture = false
+		this.denoise.options.inputLinear = true
+		this.denoise.iterations = this._options.iterations
+		this.denoise.render()
+		rfx.aoCompose(this.ctx, { power: this.power, color: this.color }, planes.depth, this.denoise.texture[0], planes.directLight, this.outputPlane)   // ao_compose.frag:6-16
+		rfx.planeDownload(this.ctx, this.outputPlane, this.outputHost)
+	}
+	get outputTexture() { return this.outputHost }
+	dispose() {
+		for (const k of ["aoPlane", "outputPlane"]) if (this[k]) { rfx.planeFree(this.ctx, this[k]); this[k] = null }
+		this.planeSource?.dispose(); this.denoise?.dispose()
+	}
+}
+HBAOEffect.DefaultOptions = defaultAOOptions
+
+// -------------------------------------------------------------------------------------------------------------------------
+export class MotionBlurEffect {
+	// new MotionBlurEffect(velocityPass, options) — src/motion-blur/MotionBlurEffect.js:16-102
+	constructor(velocityPass, options = { intensity: 1, jitter: 1, samples: 16 }) {
+		this.velocityPass = velocityPass
+		const opts = { intensity: 1, jitter: 1, samples: 16, ...options }
+		this.ctx = context()
+		reactive(this, opts, () => {})
+	}
+	initialize() {}
+	setSize(width, height) {
+		this.dispose()
+		this.width = width; this.height = height
+		this.planes = { velocity: rfx.planeAlloc(this.ctx, FMT.RGBA32F, width, height), input: rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height),
+			output: rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height) }
+		this.hostVel = new Float32Array(4 * width * height); this.hostIn = new Uint16Array(4 * width * height); this.outputHost = new Uint16Array(4 * width * height)
+	}
+	// update(renderer, inputBuffer, deltaTime) — :87-102 (frame = renderer.info.render.frame % 4096, resolution = the WINDOW size)
+	update(renderer, inputBuffer, deltaTime) {
+		if (!this.planes || inputBuffer.width !== this.width) this.setSize(inputBuffer.width, inputBuffer.height)
+		renderer.readRenderTargetPixels(this.velocityPass.renderTarget, 0, 0, this.width, this.height, this.hostVel)
+		renderer.readRenderTargetPixels(inputBuffer, 0, 0, this.width, this.height, this.hostIn)
+		rfx.planeUpload(this.ctx, this.planes.velocity, this.hostVel); rfx.planeUpload(this.ctx, this.planes.input, this.hostIn)
+		rfx.motionBlur(this.ctx, { intensity: this.intensity, jitter: this.jitter, deltaTime: Math.max(1 / 1000, deltaTime), samples: this.samples,
+			frame: renderer.info.render.frame % 4096, resolution: [globalThis.innerWidth ?? this.width, globalThis.innerHeight ?? this.height] },
+		this.planes.velocity, this.planes.input, this.planes.output)
+		rfx.planeDownload(this.ctx, this.planes.output, this.outputHost)
+	}
+	get outputTexture() { return this.outputHost }
+	dispose() { if (this.planes) for (const p of Object.values(this.planes)) rfx.planeFree(this.ctx, p); this.planes = null }
+}

@@ -983,7 +983,7 @@ struct PoissonShader {
 // ======================================================================================
 struct ComposeShader {
   Camera cam;
-  Tex depthTexture, gBufferTexture, diffuseGiTexture, specularGiTexture;
+  Tex depthTexture, gBufferTexture, diffuseGiTexture, specularGiTexture, sceneTexture;
   int inputType, W, H;
   static constexpr float EPSILON = 1e-6f;  // three <common>
 
@@ -1029,7 +1029,8 @@ struct ComposeShader {
     vec3 diffuse = mat.diffuse.xyz();
     vec3 f0 = mix(vec3(0.04f), diffuse, mat.metalness);
     vec3 F = f0 + (vec3(1.0f) - f0) * powcr(1.0f - VoH, 5.0f);
-    vec3 diffuseComponent = diffuse * (1.0f - mat.metalness) * (vec3(1.0f) - F) * diffuseGi.xyz();
+    // #if inputType != TYPE_SPECULAR ... #else textureLod(sceneTexture, vUv, 0.).rgb   (denoiser_compose_functions.glsl:97-101)
+    vec3 diffuseComponent = inputType != RFX_INPUT_SPECULAR ? diffuse * (1.0f - mat.metalness) * (vec3(1.0f) - F) * diffuseGi.xyz() : textureLod0(sceneTexture, vUv).xyz();
     vec3 specularComponent = specularGi.xyz() * F;
     vec3 gi = diffuseComponent + specularComponent + mat.emissive;
     out = vec4(gi, 1.0f);
@@ -1238,14 +1239,17 @@ void orc_poisson_denoise(const rfx_poisson_params* p, int W, int H, const float*
 }
 
 // K4.  diffuse/specular RGBA16F (nearest fetch at pixel centre; filter irrelevant), out RGBA32F; discarded pixels untouched.
+// diffuse_gi / specular_gi / scene may be NULL (null sampler => (0,0,0,1)): DenoiserComposePass.js:23-33 binds only the textures of its
+// inputType; `scene` is the composer input buffer (Denoiser.js:100-102, LINEAR RGBA16F), read by TYPE_SPECULAR only
 void orc_gi_compose(const rfx_compose_params* p, int W, int H, const float* depth, const float* gbuffer, const uint16_t* diffuse_gi,
-                    const uint16_t* specular_gi, float* out) {
+                    const uint16_t* specular_gi, const uint16_t* scene, float* out) {
   ComposeShader s(*p);
   s.W = W; s.H = H;
   s.depthTexture = mk(depth, W, H, F_R32F);
   s.gBufferTexture = mk(gbuffer, W, H, F_RGBA32F);
   s.diffuseGiTexture = mk(diffuse_gi, W, H, F_RGBA16F, true);
   s.specularGiTexture = mk(specular_gi, W, H, F_RGBA16F, true);
+  s.sceneTexture = mk(scene, W, H, F_RGBA16F, true);
 #pragma omp parallel for schedule(dynamic, 4)
   for (int y = 0; y < H; y++)
     for (int x = 0; x < W; x++) {

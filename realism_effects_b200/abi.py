@@ -155,7 +155,7 @@ def _sig(lib):
     lib.rfx_ssgi_trace_launch.argtypes = [vp, vp, _P(SsgiParams), PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_temporal_reproject_launch.argtypes = [vp, vp, _P(TemporalParams), PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_poisson_denoise_launch.argtypes = [vp, vp, _P(PoissonParams), PP, PP, PP, PP, PP, PP, u32, u32]
-    lib.rfx_gi_compose_launch.argtypes = [vp, vp, _P(ComposeParams), PP, PP, PP, PP, PP, u32, u32]
+    lib.rfx_gi_compose_launch.argtypes = [vp, vp, _P(ComposeParams), PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_ssgi_compose_launch.argtypes = [vp, vp, PP, PP, PP, PP, u32, u32]
     lib.rfx_hbao_launch.argtypes = [vp, vp, _P(HbaoParams), PP, PP, u32, u32]
     lib.rfx_ao_compose_launch.argtypes = [vp, vp, _P(AoComposeParams), PP, PP, PP, PP, u32, u32]

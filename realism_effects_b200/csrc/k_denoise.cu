@@ -335,8 +335,10 @@ __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_const
   // pixel-centre fetch of the LINEAR Poisson targets (literal bilinear, like the GL sampler)
   // exact variant: the literal bilinear fetch a GL sampler performs at the pixel centre; fast variant: the centre texel itself
   // (the literal weights are (1,0,0,0) up to one ulp of u*W, i.e. the two differ by <= 1.2e-4 x the neighbour contrast)
-  const v4 dgi = a.fast ? ld_h4(a.diffuse, x, y) : tex_h4_linear(a.diffuse, vUv);
-  const v4 sgi = a.fast ? ld_h4(a.specular, x, y) : tex_h4_linear(a.specular, vUv);
+  // a texture the inputType does not bind is a null sampler: (0,0,0,1)  (DenoiserComposePass.js:23-33)
+  const v4 nul = mk4(0.0f, 0.0f, 0.0f, 1.0f);
+  const v4 dgi = !a.diffuse.p ? nul : (a.fast ? ld_h4(a.diffuse, x, y) : tex_h4_linear(a.diffuse, vUv));
+  const v4 sgi = !a.specular.p ? nul : (a.fast ? ld_h4(a.specular, x, y) : tex_h4_linear(a.specular, vUv));
 
   // constructGlobalIllumination :53-107
   const float roughness = rough0 * rough0;
@@ -364,14 +366,15 @@ __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_const
   const v3 f0 = mix(mk3(0.04f), diffuse, metalness);
   const float omv = 1.0f - VoH, omv2 = omv * omv;
   const v3 F = f0 + (mk3(1.0f) - f0) * (a.fast ? omv2 * omv2 * omv : powf(omv, 5.0f));
-  const v3 diffuseComponent = diffuse * (1.0f - metalness) * (mk3(1.0f) - F) * xyz(dgi);
+  // TYPE_SPECULAR (SSR): the diffuse component is the scene colour (composer input buffer, LINEAR)  denoiser_compose_functions.glsl:97-101
+  const v3 diffuseComponent = a.input_type != RFX_INPUT_SPECULAR ? diffuse * (1.0f - metalness) * (mk3(1.0f) - F) * xyz(dgi)
+                                                                 : (a.scene.p ? xyz(tex_h4_linear(a.scene, vUv)) : mk3(0.0f));
   const v3 specularComponent = xyz(sgi) * F;
   const v3 gi = diffuseComponent + specularComponent + emissive;
   st_f4(a.out.p, a.out.pitch, x, y, make_float4(gi.x, gi.y, gi.z, 1.0f));
 }
 
 cudaError_t launch_gi_compose(const ComposeArgs& a, cudaStream_t s) {
-  if (a.input_type != RFX_INPUT_DIFFUSE_SPECULAR) return cudaErrorNotSupported;
   dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   gi_compose_kernel<<<grid, kThreads, 0, s>>>(a);
   return cudaGetLastError();

@@ -546,15 +546,21 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
 }
 
 rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_params* p, const rfx_plane* depth, const rfx_plane* gb,
-                                 const rfx_plane* dgi, const rfx_plane* sgi, const rfx_plane* out, uint32_t row0, uint32_t row1) {
+                                 const rfx_plane* dgi, const rfx_plane* sgi, const rfx_plane* scene, const rfx_plane* out, uint32_t row0, uint32_t row1) {
   if (!ctx || !p || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "gi_compose: null argument");
   ComposeArgs a{};
-  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gb, RFX_FMT_RGBA32F, a.gb) || !pv(dgi, RFX_FMT_RGBA16F, a.diffuse) || !pv(sgi, RFX_FMT_RGBA16F, a.specular) ||
-      !ov(out, RFX_FMT_RGBA32F, a.out))
-    return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: depth R32F, gbuffer RGBA32F, gi RGBA16F, out RGBA32F required");
-  if (p->input_type != RFX_INPUT_DIFFUSE_SPECULAR) return fail(ctx, RFX_ERR_UNSUPPORTED, "gi_compose: only inputType diffuseSpecular is implemented");
+  if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gb, RFX_FMT_RGBA32F, a.gb) || !ov(out, RFX_FMT_RGBA32F, a.out))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: depth R32F, gbuffer RGBA32F, out RGBA32F required");
+  if (p->input_type != RFX_INPUT_DIFFUSE_SPECULAR && p->input_type != RFX_INPUT_DIFFUSE && p->input_type != RFX_INPUT_SPECULAR)
+    return fail(ctx, RFX_ERR_INVALID_ARG, "gi_compose: bad input_type");
+  // DenoiserComposePass.js:23-33: diffuseSpecular binds both GI textures, diffuse only the first, specular only the second
+  const bool need_d = p->input_type != RFX_INPUT_SPECULAR, need_s = p->input_type != RFX_INPUT_DIFFUSE;
+  if (need_d && !pv(dgi, RFX_FMT_RGBA16F, a.diffuse)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: diffuse GI must be RGBA16F");
+  if (need_s && !pv(sgi, RFX_FMT_RGBA16F, a.specular)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: specular GI must be RGBA16F");
+  if (p->input_type == RFX_INPUT_SPECULAR && scene && !pv(scene, RFX_FMT_RGBA16F, a.scene)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: scene must be RGBA16F");
   a.W = (int)out->width; a.H = (int)out->height;
-  if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.diffuse.w != a.W || a.specular.w != a.W || a.diffuse.h != a.H)
+  if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.gb.h != a.H || (a.diffuse.p && (a.diffuse.w != a.W || a.diffuse.h != a.H)) ||
+      (a.specular.p && (a.specular.w != a.W || a.specular.h != a.H)) || (a.scene.p && (a.scene.w != a.W || a.scene.h != a.H)))
     return fail(ctx, RFX_ERR_SIZE_MISMATCH, "gi_compose: plane sizes differ");
   rows(row0, row1, out->height, a.row0, a.row1);
   set_segs(ctx, a.row0, a.row1, a.segs);
@@ -1011,7 +1017,7 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
   rfx_ctx* ctx = ch->ctx;
   const rfx_ssgi_chain_options& o = ch->opt;
   rfx_status st = RFX_OK;
-  const uint32_t n_launches = 2u + 2u * (uint32_t)o.denoise_iterations + (o.mode == RFX_MODE_SSGI ? 1u : 0u);
+  const uint32_t n_launches = 3u + 2u * (uint32_t)o.denoise_iterations;  // K1, K2, K3 passes, K4 (both modes: DenoiserComposePass runs for inputType specular too)
   if (!ranges) n_blocks = 1;
   auto R0 = [&](uint32_t blk, uint32_t k) -> uint32_t { return ranges ? ranges[(blk * n_launches + k) * 2] : 0u; };
   auto R1 = [&](uint32_t blk, uint32_t k) -> uint32_t { return ranges ? ranges[(blk * n_launches + k) * 2 + 1] : 0u; };
@@ -1097,14 +1103,15 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     if (st != RFX_OK) return st;
   }
   // ---- K4  DenoiserComposePass.render
-  if (o.mode == RFX_MODE_SSGI && on(k)) {
+  if (on(k)) {
     rfx_compose_params cp{};
     cp.cam = f->cam;
-    cp.input_type = RFX_INPUT_DIFFUSE_SPECULAR;
+    cp.input_type = o.mode == RFX_MODE_SSGI ? RFX_INPUT_DIFFUSE_SPECULAR : RFX_INPUT_SPECULAR;  // SSGIEffect.js:70-77
     for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
       SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       SpanGuard g(ch, cs, 4);
-      st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], &ch->composed, R0(blk, k), R1(blk, k));
+      if (o.mode == RFX_MODE_SSGI) st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], nullptr, &ch->composed, R0(blk, k), R1(blk, k));
+      else st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, nullptr, &ch->dnB[0], f->direct_light, &ch->composed, R0(blk, k), R1(blk, k));  // scene = the composer input buffer (Denoiser.js:100-102)
     }
     if (st != RFX_OK) return st;
   }
@@ -1116,7 +1123,7 @@ rfx_status rfx_ssgi_chain_render(rfx_ssgi_chain* ch, void* stream, const rfx_ssg
   return chain_render_impl(ch, stream, f, nullptr, 1, 0, 0xffffffffu);
 }
 static rfx_status check_ranges(rfx_ssgi_chain* ch, const uint32_t* ranges, uint32_t n_launches, uint32_t n_blocks) {
-  const uint32_t expect = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
+  const uint32_t expect = 3u + 2u * (uint32_t)ch->opt.denoise_iterations;
   if (n_launches != expect || n_blocks == 0 || n_blocks > RFX_MAX_SEGS) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: expected %u launches per block, got %u (blocks %u)", expect, n_launches, n_blocks);
   for (uint32_t i = 0; i < n_launches * n_blocks; i++)
     if (ranges[2 * i] >= ranges[2 * i + 1] || ranges[2 * i + 1] > ch->opt.height) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain ranges: bad range %u", i);
@@ -1201,8 +1208,8 @@ rfx_status rfx_ssgi_chain_submit_host(rfx_ssgi_chain* ch, const rfx_ssgi_host_fr
     result = &ch->composed2[cur];
     ch->dn_buf[set] = cur;
   } else {
-    const uint32_t n_launches = 2u + 2u * (uint32_t)ch->opt.denoise_iterations + (ch->opt.mode == RFX_MODE_SSGI ? 1u : 0u);
-    const uint32_t split = ch->opt.mode == RFX_MODE_SSGI ? n_launches - 1 : 0;  // K4 is the only launch that writes `composed`
+    const uint32_t n_launches = 3u + 2u * (uint32_t)ch->opt.denoise_iterations;
+    const uint32_t split = n_launches - 1;  // K4 is the only launch that writes `composed`
     if (split && (st = chain_render_impl(ch, nullptr, &f, nullptr, 1, 0, split)) != RFX_OK) return st;
     if (ch->host_submitted >= 1) CU(cudaStreamWaitEvent(ctx->stream, ch->ev_dn[set ^ 1], 0));
     if ((st = chain_render_impl(ch, nullptr, &f, nullptr, 1, split, 0xffffffffu)) != RFX_OK) return st;

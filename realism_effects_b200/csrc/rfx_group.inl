@@ -58,11 +58,12 @@ __global__ void elapsed_kernel(const unsigned long long* t0, float* ms) {
 }  // namespace
 
 // ---- sharding plan (pure host arithmetic; mirrored by realism_effects_b200/parallel.py:ShardPlan for the CPU tests) -------------
-// Output rows [a,b) of every launch of one frame (chain order: K1, K2, K3 pass 0..n-1, K4 in SSGI mode) for the band [own0, own1):
+// Output rows [a,b) of every launch of one frame (chain order: K1, K2, K3 pass 0..n-1, K4) for the band [own0, own1):
 // launch k runs on the band widened by the rows all later launches read around their outputs.
 extern "C" rfx_status rfx_shard_ranges(uint32_t width, uint32_t height, uint32_t own0, uint32_t own1, int32_t n_poisson_passes, float radius, int32_t ssgi_mode,
                                        uint32_t* ranges, uint32_t n_launches) {
-  const uint32_t expect = 2u + (uint32_t)n_poisson_passes + (ssgi_mode ? 1u : 0u);
+  (void)ssgi_mode;  // K4 runs in both modes (SSR composes with inputType specular, DenoiserComposePass.js:26-33)
+  const uint32_t expect = 3u + (uint32_t)n_poisson_passes;
   if (!ranges || n_launches != expect || own0 >= own1 || own1 > height || width == 0 || n_poisson_passes < 0) return RFX_ERR_INVALID_ARG;
   const int H = (int)height;
   // a Poisson tap offset is rotated AFTER the division by the resolution (poisson_denoise.frag:183-189), so its row reach is
@@ -74,9 +75,9 @@ extern "C" rfx_status rfx_shard_ranges(uint32_t width, uint32_t height, uint32_t
   const int n = n_poisson_passes;
   std::vector<int> r0(expect), r1(expect);
   int a = (int)own0, b = (int)own1;
-  if (ssgi_mode) { r0[expect - 1] = a; r1[expect - 1] = b; }
+  r0[expect - 1] = a; r1[expect - 1] = b;
   if (n) {
-    if (ssgi_mode) expand(a, b, k4_rows);
+    expand(a, b, k4_rows);
     r0[2 + n - 1] = a; r1[2 + n - 1] = b;
     for (int j = n - 2; j >= 0; j--) { expand(a, b, poisson_halo); r0[2 + j] = a; r1[2 + j] = b; }
     expand(a, b, poisson_halo);

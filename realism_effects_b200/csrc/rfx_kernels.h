@@ -82,7 +82,7 @@ cudaError_t launch_gbuffer_decode(PV gb, OutV nrd, int W, int H, int gbuffer_tex
 
 // ---- K4 / K5 -------------------------------------------------------------------------------
 struct ComposeArgs {
-  PV depth, gb, diffuse, specular;
+  PV depth, gb, diffuse, specular, scene;  // diffuse / specular / scene: p == nullptr = not bound (null sampler)
   OutV out;
   int W, H, row0, row1;
   RowSegs segs;

@@ -213,7 +213,7 @@ class SSGIEffect(_Reactive):
         scene_buf = inputBuffer if inputBuffer is not None else self.composer.inputBuffer
         self._chain.render(abi.make_camera(cam_u), self._scene.depth, self._scene.gbuffer, self.velocityDepthNormalPass.texture,
                            scene_buf if self.isUsingRenderPass else None, cam_u["position"], moved)
-        if self._options["mode"] != "ssr" and getattr(self.composer, "outputBuffer", None) is not None:
+        if getattr(self.composer, "outputBuffer", None) is not None:  # both modes: SSR composes with inputType "specular" (Denoiser.js:56-64)
             self.ctx.ssgi_compose(self._scene.depth, self.outputTexture, scene_buf, self.composer.outputBuffer)  # K5 (mainImage of the effect)
 
     def dispose(self):
@@ -230,6 +230,23 @@ class SSREffect(SSGIEffect):
 
 
 # ---------------------------------------------------------------------------------------------------
+def generateR2(count: int) -> list:
+    """src/temporal-reproject/utils/QuasirandomGenerator.js:11-24 (JS doubles)"""
+    g = 1.32471795724474602596090885447809  # plastic number
+    a1, a2, base = 1.0 / g, 1.0 / (g * g), 1.1127756842787055
+    return [[math.fmod(base + a1 * n, 1.0), math.fmod(base + a2 * n, 1.0)] for n in range(count)]
+
+
+r2Sequence = [[a - 0.5, b - 0.5] for a, b in generateR2(256)]  # src/taa/TAAUtils.js:3
+
+
+def jitter(width, height, camera, frame: int, jitterScale: float = 1.0):
+    """src/taa/TAAUtils.js:5-11: sub-pixel view offset from the R2 sequence (a no-op for cameras without setViewOffset)"""
+    x, y = r2Sequence[frame % len(r2Sequence)]
+    if hasattr(camera, "setViewOffset"):
+        camera.setViewOffset(width, height, x * jitterScale, y * jitterScale, width, height)
+
+
 class TemporalReprojectPass:
     """new TemporalReprojectPass(scene, camera, velocityDepthNormalPass, texture, textureCount, options)
     (src/temporal-reproject/TemporalReprojectPass.js:38-225).  1-plane RGBA16F configuration (TRAA)."""
@@ -256,14 +273,24 @@ class TemporalReprojectPass:
 
     @property
     def texture(self):
+        """renderTarget.texture[0]: the plane rendered by the most recent render() (TemporalReprojectPass.js:150-156)"""
         return self.renderTarget
 
     def reset(self):
         self.keepData = 0.0
 
+    def jitter(self, jitterScale: float = 1.0):  # TemporalReprojectPass.js:216-220
+        self.unjitter()
+        jitter(self.renderTarget.width, self.renderTarget.height, self._camera, self.frame, jitterScale)
+
+    def unjitter(self):  # :222-224
+        if hasattr(self._camera, "clearViewOffset"):
+            self._camera.clearViewOffset()
+
     def render(self, renderer=None):
         self.frame = (self.frame + 1) % 4096
-        cam_u = self._camera.uniforms()
+        # the pass uploads the UN-jittered projection (camera.view disabled around updateProjectionMatrix, :168-186)
+        cam_u = self._camera.unjittered_uniforms() if hasattr(self._camera, "unjittered_uniforms") else self._camera.uniforms()
         prev = self._prev or cam_u
         o, p = self.options, abi.TemporalParams()
         p.cam = abi.make_camera(cam_u)
@@ -278,15 +305,16 @@ class TemporalReprojectPass:
         p.full_accumulate = int(bool(o["fullAccumulate"]) and not _did_camera_move(cam_u, self._prev))
         p.texture_count, p.input_type, p.log_transform, p.history_linear = 1, abi.INPUT_DIFFUSE, int(bool(o["logTransform"])), 1
         p.reproject_specular[:] = [0, 0]
+        # the reference copies the framebuffer into framebufferTexture after the draw (:197-200); here the two planes swap roles
+        # BEFORE the launch instead, so that `renderTarget` / `texture` is always the plane this render() wrote
+        self.renderTarget, self.framebufferTexture = self.framebufferTexture, self.renderTarget
         self.ctx.temporal_reproject(p, self.inputTexture, self.velocityDepthNormalPass.texture, self.framebufferTexture, None, self.renderTarget, None)
         self.keepData = 1.0
-        # history = copy of what was just rendered
-        self.renderTarget, self.framebufferTexture = self.framebufferTexture, self.renderTarget
         self._prev = cam_u
 
     @property
     def accumulated(self):
-        return self.framebufferTexture  # after the swap in render(): the plane written this frame
+        return self.renderTarget
 
     def dispose(self):
         for p in (self.renderTarget, self.framebufferTexture):
@@ -316,8 +344,11 @@ class TRAAEffect:
         if self.temporalReprojectPass is None:
             self.temporalReprojectPass = TemporalReprojectPass(self._scene, self._camera, self.velocityDepthNormalPass, inputBuffer, 1, self.options)
         self.temporalReprojectPass.inputTexture = inputBuffer
-        # (sub-pixel jitter of the projection is a host-camera concern: src/taa/TAAUtils.js:5-11)
-        self.temporalReprojectPass.render(renderer)
+        trp = self.temporalReprojectPass
+        trp.unjitter()                                                       # TRAAEffect.js:67-72
+        self.unjitteredProjectionMatrix = np.array(getattr(self._camera, "proj", np.eye(4)), copy=True)
+        trp.jitter()                                                         # the NEXT scene render is rasterised with this sub-pixel offset
+        trp.render(renderer)
 
     def compose(self, outputBuffer):
         """traa_compose.frag: rgb passthrough, alpha 1"""

@@ -167,8 +167,8 @@ class Context:
         self._chk(self.lib.rfx_poisson_denoise_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer_or_normal), _r(in0), _r(in1), _r(out0),
                                                       _r(out1), rows[0], rows[1]))
 
-    def gi_compose(self, p, depth, gbuffer, diffuse_gi, specular_gi, out, rows=(0, 0), stream=None):
-        self._chk(self.lib.rfx_gi_compose_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer), _r(diffuse_gi), _r(specular_gi), _r(out),
+    def gi_compose(self, p, depth, gbuffer, diffuse_gi, specular_gi, out, rows=(0, 0), stream=None, scene=None):
+        self._chk(self.lib.rfx_gi_compose_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer), _r(diffuse_gi), _r(specular_gi), _r(scene), _r(out),
                                                  rows[0], rows[1]))
 
     def ssgi_compose(self, depth, gi, scene, out, rows=(0, 0), stream=None):

@@ -33,7 +33,7 @@ from dataclasses import dataclass
 
 @dataclass
 class ShardPlan:
-    """Row ranges [a, b) per launch of one frame, in chain order: K1, K2, K3 pass 0..n-1, K4 (SSGI mode only),
+    """Row ranges [a, b) per launch of one frame, in chain order: K1, K2, K3 pass 0..n-1, K4,
     for every row block this rank owns."""
 
     height: int
@@ -102,16 +102,13 @@ class ShardPlan:
         k3 = [None] * n
         nxt = own
         if n:
-            k3[n - 1] = self._expand(own, self.K4_INPUT_ROWS if self.ssgi_mode else 0)
+            k3[n - 1] = self._expand(own, self.K4_INPUT_ROWS)
             for j in range(n - 2, -1, -1):
                 k3[j] = self._expand(k3[j + 1], self.poisson_halo)
             nxt = self._expand(k3[0], self.poisson_halo)
         k2 = nxt
         k1 = self._expand(k2, self.K2_NEIGHBOURHOOD_ROWS)
-        out = [k1, k2, *k3]
-        if self.ssgi_mode:
-            out.append(own)
-        return out
+        return [k1, k2, *k3, own]  # K4 runs in both modes (SSR composes with inputType specular)
 
     @property
     def ranges(self) -> list:
@@ -125,7 +122,7 @@ class ShardPlan:
 
     @property
     def n_launches(self) -> int:
-        return 2 + self.n_poisson_passes + (1 if self.ssgi_mode else 0)
+        return 3 + self.n_poisson_passes
 
     def super_block(self, j: int):
         """rows of super-block j: N consecutive blocks, one per rank, in rank order (an in-place all-gather unit)"""

@@ -77,8 +77,49 @@ class Camera:
     world: np.ndarray = field(init=False)
 
     def __post_init__(self):
-        self.proj = perspective_matrix(self.fov, self.aspect, self.near, self.far)
+        self.view_offset = None  # three.js camera.view (setViewOffset): sub-pixel TRAA jitter
+        self.updateProjectionMatrix()
         self.world = look_at_world_matrix(self.position, self.target)
+
+    # -- three.js PerspectiveCamera.setViewOffset / clearViewOffset / updateProjectionMatrix -----------------------------------
+    def setViewOffset(self, fullWidth, fullHeight, x, y, width, height):
+        self.view_offset = dict(enabled=True, fullWidth=fullWidth, fullHeight=fullHeight, offsetX=x, offsetY=y, width=width, height=height)
+        self.updateProjectionMatrix()
+
+    def clearViewOffset(self):
+        if self.view_offset is not None:
+            self.view_offset["enabled"] = False
+        self.updateProjectionMatrix()
+
+    def updateProjectionMatrix(self):
+        near = self.near
+        top = near * math.tan(math.radians(0.5 * self.fov))
+        height = 2 * top
+        width = self.aspect * height
+        left = -0.5 * width
+        v = self.view_offset
+        if v is not None and v["enabled"]:
+            left += v["offsetX"] * width / v["fullWidth"]
+            top -= v["offsetY"] * height / v["fullHeight"]
+            width *= v["width"] / v["fullWidth"]
+            height *= v["height"] / v["fullHeight"]
+        right, bottom, far = left + width, top - height, self.far
+        x, y = 2 * near / (right - left), 2 * near / (top - bottom)
+        a, b = (right + left) / (right - left), (top + bottom) / (top - bottom)
+        c, d = -(far + near) / (far - near), -2 * far * near / (far - near)
+        self.proj = np.array([[x, 0, a, 0], [0, y, b, 0], [0, 0, c, d], [0, 0, -1, 0]], dtype=np.float64)
+
+    def unjittered_uniforms(self) -> dict:
+        """uniforms with camera.view disabled, as TemporalReprojectPass.render uploads them (TemporalReprojectPass.js:168-186)"""
+        v, saved = self.view_offset, self.proj
+        if v is not None and v["enabled"]:
+            v["enabled"] = False
+            self.updateProjectionMatrix()
+            u = self.uniforms()
+            v["enabled"] = True
+            self.proj = saved
+            return u
+        return self.uniforms()
 
     @property
     def view(self):

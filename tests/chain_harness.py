@@ -138,10 +138,10 @@ def poisson_params(o: Opts, index: int, first: bool) -> abi.PoissonParams:
     return p
 
 
-def compose_params(cam: abi.CameraS) -> abi.ComposeParams:
+def compose_params(cam: abi.CameraS, mode: int = abi.MODE_SSGI) -> abi.ComposeParams:
     p = abi.ComposeParams()
     p.cam = cam
-    p.input_type = abi.INPUT_DIFFUSE_SPECULAR
+    p.input_type = abi.INPUT_DIFFUSE_SPECULAR if mode == abi.MODE_SSGI else abi.INPUT_SPECULAR  # SSGIEffect.js:70-77
     return p
 
 
@@ -206,9 +206,12 @@ def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0",
             else:
                 dnB = [o0, o1]
         # K4
-        cp = compose_params(cam)
+        cp = compose_params(cam, o.mode)
         rec["_k4_params"], rec["_k4_prev"] = cp, composed.copy()
-        composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed)
+        if o.mode == abi.MODE_SSGI:
+            composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed)
+        else:  # SSR: specular GI = the single Poisson target, diffuse component = the scene colour (composer input buffer)
+            composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], None, dnB[0], composed, scene=fr["direct"])
         full = dict(ssgi=ssgi, tr0=tr[0], tr1=tr[1], dn0=dnB[0], dn1=dnB[1], composed=composed)
         if lean:
             rec = {}
@@ -277,8 +280,14 @@ def run_chain_parity(width=192, height=108, frames=2, max_frac=2e-3, fast_math=T
     # pixels outside 1e-3 to stay small and (b) essentially all pixels inside 4 fp16 ulps (4e-3).
     loose_frac = 5 * max_frac if fast_math else max_frac
     worst, worst4, lines = 0.0, 0.0, []
+    ssr = o.mode == abi.MODE_SSR
     for t, (r, g) in enumerate(zip(ref, got)):
         for k in ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"):
+            if ssr and k == "ssgi":  # SSR: rgb fp32 + (rayLength, roughness) packed in alpha (ssgi.frag:302-308): compare the colour channels
+                c, c4 = compare(r[k][..., :3], g[k][..., :3]), compare(r[k][..., :3], g[k][..., :3], rtol=4e-3)
+                worst, worst4 = max(worst, c["frac_bad"]), max(worst4, c4["frac_bad"])
+                lines.append(f"f{t}.{k}: bad={c['frac_bad']:.2e} bad@4e-3={c4['frac_bad']:.1e} biteq={c['bit_equal']:.4f}")
+                continue
             c = compare(r[k], g[k], packed=(k == "ssgi"))
             c4 = compare(r[k], g[k], packed=(k == "ssgi"), rtol=4e-3)
             worst, worst4 = max(worst, c["frac_bad"]), max(worst4, c4["frac_bad"])

@@ -139,11 +139,12 @@ def poisson_denoise(p: abi.PoissonParams, depth, gbuffer_or_normal, in0, in1, bl
     return o0.view(np.float16), None if o1 is None else o1.view(np.float16)
 
 
-def gi_compose(p: abi.ComposeParams, depth, gbuffer, diffuse_gi, specular_gi, out_prev):
+def gi_compose(p: abi.ComposeParams, depth, gbuffer, diffuse_gi, specular_gi, out_prev, scene=None):
+    """diffuse_gi / specular_gi / scene may be None (null sampler)"""
     H, W = depth.shape
     out = np.array(out_prev, np.float32, copy=True)
     lib().orc_gi_compose(C.byref(p), C.c_int(W), C.c_int(H), _p(_c(depth, np.float32)), _p(_c(gbuffer, np.float32)), _p(f16bits(diffuse_gi)),
-                         _p(f16bits(specular_gi)), _p(out))
+                         _p(f16bits(specular_gi)), _p(f16bits(scene)), _p(out))
     return out
 
 

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(built):
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(set(abi.EXPORTS)) == declared
-    assert lib.rfx_version() == 1
+    assert lib.rfx_version() == 2
     assert [lib.rfx_format_bytes(f) for f in range(4)] == [4, 16, 8, 4]
 
 

@@ -13,6 +13,8 @@ CASES = [
     dict(width=128, height=72, frames=2, importance_sampling=False),
     dict(width=128, height=72, frames=2, use_envmap=False, use_direct_light=False, steps=8, refine_steps=0),
     dict(width=128, height=72, frames=2, missed_rays=True),
+    dict(width=160, height=90, frames=3, mode=1),                         # SSR: 1 plane, K4 with inputType "specular" (scene colour + specular GI * F)
+    dict(width=128, height=72, frames=2, mode=1, denoise_iterations=0),   # SSR without Poisson passes
 ]
 
 
@@ -23,6 +25,20 @@ def test_chain_parity(built, kw, fast):
     print(res["summary"])
     assert res["ok"], res["summary"]
     assert res["launches"] > 0
+
+
+def test_ssr_chain_writes_composed_and_feeds_it_back(built):
+    """SSR mode end to end: `composed` = sceneTexture + specularGi * F + emissive is written every frame and is what
+    the next frame's hit rays sample (src/ssgi/pass/SSGIPass.js:88) — it must not stay zero."""
+    o = ch.Opts(mode=1)
+    inp = ch.make_inputs(160, 90, 3)
+    ref = ch.run_oracle_chain(inp, o)
+    got, _ = ch.run_cuda_chain(inp, o)
+    for t in range(3):
+        assert np.abs(got[t]["composed"][..., :3]).max() > 0.05
+        c = ch.compare(ref[t]["composed"], got[t]["composed"])
+        assert c["frac_bad"] <= 1e-3, (t, c)
+    assert not np.array_equal(got[1]["ssgi"], got[0]["ssgi"])
 
 
 def test_static_camera_full_accumulate(built):

@@ -77,3 +77,38 @@ def test_chain_option_mirrors_defaults():
             o.env_blur, o.steps, o.refine_steps) == (10, 10, 1, 3, 0.5, 5, 2, 50, 50, 50, 0.5, 20, 5)
     assert o.flags == abi.SSGI_IMPORTANCE_SAMPLING | abi.SSGI_USE_DIRECT_LIGHT | abi.SSGI_USE_ENVMAP
     assert ch.max_mip_level(1024, 512) == 11.0
+
+
+def test_traa_jitter_r2_sequence_and_view_offset():
+    """TRAA projection jitter: generateR2 (QuasirandomGenerator.js:11-24), r2Sequence / jitter (TAAUtils.js:3-11),
+    three.js PerspectiveCamera.setViewOffset -> updateProjectionMatrix, and the un-jittered projection K2 uploads
+    (TemporalReprojectPass.js:168-186)."""
+    from realism_effects_b200 import effects
+
+    g = 1.32471795724474602596090885447809
+    pts = effects.generateR2(5)
+    base = 1.1127756842787055
+    for n, (a, b) in enumerate(pts):
+        assert a == (base + n / g) % 1 and b == (base + n / (g * g)) % 1 and 0 <= a < 1 and 0 <= b < 1
+    assert len(effects.r2Sequence) == 256 and all(-0.5 <= x < 0.5 and -0.5 <= y < 0.5 for x, y in effects.r2Sequence)
+    # low discrepancy: 256 points cover a 8x8 grid with every cell hit
+    cells = {(int((x + 0.5) * 8), int((y + 0.5) * 8)) for x, y in effects.r2Sequence}
+    assert len(cells) == 64
+    W, H = 1920, 1080
+    cam = synth.Camera(aspect=W / H)
+    P0 = cam.proj.copy()
+    frame = 37
+    effects.jitter(W, H, cam, frame)
+    x, y = effects.r2Sequence[frame]
+    # a view offset of (x, y) pixels shifts the frustum: only the third column of the projection changes, by 2x/W and -2y/H (NDC per pixel)
+    assert np.allclose(cam.proj[:, [0, 1, 3]], P0[:, [0, 1, 3]])
+    assert np.isclose(cam.proj[0, 2] - P0[0, 2], 2 * x / W) and np.isclose(cam.proj[1, 2] - P0[1, 2], -2 * y / H)
+    # a point at the centre of the image moves by exactly (x, y) pixels... in the opposite direction of the window shift
+    p = np.array([0.3, -0.2, -5.0, 1.0])
+    ndc0, ndc1 = (P0 @ p)[:2] / (P0 @ p)[3], (cam.proj @ p)[:2] / (cam.proj @ p)[3]
+    assert np.allclose((ndc1 - ndc0) * np.array([W, H]) / 2, [-x, y])
+    # K2 sees the un-jittered matrix while the camera stays jittered
+    assert np.array_equal(cam.unjittered_uniforms()["projection"], synth.col_major32(P0)) and not np.array_equal(cam.proj, P0)
+    cam.clearViewOffset()
+    assert np.array_equal(cam.proj, P0)
+    effects.jitter(W, H, object(), 3)  # cameras without setViewOffset are left alone (TAAUtils.js:8)

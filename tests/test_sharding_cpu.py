@@ -27,7 +27,7 @@ def test_shard_plan_ranges():
     assert first.ranges[0][0] == 0 and last.ranges[0][1] == 2160                 # clipped at the frame border
     assert ShardPlan(2160, 1, 0, 4, 3.0).ranges == [(0, 2160)] * 7               # one GPU: whole planes
     assert ShardPlan(64, 2, 1, 0, 3.0).ranges == [(30, 64), (32, 64), (32, 64)]   # denoiseIterations = 0: K1, K2, K4 only
-    assert len(ShardPlan(64, 2, 0, 2, 3.0, ssgi_mode=False).ranges) == 4          # SSR: no K4
+    assert len(ShardPlan(64, 2, 0, 2, 3.0, ssgi_mode=False).ranges) == 5          # SSR composes too (inputType specular)
     cyc = ShardPlan(2160, 2, 1, 4, 3.0, True, 4)                                  # block-cyclic: rank 1 of 2, 4 blocks each of 270 rows
     assert cyc.blocks == [(270, 540), (810, 1080), (1350, 1620), (1890, 2160)] and cyc.super_block(2) == (1080, 1620)
     assert cyc.rows_per_rank == 1080 and len(cyc.block_ranges) == 4 and cyc.block_ranges[3][-1] == (1890, 2160)

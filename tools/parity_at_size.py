@@ -18,7 +18,6 @@ PLANES = ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed")
 
 
 def run(name, frames, variants=(True, False)):
-    variants = (True,) if "--fast-only" in sys.argv else variants
     kw = dict(CONFIGS[name])
     W, H = kw.pop("width"), kw.pop("height")
     o = ch.Opts(**kw)
@@ -54,7 +53,7 @@ if __name__ == "__main__":
         out = args[args.index("--out") + 1]
     doc = []
     for n in names:
-        r = run(n, frames)
+        r = run(n, frames, (True,) if "--fast-only" in args else (True, False))
         doc.append(r)
         for v, d in r["variants"].items():
             print(f"{n} {v}: worst frac_bad@1e-3 {d['worst_frac_bad_1e3']:.3e}  @4e-3 {d['worst_frac_bad_4e3']:.3e}  (oracle {r['oracle_s']} s)")
