@@ -215,6 +215,12 @@ rfx_status rfx_blue_noise_set(rfx_ctx* ctx, const uint8_t* rgba8_host, uint32_t 
 /* env map: uploads mip 0, builds the box-filter mip chain on the device
  * (generateMipmaps, src/ssgi/SSGIEffect.js:324-329) and uploads the CDF tables */
 rfx_status rfx_env_set(rfx_ctx* ctx, const rfx_env_desc* env);
+/* env map with the importance-sampling tables built ON THE DEVICE (replaces the reference's Web Worker:
+ * src/ssgi/utils/EquirectHdrInfoUniform.js:323-358 -> gatherData :149-245; same summation order, bit-identical tables).
+ * flip_y = texture.flipY of the source (RGBELoader sets it): the reference's in-place "un-flip" is reproduced as written */
+rfx_status rfx_env_build(rfx_ctx* ctx, const void* map_rgba16f_host, uint32_t width, uint32_t height, int32_t flip_y);
+/* host copies of the current tables: marginal[height], conditional[width*height], totalSum (any pointer may be NULL) */
+rfx_status rfx_env_tables_download(rfx_ctx* ctx, float* marginal, float* conditional, double* total_sum);
 rfx_status rfx_env_clear(rfx_ctx* ctx);
 
 /* ---- planes ------------------------------------------------------------------------ */

@@ -142,6 +142,8 @@ def _sig(lib):
     lib.rfx_blue_noise_set.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
     lib.rfx_env_set.argtypes = [vp, _P(EnvDesc)]
     lib.rfx_env_clear.argtypes = [vp]
+    lib.rfx_env_build.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int32]
+    lib.rfx_env_tables_download.argtypes = [vp, vp, vp, _P(C.c_double)]
     lib.rfx_plane_alloc.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, PP]
     lib.rfx_plane_free.argtypes = [vp, PP]
     lib.rfx_plane_clear.argtypes = [vp, vp, PP]
@@ -201,7 +203,7 @@ def _sig(lib):
 EXPORTS = [
     "rfx_ctx_create", "rfx_ctx_destroy", "rfx_last_error", "rfx_version", "rfx_ctx_stream", "rfx_ctx_sync", "rfx_launch_count",
     "rfx_ctx_set_fast_math",
-    "rfx_blue_noise_set", "rfx_env_set", "rfx_env_clear", "rfx_plane_alloc", "rfx_plane_free", "rfx_plane_clear", "rfx_plane_upload",
+    "rfx_blue_noise_set", "rfx_env_set", "rfx_env_clear", "rfx_env_build", "rfx_env_tables_download", "rfx_plane_alloc", "rfx_plane_free", "rfx_plane_clear", "rfx_plane_upload",
     "rfx_plane_download", "rfx_host_alloc", "rfx_host_free", "rfx_format_bytes", "rfx_ssgi_trace_launch",
     "rfx_temporal_reproject_launch", "rfx_poisson_denoise_launch", "rfx_gi_compose_launch", "rfx_ssgi_compose_launch", "rfx_hbao_launch",
     "rfx_ao_compose_launch", "rfx_motion_blur_launch", "rfx_traa_compose_launch", "rfx_ssgi_chain_create", "rfx_ssgi_chain_destroy",

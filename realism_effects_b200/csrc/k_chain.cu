@@ -96,81 +96,99 @@ RFX_D v2 c_reproject_hit(const CTemporalArgs& a, const CTState& s) {
   return mk2(q.x * 0.5f + 0.5f, q.y * 0.5f + 0.5f);
 }
 
-// one LINEAR fetch of plane `PL` (0 diffuse, 1 specular) of the interleaved dn history
+// one LINEAR fetch of plane `PL` (0 diffuse, 1 specular) of the interleaved dn history; channels packed as (r,g) and (b,a)
+struct H4 { f2 rg, ba; };
 template <int PL, bool PEER>
-RFX_D v4 c_hist_bilinear(const PeerPV& h, v2 uv) {
+RFX_D H4 c_hist_bilinear(const PeerPV& h, v2 uv) {
   const Bilin b = bilin_setup(uv, h.local.w, h.local.h);
   const unsigned char* r0 = PEER ? peer_row_base(h, b.y0) : h.local.p;
   const unsigned char* r1 = PEER ? peer_row_base(h, b.y1) : h.local.p;
   const unsigned o0 = (unsigned)b.y0 * (unsigned)h.local.pitch + 8u * PL, o1 = (unsigned)b.y1 * (unsigned)h.local.pitch + 8u * PL;
   const uint2 t00 = __ldg((const uint2*)(r0 + (o0 + (unsigned)b.x0 * 16u))), t10 = __ldg((const uint2*)(r0 + (o0 + (unsigned)b.x1 * 16u)));
   const uint2 t01 = __ldg((const uint2*)(r1 + (o1 + (unsigned)b.x0 * 16u))), t11 = __ldg((const uint2*)(r1 + (o1 + (unsigned)b.x1 * 16u)));
-  return mk4(bilin_blend(b, h_lo(t00.x), h_lo(t10.x), h_lo(t01.x), h_lo(t11.x)), bilin_blend(b, h_hi(t00.x), h_hi(t10.x), h_hi(t01.x), h_hi(t11.x)),
-             bilin_blend(b, h_lo(t00.y), h_lo(t10.y), h_lo(t01.y), h_lo(t11.y)), bilin_blend(b, h_hi(t00.y), h_hi(t10.y), h_hi(t01.y), h_hi(t11.y)));
+#define C_BL(M) f2fma(mkf2(h_lo(t11.M), h_hi(t11.M)), mkf2(b.w11), f2fma(mkf2(h_lo(t01.M), h_hi(t01.M)), mkf2(b.w01), \
+                f2fma(mkf2(h_lo(t10.M), h_hi(t10.M)), mkf2(b.w10), f2mul(mkf2(h_lo(t00.M), h_hi(t00.M)), mkf2(b.w00)))))
+  H4 r;
+  r.rg = C_BL(x); r.ba = C_BL(y);
+#undef C_BL
+  return r;
 }
 
 // BiCubicCatmullRom5Tap  reproject.frag:212-255 (texel choice: IEEE; weights: SFU reciprocals)
 template <int PL, bool PEER>
-RFX_D v4 c_catmull5(const CTemporalArgs& a, v2 P) {
+RFX_D H4 c_catmull5(const CTemporalArgs& a, v2 P) {
   const v2 inv = mk2(a.inv_w, a.inv_h);
   const v2 UV = mk2(P.x / inv.x, P.y / inv.y);
   const v2 tc = mk2(floorf(UV.x - 0.5f) + 0.5f, floorf(UV.y - 0.5f) + 0.5f);
   const v2 f = UV - tc;
-  const v2 f2 = f * f;
-  const v2 f3 = f2 * f;
-  const v2 w0 = f2 - 0.5f * (f3 + f);
-  const v2 w1 = 1.5f * f3 - 2.5f * f2 + mk2(1.0f, 1.0f);
-  const v2 w3 = 0.5f * (f3 - f2);
+  const v2 f2_ = f * f;
+  const v2 f3 = f2_ * f;
+  const v2 w0 = f2_ - 0.5f * (f3 + f);
+  const v2 w1 = 1.5f * f3 - 2.5f * f2_ + mk2(1.0f, 1.0f);
+  const v2 w3 = 0.5f * (f3 - f2_);
   const v2 w2 = mk2(1.0f, 1.0f) - w0 - w1 - w3;
   const v2 W0 = w0, W1 = w1 + w2, W2 = w3;
   const v2 S0 = (tc - mk2(1.0f, 1.0f)) * inv, S1 = mk2((tc.x + w2.x * fx_rcp(W1.x)) * inv.x, (tc.y + w2.y * fx_rcp(W1.y)) * inv.y), S2 = (tc + mk2(2.0f, 2.0f)) * inv;
   const float sw0 = W1.x * W0.y, sw1 = W0.x * W1.y, sw2 = W1.x * W1.y, sw3 = W2.x * W1.y, sw4 = W1.x * W2.y;
-  const v4 Ct = c_hist_bilinear<PL, PEER>(a.hist, mk2(S1.x, S0.y)), Cl = c_hist_bilinear<PL, PEER>(a.hist, mk2(S0.x, S1.y)),
+  const H4 Ct = c_hist_bilinear<PL, PEER>(a.hist, mk2(S1.x, S0.y)), Cl = c_hist_bilinear<PL, PEER>(a.hist, mk2(S0.x, S1.y)),
            Cc = c_hist_bilinear<PL, PEER>(a.hist, mk2(S1.x, S1.y)), Cr = c_hist_bilinear<PL, PEER>(a.hist, mk2(S2.x, S1.y)),
            Cb = c_hist_bilinear<PL, PEER>(a.hist, mk2(S1.x, S2.y));
-  const float wm = fx_rcp(sw0 + sw1 + sw2 + sw3 + sw4);
-  v4 r;
-  r.x = fmaxf(fma_(Cb.x, sw4, fma_(Cr.x, sw3, fma_(Cc.x, sw2, fma_(Cl.x, sw1, Ct.x * sw0)))) * wm, 0.0f);
-  r.y = fmaxf(fma_(Cb.y, sw4, fma_(Cr.y, sw3, fma_(Cc.y, sw2, fma_(Cl.y, sw1, Ct.y * sw0)))) * wm, 0.0f);
-  r.z = fmaxf(fma_(Cb.z, sw4, fma_(Cr.z, sw3, fma_(Cc.z, sw2, fma_(Cl.z, sw1, Ct.z * sw0)))) * wm, 0.0f);
-  r.w = fmaxf(fma_(Cb.w, sw4, fma_(Cr.w, sw3, fma_(Cc.w, sw2, fma_(Cl.w, sw1, Ct.w * sw0)))) * wm, 0.0f);
+  const f2 wm = mkf2(fx_rcp(sw0 + sw1 + sw2 + sw3 + sw4));
+  const f2 rg = f2mul(f2fma(Cb.rg, mkf2(sw4), f2fma(Cr.rg, mkf2(sw3), f2fma(Cc.rg, mkf2(sw2), f2fma(Cl.rg, mkf2(sw1), f2mul(Ct.rg, mkf2(sw0)))))), wm);
+  const f2 ba = f2mul(f2fma(Cb.ba, mkf2(sw4), f2fma(Cr.ba, mkf2(sw3), f2fma(Cc.ba, mkf2(sw2), f2fma(Cl.ba, mkf2(sw1), f2mul(Ct.ba, mkf2(sw0)))))), wm);
+  H4 r;
+  r.rg = mkf2(fmaxf(f2lo(rg), 0.0f), fmaxf(f2hi(rg), 0.0f));
+  r.ba = mkf2(fmaxf(f2lo(ba), 0.0f), fmaxf(f2hi(ba), 0.0f));
   return r;
 }
 
-template <int PL, bool PEER>
-RFX_D float4 c_temporal_plane(const CTemporalArgs& a, const CTState& s, v3 uvc, v4 inp, bool sampled, v3 mn, v3 mx) {
-  constexpr bool spec = PL == 1;
-  // reproject()  temporal_reproject.frag:83-122
-  const v4 acc = c_catmull5<PL, PEER>(a, mk2(uvc.x, uvc.y));
-  v3 accRgb = c_log1p(xyz(acc));
-  float accA = acc.w;
-  v3 inRgb = xyz(inp);
-  if (!sampled) {
-    inRgb = accRgb;
-  } else {
-    accA += 1.0f;
-    const v3 lo = c_log1p(mn), hi = c_log1p(mx);
-    const v3 clamped = mk3(clampf(accRgb.x, lo.x, hi.x), clampf(accRgb.y, lo.y, hi.y), clampf(accRgb.z, lo.z, hi.z));
-    const float r = spec ? s.roughness : 1.0f;
-    const float clampAggressiveness = fminf(1.0f, uvc.z * r);
-    const float clampIntensity = fminf(1.0f, fma_(s.moveFactor, 50.0f, a.clamp_intensity)) * clampAggressiveness;  // mix(0., x, t) = x*t
-    const v3 newColor = mix(accRgb, clamped, clampIntensity);
-    const float colorDiff = fminf(fx_length(newColor - accRgb), 1.0f);
-    accA *= 1.0f - colorDiff;
-    accRgb = newColor;
+// reproject() + accumulate() (temporal_reproject.frag:83-122, 42-79) for BOTH planes at once: every quantity is a packed pair
+// (.lo = diffuse plane, .hi = specular plane), so the arithmetic the two planes share issues as FFMA2 / FMUL2 / FADD2.
+RFX_D f2 p_log1p(f2 c) { return f2mul(f2lg2(f2add(c, mkf2(1.0f))), mkf2(C_LN2)); }
+RFX_D f2 p_expm1(f2 c) { return f2sub(f2ex2(f2mul(c, mkf2(C_LOG2E))), mkf2(1.0f)); }
+RFX_D f2 p_min(f2 a, f2 b) { return mkf2(fminf(f2lo(a), f2lo(b)), fminf(f2hi(a), f2hi(b))); }
+RFX_D f2 p_max(f2 a, f2 b) { return mkf2(fmaxf(f2lo(a), f2lo(b)), fmaxf(f2hi(a), f2hi(b))); }
+RFX_D f2 p_sel(bool s0, bool s1, f2 a, f2 b) { return mkf2(s0 ? f2lo(a) : f2lo(b), s1 ? f2hi(a) : f2hi(b)); }
+RFX_D f2 p_rcp(f2 a) { return mkf2(fx_rcp(f2lo(a)), fx_rcp(f2hi(a))); }
+RFX_D f2 p_mix(f2 x, f2 y, f2 t, f2 omt) { return f2fma(y, t, f2mul(x, omt)); }  // mix(x, y, t) with omt = 1 - t
+
+template <bool PEER>
+RFX_D void c_temporal_planes(const CTemporalArgs& a, const CTState& s, v3 ruvD, v3 ruvS, const v4* inp, const bool* sampled, const v3* mn, const v3* mx, float4& out0, float4& out1) {
+  const H4 h0 = c_catmull5<0, PEER>(a, mk2(ruvD.x, ruvD.y)), h1 = c_catmull5<1, PEER>(a, mk2(ruvS.x, ruvS.y));
+  const f2 one = mkf2(1.0f);
+  f2 accR = p_log1p(mkf2(f2lo(h0.rg), f2lo(h1.rg))), accG = p_log1p(mkf2(f2hi(h0.rg), f2hi(h1.rg))), accB = p_log1p(mkf2(f2lo(h0.ba), f2lo(h1.ba)));
+  f2 accA = mkf2(f2hi(h0.ba), f2hi(h1.ba));
+  const f2 conf = mkf2(ruvD.z, ruvS.z);
+  const bool s0 = sampled[0], s1 = sampled[1];
+  f2 inR = mkf2(inp[0].x, inp[1].x), inG = mkf2(inp[0].y, inp[1].y), inB = mkf2(inp[0].z, inp[1].z);
+  {  // sampled this frame: clamp the history towards the neighbourhood AABB (always evaluated; selected per plane below)
+    const f2 loR = p_log1p(mkf2(mn[0].x, mn[1].x)), loG = p_log1p(mkf2(mn[0].y, mn[1].y)), loB = p_log1p(mkf2(mn[0].z, mn[1].z));
+    const f2 hiR = p_log1p(mkf2(mx[0].x, mx[1].x)), hiG = p_log1p(mkf2(mx[0].y, mx[1].y)), hiB = p_log1p(mkf2(mx[0].z, mx[1].z));
+    const f2 clR = p_min(p_max(accR, loR), hiR), clG = p_min(p_max(accG, loG), hiG), clB = p_min(p_max(accB, loB), hiB);
+    const f2 aggr = p_min(one, f2mul(conf, mkf2(1.0f, s.roughness)));
+    const f2 ci = f2mul(mkf2(fminf(1.0f, fma_(s.moveFactor, 50.0f, a.clamp_intensity))), aggr);
+    const f2 omci = f2sub(one, ci);
+    const f2 nR = p_mix(accR, clR, ci, omci), nG = p_mix(accG, clG, ci, omci), nB = p_mix(accB, clB, ci, omci);
+    const f2 dR = f2sub(nR, accR), dG = f2sub(nG, accG), dB = f2sub(nB, accB);
+    const f2 l2 = f2fma(dB, dB, f2fma(dG, dG, f2mul(dR, dR)));
+    const f2 cd = p_min(mkf2(fx_sqrt(f2lo(l2)), fx_sqrt(f2hi(l2))), one);
+    const f2 accAs = f2mul(f2add(accA, one), f2sub(one, cd));
+    // not sampled: inputTexel.rgb = accumulatedTexel.rgb, history untouched
+    inR = p_sel(s0, s1, inR, accR); inG = p_sel(s0, s1, inG, accG); inB = p_sel(s0, s1, inB, accB);
+    accR = p_sel(s0, s1, nR, accR); accG = p_sel(s0, s1, nG, accG); accB = p_sel(s0, s1, nB, accB);
+    accA = p_sel(s0, s1, accAs, accA);
   }
-  // accumulate()  temporal_reproject.frag:42-79
-  const float confidence = c_pow(uvc.z, a.confidence_power);
-  const float accumBlend = (1.0f - fx_rcp(accA + 1.0f)) * confidence;
-  float maxValue = (a.full_accumulate ? 1.0f : a.max_blend) * a.keep_data;
-  if (spec && s.roughness >= 0.0f && s.roughness < 0.1f) {
-    const float maxRoughnessValue = maxValue * (s.roughness * 10.0f);
-    maxValue = mixf(maxValue, maxRoughnessValue, fminf(100.0f * s.moveFactor, 1.0f));
-  }
-  const float tmix = fminf(accumBlend, maxValue);
-  const float oa = fminf(65536.0f, fx_rcp(1.0f - tmix) - 1.0f);
-  const v3 orgb = c_expm1(mix(inRgb, accRgb, tmix));
-  return make_float4(orgb.x, orgb.y, orgb.z, oa);
+  const f2 confidence = f2ex2(f2mul(f2lg2(conf), mkf2(a.confidence_power)));
+  const f2 accumBlend = f2mul(f2sub(one, p_rcp(f2add(accA, one))), confidence);
+  const float mv = (a.full_accumulate ? 1.0f : a.max_blend) * a.keep_data;
+  float mvS = mv;
+  if (s.roughness >= 0.0f && s.roughness < 0.1f) mvS = mixf(mv, mv * (s.roughness * 10.0f), fminf(100.0f * s.moveFactor, 1.0f));
+  const f2 tmix = p_min(accumBlend, mkf2(mv, mvS));
+  const f2 omt = f2sub(one, tmix);
+  const f2 oa = p_min(mkf2(65536.0f), f2sub(p_rcp(omt), one));
+  const f2 oR = p_expm1(p_mix(inR, accR, tmix, omt)), oG = p_expm1(p_mix(inG, accG, tmix, omt)), oB = p_expm1(p_mix(inB, accB, tmix, omt));
+  out0 = make_float4(f2lo(oR), f2lo(oG), f2lo(oB), f2lo(oa));
+  out1 = make_float4(f2hi(oR), f2hi(oG), f2hi(oB), f2hi(oa));
 }
 
 template <bool PEER>
@@ -254,8 +272,10 @@ __global__ void __launch_bounds__(kThreads, 4) ctemporal_kernel(const __grid_con
     }
   }
   float4* o = (float4*)(a.out.p + ((unsigned)y * (unsigned)a.out.pitch + (unsigned)x * 32u));
-  o[0] = c_temporal_plane<0, PEER>(a, s, ruvD, inp[0], sampled[0], mn[0], mx[0]);
-  o[1] = c_temporal_plane<1, PEER>(a, s, ruvS, inp[1], sampled[1], mn[1], mx[1]);
+  float4 o0, o1;
+  c_temporal_planes<PEER>(a, s, ruvD, ruvS, inp, sampled, mn, mx, o0, o1);
+  o[0] = o0;
+  o[1] = o1;
 }
 
 cudaError_t launch_ctemporal(const CTemporalArgs& a, cudaStream_t s) {
@@ -324,10 +344,12 @@ RFX_D float cp_lum(v3 c2) { return fx_ex2(fma_(0.125f, fx_lg2(dot(mk3(0.2125f, 0
 
 // The two planes ride in the two halves of packed fp32x2 registers (f2: .lo = diffuse plane, .hi = specular plane).
 struct CTexel2 { f2 r, g, b, a; };
+// TMA-staged tile of this block (cpoisson_tma_kernel): texel (x, y) of `in` / `nrdz` lives at ((y - y0) * bw + (x - x0)) * 16
+struct SmemTile { const unsigned char* in; const unsigned char* nrdz; int x0, y0, bw; };
 // INTERIOR: every tap of this block stays inside the image, so no index is clamped and the four bilinear corners are
 // p, p + 16, p + pitch, p + pitch + 16 (immediate offsets off two address computations).
-template <bool FIRST, bool ALPHA, bool INTERIOR>
-RFX_D CTexel2 cp_fetch(const CPoissonArgs& a, float fxn, float fyn, int nx, int ny) {
+template <bool FIRST, bool ALPHA, bool INTERIOR, bool SMEM = false>
+RFX_D CTexel2 cp_fetch(const CPoissonArgs& a, float fxn, float fyn, int nx, int ny, const SmemTile& st) {
   CTexel2 t;
   t.a = mkf2(0.0f);
   if (FIRST) {  // NEAREST fp32 pair
@@ -342,7 +364,11 @@ RFX_D CTexel2 cp_fetch(const CPoissonArgs& a, float fxn, float fyn, int nx, int 
     const float ax = fx - x0f, ay = fy - y0f;
     const float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
     uint4 t00, t10, t01, t11;
-    if (INTERIOR) {
+    if (SMEM) {  // the four corners from the staged tile (LDS.128)
+      const unsigned char* p0 = st.in + (((iy - st.y0) * st.bw + (ix - st.x0)) << 4);
+      const unsigned char* p1 = p0 + (st.bw << 4);
+      t00 = *(const uint4*)p0; t10 = *(const uint4*)(p0 + 16); t01 = *(const uint4*)p1; t11 = *(const uint4*)(p1 + 16);
+    } else if (INTERIOR) {
       const unsigned char* p0 = a.in.p + ((unsigned)iy * (unsigned)a.in.pitch + (unsigned)ix * 16u);
       const unsigned char* p1 = p0 + a.in.pitch;
       t00 = __ldg((const uint4*)p0); t10 = __ldg((const uint4*)(p0 + 16)); t01 = __ldg((const uint4*)p1); t11 = __ldg((const uint4*)(p1 + 16));
@@ -366,8 +392,8 @@ RFX_D f2 cp_lum2(f2 r, f2 g, f2 b) {  // luminance(): pow(dot(w, c), 0.125) on l
   return f2ex2(f2fma(f2lg2(d), mkf2(0.125f), mkf2(CP_LUM_C)));
 }
 
-template <bool FIRST, bool COMPOSE, bool INTERIOR>
-RFX_D void cpoisson_body(const CPoissonArgs& a, int x, int y, float4 nc, float fwn) {
+template <bool FIRST, bool COMPOSE, bool INTERIOR, bool SMEM = false>
+RFX_D void cpoisson_body(const CPoissonArgs& a, int x, int y, float4 nc, float fwn, const SmemTile& st = SmemTile{}) {
   const v2 vUv = pixel_uv(x, y, a.W, a.H);
   const float depth = nc.w;
   const v3 normal = mk3(nc.x, nc.y, nc.z);
@@ -375,7 +401,7 @@ RFX_D void cpoisson_body(const CPoissonArgs& a, int x, int y, float4 nc, float f
   const float resx = (float)a.W, resy = (float)a.H;
   f2 accr, accg, accb, tw = mkf2(1.0f), lumc, age, alpha;
   {
-    const CTexel2 c = cp_fetch<FIRST, true, INTERIOR>(a, vUv.x * resx, vUv.y * resy, x, y);
+    const CTexel2 c = cp_fetch<FIRST, true, INTERIOR, SMEM>(a, vUv.x * resx, vUv.y * resy, x, y, st);
     alpha = c.a;
     age = f2ex2(f2mul(f2lg2(f2add(alpha, mkf2(1.0f))), mkf2(-1.2f * a.phi)));
     accr = f2lg2(f2fma(c.r, mkf2(1.0003f), mkf2(1.0f))); accg = f2lg2(f2fma(c.g, mkf2(1.0003f), mkf2(1.0f))); accb = f2lg2(f2fma(c.b, mkf2(1.0003f), mkf2(1.0f)));
@@ -401,14 +427,14 @@ RFX_D void cpoisson_body(const CPoissonArgs& a, int x, int y, float4 nc, float f
     const float fxn = nuv.x * resx, fyn = nuv.y * resy;
     int nx = floor_i(fxn), ny = floor_i(fyn);
     if (!INTERIOR) { nx = clamp_idx(nx, a.W - 1); ny = clamp_idx(ny, a.H - 1); }
-    const float4 nn = ld_f4(a.nrdz, nx, ny);
+    const float4 nn = SMEM ? *(const float4*)(st.nrdz + (((ny - st.y0) * st.bw + (nx - st.x0)) << 4)) : ld_f4(a.nrdz, nx, ny);
     if (nn.w == 1.0f) continue;  // background tap: wBasic = 0
     const float normalDiff = 1.0f - fmaxf(dot(normal, mk3(nn.x, nn.y, nn.z)), 0.0f);
     const float depthDiff = 10000.0f * fabsf(depth - nn.w);
     const float roughnessDiff = fabsf(roughness - nrdz_roughness(nn));
     const float A2 = (-normalDiff * a.normal_phi - depthDiff * a.depth_phi - roughnessDiff * a.roughness_phi) * C_LOG2E;
     const float wdA = fx_ex2(A2 * 0.1f);
-    const CTexel2 c = cp_fetch<FIRST, false, INTERIOR>(a, fxn, fyn, nx, ny);
+    const CTexel2 c = cp_fetch<FIRST, false, INTERIOR, SMEM>(a, fxn, fyn, nx, ny, st);
     const f2 lr = f2lg2(f2add(c.r, mkf2(1.0f))), lg = f2lg2(f2add(c.g, mkf2(1.0f))), lb = f2lg2(f2add(c.b, mkf2(1.0f)));
     const f2 dl = f2sub(lumc, cp_lum2(lr, lg, lb));
     const f2 lumaDiff = mkf2(fminf(fabsf(f2lo(dl)), 0.5f), fminf(fabsf(f2hi(dl)), 0.5f));
@@ -467,6 +493,93 @@ cudaError_t launch_cpoisson(const CPoissonArgs& a, cudaStream_t s) {
   dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   if (a.first) { if (a.compose) cpoisson_kernel<true, true><<<grid, kThreads, 0, s>>>(a); else cpoisson_kernel<true, false><<<grid, kThreads, 0, s>>>(a); }
   else { if (a.compose) cpoisson_kernel<false, true><<<grid, kThreads, 0, s>>>(a); else cpoisson_kernel<false, false><<<grid, kThreads, 0, s>>>(a); }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K3 passes >= 1 with TMA staging (the experiment BASELINE.json's north_star asks for): an interior block stages the
+// (16 + 2 reach_x) x (16 + 2 reach_y) texel tiles of `in` and `nrdz` its taps can touch into shared memory with two
+// cp.async.bulk.tensor.2d loads completing on one mbarrier, then every tap reads LDS.128 instead of LDG.128.  Border blocks
+// (TMA fills out-of-range texels with zeros, the samplers clamp to the edge) take the global path.  Same arithmetic, same
+// bytes out.  Selected with RFX_K3_TMA=1; measured A/B in profiles/r02_tma_experiment.txt.
+// ------------------------------------------------------------------------------------------------------------------
+RFX_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+RFX_D void mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+RFX_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+RFX_D void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+RFX_D void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool COMPOSE>
+__global__ void __launch_bounds__(kThreads, 4) cpoisson_tma_kernel(const __grid_constant__ CPoissonTmaArgs t) {
+  extern __shared__ __align__(1024) unsigned char tile[];
+  __shared__ unsigned long long bar;
+  const CPoissonArgs& a = t.a;
+  int x, y;
+  const bool in_rows = seg_pixel(a.segs, x, y);
+  const bool active = x < a.W && y < a.H && in_rows;
+  int lx, ly;
+  lane_to_pixel(threadIdx.x & 31, lx, ly);
+  const int bx0 = blockIdx.x * kTileW, by0 = y - ((int)((threadIdx.x >> 6) << 2) + ly);
+  // block-uniform: every texel of the staged tile exists (no clamping anywhere in this block)
+  const bool interior = bx0 - a.reach_x >= 0 && bx0 + kTileW - 1 + a.reach_x <= a.W - 1 && by0 - a.reach_y >= 0 && by0 + kTileH - 1 + a.reach_y <= a.H - 1;
+  SmemTile st{};
+  if (interior) {
+    const unsigned tile_bytes = (unsigned)t.box_w * (unsigned)t.box_h * 16u;
+    const unsigned off2 = (tile_bytes + 127u) & ~127u;  // TMA destinations are 128-byte aligned
+    st.in = tile; st.nrdz = tile + off2; st.x0 = bx0 - a.reach_x; st.y0 = by0 - a.reach_y; st.bw = t.box_w;
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, 2u * tile_bytes);
+      tma_load_2d(tile, &t.map_in, st.x0 * 4, st.y0, &bar);                  // coordinates in 4-byte elements: 4 per 16-byte texel
+      tma_load_2d(tile + off2, &t.map_nrdz, st.x0 * 4, st.y0, &bar);
+    }
+  }
+  const int xc = min(x, a.W - 1), yc = min(y, a.H - 1);
+  const float4 nc = ld_f4(a.nrdz, xc, yc);
+  const float depth = nc.w;
+  const float fwd = fwidth_f(depth);
+  const float fwn = fx_length(fwidth_3(mk3(nc.x, nc.y, nc.z)));
+  if (interior) mbar_wait(&bar, 0);  // every thread waits (also the ones that leave below): the tile must have landed before the block can retire
+  if (!active) return;
+  if (depth == 1.0f && fwd == 0.0f) {
+    if (a.carry.local.p) {
+      const unsigned off = (unsigned)y * (unsigned)a.carry.local.pitch + (unsigned)x * 16u;
+      *((uint4*)(a.out.p + ((unsigned)y * (unsigned)a.out.pitch + (unsigned)x * 16u))) = *((const uint4*)(peer_row_base(a.carry, y) + off));
+    }
+    if (COMPOSE && a.composed_carry.local.p && in_segs(a.csegs, y)) {
+      const unsigned off = (unsigned)y * (unsigned)a.composed_carry.local.pitch + (unsigned)x * 16u;
+      st_f4(a.composed.p, a.composed.pitch, x, y, *((const float4*)(peer_row_base(a.composed_carry, y) + off)));
+    }
+    return;
+  }
+  if (interior) cpoisson_body<false, COMPOSE, true, true>(a, x, y, nc, fwn, st);
+  else cpoisson_body<false, COMPOSE, false, false>(a, x, y, nc, fwn);
+}
+
+cudaError_t launch_cpoisson_tma(const CPoissonTmaArgs& t, cudaStream_t s) {
+  dim3 grid((t.a.W + kTileW - 1) / kTileW, t.a.segs.tiles);
+  const size_t tile_bytes = (size_t)t.box_w * t.box_h * 16, smem = ((tile_bytes + 127) & ~(size_t)127) + tile_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(cpoisson_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(cpoisson_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  if (smem > 100 * 1024) return cudaErrorInvalidValue;
+  if (t.a.compose) cpoisson_tma_kernel<true><<<grid, kThreads, smem, s>>>(t); else cpoisson_tma_kernel<false><<<grid, kThreads, smem, s>>>(t);
   return cudaGetLastError();
 }
 

@@ -177,4 +177,68 @@ cudaError_t launch_env_downsample(PV src, OutV dst, int w1, int h1, cudaStream_t
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Env-map importance-sampling tables on the device: restates `gatherData`
+// (src/ssgi/utils/EquirectHdrInfoUniform.js:149-245) with the SAME summation order as the JS loops — every accumulator is a JS
+// double advanced pixel after pixel — so the tables are bit-identical to the worker's: one thread walks one row (rows are
+// independent), one thread walks the global sums (two dependent chains of W*H and H doubles: ~5 ms for 1024x512, once per
+// environment change; the reference spends ~100 ms in a Web Worker), then every inverse-CDF entry is an independent binary search.
+// flipY: the reference "un-flips" IN PLACE (row y -> row h-1-y for y = 0..h-1), which mirrors the top half over the bottom half
+// (SURVEY.md A4): the source row of row r is min(r, h-1-r).
+// ------------------------------------------------------------------------------------------------------------------------
+RFX_D double env_weight(const PV& map, int x, int row) {  // colorToLuminance on the fp16 texel widened to fp32 (DataUtils.fromHalfFloat)
+  const uint2 t = __ldg((const uint2*)(map.p + ((long long)row * map.pitch + (long long)x * 8)));
+  const double r = (double)h_lo(t.x), g = (double)h_hi(t.x), b = (double)h_lo(t.y);
+  return __dadd_rn(__dadd_rn(__dmul_rn(0.2126, r), __dmul_rn(0.7152, g)), __dmul_rn(0.0722, b));
+}
+__global__ void env_row_scan_kernel(PV map, int flip_y, float* cdf_c, double* row_sum) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= map.h) return;
+  const int src = flip_y ? min(y, map.h - 1 - y) : y;
+  double cum = 0.0;
+  float* out = cdf_c + (size_t)y * map.w;
+  for (int x = 0; x < map.w; x++) {
+    cum = __dadd_rn(cum, env_weight(map, x, src));
+    out[x] = (float)cum;                                   // cdfConditional[i] = cumulativeRowWeight (Float32Array store)
+  }
+  row_sum[y] = cum;
+  if (cum != 0.0)
+    for (int x = 0; x < map.w; x++) out[x] = (float)((double)out[x] / cum);   // cdfConditional[i] /= cumulativeRowWeight
+}
+__global__ void env_totals_kernel(PV map, int flip_y, const double* row_sum, float* cdf_m, double* total_out) {
+  if (blockIdx.x || threadIdx.x) return;
+  double total = 0.0;
+  for (int y = 0; y < map.h; y++) {                         // totalSumValue += weight, pixel after pixel in row-major order
+    const int src = flip_y ? min(y, map.h - 1 - y) : y;
+    for (int x = 0; x < map.w; x++) total = __dadd_rn(total, env_weight(map, x, src));
+  }
+  *total_out = total;
+  double cum = 0.0;
+  for (int y = 0; y < map.h; y++) { cum = __dadd_rn(cum, row_sum[y]); cdf_m[y] = (float)cum; }
+  if (cum != 0.0)
+    for (int y = 0; y < map.h; y++) cdf_m[y] = (float)((double)cdf_m[y] / cum);
+}
+RFX_D int env_closest(const float* a, double target, int count) {  // binarySearchFindClosestIndexOf :130-147
+  int lower = 0, upper = count - 1;
+  while (lower < upper) {
+    const int mid = (lower + upper) >> 1;
+    if ((double)a[mid] < target) lower = mid + 1; else upper = mid;
+  }
+  return lower;
+}
+__global__ void env_inverse_cdf_kernel(const float* cdf_m, const float* cdf_c, int W, int H, float* marginal, float* conditional) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H) marginal[i] = (float)(((double)env_closest(cdf_m, (double)(i + 1) / (double)H, H) + 0.5) / (double)H);
+  if (i < W * H) {
+    const int y = i / W, x = i - y * W;
+    conditional[i] = (float)(((double)env_closest(cdf_c + (size_t)y * W, (double)(x + 1) / (double)W, W) + 0.5) / (double)W);
+  }
+}
+cudaError_t launch_env_cdf(PV map, int flip_y, float* cdf_c, float* cdf_m, double* row_sum, double* total, float* marginal, float* conditional, cudaStream_t s) {
+  env_row_scan_kernel<<<(map.h + 63) / 64, 64, 0, s>>>(map, flip_y, cdf_c, row_sum);
+  env_totals_kernel<<<1, 1, 0, s>>>(map, flip_y, row_sum, cdf_m, total);
+  env_inverse_cdf_kernel<<<(map.w * map.h + 255) / 256, 256, 0, s>>>(cdf_m, cdf_c, map.w, map.h, marginal, conditional);
+  return cudaGetLastError();
+}
+
 }  // namespace rfx

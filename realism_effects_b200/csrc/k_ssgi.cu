@@ -594,26 +594,33 @@ RFX_D v3 fma3(v3 d, float s, v3 p) {
   const f2 xy = f2fma(mkf2(d.x, d.y), mkf2(s), mkf2(p.x, p.y));
   return mk3(f2lo(xy), f2hi(xy), fma_(d.z, s, p.z));
 }
-// RayMarch + BinarySearch  ssgi.frag:441-503.  The ray positions do not depend on the fetched depths, so two steps are projected
+// RayMarch + BinarySearch  ssgi.frag:441-503.  The ray positions do not depend on the fetched depths, so BATCH steps are projected
 // and fetched together and tested in order: the march is a chain of dependent L2-latency gathers (L1 hit ~50 %), and at ~25
-// instructions per tap the other resident warps no longer hide that latency on their own (one wasted tap per hit at most).
-template <bool SPARSE>
+// instructions per tap the other resident warps no longer hide that latency on their own (at most BATCH - 1 wasted taps per hit).
+// BATCH is picked at run time (SsgiArgs::march_batch; RFX_K1_BATCH in the environment) from {1, 2, 4}: profiles/r02_k1_batch.txt.
+template <bool SPARSE, int BATCH>
 RFX_D v2 march_fast(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hit) {
   dir = dir * (a.ray_distance / (float)a.steps);
   hit = false;
-  const float* cs_row = a.step_table + noiseB;  // row i-1 holds cs(i, b); the table carries one spare row for the speculative read
+  const float* cs_row = a.step_table + noiseB;  // row i-1 holds cs(i, b); the table carries BATCH spare rows for the speculative reads
   v3 p = hitPos;
-  for (int i = 1; i < a.steps; i += 2, cs_row += 512) {
-    const v3 p1 = fma3(dir, __ldg(cs_row), p);
-    const v3 p2 = fma3(dir, __ldg(cs_row + 256), p1);
-    const float z1 = tap_viewz<SPARSE>(a, p1), z2 = tap_viewz<SPARSE>(a, p2);
-    const float d1 = z1 - p1.z, d2 = z2 - p2.z;
-    if (d1 >= 0.0f && d1 < a.thickness) { hit = true; p = p1; break; }
-    if (i + 1 < a.steps) {
-      p = p2;
-      if (d2 >= 0.0f && d2 < a.thickness) { hit = true; break; }
-    } else {
-      p = p1;
+  for (int i = 1; i < a.steps && !hit; i += BATCH, cs_row += 256 * BATCH) {
+    v3 q[BATCH];
+    float z[BATCH];
+    v3 t = p;
+#pragma unroll
+    for (int k = 0; k < BATCH; k++) {  // BATCH steps are projected and fetched together ...
+      t = fma3(dir, __ldg(cs_row + 256 * k), t);
+      q[k] = t;
+      z[k] = tap_viewz<SPARSE>(a, t);
+    }
+#pragma unroll
+    for (int k = 0; k < BATCH; k++) {  // ... and tested in order
+      if (!hit && i + k < a.steps) {
+        p = q[k];
+        const float d = z[k] - q[k].z;
+        hit = d >= 0.0f && d < a.thickness;
+      }
     }
   }
   if (!hit) {
@@ -634,7 +641,7 @@ RFX_D v2 march_fast(const SsgiArgs& a, v3& dir, v3& hitPos, int noiseB, bool& hi
 }
 
 // doSample  ssgi.frag:362-439 (SFU arithmetic; `desat` = (1 - roughnessSq) * saturation(diffuse) * 0.4)
-template <bool SPARSE, bool PEER>
+template <bool SPARSE, bool PEER, int BATCH>
 RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughnessSq, float metalness, float desat, bool isDiffuseSample, bool isEnvSample, float NoV,
                      float NoL, float NoH, float LoH, int noiseB, v3 l, v3& hitPos, float& brdf, float& pdf) {
   const float cosTheta = fmaxf(0.0f, dot(viewNormal, l));
@@ -649,7 +656,7 @@ RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughne
   pdf = fmaxf(SSGI_EPSILON, pdf);
   hitPos = viewPos;
   bool hit;
-  const v2 coords = march_fast<SPARSE>(a, l, hitPos, noiseB, hit);
+  const v2 coords = march_fast<SPARSE, BATCH>(a, l, hitPos, noiseB, hit);
   const bool allowMissedRays = (a.flags & RFX_SSGI_MISSED_RAYS) != 0;
   if (!hit && !allowMissedRays) return getEnvColor<true, true>(a, l, roughnessSq, isDiffuseSample, isEnvSample);
   v2 vel = mk2(0.0f, 0.0f);
@@ -681,7 +688,7 @@ RFX_D v3 sample_fast(const SsgiArgs& a, v3 viewPos, v3 viewNormal, float roughne
   return SSGI;
 }
 
-template <int MODE, bool IS, bool SPARSE, bool PEER>
+template <int MODE, bool IS, bool SPARSE, bool PEER, int BATCH>
 __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_fast_kernel(const __grid_constant__ SsgiArgs a) {
   int x, y;
   const bool in_rows = seg_pixel(a.segs, x, y);
@@ -786,14 +793,14 @@ __global__ void __launch_bounds__(kThreads, RFX_K1_MIN_BLOCKS) ssgi_fast_kernel(
   if (MODE == RFX_MODE_SSGI && isDiffuseSample) {  // :222-242
     const v3 dray = emsIsEnvSample ? envMisDir : cosineSampleHemisphere_cs<true>(viewNormal, random.x, sc.x, sc.y);
     calculateAngles<true>(dray, v, n, NoL, NoH, LoH, VoH);
-    v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, dray, hitPos, brdf, pdf);
+    v3 gi = sample_fast<SPARSE, PEER, BATCH>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, true, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, dray, hitPos, brdf, pdf);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
     diffuseGI = gi * inv_ems;
   }
   calculateAngles<true>(l, v, n, NoL, NoH, LoH, VoH);  // the specular ray :246-265
   {
-    v3 gi = sample_fast<SPARSE, PEER>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
+    v3 gi = sample_fast<SPARSE, PEER, BATCH>(a, viewPos, viewNormal, roughnessSq, m.metalness, desat, isDiffuseSample, emsIsEnvSample, NoV, NoL, NoH, LoH, bn.z, l, hitPos, brdf, pdf);
     gi = gi * brdf;
     if (emsIsEnvSample) { const float aa = emsPdf * emsPdf, bb = pdf * pdf; gi = gi * div_<true>(aa, aa + bb); } else gi = vdiv_<true>(gi, pdf);
     specularGI = gi * inv_ems;
@@ -825,8 +832,12 @@ static void launch_ssgi_t(const SsgiArgs& a, dim3 grid, cudaStream_t s) {
 #define RFX_K1_LAUNCH(SP, F, PH) ssgi_kernel<MODE, IS, SP, F, PH><<<grid, kThreads, 0, s>>>(a)
   if (a.phase == 0 && a.fast && !a.legacy_fast) {
     const bool peer = a.acc_peer.n > 1;
-    if (a.proj_sparse) { if (peer) ssgi_fast_kernel<MODE, IS, true, true><<<grid, kThreads, 0, s>>>(a); else ssgi_fast_kernel<MODE, IS, true, false><<<grid, kThreads, 0, s>>>(a); }
-    else { if (peer) ssgi_fast_kernel<MODE, IS, false, true><<<grid, kThreads, 0, s>>>(a); else ssgi_fast_kernel<MODE, IS, false, false><<<grid, kThreads, 0, s>>>(a); }
+#define RFX_K1F(SP, PE, BA) ssgi_fast_kernel<MODE, IS, SP, PE, BA><<<grid, kThreads, 0, s>>>(a)
+#define RFX_K1F_B(SP, PE) do { if (a.march_batch >= 4) RFX_K1F(SP, PE, 4); else if (a.march_batch <= 1) RFX_K1F(SP, PE, 1); else RFX_K1F(SP, PE, 2); } while (0)
+    if (a.proj_sparse) { if (peer) RFX_K1F_B(true, true); else RFX_K1F_B(true, false); }
+    else { if (peer) RFX_K1F_B(false, true); else RFX_K1F_B(false, false); }
+#undef RFX_K1F_B
+#undef RFX_K1F
   } else if (a.phase == 0) {
     if (a.proj_sparse) { if (a.fast) RFX_K1_LAUNCH(true, true, 0); else RFX_K1_LAUNCH(true, false, 0); }
     else { if (a.fast) RFX_K1_LAUNCH(false, true, 0); else RFX_K1_LAUNCH(false, false, 0); }

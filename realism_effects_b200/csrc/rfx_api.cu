@@ -30,6 +30,7 @@ struct rfx_ctx {
   int step_table_steps = 0;
   // env
   bool env_set = false;
+  double env_total = 0.0;  // totalSumValue of the device-built tables (rfx_env_build)
   EnvD env{};
   std::vector<void*> env_allocs;
   // fast-math kernel variants (SFU lg2/ex2 instead of libm polynomials); 0 selects the exact-libm variants
@@ -49,6 +50,8 @@ struct rfx_ctx {
   size_t k1rec_pitch = 0;
   int k1rec_w = 0, k1rec_h = 0;
   const RowSegs* segs_override = nullptr;  // set by the native chain: all owned row blocks in ONE launch
+  int k3_tma = 0;     // RFX_K3_TMA=1: Poisson passes >= 1 stage their tap tiles with TMA (experiment; same bytes out)
+  int k1_batch = 2;   // RFX_K1_BATCH: march steps fetched together (1, 2, 4)
   int legacy_k1 = 0;  // RFX_LEGACY_K1=1 in the environment: the round-1 fast K1 kernel (A/B timing)
   const PeerPV* peer_accumulated = nullptr;  // set by the native chain in a row-sharded group: K1's `accumulated` rows live on their owners
 };
@@ -85,6 +88,8 @@ rfx_status rfx_ctx_create(int device, rfx_ctx** out) {
   rfx_ctx* ctx = new rfx_ctx();
   ctx->device = device;
   if (const char* e = getenv("RFX_LEGACY_K1")) ctx->legacy_k1 = atoi(e);
+  if (const char* e = getenv("RFX_K3_TMA")) ctx->k3_tma = atoi(e);
+  if (const char* e = getenv("RFX_K1_BATCH")) ctx->k1_batch = atoi(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return RFX_ERR_CUDA;
@@ -253,6 +258,7 @@ rfx_status rfx_env_set(rfx_ctx* ctx, const rfx_env_desc* e) {
   d.size_y = (float)e->height;
   d.total_sum_whole = e->total_sum_whole;
   d.total_sum_decimal = e->total_sum_decimal;
+  ctx->env_total = (double)e->total_sum_whole + (double)e->total_sum_decimal;
   if (e->marginal && e->conditional) {
     float *m = nullptr, *c = nullptr;
     CU(cudaMalloc(&m, (size_t)e->height * 4));
@@ -267,6 +273,47 @@ rfx_status rfx_env_set(rfx_ctx* ctx, const rfx_env_desc* e) {
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->env = d;
   ctx->env_set = true;
+  return RFX_OK;
+}
+
+// Env map + importance-sampling tables built ON THE DEVICE (replaces the reference's Web Worker,
+// src/ssgi/utils/EquirectHdrInfoUniform.js:323-358 -> gatherData :149-245): uploads mip 0, builds the mip chain, the per-row
+// cumulative distributions and the two inverse-CDF tables with the JS loops' summation order (bit-identical tables).
+rfx_status rfx_env_build(rfx_ctx* ctx, const void* map_rgba16f, uint32_t width, uint32_t height, int32_t flip_y) {
+  if (!ctx || !map_rgba16f || width == 0 || height == 0) return fail(ctx, RFX_ERR_INVALID_ARG, "env_build: bad arguments");
+  rfx_env_desc e{};
+  e.map_rgba16f = map_rgba16f; e.width = width; e.height = height;
+  rfx_status st = rfx_env_set(ctx, &e);  // mip chain; no tables yet
+  if (st != RFX_OK) return st;
+  const size_t n = (size_t)width * height;
+  float *cdf_c = nullptr, *cdf_m = nullptr, *marg = nullptr, *cond = nullptr;
+  double *row_sum = nullptr, *total = nullptr;
+  CU(cudaMalloc(&cdf_c, n * 4)); CU(cudaMalloc(&cdf_m, (size_t)height * 4)); CU(cudaMalloc(&row_sum, (size_t)height * 8)); CU(cudaMalloc(&total, 8));
+  CU(cudaMalloc(&marg, (size_t)height * 4)); ctx->env_allocs.push_back(marg);
+  CU(cudaMalloc(&cond, n * 4)); ctx->env_allocs.push_back(cond);
+  cudaError_t ce = launch_env_cdf(ctx->env.mip[0], flip_y ? 1 : 0, cdf_c, cdf_m, row_sum, total, marg, cond, ctx->stream);
+  ctx->launches += 3;
+  double t = 0.0;
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&t, total, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  cudaFree(cdf_c); cudaFree(cdf_m); cudaFree(row_sum); cudaFree(total);
+  if (ce != cudaSuccess) return fail(ctx, RFX_ERR_CUDA, "env_build: %s", cudaGetErrorString(ce));
+  ctx->env.marginal = PV{(const unsigned char*)marg, (int)height, 1, (long long)height * 4};
+  ctx->env.conditional = PV{(const unsigned char*)cond, (int)width, (int)height, (long long)width * 4};
+  const double whole = (double)(int32_t)t;  // ~~totalSumValue (EquirectHdrInfoUniform.js:346-349)
+  ctx->env.total_sum_whole = (float)whole;
+  ctx->env.total_sum_decimal = (float)(t - whole);
+  ctx->env_total = t;
+  return RFX_OK;
+}
+// the tables of the current environment (host copies): marginal[height], conditional[width*height], totalSum; any pointer may be NULL
+rfx_status rfx_env_tables_download(rfx_ctx* ctx, float* marginal, float* conditional, double* total_sum) {
+  if (!ctx) return RFX_ERR_INVALID_ARG;
+  if (!ctx->env_set || !ctx->env.marginal.p) return fail(ctx, RFX_ERR_NOT_READY, "env_tables_download: no importance-sampling tables");
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (marginal) CU(cudaMemcpy(marginal, ctx->env.marginal.p, (size_t)ctx->env.marginal.w * 4, cudaMemcpyDeviceToHost));
+  if (conditional) CU(cudaMemcpy(conditional, ctx->env.conditional.p, (size_t)ctx->env.conditional.w * ctx->env.conditional.h * 4, cudaMemcpyDeviceToHost));
+  if (total_sum) *total_sum = ctx->env_total;
   return RFX_OK;
 }
 
@@ -342,7 +389,7 @@ static rfx_status ensure_step_table(rfx_ctx* ctx, int steps) {
   CU(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->step_table);
   ctx->step_table = nullptr;
-  int rows_n = steps + 1;  // rows 0..steps-2 hold cs(1..steps-1, b); two spare zero rows: the fast march reads one step ahead
+  int rows_n = steps + 4;  // rows 0..steps-2 hold cs(1..steps-1, b); spare zero rows: the fast march reads up to 3 steps ahead
   std::vector<float> t((size_t)rows_n * 256, 0.0f);
   for (int i = 1; i < steps; i++)
     for (int k = 0; k < 256; k++) {  // ssgi.frag:453   cs = 1. - exp(-0.25 * pow(float(i) + random.b - 0.5, 2.))
@@ -424,6 +471,7 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     a.ps_x0 = hw * M[0]; a.ps_x2 = hw * M[8]; a.ps_y1 = hh * M[5]; a.ps_y2 = hh * M[9]; a.ps_hw = hw; a.ps_hh = hh;
     a.vz_pitchw = (int)(ctx->viewz_pitch / 4);
     a.legacy_fast = ctx->legacy_k1;
+    a.march_batch = ctx->k1_batch;
     if (ctx->peer_accumulated) a.acc_peer = *ctx->peer_accumulated;
   }
   a.phase = ctx->k1_phase;
@@ -871,6 +919,26 @@ static void peer_single(PeerPV& pp, PV local) {
   pp.own0 = 0; pp.own1 = local.h;
 }
 
+// 2-D TMA descriptor over a plane of 16-byte texels, addressed as rows of 4-byte elements (box dims are limited to 256 elements)
+static bool encode_texel_map(CUtensorMap* map, const void* base, int W, int H, size_t pitch, int box_w, int box_h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return false;
+    fn = (EncodeFn)p;
+  }
+  if (box_w * 4 > 256 || box_h > 256) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)W * 4, (cuuint64_t)H};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w * 4, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_ssgi_frame* f, const uint32_t* ranges, uint32_t n_blocks,
                                     uint32_t k_begin, uint32_t k_end, int k1_phase) {
   rfx_ctx* ctx = ch->ctx;
@@ -987,6 +1055,15 @@ static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_
       a.cam = cam;
     }
     SpanGuard g(ch, cs, i == 0 ? 2 : 3);
+    if (ctx->k3_tma && i > 0) {  // experiment: TMA-staged tap tiles for the LINEAR passes
+      CPoissonTmaArgs t{};
+      t.a = a;
+      t.box_w = kTileW + 2 * a.reach_x; t.box_h = kTileH + 2 * a.reach_y;
+      if (encode_texel_map(&t.map_in, a.in.p, W, H, (size_t)a.in.pitch, t.box_w, t.box_h) && encode_texel_map(&t.map_nrdz, a.nrdz.p, W, H, (size_t)a.nrdz.pitch, t.box_w, t.box_h)) {
+        LAUNCHED(launch_cpoisson_tma(t, cs));
+        continue;
+      }
+    }
     LAUNCHED(launch_cpoisson(a, cs));
   }
   // ---- K4 stand-alone (no Poisson pass to ride on, or the caller split the frame between the last pass and K4)

@@ -1,6 +1,8 @@
 // rfx_kernels.h — internal launch interface between the C-ABI layer (rfx_api.cu) and the
 // sm_100a kernels (k_*.cu).  Everything here is plain structs of device pointers + uniforms.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encode entry point is resolved at run time)
+
 #include "rfx_device.cuh"
 #include "../../include/rfx.h"
 
@@ -142,6 +144,7 @@ struct SsgiArgs {
   float ps_x0, ps_x2, ps_y1, ps_y2, ps_hw, ps_hh;  // projection rows scaled to texel units: tx = (ps_x0*x + ps_x2*z) / -z + ps_hw
   int vz_pitchw;             // viewZ pitch in 4-byte words
   int legacy_fast;           // 1: use the round-1 fast kernel (tools/ A/B comparisons)
+  int march_batch;           // march steps fetched together before they are tested: 1, 2 or 4
   PeerPV acc_peer;           // `accumulated` in a row-sharded group (n > 1): rows live on their owners
 };
 cudaError_t launch_ssgi(const SsgiArgs& a, cudaStream_t s);
@@ -187,6 +190,8 @@ cudaError_t launch_traa_compose(const TraaComposeArgs& a, cudaStream_t s);
 
 // env mip chain: dst (w1 x h1) = box filter of src (w0 x h0), RGBA16F
 cudaError_t launch_env_downsample(PV src, OutV dst, int w1, int h1, cudaStream_t s);
+// importance-sampling tables of an equirect map on the device (gatherData, EquirectHdrInfoUniform.js:149-245); 3 launches
+cudaError_t launch_env_cdf(PV map, int flip_y, float* cdf_c, float* cdf_m, double* row_sum, double* total, float* marginal, float* conditional, cudaStream_t s);
 
 
 // ==========================================================================================
@@ -239,6 +244,12 @@ struct CPoissonArgs {
   CamD cam;
 };
 cudaError_t launch_cpoisson(const CPoissonArgs& a, cudaStream_t s);
+struct CPoissonTmaArgs {  // passes >= 1 with TMA-staged tiles (experiment, RFX_K3_TMA=1)
+  CPoissonArgs a;
+  CUtensorMap map_in, map_nrdz;  // 2-D maps over the 16-byte texel planes as rows of 4-byte elements; box = box_w*4 x box_h
+  int box_w, box_h;              // texels: 16 + 2 * reach_x, 16 + 2 * reach_y
+};
+cudaError_t launch_cpoisson_tma(const CPoissonTmaArgs& t, cudaStream_t s);
 
 struct CComposeArgs {   // stand-alone K4 over dn (denoiseIterations == 0)
   PV nrdz, gb, dn;

@@ -143,6 +143,21 @@ class Context:
         d.total_sum_whole = float(np.float32(whole))
         d.total_sum_decimal = float(np.float32(total_sum - whole))
         self._chk(self.lib.rfx_env_set(self.h, C.byref(d)))
+        self._env_shape = (m.shape[0], m.shape[1])
+
+    def build_env(self, map_f16: np.ndarray, flip_y: bool = False):
+        """env map + importance-sampling tables built on the device (rfx_env_build)"""
+        m = np.ascontiguousarray(map_f16)
+        assert m.dtype in (np.float16, np.uint16) and m.ndim == 3 and m.shape[2] == 4
+        self._chk(self.lib.rfx_env_build(self.h, m.ctypes.data, m.shape[1], m.shape[0], int(flip_y)))
+        self._env_shape = (m.shape[0], m.shape[1])
+
+    def env_tables(self):
+        """(marginal[H], conditional[H, W], totalSum) of the current environment, downloaded"""
+        h, w = self._env_shape
+        marg, cond, tot = np.empty(h, np.float32), np.empty((h, w), np.float32), C.c_double()
+        self._chk(self.lib.rfx_env_tables_download(self.h, marg.ctypes.data, cond.ctypes.data, C.byref(tot)))
+        return marg, cond, float(tot.value)
 
     def clear_env(self):
         self._chk(self.lib.rfx_env_clear(self.h))

@@ -411,11 +411,11 @@ def build_env_cdf(data_f32: np.ndarray, flip_y: bool = False):
     if flip_y:
         for y in range(h):  # y = 0..h-1 inclusive, in place  (:154-166)
             data[h - 1 - y] = data[y]
-    lum = (0.2126 * data[..., 0].astype(np.float64) + 0.7152 * data[..., 1].astype(np.float64) + 0.0722 * data[..., 2].astype(np.float64))
-    pdf_c = lum.astype(np.float32)                       # pdfConditional[i] = weight (Float32Array)
-    cdf_c = np.cumsum(lum, axis=1).astype(np.float32)    # cumulativeRowWeight is a JS double
-    row_sum = lum.sum(axis=1)
-    total = float(lum.sum())
+    lum = (0.2126 * data[..., 0].astype(np.float64) + 0.7152 * data[..., 1].astype(np.float64)) + 0.0722 * data[..., 2].astype(np.float64)  # JS: left to right
+    cum64 = np.cumsum(lum, axis=1)                       # cumulativeRowWeight: a JS double accumulated left to right
+    cdf_c = cum64.astype(np.float32)                     # cdfConditional[i] = cumulativeRowWeight (Float32Array store)
+    row_sum = cum64[:, -1].copy()                        # the row's final cumulativeRowWeight (sequential, not a pairwise sum)
+    total = float(np.cumsum(lum.reshape(-1))[-1])        # totalSumValue += weight, pixel after pixel in row-major order
     nz = row_sum != 0
     cdf_c[nz] = (cdf_c[nz].astype(np.float64) / row_sum[nz, None]).astype(np.float32)
     cdf_m = np.cumsum(row_sum)

@@ -269,16 +269,18 @@ def compare(a: np.ndarray, b: np.ndarray, packed: bool = False, rtol: float | No
                 bit_equal=float(((a == b) | (np.isnan(a) & np.isnan(b))).mean()))
 
 
-def run_chain_parity(width=192, height=108, frames=2, max_frac=2e-3, fast_math=True, **opt_kw) -> dict:
+def run_chain_parity(width=192, height=108, frames=2, fast_math=True, **opt_kw) -> dict:
     o = Opts(**opt_kw)
     inp = make_inputs(width, height, frames)
     ref = run_oracle_chain(inp, o)
     got, launches = run_cuda_chain(inp, o, fast_math=fast_math)
     # Chain level: every pass of every frame re-quantises to fp16 (K1 pack, Poisson targets), so a last-ulp difference in one
-    # pass can become a 1-fp16-ulp (<= 9.8e-4 relative) difference at the next quantisation point and these compound over the
-    # chain.  The per-pass tests (same inputs into one kernel) hold the 1e-3 bar; for the chain we require (a) the fraction of
-    # pixels outside 1e-3 to stay small and (b) essentially all pixels inside 4 fp16 ulps (4e-3).
-    loose_frac = 5 * max_frac if fast_math else max_frac
+    # pass can become a 1-fp16-ulp (<= 9.8e-4 relative) difference at the next quantisation point.  Bars (fraction of pixels with a
+    # channel outside the band, worst plane of any frame): 2e-3 outside 1e-3 / 1e-3 outside 4e-3 for the fast variant, 1e-3 / 2e-4
+    # for the exact one.  These small frames have ~2e4 pixels, so ONE ray that resolves differently (its footprint after the
+    # denoiser is ~50 pixels) is 2e-3 of a plane: the statistically meaningful bars — 1e-3 / 2e-4 at 1080p and 4K, measured
+    # 7e-4 / 4e-5 — are in tests/test_gpu_parity_at_size.py.
+    loose_frac, max_frac = (2e-3, 1e-3) if fast_math else (1e-3, 2e-4)
     worst, worst4, lines = 0.0, 0.0, []
     ssr = o.mode == abi.MODE_SSR
     for t, (r, g) in enumerate(zip(ref, got)):

@@ -60,3 +60,25 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for bad in ("import orc", "librfx_oracle", "chain_harness", "from tests", "rfx_oracle", "orc_"):
                     assert bad not in txt, (f, bad)
+
+
+def test_napi_shim_type_checks_against_the_header():
+    """js/napi/shim.cc cannot be built here (no Node), but every rfx_* call in it must match include/rfx.h: it is type-checked with
+    g++ -fsyntax-only against the real header and a stub of the N-API prototypes (tools/check_shim.sh); and js/index.js exports the
+    reference's eight plugin classes (src/index.js:16-31)."""
+    import os
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["bash", os.path.join(root, "tools", "check_shim.sh")], capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    js = open(os.path.join(root, "js", "index.js")).read()
+    exported = set(re.findall(r"export class (\w+)", js))
+    assert {"SSGIEffect", "SSREffect", "TRAAEffect", "MotionBlurEffect", "HBAOEffect", "VelocityDepthNormalPass", "TemporalReprojectPass", "PoissonDenoisePass"} <= exported
+    shim = open(os.path.join(root, "js", "napi", "shim.cc")).read()
+    bound = set(re.findall(r'FN\("(\w+)"', shim))
+    used = set(re.findall(r"rfx\.(\w+)\(", js))
+    assert used <= bound, sorted(used - bound)                      # every rfx.<fn> the JS classes call is exported by the shim
+    for sig in ("update(renderer, inputBuffer, deltaTime)", "update(renderer, inputBuffer)", "render(renderer)"):
+        assert sig in js

@@ -50,7 +50,7 @@ def test_static_camera_full_accumulate(built):
     for t in range(4):
         for k in ("tr0", "tr1", "composed"):
             c = ch.compare(ref[t][k], got[t][k])
-            assert c["frac_bad"] <= 1e-2 and ch.compare(ref[t][k], got[t][k], rtol=4e-3)["frac_bad"] <= 2e-3, (t, k, c)  # chain-level bar, see chain_harness
+            assert c["frac_bad"] <= 2e-3 and ch.compare(ref[t][k], got[t][k], rtol=4e-3)["frac_bad"] <= 1e-3, (t, k, c)  # chain-level bar, see chain_harness
     assert got[3]["tr0"][..., 3].max() > got[1]["tr0"][..., 3].max()
 
 

@@ -57,7 +57,7 @@ def test_ssgi_effect_matches_oracle_chain(built):
             fx.update(None, comp.inputBuffer)
             got = fx._chain.download(0)
             c = ch.compare(ref[t]["composed"], got)
-            assert c["frac_bad"] <= 1e-2 and ch.compare(ref[t]["composed"], got, rtol=4e-3)["frac_bad"] <= 2e-3, (t, c)
+            assert c["frac_bad"] <= 2e-3 and ch.compare(ref[t]["composed"], got, rtol=4e-3)["frac_bad"] <= 1e-3, (t, c)
             want5 = orc.ssgi_compose(fr["depth"], got, fr["direct"])  # K5 on the engine's own GI plane
             assert ch.compare(want5, comp.outputBuffer.download())["n_bad"] == 0
         # reactive option: the setter reconfigures the native chain and resets the history (SSGIEffect.js:203-209)
@@ -135,5 +135,35 @@ def test_hbao_effect_traa_effect_motion_blur_effect(built):
         mb.update(None, comp.inputBuffer, 1 / 60, comp.outputBuffer)
         want = orc.motion_blur(ch.motion_blur_params(W, H, frame=7), vel, f1["direct"], inp.blue)
         assert ch.compare(want, comp.outputBuffer.download())["frac_bad"] <= 2e-3
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("flip_y", [False, True])
+def test_env_cdf_tables_built_on_device_are_bit_identical(built, flip_y):
+    """rfx_env_build: the device-built marginal / conditional inverse-CDF tables and totalSum equal the
+    restatement of `gatherData` (EquirectHdrInfoUniform.js:149-245, synth.build_env_cdf) bit for bit, including the reference's
+    mirroring "un-flip" for flipY textures (A4); and K1 gives the same bytes with either set of tables."""
+    env = synth.synthetic_env(256, 128)
+    env[40:60, 100:140, :3] = 0  # a black patch: flat CDF stretches (ties in the binary search)
+    env[7] = 0                   # an all-black row: cumulativeRowWeight == 0 branch
+    marg, cond, total = synth.build_env_cdf(env.astype(np.float32), flip_y=flip_y)
+    inp = ch.make_inputs(96, 54, 1)
+    ctx = engine.Context(0, inp.blue)
+    try:
+        ctx.build_env(env, flip_y=flip_y)
+        gm, gc, gt = ctx.env_tables()
+        assert gt == total
+        assert np.array_equal(gm.view(np.uint32), marg.view(np.uint32))
+        assert np.array_equal(gc.view(np.uint32), cond.view(np.uint32))
+        fr = inp.frames[0]
+        p = ch.ssgi_params(ch.Opts(), abi.make_camera(fr["cam"]), 4242, (256, 128))
+        planes = [ctx.upload(fr[k]) for k in ("depth", "gbuffer", "direct")]
+        out_dev = ctx.alloc(abi.FMT_RGBA32F, 96, 54)
+        ctx.ssgi_trace(p, planes[0], planes[1], None, planes[2], None, out_dev)
+        a = out_dev.download()
+        ctx.set_env(env, marg, cond, total)
+        ctx.ssgi_trace(p, planes[0], planes[1], None, planes[2], None, out_dev)
+        assert a.tobytes() == out_dev.download().tobytes()
     finally:
         ctx.close()
