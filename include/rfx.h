@@ -273,8 +273,19 @@ rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_p
                                  const rfx_plane* diffuse_gi, const rfx_plane* specular_gi, const rfx_plane* scene,
                                  const rfx_plane* out, uint32_t row0, uint32_t row1);
 
-/* K5. src/ssgi/shader/ssgi_compose.frag:20-44 (no fog). gi RGBA32F, scene RGBA16F, out RGBA16F */
-rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* depth,
+/* K5. src/ssgi/shader/ssgi_compose.frag:20-44.  gi RGBA32F, scene RGBA16F, out RGBA16F.  `p` may be NULL (no fog, no debug).
+ * Fog = three.js <fog_fragment> as patched by src/ssgi/SSGIEffect.js:34-43 on vFogDepth = -getViewZ(depth) * 0.4:
+ * FogExp2: 1 - exp(-density^2 * d^2); Fog: smoothstep(near, far, d); uniforms from scene.fog (SSGIEffect.js:404-412). */
+typedef struct rfx_ssgi_compose_params {
+  int32_t use_fog;      /* #define USE_FOG  (scene.fog != null)            */
+  int32_t fog_exp2;     /* #define FOG_EXP2 (scene.fog.isFogExp2)          */
+  float fog_color[3];
+  float fog_near, fog_far, fog_density;
+  float camera_near, camera_far;
+  int32_t perspective;  /* PERSPECTIVE_CAMERA                              */
+  int32_t is_debug;     /* uniform isDebug: pass the GI texture through    */
+} rfx_ssgi_compose_params;
+rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_compose_params* p, const rfx_plane* depth,
                                    const rfx_plane* gi, const rfx_plane* scene,
                                    const rfx_plane* out, uint32_t row0, uint32_t row1);
 

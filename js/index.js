@@ -139,7 +139,11 @@ export class SSGIEffect {
 		rfx.chainRender(this.ctx, this.chain, cam, planes.depth, planes.gbuffer, planes.velocity, this.isUsingRenderPass ? planes.directLight : null,
 			new Float32Array(this._camera.position.toArray()), moved)
 		// K5: ssgi_compose.frag (mainImage of the effect)
-		rfx.ssgiCompose(this.ctx, planes.depth, rfx.chainOutput(this.ctx, this.chain, 0), planes.directLight, this.outputPlane)
+		const fog = this._scene.fog   // SSGIEffect.js:404-412
+		rfx.ssgiCompose(this.ctx, planes.depth, rfx.chainOutput(this.ctx, this.chain, 0), planes.directLight, this.outputPlane, {
+			near: this._camera.near, far: this._camera.far, perspective: this._camera.isPerspectiveCamera !== false, isDebug: false,
+			...(fog ? { fog: { color: fog.color.toArray(), near: fog.near, far: fog.far, density: fog.density, isFogExp2: !!fog.isFogExp2 } } : {})
+		})
 		rfx.planeDownload(this.ctx, this.outputPlane, this.outputHost)
 	}
 	dispose() {

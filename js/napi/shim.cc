@@ -230,10 +230,22 @@ napi_value ChainReset(napi_env env, napi_callback_info info) { ARGS(1); rfx_ssgi
 napi_value ChainDestroy(napi_env env, napi_callback_info info) { ARGS(1); rfx_ssgi_chain_destroy(unwrap<rfx_ssgi_chain>(env, argv[0])); return undefined(env); }
 
 // ---- per-pass launches (one per reference fullscreen draw; whole planes) ------------------------------------------------------------
-napi_value SsgiCompose(napi_env env, napi_callback_info info) {  // ssgiCompose(ctx, depth, gi, scene, out)
-  ARGS(5); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
-  CHECK(c, rfx_ssgi_compose_launch(c, nullptr, unwrap<rfx_plane>(env, argv[1]), unwrap<rfx_plane>(env, argv[2]), unwrap<rfx_plane>(env, argv[3]), unwrap<rfx_plane>(env, argv[4]), 0, 0),
-        "rfx_ssgi_compose_launch");
+napi_value SsgiCompose(napi_env env, napi_callback_info info) {  // ssgiCompose(ctx, depth, gi, scene, out[, {fog: {color, near, far, density, isFogExp2}, near, far, perspective, isDebug}])
+  ARGS(6); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  rfx_ssgi_compose_params p{};
+  napi_valuetype t = napi_undefined;
+  if (argc > 5) napi_typeof(env, argv[5], &t);
+  if (t == napi_object) {
+    Obj b{env, argv[5]};
+    p.camera_near = (float)b.num("near", 0.1); p.camera_far = (float)b.num("far", 1000); p.perspective = (int32_t)b.num("perspective", 1); p.is_debug = (int32_t)b.num("isDebug", 0);
+    if (b.has("fog")) {
+      Obj f{env, b.get("fog")};
+      p.use_fog = 1; p.fog_exp2 = (int32_t)f.num("isFogExp2", 0); f.floats("color", p.fog_color, 3);
+      p.fog_near = (float)f.num("near", 1); p.fog_far = (float)f.num("far", 1000); p.fog_density = (float)f.num("density", 0.00025);
+    }
+  }
+  CHECK(c, rfx_ssgi_compose_launch(c, nullptr, t == napi_object ? &p : nullptr, unwrap<rfx_plane>(env, argv[1]), unwrap<rfx_plane>(env, argv[2]), unwrap<rfx_plane>(env, argv[3]),
+                                   unwrap<rfx_plane>(env, argv[4]), 0, 0), "rfx_ssgi_compose_launch");
   return undefined(env);
 }
 napi_value TemporalReproject(napi_env env, napi_callback_info info) {  // temporalReproject(ctx, params, input, velocity, hist0, hist1|null, out0, out1|null)

@@ -1258,15 +1258,29 @@ void orc_gi_compose(const rfx_compose_params* p, int W, int H, const float* dept
     }
 }
 
-// K5.  ssgi_compose.frag:20-44 without fog / debug.  gi RGBA32F, scene RGBA16F, out RGBA16F
-void orc_ssgi_compose(int W, int H, const float* depth, const float* gi, const uint16_t* scene, uint16_t* out) {
+// K5.  ssgi_compose.frag:20-44 (+ three.js <fog_fragment> on vFogDepth = -getViewZ(depth) * 0.4, SSGIEffect.js:34-43).  gi RGBA32F, scene RGBA16F,
+// out RGBA16F; p may be NULL (no fog, no debug)
+void orc_ssgi_compose(const rfx_ssgi_compose_params* p, int W, int H, const float* depth, const float* gi, const uint16_t* scene, uint16_t* out) {
   Tex d = mk(depth, W, H, F_R32F), g = mk(gi, W, H, F_RGBA32F), sc = mk(scene, W, H, F_RGBA16F, true);
 #pragma omp parallel for
   for (int y = 0; y < H; y++)
     for (int x = 0; x < W; x++) {
       vec2 uv = pixelUv(x, y, W, H);
+      if (p && p->is_debug) { store_rgba16f(out, W, x, y, textureLod0(g, uv)); continue; }
       float depthv = textureLod0(d, uv).x;
-      vec3 c = depthv == 1.0f ? textureLod0(sc, uv).xyz() : textureLod0(g, uv).xyz();
+      vec3 c;
+      if (depthv == 1.0f) {
+        c = textureLod0(sc, uv).xyz();
+      } else {
+        c = textureLod0(g, uv).xyz();
+        if (p && p->use_fog) {
+          float gz = p->perspective ? perspectiveDepthToViewZ(depthv, p->camera_near, p->camera_far) : orthographicDepthToViewZ(depthv, p->camera_near, p->camera_far);
+          float viewZ = gz * 0.4f;
+          float vFogDepth = -viewZ;
+          float fogFactor = p->fog_exp2 ? 1.0f - expcr(-p->fog_density * p->fog_density * vFogDepth * vFogDepth) : smoothstepf(p->fog_near, p->fog_far, vFogDepth);
+          c = mix(c, vec3(p->fog_color[0], p->fog_color[1], p->fog_color[2]), fogFactor);
+        }
+      }
       store_rgba16f(out, W, x, y, vec4(c, 1.0f));
     }
 }

@@ -66,6 +66,11 @@ class ComposeParams(C.Structure):
     _fields_ = [("cam", CameraS), ("input_type", C.c_int32), ("_pad", C.c_int32)]
 
 
+class SsgiComposeParams(C.Structure):
+    _fields_ = [("use_fog", C.c_int32), ("fog_exp2", C.c_int32), ("fog_color", F3), ("fog_near", C.c_float), ("fog_far", C.c_float),
+                ("fog_density", C.c_float), ("camera_near", C.c_float), ("camera_far", C.c_float), ("perspective", C.c_int32), ("is_debug", C.c_int32)]
+
+
 class HbaoParams(C.Structure):
     _fields_ = [("projection_view", F16), ("projection_inverse", F16), ("camera_matrix_world", F16), ("ao_distance", C.c_float),
                 ("distance_power", C.c_float), ("bias", C.c_float), ("thickness", C.c_float), ("spp", C.c_int32), ("blue_noise_index", C.c_int32)]
@@ -158,7 +163,7 @@ def _sig(lib):
     lib.rfx_temporal_reproject_launch.argtypes = [vp, vp, _P(TemporalParams), PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_poisson_denoise_launch.argtypes = [vp, vp, _P(PoissonParams), PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_gi_compose_launch.argtypes = [vp, vp, _P(ComposeParams), PP, PP, PP, PP, PP, PP, u32, u32]
-    lib.rfx_ssgi_compose_launch.argtypes = [vp, vp, PP, PP, PP, PP, u32, u32]
+    lib.rfx_ssgi_compose_launch.argtypes = [vp, vp, _P(SsgiComposeParams), PP, PP, PP, PP, u32, u32]
     lib.rfx_hbao_launch.argtypes = [vp, vp, _P(HbaoParams), PP, PP, u32, u32]
     lib.rfx_ao_compose_launch.argtypes = [vp, vp, _P(AoComposeParams), PP, PP, PP, PP, u32, u32]
     lib.rfx_motion_blur_launch.argtypes = [vp, vp, _P(MotionBlurParams), PP, PP, PP, u32, u32]

@@ -619,8 +619,8 @@ rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_p
   return RFX_OK;
 }
 
-rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* depth, const rfx_plane* gi, const rfx_plane* scene, const rfx_plane* out,
-                                   uint32_t row0, uint32_t row1) {
+rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_compose_params* p, const rfx_plane* depth, const rfx_plane* gi, const rfx_plane* scene,
+                                   const rfx_plane* out, uint32_t row0, uint32_t row1) {
   if (!ctx || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "ssgi_compose: null argument");
   SsgiComposeArgs a{};
   if (!pv(depth, RFX_FMT_R32F, a.depth) || !pv(gi, RFX_FMT_RGBA32F, a.gi) || !pv(scene, RFX_FMT_RGBA16F, a.scene) || !ov(out, RFX_FMT_RGBA16F, a.out))
@@ -628,6 +628,11 @@ rfx_status rfx_ssgi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* 
   a.W = (int)out->width; a.H = (int)out->height;
   if (a.depth.w != a.W || a.depth.h != a.H || a.gi.w != a.W || a.scene.w != a.W) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_compose: plane sizes differ");
   rows(row0, row1, out->height, a.row0, a.row1);
+  if (p) {
+    a.use_fog = p->use_fog; a.fog_exp2 = p->fog_exp2; a.perspective = p->perspective; a.is_debug = p->is_debug;
+    memcpy(a.fog_color, p->fog_color, 12);
+    a.fog_near = p->fog_near; a.fog_far = p->fog_far; a.fog_density = p->fog_density; a.camera_near = p->camera_near; a.camera_far = p->camera_far;
+  }
   LAUNCHED(launch_ssgi_compose(a, pick(ctx, stream)));
   return RFX_OK;
 }

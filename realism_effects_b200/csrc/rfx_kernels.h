@@ -98,6 +98,8 @@ struct SsgiComposeArgs {
   PV depth, gi, scene;
   OutV out;
   int W, H, row0, row1;
+  int use_fog, fog_exp2, perspective, is_debug;
+  float fog_color[3], fog_near, fog_far, fog_density, camera_near, camera_far;
 };
 cudaError_t launch_ssgi_compose(const SsgiComposeArgs& a, cudaStream_t s);
 

@@ -214,7 +214,20 @@ class SSGIEffect(_Reactive):
         self._chain.render(abi.make_camera(cam_u), self._scene.depth, self._scene.gbuffer, self.velocityDepthNormalPass.texture,
                            scene_buf if self.isUsingRenderPass else None, cam_u["position"], moved)
         if getattr(self.composer, "outputBuffer", None) is not None:  # both modes: SSR composes with inputType "specular" (Denoiser.js:56-64)
-            self.ctx.ssgi_compose(self._scene.depth, self.outputTexture, scene_buf, self.composer.outputBuffer)  # K5 (mainImage of the effect)
+            self.ctx.ssgi_compose(self._scene.depth, self.outputTexture, scene_buf, self.composer.outputBuffer, params=self._compose_params(cam_u))  # K5 (mainImage of the effect)
+
+    def _compose_params(self, cam_u):
+        """scene.fog -> the fog uniforms of ssgi_compose.frag (src/ssgi/SSGIEffect.js:80-90, 404-412); fog = dict(color, near, far) or
+        dict(color, density, isFogExp2=True) like three.js Fog / FogExp2"""
+        fog = getattr(self._scene, "fog", None)
+        if not fog:
+            return None
+        p = abi.SsgiComposeParams()
+        p.use_fog, p.fog_exp2 = 1, int(bool(fog.get("isFogExp2", False)))
+        p.fog_color[:] = [float(x) for x in fog.get("color", (1.0, 1.0, 1.0))]
+        p.fog_near, p.fog_far, p.fog_density = float(fog.get("near", 1.0)), float(fog.get("far", 1000.0)), float(fog.get("density", 0.00025))
+        p.camera_near, p.camera_far, p.perspective = float(cam_u["near"]), float(cam_u["far"]), 1
+        return p
 
     def dispose(self):
         if self._chain is not None:

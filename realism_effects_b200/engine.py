@@ -186,8 +186,10 @@ class Context:
         self._chk(self.lib.rfx_gi_compose_launch(self.h, stream, C.byref(p), _r(depth), _r(gbuffer), _r(diffuse_gi), _r(specular_gi), _r(scene), _r(out),
                                                  rows[0], rows[1]))
 
-    def ssgi_compose(self, depth, gi, scene, out, rows=(0, 0), stream=None):
-        self._chk(self.lib.rfx_ssgi_compose_launch(self.h, stream, _r(depth), _r(gi), _r(scene), _r(out), rows[0], rows[1]))
+    def ssgi_compose(self, depth, gi, scene, out, rows=(0, 0), stream=None, params=None):
+        """params: abi.SsgiComposeParams (scene fog / isDebug) or None"""
+        self._chk(self.lib.rfx_ssgi_compose_launch(self.h, stream, C.byref(params) if params is not None else None, _r(depth), _r(gi), _r(scene), _r(out),
+                                                   rows[0], rows[1]))
 
     def hbao(self, p, depth, out, rows=(0, 0), stream=None):
         self._chk(self.lib.rfx_hbao_launch(self.h, stream, C.byref(p), _r(depth), _r(out), rows[0], rows[1]))

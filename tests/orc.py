@@ -148,10 +148,12 @@ def gi_compose(p: abi.ComposeParams, depth, gbuffer, diffuse_gi, specular_gi, ou
     return out
 
 
-def ssgi_compose(depth, gi, scene):
+def ssgi_compose(depth, gi, scene, params=None):
+    """params: abi.SsgiComposeParams (fog / debug) or None"""
     H, W = depth.shape
     out = np.zeros((H, W, 4), np.uint16)
-    lib().orc_ssgi_compose(C.c_int(W), C.c_int(H), _p(_c(depth, np.float32)), _p(_c(gi, np.float32)), _p(f16bits(scene)), _p(out))
+    lib().orc_ssgi_compose(C.byref(params) if params is not None else None, C.c_int(W), C.c_int(H), _p(_c(depth, np.float32)), _p(_c(gi, np.float32)),
+                           _p(f16bits(scene)), _p(out))
     return out.view(np.float16)
 
 

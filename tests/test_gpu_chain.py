@@ -118,3 +118,34 @@ def test_three_part_frame_equals_fused_frame(built, fast):
             chain.close()
         finally:
             ctx.close()
+
+
+def test_group_of_one_rank_equals_plain_chain(built):
+    """rfx_group_* with world = 1 on a single GPU: NCCL is loaded and initialised, the chain is attached, every frame ends with the
+    group's collective, the band is the whole frame — and the bytes are those of rfx_ssgi_chain_render.  (The peer-mapped reads need
+    >= 2 GPUs: tests/test_gpu_multi.py; this keeps the group plumbing covered on a 1-GPU box.)"""
+    import ctypes as C
+
+    from realism_effects_b200 import abi, engine, parallel
+
+    o = ch.Opts(denoise_iterations=1)
+    inp = ch.make_inputs(160, 128, 3)
+    want, _ = ch.run_cuda_chain(inp, o)
+    ctx = engine.Context(0, inp.blue)
+    try:
+        ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+        buf = C.create_string_buffer(abi.GROUP_ID_BYTES)
+        ctx._chk(ctx.lib.rfx_group_get_unique_id(buf))
+        sh = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), rank=0, world=1, unique_id=bytes(buf.raw), rebalance_every=1, rebalance_lag=1)
+        assert sh.bounds == (0, 128)
+        keep = []
+        for t, fr in enumerate(inp.frames):
+            pl = [ctx.upload(fr[k]) for k in ("depth", "gbuffer", "velocity", "direct")]
+            keep.append(pl)
+            sh.render(abi.make_camera(fr["cam"]), *pl, fr["cam"]["position"], fr["moved"])
+            for k, which in (("composed", 0), ("ssgi", 1), ("tr0", 2), ("dn1", 5)):
+                assert sh.chain.download(which).tobytes() == want[t][k].tobytes(), (t, k)
+        assert len(sh.last_costs) == 1
+        sh.close()
+    finally:
+        ctx.close()

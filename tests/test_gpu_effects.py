@@ -167,3 +167,36 @@ def test_env_cdf_tables_built_on_device_are_bit_identical(built, flip_y):
         assert a.tobytes() == out_dev.download().tobytes()
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("exp2", [False, True])
+def test_ssgi_compose_fog_and_debug(built, exp2):
+    """K5 with scene fog (three.js Fog / FogExp2 through <fog_fragment> on vFogDepth = -getViewZ(depth) * 0.4, SSGIEffect.js:34-43,
+    404-412) and the isDebug pass-through, against the oracle."""
+    import orc
+
+    inp = ch.make_inputs(128, 72, 1)
+    fr = inp.frames[0]
+    rng = np.random.default_rng(3)
+    gi = rng.uniform(0, 2, (72, 128, 4)).astype(np.float32)
+    p = abi.SsgiComposeParams()
+    p.use_fog, p.fog_exp2, p.perspective = 1, int(exp2), 1
+    p.fog_color[:] = [0.6, 0.7, 0.8]
+    p.fog_near, p.fog_far, p.fog_density = 2.0, 30.0, 0.05
+    p.camera_near, p.camera_far = float(fr["cam"]["near"]), float(fr["cam"]["far"])
+    ctx = engine.Context(0, inp.blue)
+    try:
+        d, g, sc = ctx.upload(fr["depth"]), ctx.upload(gi), ctx.upload(fr["direct"])
+        out = ctx.alloc(abi.FMT_RGBA16F, 128, 72)
+        ctx.ssgi_compose(d, g, sc, out, params=p)
+        want = orc.ssgi_compose(fr["depth"], gi, fr["direct"], p)
+        nofog = orc.ssgi_compose(fr["depth"], gi, fr["direct"])
+        assert ch.compare(want, out.download())["n_bad"] == 0
+        assert not np.array_equal(want, nofog)                                         # the fog does something on foreground pixels ...
+        bg = fr["depth"] == 1.0
+        assert np.array_equal(want[bg], nofog[bg])                                     # ... and nothing on the background (scene colour)
+        p.is_debug = 1
+        ctx.ssgi_compose(d, g, sc, out, params=p)
+        assert np.array_equal(out.download(), gi.astype(np.float16))                   # isDebug: the GI texture passes through
+    finally:
+        ctx.close()

@@ -5,9 +5,10 @@ import json
 import subprocess
 import sys
 
-KEY = [("ssgi_kernel", "K1_ssgi_trace"), ("temporal_kernel", "K2_temporal_reproject"), ("poisson_fast_kernel<2, 0>", "K3_poisson_pass0"),
-       ("poisson_fast_kernel<2, 1>", "K3_poisson_pass1plus"), ("gi_compose_kernel", "K4_gi_compose"), ("viewz_kernel", "prepass_viewz"),
-       ("gbuffer_decode_kernel", "prepass_gbuffer_decode")]
+KEY = [("ssgi_fast_kernel", "K1_ssgi_trace"), ("ssgi_kernel", "K1_ssgi_trace"), ("ctemporal_kernel", "K2_temporal_reproject"), ("temporal_kernel", "K2_temporal_reproject"),
+       ("cpoisson_kernel<1,", "K3_poisson_pass0"), ("cpoisson_kernel<0,", "K3_poisson_pass1plus"), ("cpoisson_tma_kernel", "K3_poisson_pass1plus_tma"),
+       ("poisson_fast_kernel<2, 0>", "K3_poisson_pass0"), ("poisson_fast_kernel<2, 1>", "K3_poisson_pass1plus"), ("gi_compose_kernel", "K4_gi_compose"),
+       ("viewz_kernel", "prepass_viewz"), ("cdecode_kernel", "prepass_gbuffer_decode"), ("gbuffer_decode_kernel", "prepass_gbuffer_decode")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
