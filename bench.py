@@ -199,7 +199,7 @@ def other_configs(ctx, ch, dev, stream, peak):
     # C4: HBAOEffect 3840x2160 (spp form) + 2 single-plane Poisson passes (velocity-layout normals) + ao_compose
     W, H = WIDTH, HEIGHT
     f = make_gpu_frames(W, H, 1, dev)[0]
-    d, g, v, dl = frame_planes(f)
+    d, g, v, dl = (pw.p for pw in frame_planes(f))
     ao, tA, tB, outp = (ctx.alloc(abi.FMT_RGBA16F, W, H) for _ in range(4))
     hp = ch.hbao_params(f["cam"], 778)
     pps = []

@@ -288,45 +288,109 @@ cudaError_t launch_ctemporal(const CTemporalArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------------------
 // K4 as a device function: constructGlobalIllumination (denoiser_compose_functions.glsl:53-107)
 // ------------------------------------------------------------------------------------------------------------------
-// The arithmetic is the exact K4's (IEEE division / sqrt, k_denoise.cu: gi_compose_kernel) — measured at 4K (tools/parity_at_size.py): with SFU
-// reciprocals here another 2.4e-4 of the pixels leave the 1e-3 band, because the two fp16 inputs already sit up to one fp16 ulp
-// (9.8e-4) from the oracle's; the pixel-centre fetch is the centre texel and pow(x, 5) is multiplies, as in the round-1 fast K4.
-RFX_D float4 c_compose(const CamD& cam, int x, int y, int W, int H, float4 g, float rough0, float depth, v3 dgi, v3 sgi) {
+// Arithmetic precision is a template parameter because it was MEASURED to matter (tools/parity_at_size.py at 4K): the two fp16 inputs
+// already sit up to one fp16 ulp (9.8e-4) from the oracle's, so composed pixels crowd the 1e-3 line.  CM = 0: the exact K4's IEEE
+// division / sqrt (k_denoise.cu: gi_compose_kernel); 1: SFU rcp / rsqrt / sqrt (2^-22: pushed another 2.4e-4 of the pixels over the line);
+// 2: SFU seed + one Newton step (<= 1 ulp, a fifth of the IEEE instruction count).  The pixel-centre fetch is the centre texel and
+// pow(x, 5) is multiplies in every mode, as in the round-1 fast K4.  profiles/r02_compose_modes.txt has the three measurements.
+template <int CM> RFX_D float cm_rsqrt(float x) {
+  if (CM == 0) return 1.0f / sqrtf(x);
+  const float y = fx_rsqrt(x);
+  if (CM == 1) return y;
+  return y * fma_(-0.5f * x * y, y, 1.5f);  // y (1.5 - 0.5 x y^2)
+}
+template <int CM> RFX_D float cm_rcp(float x) {
+  if (CM == 0) return 1.0f / x;
+  const float r = fx_rcp(x);
+  if (CM == 1) return r;
+  return r * fma_(-x, r, 2.0f);
+}
+template <int CM> RFX_D float cm_sqrt(float x) {
+  if (CM == 0) return sqrtf(x);
+  if (CM == 1) return fx_sqrt(x);
+  return x > 0.0f ? x * cm_rsqrt<2>(x) : 0.0f;
+}
+template <int CM> RFX_D v3 cm_normalize(v3 a) { return a * cm_rsqrt<CM>(dot(a, a)); }
+template <int CM> RFX_D v3 cm_unpack_normal(float packed) {
+  v2 f = unpackHalf2x16(__float_as_uint(packed));
+  f = f * 2.0f - 1.0f;
+  v3 n = mk3(f.x, f.y, 1.0f - fabsf(f.x) - fabsf(f.y));
+  const float t = fmaxf(-n.z, 0.0f);
+  n.x += n.x >= 0.0f ? -t : t;
+  n.y += n.y >= 0.0f ? -t : t;
+  return cm_normalize<CM>(n);
+}
+template <int CM> RFX_D v3 cm_byte3(uint32_t v) {  // floatToVec4(...).rgb
+  if (CM == 0) return mk3(fmaxf((float)(v & 0xFFu) / 255.0f - RFX_NON_ZERO_OFFSET, 0.0f), fmaxf((float)((v >> 8) & 0xFFu) / 255.0f - RFX_NON_ZERO_OFFSET, 0.0f),
+                          fmaxf((float)((v >> 16) & 0xFFu) / 255.0f - RFX_NON_ZERO_OFFSET, 0.0f));
+  const float k = 1.0f / 255.0f;
+  return mk3(fmaxf((float)(v & 0xFFu) * k - RFX_NON_ZERO_OFFSET, 0.0f), fmaxf((float)((v >> 8) & 0xFFu) * k - RFX_NON_ZERO_OFFSET, 0.0f),
+             fmaxf((float)((v >> 16) & 0xFFu) * k - RFX_NON_ZERO_OFFSET, 0.0f));
+}
+template <int CM>
+RFX_D v3 cm_sample_ggx_vndf(v3 V, float ax, float ay, float r1, float cphi, float sphi) {
+  const v3 Vh = cm_normalize<CM>(mk3(ax * V.x, ay * V.y, V.z));
+  const float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+  const v3 T1 = lensq > 0.0f ? mk3(-Vh.y, Vh.x, 0.0f) * cm_rsqrt<CM>(lensq) : mk3(1.0f, 0.0f, 0.0f);
+  const v3 T2 = cross(Vh, T1);
+  const float r = cm_sqrt<CM>(r1);
+  const float t1 = r * cphi;
+  float t2 = r * sphi;
+  const float sv = 0.5f * (1.0f + Vh.z);
+  t2 = (1.0f - sv) * cm_sqrt<CM>(1.0f - t1 * t1) + sv * t2;
+  const v3 Nh = t1 * T1 + t2 * T2 + cm_sqrt<CM>(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+  return cm_normalize<CM>(mk3(ax * Nh.x, ay * Nh.y, fmaxf(0.0f, Nh.z)));
+}
+template <int CM>
+RFX_D float4 c_compose_t(const CamD& cam, int x, int y, int W, int H, float4 g, float rough0, float depth, v3 dgi, v3 sgi) {
   const v2 vUv = pixel_uv(x, y, W, H);
-  const v3 diffuse = xyz(floatToVec4(g.x));
-  const v3 wn = unpackNormal(g.y);
+  const v3 diffuse = cm_byte3<CM>(__float_as_uint(g.x));
+  const v3 wn = cm_unpack_normal<CM>(g.y);  // the exact packed normal (the nrdz copy carries the roughness code in its low mantissa bits)
   const float metalness = gb_metalness(g.z);
-  const v3 emissive = decodeRGBE8(floatToVec4(g.w));
+  const uint32_t ev = __float_as_uint(g.w);
+  const float ew = CM == 0 ? fmaxf((float)(ev >> 24) / 255.0f - RFX_NON_ZERO_OFFSET, 0.0f) : fmaxf((float)(ev >> 24) * (1.0f / 255.0f) - RFX_NON_ZERO_OFFSET, 0.0f);
+  const float fexp = ew * 255.0f - 128.0f;
+  const v3 emissive = cm_byte3<CM>(ev) * (CM == 0 ? exp2f(fexp) : fx_ex2(fexp));  // decodeRGBE8
   const v3 viewNormal = mul_dir_left(wn, cam.camera_matrix_world);
-  const float gz = cam.perspective ? perspectiveDepthToViewZ(depth, cam.near_plane, cam.far_plane) : orthographicDepthToViewZ(depth, cam.near_plane, cam.far_plane);
+  const float gz = cam.perspective ? (cam.near_plane * cam.far_plane) * cm_rcp<CM>((cam.far_plane - cam.near_plane) * depth - cam.far_plane)
+                                   : orthographicDepthToViewZ(depth, cam.near_plane, cam.far_plane);
   const float viewZ = -gz;
   const float clipW = cam.projection.m[2 * 4 + 3] * viewZ + cam.projection.m[3 * 4 + 3];
   v4 clip = mk4((vUv.x - 0.5f) * 2.0f, (vUv.y - 0.5f) * 2.0f, (viewZ - 0.5f) * 2.0f, 1.0f);
   clip = mk4(clip.x * clipW, clip.y * clipW, clip.z * clipW, clip.w * clipW);
   v3 viewPos = xyz(mul(cam.projection_inverse, clip));
   viewPos.z = -viewZ;
-  const v3 viewDir = normalize(viewPos);
+  const v3 viewDir = cm_normalize<CM>(viewPos);
   const float roughness = rough0 * rough0;
   const v3 N = mul_dir_left(viewNormal, cam.view_matrix);
   v3 T, B;
   const v3 v = -viewDir;
   v3 V = mul_dir_left(v, cam.view_matrix);
-  Onb(N, T, B);
+  {  // Onb
+    const v3 up = fabsf(N.z) < 0.9999999f ? mk3(0, 0, 1) : mk3(1, 0, 0);
+    T = cm_normalize<CM>(cross(up, N));
+    B = cross(N, T);
+  }
   V = ToLocal(T, B, N, V);
-  v3 Hh = SampleGGXVNDF_cs(V, roughness, roughness, 0.25f, -4.37113883e-08f, 1.0f);  // r2 = 0.25: (cos, sin) of fp32(pi/2)
+  v3 Hh = cm_sample_ggx_vndf<CM>(V, roughness, roughness, 0.25f, -4.37113883e-08f, 1.0f);  // r2 = 0.25: (cos, sin) of fp32(pi/2)
   if (Hh.z < 0.0f) Hh = -Hh;
-  v3 l = normalize(reflect(-V, Hh));
+  v3 l = cm_normalize<CM>(reflect(-V, Hh));
   l = ToWorld(T, B, N, l);
   l = xyz(mul(mk4(l, 1.0f), cam.camera_matrix_world));
-  l = normalize(l);
+  l = cm_normalize<CM>(l);
   if (dot(viewNormal, l) < 0.0f) l = -l;
-  const v3 h = normalize(v + l);
+  const v3 h = cm_normalize<CM>(v + l);
   const float VoH = fmaxf(1e-6f, dot(v, h));
   const v3 f0 = mix(mk3(0.04f), diffuse, metalness);
   const float omv = 1.0f - VoH, omv2 = omv * omv;
   const v3 F = f0 + (mk3(1.0f) - f0) * (omv2 * omv2 * omv);
   const v3 gi = diffuse * (1.0f - metalness) * (mk3(1.0f) - F) * dgi + sgi * F + emissive;
   return make_float4(gi.x, gi.y, gi.z, 1.0f);
+}
+RFX_D float4 c_compose(int mode, const CamD& cam, int x, int y, int W, int H, float4 g, float rough0, float depth, v3 dgi, v3 sgi) {
+  if (mode == 0) return c_compose_t<0>(cam, x, y, W, H, g, rough0, depth, dgi, sgi);
+  if (mode == 1) return c_compose_t<1>(cam, x, y, W, H, g, rough0, depth, dgi, sgi);
+  return c_compose_t<2>(cam, x, y, W, H, g, rough0, depth, dgi, sgi);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -453,7 +517,7 @@ RFX_D void cpoisson_body(const CPoissonArgs& a, int x, int y, float4 nc, float f
     if (in_segs(a.csegs, y)) {  // K4 reads the fp16 texel just stored (DenoiserComposePass.js:66-67)
       const float4 g = ld_f4(a.gb, x, y);
       st_f4(a.composed.p, a.composed.pitch, x, y,
-            c_compose(a.cam, x, y, a.W, a.H, g, roughness, depth, mk3(h_lo(q.x), h_hi(q.x), h_lo(q.y)), mk3(h_lo(q.z), h_hi(q.z), h_lo(q.w))));
+            c_compose(a.compose_mode, a.cam, x, y, a.W, a.H, g, roughness, depth, mk3(h_lo(q.x), h_hi(q.x), h_lo(q.y)), mk3(h_lo(q.z), h_hi(q.z), h_lo(q.w))));
     }
   }
 }
@@ -529,8 +593,9 @@ __global__ void __launch_bounds__(kThreads, 4) cpoisson_tma_kernel(const __grid_
   int lx, ly;
   lane_to_pixel(threadIdx.x & 31, lx, ly);
   const int bx0 = blockIdx.x * kTileW, by0 = y - ((int)((threadIdx.x >> 6) << 2) + ly);
-  // block-uniform: every texel of the staged tile exists (no clamping anywhere in this block)
-  const bool interior = bx0 - a.reach_x >= 0 && bx0 + kTileW - 1 + a.reach_x <= a.W - 1 && by0 - a.reach_y >= 0 && by0 + kTileH - 1 + a.reach_y <= a.H - 1;
+  // block-uniform: every texel of the staged tile exists (no clamping anywhere in this block); box_w may exceed 16 + 2 reach_x by
+  // one texel: an ODD row pitch (in 16-byte texels) spreads the rows of the tile over the shared-memory banks
+  const bool interior = bx0 - a.reach_x >= 0 && bx0 - a.reach_x + t.box_w - 1 <= a.W - 1 && by0 - a.reach_y >= 0 && by0 + kTileH - 1 + a.reach_y <= a.H - 1;
   SmemTile st{};
   if (interior) {
     const unsigned tile_bytes = (unsigned)t.box_w * (unsigned)t.box_h * 16u;
@@ -602,7 +667,7 @@ __global__ void __launch_bounds__(kThreads) ccompose_kernel(const __grid_constan
   const uint4 q = __ldg((const uint4*)(a.dn.p + ((unsigned)y * (unsigned)a.dn.pitch + (unsigned)x * 16u)));
   const float4 g = ld_f4(a.gb, x, y);
   st_f4(a.composed.p, a.composed.pitch, x, y,
-        c_compose(a.cam, x, y, a.W, a.H, g, nrdz_roughness(nc), nc.w, mk3(h_lo(q.x), h_hi(q.x), h_lo(q.y)), mk3(h_lo(q.z), h_hi(q.z), h_lo(q.w))));
+        c_compose(a.compose_mode, a.cam, x, y, a.W, a.H, g, nrdz_roughness(nc), nc.w, mk3(h_lo(q.x), h_hi(q.x), h_lo(q.y)), mk3(h_lo(q.z), h_hi(q.z), h_lo(q.w))));
 }
 cudaError_t launch_ccompose(const CComposeArgs& a, cudaStream_t s) {
   dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);

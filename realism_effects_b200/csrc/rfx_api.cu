@@ -50,8 +50,9 @@ struct rfx_ctx {
   size_t k1rec_pitch = 0;
   int k1rec_w = 0, k1rec_h = 0;
   const RowSegs* segs_override = nullptr;  // set by the native chain: all owned row blocks in ONE launch
-  int k3_tma = 0;     // RFX_K3_TMA=1: Poisson passes >= 1 stage their tap tiles with TMA (experiment; same bytes out)
-  int k1_batch = 2;   // RFX_K1_BATCH: march steps fetched together (1, 2, 4)
+  int k3_tma = 1;     // RFX_K3_TMA=0 disables the TMA-staged tap tiles of the Poisson passes >= 1 (same bytes out; measured 0.39 vs 0.42 ms per pass at 4K)
+  int k1_batch = 4;   // RFX_K1_BATCH: march steps fetched together (1, 2, 4); measured at 4K: 1.195 / 1.119 / 1.079 ms
+  int compose_mode = 2;  // RFX_COMPOSE_MODE: arithmetic of the fused K4 (0 IEEE, 1 SFU, 2 SFU + Newton)
   int legacy_k1 = 0;  // RFX_LEGACY_K1=1 in the environment: the round-1 fast K1 kernel (A/B timing)
   const PeerPV* peer_accumulated = nullptr;  // set by the native chain in a row-sharded group: K1's `accumulated` rows live on their owners
 };
@@ -90,6 +91,7 @@ rfx_status rfx_ctx_create(int device, rfx_ctx** out) {
   if (const char* e = getenv("RFX_LEGACY_K1")) ctx->legacy_k1 = atoi(e);
   if (const char* e = getenv("RFX_K3_TMA")) ctx->k3_tma = atoi(e);
   if (const char* e = getenv("RFX_K1_BATCH")) ctx->k1_batch = atoi(e);
+  if (const char* e = getenv("RFX_COMPOSE_MODE")) ctx->compose_mode = atoi(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return RFX_ERR_CUDA;
@@ -1053,6 +1055,7 @@ static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_
     }
     if (last && on(k_compose)) {
       a.compose = 1;
+      a.compose_mode = ctx->compose_mode;
       a.csegs = segs_for(ranges, n_blocks, n_launches, k_compose, H);
       a.gb = gb;
       a.composed = OutV{(unsigned char*)ch->composed2[cur].ptr, (long long)ch->composed2[cur].pitch};
@@ -1063,7 +1066,8 @@ static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_
     if (ctx->k3_tma && i > 0) {  // experiment: TMA-staged tap tiles for the LINEAR passes
       CPoissonTmaArgs t{};
       t.a = a;
-      t.box_w = kTileW + 2 * a.reach_x; t.box_h = kTileH + 2 * a.reach_y;
+      t.box_w = (kTileW + 2 * a.reach_x) | 1;  // odd row pitch in texels: consecutive tile rows start 4 banks apart
+      t.box_h = kTileH + 2 * a.reach_y;
       if (encode_texel_map(&t.map_in, a.in.p, W, H, (size_t)a.in.pitch, t.box_w, t.box_h) && encode_texel_map(&t.map_nrdz, a.nrdz.p, W, H, (size_t)a.nrdz.pitch, t.box_w, t.box_h)) {
         LAUNCHED(launch_cpoisson_tma(t, cs));
         continue;
@@ -1081,6 +1085,7 @@ static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_
     a.composed = OutV{(unsigned char*)ch->composed2[cur].ptr, (long long)ch->composed2[cur].pitch};
     if (ch->group) a.composed_carry = ch->peer_composed[prev]; else peer_single(a.composed_carry, rpv(ch->composed2[prev]));
     a.W = W; a.H = H; a.cam = cam;
+    a.compose_mode = ctx->compose_mode;
     SpanGuard g(ch, cs, 4);
     LAUNCHED(launch_ccompose(a, cs));
   }

