@@ -430,7 +430,7 @@ def run_sharded(args):
         barrier()
         ms = reduce(ms, dist.ReduceOp.MAX)
         info = {"bounds": list(sh.bounds), "per_rank_kernel_ms": [round(c, 4) for c in sh.last_costs], "launches_per_frame": (ctx.launch_count - launches0) / steps,
-                "multi_gpu_bit_exact": bit_exact}
+                "multi_gpu_bit_exact": bit_exact, "peer_reads": sh.uses_peer_reads}
         return ms, info, sh, frames, cams
 
     clocks = ClockSampler(local)
@@ -486,8 +486,9 @@ def run_sharded(args):
                "inputs": "2 alternating synthetic G-buffer frames resident on every rank (365 MB per frame > 126 MB L2), moving camera", "l2": "inputs larger than L2; no explicit flush",
                "fast_math": True,
                "multi_gpu": {"sharding": "one contiguous row band per rank, borders rebalanced every 4 frames from the ranks' device-timed kernel cost; halo rows recomputed locally",
-                             "exchange": "none per pass; last frame's composed / dn history is read in place on the owning rank (CUDA IPC peer mappings over NVLink); one NCCL all-gather of "
-                                         f"{world} floats per frame (kernel costs) doubles as the frame barrier",
+                             "exchange": ("none per pass; last frame's composed / dn history is read in place on the owning rank (CUDA IPC peer mappings over NVLink); one NCCL all-gather of "
+                                          f"{world} floats per frame (kernel costs) doubles as the frame barrier") if info["peer_reads"] else
+                                         "FALLBACK: peer mappings unavailable (or RFX_GROUP_EXCHANGE=allgather) - composed + dn rows replicated with an NCCL exchange after every frame",
                              "bounds_during_timed_frames": info["bounds"], "per_rank_kernel_ms_per_frame": info["per_rank_kernel_ms"], "launches_per_frame_per_rank": info["launches_per_frame"]}}
         line = {"metric": "SSGI+denoise Mpixels/s at 4K", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 accumulate planes)", "data": "synthetic", "impl": "ours", "config": cfg,

@@ -409,6 +409,9 @@ rfx_status rfx_group_set_bounds(rfx_group* group, const uint32_t* bounds);   /* 
 /* every > 0: move the borders towards equal device-timed kernel cost every `every` frames, from times `lag` frames old */
 rfx_status rfx_group_set_rebalance(rfx_group* group, int32_t every, int32_t lag);
 rfx_status rfx_group_last_costs(const rfx_group* group, float* ms_per_rank);  /* the times the last rebalance used */
+/* 1: history rows are read in place on their owner (CUDA IPC peer mappings); 0: the mappings could not be opened on some rank (or
+ * RFX_GROUP_EXCHANGE=allgather is set) and the group replicates the two history planes with an NCCL exchange after every frame */
+int32_t rfx_group_uses_peer_reads(const rfx_group* group);
 /* in lockstep on every rank, no communication: applies the border move that is due and returns the borders of the NEXT frame
  * (render_sharded calls it implicitly; a host path calls it first to size its uploads) */
 rfx_status rfx_group_begin_frame(rfx_group* group, uint32_t* bounds_out);

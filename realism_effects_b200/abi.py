@@ -192,6 +192,7 @@ def _sig(lib):
     lib.rfx_group_destroy.restype = None
     lib.rfx_group_rank.argtypes = [vp]
     lib.rfx_group_world.argtypes = [vp]
+    lib.rfx_group_uses_peer_reads.argtypes = [vp]
     lib.rfx_group_attach_chain.argtypes = [vp, vp]
     lib.rfx_group_get_bounds.argtypes = [vp, U32P]
     lib.rfx_group_set_bounds.argtypes = [vp, U32P]
@@ -215,7 +216,7 @@ EXPORTS = [
     "rfx_ssgi_chain_reset", "rfx_ssgi_chain_render", "rfx_ssgi_chain_output", "rfx_ssgi_chain_render_host",
     "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host", "rfx_ssgi_chain_render_part",
     "rfx_ssgi_chain_set_profiling", "rfx_ssgi_chain_get_profile", "rfx_ssgi_chain_set_options", "rfx_ssgi_chain_render_ranges", "rfx_ssgi_chain_render_blocks",
-    "rfx_plane_download_rows", "rfx_group_get_unique_id", "rfx_group_create", "rfx_group_destroy", "rfx_group_rank", "rfx_group_world",
+    "rfx_plane_download_rows", "rfx_group_get_unique_id", "rfx_group_create", "rfx_group_destroy", "rfx_group_rank", "rfx_group_world", "rfx_group_uses_peer_reads",
     "rfx_group_attach_chain", "rfx_group_get_bounds", "rfx_group_set_bounds", "rfx_group_set_rebalance", "rfx_group_last_costs",
     "rfx_group_begin_frame", "rfx_group_get_last_bounds", "rfx_group_allgather_rows", "rfx_ssgi_chain_render_sharded", "rfx_shard_ranges",
     "rfx_shard_rebalance",

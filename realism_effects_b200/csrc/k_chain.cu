@@ -288,11 +288,12 @@ cudaError_t launch_ctemporal(const CTemporalArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------------------
 // K4 as a device function: constructGlobalIllumination (denoiser_compose_functions.glsl:53-107)
 // ------------------------------------------------------------------------------------------------------------------
-// Arithmetic precision is a template parameter because it was MEASURED to matter (tools/parity_at_size.py at 4K): the two fp16 inputs
-// already sit up to one fp16 ulp (9.8e-4) from the oracle's, so composed pixels crowd the 1e-3 line.  CM = 0: the exact K4's IEEE
-// division / sqrt (k_denoise.cu: gi_compose_kernel); 1: SFU rcp / rsqrt / sqrt (2^-22: pushed another 2.4e-4 of the pixels over the line);
-// 2: SFU seed + one Newton step (<= 1 ulp, a fifth of the IEEE instruction count).  The pixel-centre fetch is the centre texel and
-// pow(x, 5) is multiplies in every mode, as in the round-1 fast K4.  profiles/r02_compose_modes.txt has the three measurements.
+// Arithmetic precision is a template parameter because it was MEASURED to matter (tools/parity_at_size.py at 4K, profiles/r02_compose_modes.txt):
+// the two fp16 inputs already sit up to one fp16 ulp (9.8e-4) from the oracle's, so composed pixels crowd the 1e-3 line.
+//   CM = 0  the exact K4's IEEE division / sqrt (k_denoise.cu: gi_compose_kernel): 3.5-4.4e-4 of the pixels outside 1e-3 — the default;
+//   CM = 1  SFU rcp / rsqrt / sqrt / ex2 (2^-22): 6.1-6.9e-4, 0.08 ms per 4K frame faster;
+//   CM = 2  SFU seed + one Newton step (<= 1 ulp): 6.0-6.9e-4 — no better than 1, so the residue is not the reciprocals' precision.
+// The pixel-centre fetch is the centre texel and pow(x, 5) is multiplies in every mode, as in the round-1 fast K4.
 template <int CM> RFX_D float cm_rsqrt(float x) {
   if (CM == 0) return 1.0f / sqrtf(x);
   const float y = fx_rsqrt(x);

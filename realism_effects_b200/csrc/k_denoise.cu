@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(256) gbuffer_decode_kernel(PV gb, OutV nrd, in
   if (x >= W || y >= row1) return;
   const float4 g = ld_f4(gb, x, y);
   const v3 n = unpackNormal(gbuffer_texture ? g.y : g.z);
-  const float r = gbuffer_texture ? gb_roughness(g.z) : gb_roughness(0.0f);
+  // .w: roughness (packed gBuffer) or, for the velocity layout, the texel's own depth (its taps read depth from there: poisson_denoise.frag:58-60)
+  const float r = gbuffer_texture ? gb_roughness(g.z) : g.w;
   st_f4(nrd.p, nrd.pitch, x, y, make_float4(n.x, n.y, n.z, r));
 }
 // Decodes the rows the Poisson taps of `segs` can reach: every output segment widened by `halo` rows (ceil(radius) + 1: tap offsets
@@ -191,7 +192,7 @@ RFX_D void fetch2(const PoissonArgs& a, v2 uv, bool two, v3& c0, v3& c1, float* 
 }
 
 // TC planes; plane j is "specular" per a.spec0/spec1; with TC == 2 plane 1 reads in1, with TC == 1 the single plane reads in0.
-template <int TC, bool LINEAR>
+template <int TC, bool LINEAR, bool GB>
 #ifndef RFX_K3_MIN_BLOCKS
 #define RFX_K3_MIN_BLOCKS 4
 #endif
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, RFX_K3_MIN_BLOCKS) poisson_fast_kern
   const float fwn = length(fwidth_3(normal));
   if (!active) return;
   if (depth == 1.0f && fwd == 0.0f) return;
-  const float roughness = nc.w;
+  const float roughness = GB ? nc.w : 0.0f;  // without GBUFFER_TEXTURE getMaterial() decodes the null sampler's (0,0,0,1): roughness 0 (A8)
 
   v3 rgb[2];
   float alpha[2], lumc[2], age[2], tw[2];
@@ -244,13 +245,20 @@ __global__ void __launch_bounds__(kThreads, RFX_K3_MIN_BLOCKS) poisson_fast_kern
     const float ox = a.tap_ox[i], oy = a.tap_oy[i];  // POISSON[i] / resolution, divided on the host (IEEE, same value)
     const v2 nuv = mk2(vUv.x + (m00 * ox + m10 * oy), vUv.y + (m01 * ox + m11 * oy));
     const int nx = nearest_i(nuv.x, a.W), ny = nearest_i(nuv.y, a.H);
-    const float ndepth = ld_r32f(a.depth, nx, ny);
-    if (ndepth == 1.0f) continue;  // wBasic = 0 => w = 0 for every plane: the tap contributes nothing
-    const float4 nn = ld_f4(a.nrd, nx, ny);
+    float4 nn;
+    float ndepth;
+    if (GB) {
+      ndepth = ld_r32f(a.depth, nx, ny);
+      if (ndepth == 1.0f) continue;  // wBasic = 0 => w = 0 for every plane: the tap contributes nothing
+      nn = ld_f4(a.nrd, nx, ny);
+    } else {  // velocity layout: the tap's depth is the normal texel's alpha
+      nn = ld_f4(a.nrd, nx, ny);
+      ndepth = nn.w;
+      if (ndepth == 1.0f) continue;
+    }
     const float normalDiff = 1.0f - fmaxf(dot(normal, mk3(nn.x, nn.y, nn.z)), 0.0f);
     const float depthDiff = 10000.0f * fabsf(depth - ndepth);
-    const float roughnessDiff = fabsf(roughness - nn.w);
-    const float A = -normalDiff * a.normal_phi - depthDiff * a.depth_phi - roughnessDiff * a.roughness_phi;
+    const float A = GB ? -normalDiff * a.normal_phi - depthDiff * a.depth_phi - fabsf(roughness - nn.w) * a.roughness_phi : -normalDiff * a.normal_phi - depthDiff * a.depth_phi;
     const float A2 = A * RFX_LOG2E;
     const float wdA = ex2a(A2 * 0.1f);
     v3 c[2];
@@ -281,11 +289,10 @@ cudaError_t launch_poisson_fast(const PoissonArgs& a, cudaStream_t s) {
   dim3 grid((a.W + kTileW - 1) / kTileW, a.segs.tiles);
   if (a.input_linear && !a.in_half) return cudaErrorInvalidValue;
   if (!a.input_linear && a.in_half) return cudaErrorNotSupported;
-  if (a.texture_count == 2) {
-    if (a.input_linear) poisson_fast_kernel<2, true><<<grid, kThreads, 0, s>>>(a); else poisson_fast_kernel<2, false><<<grid, kThreads, 0, s>>>(a);
-  } else {
-    if (a.input_linear) poisson_fast_kernel<1, true><<<grid, kThreads, 0, s>>>(a); else poisson_fast_kernel<1, false><<<grid, kThreads, 0, s>>>(a);
-  }
+#define RFX_PF(TC, LIN) do { if (a.gbuffer_texture) poisson_fast_kernel<TC, LIN, true><<<grid, kThreads, 0, s>>>(a); else poisson_fast_kernel<TC, LIN, false><<<grid, kThreads, 0, s>>>(a); } while (0)
+  if (a.texture_count == 2) { if (a.input_linear) RFX_PF(2, true); else RFX_PF(2, false); }
+  else { if (a.input_linear) RFX_PF(1, true); else RFX_PF(1, false); }
+#undef RFX_PF
   return cudaGetLastError();
 }
 

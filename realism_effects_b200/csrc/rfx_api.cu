@@ -52,7 +52,7 @@ struct rfx_ctx {
   const RowSegs* segs_override = nullptr;  // set by the native chain: all owned row blocks in ONE launch
   int k3_tma = 1;     // RFX_K3_TMA=0 disables the TMA-staged tap tiles of the Poisson passes >= 1 (same bytes out; measured 0.39 vs 0.42 ms per pass at 4K)
   int k1_batch = 4;   // RFX_K1_BATCH: march steps fetched together (1, 2, 4); measured at 4K: 1.195 / 1.119 / 1.079 ms
-  int compose_mode = 2;  // RFX_COMPOSE_MODE: arithmetic of the fused K4 (0 IEEE, 1 SFU, 2 SFU + Newton)
+  int compose_mode = 0;  // RFX_COMPOSE_MODE: arithmetic of the fused K4: 0 IEEE (default: 4.4e-4 of the 4K pixels outside 1e-3), 1 SFU, 2 SFU + Newton (both 6.9e-4, 0.06 ms faster)
   int legacy_k1 = 0;  // RFX_LEGACY_K1=1 in the environment: the round-1 fast K1 kernel (A/B timing)
   const PeerPV* peer_accumulated = nullptr;  // set by the native chain in a row-sharded group: K1's `accumulated` rows live on their owners
 };
@@ -567,7 +567,7 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
   if (st != RFX_OK) return st;
   if (p->blue_noise_index == 0) return fail(ctx, RFX_ERR_UNSUPPORTED, "poisson: blue_noise_index 0 is not used by this pass");
   a.rot_table = ctx->rot_table;
-  const bool fast = ctx->fast_math && p->gbuffer_texture && ((p->input_linear && a.in_half) || (!p->input_linear && !a.in_half));
+  const bool fast = ctx->fast_math && ((p->input_linear && a.in_half) || (!p->input_linear && !a.in_half));
   if (!fast) {
     LAUNCHED(launch_poisson(a, pick(ctx, stream)));
     return RFX_OK;
@@ -583,7 +583,8 @@ rfx_status rfx_poisson_denoise_launch(rfx_ctx* ctx, void* stream, const rfx_pois
     ctx->nrd_reuse = false;
   }
   if (!ctx->nrd_reuse)  // (the chain's first pass of a frame has the widest rows of all its passes, so its decode serves the later ones)
-    LAUNCHED(launch_gbuffer_decode(a.gb, OutV{(unsigned char*)ctx->nrd, (long long)ctx->nrd_pitch}, a.W, a.H, 1, a.segs, (int)std::ceil(p->radius) + 1, pick(ctx, stream)));
+    LAUNCHED(launch_gbuffer_decode(a.gb, OutV{(unsigned char*)ctx->nrd, (long long)ctx->nrd_pitch}, a.W, a.H, p->gbuffer_texture ? 1 : 0, a.segs,
+                                   (int)std::ceil(p->radius * std::max(1.0f, (float)a.H / (float)a.W)) + 1, pick(ctx, stream)));
   a.nrd = PV{(const unsigned char*)ctx->nrd, a.W, a.H, (long long)ctx->nrd_pitch};
   {
     const float SQ = 1.41421356237f;

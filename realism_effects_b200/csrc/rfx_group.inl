@@ -138,6 +138,7 @@ struct rfx_group {
   std::vector<uint32_t> bounds_ring[RFX_GROUP_RING];  // bands each recent frame was rendered with
   uint64_t frame = 0;
   bool began = false;  // begin_frame already ran for the frame about to be rendered
+  bool use_peer = true;  // history rows read in place on their owner (CUDA IPC); false: replicated by an NCCL exchange after every frame
   // device-timed cost of this rank's kernels, all-gathered every frame (the collective doubles as the frame barrier)
   unsigned long long* d_t0 = nullptr;
   float* d_ms = nullptr;     // [1 + world]: own, then everyone's
@@ -202,6 +203,7 @@ void rfx_group_destroy(rfx_group* g) {
 
 int32_t rfx_group_rank(const rfx_group* g) { return g ? g->rank : -1; }
 int32_t rfx_group_world(const rfx_group* g) { return g ? g->world : 0; }
+int32_t rfx_group_uses_peer_reads(const rfx_group* g) { return g && g->use_peer ? 1 : 0; }
 
 // Collective.  Attaches a fast SSGI chain (same options on every rank) to the group: every rank exports its double-buffered
 // `composed` and `dn` planes (CUDA IPC), the handles are all-gathered and every peer's planes are mapped here.  Bands start equal.
@@ -227,15 +229,33 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpy(hs.data(), d + sizeof my, sizeof(my) * (size_t)n, cudaMemcpyDeviceToHost));
     CU(cudaFree(d));
-    for (int r = 0; r < n; r++)
-      for (int i = 0; i < 4; i++) {
+    int ok = 1;
+    if (const char* e = getenv("RFX_GROUP_EXCHANGE")) ok = strcmp(e, "allgather") != 0;  // force the replicated fallback (A/B measurements)
+    for (int r = 0; r < n && ok; r++)
+      for (int i = 0; i < 4 && ok; i++) {
         if (r == g->rank) { all[(size_t)r * 4 + i] = mine[i]; continue; }
         void* p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, hs[(size_t)r * 4 + i], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) return fail(ctx, RFX_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, plane %d) failed: %s", r, i, cudaGetErrorString(e));
+        if (e != cudaSuccess) { ok = 0; cudaGetLastError(); ctx->err = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e); break; }
         g->opened.push_back(p);
         all[(size_t)r * 4 + i] = p;
       }
+    // every rank must take the same path: all-gather the flags (device bounce) and AND them
+    int* dflag = nullptr;
+    CU(cudaMalloc(&dflag, sizeof(int) * (size_t)(n + 1)));
+    CU(cudaMemcpy(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NC(nccl_api()->AllGather(dflag, dflag + 1, sizeof(int), ncclChar, g->comm, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> flags((size_t)n);
+    CU(cudaMemcpy(flags.data(), dflag + 1, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    CU(cudaFree(dflag));
+    for (int r = 0; r < n; r++) ok = ok && flags[(size_t)r];
+    g->use_peer = ok != 0;
+    if (!g->use_peer) {  // replicated fallback: every rank keeps full copies, exchanged after every frame (rfx_group_allgather_rows)
+      for (void* p : g->opened) cudaIpcCloseMemHandle(p);
+      g->opened.clear();
+      for (int r = 0; r < n; r++) for (int i = 0; i < 4; i++) all[(size_t)r * 4 + i] = mine[i];
+    }
   } else {
     for (int i = 0; i < 4; i++) all[i] = mine[i];
   }
@@ -246,7 +266,7 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     PeerPV& pd = ch->peer_dn[b];
     pd = PeerPV{};
     pd.local = PV{(const unsigned char*)ch->dnB16[b].p, W, H, (long long)ch->dnB16[b].pitch};
-    pc.n = pd.n = n;
+    pc.n = pd.n = g->use_peer ? n : 1;
     for (int r = 0; r < n; r++) { pc.base[r] = (const unsigned char*)all[(size_t)r * 4 + b]; pd.base[r] = (const unsigned char*)all[(size_t)r * 4 + 2 + b]; }
   }
   g->bounds.assign((size_t)n + 1, 0);
@@ -353,7 +373,7 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
   for (PeerPV* p : {&ch->peer_composed[prev], &ch->peer_dn[prev]}) {
     for (int i = 0; i <= n; i++) p->bound[i] = (int)pb[i];
     p->own0 = (int)pb[g->rank]; p->own1 = (int)pb[g->rank + 1];
-    if (g->frame == 0) { p->own0 = 0; p->own1 = (int)ch->opt.height; }  // nothing was rendered yet: every plane is zero everywhere
+    if (g->frame == 0 || !g->use_peer) { p->own0 = 0; p->own1 = (int)ch->opt.height; }  // nothing rendered yet (all zero) / replicated planes: every row is local
   }
   const uint32_t n_launches = 3u + 2u * (uint32_t)ch->opt.denoise_iterations;
   std::vector<uint32_t> ranges((size_t)n_launches * 2);
@@ -363,6 +383,12 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
   if ((st = chain_render_impl(ch, stream, f, ranges.data(), 1, 0, 0xffffffffu)) != RFX_OK) return st;
   elapsed_kernel<<<1, 1, 0, cs>>>(g->d_t0, g->d_ms);
   ctx->launches += 2;
+  if (!g->use_peer && n > 1) {  // replicated fallback: every rank's rows of this frame's history planes to every other rank (32 B/px of the whole frame)
+    rfx_plane dnp{};
+    dnp.ptr = ch->dnB16[cur].p; dnp.width = ch->opt.width; dnp.height = ch->opt.height; dnp.pitch = ch->dnB16[cur].pitch; dnp.format = RFX_FMT_RGBA32F;
+    if ((st = rfx_group_allgather_rows(g, stream, &ch->composed2[cur], g->bounds.data())) != RFX_OK) return st;
+    if ((st = rfx_group_allgather_rows(g, stream, &dnp, g->bounds.data())) != RFX_OK) return st;
+  }
   const int slot = (int)(g->frame % RFX_GROUP_RING);
   NC(nccl_api()->AllGather(g->d_ms, g->d_ms + 1, 1, ncclFloat, g->comm, cs));  // every rank's frame is complete when this completes
   CU(cudaMemcpyAsync(g->h_ms + (size_t)slot * n, g->d_ms + 1, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, cs));

@@ -251,6 +251,11 @@ class ShardedSsgiChain:
         return b[self.rank], b[self.rank + 1]
 
     @property
+    def uses_peer_reads(self) -> bool:
+        """True: history rows are read in place on their owner over NVLink; False: replicated by an NCCL exchange every frame (fallback)"""
+        return bool(self.lib.rfx_group_uses_peer_reads(self.g))
+
+    @property
     def last_costs(self) -> list:
         c = (self._C.c_float * self.world)()
         self.ctx._chk(self.lib.rfx_group_last_costs(self.g, c))

@@ -26,6 +26,8 @@ def _worker(rank, world, port, q, case):
     from realism_effects_b200 import abi, engine, parallel
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if case.get("exchange"):
+        os.environ["RFX_GROUP_EXCHANGE"] = case["exchange"]
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only: carries the 128-byte NCCL id
     try:
@@ -34,6 +36,7 @@ def _worker(rank, world, port, q, case):
         ctx = engine.Context(rank, inp.blue)
         ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
         chain = parallel.ShardedSsgiChain(ctx, ch.chain_options(inp, o), rebalance_every=case.get("every", 0), rebalance_lag=1)
+        assert chain.uses_peer_reads == (case.get("exchange") != "allgather")
         keep, rows, bands = [], [], []
         for t, fr in enumerate(inp.frames):
             if case.get("forced"):  # borders that jump between frames (every rank passes the same values)
@@ -78,6 +81,7 @@ CASES = [
     dict(w=256, h=256, frames=4, iters=1, every=1),                                          # cost-driven borders, every frame
     dict(w=192, h=256, frames=4, iters=1, forced=[(0, 128, 256), (0, 64, 256), (0, 192, 256), (0, 112, 256)]),  # jumping borders
     dict(w=144, h=256, frames=3, iters=2),                                                   # portrait: Poisson halo = ceil(3 * 256/144) + 1
+    dict(w=256, h=256, frames=4, iters=1, every=1, exchange="allgather"),                    # the replicated fallback (no peer mappings)
 ]
 
 
