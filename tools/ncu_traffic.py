@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 KEY = [("ssgi_fast_kernel", "K1_ssgi_trace"), ("ssgi_kernel", "K1_ssgi_trace"), ("ctemporal_kernel", "K2_temporal_reproject"), ("temporal_kernel", "K2_temporal_reproject"),
-       ("cpoisson_kernel<1,", "K3_poisson_pass0"), ("cpoisson_kernel<0,", "K3_poisson_pass1plus"), ("cpoisson_tma_kernel", "K3_poisson_pass1plus_tma"),
+       ("cpoisson_kernel<1,", "K3_poisson_pass0"), ("cpoisson_kernel<0,", "K3_poisson_pass1plus"), ("cpoisson_tma_kernel", "K3_poisson_pass1plus"),
        ("poisson_fast_kernel<2, 0>", "K3_poisson_pass0"), ("poisson_fast_kernel<2, 1>", "K3_poisson_pass1plus"), ("gi_compose_kernel", "K4_gi_compose"),
        ("viewz_kernel", "prepass_viewz"), ("cdecode_kernel", "prepass_gbuffer_decode"), ("gbuffer_decode_kernel", "prepass_gbuffer_decode")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
