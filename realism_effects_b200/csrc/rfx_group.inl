@@ -55,6 +55,38 @@ __global__ void elapsed_kernel(const unsigned long long* t0, float* ms) {
   *ms = (float)((double)(v - *t0) * 1e-6);
 }
 
+// Frame barrier through peer memory (RFX_GROUP_BARRIER=flags): after its last kernel every rank stores (frame, kernel ms) into its
+// slot of EVERY rank's flag array (peer stores over NVLink); the next thing on each rank's stream spins until all slots carry the
+// frame.  Same information as the NCCL all-gather, without a collective launch.  A rank that never arrives makes the waiters give
+// up after ~2^32 cycles and raise `err` instead of hanging the GPU.
+struct SyncPeers { unsigned long long* slots[RFX_MAX_PEERS]; int n; };
+__global__ void publish_kernel(const unsigned long long* t0, float* ms_out, SyncPeers sp, int rank, unsigned frame) {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  const float ms = (float)((double)(v - *t0) * 1e-6);
+  *ms_out = ms;
+  const unsigned long long word = ((unsigned long long)frame << 32) | (unsigned long long)__float_as_uint(ms);
+  __threadfence_system();  // this rank's frame (earlier kernels on the stream) is visible before the flag is
+  // two slot sets by frame parity: a rank can publish frame f + 1 before a slow peer has READ its frame-f word, but not f + 2
+  // (that needs the peer's own f + 1 flag, which the peer sets after its frame-f wait) - so every rank reads the same costs
+  const int set = (int)(frame & 1u) * RFX_MAX_PEERS;
+  for (int p = 0; p < sp.n; p++) *((volatile unsigned long long*)(sp.slots[p] + set + rank)) = word;
+}
+__global__ void wait_flags_kernel(volatile unsigned long long* slots, int n, unsigned frame, float* ms_all, int* err) {
+  const int r = threadIdx.x;
+  if (r < n) {
+    slots += (frame & 1u) * RFX_MAX_PEERS;
+    const long long start = clock64();
+    unsigned long long v = slots[r];
+    while ((unsigned)(v >> 32) != frame) {
+      if (clock64() - start > (1LL << 32)) { *err = 1; break; }
+      v = slots[r];
+    }
+    ms_all[r] = __uint_as_float((unsigned)(v & 0xffffffffull));
+  }
+  __threadfence_system();
+}
+
 }  // namespace
 
 // ---- sharding plan (pure host arithmetic; mirrored by realism_effects_b200/parallel.py:ShardPlan for the CPU tests) -------------
@@ -139,6 +171,10 @@ struct rfx_group {
   uint64_t frame = 0;
   bool began = false;  // begin_frame already ran for the frame about to be rendered
   bool use_peer = true;  // history rows read in place on their owner (CUDA IPC); false: replicated by an NCCL exchange after every frame
+  bool use_flags = false;  // frame barrier through peer-memory flags instead of the NCCL all-gather (RFX_GROUP_BARRIER=flags; needs use_peer)
+  unsigned long long* d_sync = nullptr;  // [2][RFX_MAX_PEERS] slots by frame parity: rank r's (frame, ms) word, written by rank r
+  SyncPeers sync_peers{};
+  int* d_err = nullptr;
   // device-timed cost of this rank's kernels, all-gathered every frame (the collective doubles as the frame barrier)
   unsigned long long* d_t0 = nullptr;
   float* d_ms = nullptr;     // [1 + world]: own, then everyone's
@@ -195,7 +231,7 @@ void rfx_group_destroy(rfx_group* g) {
   if (g->chain) { g->chain->group = nullptr; g->chain = nullptr; }
   for (void* p : g->opened) cudaIpcCloseMemHandle(p);
   if (g->comm) nccl_api()->CommDestroy(g->comm);
-  cudaFree(g->d_t0); cudaFree(g->d_ms);
+  cudaFree(g->d_t0); cudaFree(g->d_ms); cudaFree(g->d_sync); cudaFree(g->d_err);
   if (g->h_ms) cudaFreeHost(g->h_ms);
   for (cudaEvent_t e : g->ev) if (e) cudaEventDestroy(e);
   delete g;
@@ -216,12 +252,19 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
   const int W = (int)ch->opt.width, H = (int)ch->opt.height, n = g->world;
   if (H < n * 64) return fail(ctx, RFX_ERR_UNSUPPORTED, "group_attach_chain: need at least 64 rows per rank");
   CU(cudaSetDevice(ctx->device));
-  void* mine[4] = {ch->composed2[0].ptr, ch->composed2[1].ptr, ch->dnB16[0].p, ch->dnB16[1].p};
-  std::vector<void*> all((size_t)4 * n, nullptr);
+  if (!g->d_sync) {
+    CU(cudaMalloc(&g->d_sync, sizeof(unsigned long long) * 2 * RFX_MAX_PEERS));
+    CU(cudaMemset(g->d_sync, 0, sizeof(unsigned long long) * 2 * RFX_MAX_PEERS));
+    CU(cudaMalloc(&g->d_err, sizeof(int)));
+    CU(cudaMemset(g->d_err, 0, sizeof(int)));
+  }
+  constexpr int NH = 5;  // exported allocations per rank: composed x2, dn x2, the flag array
+  void* mine[NH] = {ch->composed2[0].ptr, ch->composed2[1].ptr, ch->dnB16[0].p, ch->dnB16[1].p, g->d_sync};
+  std::vector<void*> all((size_t)NH * n, nullptr);
   if (n > 1) {
-    std::vector<cudaIpcMemHandle_t> hs((size_t)4 * n);
-    cudaIpcMemHandle_t my[4];
-    for (int i = 0; i < 4; i++) CU(cudaIpcGetMemHandle(&my[i], mine[i]));
+    std::vector<cudaIpcMemHandle_t> hs((size_t)NH * n);
+    cudaIpcMemHandle_t my[NH];
+    for (int i = 0; i < NH; i++) CU(cudaIpcGetMemHandle(&my[i], mine[i]));
     unsigned char* d = nullptr;
     CU(cudaMalloc(&d, sizeof(my) * (size_t)(n + 1)));
     CU(cudaMemcpy(d, my, sizeof my, cudaMemcpyHostToDevice));
@@ -232,13 +275,13 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     int ok = 1;
     if (const char* e = getenv("RFX_GROUP_EXCHANGE")) ok = strcmp(e, "allgather") != 0;  // force the replicated fallback (A/B measurements)
     for (int r = 0; r < n && ok; r++)
-      for (int i = 0; i < 4 && ok; i++) {
-        if (r == g->rank) { all[(size_t)r * 4 + i] = mine[i]; continue; }
+      for (int i = 0; i < NH && ok; i++) {
+        if (r == g->rank) { all[(size_t)r * NH + i] = mine[i]; continue; }
         void* p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, hs[(size_t)r * 4 + i], cudaIpcMemLazyEnablePeerAccess);
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hs[(size_t)r * NH + i], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { ok = 0; cudaGetLastError(); ctx->err = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e); break; }
         g->opened.push_back(p);
-        all[(size_t)r * 4 + i] = p;
+        all[(size_t)r * NH + i] = p;
       }
     // every rank must take the same path: all-gather the flags (device bounce) and AND them
     int* dflag = nullptr;
@@ -254,10 +297,10 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     if (!g->use_peer) {  // replicated fallback: every rank keeps full copies, exchanged after every frame (rfx_group_allgather_rows)
       for (void* p : g->opened) cudaIpcCloseMemHandle(p);
       g->opened.clear();
-      for (int r = 0; r < n; r++) for (int i = 0; i < 4; i++) all[(size_t)r * 4 + i] = mine[i];
+      for (int r = 0; r < n; r++) for (int i = 0; i < NH; i++) all[(size_t)r * NH + i] = mine[i];
     }
   } else {
-    for (int i = 0; i < 4; i++) all[i] = mine[i];
+    for (int i = 0; i < NH; i++) all[i] = mine[i];
   }
   for (int b = 0; b < 2; b++) {
     PeerPV& pc = ch->peer_composed[b];
@@ -267,8 +310,12 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     pd = PeerPV{};
     pd.local = PV{(const unsigned char*)ch->dnB16[b].p, W, H, (long long)ch->dnB16[b].pitch};
     pc.n = pd.n = g->use_peer ? n : 1;
-    for (int r = 0; r < n; r++) { pc.base[r] = (const unsigned char*)all[(size_t)r * 4 + b]; pd.base[r] = (const unsigned char*)all[(size_t)r * 4 + 2 + b]; }
+    for (int r = 0; r < n; r++) { pc.base[r] = (const unsigned char*)all[(size_t)r * NH + b]; pd.base[r] = (const unsigned char*)all[(size_t)r * NH + 2 + b]; }
   }
+  g->sync_peers.n = n;
+  for (int r = 0; r < n; r++) g->sync_peers.slots[r] = (unsigned long long*)all[(size_t)r * NH + 4];
+  g->use_flags = false;
+  if (const char* e = getenv("RFX_GROUP_BARRIER")) g->use_flags = g->use_peer && n > 1 && strcmp(e, "flags") == 0;
   g->bounds.assign((size_t)n + 1, 0);
   for (int i = 0; i < n; i++) g->bounds[i] = (uint32_t)(std::lround((double)H * i / n / 16.0) * 16);
   g->bounds[n] = (uint32_t)H;
@@ -381,8 +428,14 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
   if (st != RFX_OK) return fail(ctx, st, "render_sharded: bad band");
   stamp_kernel<<<1, 1, 0, cs>>>(g->d_t0);
   if ((st = chain_render_impl(ch, stream, f, ranges.data(), 1, 0, 0xffffffffu)) != RFX_OK) return st;
-  elapsed_kernel<<<1, 1, 0, cs>>>(g->d_t0, g->d_ms);
-  ctx->launches += 2;
+  if (g->use_flags) {  // barrier + cost exchange through peer-memory flags
+    publish_kernel<<<1, 1, 0, cs>>>(g->d_t0, g->d_ms, g->sync_peers, g->rank, (unsigned)(g->frame + 1));
+    wait_flags_kernel<<<1, 32, 0, cs>>>(g->d_sync, n, (unsigned)(g->frame + 1), g->d_ms + 1, g->d_err);
+    ctx->launches += 3;
+  } else {
+    elapsed_kernel<<<1, 1, 0, cs>>>(g->d_t0, g->d_ms);
+    ctx->launches += 2;
+  }
   if (!g->use_peer && n > 1) {  // replicated fallback: every rank's rows of this frame's history planes to every other rank (32 B/px of the whole frame)
     rfx_plane dnp{};
     dnp.ptr = ch->dnB16[cur].p; dnp.width = ch->opt.width; dnp.height = ch->opt.height; dnp.pitch = ch->dnB16[cur].pitch; dnp.format = RFX_FMT_RGBA32F;
@@ -390,7 +443,7 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
     if ((st = rfx_group_allgather_rows(g, stream, &dnp, g->bounds.data())) != RFX_OK) return st;
   }
   const int slot = (int)(g->frame % RFX_GROUP_RING);
-  NC(nccl_api()->AllGather(g->d_ms, g->d_ms + 1, 1, ncclFloat, g->comm, cs));  // every rank's frame is complete when this completes
+  if (!g->use_flags) NC(nccl_api()->AllGather(g->d_ms, g->d_ms + 1, 1, ncclFloat, g->comm, cs));  // every rank's frame is complete when this completes
   CU(cudaMemcpyAsync(g->h_ms + (size_t)slot * n, g->d_ms + 1, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, cs));
   CU(cudaEventRecord(g->ev[slot], cs));
   g->ev_valid[slot] = true;

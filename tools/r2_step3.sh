@@ -19,4 +19,5 @@ print('   exchange', m['exchange'][:90]); print('   c5', d.get('c5_8k'))
 PY
   tail -4 gpurun_out/$1.err; }
 run r02_n${N}_bench ""
+RFX_GROUP_BARRIER=flags run r02_n${N}_bench_flags "--no-c5"
 RFX_GROUP_EXCHANGE=allgather run r02_n${N}_bench_allgather "--no-c5"
