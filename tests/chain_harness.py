@@ -157,14 +157,18 @@ def chain_options(inp: Inputs, o: Opts) -> abi.ChainOptions:
 
 
 # ----------------------------------------------------------------------------------------------
-def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"), lean: bool = False):
+def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"), lean: bool = False, impl=None):
     """Returns a list (one dict per frame) of the planes named in `capture` (+ the per-pass inputs
     needed for isolated kernel tests under keys starting with '_'; lean=True drops those copies: at 4K they are
-    ~2.5 GB per frame)."""
-    import orc
+    ~2.5 GB per frame).  `impl`: the module that executes the passes — tests/orc.py (the C++ restatement, default) or
+    tests/refglsl.py (the reference's own shaders compiled for the CPU); both have the same pass signatures."""
+    import orc as _orc
+
+    orc = impl if impl is not None else _orc
+    Env = _orc.Env  # the env tables / mip chain container is shared (host-built inputs of K1)
 
     H, W = inp.height, inp.width
-    env = orc.Env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total) if o.use_envmap else None
+    env = Env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total) if o.use_envmap else None
     z32 = lambda: np.zeros((H, W, 4), np.float32)  # noqa: E731
     z16 = lambda: np.zeros((H, W, 4), np.float16)  # noqa: E731
     tr = [z32(), z32()]
