@@ -18,7 +18,8 @@ roofline: the dominant kernel's algorithmic bytes / its mean CUDA-event duration
           HBM copy bandwidth in MEASURED_PEAKS.json (+ the chain-level figure).
 parity  : the first frame of the timed workload against the CPU oracle's frame (the one cpu_baseline times anyway).
 configs : device time + roofline of the other single-GPU BASELINE configs (C1 motion blur 256^2, C2 SSGI 1080p, C4 HBAO 4K).
-cpu_baseline / --impl reference: the CPU restatement in oracle/ (the reference itself is WebGL-only and cannot run here: no GL,
+cpu_baseline / --impl reference: the reference's own shaders compiled for the CPU (oracle/_ref, when built) or the CPU restatement in
+oracle/ (the reference's run time is WebGL-only and cannot run here: no GL,
           no JS engine) on the box's host cores, bounded sample, thread count pinned and reported.
 """
 from __future__ import annotations
@@ -523,18 +524,42 @@ def cpu_baseline_sample(ch, o, inp):
     ref = ch.run_oracle_chain(inp, o, capture=("composed",), lean=True)
     dt = time.perf_counter() - t0
     cores = int(orc.lib().orc_num_threads())
-    return ({"value": round(width * height * frames_n / 1e6 / dt, 4), "unit": "Mpixels/s", "cores": cores, "threads_requested": want, "kind": "port",
-             "sample": f"{frames_n} frame(s) of the same chain at {width}x{height} ({dt:.1f} s of CPU work; first frame => empty history)"}, ref[-1]["composed"])
+    out = {"value": round(width * height * frames_n / 1e6 / dt, 4), "unit": "Mpixels/s", "cores": cores, "threads_requested": want, "kind": "port",
+           "sample": f"{frames_n} frame(s) of the same chain at {width}x{height} ({dt:.1f} s of CPU work; first frame => empty history)"}
+    rs = reference_shaders()
+    if rs is not None:  # the reference's own shaders on the same cores, on a 1/16 sample (the port above also supplies the parity pixels)
+        small = ch.make_inputs(960, 540, 1, env_size=(1024, 512))
+        t0 = time.perf_counter()
+        ch.run_oracle_chain(small, o, capture=("composed",), lean=True, impl=rs)
+        dts = time.perf_counter() - t0
+        out["reference_shaders"] = {"value": round(960 * 540 / 1e6 / dts, 4), "unit": "Mpixels/s", "kind": "reference", "cores": cores,
+                                    "sample": f"one 960x540 frame of the same chain through oracle/_ref ({dts:.1f} s)"}
+    return (out, ref[-1]["composed"])
+
+
+def reference_shaders():
+    """tests/refglsl.py when the reference's own shaders, compiled for the CPU, can run the C3 chain here (oracle/_ref/*.so built by
+    __graft_entry__.build() from the reference checkout; they travel to the GPU box), else None"""
+    try:
+        import refglsl
+
+        return refglsl if refglsl.chain_available(0) else None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_reference(args):
-    """--impl reference: the reference's own implementation is WebGL-only (no GL / JS engine here), so the arm times the CPU
-    restatement in oracle/ with all host threads (pinned explicitly), each step a bounded sample of the workload."""
+    """--impl reference: the reference's run time is WebGL (no GL / JS engine here), so the arm runs the reference's OWN FRAGMENT
+    SHADERS compiled for the host CPU (oracle/_ref, kind "reference": the GLSL text of the reference on the GLSL runtime
+    oracle/ref/glsl_rt.h, driven by the reference's frame logic) with all host threads, each step a bounded sample of the workload.
+    Without those libraries it falls back to the C++ restatement in oracle/ (kind "port")."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     want = oracle_threads()
     import chain_harness as ch
     import orc
+
+    ref = reference_shaders()
 
     o = ch.Opts(denoise_iterations=DENOISE_ITERATIONS)
     sw, sh = (960, 540) if (args.cpu_width, args.cpu_height) == (0, 0) else (args.cpu_width, args.cpu_height)
@@ -547,7 +572,7 @@ def run_reference(args):
 
     def step_block(n):
         inp.frames = [frames[i % 2] for i in range(n)]
-        ch.run_oracle_chain(inp, o, capture=("composed",), lean=True)
+        ch.run_oracle_chain(inp, o, capture=("composed",), lean=True, impl=ref)
 
     step_block(Wm)
     t0 = time.perf_counter()
@@ -556,9 +581,11 @@ def run_reference(args):
     v = round(sw * sh / 1e6 / dt, 4)
     line = {"metric": "SSGI+denoise Mpixels/s at 4K", "value": v, "unit": "Mpixels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": Wm,
             "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS})+compose, CPU restatement (oracle/), bounded sample {sw}x{sh} per step "
-                                   f"(1/16 of the 4K frame), {cores} OpenMP threads"},
-            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": cores, "threads_requested": want, "kind": "port", "sample": f"{K} steps x one {sw}x{sh} frame (1/16 of the 4K frame)"},
+            "config": {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS})+compose, " +
+                                   ("the reference's own fragment shaders compiled for the CPU (oracle/_ref)" if ref else "CPU restatement (oracle/)") +
+                                   f", bounded sample {sw}x{sh} per step (1/16 of the 4K frame), {cores} OpenMP threads"},
+            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": cores, "threads_requested": want, "kind": "reference" if ref else "port",
+                             "sample": f"{K} steps x one {sw}x{sh} frame (1/16 of the 4K frame)"},
             "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 

@@ -289,4 +289,6 @@ def build(name: str, glsl: str, *, effect_main: bool = False, force: bool = Fals
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed for the transpiled shader {name} ({src}):\n{r.stderr[:6000]}")
         os.replace(so + ".tmp", so)
+        if not os.environ.get("RFX_KEEP_GENERATED"):
+            os.remove(src)  # the generated C++ carries the reference's shader text: not kept around
     return so, info

@@ -1,4 +1,4 @@
-// oracle/rfx_oracle.cpp — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see below).
+// oracle/rfx_oracle.cpp — TEST INFRASTRUCTURE ONLY.  PARITY PINNED BY THE REFERENCE'S OWN SHADERS (see below).
 //
 // CPU restatement (scalar fp32, C++17 + OpenMP) of the reference's per-pixel hot path, one
 // function per reference fragment shader, each citing the reference file:line it follows
@@ -7,12 +7,20 @@
 // bench.py can time a CPU baseline.  The product (realism_effects_b200/) never links,
 // imports or executes anything in this directory.
 //
-// PARITY UNPINNED: the reference ships no tests, golden images or known-answer vectors
-//  and its GLSL cannot be executed in this environment (no GL, no JS
-// engine).  This oracle is therefore a restatement checked by inspection against the GLSL,
-// by self-consistency properties and by independent numpy restatements of its leaf
-// functions and of every whole pass K1-K9 (tests/test_oracle_leaf.py,
-// tests/test_oracle_np_restatement.py) — not against output of a real WebGL run.
+// HOW IT IS PINNED.  The reference ships no tests, golden images or known-answer vectors
+//  and there is no GL / JS engine here, but its algorithm IS its GLSL
+// text: oracle/ref/ compiles that text (read from the reference checkout, assembled the
+// way the reference's JS assembles it) for the CPU on a GLSL language runtime
+// (oracle/ref/glsl_rt.h) into oracle/_ref/*.so — the reference run here.  This
+// restatement equals those shaders BIT FOR BIT on every plane of every pass: 8 chain
+// configurations + all effect passes (tools/pin_oracle.py), the chain at 1920x1080 x 3
+// frames and 3840x2160 x 2 frames (profiles/r02_pin_oracle_*.json), checked live by
+// tests/test_reference_glsl.py and, where the checkout is absent, against the committed
+// outputs of the reference shaders (tests/golden/, tests/test_oracle_chain_cpu.py).
+// What that does NOT pin: the reference's JavaScript host logic (uniform wiring, frame
+// sequencing, env CDF tables), which tests/chain_harness.py, tests/refglsl.py and
+// realism_effects_b200/synth.py restate from the JS, and the behaviour GLSL leaves to the
+// GL implementation, which oracle/glsl.h fixes once for both sides.
 //
 // Implementation-defined GL behaviour is fixed as documented in oracle/glsl.h.
 #include "glsl.h"

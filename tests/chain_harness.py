@@ -361,3 +361,42 @@ def traa_temporal_params(cam: abi.CameraS, cam_pos, prev: dict, keep_data: float
     p.full_accumulate, p.texture_count, p.input_type, p.log_transform, p.history_linear = 0, 1, abi.INPUT_DIFFUSE, 1, 1
     p.reproject_specular[:] = [0, 0]
     return p
+
+
+# ----------------------------------------------------------------------------------------------
+# pass sequences shared by the golden minting script (run on the reference shaders) and the tests (run on the oracle / the engine);
+# `m` is the module that executes the passes (tests/refglsl.py, tests/orc.py)
+# ----------------------------------------------------------------------------------------------
+def fog_params(cam_u, exp2):
+    p = abi.SsgiComposeParams()
+    p.use_fog, p.fog_exp2, p.perspective = 1, int(exp2), 1
+    p.fog_color[:] = [0.6, 0.7, 0.8]
+    p.fog_near, p.fog_far, p.fog_density = 2.0, 30.0, 0.05
+    p.camera_near, p.camera_far = float(cam_u["near"]), float(cam_u["far"])
+    return p
+
+
+def ao_denoise(m, f1, blue, ao):
+    """AOEffect's denoiser: 2 Poisson passes over one plane with the velocity-layout normals (non-GBUFFER branch)"""
+    H, W = f1["depth"].shape
+    tgtA, tgtB = np.zeros((H, W, 4), np.float16), np.zeros((H, W, 4), np.float16)
+    for i in range(2):
+        p = poisson_params(Opts(), 1234568 + i, False)
+        p.texture_count, p.gbuffer_texture, p.input_linear = 1, 0, 1
+        p.is_texture_specular[:] = [0, 0]
+        p.normal_phi, p.depth_phi, p.roughness_phi, p.specular_phi = 3.25, 2.0, 0.0, 0.0
+        out, _ = m.poisson_denoise(p, f1["depth"], f1["velocity"], ao if i == 0 else tgtA, None, blue, tgtA if i == 0 else tgtB, None)
+        if i == 0:
+            tgtA = out
+        else:
+            tgtB = out
+    return tgtA, tgtB
+
+
+def traa_two_frames(m, f0, f1):
+    z = np.zeros(f0["direct"].shape, np.float16)
+    p0 = traa_temporal_params(abi.make_camera(f0["cam"]), f0["cam"]["position"], f0["cam"], 0.0)
+    h0, _ = m.temporal_reproject(p0, f0["direct"], f0["velocity"], z, None, z, None, out_half=True)
+    p1 = traa_temporal_params(abi.make_camera(f1["cam"]), f1["cam"]["position"], f0["cam"], 1.0)
+    h1, _ = m.temporal_reproject(p1, f1["direct"], f1["velocity"], h0, None, h0, None, out_half=True)
+    return h0, h1

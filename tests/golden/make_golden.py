@@ -33,41 +33,6 @@ def store_inputs(d, inp):
         d[f"f{t}_moved"] = np.int32(fr["moved"])
 
 
-def fog_params(cam_u, exp2):
-    p = abi.SsgiComposeParams()
-    p.use_fog, p.fog_exp2, p.perspective = 1, int(exp2), 1
-    p.fog_color[:] = [0.6, 0.7, 0.8]
-    p.fog_near, p.fog_far, p.fog_density = 2.0, 30.0, 0.05
-    p.camera_near, p.camera_far = float(cam_u["near"]), float(cam_u["far"])
-    return p
-
-
-def ao_denoise(m, f1, blue, ao):
-    """AOEffect's denoiser: 2 Poisson passes over one plane with the velocity-layout normals (non-GBUFFER branch)"""
-    H, W = f1["depth"].shape
-    tgtA, tgtB = np.zeros((H, W, 4), np.float16), np.zeros((H, W, 4), np.float16)
-    for i in range(2):
-        p = ch.poisson_params(ch.Opts(), 1234568 + i, False)
-        p.texture_count, p.gbuffer_texture, p.input_linear = 1, 0, 1
-        p.is_texture_specular[:] = [0, 0]
-        p.normal_phi, p.depth_phi, p.roughness_phi, p.specular_phi = 3.25, 2.0, 0.0, 0.0
-        out, _ = m.poisson_denoise(p, f1["depth"], f1["velocity"], ao if i == 0 else tgtA, None, blue, tgtA if i == 0 else tgtB, None)
-        if i == 0:
-            tgtA = out
-        else:
-            tgtB = out
-    return tgtA, tgtB
-
-
-def traa_two_frames(m, f0, f1):
-    z = np.zeros(f0["direct"].shape, np.float16)
-    p0 = ch.traa_temporal_params(abi.make_camera(f0["cam"]), f0["cam"]["position"], f0["cam"], 0.0)
-    h0, _ = m.temporal_reproject(p0, f0["direct"], f0["velocity"], z, None, z, None, out_half=True)
-    p1 = ch.traa_temporal_params(abi.make_camera(f1["cam"]), f1["cam"]["position"], f0["cam"], 1.0)
-    h1, _ = m.temporal_reproject(p1, f1["direct"], f1["velocity"], h0, None, h0, None, out_half=True)
-    return h0, h1
-
-
 def main():
     assert ref.assemble.available(), "the reference checkout is needed"
     o = ch.Opts(steps=12, refine_steps=3)
@@ -87,11 +52,11 @@ def main():
     d["mb_velocity"] = vel
     d["motion_blur"] = ref.motion_blur(ch.motion_blur_params(W, H), vel, f1["direct"], inp.blue)
     d["traa_compose"] = ref.traa_compose(f1["direct"])
-    d["ao_dn_a"], d["ao_dn_b"] = ao_denoise(ref, f1, inp.blue, ao)
-    d["traa_h0"], d["traa_h1"] = traa_two_frames(ref, f0, f1)
+    d["ao_dn_a"], d["ao_dn_b"] = ch.ao_denoise(ref, f1, inp.blue, ao)
+    d["traa_h0"], d["traa_h1"] = ch.traa_two_frames(ref, f0, f1)
     d["k5_plain"] = ref.ssgi_compose(f1["depth"], out[1]["composed"], f1["direct"])
-    d["k5_fog"] = ref.ssgi_compose(f1["depth"], out[1]["composed"], f1["direct"], fog_params(f1["cam"], False))
-    d["k5_fog_exp2"] = ref.ssgi_compose(f1["depth"], out[1]["composed"], f1["direct"], fog_params(f1["cam"], True))
+    d["k5_fog"] = ref.ssgi_compose(f1["depth"], out[1]["composed"], f1["direct"], ch.fog_params(f1["cam"], False))
+    d["k5_fog_exp2"] = ref.ssgi_compose(f1["depth"], out[1]["composed"], f1["direct"], ch.fog_params(f1["cam"], True))
     path = os.path.join(HERE, "chain_96x54.npz")
     np.savez_compressed(path, **d)
     print("wrote", path, os.path.getsize(path), "bytes")

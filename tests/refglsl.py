@@ -56,9 +56,13 @@ class Shader:
 
     _cache: dict = {}
 
-    def __init__(self, name: str, **kw):
+    def __init__(self, name: str, glsl: str | None = None, **kw):
+        """name + kw: a pass of oracle/ref/assemble.py;  glsl: explicit shader text (the runtime's own tests)"""
         key = _key(name, kw)
-        if assemble.available():
+        if glsl is not None:
+            so, info = transpile.build(name, glsl)
+            self.n_out = len(info["outputs"])
+        elif assemble.available():
             glsl = getattr(assemble, name)(**kw)
             so, info = transpile.build(name, glsl)
             man = _manifest()
@@ -152,6 +156,56 @@ class Shader:
         fmts = (C.c_int * len(arrs))(*[f for f, _ in outs])
         self.lib.rtx_run(self.h, W, H, len(arrs), ptrs, fmts)
         return [a.view(np.float16) if f == F_RGBA16F else a for a, (f, _) in zip(arrs, outs)]
+
+
+# the variants the tests, smoke() and bench.py use: built by __graft_entry__.build() while the checkout is there, so that they are
+# available where it is not (the GPU box)
+STANDARD_VARIANTS = [
+    ("ssgi", dict(steps=20, refine_steps=5, mode=0, importance_sampling=True, missed_rays=False, use_direct_light=True, use_envmap=True, perspective=True)),
+    ("ssgi", dict(steps=12, refine_steps=3, mode=0, importance_sampling=True, missed_rays=False, use_direct_light=True, use_envmap=True, perspective=True)),
+    ("ssgi", dict(steps=20, refine_steps=5, mode=1, importance_sampling=True, missed_rays=False, use_direct_light=True, use_envmap=True, perspective=True)),
+    ("temporal_reproject", dict(texture_count=2, input_type=0, neighborhood_clamp=(False, True), reproject_specular=(False, True), log_transform=True,
+                                confidence_power=0.75, perspective=True)),
+    ("temporal_reproject", dict(texture_count=1, input_type=2, neighborhood_clamp=(True,), reproject_specular=(True,), log_transform=True,
+                                confidence_power=0.75, perspective=True)),
+    ("temporal_reproject", dict(texture_count=1, input_type=1, neighborhood_clamp=(True,), reproject_specular=(False,), log_transform=True,
+                                confidence_power=4.0, perspective=True)),
+    ("poisson_denoise", dict(input_type="diffuseSpecular", gbuffer=True)),
+    ("poisson_denoise", dict(input_type="specular", gbuffer=True)),
+    ("poisson_denoise", dict(input_type="diffuse", gbuffer=False)),
+    ("gi_compose", dict(input_type=0, perspective=True)),
+    ("gi_compose", dict(input_type=2, perspective=True)),
+    ("hbao", dict(spp=8)),
+    ("motion_blur", dict(samples=16)),
+    ("ao_compose", {}),
+    ("traa_compose", {}),
+    ("ssgi_compose", dict(fog=False, fog_exp2=False, perspective=True)),
+    ("ssgi_compose", dict(fog=True, fog_exp2=False, perspective=True)),
+    ("ssgi_compose", dict(fog=True, fog_exp2=True, perspective=True)),
+]
+
+
+def chain_available(mode: int = 0, steps: int = 20, refine_steps: int = 5) -> bool:
+    """can the default-option SSGI / SSR chain (K1, K2, K3, K4) run through the reference shaders here?"""
+    if assemble.available():
+        return True
+    need = [v for v in STANDARD_VARIANTS if v[0] in ("ssgi", "temporal_reproject", "poisson_denoise", "gi_compose")]
+    if mode == 0:
+        need = [need[i] for i in (0, 3, 6, 9)] if (steps, refine_steps) == (20, 5) else None
+    else:
+        need = [need[i] for i in (2, 4, 7, 10)] if (steps, refine_steps) == (20, 5) else None
+    return bool(need) and all(available(n, **kw) for n, kw in need)
+
+
+def prebuild(verbose: bool = False) -> int:
+    """compile every standard variant (needs the reference checkout); returns how many libraries exist afterwards"""
+    n = 0
+    for name, kw in STANDARD_VARIANTS:
+        Shader.get(name, **kw)
+        n += 1
+        if verbose:
+            print("reference shader", _key(name, kw))
+    return n
 
 
 # ------------------------------------------------------------------------------------------------ uniform wiring (the JS side)

@@ -179,7 +179,8 @@ def test_motion_blur_c1(built, frame_index, res):
 
 
 def test_chain_matches_golden_fixture(built):
-    """CUDA chain vs the committed golden outputs (minted from the oracle by tests/golden/make_golden.py) — no oracle here."""
+    """CUDA chain vs the committed golden outputs — OUTPUTS OF THE REFERENCE'S OWN SHADERS run on the CPU (tests/golden/make_golden.py ->
+    tests/refglsl.py) — no oracle here."""
     from test_oracle_chain_cpu import load_golden
 
     g, inp = load_golden()
@@ -188,6 +189,25 @@ def test_chain_matches_golden_fixture(built):
     for t in range(2):
         for k in ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed"):
             check(f"golden f{t}.{k}", g[f"f{t}_out_{k}"], got[t][k], packed=(k == "ssgi"), max_bad=6e-3)  # chain-level bar at this small size (one differently resolved ray = ~1e-2 of 5 184 pixels would fail it: none measured)
+
+
+def test_ssr_chain_and_exact_k1_match_reference_shader_goldens(built):
+    """mode "ssr" over 3 frames against the reference shaders' outputs (tests/golden/chain_ssr_64x36.npz), both variants; and the exact
+    variant's K1 plane is BIT-equal to what the reference's ssgi.frag produced, in both modes."""
+    from test_oracle_chain_cpu import GOLD_SSR, load_golden
+
+    g, inp = load_golden(GOLD_SSR, 3, (64, 36))
+    for fast in (True, False):
+        got, _ = ch.run_cuda_chain(inp, ch.Opts(mode=abi.MODE_SSR), capture=("ssgi", "tr0", "dn0", "composed"), fast_math=fast)
+        for t in range(3):
+            if not fast and t == 0:  # frame 0 has no history: K1 sees exactly the reference run's inputs
+                assert got[t]["ssgi"].tobytes() == g[f"f{t}_out_ssgi"].tobytes()
+            check(f"ssr golden fast={fast} f{t}.ssgi", g[f"f{t}_out_ssgi"][..., :3], got[t]["ssgi"][..., :3], max_bad=6e-3)
+            for k in ("tr0", "dn0", "composed"):
+                check(f"ssr golden fast={fast} f{t}.{k}", g[f"f{t}_out_{k}"], got[t][k], max_bad=6e-3)
+    g2, inp2 = load_golden()
+    got, _ = ch.run_cuda_chain(inp2, ch.Opts(steps=12, refine_steps=3), capture=("ssgi",), fast_math=False)
+    assert got[0]["ssgi"].tobytes() == g2["f0_out_ssgi"].tobytes()  # K1 (exact variant) == the reference's ssgi.frag, bit for bit
 
 
 def test_row_block_sharding_is_exact(scene, ctx):

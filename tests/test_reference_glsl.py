@@ -1,0 +1,142 @@
+"""The reference's own shaders run on the CPU (tests/refglsl.py) against the oracle, plus known-answer tests of the GLSL runtime
+that executes them (oracle/ref/glsl_rt.h + oracle/ref/transpile.py).
+
+* runtime tests: small GLSL programs written here whose results are known in closed form — they check the language semantics the
+  reference shaders rely on (swizzle l-values, inout copy-back, array constructors, uint arithmetic, quad derivatives with
+  helper lanes, discard / early return, sampler state).  They need only g++.
+* pinning tests: the oracle must equal the reference shaders BIT FOR BIT.  They build the shaders from the reference checkout when
+  it is there (this container) and otherwise use the libraries __graft_entry__.build() left in oracle/_ref/ (the GPU box); with
+  neither they are skipped — tests/test_oracle_chain_cpu.py then still checks the oracle against the committed reference outputs.
+"""
+import numpy as np
+import pytest
+
+import chain_harness as ch
+import orc
+import refglsl
+from realism_effects_b200 import abi
+
+F32, F16 = refglsl.F_RGBA32F, refglsl.F_RGBA16F
+
+
+def run_glsl(name, body, W=8, H=6, uniforms=None, textures=(), outs=None):
+    s = refglsl.Shader(name, glsl="varying vec2 vUv;\nuniform vec2 resolution;\n" + body)
+    s.set(resolution=[W, H], **(uniforms or {}))
+    for t in textures:
+        s.tex(*t[:3], **(t[3] if len(t) > 3 else {}))
+    return s.run(W, H, outs or [(F32, None)])
+
+
+def test_runtime_swizzles_inout_arrays_and_uint_math():
+    out = run_glsl("rt_lang", """
+      struct P { vec3 c; float w; };
+      void twice(inout vec3 v) { v *= 2.0; }
+      void split(vec4 e, out vec2 a, out vec2 b) { a = e.xy; b = e.zw; }
+      vec2 TAB[3] = vec2[](vec2(1.0, 2.0), vec2(3.0, 4.0), vec2(5.0, 6.0));
+      void main() {
+        vec4 v = vec4(1.0, 2.0, 3.0, 4.0);
+        v.xy = v.yx;                 // aliasing swizzle assignment -> (2,1,3,4)
+        twice(v.yzw);                // inout through a swizzle    -> (2,2,6,8)
+        vec2 a, b;
+        split(v, a, b);
+        P p = P(vec3(a, b.x), b.y);  // struct constructor
+        uvec4 u = uvec4(7, 7 * 15843, 7 * 31 + 4566, 7 * 2345 + 58585);
+        u = u * 1664525u + 1013904223u;
+        u.x += u.y * u.w;
+        u = u ^ (u >> 16u);
+        float s = 0.0;
+        for (int i = 0; i < 3; i++) s += TAB[i].x * TAB[i].y;   // 2 + 12 + 30
+        float h = unpackHalf2x16(packHalf2x16(vec2(0.1, -3.0))).y;
+        gl_FragColor = vec4(p.c.x + p.c.y * 10.0 + p.c.z * 100.0 + p.w * 1000.0, float(u.x % 1000u), s, h);
+      }""")[0]
+    u = np.array([7, 7 * 15843, 7 * 31 + 4566, 7 * 2345 + 58585], np.uint32)
+    u = u * np.uint32(1664525) + np.uint32(1013904223)
+    u[0] += u[1] * u[3]
+    u = u ^ (u >> np.uint32(16))
+    assert np.all(out[..., 0] == 2 + 20 + 600 + 8000)
+    assert np.all(out[..., 1] == float(int(u[0]) % 1000))
+    assert np.all(out[..., 2] == 44.0) and np.all(out[..., 3] == -3.0)
+
+
+def test_runtime_quad_derivatives_discard_and_helper_lanes():
+    """fwidth over a quad is taken from all four pixels even when some of them left main() early or were discarded; a discarded
+    fragment keeps the target's previous texel"""
+    W, H = 8, 6
+    prev = np.full((H, W, 4), 7.0, np.float32)
+    out = run_glsl("rt_deriv", """
+      void main() {
+        vec2 p = vUv * resolution;            // pixel centre: x + 0.5
+        if (p.x < 2.0) { gl_FragColor = vec4(-1.0); return; }     // columns 0,1 leave early (uniform within their quads)
+        if (p.y > 4.0 && p.x > 6.0) { discard; return; }          // the last quad column of the last quad row is discarded
+        float keyed = (p.x > 3.0 && p.x < 4.0) ? 100.0 : 0.0;     // column 3 carries a different value than column 2
+        gl_FragColor = vec4(fwidth(p.x * p.y), dFdx(keyed), dFdy(p.y * p.y), 1.0);
+      }""", W, H, outs=[(F32, prev)])[0]
+    assert np.all(out[:, :2] == -1.0)
+    assert np.all(out[4:, 6:] == 7.0)                                    # discarded: previous contents
+    y, x = 1, 4                                                          # quad (4..5, 0..1): d/dx (x*y) = y + .5, d/dy = x + .5
+    assert out[y, x, 0] == pytest.approx((y + 0.5) + (x + 0.5))
+    assert np.all(out[:4, 2:4, 1] == 100.0)                              # fine derivative inside the quad of columns 2,3
+    assert out[2, 4, 2] == pytest.approx(3.5 * 3.5 - 2.5 * 2.5)
+
+
+def test_runtime_sampler_state_and_null_sampler():
+    W, H = 4, 4
+    tex = np.zeros((2, 2, 4), np.float32)
+    tex[0, 0], tex[0, 1], tex[1, 0], tex[1, 1] = [0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1], [1, 1, 0, 1]
+    body = """
+      uniform sampler2D a; uniform sampler2D b; uniform sampler2D none;
+      void main() {
+        vec4 n = textureLod(a, vec2(0.5), 0.0);       // NEAREST at the centre: texel (1,1)
+        vec4 l = textureLod(b, vec2(0.5), 0.0);       // LINEAR at the centre: the mean of the four texels
+        gl_FragColor = vec4(n.x + n.y, l.x, textureLod(none, vUv, 0.0).a, float(textureSize(a, 0).x) + texelFetch(a, ivec2(1, 0), 0).x);
+      }"""
+    out = run_glsl("rt_tex", body, W, H, textures=[("a", tex, F32), ("b", tex, F32, dict(linear=True))])[0]
+    assert np.all(out[..., 0] == 2.0) and np.all(out[..., 1] == 0.5) and np.all(out[..., 2] == 1.0) and np.all(out[..., 3] == 3.0)
+
+
+needs_ref = pytest.mark.skipif(not refglsl.available(), reason="neither the reference checkout nor prebuilt oracle/_ref libraries")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("mode", [abi.MODE_SSGI, abi.MODE_SSR])
+def test_oracle_equals_reference_shaders_chain(mode):
+    """K1 -> K2 -> K3 x2 -> K4 with history over 3 frames, default options: every plane of every frame, bit for bit"""
+    o = ch.Opts(mode=mode)
+    inp = ch.make_inputs(80, 45, 3)
+    planes = ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed") if mode == abi.MODE_SSGI else ("ssgi", "tr0", "dn0", "composed")
+    a = ch.run_oracle_chain(inp, o, capture=planes, lean=True)
+    b = ch.run_oracle_chain(inp, o, capture=planes, lean=True, impl=refglsl)
+    for t in range(3):
+        for k in planes:
+            assert bits(a[t][k]) == bits(b[t][k]), (t, k, ch.compare(a[t][k], b[t][k], packed=(k == "ssgi" and mode == abi.MODE_SSGI)))
+    assert float(np.abs(b[2]["composed"]).max()) > 0.1  # the comparison is not of empty planes
+
+
+@needs_ref
+def test_oracle_equals_reference_shaders_effect_passes():
+    """K5 (fog), K6 + AO denoise + K7, K8, TRAA K2 + K9"""
+    inp = ch.make_inputs(64, 36, 2)
+    f0, f1 = inp.frames
+    H, W = f1["depth"].shape
+    z = np.zeros((H, W, 4), np.float16)
+    hp = ch.hbao_params(f1["cam"], 991)
+    ao_o, ao_r = orc.hbao(hp, f1["depth"], inp.blue, z), refglsl.hbao(hp, f1["depth"], inp.blue, z)
+    assert bits(ao_o) == bits(ao_r) and float(ao_r[..., 3].astype(np.float32).min()) < 0.99
+    for x, y in zip(ch.ao_denoise(orc, f1, inp.blue, ao_o), ch.ao_denoise(refglsl, f1, inp.blue, ao_r)):
+        assert bits(x) == bits(y)
+    assert bits(orc.ao_compose(ch.ao_compose_params(), f1["depth"], ao_o, f1["direct"])) == bits(refglsl.ao_compose(ch.ao_compose_params(), f1["depth"], ao_r, f1["direct"]))
+    for x, y in zip(ch.traa_two_frames(orc, f0, f1), ch.traa_two_frames(refglsl, f0, f1)):
+        assert bits(x) == bits(y)
+    assert bits(orc.traa_compose(f1["direct"])) == bits(refglsl.traa_compose(f1["direct"]))
+    vel = ch.rotation_velocity_field(W, H, f1["depth"])
+    mp = ch.motion_blur_params(W, H, frame=7)
+    assert bits(orc.motion_blur(mp, vel, f1["direct"], inp.blue)) == bits(refglsl.motion_blur(mp, vel, f1["direct"], inp.blue))
+    gi = np.random.default_rng(5).uniform(0, 2, (H, W, 4)).astype(np.float32)
+    for exp2 in (False, True):
+        fp = ch.fog_params(f1["cam"], exp2)
+        assert bits(orc.ssgi_compose(f1["depth"], gi, f1["direct"], fp)) == bits(refglsl.ssgi_compose(f1["depth"], gi, f1["direct"], fp))
+    assert bits(orc.ssgi_compose(f1["depth"], gi, f1["direct"])) == bits(refglsl.ssgi_compose(f1["depth"], gi, f1["direct"]))
