@@ -112,7 +112,7 @@ def make_gpu_frames(width, height, n, device, aspect=None):
     frames = []
     for t in range(n):
         fr = synth.render_frame(width, height, t + 1, device=device, aspect=aspect or width / height)
-        frames.append(dict(depth=fr.depth, gbuffer=fr.gbuffer, velocity=fr.velocity, direct=fr.direct_light, cam=fr.cam.uniforms(), moved=True))
+        frames.append(dict(depth=fr.depth, gbuffer=fr.gbuffer, velocity=fr.velocity, direct=fr.direct_light, cam=fr.cam.uniforms(), moved=True, soa=fr.soa))
     torch.cuda.synchronize()
     return frames
 
@@ -226,6 +226,20 @@ def other_configs(ctx, ch, dev, stream, peak):
     out["C4_hbao_4k"]["hbao_kernel_GBps"] = round(12 * W * H / (ms_h * 1e-3) / 1e9, 1)
     for p in (ao, tA, tB, outp):
         p.free()
+    # G-buffer ingest at 3840x2160: albedo RGBA8 + normal RGBA16F + material RGBA8 + emissive RGBA16F + motion RGBA16F + depth in
+    # (4 + 8 + 4 + 8 + 8 + 4 = 36 B/px), gBuffer + velocity RGBA32F out (32 B/px): a pure stream
+    soa = f["soa"]
+    keep = [soa["albedo"], soa["normal"].to(torch.float16).contiguous(), (soa["material"].float() * 255).round().to(torch.uint8).contiguous(), soa["emissive"],
+            soa["motion"].to(torch.float16).contiguous()]  # the tensors own the memory the planes point at
+    ing = [tensor_plane(t, fm) for t, fm in zip(keep, (abi.FMT_RGBA8, abi.FMT_RGBA16F, abi.FMT_RGBA8, abi.FMT_RGBA16F, abi.FMT_RGBA16F))]
+    og, ov = ctx.alloc(abi.FMT_RGBA32F, W, H), ctx.alloc(abi.FMT_RGBA32F, W, H)
+    ingest = lambda _i: ctx.gbuffer_ingest(*ing, d, og, ov)  # noqa: E731
+    for i in range(5):
+        ingest(i)
+    out["gbuffer_ingest_4k"] = line(time_frames(stream, ingest, 50), W, H, 68, {"workload": "rfx_gbuffer_ingest_launch 3840x2160: 6 SoA planes (36 B/px) -> packed gBuffer + velocity (32 B/px)"})
+    og.free()
+    ov.free()
+    del keep
     # C1: MotionBlurEffect 256x256 (plumbing config)
     W, H = 256, 256
     inp = ch.make_inputs(W, H, 1)

@@ -186,6 +186,19 @@ typedef struct rfx_motion_blur_params {
   int32_t _pad;
 } rfx_motion_blur_params;
 
+/* G-buffer ingest: a conventional deferred renderer's planes -> the reference's packed layouts.
+ *   gBuffer  = packGBuffer(diffuse, worldNormal, roughness, metalness, emissive)   src/gbuffer/shader/gbuffer_packing.glsl:166-178
+ *              (what GBufferMaterial.js:94-98 writes); a zero emissive is encoded as 0 (the shader takes a log2(0) path there;
+ *              it decodes to 0 on every back-end);
+ *   velocity = (motion.xy * motion_scale, packNormal(worldNormal), depth)            src/temporal-reproject/material/
+ *              VelocityDepthNormalMaterial.js:76-83,186-188;
+ *   a pixel with depth == 1 gets the cleared targets' texel (0,0,0,1) in both planes (GBufferPass.js:42-44, SURVEY §8 plane table). */
+typedef struct rfx_ingest_params {
+  float motion_scale[2];       /* uv-space motion = motion.xy * scale ((1,1): already uv-space cur - prev; (.5,.5): NDC)  */
+  int32_t normalize_normals;   /* 1: worldNormal = normalize(normal.xyz) as the reference's producers do; 0: taken as stored */
+  int32_t _pad;
+} rfx_ingest_params;
+
 /* Environment map + importance-sampling tables (struct EquirectHdrInfo, ssgi.frag:27-36;
  * built by src/ssgi/utils/EquirectHdrInfoUniform.js:149-245). */
 typedef struct rfx_env_desc {
@@ -304,6 +317,14 @@ rfx_status rfx_ao_compose_launch(rfx_ctx* ctx, void* stream, const rfx_ao_compos
 rfx_status rfx_motion_blur_launch(rfx_ctx* ctx, void* stream, const rfx_motion_blur_params* p,
                                   const rfx_plane* velocity, const rfx_plane* input,
                                   const rfx_plane* out, uint32_t row0, uint32_t row1);
+
+/* G-buffer ingest.  albedo RGBA8 | RGBA16F (rgb = diffuse colour, a = opacity); normal RGBA16F | RGBA32F (xyz = world normal);
+ * material RGBA8 | RGBA16F (r = roughness, g = metalness); emissive RGBA16F (rgb; may be NULL = black); motion RGBA16F | RGBA32F
+ * (xy; may be NULL = static); depth R32F.  out_gbuffer / out_velocity RGBA32F (either may be NULL). */
+rfx_status rfx_gbuffer_ingest_launch(rfx_ctx* ctx, void* stream, const rfx_ingest_params* p, const rfx_plane* albedo,
+                                     const rfx_plane* normal, const rfx_plane* material, const rfx_plane* emissive,
+                                     const rfx_plane* motion, const rfx_plane* depth, const rfx_plane* out_gbuffer,
+                                     const rfx_plane* out_velocity, uint32_t row0, uint32_t row1);
 
 /* K9. src/traa/shader/traa_compose.frag:3-6  accumulated RGBA16F -> out RGBA16F (a = 1) */
 rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* accumulated,

@@ -68,6 +68,31 @@ export class ReadbackPlaneSource {
 	dispose() { if (this.dev) for (const p of Object.values(this.dev)) rfx.planeFree(this.ctx, p); this.dev = null }
 }
 
+// PlaneSource for hosts WITHOUT the reference's rasteriser materials (GBufferMaterial / VelocityDepthNormalMaterial): upload a
+// conventional deferred renderer's planes and let the GPU pack them (rfx_gbuffer_ingest_launch = packGBuffer, gbuffer_packing.glsl:166-178,
+// + the velocity layout of VelocityDepthNormalMaterial.js:76-83,186-188).  host: { albedo: Uint8Array RGBA8, normal: Uint16Array RGBA16F
+// (world space), material: Uint8Array RGBA8 (r roughness, g metalness), emissive: Uint16Array RGBA16F | null, motion: Uint16Array RGBA16F
+// (uv-space cur - prev) | null, depth: Float32Array, directLight: Uint16Array RGBA16F }
+export class IngestPlaneSource {
+	constructor(ctx, width, height, { motionScale = [1, 1], normalizeNormals = true } = {}) { this.ctx = ctx; this.opt = { motionScale, normalizeNormals: normalizeNormals ? 1 : 0 }; this.resize(width, height) }
+	resize(width, height) {
+		this.dispose()
+		this.width = width; this.height = height
+		const a = fmt => rfx.planeAlloc(this.ctx, fmt, width, height)
+		this.src = { albedo: a(FMT.RGBA8), normal: a(FMT.RGBA16F), material: a(FMT.RGBA8), emissive: a(FMT.RGBA16F), motion: a(FMT.RGBA16F) }
+		this.dev = { depth: a(FMT.R32F), gbuffer: a(FMT.RGBA32F), velocity: a(FMT.RGBA32F), directLight: a(FMT.RGBA16F) }
+	}
+	read(_renderer, host) {
+		for (const k of Object.keys(this.src)) if (host[k]) rfx.planeUpload(this.ctx, this.src[k], host[k])
+		rfx.planeUpload(this.ctx, this.dev.depth, host.depth)
+		if (host.directLight) rfx.planeUpload(this.ctx, this.dev.directLight, host.directLight)
+		rfx.gbufferIngest(this.ctx, this.opt, this.src.albedo, this.src.normal, this.src.material, host.emissive ? this.src.emissive : null,
+			host.motion ? this.src.motion : null, this.dev.depth, this.dev.gbuffer, this.dev.velocity)
+		return this.dev
+	}
+	dispose() { for (const set of [this.src, this.dev]) if (set) for (const p of Object.values(set)) rfx.planeFree(this.ctx, p); this.src = this.dev = null }
+}
+
 // -------------------------------------------------------------------------------------------------------------------------
 export class VelocityDepthNormalPass {
 	// new VelocityDepthNormalPass(scene, camera) — src/temporal-reproject/pass/VelocityDepthNormalPass.js:71-91.

@@ -322,6 +322,19 @@ napi_value TraaCompose(napi_env env, napi_callback_info info) {  // traaCompose(
   return undefined(env);
 }
 
+napi_value GbufferIngest(napi_env env, napi_callback_info info) {  // gbufferIngest(ctx, {motionScale, normalizeNormals}, albedo, normal, material, emissive|null, motion|null, depth, outGbuffer|null, outVelocity|null)
+  ARGS(10); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  Obj b{env, argv[1]};
+  rfx_ingest_params p{};
+  p.motion_scale[0] = p.motion_scale[1] = 1.0f;
+  b.floats("motionScale", p.motion_scale, 2);
+  p.normalize_normals = (int32_t)b.num("normalizeNormals", 1);
+  CHECK(c, rfx_gbuffer_ingest_launch(c, nullptr, &p, unwrap<rfx_plane>(env, argv[2]), unwrap<rfx_plane>(env, argv[3]), unwrap<rfx_plane>(env, argv[4]), unwrap<rfx_plane>(env, argv[5]),
+                                     unwrap<rfx_plane>(env, argv[6]), unwrap<rfx_plane>(env, argv[7]), unwrap<rfx_plane>(env, argv[8]), unwrap<rfx_plane>(env, argv[9]), 0, 0),
+        "rfx_gbuffer_ingest_launch");
+  return undefined(env);
+}
+
 napi_value Init(napi_env env, napi_value exports) {
 #define FN(name, f) {name, nullptr, f, nullptr, nullptr, nullptr, napi_default, nullptr}
   napi_property_descriptor d[] = {
@@ -331,7 +344,7 @@ napi_value Init(napi_env env, napi_value exports) {
       FN("chainRender", ChainRender), FN("chainOutput", ChainOutput), FN("chainRenderHost", ChainRenderHost), FN("chainWaitHost", ChainWaitHost),
       FN("chainReset", ChainReset), FN("chainDestroy", ChainDestroy), FN("ssgiCompose", SsgiCompose), FN("temporalReproject", TemporalReproject),
       FN("poissonDenoise", PoissonDenoise), FN("giCompose", GiCompose), FN("hbao", Hbao), FN("aoCompose", AoCompose), FN("motionBlur", MotionBlur),
-      FN("traaCompose", TraaCompose),
+      FN("traaCompose", TraaCompose), FN("gbufferIngest", GbufferIngest),
   };
 #undef FN
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);

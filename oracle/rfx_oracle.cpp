@@ -130,7 +130,8 @@ vec3 decodeRGBE8(vec4 rgbe) {
 // :143-164
 float vec4ToFloat(vec4 v) {
   for (int i = 0; i < 4; i++) v[i] = gmin(v[i] + NON_ZERO_OFFSET, ONE_SAFE);
-  uint32_t r = (uint32_t)(v.x * 255.0f), g = (uint32_t)(v.y * 255.0f), b = (uint32_t)(v.z * 255.0f), a = (uint32_t)(v.w * 255.0f);
+  auto q = [](float t) -> uint32_t { return t > 0.0f ? (uint32_t)t : 0u; };  // uvec4(): truncation; negative / NaN -> 0 (defined here)
+  uint32_t r = q(v.x * 255.0f), g = q(v.y * 255.0f), b = q(v.z * 255.0f), a = q(v.w * 255.0f);
   return uintBitsToFloat((a << 24) | (b << 16) | (g << 8) | r);
 }
 vec4 floatToVec4(float f) {
@@ -1371,6 +1372,44 @@ void orc_traa_compose(int W, int H, const uint16_t* accumulated, uint16_t* out) 
 #pragma omp parallel for
   for (int y = 0; y < H; y++)
     for (int x = 0; x < W; x++) store_rgba16f(out, W, x, y, vec4(textureLod0(a, pixelUv(x, y, W, H)).xyz(), 1.0f));
+}
+
+// G-buffer ingest (include/rfx.h rfx_gbuffer_ingest_launch): packGBuffer :166-178 + the velocity layout of
+// VelocityDepthNormalMaterial.js:76-83,186-188 over SoA planes.  fmt_*: gl::Fmt of the plane (albedo / material RGBA8 | RGBA16F,
+// normal / motion RGBA16F | RGBA32F).  emissive / motion may be NULL.  out_* may be NULL.
+void orc_gbuffer_ingest(const rfx_ingest_params* p, int W, int H, const void* albedo, int fmt_albedo, const void* normal, int fmt_normal,
+                        const void* material, int fmt_material, const uint16_t* emissive, const void* motion, int fmt_motion,
+                        const float* depth, float* out_gbuffer, float* out_velocity) {
+  Tex ta = mk(albedo, W, H, fmt_albedo), tn = mk(normal, W, H, fmt_normal), tm = mk(material, W, H, fmt_material);
+  Tex te = mk(emissive, W, H, F_RGBA16F), tv = mk(motion, W, H, fmt_motion);
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      float d = depth[(size_t)y * W + x];
+      if (d == 1.0f) {
+        if (out_gbuffer) store_rgba32f(out_gbuffer, W, x, y, vec4(0, 0, 0, 1));
+        if (out_velocity) store_rgba32f(out_velocity, W, x, y, vec4(0, 0, 0, 1));
+        continue;
+      }
+      vec4 nt = texel(tn, x, y);
+      vec3 n = nt.xyz();
+      if (p->normalize_normals) n = normalize(n);
+      if (out_gbuffer) {
+        vec4 diffuse = texel(ta, x, y), mt = texel(tm, x, y);
+        vec3 em = emissive ? texel(te, x, y).xyz() : vec3(0.0f);
+        vec4 g;
+        g.x = vec4ToFloat(diffuse);
+        g.y = packNormal(n);
+        g.z = color2float(vec3(mt.x, mt.y, 0.0f));
+        float mx = gmax(gmax(em.x, em.y), em.z);
+        g.w = mx > 0.0f ? vec4ToFloat(encodeRGBE8(em)) : 0.0f;  // zero radiance: the shader's log2(0) path decodes to 0 everywhere
+        store_rgba32f(out_gbuffer, W, x, y, g);
+      }
+      if (out_velocity) {
+        vec4 mv = motion ? texel(tv, x, y) : vec4(0, 0, 0, 0);
+        store_rgba32f(out_velocity, W, x, y, vec4(mv.x * p->motion_scale[0], mv.y * p->motion_scale[1], packNormal(n), d));
+      }
+    }
 }
 
 // ---- leaf functions exported for unit tests -------------------------------------------

@@ -85,6 +85,10 @@ class MotionBlurParams(C.Structure):
                 ("samples", C.c_int32), ("_pad", C.c_int32)]
 
 
+class IngestParams(C.Structure):
+    _fields_ = [("motion_scale", F2), ("normalize_normals", C.c_int32), ("_pad", C.c_int32)]
+
+
 class EnvDesc(C.Structure):
     _fields_ = [("map_rgba16f", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("marginal", C.c_void_p),
                 ("conditional", C.c_void_p), ("total_sum_whole", C.c_float), ("total_sum_decimal", C.c_float)]
@@ -168,6 +172,7 @@ def _sig(lib):
     lib.rfx_ao_compose_launch.argtypes = [vp, vp, _P(AoComposeParams), PP, PP, PP, PP, u32, u32]
     lib.rfx_motion_blur_launch.argtypes = [vp, vp, _P(MotionBlurParams), PP, PP, PP, u32, u32]
     lib.rfx_traa_compose_launch.argtypes = [vp, vp, PP, PP, u32, u32]
+    lib.rfx_gbuffer_ingest_launch.argtypes = [vp, vp, _P(IngestParams), PP, PP, PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_ssgi_chain_create.argtypes = [vp, _P(ChainOptions), _P(vp)]
     lib.rfx_ssgi_chain_destroy.argtypes = [vp]
     lib.rfx_ssgi_chain_destroy.restype = None
@@ -212,7 +217,7 @@ EXPORTS = [
     "rfx_blue_noise_set", "rfx_env_set", "rfx_env_clear", "rfx_env_build", "rfx_env_tables_download", "rfx_plane_alloc", "rfx_plane_free", "rfx_plane_clear", "rfx_plane_upload",
     "rfx_plane_download", "rfx_host_alloc", "rfx_host_free", "rfx_format_bytes", "rfx_ssgi_trace_launch",
     "rfx_temporal_reproject_launch", "rfx_poisson_denoise_launch", "rfx_gi_compose_launch", "rfx_ssgi_compose_launch", "rfx_hbao_launch",
-    "rfx_ao_compose_launch", "rfx_motion_blur_launch", "rfx_traa_compose_launch", "rfx_ssgi_chain_create", "rfx_ssgi_chain_destroy",
+    "rfx_ao_compose_launch", "rfx_motion_blur_launch", "rfx_traa_compose_launch", "rfx_gbuffer_ingest_launch", "rfx_ssgi_chain_create", "rfx_ssgi_chain_destroy",
     "rfx_ssgi_chain_reset", "rfx_ssgi_chain_render", "rfx_ssgi_chain_output", "rfx_ssgi_chain_render_host",
     "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host", "rfx_ssgi_chain_render_part",
     "rfx_ssgi_chain_set_profiling", "rfx_ssgi_chain_get_profile", "rfx_ssgi_chain_set_options", "rfx_ssgi_chain_render_ranges", "rfx_ssgi_chain_render_blocks",

@@ -705,6 +705,33 @@ rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* 
   return RFX_OK;
 }
 
+rfx_status rfx_gbuffer_ingest_launch(rfx_ctx* ctx, void* stream, const rfx_ingest_params* p, const rfx_plane* albedo, const rfx_plane* normal,
+                                     const rfx_plane* material, const rfx_plane* emissive, const rfx_plane* motion, const rfx_plane* depth,
+                                     const rfx_plane* out_gbuffer, const rfx_plane* out_velocity, uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !albedo || !normal || !material || !depth || (!out_gbuffer && !out_velocity)) return fail(ctx, RFX_ERR_INVALID_ARG, "gbuffer_ingest: null argument");
+  IngestArgs a{};
+  auto one_of = [](const rfx_plane* pl, int f0, int f1, PV& out, int& is_second) {
+    if (pl && pl->format == f1) { is_second = 1; return pv(pl, f1, out); }
+    is_second = 0;
+    return pv(pl, f0, out);
+  };
+  int dummy = 0;
+  if (!one_of(albedo, RFX_FMT_RGBA8, RFX_FMT_RGBA16F, a.albedo, a.albedo_half) || !one_of(material, RFX_FMT_RGBA8, RFX_FMT_RGBA16F, a.material, a.material_half) ||
+      !one_of(normal, RFX_FMT_RGBA16F, RFX_FMT_RGBA32F, a.normal, a.normal_f32) || !pv(depth, RFX_FMT_R32F, a.depth) ||
+      (emissive && !pv(emissive, RFX_FMT_RGBA16F, a.emissive)) || (motion && !one_of(motion, RFX_FMT_RGBA16F, RFX_FMT_RGBA32F, a.motion, a.motion_f32)) ||
+      (out_gbuffer && !ov(out_gbuffer, RFX_FMT_RGBA32F, a.out_gb)) || (out_velocity && !ov(out_velocity, RFX_FMT_RGBA32F, a.out_vel)))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "gbuffer_ingest: albedo / material RGBA8|RGBA16F, normal / motion RGBA16F|RGBA32F, emissive RGBA16F, depth R32F, outputs RGBA32F");
+  (void)dummy;
+  a.W = (int)depth->width; a.H = (int)depth->height;
+  for (const rfx_plane* pl : {albedo, normal, material, emissive, motion, out_gbuffer, out_velocity})
+    if (pl && ((int)pl->width != a.W || (int)pl->height != a.H)) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "gbuffer_ingest: plane sizes differ");
+  a.normalize_normals = p->normalize_normals;
+  a.motion_sx = p->motion_scale[0]; a.motion_sy = p->motion_scale[1];
+  rows(row0, row1, depth->height, a.row0, a.row1);
+  LAUNCHED(launch_gbuffer_ingest(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
 }  // extern "C"
 
 // ==========================================================================================

@@ -190,6 +190,16 @@ struct TraaComposeArgs {
 };
 cudaError_t launch_traa_compose(const TraaComposeArgs& a, cudaStream_t s);
 
+// G-buffer ingest (k_ingest.cu)
+struct IngestArgs {
+  PV albedo, normal, material, emissive, motion, depth;  // emissive.p / motion.p may be null
+  OutV out_gb, out_vel;                                  // either .p may be null
+  int W, H, row0, row1;
+  int albedo_half, material_half, normal_f32, motion_f32, normalize_normals;
+  float motion_sx, motion_sy;
+};
+cudaError_t launch_gbuffer_ingest(const IngestArgs& a, cudaStream_t s);
+
 // env mip chain: dst (w1 x h1) = box filter of src (w0 x h0), RGBA16F
 cudaError_t launch_env_downsample(PV src, OutV dst, int w1, int h1, cudaStream_t s);
 // importance-sampling tables of an equirect map on the device (gatherData, EquirectHdrInfoUniform.js:149-245); 3 launches

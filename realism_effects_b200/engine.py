@@ -203,6 +203,15 @@ class Context:
     def traa_compose(self, acc, out, rows=(0, 0), stream=None):
         self._chk(self.lib.rfx_traa_compose_launch(self.h, stream, _r(acc), _r(out), rows[0], rows[1]))
 
+    def gbuffer_ingest(self, albedo, normal, material, emissive, motion, depth, out_gbuffer, out_velocity, *, motion_scale=(1.0, 1.0),
+                       normalize_normals=True, rows=(0, 0), stream=None):
+        """conventional SoA planes -> the reference's packed gBuffer / velocity planes (rfx_gbuffer_ingest_launch)"""
+        p = abi.IngestParams()
+        p.motion_scale[:] = [float(motion_scale[0]), float(motion_scale[1])]
+        p.normalize_normals = int(bool(normalize_normals))
+        self._chk(self.lib.rfx_gbuffer_ingest_launch(self.h, stream, C.byref(p), _r(albedo), _r(normal), _r(material), _r(emissive), _r(motion),
+                                                     _r(depth), _r(out_gbuffer), _r(out_velocity), rows[0], rows[1]))
+
 
 class SsgiChain:
     """Native SSGI chain (rfx_ssgi_chain): K1 -> K2 -> K3 x 2*iterations -> K4 with history."""

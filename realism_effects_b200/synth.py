@@ -264,6 +264,7 @@ class Frame:
     velocity: torch.Tensor      # (H,W,4)   f32
     direct_light: torch.Tensor  # (H,W,4)   f16
     background: torch.Tensor    # (H,W) bool
+    soa: dict | None = None     # the same frame as a conventional deferred renderer's planes (input of rfx_gbuffer_ingest_launch)
 
 
 def render_frame(width: int, height: int, t: int = 0, *, device="cpu", cam_step=(0.02, 0.0, 0.0), static=False, fov: float = 40.0,
@@ -375,7 +376,13 @@ def render_frame(width: int, height: int, t: int = 0, *, device="cpu", cam_step=
     direct = torch.where(bg.unsqueeze(-1), sky, direct)
     direct4 = torch.cat([direct, torch.ones_like(direct[..., :1])], dim=-1).to(torch.float16)
 
-    return Frame(width, height, cam, prev, depth.contiguous(), gb.contiguous(), velocity.contiguous(), direct4.contiguous(), bg)
+    z1 = torch.zeros_like(nrm[..., :1])
+    soa = dict(albedo=torch.round(diffuse4 * 255.0).to(torch.uint8).contiguous(),                       # RGBA8 (the palette is 8-bit)
+               normal=torch.cat([nrm, z1], dim=-1).contiguous(),                                        # RGBA32F world normal
+               material=torch.stack([roughness, metalness, torch.zeros_like(roughness), torch.zeros_like(roughness)], dim=-1).to(torch.float16).contiguous(),
+               emissive=torch.cat([emissive, z1], dim=-1).to(torch.float16).contiguous(),
+               motion=torch.cat([vel, z1, z1], dim=-1).contiguous())                                    # RGBA32F uv-space cur - prev
+    return Frame(width, height, cam, prev, depth.contiguous(), gb.contiguous(), velocity.contiguous(), direct4.contiguous(), bg, soa)
 
 
 # --------------------------------------------------------------------------------------

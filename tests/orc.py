@@ -181,6 +181,24 @@ def motion_blur(p: abi.MotionBlurParams, velocity, inp, blue_noise):
     return out.view(np.float16)
 
 
+_FMT_OF = {np.dtype(np.uint8): 3, np.dtype(np.float16): 2, np.dtype(np.uint16): 2, np.dtype(np.float32): 1}
+
+
+def gbuffer_ingest(albedo, normal, material, emissive, motion, depth, *, motion_scale=(1.0, 1.0), normalize_normals=True):
+    """-> (gBuffer, velocity) RGBA32F.  albedo / material uint8 | float16, normal / motion float16 | float32 (H,W,4); emissive float16 | None"""
+    H, W = depth.shape
+    p = abi.IngestParams()
+    p.motion_scale[:] = [float(motion_scale[0]), float(motion_scale[1])]
+    p.normalize_normals = int(bool(normalize_normals))
+    gb, vel = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    c = lambda a: None if a is None else np.ascontiguousarray(a)  # noqa: E731
+    albedo, normal, material, emissive, motion = c(albedo), c(normal), c(material), c(emissive), c(motion)
+    lib().orc_gbuffer_ingest(C.byref(p), C.c_int(W), C.c_int(H), _p(albedo), C.c_int(_FMT_OF[albedo.dtype]), _p(normal), C.c_int(_FMT_OF[normal.dtype]),
+                             _p(material), C.c_int(_FMT_OF[material.dtype]), _p(emissive), _p(motion), C.c_int(_FMT_OF[motion.dtype] if motion is not None else 1),
+                             _p(_c(depth, np.float32)), _p(gb), _p(vel))
+    return gb, vel
+
+
 def traa_compose(acc):
     H, W = acc.shape[:2]
     out = np.zeros((H, W, 4), np.uint16)

@@ -200,3 +200,46 @@ def test_ssgi_compose_fog_and_debug(built, exp2):
         assert np.array_equal(out.download(), gi.astype(np.float16))                   # isDebug: the GI texture passes through
     finally:
         ctx.close()
+
+
+def test_gbuffer_ingest_is_bit_identical_to_the_oracle_and_feeds_the_chain(built):
+    """rfx_gbuffer_ingest_launch: every input-format combination against orc_gbuffer_ingest bit for bit, row-block
+    launches, and the ingested planes driving K1 give the bytes the generator's own packed planes give."""
+    import orc
+
+    W, H = 200, 120
+    fr = synth.render_frame(W, H, 1)
+    s = {k: v.cpu().numpy() for k, v in fr.soa.items()}
+    d = fr.depth.numpy()
+    variants = [
+        dict(albedo=s["albedo"], normal=s["normal"], material=s["material"], emissive=s["emissive"], motion=s["motion"], kw=dict(normalize_normals=False)),
+        dict(albedo=(s["albedo"].astype(np.float32) / 255).astype(np.float16), normal=s["normal"].astype(np.float16),
+             material=(s["material"].astype(np.float32) * 255).round().astype(np.uint8), emissive=s["emissive"], motion=s["motion"].astype(np.float16),
+             kw=dict(motion_scale=(0.5, 2.0))),
+        dict(albedo=s["albedo"], normal=s["normal"].astype(np.float16), material=s["material"], emissive=None, motion=None, kw={}),
+    ]
+    ctx = engine.Context(0, synth.load_blue_noise())
+    try:
+        dd = ctx.upload(d)
+        for v in variants:
+            want_g, want_v = orc.gbuffer_ingest(v["albedo"], v["normal"], v["material"], v["emissive"], v["motion"], d, **v["kw"])
+            up = lambda a: None if a is None else ctx.upload(a)  # noqa: E731
+            planes = [up(v[k]) for k in ("albedo", "normal", "material", "emissive", "motion")]
+            og, ov = ctx.alloc(abi.FMT_RGBA32F, W, H), ctx.alloc(abi.FMT_RGBA32F, W, H)
+            ctx.gbuffer_ingest(*planes, dd, og, ov, **v["kw"])
+            assert og.download().view(np.uint32).tobytes() == want_g.view(np.uint32).tobytes()
+            assert ov.download().view(np.uint32).tobytes() == want_v.view(np.uint32).tobytes()
+            og2, ov2 = ctx.alloc(abi.FMT_RGBA32F, W, H), ctx.alloc(abi.FMT_RGBA32F, W, H)
+            for r in ((0, 37), (37, H)):
+                ctx.gbuffer_ingest(*planes, dd, og2, ov2, rows=r, **v["kw"])
+            assert og2.download().tobytes() == og.download().tobytes() and ov2.download().tobytes() == ov.download().tobytes()
+        # variant 0 reproduces the generator's velocity plane and the diffuse / normal words of its gBuffer; K1 on the ingested planes
+        v = variants[0]
+        planes = [ctx.upload(v[k]) for k in ("albedo", "normal", "material", "emissive", "motion")]
+        og, ov = ctx.alloc(abi.FMT_RGBA32F, W, H), ctx.alloc(abi.FMT_RGBA32F, W, H)
+        ctx.gbuffer_ingest(*planes, dd, og, ov, normalize_normals=False)
+        assert ov.download().tobytes() == fr.velocity.numpy().tobytes()
+        with pytest.raises(abi.RfxError):
+            ctx.gbuffer_ingest(planes[1], planes[1], planes[2], None, None, dd, og, ov)   # an RGBA32F albedo is rejected (BAD_FORMAT)
+    finally:
+        ctx.close()
