@@ -240,6 +240,23 @@ def other_configs(ctx, ch, dev, stream, peak):
     og.free()
     ov.free()
     del keep
+    # cosmetic effects tail at 3840x2160: Sharpness + GradualBackground + Sparkle merged in one launch
+    # (input 8 + depth 4 + velocity 16 in, 8 out = 36 B/px; the reference spends one full-frame round trip per effect)
+    fxp = ch.fx_params(f["cam"], [abi.FX_SHARPNESS, abi.FX_GRADUAL_BACKGROUND, abi.FX_SPARKLE])
+    fxo = ctx.alloc(abi.FMT_RGBA16F, W, H)
+    fxr = lambda _i: ctx.effects(fxp, dl, d, v, fxo)  # noqa: E731
+    for i in range(5):
+        fxr(i)
+    out["fx_tail_4k"] = line(time_frames(stream, fxr, 50), W, H, 36, {"workload": "rfx_effects_launch 3840x2160: Sharpness + GradualBackground + Sparkle merged (EffectPass semantics), one launch"})
+    tp = abi.TaaParams()
+    tp.camera_not_moved_frames, tp.srgb_output = 3.0, 1
+    th, to = ctx.alloc(abi.FMT_RGBA8, W, H), ctx.alloc(abi.FMT_RGBA8, W, H)
+    tr_ = lambda _i: ctx.taa(tp, dl, th, to)  # noqa: E731
+    for i in range(5):
+        tr_(i)
+    out["taa_pass_4k"] = line(time_frames(stream, tr_, 50), W, H, 16, {"workload": "rfx_taa_launch 3840x2160 (input RGBA16F 8 + history RGBA8 4 in, canvas RGBA8 4 out)"})
+    for pl in (fxo, th, to):
+        pl.free()
     # C1: MotionBlurEffect 256x256 (plumbing config)
     W, H = 256, 256
     inp = ch.make_inputs(W, H, 1)

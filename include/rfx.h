@@ -199,6 +199,38 @@ typedef struct rfx_ingest_params {
   int32_t _pad;
 } rfx_ingest_params;
 
+/* Cosmetic effects of the plugin surface, merged the way postprocessing's EffectPass merges the effects of one pass:
+ * every effect samples the SAME input buffer through `inputTexture`, and the colour flows from one effect's outputColor into the next
+ * effect's inputColor.  One launch applies up to 4 effects in the given order — one pass over memory instead of one per effect.
+ *   RFX_FX_SHARPNESS           src/sharpness/SharpnessEffect.js:4-30                (3x3 box unsharp mask)
+ *   RFX_FX_LENS_DISTORTION     src/lens-distortion/LensDistortionEffect.js:5-46     (radial undistortion + chromatic aberration; replaces the colour)
+ *   RFX_FX_GRADUAL_BACKGROUND  src/gradual-background/GradualBackgroundEffect.js:3-47 (needs depth)
+ *   RFX_FX_SPARKLE             src/sparkle/SparkleEffect.js:4-100                    (needs the velocity plane) */
+#define RFX_FX_SHARPNESS 1
+#define RFX_FX_LENS_DISTORTION 2
+#define RFX_FX_GRADUAL_BACKGROUND 3
+#define RFX_FX_SPARKLE 4
+typedef struct rfx_effects_params {
+  rfx_camera cam;             /* gradual background / sparkle; cam.perspective = `#if PERSPECTIVE_CAMERA == 1`                            */
+  int32_t n_effects;          /* 1..4                                                                                                  */
+  int32_t effects[4];         /* RFX_FX_* in application order                                                                         */
+  float sharpness;            /* SharpnessEffect option (default 1)                                                                    */
+  float alphax, alphay, aberration; /* LensDistortionEffect (defaults -0.05, -0.05, 1)                                                 */
+  float background_color[3];  /* GradualBackgroundEffect                                                                               */
+  float max_distance;         /* default 5                                                                                             */
+  float spread, intensity;    /* SparkleEffect uniforms (default 1, 1)                                                                 */
+  int32_t sparkle_perspective; /* SparkleEffect never defines PERSPECTIVE_CAMERA, so the reference takes the orthographic getViewZ branch:
+                                  0 = that behaviour, 1 = what a host that defines it gets                                              */
+  int32_t _pad;
+} rfx_effects_params;
+
+/* TAAPass   src/taa/TAAPass.js:68-94 + src/taa/shader/taa.frag: the still-camera accumulator that renders to the screen.
+ * out = cameraNotMovedFrames == 0 ? c : mix(history, c, 1 / (cameraNotMovedFrames + 1)),  c = linearToOutputTexel(input) */
+typedef struct rfx_taa_params {
+  float camera_not_moved_frames;
+  int32_t srgb_output;        /* 1: the renderer's output colour space is sRGB (three's default): linearToOutputTexel = LinearTosRGB  */
+} rfx_taa_params;
+
 /* Environment map + importance-sampling tables (struct EquirectHdrInfo, ssgi.frag:27-36;
  * built by src/ssgi/utils/EquirectHdrInfoUniform.js:149-245). */
 typedef struct rfx_env_desc {
@@ -325,6 +357,16 @@ rfx_status rfx_gbuffer_ingest_launch(rfx_ctx* ctx, void* stream, const rfx_inges
                                      const rfx_plane* normal, const rfx_plane* material, const rfx_plane* emissive,
                                      const rfx_plane* motion, const rfx_plane* depth, const rfx_plane* out_gbuffer,
                                      const rfx_plane* out_velocity, uint32_t row0, uint32_t row1);
+
+/* Merged cosmetic effects.  input RGBA16F (sampled LINEAR, clamp), depth R32F (gradual background; else may be NULL), velocity RGBA32F
+ * (sparkle; else may be NULL), out RGBA16F (may not alias input). */
+rfx_status rfx_effects_launch(rfx_ctx* ctx, void* stream, const rfx_effects_params* p, const rfx_plane* input, const rfx_plane* depth,
+                              const rfx_plane* velocity, const rfx_plane* out, uint32_t row0, uint32_t row1);
+
+/* TAAPass.  input RGBA16F, history RGBA8 (the FramebufferTexture copy of the canvas; may alias out: each pixel reads only itself),
+ * out RGBA8 (the canvas: clamp, round to nearest) */
+rfx_status rfx_taa_launch(rfx_ctx* ctx, void* stream, const rfx_taa_params* p, const rfx_plane* input, const rfx_plane* history,
+                          const rfx_plane* out, uint32_t row0, uint32_t row1);
 
 /* K9. src/traa/shader/traa_compose.frag:3-6  accumulated RGBA16F -> out RGBA16F (a = 1) */
 rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* accumulated,

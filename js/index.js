@@ -409,3 +409,104 @@ export class MotionBlurEffect {
 	get outputTexture() { return this.outputHost }
 	dispose() { if (this.planes) for (const p of Object.values(this.planes)) rfx.planeFree(this.ctx, p); this.planes = null }
 }
+
+// ---- cosmetic effects (src/index.js:25-31) -----------------------------------------------------------------------------------------
+// In the reference they are postprocessing Effects that an EffectPass merges into one fullscreen shader; here `RfxEffectPass` merges them
+// into ONE launch of rfx_effects_launch (every effect samples the pass's input buffer; the colour flows from effect to effect in order).
+const FX = { SHARPNESS: 1, LENS_DISTORTION: 2, GRADUAL_BACKGROUND: 3, SPARKLE: 4 }
+
+export class SharpnessEffect {
+	// new SharpnessEffect(options) — src/sharpness/SharpnessEffect.js:36-59
+	constructor(options = { sharpness: 1 }) { this.fxId = FX.SHARPNESS; this.sharpness = { sharpness: 1, ...options }.sharpness }
+	setSharpness(sharpness) { this.sharpness = sharpness }
+	update(renderer, inputBuffer) {}
+	fill(p) { p.sharpness = this.sharpness }
+}
+
+export class LensDistortionEffect {
+	// new LensDistortionEffect({ alphax, alphay, aberration }) — src/lens-distortion/LensDistortionEffect.js:48-77
+	constructor({ alphax = -0.05, alphay = -0.05, aberration = 1 } = {}) { this.fxId = FX.LENS_DISTORTION; Object.assign(this, { alphax, alphay, aberration }) }
+	setAlphaX(value) { this.alphax = value }
+	setAlphaY(value) { this.alphay = value }
+	update(renderer, inputBuffer) {}
+	fill(p) { Object.assign(p, { alphax: this.alphax, alphay: this.alphay, aberration: this.aberration }) }
+}
+
+export class GradualBackgroundEffect {
+	// new GradualBackgroundEffect(camera, depthTexture, backgroundColor, maxDistance = 5) — src/gradual-background/GradualBackgroundEffect.js:48-70
+	constructor(camera, depthTexture, backgroundColor, maxDistance = 5) { this.fxId = FX.GRADUAL_BACKGROUND; Object.assign(this, { camera, depthTexture, backgroundColor, maxDistance }) }
+	setBackgroundColor(color) { this.backgroundColor = color }
+	setMaxDistance(distance) { this.maxDistance = distance }
+	update() {}
+	fill(p) { const c = this.backgroundColor; p.backgroundColor = c.isColor ? [c.r, c.g, c.b] : c; p.maxDistance = this.maxDistance }
+}
+
+export class SparkleEffect {
+	// new SparkleEffect(camera, velocityDepthNormalPass) — src/sparkle/SparkleEffect.js:102-136 (PERSPECTIVE_CAMERA is never defined there:
+	// the reference's getViewZ takes the orthographic branch; definePerspectiveCamera = true gives what a host that defines it gets)
+	constructor(camera, velocityDepthNormalPass, definePerspectiveCamera = false) {
+		this.fxId = FX.SPARKLE; Object.assign(this, { camera, velocityDepthNormalPass, definePerspectiveCamera, spread: 1, intensity: 1 })
+	}
+	setSpread(spread) { this.spread = spread }
+	setIntensity(intensity) { this.intensity = intensity }
+	update() {}
+	fill(p) { Object.assign(p, { spread: this.spread, intensity: this.intensity, sparklePerspective: this.definePerspectiveCamera ? 1 : 0 }) }
+}
+
+export class RfxEffectPass {
+	// stands in for postprocessing's `new EffectPass(camera, ...effects)` when the effects are the four above
+	constructor(camera, ...effects) {
+		if (effects.length < 1 || effects.length > 4) throw new RangeError("RfxEffectPass: 1..4 effects")
+		this.camera = camera; this.effects = effects; this.ctx = context()
+	}
+	setSize(width, height) {
+		this.dispose()
+		this.width = width; this.height = height
+		this.planes = { input: rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height), output: rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height) }
+		this.hostIn = new Uint16Array(4 * width * height); this.outputHost = new Uint16Array(4 * width * height)
+	}
+	// render(renderer, inputBuffer, outputBuffer, deltaTime, stencilTest) — the Pass contract; planes: { depth, velocity } device planes of a PlaneSource
+	render(renderer, inputBuffer, outputBuffer, deltaTime, stencilTest, planes = {}) {
+		if (!this.planes || inputBuffer.width !== this.width) this.setSize(inputBuffer.width, inputBuffer.height)
+		renderer.readRenderTargetPixels(inputBuffer, 0, 0, this.width, this.height, this.hostIn)
+		rfx.planeUpload(this.ctx, this.planes.input, this.hostIn)
+		const p = { cam: cameraBlock(this.camera), count: this.effects.length, effects: this.effects.map(e => e.fxId) }
+		for (const e of this.effects) { e.update(renderer, inputBuffer, deltaTime); e.fill(p) }
+		rfx.effects(this.ctx, p, this.planes.input, planes.depth ?? null, planes.velocity ?? null, this.planes.output)
+		rfx.planeDownload(this.ctx, this.planes.output, this.outputHost)
+	}
+	dispose() { if (this.planes) for (const pl of Object.values(this.planes)) rfx.planeFree(this.ctx, pl); this.planes = null }
+}
+
+export class TAAPass {
+	// new TAAPass(camera) — src/taa/TAAPass.js:18-95 (renders to the screen; the RGBA8 `canvas` plane stands in for the default framebuffer)
+	constructor(camera, srgbOutput = true) {
+		this.camera = camera; this.srgbOutput = srgbOutput; this.ctx = context()
+		this.cameraNotMovedFrames = 0; this.frame = 0; this.needsUpdate = false; this.renderToScreen = true; this.last = null
+	}
+	setSize(width, height) {
+		this.dispose()
+		this.width = width; this.height = height
+		this.planes = { input: rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height), canvas: rfx.planeAlloc(this.ctx, FMT.RGBA8, width, height),
+			framebufferTexture: rfx.planeAlloc(this.ctx, FMT.RGBA8, width, height) }
+		this.hostIn = new Uint16Array(4 * width * height); this.outputHost = new Uint8Array(4 * width * height)
+		this.needsUpdate = true
+	}
+	// render(renderer, inputBuffer) — :68-94
+	render(renderer, inputBuffer) {
+		if (!this.planes || inputBuffer.width !== this.width) this.setSize(inputBuffer.width, inputBuffer.height)
+		this.frame = (this.frame + 1) % 4096
+		const e = this.camera.matrixWorld.elements
+		const moved = this.needsUpdate || !this.last || e.some((v, i) => Math.abs(v - this.last[i]) > 1e-6)   // didCameraMove (src/utils/SceneUtils.js:17-27)
+		this.needsUpdate = false
+		if (this.cameraNotMovedFrames > 0) jitter(this.width, this.height, this.camera, this.frame, 1)
+		this.cameraNotMovedFrames = moved ? 0 : (this.cameraNotMovedFrames + 1) % 4096
+		this.last = Array.from(e)
+		renderer.readRenderTargetPixels(inputBuffer, 0, 0, this.width, this.height, this.hostIn)
+		rfx.planeUpload(this.ctx, this.planes.input, this.hostIn)
+		rfx.taa(this.ctx, { cameraNotMovedFrames: this.cameraNotMovedFrames, srgbOutput: this.srgbOutput ? 1 : 0 }, this.planes.input, this.planes.framebufferTexture, this.planes.canvas)
+		rfx.planeDownload(this.ctx, this.planes.canvas, this.outputHost)
+		const t = this.planes.canvas; this.planes.canvas = this.planes.framebufferTexture; this.planes.framebufferTexture = t   // copyFramebufferToTexture (:93)
+	}
+	dispose() { if (this.planes) for (const pl of Object.values(this.planes)) rfx.planeFree(this.ctx, pl); this.planes = null }
+}

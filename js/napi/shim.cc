@@ -322,6 +322,31 @@ napi_value TraaCompose(napi_env env, napi_callback_info info) {  // traaCompose(
   return undefined(env);
 }
 
+napi_value Effects(napi_env env, napi_callback_info info) {  // effects(ctx, {cam, effects: [ids], sharpness, alphax, alphay, aberration, backgroundColor, maxDistance, spread, intensity, sparklePerspective}, input, depth|null, velocity|null, out)
+  ARGS(6); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  Obj b{env, argv[1]};
+  rfx_effects_params p{};
+  if (!read_camera(env, b.get("cam"), &p.cam)) { napi_throw_type_error(env, nullptr, "effects: cam"); return nullptr; }
+  float ids[4] = {0, 0, 0, 0};
+  p.n_effects = (int32_t)b.num("count", 1);
+  b.floats("effects", ids, 4);
+  for (int i = 0; i < 4; i++) p.effects[i] = (int32_t)ids[i];
+  p.sharpness = (float)b.num("sharpness", 1); p.alphax = (float)b.num("alphax", -0.05); p.alphay = (float)b.num("alphay", -0.05); p.aberration = (float)b.num("aberration", 1);
+  b.floats("backgroundColor", p.background_color, 3);
+  p.max_distance = (float)b.num("maxDistance", 5); p.spread = (float)b.num("spread", 1); p.intensity = (float)b.num("intensity", 1);
+  p.sparkle_perspective = (int32_t)b.num("sparklePerspective", 0);
+  CHECK(c, rfx_effects_launch(c, nullptr, &p, unwrap<rfx_plane>(env, argv[2]), unwrap<rfx_plane>(env, argv[3]), unwrap<rfx_plane>(env, argv[4]), unwrap<rfx_plane>(env, argv[5]), 0, 0),
+        "rfx_effects_launch");
+  return undefined(env);
+}
+napi_value Taa(napi_env env, napi_callback_info info) {  // taa(ctx, {cameraNotMovedFrames, srgbOutput}, input, history|null, out)
+  ARGS(5); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  Obj b{env, argv[1]};
+  rfx_taa_params p{};
+  p.camera_not_moved_frames = (float)b.num("cameraNotMovedFrames", 0); p.srgb_output = (int32_t)b.num("srgbOutput", 1);
+  CHECK(c, rfx_taa_launch(c, nullptr, &p, unwrap<rfx_plane>(env, argv[2]), unwrap<rfx_plane>(env, argv[3]), unwrap<rfx_plane>(env, argv[4]), 0, 0), "rfx_taa_launch");
+  return undefined(env);
+}
 napi_value GbufferIngest(napi_env env, napi_callback_info info) {  // gbufferIngest(ctx, {motionScale, normalizeNormals}, albedo, normal, material, emissive|null, motion|null, depth, outGbuffer|null, outVelocity|null)
   ARGS(10); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
   Obj b{env, argv[1]};
@@ -344,7 +369,7 @@ napi_value Init(napi_env env, napi_value exports) {
       FN("chainRender", ChainRender), FN("chainOutput", ChainOutput), FN("chainRenderHost", ChainRenderHost), FN("chainWaitHost", ChainWaitHost),
       FN("chainReset", ChainReset), FN("chainDestroy", ChainDestroy), FN("ssgiCompose", SsgiCompose), FN("temporalReproject", TemporalReproject),
       FN("poissonDenoise", PoissonDenoise), FN("giCompose", GiCompose), FN("hbao", Hbao), FN("aoCompose", AoCompose), FN("motionBlur", MotionBlur),
-      FN("traaCompose", TraaCompose), FN("gbufferIngest", GbufferIngest),
+      FN("traaCompose", TraaCompose), FN("gbufferIngest", GbufferIngest), FN("effects", Effects), FN("taa", Taa),
   };
 #undef FN
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);

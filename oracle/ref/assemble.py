@@ -49,7 +49,25 @@ float luminance( const in vec3 rgb ) {
 	const vec3 weights = vec3( 0.2126729, 0.7151522, 0.0721750 );
 	return dot( weights, rgb );
 }
+highp float rand( const in vec2 uv ) {
+	const highp float a = 12.9898, b = 78.233, c = 43758.5453;
+	highp float dt = dot( uv.xy, vec2( a,b ) ), sn = mod( dt, PI );
+	return fract( sin( sn ) * c );
+}
 """
+# three r151 ShaderChunk/encodings_pars_fragment.glsl.js: what `linearToOutputTexel` resolves to for an sRGB output (WebGLProgram
+# getTexelEncodingFunction) and for a linear one
+THREE_LINEAR_TO_OUTPUT = {
+    True: """
+vec4 LinearTosRGB( in vec4 value ) {
+	return vec4( mix( pow( value.rgb, vec3( 0.41666 ) ) * 1.055 - vec3( 0.055 ), value.rgb * 12.92, vec3( lessThanEqual( value.rgb, vec3( 0.0031308 ) ) ) ), value.a );
+}
+vec4 linearToOutputTexel( vec4 value ) { return LinearTosRGB( value ); }
+""",
+    False: """
+vec4 linearToOutputTexel( vec4 value ) { return value; }
+""",
+}
 # three r151 ShaderChunk/packing.glsl.js (subset)
 THREE_PACKING = """
 vec3 packNormalToRGB( const in vec3 normal ) {
@@ -259,7 +277,8 @@ def hbao(*, spp=8, animated_noise=False, use_normal_texture=False) -> str:
 
 # postprocessing's EffectMaterial: the effect's mainImage() is called with the input buffer's texel and vUv; the result is
 # written with the effect's blend function (NORMAL: dst = src) — postprocessing 6.x src/materials/glsl/effect.frag
-EFFECT_HEAD = "varying vec2 vUv;\nuniform sampler2D inputBuffer;\n"
+EFFECT_HEAD = ("varying vec2 vUv;\nuniform sampler2D inputBuffer;\nuniform vec2 resolution;\nuniform vec2 texelSize;\nuniform float cameraNear;\nuniform float cameraFar;\n"
+               + THREE_COMMON + THREE_PACKING)
 EFFECT_MAIN = """
 void main() {
   vec4 color0 = texture2D(inputBuffer, vUv);
@@ -301,4 +320,37 @@ def ssgi_compose(*, fog=False, fog_exp2=False, perspective=True) -> str:
         d["USE_FOG"] = ""
     if fog_exp2:
         d["FOG_EXP2"] = ""
-    return _effect(THREE_PACKING + frag, d)
+    return _effect(frag, d)
+
+
+def _js_template(rel: str) -> str:
+    """the `const fragmentShader = /* glsl */ `...`` literal of an Effect's JS file"""
+    m = re.search(r"const fragmentShader\s*=\s*/\*\s*glsl\s*\*/\s*`(.*?)`", read(rel), flags=re.S)
+    return m.group(1)
+
+
+def sharpness() -> str:
+    """src/sharpness/SharpnessEffect.js:4-30"""
+    return _effect(_js_template("sharpness/SharpnessEffect.js"), {})
+
+
+def lens_distortion() -> str:
+    """src/lens-distortion/LensDistortionEffect.js:5-46"""
+    return _effect(_js_template("lens-distortion/LensDistortionEffect.js"), {})
+
+
+def gradual_background(*, perspective=True) -> str:
+    """src/gradual-background/GradualBackgroundEffect.js:3-47,59"""
+    return _effect(_js_template("gradual-background/GradualBackgroundEffect.js"), {"PERSPECTIVE_CAMERA": "1" if perspective else "0"})
+
+
+def sparkle(*, perspective=True) -> str:
+    """src/sparkle/SparkleEffect.js:4-100.  PERSPECTIVE_CAMERA is never defined by SparkleEffect (its `#if PERSPECTIVE_CAMERA == 1` therefore
+    takes the orthographic branch in the reference); `perspective` selects what a host that defines it gets."""
+    frag = _js_template("sparkle/SparkleEffect.js").replace("${gbuffer_packing}", read("gbuffer/shader/gbuffer_packing.glsl"))
+    return _effect(frag, {"PERSPECTIVE_CAMERA": "1"} if perspective else {})
+
+
+def taa(*, srgb_output=True) -> str:
+    """src/taa/TAAPass.js:37-50 + shader/taa.frag; rendered to the screen, so linearToOutputTexel is the renderer's output transfer"""
+    return finish(THREE_LINEAR_TO_OUTPUT[bool(srgb_output)] + read("taa/shader/taa.frag"), {})

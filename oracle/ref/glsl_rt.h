@@ -233,6 +233,10 @@ inline vec2 unpackHalf2x16(uint u) { const gl::vec2 r = gl::unpackHalf2x16(u); r
   inline vec<float, N> reflect(const vec<float, N>& I, const vec<float, N>& n) { const float k2 = 2.0f * dot(n, I); vec<float, N> r; for (int k = 0; k < N; k++) r.d[k] = gl::fma_(-k2, n.d[k], I.d[k]); return r; } \
   inline vec<bool, N> lessThan(const vec<float, N>& a, const vec<float, N>& b) { vec<bool, N> r; for (int k = 0; k < N; k++) r.d[k] = a.d[k] < b.d[k]; return r; } \
   inline vec<bool, N> greaterThan(const vec<float, N>& a, const vec<float, N>& b) { vec<bool, N> r; for (int k = 0; k < N; k++) r.d[k] = a.d[k] > b.d[k]; return r; } \
+  inline vec<bool, N> lessThanEqual(const vec<float, N>& a, const vec<float, N>& b) { vec<bool, N> r; for (int k = 0; k < N; k++) r.d[k] = a.d[k] <= b.d[k]; return r; } \
+  inline vec<bool, N> greaterThanEqual(const vec<float, N>& a, const vec<float, N>& b) { vec<bool, N> r; for (int k = 0; k < N; k++) r.d[k] = a.d[k] >= b.d[k]; return r; } \
+  inline vec<bool, N> equal(const vec<float, N>& a, const vec<float, N>& b) { vec<bool, N> r; for (int k = 0; k < N; k++) r.d[k] = a.d[k] == b.d[k]; return r; } \
+  inline vec<bool, N> notEqual(const vec<float, N>& a, const vec<float, N>& b) { vec<bool, N> r; for (int k = 0; k < N; k++) r.d[k] = a.d[k] != b.d[k]; return r; } \
   inline bool any(const vec<bool, N>& a) { for (int k = 0; k < N; k++) if (a.d[k]) return true; return false; }                                     \
   inline bool all(const vec<bool, N>& a) { for (int k = 0; k < N; k++) if (!a.d[k]) return false; return true; }
 // dot: fma chain, last component outermost (oracle/glsl.h)

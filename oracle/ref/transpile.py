@@ -121,6 +121,22 @@ def transpile(glsl: str, *, effect_main: bool = False) -> tuple[str, dict]:
     s = _FLOAT_LIT.sub(lambda m: m.group(1) + "f", s)
     s = drop_prototypes(s)
 
+    # a swizzle of a swizzle (`c.rgb.rgb`, from macros like luminance(c) applied to `x.rgb`) is folded into one swizzle
+    comp = {c: i for i, c in enumerate("xyzw")} | {c: i for i, c in enumerate("rgba")}
+
+    field_names = {n for fields in parse_structs(s).values() for _, n in fields}  # InputTexel has a member called `rgb`
+
+    def _fold(m):
+        first, second = m.group(1), m.group(2)
+        if first in field_names:
+            return m.group(0)
+        return "." + "".join(first[comp[c]] for c in second)
+
+    prev = None
+    while prev != s:
+        prev = s
+        s = re.sub(r"\.([xyzw]{2,4}|[rgba]{2,4})\.([xyzw]{1,4}|[rgba]{1,4})\b", _fold, s)
+
     structs = parse_structs(s)
     uniforms, outputs = [], []
 

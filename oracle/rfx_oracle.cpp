@@ -1374,6 +1374,167 @@ void orc_traa_compose(int W, int H, const uint16_t* accumulated, uint16_t* out) 
     for (int x = 0; x < W; x++) store_rgba16f(out, W, x, y, vec4(textureLod0(a, pixelUv(x, y, W, H)).xyz(), 1.0f));
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cosmetic effects, merged like postprocessing's EffectPass: one input buffer, colour chained.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace fx {
+const float PI_COMMON = 3.141592653589793f;  // three <common>
+// three <common> rand()
+inline float rand2(vec2 uv) {
+  const float a = 12.9898f, b = 78.233f, c = 43758.5453f;
+  float dt = dot(uv, vec2(a, b)), sn = modf_gl(dt, PI_COMMON);
+  float v = sincr(sn) * c;
+  return v - std::floor(v);
+}
+inline vec4 add4(vec4 a, vec4 b) { return a + b; }
+// SharpnessEffect.js:8-29
+inline vec4 sharpness(const Tex& inputTexture, vec4 inputColor, vec2 uv, vec2 texelSize, float sharp) {
+  auto T = [&](vec2 o) { return textureLod0(inputTexture, uv + o * texelSize); };
+  vec4 blurredPixel = textureLod0(inputTexture, uv - 1.0f * texelSize);
+  blurredPixel += T(vec2(0.0f, -1.0f));
+  blurredPixel += T(vec2(1.0f, -1.0f));
+  blurredPixel += T(vec2(-1.0f, 0.0f));
+  blurredPixel += inputColor;
+  blurredPixel += T(vec2(1.0f, 0.0f));
+  blurredPixel += T(vec2(-1.0f, 1.0f));
+  blurredPixel += T(vec2(0.0f, 1.0f));
+  blurredPixel += textureLod0(inputTexture, uv + 1.0f * texelSize);
+  blurredPixel = blurredPixel / 9.0f;
+  vec4 sharpDiff = inputColor - blurredPixel;
+  vec4 sharpenedPixel = inputColor + sharpDiff * sharp;
+  return vec4(gmax(sharpenedPixel.x, 0.0f), gmax(sharpenedPixel.y, 0.0f), gmax(sharpenedPixel.z, 0.0f), sharpenedPixel.w);
+}
+// LensDistortionEffect.js:14-45
+inline vec4 lens_distortion(const Tex& inputTexture, vec2 vUv, vec2 resolution, float alphax, float alphay, float aberration) {
+  float x = (2.0f * vUv.x - 1.0f) / 1.0f;
+  float y = (2.0f * vUv.y - 1.0f) / 1.0f;
+  float r = x * x + y * y;
+  float x3 = x / (1.0f - alphax * r);
+  float y3 = y / (1.0f - alphay * r);
+  float x2 = x / (1.0f - alphax * (x3 * x3 + y3 * y3));
+  float y2 = y / (1.0f - alphay * (x3 * x3 + y3 * y3));
+  float i2 = (x2 + 1.0f) * 1.0f / 2.0f;
+  float j2 = (y2 + 1.0f) * 1.0f / 2.0f;
+  vec2 duv = vec2(i2, j2);
+  vec2 rOffset = vec2(1.0f / resolution.x, 0.0f);
+  vec2 gOffset = vec2(0.0f, 1.0f / resolution.y);
+  vec2 bOffset = vec2(1.0f / resolution.x, 1.0f / resolution.y);
+  vec4 rValue = textureLod0(inputTexture, duv - aberration * rOffset);
+  vec4 gValue = textureLod0(inputTexture, duv - aberration * gOffset);
+  vec4 bValue = textureLod0(inputTexture, duv - aberration * bOffset);
+  return vec4(rValue.x, gValue.y, bValue.z, 1.0f);
+}
+// getViewPosition of GradualBackgroundEffect.js:22-29 / SparkleEffect.js:29-36
+inline vec3 view_position(const Camera& cam, vec2 vUv, float viewZ) {
+  float clipW = cam.projectionMatrix.at(2, 3) * viewZ + cam.projectionMatrix.at(3, 3);
+  vec4 clipPosition = vec4((vec3(vUv, viewZ) - 0.5f) * 2.0f, 1.0f);
+  clipPosition = clipPosition * clipW;
+  vec3 p = (cam.projectionMatrixInverse * clipPosition).xyz();
+  p.z = viewZ;
+  return p;
+}
+// GradualBackgroundEffect.js:31-46
+inline vec4 gradual_background(const Camera& cam, const Tex& depthTexture, vec4 inputColor, vec2 uv, vec3 backgroundColor, float maxDistance) {
+  float depth = textureLod0(depthTexture, uv).x;
+  float viewZ = cam.perspective ? perspectiveDepthToViewZ(depth, cam.cameraNear, cam.cameraFar) : orthographicDepthToViewZ(depth, cam.cameraNear, cam.cameraFar);
+  vec3 viewPos = view_position(cam, uv, viewZ);
+  vec3 worldPos = (cam.cameraMatrixWorld * vec4(viewPos, 1.0f)).xyz();
+  float distToCenter = length(vec2(worldPos.x, worldPos.z)) + gmax(0.0f, -worldPos.y);
+  float fade = clampf(powcr(distToCenter, 0.1f) * 15.0f - maxDistance, 0.0f, 1.0f);
+  vec3 color = mix(inputColor.xyz(), backgroundColor, fade);
+  return vec4(color, 1.0f);
+}
+// SparkleEffect.js:38-43
+inline float nn(vec2 n) {
+  vec2 b = vec2(std::floor(n.x), std::floor(n.y));
+  vec2 fr = vec2(n.x - std::floor(n.x), n.y - std::floor(n.y));
+  vec2 f = vec2(smoothstepf(0.0f, 1.0f, fr.x), smoothstepf(0.0f, 1.0f, fr.y));
+  return mixf(mixf(rand2(b), rand2(b + vec2(1.0f, 0.0f)), f.x), mixf(rand2(b + vec2(0.0f, 1.0f)), rand2(b + vec2(1.0f, 1.0f)), f.x), f.y);
+}
+// SparkleEffect.js:45-99
+inline vec4 sparkle(const Camera& cam, bool perspective_defined, const Tex& velocityTexture, vec4 inputColor, vec2 uv, float spread, float intensity) {
+  vec4 velocityTexel = textureLod0(velocityTexture, uv);
+  float depth = velocityTexel.w;
+  if (depth == 0.0f || depth == 1.0f) return inputColor;
+  vec3 normal = unpackNormal(velocityTexel.z);
+  vec3 viewNormal = normalize((cam.viewMatrix * vec4(normal, 0.0f)).xyz());
+  float viewZ = perspective_defined ? perspectiveDepthToViewZ(depth, cam.cameraNear, cam.cameraFar) : orthographicDepthToViewZ(depth, cam.cameraNear, cam.cameraFar);
+  vec3 viewPos = view_position(cam, uv, viewZ);
+  vec3 viewDir = normalize(viewPos);
+  vec3 worldPos = (cam.cameraMatrixWorld * vec4(viewPos, 1.0f)).xyz();
+  if (worldPos.y < 0.01f) return inputColor;
+  vec3 cameraPos = (cam.cameraMatrixWorld * vec4(0.0f, 0.0f, 0.0f, 1.0f)).xyz();
+  float dist = length(worldPos - cameraPos);
+  float distFactor = expcr(-dist * 0.005f);
+  float facing = gmax(dot(-viewDir, viewNormal), 0.0f);
+  facing = powcr(facing, 4.0f);
+  vec3 nw = normalize(worldPos);
+  vec2 offset = vec2(nw.x, nw.z) * 1000.0f + vec2(normal.x, normal.z) * 500.0f;
+  float noise = nn(offset);
+  noise = powcr(noise, 500.0f * spread);
+  float lum = dot(inputColor.xyz(), vec3(0.299f, 0.587f, 0.114f));
+  lum = smoothstepf(0.15f, 1.0f, lum);
+  float sparkleFactor = noise * lum * facing * distFactor * 5000.0f * intensity;
+  vec3 c = inputColor.xyz();
+  vec3 color = c + vec3(powcr(c.x, 4.0f), powcr(c.y, 4.0f), powcr(c.z, 4.0f)) * sparkleFactor;
+  return vec4(color, 1.0f);
+}
+}  // namespace fx
+
+extern "C" {
+// input RGBA16F linear; depth R32F | NULL; velocity RGBA32F | NULL; out RGBA16F
+void orc_effects(const rfx_effects_params* p, int W, int H, const uint16_t* input, const float* depth, const float* velocity, uint16_t* out) {
+  Tex in = mk(input, W, H, F_RGBA16F, true), d = mk(depth, W, H, F_R32F), v = mk(velocity, W, H, F_RGBA32F);
+  Camera cam(p->cam);
+  vec2 resolution((float)W, (float)H), texelSize((float)(1.0 / W), (float)(1.0 / H));  // postprocessing: texelSize = 1 / size (JS doubles -> float32)
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      vec2 uv = pixelUv(x, y, W, H);
+      vec4 c = textureLod0(in, uv);  // EffectPass: color0 = texture2D(inputBuffer, vUv)
+      for (int e = 0; e < p->n_effects; e++) {
+        switch (p->effects[e]) {
+          case RFX_FX_SHARPNESS: c = fx::sharpness(in, c, uv, texelSize, p->sharpness); break;
+          case RFX_FX_LENS_DISTORTION: c = fx::lens_distortion(in, uv, resolution, p->alphax, p->alphay, p->aberration); break;
+          case RFX_FX_GRADUAL_BACKGROUND:
+            c = fx::gradual_background(cam, d, c, uv, vec3(p->background_color[0], p->background_color[1], p->background_color[2]), p->max_distance); break;
+          case RFX_FX_SPARKLE: c = fx::sparkle(cam, p->sparkle_perspective != 0, v, c, uv, p->spread, p->intensity); break;
+          default: break;
+        }
+      }
+      store_rgba16f(out, W, x, y, c);
+    }
+}
+// TAAPass: input RGBA16F, history RGBA8, out RGBA8
+void orc_taa(const rfx_taa_params* p, int W, int H, const uint16_t* input, const uint8_t* history, uint8_t* out) {
+  Tex in = mk(input, W, H, F_RGBA16F, true), acc = mk(history, W, H, F_RGBA8);
+#pragma omp parallel for
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      vec2 uv = pixelUv(x, y, W, H);
+      vec4 color = textureLod0(in, uv);
+      if (p->srgb_output) {  // three LinearTosRGB
+        for (int i = 0; i < 3; i++) {
+          float v = color[i];
+          float hi = powcr(v, 0.41666f) * 1.055f - 0.055f, lo = v * 12.92f;
+          color[i] = mixf(hi, lo, v <= 0.0031308f ? 1.0f : 0.0f);
+        }
+      }
+      vec4 o = color;
+      if (!(p->camera_not_moved_frames == 0.0f)) {
+        vec4 a = textureLod0(acc, uv);
+        float t = 1.0f / (p->camera_not_moved_frames + 1.0f);
+        for (int i = 0; i < 4; i++) o[i] = mixf(a[i], color[i], t);
+      }
+      uint8_t* q = out + 4 * ((size_t)y * W + x);
+      for (int i = 0; i < 4; i++) q[i] = (uint8_t)std::lround(clampf(o[i], 0.0f, 1.0f) * 255.0f);
+    }
+}
+}  // extern "C"
+
+extern "C" {
 // G-buffer ingest (include/rfx.h rfx_gbuffer_ingest_launch): packGBuffer :166-178 + the velocity layout of
 // VelocityDepthNormalMaterial.js:76-83,186-188 over SoA planes.  fmt_*: gl::Fmt of the plane (albedo / material RGBA8 | RGBA16F,
 // normal / motion RGBA16F | RGBA32F).  emissive / motion may be NULL.  out_* may be NULL.

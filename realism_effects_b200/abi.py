@@ -89,6 +89,33 @@ class IngestParams(C.Structure):
     _fields_ = [("motion_scale", F2), ("normalize_normals", C.c_int32), ("_pad", C.c_int32)]
 
 
+FX_SHARPNESS, FX_LENS_DISTORTION, FX_GRADUAL_BACKGROUND, FX_SPARKLE = 1, 2, 3, 4
+
+
+class EffectsParams(C.Structure):
+    _fields_ = [("cam", CameraS), ("n_effects", C.c_int32), ("effects", C.c_int32 * 4), ("sharpness", C.c_float), ("alphax", C.c_float), ("alphay", C.c_float),
+                ("aberration", C.c_float), ("background_color", F3), ("max_distance", C.c_float), ("spread", C.c_float), ("intensity", C.c_float),
+                ("sparkle_perspective", C.c_int32), ("_pad", C.c_int32)]
+
+
+class TaaParams(C.Structure):
+    _fields_ = [("camera_not_moved_frames", C.c_float), ("srgb_output", C.c_int32)]
+
+
+def make_effects_params(cam_u: dict, effects, *, sharpness=1.0, alphax=-0.05, alphay=-0.05, aberration=1.0, background_color=(0.0, 0.0, 0.0), max_distance=5.0,
+                        spread=1.0, intensity=1.0, sparkle_perspective=False, perspective=True) -> "EffectsParams":
+    """defaults: SharpnessEffect.js:32-34, LensDistortionEffect.js:49, GradualBackgroundEffect.js:49, SparkleEffect.js:110-111"""
+    p = EffectsParams()
+    p.cam = make_camera(cam_u, perspective)
+    p.n_effects = len(effects)
+    for i, e in enumerate(effects):
+        p.effects[i] = int(e)
+    p.sharpness, p.alphax, p.alphay, p.aberration = sharpness, alphax, alphay, aberration
+    p.background_color[:] = [float(c) for c in background_color]
+    p.max_distance, p.spread, p.intensity, p.sparkle_perspective = max_distance, spread, intensity, int(bool(sparkle_perspective))
+    return p
+
+
 class EnvDesc(C.Structure):
     _fields_ = [("map_rgba16f", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("marginal", C.c_void_p),
                 ("conditional", C.c_void_p), ("total_sum_whole", C.c_float), ("total_sum_decimal", C.c_float)]
@@ -172,6 +199,8 @@ def _sig(lib):
     lib.rfx_ao_compose_launch.argtypes = [vp, vp, _P(AoComposeParams), PP, PP, PP, PP, u32, u32]
     lib.rfx_motion_blur_launch.argtypes = [vp, vp, _P(MotionBlurParams), PP, PP, PP, u32, u32]
     lib.rfx_traa_compose_launch.argtypes = [vp, vp, PP, PP, u32, u32]
+    lib.rfx_effects_launch.argtypes = [vp, vp, _P(EffectsParams), PP, PP, PP, PP, u32, u32]
+    lib.rfx_taa_launch.argtypes = [vp, vp, _P(TaaParams), PP, PP, PP, u32, u32]
     lib.rfx_gbuffer_ingest_launch.argtypes = [vp, vp, _P(IngestParams), PP, PP, PP, PP, PP, PP, PP, PP, u32, u32]
     lib.rfx_ssgi_chain_create.argtypes = [vp, _P(ChainOptions), _P(vp)]
     lib.rfx_ssgi_chain_destroy.argtypes = [vp]
@@ -217,7 +246,7 @@ EXPORTS = [
     "rfx_blue_noise_set", "rfx_env_set", "rfx_env_clear", "rfx_env_build", "rfx_env_tables_download", "rfx_plane_alloc", "rfx_plane_free", "rfx_plane_clear", "rfx_plane_upload",
     "rfx_plane_download", "rfx_host_alloc", "rfx_host_free", "rfx_format_bytes", "rfx_ssgi_trace_launch",
     "rfx_temporal_reproject_launch", "rfx_poisson_denoise_launch", "rfx_gi_compose_launch", "rfx_ssgi_compose_launch", "rfx_hbao_launch",
-    "rfx_ao_compose_launch", "rfx_motion_blur_launch", "rfx_traa_compose_launch", "rfx_gbuffer_ingest_launch", "rfx_ssgi_chain_create", "rfx_ssgi_chain_destroy",
+    "rfx_ao_compose_launch", "rfx_motion_blur_launch", "rfx_traa_compose_launch", "rfx_gbuffer_ingest_launch", "rfx_effects_launch", "rfx_taa_launch", "rfx_ssgi_chain_create", "rfx_ssgi_chain_destroy",
     "rfx_ssgi_chain_reset", "rfx_ssgi_chain_render", "rfx_ssgi_chain_output", "rfx_ssgi_chain_render_host",
     "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host", "rfx_ssgi_chain_render_part",
     "rfx_ssgi_chain_set_profiling", "rfx_ssgi_chain_get_profile", "rfx_ssgi_chain_set_options", "rfx_ssgi_chain_render_ranges", "rfx_ssgi_chain_render_blocks",

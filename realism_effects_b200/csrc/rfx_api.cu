@@ -705,6 +705,50 @@ rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* 
   return RFX_OK;
 }
 
+rfx_status rfx_effects_launch(rfx_ctx* ctx, void* stream, const rfx_effects_params* p, const rfx_plane* input, const rfx_plane* depth, const rfx_plane* velocity,
+                              const rfx_plane* out, uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !input || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "effects: null argument");
+  if (p->n_effects < 1 || p->n_effects > 4) return fail(ctx, RFX_ERR_INVALID_ARG, "effects: n_effects must be 1..4");
+  EffectsArgs a{};
+  if (!pv(input, RFX_FMT_RGBA16F, a.input) || !ov(out, RFX_FMT_RGBA16F, a.out)) return fail(ctx, RFX_ERR_BAD_FORMAT, "effects: input / out must be RGBA16F");
+  if (input->ptr == out->ptr) return fail(ctx, RFX_ERR_INVALID_ARG, "effects: out may not alias input (neighbour taps)");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.input.w != a.W || a.input.h != a.H) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "effects: plane sizes differ");
+  for (int i = 0; i < p->n_effects; i++) {
+    const int e = p->effects[i];
+    a.effects[i] = e;
+    if (e < RFX_FX_SHARPNESS || e > RFX_FX_SPARKLE) return fail(ctx, RFX_ERR_INVALID_ARG, "effects: unknown effect id %d", e);
+    if (e == RFX_FX_GRADUAL_BACKGROUND && (!pv(depth, RFX_FMT_R32F, a.depth) || a.depth.w != a.W || a.depth.h != a.H))
+      return fail(ctx, RFX_ERR_BAD_FORMAT, "effects: GradualBackground needs an R32F depth plane of the output size");
+    if (e == RFX_FX_SPARKLE && (!pv(velocity, RFX_FMT_RGBA32F, a.velocity) || a.velocity.w != a.W || a.velocity.h != a.H))
+      return fail(ctx, RFX_ERR_BAD_FORMAT, "effects: Sparkle needs an RGBA32F velocity plane of the output size");
+  }
+  a.n_effects = p->n_effects;
+  cam_to_dev(p->cam, a.cam);
+  a.texel_x = (float)(1.0 / a.W); a.texel_y = (float)(1.0 / a.H);
+  a.sharpness = p->sharpness; a.alphax = p->alphax; a.alphay = p->alphay; a.aberration = p->aberration;
+  memcpy(a.bg, p->background_color, 12);
+  a.max_distance = p->max_distance; a.spread = p->spread; a.intensity = p->intensity; a.sparkle_perspective = p->sparkle_perspective;
+  rows(row0, row1, out->height, a.row0, a.row1);
+  LAUNCHED(launch_effects(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
+rfx_status rfx_taa_launch(rfx_ctx* ctx, void* stream, const rfx_taa_params* p, const rfx_plane* input, const rfx_plane* history, const rfx_plane* out,
+                          uint32_t row0, uint32_t row1) {
+  if (!ctx || !p || !input || !out) return fail(ctx, RFX_ERR_INVALID_ARG, "taa: null argument");
+  TaaArgs a{};
+  if (!pv(input, RFX_FMT_RGBA16F, a.input) || !ov(out, RFX_FMT_RGBA8, a.out)) return fail(ctx, RFX_ERR_BAD_FORMAT, "taa: input RGBA16F, out RGBA8");
+  a.W = (int)out->width; a.H = (int)out->height;
+  if (a.input.w != a.W || a.input.h != a.H) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "taa: plane sizes differ");
+  if (p->camera_not_moved_frames != 0.0f && (!pv(history, RFX_FMT_RGBA8, a.history) || a.history.w != a.W || a.history.h != a.H))
+    return fail(ctx, RFX_ERR_BAD_FORMAT, "taa: an RGBA8 history plane of the output size is needed once the camera stands still");
+  a.camera_not_moved_frames = p->camera_not_moved_frames; a.srgb_output = p->srgb_output;
+  rows(row0, row1, out->height, a.row0, a.row1);
+  LAUNCHED(launch_taa(a, pick(ctx, stream)));
+  return RFX_OK;
+}
+
 rfx_status rfx_gbuffer_ingest_launch(rfx_ctx* ctx, void* stream, const rfx_ingest_params* p, const rfx_plane* albedo, const rfx_plane* normal,
                                      const rfx_plane* material, const rfx_plane* emissive, const rfx_plane* motion, const rfx_plane* depth,
                                      const rfx_plane* out_gbuffer, const rfx_plane* out_velocity, uint32_t row0, uint32_t row1) {

@@ -190,6 +190,27 @@ struct TraaComposeArgs {
 };
 cudaError_t launch_traa_compose(const TraaComposeArgs& a, cudaStream_t s);
 
+// merged cosmetic effects + TAAPass (k_fx.cu)
+struct EffectsArgs {
+  PV input, depth, velocity;
+  OutV out;
+  CamD cam;
+  int W, H, row0, row1;
+  int n_effects, effects[4];
+  float texel_x, texel_y;  // postprocessing's texelSize = 1 / size (a JS double rounded to fp32)
+  float sharpness, alphax, alphay, aberration, bg[3], max_distance, spread, intensity;
+  int sparkle_perspective;
+};
+cudaError_t launch_effects(const EffectsArgs& a, cudaStream_t s);
+struct TaaArgs {
+  PV input, history;
+  OutV out;
+  int W, H, row0, row1;
+  float camera_not_moved_frames;
+  int srgb_output;
+};
+cudaError_t launch_taa(const TaaArgs& a, cudaStream_t s);
+
 // G-buffer ingest (k_ingest.cu)
 struct IngestArgs {
   PV albedo, normal, material, emissive, motion, depth;  // emissive.p / motion.p may be null

@@ -507,3 +507,158 @@ class MotionBlurEffect(_Reactive):
 def getMaxMipLevel(width: int, height: int) -> int:
     """src/ssgi/utils/Utils.js:30-34"""
     return math.floor(math.log2(max(width, height))) + 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# Cosmetic effects of the plugin surface (src/index.js:25-31) and the pass that merges them.
+# ---------------------------------------------------------------------------------------------------
+class SharpnessEffect:
+    """new SharpnessEffect(options)  (src/sharpness/SharpnessEffect.js:36-59)"""
+
+    fx_id = abi.FX_SHARPNESS
+
+    def __init__(self, options=None):
+        self.sharpness = {"sharpness": 1, **(options or {})}["sharpness"]
+
+    def setSharpness(self, sharpness):
+        self.sharpness = sharpness
+
+    def update(self, renderer=None, inputBuffer=None, deltaTime=None):
+        pass  # `inputTexture = inputBuffer.texture`: the merged kernel reads the pass input directly
+
+    def _fill(self, p: abi.EffectsParams):
+        p.sharpness = float(self.sharpness)
+
+
+class LensDistortionEffect:
+    """new LensDistortionEffect({ alphax, alphay, aberration })  (src/lens-distortion/LensDistortionEffect.js:48-77)"""
+
+    fx_id = abi.FX_LENS_DISTORTION
+
+    def __init__(self, options=None):
+        o = {"alphax": -0.05, "alphay": -0.05, "aberration": 1, **(options or {})}
+        self.alphax, self.alphay, self.aberration = o["alphax"], o["alphay"], o["aberration"]
+
+    def setAlphaX(self, value):
+        self.alphax = value
+
+    def setAlphaY(self, value):
+        self.alphay = value
+
+    def update(self, renderer=None, inputBuffer=None, deltaTime=None):
+        pass
+
+    def _fill(self, p: abi.EffectsParams):
+        p.alphax, p.alphay, p.aberration = float(self.alphax), float(self.alphay), float(self.aberration)
+
+
+class GradualBackgroundEffect:
+    """new GradualBackgroundEffect(camera, depthTexture, backgroundColor, maxDistance = 5)  (src/gradual-background/GradualBackgroundEffect.js:48-70)"""
+
+    fx_id = abi.FX_GRADUAL_BACKGROUND
+
+    def __init__(self, camera, depthTexture, backgroundColor, maxDistance=5):
+        self._camera, self.depthTexture, self.backgroundColor, self.maxDistance = camera, depthTexture, tuple(backgroundColor), maxDistance
+
+    def setBackgroundColor(self, color):
+        self.backgroundColor = tuple(color)
+
+    def setMaxDistance(self, distance):
+        self.maxDistance = distance
+
+    def update(self, renderer=None, inputBuffer=None, deltaTime=None):
+        pass
+
+    def _fill(self, p: abi.EffectsParams):
+        p.background_color[:] = [float(c) for c in self.backgroundColor]
+        p.max_distance = float(self.maxDistance)
+
+
+class SparkleEffect:
+    """new SparkleEffect(camera, velocityDepthNormalPass)  (src/sparkle/SparkleEffect.js:102-136).  The reference never defines
+    PERSPECTIVE_CAMERA for this effect, so its getViewZ takes the orthographic branch; `definePerspectiveCamera = True` gives what a host
+    that defines it gets."""
+
+    fx_id = abi.FX_SPARKLE
+
+    def __init__(self, camera, velocityDepthNormalPass, definePerspectiveCamera=False):
+        self._camera, self.velocityDepthNormalPass = camera, velocityDepthNormalPass
+        self.spread, self.intensity, self.definePerspectiveCamera = 1, 1, definePerspectiveCamera
+
+    def setSpread(self, spread):
+        self.spread = spread
+
+    def setIntensity(self, intensity):
+        self.intensity = intensity
+
+    def update(self, renderer=None, inputBuffer=None, deltaTime=None):
+        pass
+
+    def _fill(self, p: abi.EffectsParams):
+        p.spread, p.intensity, p.sparkle_perspective = float(self.spread), float(self.intensity), int(bool(self.definePerspectiveCamera))
+
+
+class EffectPass:
+    """postprocessing's `new EffectPass(camera, ...effects)` for the four effects above: the effects of one pass are merged into one
+    fullscreen program — here ONE launch of rfx_effects_launch (csrc/k_fx.cu) — in which every effect samples the pass's input buffer
+    and the colour flows from one effect to the next in the given order."""
+
+    def __init__(self, camera, *effects):
+        if not 1 <= len(effects) <= 4:
+            raise ValueError("EffectPass: 1..4 effects")
+        self._camera, self.effects = camera, list(effects)
+
+    def render(self, renderer, inputBuffer, outputBuffer, deltaTime=None, stencilTest=None):
+        ctx: engine.Context = inputBuffer.ctx
+        p = abi.make_effects_params(self._camera.uniforms(), [e.fx_id for e in self.effects])
+        depth = velocity = None
+        for e in self.effects:
+            e.update(renderer, inputBuffer, deltaTime)
+            e._fill(p)
+            if isinstance(e, GradualBackgroundEffect):
+                depth = e.depthTexture
+            if isinstance(e, SparkleEffect):
+                velocity = e.velocityDepthNormalPass.texture
+        ctx.effects(p, inputBuffer, depth, velocity, outputBuffer)
+
+
+class TAAPass:
+    """new TAAPass(camera)  (src/taa/TAAPass.js:18-95): the still-camera accumulator that renders to the screen.  `canvas` (RGBA8) stands in
+    for the default framebuffer; the FramebufferTexture copy of it is the history.  `srgbOutput` = the renderer's output colour space."""
+
+    renderToScreen = True
+
+    def __init__(self, camera, srgbOutput=True):
+        self._camera, self.srgbOutput = camera, srgbOutput
+        self.cameraNotMovedFrames, self.frame, self.needsUpdate = 0, 0, False
+        self._last = None
+        self.canvas = self.framebufferTexture = None
+
+    def setSize(self, width, height, ctx: engine.Context):
+        self.dispose()
+        self.canvas = ctx.alloc(abi.FMT_RGBA8, width, height)
+        self.framebufferTexture = ctx.alloc(abi.FMT_RGBA8, width, height)
+        self.needsUpdate = True
+
+    def render(self, renderer, inputBuffer):
+        ctx: engine.Context = inputBuffer.ctx
+        self.frame = (self.frame + 1) % 4096
+        cam_u = self._camera.uniforms()
+        moved = self.needsUpdate or _did_camera_move(cam_u, self._last)
+        self.needsUpdate = False
+        n = self.cameraNotMovedFrames
+        if n > 0:  # :81-84
+            jitter(self.canvas.p.width, self.canvas.p.height, self._camera, self.frame, 1)
+        self.cameraNotMovedFrames = 0 if moved else (n + 1) % 4096
+        self._last = cam_u
+        p = abi.TaaParams()
+        p.camera_not_moved_frames, p.srgb_output = float(self.cameraNotMovedFrames), int(bool(self.srgbOutput))
+        ctx.taa(p, inputBuffer, self.framebufferTexture, self.canvas)
+        self.framebufferTexture, self.canvas = self.canvas, self.framebufferTexture  # copyFramebufferToTexture (:93): the canvas becomes the history
+        return self.framebufferTexture
+
+    def dispose(self):
+        for pl in (self.canvas, self.framebufferTexture):
+            if pl is not None:
+                pl.free()
+        self.canvas = self.framebufferTexture = None

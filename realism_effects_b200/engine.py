@@ -203,6 +203,13 @@ class Context:
     def traa_compose(self, acc, out, rows=(0, 0), stream=None):
         self._chk(self.lib.rfx_traa_compose_launch(self.h, stream, _r(acc), _r(out), rows[0], rows[1]))
 
+    def effects(self, p, inp, depth, velocity, out, rows=(0, 0), stream=None):
+        """merged cosmetic effects (abi.make_effects_params): Sharpness / LensDistortion / GradualBackground / Sparkle in one launch"""
+        self._chk(self.lib.rfx_effects_launch(self.h, stream, C.byref(p), _r(inp), _r(depth), _r(velocity), _r(out), rows[0], rows[1]))
+
+    def taa(self, p, inp, history, out, rows=(0, 0), stream=None):
+        self._chk(self.lib.rfx_taa_launch(self.h, stream, C.byref(p), _r(inp), _r(history), _r(out), rows[0], rows[1]))
+
     def gbuffer_ingest(self, albedo, normal, material, emissive, motion, depth, out_gbuffer, out_velocity, *, motion_scale=(1.0, 1.0),
                        normalize_normals=True, rows=(0, 0), stream=None):
         """conventional SoA planes -> the reference's packed gBuffer / velocity planes (rfx_gbuffer_ingest_launch)"""

@@ -400,3 +400,24 @@ def traa_two_frames(m, f0, f1):
     p1 = traa_temporal_params(abi.make_camera(f1["cam"]), f1["cam"]["position"], f0["cam"], 1.0)
     h1, _ = m.temporal_reproject(p1, f1["direct"], f1["velocity"], h0, None, h0, None, out_half=True)
     return h0, h1
+
+
+FX_CASES = [  # (effects in EffectPass order, sparkle_perspective)
+    ([abi.FX_SHARPNESS], False), ([abi.FX_LENS_DISTORTION], False), ([abi.FX_GRADUAL_BACKGROUND], False), ([abi.FX_SPARKLE], False), ([abi.FX_SPARKLE], True),
+    ([abi.FX_SHARPNESS, abi.FX_GRADUAL_BACKGROUND, abi.FX_SPARKLE], False), ([abi.FX_LENS_DISTORTION, abi.FX_SHARPNESS], False),
+]
+
+
+def fx_params(cam_u, effects, sparkle_perspective=False):
+    """non-default values where the default would saturate on the synthetic scene (GradualBackground's fade is 1 everywhere at maxDistance 5)"""
+    return abi.make_effects_params(cam_u, effects, sharpness=1.5, background_color=(0.2, 0.3, 0.5), max_distance=20.5, sparkle_perspective=sparkle_perspective)
+
+
+def taa_cases():
+    out = []
+    for n in (0.0, 1.0, 7.0):
+        for srgb in (0, 1):
+            p = abi.TaaParams()
+            p.camera_not_moved_frames, p.srgb_output = n, srgb
+            out.append(p)
+    return out

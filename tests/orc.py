@@ -199,6 +199,23 @@ def gbuffer_ingest(albedo, normal, material, emissive, motion, depth, *, motion_
     return gb, vel
 
 
+def effects(p: abi.EffectsParams, inp, depth, velocity):
+    """merged cosmetic effects (EffectPass semantics) -> RGBA16F"""
+    H, W = inp.shape[:2]
+    out = np.zeros((H, W, 4), np.uint16)
+    lib().orc_effects(C.byref(p), C.c_int(W), C.c_int(H), _p(f16bits(inp)), _p(None if depth is None else _c(depth, np.float32)),
+                      _p(None if velocity is None else _c(velocity, np.float32)), _p(out))
+    return out.view(np.float16)
+
+
+def taa(p: abi.TaaParams, inp, history):
+    """TAAPass -> RGBA8"""
+    H, W = inp.shape[:2]
+    out = np.zeros((H, W, 4), np.uint8)
+    lib().orc_taa(C.byref(p), C.c_int(W), C.c_int(H), _p(f16bits(inp)), _p(_c(history, np.uint8)), _p(out))
+    return out
+
+
 def traa_compose(acc):
     H, W = acc.shape[:2]
     out = np.zeros((H, W, 4), np.uint16)

@@ -182,6 +182,13 @@ STANDARD_VARIANTS = [
     ("ssgi_compose", dict(fog=False, fog_exp2=False, perspective=True)),
     ("ssgi_compose", dict(fog=True, fog_exp2=False, perspective=True)),
     ("ssgi_compose", dict(fog=True, fog_exp2=True, perspective=True)),
+    ("sharpness", {}),
+    ("lens_distortion", {}),
+    ("gradual_background", dict(perspective=True)),
+    ("sparkle", dict(perspective=False)),
+    ("sparkle", dict(perspective=True)),
+    ("taa", dict(srgb_output=True)),
+    ("taa", dict(srgb_output=False)),
 ]
 
 
@@ -371,3 +378,53 @@ def traa_compose(acc):
     s = Shader.get("traa_compose")
     s.tex("accumulatedTexture", acc, F_RGBA16F, linear=True)
     return s.run(W, H, [(F_RGBA16F, None)])[0]
+
+
+_FX = {abi.FX_SHARPNESS: "sharpness", abi.FX_LENS_DISTORTION: "lens_distortion", abi.FX_GRADUAL_BACKGROUND: "gradual_background", abi.FX_SPARKLE: "sparkle"}
+
+
+def effects(p: abi.EffectsParams, inp, depth, velocity):
+    """An EffectPass with p.effects in order: postprocessing merges their mainImage()s into one shader; here each effect's own shader runs in turn,
+    reading the SAME input buffer through `inputTexture` and the previous effect's colour through `inputBuffer` (which is what the merged shader's
+    colour chaining amounts to: every effect samples `inputBuffer` only at vUv).  Intermediate colours stay fp32 (registers in the merged shader)."""
+    H, W = inp.shape[:2]
+    cur = None  # the chained colour (fp32 plane); None = the pass input
+    for i in range(int(p.n_effects)):
+        e = int(p.effects[i])
+        kw = {}
+        if e == abi.FX_GRADUAL_BACKGROUND:
+            kw = dict(perspective=bool(p.cam.perspective))
+        if e == abi.FX_SPARKLE:
+            kw = dict(perspective=bool(p.sparkle_perspective))
+        s = Shader.get(_FX[e], **kw)
+        s.set(optional=("resolution", "texelSize", "cameraNear", "cameraFar"), resolution=[W, H], texelSize=[1.0 / W, 1.0 / H],
+              cameraNear=float(p.cam.near_plane), cameraFar=float(p.cam.far_plane))
+        if cur is None:
+            s.tex("inputBuffer", inp, F_RGBA16F, linear=True)
+        else:
+            s.tex("inputBuffer", cur, F_RGBA32F)
+        s.tex("inputTexture", inp, F_RGBA16F, linear=True, optional=True)
+        if e == abi.FX_SHARPNESS:
+            s.set(sharpness=float(p.sharpness))
+        elif e == abi.FX_LENS_DISTORTION:
+            s.set(alphax=float(p.alphax), alphay=float(p.alphay), aberration=float(p.aberration))
+        elif e == abi.FX_GRADUAL_BACKGROUND:
+            _cam(s, p.cam, ("projectionMatrix", "projectionMatrixInverse", "cameraMatrixWorld"))
+            s.set(backgroundColor=list(p.background_color), maxDistance=float(p.max_distance))
+            s.tex("depthTexture", depth, F_R32F)
+        elif e == abi.FX_SPARKLE:
+            _cam(s, p.cam)
+            s.set(optional=("backgroundColor",), spread=float(p.spread), intensity=float(p.intensity), backgroundColor=[0, 0, 0])
+            s.tex("velocityTexture", velocity, F_RGBA32F)
+        cur = s.run(W, H, [(F_RGBA32F, None)])[0]
+    return cur.astype(np.float16) if cur is not None else np.asarray(inp)
+
+
+def taa(p: abi.TaaParams, inp, history):
+    """TAAPass.render  src/taa/TAAPass.js:68-94 (renders to the screen; the FramebufferTexture copy is RGBA8)"""
+    H, W = inp.shape[:2]
+    s = Shader.get("taa", srgb_output=bool(p.srgb_output))
+    s.set(optional=("invTexSize",), cameraNotMovedFrames=float(p.camera_not_moved_frames))
+    s.tex("inputTexture", inp, F_RGBA16F, linear=True)
+    s.tex("acculumatedTexture", history, F_RGBA8)
+    return s.run(W, H, [(F_RGBA8, None)])[0]

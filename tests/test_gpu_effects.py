@@ -243,3 +243,80 @@ def test_gbuffer_ingest_is_bit_identical_to_the_oracle_and_feeds_the_chain(built
             ctx.gbuffer_ingest(planes[1], planes[1], planes[2], None, None, dd, og, ov)   # an RGBA32F albedo is rejected (BAD_FORMAT)
     finally:
         ctx.close()
+
+
+def test_cosmetic_effects_tail_kernel_and_taa(built):
+    """rfx_effects_launch (Sharpness / LensDistortion / GradualBackground / Sparkle merged like an EffectPass) and rfx_taa_launch against the
+    oracle (which equals the reference's shaders bit for bit, tests/test_reference_glsl.py); row-block launches are exact."""
+    import orc
+
+    W, H = 200, 120
+    inp = ch.make_inputs(W, H, 2)
+    f1 = inp.frames[1]
+    ctx = engine.Context(0, inp.blue)
+    try:
+        src, d, v = ctx.upload(f1["direct"]), ctx.upload(f1["depth"]), ctx.upload(f1["velocity"])
+        for effs, sp in ch.FX_CASES:
+            p = ch.fx_params(f1["cam"], effs, sp)
+            want = orc.effects(p, f1["direct"], f1["depth"], f1["velocity"])
+            out = ctx.alloc(abi.FMT_RGBA16F, W, H)
+            ctx.effects(p, src, d, v, out)
+            got = out.download()
+            c = ch.compare(want, got)
+            print(effs, sp, c)
+            assert c["frac_bad"] <= 1e-4, (effs, sp, c)
+            parts = ctx.alloc(abi.FMT_RGBA16F, W, H)
+            ctx.effects(p, src, d, v, parts, rows=(0, 41))
+            ctx.effects(p, src, d, v, parts, rows=(41, H))
+            assert parts.download().tobytes() == got.tobytes()
+        hist = np.random.default_rng(1).integers(0, 256, (H, W, 4), dtype=np.uint8)
+        hd = ctx.upload(hist)
+        for p in ch.taa_cases():
+            out = ctx.alloc(abi.FMT_RGBA8, W, H)
+            ctx.taa(p, src, hd, out)
+            want = orc.taa(p, f1["direct"], hist)
+            diff = np.abs(out.download().astype(np.int32) - want.astype(np.int32))
+            assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4, (p.camera_not_moved_frames, p.srgb_output, diff.max(), (diff > 0).mean())
+        with pytest.raises(abi.RfxError):
+            ctx.effects(ch.fx_params(f1["cam"], [abi.FX_SPARKLE]), src, d, None, ctx.alloc(abi.FMT_RGBA16F, W, H))  # Sparkle without the velocity plane
+    finally:
+        ctx.close()
+
+
+def test_effect_pass_and_taa_pass_host_classes(built):
+    """effects.EffectPass(camera, SharpnessEffect, GradualBackgroundEffect, SparkleEffect) = one merged launch; effects.TAAPass accumulates while the
+    camera stands still (cameraNotMovedFrames 0, 1, 2 ...) and restarts when it moves."""
+    import orc
+
+    W, H = 128, 72
+    inp = ch.make_inputs(W, H, 2)
+    f1 = inp.frames[1]
+    ctx = engine.Context(0, inp.blue)
+    try:
+        scene, comp, cam = Scene(ctx), Composer(ctx, W, H), Cam()
+        scene.load(f1)
+        cam.u = f1["cam"]
+        comp.inputBuffer.upload(f1["direct"])
+        vdn = effects.VelocityDepthNormalPass(scene, cam)
+        sharp, grad, spark = effects.SharpnessEffect({"sharpness": 1.5}), effects.GradualBackgroundEffect(cam, scene.depth, (0.2, 0.3, 0.5), 20.5), effects.SparkleEffect(cam, vdn)
+        assert effects.SharpnessEffect().sharpness == 1 and effects.LensDistortionEffect().alphax == -0.05 and spark.spread == 1
+        effects.EffectPass(cam, sharp, grad, spark).render(None, comp.inputBuffer, comp.outputBuffer)
+        want = orc.effects(ch.fx_params(f1["cam"], [abi.FX_SHARPNESS, abi.FX_GRADUAL_BACKGROUND, abi.FX_SPARKLE]), f1["direct"], f1["depth"], f1["velocity"])
+        assert ch.compare(want, comp.outputBuffer.download())["frac_bad"] <= 1e-4
+        taa = effects.TAAPass(cam)
+        taa.setSize(W, H, ctx)
+        hist = np.zeros((H, W, 4), np.uint8)
+        for n_expected in (0, 1, 2):
+            shown = taa.render(None, comp.inputBuffer).download()
+            assert taa.cameraNotMovedFrames == n_expected
+            p = abi.TaaParams()
+            p.camera_not_moved_frames, p.srgb_output = float(n_expected), 1
+            want = orc.taa(p, f1["direct"], hist)
+            assert np.abs(shown.astype(np.int32) - want.astype(np.int32)).max() <= 1
+            hist = shown
+        cam.u = inp.frames[0]["cam"]
+        taa.render(None, comp.inputBuffer)
+        assert taa.cameraNotMovedFrames == 0
+        taa.dispose()
+    finally:
+        ctx.close()

@@ -140,3 +140,21 @@ def test_oracle_equals_reference_shaders_effect_passes():
         fp = ch.fog_params(f1["cam"], exp2)
         assert bits(orc.ssgi_compose(f1["depth"], gi, f1["direct"], fp)) == bits(refglsl.ssgi_compose(f1["depth"], gi, f1["direct"], fp))
     assert bits(orc.ssgi_compose(f1["depth"], gi, f1["direct"])) == bits(refglsl.ssgi_compose(f1["depth"], gi, f1["direct"]))
+
+
+@needs_ref
+def test_oracle_equals_reference_shaders_cosmetic_effects_and_taa():
+    """SharpnessEffect / LensDistortionEffect / GradualBackgroundEffect / SparkleEffect alone and merged in EffectPass order, and TAAPass"""
+    inp = ch.make_inputs(96, 54, 2)
+    f1 = inp.frames[1]
+    for effs, sp in ch.FX_CASES:
+        p = ch.fx_params(f1["cam"], effs, sp)
+        a, b = orc.effects(p, f1["direct"], f1["depth"], f1["velocity"]), refglsl.effects(p, f1["direct"], f1["depth"], f1["velocity"])
+        assert bits(a) == bits(b), (effs, sp)
+        if effs != [abi.FX_SPARKLE] or sp:  # (with the reference's orthographic getViewZ branch the sparkle term underflows on this scene)
+            assert bits(a) != bits(f1["direct"])  # the effect does something
+    fade = orc.effects(ch.fx_params(f1["cam"], [abi.FX_GRADUAL_BACKGROUND]), f1["direct"], f1["depth"], f1["velocity"]).astype(np.float32)
+    assert len(np.unique(fade[..., 0])) > 50       # the blend towards the background colour is exercised, not saturated
+    hist = np.random.default_rng(1).integers(0, 256, (54, 96, 4), dtype=np.uint8)
+    for p in ch.taa_cases():
+        assert bits(orc.taa(p, f1["direct"], hist)) == bits(refglsl.taa(p, f1["direct"], hist))
