@@ -377,6 +377,16 @@ rfx_status rfx_traa_compose_launch(rfx_ctx* ctx, void* stream, const rfx_plane* 
  *      cross-frame state (prev matrices, keepData, history). ---------------------------- */
 typedef struct rfx_ssgi_chain rfx_ssgi_chain;
 
+/* option denoiseMode of the Denoiser (src/denoise/Denoiser.js:7):
+ *   "full"          K2 -> K3 x 2*iterations -> K4; history = the Poisson targets (default)
+ *   "full_temporal" K2 -> K4 on the temporal textures; no Poisson pass, so both accumulated textures are the one FramebufferTexture
+ *                   copy of the temporal target's first attachment (RGBA32F, LINEAR) — what preset "low" selects (SSGIEffect.js:82-86)
+ *   "temporal"      K2 only; output 0 and K1's accumulatedTexture are the temporal pass's first texture
+ *   ("denoised" binds an ARRAY of textures to K1's sampler in the reference and cannot run there: rejected with RFX_ERR_UNSUPPORTED) */
+#define RFX_DENOISE_FULL 0
+#define RFX_DENOISE_FULL_TEMPORAL 1
+#define RFX_DENOISE_TEMPORAL 2
+
 typedef struct rfx_ssgi_chain_options {
   uint32_t width, height;
   int32_t denoise_iterations;  /* option denoiseIterations (=> 2*iterations K3 passes) */
@@ -386,7 +396,7 @@ typedef struct rfx_ssgi_chain_options {
   uint32_t ssgi_flags;         /* RFX_SSGI_* */
   int32_t mode;                /* RFX_MODE_* */
   int32_t blue_noise_start;    /* startIndex of BlueNoiseUtils.js:19 (pinned)          */
-  int32_t _reserved;           /* (was use_cuda_graph: never implemented, removed)      */
+  int32_t denoise_mode;        /* RFX_DENOISE_*: option denoiseMode (Denoiser.js:7,45-78); constructor-time, like mode   */
 } rfx_ssgi_chain_options;
 
 typedef struct rfx_ssgi_frame {

@@ -117,7 +117,11 @@ export class SSGIEffect {
 	// new SSGIEffect(composer, scene, camera, options) — src/ssgi/SSGIEffect.js:31 (the code's signature, SURVEY.md D6)
 	constructor(composer, scene, camera, options = {}) {
 		this.composer = composer; this._scene = scene; this._camera = camera
-		const opts = { ...defaultSSGIOptions, ...options }
+		const opts = { denoiseMode: "full", ...defaultSSGIOptions, ...options }
+		if (typeof opts.preset === "string") {   // src/ssgi/SSGIEffect.js:79-99
+			if (opts.preset === "low") Object.assign(opts, { steps: 10, refineSteps: 2, denoiseMode: "full_temporal" })
+			else if (opts.preset === "medium") Object.assign(opts, { steps: 20, refineSteps: 4, denoiseMode: "full" })
+		}
 		this._options = opts
 		this.ctx = context(options.device ?? 0)
 		this.velocityDepthNormalPass = options.velocityDepthNormalPass
@@ -133,7 +137,11 @@ export class SSGIEffect {
 		return (o.importanceSampling && this._hasEnv ? FLAG.importanceSampling : 0) | (o.missedRays ? FLAG.missedRays : 0) |
 			(this.isUsingRenderPass ? FLAG.useDirectLight : 0) | (this._hasEnv ? FLAG.useEnvMap : 0)
 	}
-	_chainOptions() { return { ...this._options, width: this.width, height: this.height, flags: this._flags(), mode: this._options.mode === "ssr" ? 1 : 0 } }
+	_chainOptions() {
+		const denoiseModeId = ["full", "full_temporal", "temporal"].indexOf(this._options.denoiseMode ?? "full")   // Denoiser.js:7
+		if (denoiseModeId < 0) throw new Error(`denoiseMode "${this._options.denoiseMode}" cannot run (in the reference "denoised" binds an array of textures to a sampler)`)
+		return { ...this._options, width: this.width, height: this.height, flags: this._flags(), mode: this._options.mode === "ssr" ? 1 : 0, denoiseModeId }
+	}
 	_setOptions() { if (this.chain) rfx.chainSetOptions(this.ctx, this.chain, this._chainOptions()) }   // setters end with reset() (SSGIEffect.js:203-209)
 	setSize(width, height, force = false) {
 		if (width === undefined || (!force && width === this.width && height === this.height)) return

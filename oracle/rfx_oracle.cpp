@@ -1196,16 +1196,17 @@ void orc_ssgi_trace(const rfx_ssgi_params* p, int W, int H, const float* depth, 
 
 // K2.  input RGBA32F (diffuseSpecular / specular) or RGBA16F (diffuse); history RGBA16F; out fp32 (out_half=0) or fp16 (out_half=1).
 // Discarded pixels are left untouched in out0/out1.
+// history_float: the history planes are RGBA32F (denoiseMode "full_temporal" / "temporal": the FramebufferTexture copy of the FloatType target)
 void orc_temporal_reproject(const rfx_temporal_params* p, int W, int H, const void* input, int input_half, const float* velocity,
-                            const uint16_t* history0, const uint16_t* history1, void* out0, void* out1, int out_half) {
+                            const void* history0, const void* history1, void* out0, void* out1, int out_half, int history_float) {
 #pragma omp parallel
   {
     TemporalShader s(*p);
     s.W = W; s.H = H;
     s.inputTexture = mk(input, W, H, input_half ? F_RGBA16F : F_RGBA32F, input_half != 0);
     s.velocityTexture = mk(velocity, W, H, F_RGBA32F);
-    s.accumulatedTexture[0] = mk(history0, W, H, F_RGBA16F, p->history_linear != 0);
-    s.accumulatedTexture[1] = mk(history1, W, H, F_RGBA16F, p->history_linear != 0);
+    s.accumulatedTexture[0] = mk(history0, W, H, history_float ? F_RGBA32F : F_RGBA16F, p->history_linear != 0);
+    s.accumulatedTexture[1] = mk(history1, W, H, history_float ? F_RGBA32F : F_RGBA16F, p->history_linear != 0);
     s.invTexSize = vec2((float)(1.0 / W), (float)(1.0 / H));  // TemporalReprojectPass.js:135 (JS doubles -> float32 uniform)
     void* outs[2] = {out0, out1};
 #pragma omp for schedule(dynamic, 4)
@@ -1250,14 +1251,15 @@ void orc_poisson_denoise(const rfx_poisson_params* p, int W, int H, const float*
 // K4.  diffuse/specular RGBA16F (nearest fetch at pixel centre; filter irrelevant), out RGBA32F; discarded pixels untouched.
 // diffuse_gi / specular_gi / scene may be NULL (null sampler => (0,0,0,1)): DenoiserComposePass.js:23-33 binds only the textures of its
 // inputType; `scene` is the composer input buffer (Denoiser.js:100-102, LINEAR RGBA16F), read by TYPE_SPECULAR only
-void orc_gi_compose(const rfx_compose_params* p, int W, int H, const float* depth, const float* gbuffer, const uint16_t* diffuse_gi,
-                    const uint16_t* specular_gi, const uint16_t* scene, float* out) {
+// gi_float: diffuse_gi / specular_gi are RGBA32F NEAREST (denoiseMode "full_temporal": the temporal pass's FloatType targets)
+void orc_gi_compose(const rfx_compose_params* p, int W, int H, const float* depth, const float* gbuffer, const void* diffuse_gi,
+                    const void* specular_gi, const uint16_t* scene, float* out, int gi_float) {
   ComposeShader s(*p);
   s.W = W; s.H = H;
   s.depthTexture = mk(depth, W, H, F_R32F);
   s.gBufferTexture = mk(gbuffer, W, H, F_RGBA32F);
-  s.diffuseGiTexture = mk(diffuse_gi, W, H, F_RGBA16F, true);
-  s.specularGiTexture = mk(specular_gi, W, H, F_RGBA16F, true);
+  s.diffuseGiTexture = mk(diffuse_gi, W, H, gi_float ? F_RGBA32F : F_RGBA16F, !gi_float);
+  s.specularGiTexture = mk(specular_gi, W, H, gi_float ? F_RGBA32F : F_RGBA16F, !gi_float);
   s.sceneTexture = mk(scene, W, H, F_RGBA16F, true);
 #pragma omp parallel for schedule(dynamic, 4)
   for (int y = 0; y < H; y++)

@@ -21,6 +21,8 @@ MODE_SSGI, MODE_SSR = 0, 1
 GROUP_ID_BYTES = 128
 ERR_NCCL = 7
 INPUT_DIFFUSE_SPECULAR, INPUT_DIFFUSE, INPUT_SPECULAR = 0, 1, 2
+DENOISE_FULL, DENOISE_FULL_TEMPORAL, DENOISE_TEMPORAL = 0, 1, 2  # option denoiseMode (src/denoise/Denoiser.js:7)
+DENOISE_MODES = {"full": 0, "full_temporal": 1, "temporal": 2}
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3
@@ -126,7 +128,7 @@ class ChainOptions(C.Structure):
                 ("refine_steps", C.c_int32), ("distance", C.c_float), ("thickness", C.c_float), ("env_blur", C.c_float),
                 ("radius", C.c_float), ("phi", C.c_float), ("luma_phi", C.c_float), ("depth_phi", C.c_float), ("normal_phi", C.c_float),
                 ("roughness_phi", C.c_float), ("specular_phi", C.c_float), ("ssgi_flags", C.c_uint32), ("mode", C.c_int32),
-                ("blue_noise_start", C.c_int32), ("_reserved", C.c_int32)]
+                ("blue_noise_start", C.c_int32), ("denoise_mode", C.c_int32)]
 
 
 class SsgiFrame(C.Structure):

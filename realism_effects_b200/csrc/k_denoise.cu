@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(kThreads) gi_compose_kernel(const __grid_const
   // (the literal weights are (1,0,0,0) up to one ulp of u*W, i.e. the two differ by <= 1.2e-4 x the neighbour contrast)
   // a texture the inputType does not bind is a null sampler: (0,0,0,1)  (DenoiserComposePass.js:23-33)
   const v4 nul = mk4(0.0f, 0.0f, 0.0f, 1.0f);
-  const v4 dgi = !a.diffuse.p ? nul : (a.fast ? ld_h4(a.diffuse, x, y) : tex_h4_linear(a.diffuse, vUv));
-  const v4 sgi = !a.specular.p ? nul : (a.fast ? ld_h4(a.specular, x, y) : tex_h4_linear(a.specular, vUv));
+  const v4 dgi = !a.diffuse.p ? nul : (a.gi_f32 ? f4v(ld_f4(a.diffuse, x, y)) : (a.fast ? ld_h4(a.diffuse, x, y) : tex_h4_linear(a.diffuse, vUv)));
+  const v4 sgi = !a.specular.p ? nul : (a.gi_f32 ? f4v(ld_f4(a.specular, x, y)) : (a.fast ? ld_h4(a.specular, x, y) : tex_h4_linear(a.specular, vUv)));
 
   // constructGlobalIllumination :53-107
   const float roughness = rough0 * rough0;

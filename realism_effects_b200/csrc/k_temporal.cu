@@ -85,7 +85,10 @@ RFX_D v2 reprojectHitPoint(const TemporalArgs& a, const TState& s) {
 }
 
 template <bool HLIN>
-RFX_D v4 fetch_hist(const PV& t, v2 uv) { return HLIN ? tex_h4_linear(t, uv) : tex_h4_nearest(t, uv); }
+RFX_D v4 fetch_hist(const TemporalArgs& a, const PV& t, v2 uv) {
+  if (a.hist_f32) return HLIN ? tex_f4_linear(t, uv) : f4v(tex_f4_nearest(t, uv));  // block-uniform: the FloatType FramebufferTexture history
+  return HLIN ? tex_h4_linear(t, uv) : tex_h4_nearest(t, uv);
+}
 
 // BiCubicCatmullRom5Tap  reproject.frag:212-255
 template <bool HLIN>
@@ -103,8 +106,8 @@ RFX_D v4 catmull5(const TemporalArgs& a, const PV& tex, v2 P) {
   const v2 W0 = w0, W1 = w1 + w2, W2 = w3;
   const v2 S0 = (tc - mk2(1.0f, 1.0f)) * inv, S1 = (tc + w2 / W1) * inv, S2 = (tc + mk2(2.0f, 2.0f)) * inv;
   const float sw0 = W1.x * W0.y, sw1 = W0.x * W1.y, sw2 = W1.x * W1.y, sw3 = W2.x * W1.y, sw4 = W1.x * W2.y;
-  const v4 Ct = fetch_hist<HLIN>(tex, mk2(S1.x, S0.y)), Cl = fetch_hist<HLIN>(tex, mk2(S0.x, S1.y)), Cc = fetch_hist<HLIN>(tex, mk2(S1.x, S1.y)),
-           Cr = fetch_hist<HLIN>(tex, mk2(S2.x, S1.y)), Cb = fetch_hist<HLIN>(tex, mk2(S1.x, S2.y));
+  const v4 Ct = fetch_hist<HLIN>(a, tex, mk2(S1.x, S0.y)), Cl = fetch_hist<HLIN>(a, tex, mk2(S0.x, S1.y)), Cc = fetch_hist<HLIN>(a, tex, mk2(S1.x, S1.y)),
+           Cr = fetch_hist<HLIN>(a, tex, mk2(S2.x, S1.y)), Cb = fetch_hist<HLIN>(a, tex, mk2(S1.x, S2.y));
   const float wm = 1.0f / (sw0 + sw1 + sw2 + sw3 + sw4);
   v4 r;
   r.x = fmaxf(((((Ct.x * sw0 + Cl.x * sw1) + Cc.x * sw2) + Cr.x * sw3) + Cb.x * sw4) * wm, 0.0f);

@@ -509,11 +509,13 @@ rfx_status rfx_temporal_reproject_launch(rfx_ctx* ctx, void* stream, const rfx_t
   if (!pv(input, a.input_half ? RFX_FMT_RGBA16F : RFX_FMT_RGBA32F, a.input)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: input must be RGBA32F or RGBA16F");
   if (p->input_type != RFX_INPUT_DIFFUSE && a.input_half) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: packed inputs must be RGBA32F");
   if (!pv(velocity, RFX_FMT_RGBA32F, a.velocity)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: velocity must be RGBA32F");
-  if (!pv(history0, RFX_FMT_RGBA16F, a.hist0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: history must be RGBA16F");
+  a.hist_f32 = history0 && history0->format == RFX_FMT_RGBA32F;  // the FloatType FramebufferTexture history of denoiseMode "full_temporal" / "temporal"
+  const int hfmt = a.hist_f32 ? RFX_FMT_RGBA32F : RFX_FMT_RGBA16F;
+  if (!pv(history0, hfmt, a.hist0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: history must be RGBA16F or RGBA32F");
   a.out_half = out0->format == RFX_FMT_RGBA16F;
   if (!ov(out0, a.out_half ? RFX_FMT_RGBA16F : RFX_FMT_RGBA32F, a.out0)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: out must be RGBA32F or RGBA16F");
   if (p->texture_count == 2) {
-    if (!pv(history1, RFX_FMT_RGBA16F, a.hist1) || !ov(out1, out0->format, a.out1)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: second plane missing / wrong format");
+    if (!pv(history1, hfmt, a.hist1) || !ov(out1, out0->format, a.out1)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: second plane missing / wrong format");
   }
   a.W = (int)out0->width; a.H = (int)out0->height;
   if (a.input.w != a.W || a.input.h != a.H || a.velocity.w != a.W || a.velocity.h != a.H || a.hist0.w != a.W || a.hist0.h != a.H)
@@ -606,8 +608,11 @@ rfx_status rfx_gi_compose_launch(rfx_ctx* ctx, void* stream, const rfx_compose_p
     return fail(ctx, RFX_ERR_INVALID_ARG, "gi_compose: bad input_type");
   // DenoiserComposePass.js:23-33: diffuseSpecular binds both GI textures, diffuse only the first, specular only the second
   const bool need_d = p->input_type != RFX_INPUT_SPECULAR, need_s = p->input_type != RFX_INPUT_DIFFUSE;
-  if (need_d && !pv(dgi, RFX_FMT_RGBA16F, a.diffuse)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: diffuse GI must be RGBA16F");
-  if (need_s && !pv(sgi, RFX_FMT_RGBA16F, a.specular)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: specular GI must be RGBA16F");
+  const rfx_plane* first = need_d ? dgi : sgi;
+  a.gi_f32 = first && first->format == RFX_FMT_RGBA32F;  // denoiseMode "full_temporal": the temporal pass's FloatType NEAREST targets
+  const int gfmt = a.gi_f32 ? RFX_FMT_RGBA32F : RFX_FMT_RGBA16F;
+  if (need_d && !pv(dgi, gfmt, a.diffuse)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: diffuse GI must be RGBA16F (or both RGBA32F)");
+  if (need_s && !pv(sgi, gfmt, a.specular)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: specular GI must be RGBA16F (or both RGBA32F)");
   if (p->input_type == RFX_INPUT_SPECULAR && scene && !pv(scene, RFX_FMT_RGBA16F, a.scene)) return fail(ctx, RFX_ERR_BAD_FORMAT, "gi_compose: scene must be RGBA16F");
   a.W = (int)out->width; a.H = (int)out->height;
   if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.gb.h != a.H || (a.diffuse.p && (a.diffuse.w != a.W || a.diffuse.h != a.H)) ||
@@ -789,6 +794,7 @@ struct rfx_ssgi_chain {
   rfx_ctx* ctx;
   rfx_ssgi_chain_options opt;
   rfx_plane ssgi_out{}, tr[2]{}, dnA[2]{}, dnB[2]{}, composed{};
+  rfx_plane fb{};  // denoise_mode != full: the FramebufferTexture copy of the temporal target's attachment 0 (TemporalReprojectPass.js:134-152,197-200)
   // fast chain (fast_math on at creation, mode SSGI): interleaved internal planes; history planes are double-buffered by frame
   // parity so that, in a row-sharded group, no rank overwrites rows a peer may still be reading (see rfx_group_*)
   bool fastpath = false;
@@ -853,8 +859,13 @@ rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt
     if (cudaMalloc(&p->p, p->pitch * opt->height) != cudaSuccess || cudaMemset(p->p, 0, p->pitch * opt->height) != cudaSuccess) st = fail(ctx, RFX_ERR_CUDA, "chain_create: cudaMalloc failed");
   };
   CU(cudaSetDevice(ctx->device));
-  ch->fastpath = ctx->fast_math && opt->mode == RFX_MODE_SSGI;  // latched: the history formats differ between the two paths
+  if (opt->denoise_mode < RFX_DENOISE_FULL || opt->denoise_mode > RFX_DENOISE_TEMPORAL) {
+    delete ch;
+    return fail(ctx, RFX_ERR_UNSUPPORTED, "chain_create: denoise_mode must be full / full_temporal / temporal (\"denoised\" hands an array of textures to a sampler in the reference and cannot run there either)");
+  }
+  ch->fastpath = ctx->fast_math && opt->mode == RFX_MODE_SSGI && opt->denoise_mode == RFX_DENOISE_FULL;  // latched: the history formats differ between the paths
   alloc(RFX_FMT_RGBA32F, &ch->ssgi_out);
+  if (opt->denoise_mode != RFX_DENOISE_FULL) alloc(RFX_FMT_RGBA32F, &ch->fb);
   if (ch->fastpath) {
     ialloc(16, &ch->nrdz); ialloc(32, &ch->tr32); ialloc(16, &ch->dnA16); ialloc(16, &ch->dnB16[0]); ialloc(16, &ch->dnB16[1]);
     alloc(RFX_FMT_RGBA32F, &ch->composed2[0]); alloc(RFX_FMT_RGBA32F, &ch->composed2[1]);
@@ -873,7 +884,7 @@ void rfx_ssgi_chain_destroy(rfx_ssgi_chain* ch) {
   cudaStreamSynchronize(ctx->stream);
   if (ch->s_up) cudaStreamSynchronize(ch->s_up);
   if (ch->s_dn) cudaStreamSynchronize(ch->s_dn);
-  rfx_plane* all[] = {&ch->ssgi_out, &ch->tr[0], &ch->tr[1], &ch->dnA[0], &ch->dnA[1], &ch->dnB[0], &ch->dnB[1], &ch->composed,
+  rfx_plane* all[] = {&ch->fb, &ch->ssgi_out, &ch->tr[0], &ch->tr[1], &ch->dnA[0], &ch->dnA[1], &ch->dnB[0], &ch->dnB[1], &ch->composed,
                       &ch->in_depth[0], &ch->in_gb[0], &ch->in_vel[0], &ch->in_direct[0], &ch->in_depth[1], &ch->in_gb[1], &ch->in_vel[1], &ch->in_direct[1]};
   for (rfx_plane* p : all) if (p->ptr) rfx_plane_free(ctx, p);
   for (rfx_plane* p : {&ch->composed2[0], &ch->composed2[1]}) if (p->ptr) rfx_plane_free(ctx, p);
@@ -911,6 +922,7 @@ rfx_status rfx_ssgi_chain_set_options(rfx_ssgi_chain* ch, const rfx_ssgi_chain_o
   if (!ch || !opt) return RFX_ERR_INVALID_ARG;
   if (opt->width != ch->opt.width || opt->height != ch->opt.height) return fail(ch->ctx, RFX_ERR_SIZE_MISMATCH, "chain_set_options: size change needs a new chain");
   if (opt->denoise_iterations < 0 || opt->steps < 1 || opt->refine_steps < 0) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_set_options: bad option value");
+  if (opt->denoise_mode != ch->opt.denoise_mode || opt->mode != ch->opt.mode) return fail(ch->ctx, RFX_ERR_UNSUPPORTED, "chain_set_options: mode / denoise_mode are constructor options (Denoiser.js:17-64): create a new chain");
   const int32_t start = ch->opt.blue_noise_start;
   ch->opt = *opt;
   ch->opt.blue_noise_start = start;  // the blue-noise closures keep their start index for the life of the material
@@ -953,7 +965,7 @@ rfx_status rfx_ssgi_chain_output(rfx_ssgi_chain* ch, int32_t which, rfx_plane* o
     return RFX_OK;
   }
   switch (which) {
-    case 0: *out = ch->composed; break;
+    case 0: *out = ch->opt.denoise_mode == RFX_DENOISE_TEMPORAL ? ch->tr[0] : ch->composed; break;  // denoiser.texture (Denoiser.js:67-78)
     case 1: *out = ch->ssgi_out; break;
     case 2: *out = ch->tr[0]; break;
     case 3: *out = ch->tr[1]; break;
@@ -1176,8 +1188,12 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
   rfx_ctx* ctx = ch->ctx;
   const rfx_ssgi_chain_options& o = ch->opt;
   rfx_status st = RFX_OK;
+  const bool dm_full = o.denoise_mode == RFX_DENOISE_FULL;
+  if (!dm_full && ranges) return fail(ctx, RFX_ERR_UNSUPPORTED, "chain: row-range rendering is implemented for denoise_mode full only");
   const uint32_t n_launches = 3u + 2u * (uint32_t)o.denoise_iterations;  // K1, K2, K3 passes, K4 (both modes: DenoiserComposePass runs for inputType specular too)
   if (!ranges) n_blocks = 1;
+  // what SSGIPass samples as accumulatedTexture = denoiser.texture (Denoiser.js:67-78): the compose target, or the temporal pass's first texture
+  rfx_plane* accumulated = o.denoise_mode == RFX_DENOISE_TEMPORAL ? &ch->tr[0] : &ch->composed;
   auto R0 = [&](uint32_t blk, uint32_t k) -> uint32_t { return ranges ? ranges[(blk * n_launches + k) * 2] : 0u; };
   auto R1 = [&](uint32_t blk, uint32_t k) -> uint32_t { return ranges ? ranges[(blk * n_launches + k) * 2 + 1] : 0u; };
   auto on = [&](uint32_t k) { return k >= k_begin && k < k_end; };
@@ -1197,7 +1213,7 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
       ctx->viewz_reuse = blk > 0;  // the view-z plane depends on the depth plane only: one prepass per frame
       ctx->k1_phase = k1_phase;
       SpanGuard g(ch, cs, 0);
-      st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, &ch->composed, &ch->ssgi_out, R0(blk, k), R1(blk, k));
+      st = rfx_ssgi_trace_launch(ctx, stream, &sp, f->depth, f->gbuffer, nullptr, f->direct_light, accumulated, &ch->ssgi_out, R0(blk, k), R1(blk, k));
     }
     ctx->viewz_reuse = false;
     ctx->k1_phase = 0;
@@ -1226,10 +1242,15 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
       SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       SpanGuard g(ch, cs, 1);
-      st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, &ch->dnB[0], tc == 2 ? &ch->dnB[1] : nullptr, &ch->tr[0],
+      // without a denoise pass overrideAccumulatedTextures stays empty: BOTH accumulated textures are the one FramebufferTexture
+      rfx_plane* h0 = dm_full ? &ch->dnB[0] : &ch->fb;
+      rfx_plane* h1 = dm_full ? &ch->dnB[1] : &ch->fb;
+      st = rfx_temporal_reproject_launch(ctx, stream, &tp, &ch->ssgi_out, f->velocity, h0, tc == 2 ? h1 : nullptr, &ch->tr[0],
                                          tc == 2 ? &ch->tr[1] : nullptr, R0(blk, k), R1(blk, k));
     }
     if (st != RFX_OK) return st;
+    if (!dm_full)  // renderer.copyFramebufferToTexture(tmpVec2, this.framebufferTexture) after the draw (:197-200)
+      CU(cudaMemcpy2DAsync(ch->fb.ptr, ch->fb.pitch, ch->tr[0].ptr, ch->tr[0].pitch, (size_t)ch->tr[0].width * 16, ch->tr[0].height, cudaMemcpyDeviceToDevice, cs));
     ch->keep_data = 1.0f;  // :195
     memcpy(ch->prev_world, f->cam.camera_matrix_world, 64); memcpy(ch->prev_view, f->cam.view_matrix, 64);
     memcpy(ch->prev_proj, f->cam.projection, 64); memcpy(ch->prev_proj_inv, f->cam.projection_inverse, 64);
@@ -1244,7 +1265,7 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
   if (o.mode == RFX_MODE_SSGI) { pp.is_texture_specular[0] = 0; pp.is_texture_specular[1] = 1; } else { pp.is_texture_specular[0] = 1; pp.is_texture_specular[1] = 1; }
   bool decoded = false;
   for (int i = 0; i < 2 * o.denoise_iterations; i++, k++) {
-    if (!on(k)) continue;
+    if (!on(k) || !dm_full) continue;  // "full_temporal" / "temporal": no denoise pass (Denoiser.js:47-52)
     const bool horizontal = (i % 2) == 0;
     rfx_plane* inp = i == 0 ? ch->tr : (horizontal ? ch->dnB : ch->dnA);
     rfx_plane* outp = horizontal ? ch->dnA : ch->dnB;
@@ -1261,16 +1282,17 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
     ctx->nrd_reuse = false;
     if (st != RFX_OK) return st;
   }
-  // ---- K4  DenoiserComposePass.render
-  if (on(k)) {
+  // ---- K4  DenoiserComposePass.render ("full" and "full_temporal": Denoiser.js:55-64)
+  rfx_plane* gi = dm_full ? ch->dnB : ch->tr;  // composerInputTextures = denoisePass?.texture ?? the temporal textures
+  if (on(k) && o.denoise_mode != RFX_DENOISE_TEMPORAL) {
     rfx_compose_params cp{};
     cp.cam = f->cam;
     cp.input_type = o.mode == RFX_MODE_SSGI ? RFX_INPUT_DIFFUSE_SPECULAR : RFX_INPUT_SPECULAR;  // SSGIEffect.js:70-77
     for (uint32_t blk = 0; blk < 1; blk++) {  // ONE launch covers every owned row block (SegScope installs the segment table)
       SegScope seg_scope(ctx, ranges, n_blocks, n_launches, k);
       SpanGuard g(ch, cs, 4);
-      if (o.mode == RFX_MODE_SSGI) st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &ch->dnB[0], &ch->dnB[1], nullptr, &ch->composed, R0(blk, k), R1(blk, k));
-      else st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, nullptr, &ch->dnB[0], f->direct_light, &ch->composed, R0(blk, k), R1(blk, k));  // scene = the composer input buffer (Denoiser.js:100-102)
+      if (o.mode == RFX_MODE_SSGI) st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, &gi[0], &gi[1], nullptr, &ch->composed, R0(blk, k), R1(blk, k));
+      else st = rfx_gi_compose_launch(ctx, stream, &cp, f->depth, f->gbuffer, nullptr, &gi[0], f->direct_light, &ch->composed, R0(blk, k), R1(blk, k));  // scene = the composer input buffer (Denoiser.js:100-102)
     }
     if (st != RFX_OK) return st;
   }

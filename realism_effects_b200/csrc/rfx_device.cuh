@@ -213,6 +213,10 @@ RFX_D v4 tex_h4_linear(const PV& t, v2 uv) {
   Bilin b = bilin_setup(uv, t.w, t.h);
   return bilin_blend4(b, ld_h4(t, b.x0, b.y0), ld_h4(t, b.x1, b.y0), ld_h4(t, b.x0, b.y1), ld_h4(t, b.x1, b.y1));
 }
+RFX_D v4 tex_f4_linear(const PV& t, v2 uv) {  // LINEAR fetch of an RGBA32F plane (the FramebufferTexture history of denoiseMode "full_temporal")
+  Bilin b = bilin_setup(uv, t.w, t.h);
+  return bilin_blend4(b, f4v(ld_f4(t, b.x0, b.y0)), f4v(ld_f4(t, b.x1, b.y0)), f4v(ld_f4(t, b.x0, b.y1)), f4v(ld_f4(t, b.x1, b.y1)));
+}
 RFX_D v4 tex_h4_nearest(const PV& t, v2 uv) { return ld_h4(t, nearest_i(uv.x, t.w), nearest_i(uv.y, t.h)); }
 
 // ---- blue noise (reference src/utils/shader/blue_noise.glsl:9-48) ---------------------------

@@ -90,6 +90,7 @@ struct ComposeArgs {
   RowSegs segs;
   CamD cam;
   int input_type;
+  int gi_f32;  // diffuse / specular are RGBA32F NEAREST (denoiseMode "full_temporal": the temporal pass's targets)
   int fast;
 };
 cudaError_t launch_gi_compose(const ComposeArgs& a, cudaStream_t s);
@@ -117,6 +118,7 @@ struct TemporalArgs {
   float inv_w, inv_h;  // invTexSize
   int full_accumulate, texture_count, input_type, log_transform, rs0, rs1, history_linear;
   int input_half, out_half;
+  int hist_f32;  // history planes are RGBA32F (denoiseMode "full_temporal" / "temporal")
   int fast;  // SFU variants of log/exp/pow
 };
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t s);

@@ -139,6 +139,16 @@ class SSGIEffect(_Reactive):
             opts.update(reprojectSpecular=True, neighborhoodClamp=True, inputType="specular")
         else:
             opts.update(reprojectSpecular=[False, True], neighborhoodClamp=[False, True])
+        opts.setdefault("denoiseMode", "full")  # Denoiser.js:6-11 (spread into the Denoiser through ...options, SSGIEffect.js:104-108)
+        preset = opts.get("preset")
+        if isinstance(preset, str):  # src/ssgi/SSGIEffect.js:79-99 (the third case is a second, unreachable "medium" in the reference)
+            if preset == "low":
+                opts.update(steps=10, refineSteps=2, denoiseMode="full_temporal")
+            elif preset == "medium":
+                opts.update(steps=20, refineSteps=4, denoiseMode="full")
+        if opts["denoiseMode"] not in abi.DENOISE_MODES:
+            raise abi.RfxError(f"denoiseMode {opts['denoiseMode']!r}: 'denoised' binds an array of textures to a sampler in the reference and cannot run there; "
+                               f"supported: {sorted(abi.DENOISE_MODES)}")
         self.composer, self._scene, self._camera = composer, scene, camera
         self.ctx: engine.Context = composer.ctx
         self.velocityDepthNormalPass = opts.get("velocityDepthNormalPass") or VelocityDepthNormalPass(scene, camera)
@@ -167,6 +177,7 @@ class SSGIEffect(_Reactive):
         c.ssgi_flags = flags
         c.mode = abi.MODE_SSR if o["mode"] == "ssr" else abi.MODE_SSGI
         c.blue_noise_start = self._blue_start
+        c.denoise_mode = abi.DENOISE_MODES[o["denoiseMode"]]
         return c
 
     def setSize(self, width, height, force=False):

@@ -49,6 +49,7 @@ class Opts:
     use_envmap: bool = True
     mode: int = abi.MODE_SSGI
     blue_noise_start: int = 1234567
+    denoise_mode: int = 0  # Denoiser.js:7: 0 "full", 1 "full_temporal" (no Poisson pass), 2 "temporal" (no Poisson pass, no compose)
 
     @property
     def flags(self) -> int:
@@ -153,6 +154,7 @@ def chain_options(inp: Inputs, o: Opts) -> abi.ChainOptions:
     c.radius, c.phi, c.luma_phi, c.depth_phi, c.normal_phi = o.radius, o.phi, o.luma_phi, o.depth_phi, o.normal_phi
     c.roughness_phi, c.specular_phi = o.roughness_phi, o.specular_phi
     c.ssgi_flags, c.mode, c.blue_noise_start = o.flags, o.mode, o.blue_noise_start
+    c.denoise_mode = o.denoise_mode
     return c
 
 
@@ -174,6 +176,7 @@ def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0",
     tr = [z32(), z32()]
     dnA, dnB = [z16(), z16()], [z16(), z16()]
     composed = z32()
+    fb = z32()  # denoiseMode != "full": the FramebufferTexture copy of the temporal target's attachment 0 (TemporalReprojectPass.js:134-152,197-200)
     keep_data, prev = 0.0, None
     bn_trace = bn_poisson = 0
     out = []
@@ -191,9 +194,25 @@ def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0",
             prev = fr["cam"]
         tp = temporal_params(o, cam, fr["cam"]["position"], prev, keep_data, fr["moved"])
         rec["_k2_params"], rec["_k2_hist"], rec["_k2_prev_out"] = tp, [dnB[0].copy(), dnB[1].copy()], [tr[0].copy(), tr[1].copy()]
-        tr0, tr1 = orc.temporal_reproject(tp, ssgi, fr["velocity"], dnB[0], dnB[1], tr[0], tr[1])
+        if o.denoise_mode == 0:
+            tr0, tr1 = orc.temporal_reproject(tp, ssgi, fr["velocity"], dnB[0], dnB[1], tr[0], tr[1])
+        else:  # no denoise pass => overrideAccumulatedTextures is empty: BOTH accumulated textures are the one FramebufferTexture
+            tr0, tr1 = orc.temporal_reproject(tp, ssgi, fr["velocity"], fb, fb, tr[0], tr[1])
+            fb = tr0.copy()  # copyFramebufferToTexture after the draw (:197-200)
         tr = [tr0, tr1]
         keep_data, prev = 1.0, fr["cam"]
+        if o.denoise_mode != 0:
+            cp = compose_params(cam, o.mode)
+            if o.denoise_mode == 1:  # "full_temporal": DenoiserComposePass on the temporal textures (Denoiser.js:55-64)
+                if o.mode == abi.MODE_SSGI:
+                    composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], tr[0], tr[1], composed)
+                else:
+                    composed = orc.gi_compose(cp, fr["depth"], fr["gbuffer"], None, tr[0], composed, scene=fr["direct"])
+            else:  # "temporal": denoiser.texture is the temporal pass's first texture (Denoiser.js:73-74); it is what K1 samples next frame
+                composed = tr[0].copy()
+            full = dict(ssgi=ssgi, tr0=tr[0], tr1=tr[1], dn0=dnB[0], dn1=dnB[1], composed=composed)
+            out.append({k: full[k].copy() for k in capture})
+            continue
         # K3
         rec["_k3"] = []
         for i in range(2 * o.denoise_iterations):

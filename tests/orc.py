@@ -117,9 +117,13 @@ def temporal_reproject(p: abi.TemporalParams, inp, velocity, hist0, hist1, out0_
     inp_c = f16bits(inp) if input_half else _c(inp, np.float32)
     o0 = np.array(f16bits(out0_prev) if out_half else out0_prev, copy=True)
     o1 = None if out1_prev is None else np.array(f16bits(out1_prev) if out_half else out1_prev, copy=True)
-    h0, h1 = f16bits(hist0), f16bits(hist1) if hist1 is not None else None
+    hist_float = hist0.dtype == np.float32  # denoiseMode "full_temporal" / "temporal": RGBA32F history
+    if hist_float:
+        h0, h1 = _c(hist0, np.float32), _c(hist1, np.float32) if hist1 is not None else None
+    else:
+        h0, h1 = f16bits(hist0), f16bits(hist1) if hist1 is not None else None
     lib().orc_temporal_reproject(C.byref(p), C.c_int(W), C.c_int(H), _p(inp_c), C.c_int(int(input_half)), _p(_c(velocity, np.float32)),
-                                 _p(h0), _p(h1), _p(o0), _p(o1), C.c_int(int(out_half)))
+                                 _p(h0), _p(h1), _p(o0), _p(o1), C.c_int(int(out_half)), C.c_int(int(hist_float)))
     if out_half:
         o0 = o0.view(np.float16)
         o1 = None if o1 is None else o1.view(np.float16)
@@ -143,8 +147,10 @@ def gi_compose(p: abi.ComposeParams, depth, gbuffer, diffuse_gi, specular_gi, ou
     """diffuse_gi / specular_gi / scene may be None (null sampler)"""
     H, W = depth.shape
     out = np.array(out_prev, np.float32, copy=True)
-    lib().orc_gi_compose(C.byref(p), C.c_int(W), C.c_int(H), _p(_c(depth, np.float32)), _p(_c(gbuffer, np.float32)), _p(f16bits(diffuse_gi)),
-                         _p(f16bits(specular_gi)), _p(f16bits(scene)), _p(out))
+    gi_float = any(a is not None and a.dtype == np.float32 for a in (diffuse_gi, specular_gi))
+    cv = (lambda a: None if a is None else _c(a, np.float32)) if gi_float else f16bits
+    lib().orc_gi_compose(C.byref(p), C.c_int(W), C.c_int(H), _p(_c(depth, np.float32)), _p(_c(gbuffer, np.float32)), _p(cv(diffuse_gi)),
+                         _p(cv(specular_gi)), _p(f16bits(scene)), _p(out), C.c_int(int(gi_float)))
     return out
 
 

@@ -277,9 +277,10 @@ def temporal_reproject(p: abi.TemporalParams, inp, velocity, hist0, hist1, out0_
     s.tex("inputTexture", inp, F_RGBA16F if half_in else F_RGBA32F, linear=half_in)
     s.tex("velocityTexture", velocity, F_RGBA32F)
     lin = bool(p.history_linear)
-    s.tex("accumulatedTexture0", hist0, F_RGBA16F, linear=lin)
+    hfmt = F_RGBA32F if hist0.dtype == np.float32 else F_RGBA16F  # RGBA32F: the FramebufferTexture of denoiseMode "full_temporal" / "temporal"
+    s.tex("accumulatedTexture0", hist0, hfmt, linear=lin)
     if tc == 2:
-        s.tex("accumulatedTexture1", hist1, F_RGBA16F, linear=lin)
+        s.tex("accumulatedTexture1", hist1, hfmt, linear=lin)
     fmt = F_RGBA16F if out_half else F_RGBA32F
     outs = s.run(W, H, [(fmt, out0_prev)] + ([(fmt, out1_prev)] if tc == 2 else []))
     return outs[0], (outs[1] if tc == 2 else out1_prev)  # a second target that is not bound keeps its contents
@@ -314,8 +315,9 @@ def gi_compose(p: abi.ComposeParams, depth, gbuffer, diffuse_gi, specular_gi, ou
     s.set(cameraNear=float(p.cam.near_plane), cameraFar=float(p.cam.far_plane))
     s.tex("depthTexture", depth, F_R32F)
     s.tex("gBufferTexture", gbuffer, F_RGBA32F)
-    s.tex("diffuseGiTexture", diffuse_gi, F_RGBA16F, linear=True)
-    s.tex("specularGiTexture", specular_gi, F_RGBA16F, linear=True)
+    gi_float = any(a is not None and a.dtype == np.float32 for a in (diffuse_gi, specular_gi))  # "full_temporal": the temporal pass's FloatType NEAREST targets
+    s.tex("diffuseGiTexture", diffuse_gi, F_RGBA32F if gi_float else F_RGBA16F, linear=not gi_float)
+    s.tex("specularGiTexture", specular_gi, F_RGBA32F if gi_float else F_RGBA16F, linear=not gi_float)
     s.tex("sceneTexture", scene, F_RGBA16F, linear=True)
     return s.run(W, H, [(F_RGBA32F, np.asarray(out_prev, np.float32))])[0]
 

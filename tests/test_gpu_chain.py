@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import chain_harness as ch
+from realism_effects_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
@@ -164,3 +165,31 @@ def test_tma_staged_poisson_passes_are_bit_identical(built, monkeypatch):
     for t in range(3):
         for k in ("dn0", "dn1", "composed", "tr0"):
             assert outs["1"][t][k].tobytes() == outs["0"][t][k].tobytes(), (t, k)
+
+
+@pytest.mark.parametrize("mode", [abi.MODE_SSGI, abi.MODE_SSR])
+@pytest.mark.parametrize("denoise_mode", [abi.DENOISE_FULL_TEMPORAL, abi.DENOISE_TEMPORAL])
+def test_chain_denoise_modes_full_temporal_and_temporal(built, mode, denoise_mode):
+    """option denoiseMode (src/denoise/Denoiser.js:7,45-78): "full_temporal" (what preset "low" selects: K2 -> K4 on the temporal textures, the history
+    is the RGBA32F FramebufferTexture copy of the temporal target for BOTH planes) and "temporal" (K2 only; K1 samples the temporal texture).  3 frames
+    with history against the oracle chain (which equals the reference shaders bit for bit in these modes too: tools/pin_oracle.py)."""
+    o = ch.Opts(mode=mode, denoise_mode=denoise_mode)
+    inp = ch.make_inputs(160, 90, 3)
+    planes = ("ssgi", "tr0", "tr1", "composed") if mode == abi.MODE_SSGI else ("ssgi", "tr0", "composed")
+    ref = ch.run_oracle_chain(inp, o, capture=planes, lean=True)
+    for fast in (True, False):
+        got, launches = ch.run_cuda_chain(inp, o, capture=planes, fast_math=fast)
+        for t in range(3):
+            for k in planes:
+                a, b = (ref[t][k][..., :3], got[t][k][..., :3]) if (k == "ssgi" and mode == abi.MODE_SSR) else (ref[t][k], got[t][k])
+                c = ch.compare(a, b, packed=(k == "ssgi" and mode == abi.MODE_SSGI))
+                assert c["frac_bad"] <= (6e-3 if fast else 1e-3), (fast, t, k, c)
+    with pytest.raises(abi.RfxError):
+        bad = ch.chain_options(inp, o)
+        bad.denoise_mode = 3  # "denoised": cannot run in the reference either
+        from realism_effects_b200 import engine
+        ctx = engine.Context(0, inp.blue)
+        try:
+            engine.SsgiChain(ctx, bad)
+        finally:
+            ctx.close()

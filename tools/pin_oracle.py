@@ -53,6 +53,9 @@ CHAIN_CASES = {
     "ssgi_static": (64, 48, 3, {}, dict(static=True)),
     "ssgi_refine0": (64, 48, 1, dict(refine_steps=0, steps=12), {}),
     "ssr": (96, 64, 3, dict(mode=abi.MODE_SSR), {}),
+    "ssgi_full_temporal": (64, 48, 3, dict(denoise_mode=abi.DENOISE_FULL_TEMPORAL), {}),
+    "ssgi_temporal": (64, 48, 3, dict(denoise_mode=abi.DENOISE_TEMPORAL), {}),
+    "ssr_full_temporal": (64, 48, 3, dict(mode=abi.MODE_SSR, denoise_mode=abi.DENOISE_FULL_TEMPORAL), {}),
 }
 
 
@@ -60,7 +63,7 @@ def run_chain_case(name, golden: bool):
     W, H, F, okw, ikw = CHAIN_CASES[name]
     o = ch.Opts(**okw)
     inp = ch.make_inputs(W, H, F, **ikw)
-    planes = [p for p in PLANES if not (o.mode == abi.MODE_SSR and p in ("tr1", "dn1"))]
+    planes = [p for p in PLANES if not (o.mode == abi.MODE_SSR and p in ("tr1", "dn1")) and not (o.denoise_mode != 0 and p in ("dn0", "dn1"))]
     a = ch.run_oracle_chain(inp, o, capture=planes, lean=True)
     t = time.time()
     b = ch.run_oracle_chain(inp, o, capture=planes, lean=True, impl=refglsl)
