@@ -397,6 +397,9 @@ typedef struct rfx_ssgi_chain_options {
   int32_t mode;                /* RFX_MODE_* */
   int32_t blue_noise_start;    /* startIndex of BlueNoiseUtils.js:19 (pinned)          */
   int32_t denoise_mode;        /* RFX_DENOISE_*: option denoiseMode (Denoiser.js:7,45-78); constructor-time, like mode   */
+  float resolution_scale;      /* option resolutionScale (SSGIPass.js:52-57): the SSGI target is (int)(width*scale) x (int)(height*scale),
+                                  everything else stays at full size; 0 or 1 = full size.  Constructor-time (a size change).      */
+  int32_t _pad;
 } rfx_ssgi_chain_options;
 
 typedef struct rfx_ssgi_frame {

@@ -145,7 +145,6 @@ export class SSGIEffect {
 	_setOptions() { if (this.chain) rfx.chainSetOptions(this.ctx, this.chain, this._chainOptions()) }   // setters end with reset() (SSGIEffect.js:203-209)
 	setSize(width, height, force = false) {
 		if (width === undefined || (!force && width === this.width && height === this.height)) return
-		if (this._options.resolutionScale !== 1) throw new Error("resolutionScale != 1 is not supported by the CUDA engine")
 		this.width = width; this.height = height
 		if (this.chain) rfx.chainDestroy(this.chain)
 		this.chain = rfx.chainCreate(this.ctx, this._chainOptions())
@@ -352,7 +351,6 @@ export class HBAOEffect {
 	}
 	setSize(width, height) {
 		if (width === undefined) return
-		if (this._options.resolutionScale !== 1) throw new Error("resolutionScale != 1 is not supported by the CUDA engine")
 		this.dispose()
 		this.width = width; this.height = height
 		this.aoPlane = rfx.planeAlloc(this.ctx, FMT.RGBA16F, width, height)

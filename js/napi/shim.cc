@@ -89,6 +89,7 @@ void read_chain_options(const Obj& b, rfx_ssgi_chain_options* o) {  // keys = sr
   o->normal_phi = (float)b.num("normalPhi", 50); o->roughness_phi = (float)b.num("roughnessPhi", 50); o->specular_phi = (float)b.num("specularPhi", 50);
   o->ssgi_flags = (uint32_t)b.num("flags", RFX_SSGI_USE_DIRECT_LIGHT); o->mode = (int32_t)b.num("mode", RFX_MODE_SSGI);
   o->blue_noise_start = (int32_t)b.num("blueNoiseStart", 1234567);
+  o->resolution_scale = (float)b.num("resolutionScale", 1);
   o->denoise_mode = (int32_t)b.num("denoiseModeId", RFX_DENOISE_FULL);  // index of denoiseMode in ["full", "full_temporal", "temporal"]
 }
 

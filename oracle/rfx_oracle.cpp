@@ -1174,17 +1174,19 @@ static void fill_env(EnvInfo& e, const orc_env* env) {
 }
 
 // K1.  depth R32F, gbuffer RGBA32F, velocity RGBA32F|NULL, direct_light RGBA16F|NULL, accumulated RGBA32F|NULL, out RGBA32F
+// W x H: the render target (= `resolution`); TW x TH: the size of the input planes — larger than W x H when resolutionScale < 1
+// (SSGIPass.js:52-57: only the SSGI target is scaled, the G-buffer / depth / denoiser textures stay at full size)
 void orc_ssgi_trace(const rfx_ssgi_params* p, int W, int H, const float* depth, const float* gbuffer, const float* velocity,
                     const uint16_t* direct_light, const float* accumulated, const orc_env* env, const uint8_t* blue_noise, int bn_w, int bn_h,
-                    float* out) {
+                    float* out, int TW, int TH) {
 #pragma omp parallel
   {
     SsgiShader s(*p);
-    s.depthTexture = mk(depth, W, H, F_R32F);
-    s.gBufferTexture = mk(gbuffer, W, H, F_RGBA32F);
-    s.velocityTexture = mk(velocity, W, H, F_RGBA32F);
-    s.directLightTexture = mk(direct_light, W, H, F_RGBA16F, true);
-    s.accumulatedTexture = mk(accumulated, W, H, F_RGBA32F);
+    s.depthTexture = mk(depth, TW, TH, F_R32F);
+    s.gBufferTexture = mk(gbuffer, TW, TH, F_RGBA32F);
+    s.velocityTexture = mk(velocity, TW, TH, F_RGBA32F);
+    s.directLightTexture = mk(direct_light, TW, TH, F_RGBA16F, true);
+    s.accumulatedTexture = mk(accumulated, TW, TH, F_RGBA32F);
     s.bn.tex = mk(blue_noise, bn_w, bn_h, F_RGBA8, false, true);
     s.resolution = vec2((float)W, (float)H);
     fill_env(s.envMapInfo, env);
@@ -1198,12 +1200,13 @@ void orc_ssgi_trace(const rfx_ssgi_params* p, int W, int H, const float* depth, 
 // Discarded pixels are left untouched in out0/out1.
 // history_float: the history planes are RGBA32F (denoiseMode "full_temporal" / "temporal": the FramebufferTexture copy of the FloatType target)
 void orc_temporal_reproject(const rfx_temporal_params* p, int W, int H, const void* input, int input_half, const float* velocity,
-                            const void* history0, const void* history1, void* out0, void* out1, int out_half, int history_float) {
+                            const void* history0, const void* history1, void* out0, void* out1, int out_half, int history_float, int IW, int IH) {
+  // IW x IH: the size of inputTexture (the SSGI target: smaller than W x H when resolutionScale < 1; NEAREST, fetched by uv)
 #pragma omp parallel
   {
     TemporalShader s(*p);
     s.W = W; s.H = H;
-    s.inputTexture = mk(input, W, H, input_half ? F_RGBA16F : F_RGBA32F, input_half != 0);
+    s.inputTexture = mk(input, IW, IH, input_half ? F_RGBA16F : F_RGBA32F, input_half != 0);
     s.velocityTexture = mk(velocity, W, H, F_RGBA32F);
     s.accumulatedTexture[0] = mk(history0, W, H, history_float ? F_RGBA32F : F_RGBA16F, p->history_linear != 0);
     s.accumulatedTexture[1] = mk(history1, W, H, history_float ? F_RGBA32F : F_RGBA16F, p->history_linear != 0);

@@ -128,7 +128,7 @@ class ChainOptions(C.Structure):
                 ("refine_steps", C.c_int32), ("distance", C.c_float), ("thickness", C.c_float), ("env_blur", C.c_float),
                 ("radius", C.c_float), ("phi", C.c_float), ("luma_phi", C.c_float), ("depth_phi", C.c_float), ("normal_phi", C.c_float),
                 ("roughness_phi", C.c_float), ("specular_phi", C.c_float), ("ssgi_flags", C.c_uint32), ("mode", C.c_int32),
-                ("blue_noise_start", C.c_int32), ("denoise_mode", C.c_int32)]
+                ("blue_noise_start", C.c_int32), ("denoise_mode", C.c_int32), ("resolution_scale", C.c_float), ("_pad", C.c_int32)]
 
 
 class SsgiFrame(C.Structure):

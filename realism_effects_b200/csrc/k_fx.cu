@@ -5,9 +5,10 @@
 // the colour is handed from one mainImage() to the next.  effects_kernel is that merged shader, selected at run time: up to four
 // effects in caller order, one read of the frame, one write — instead of one full-frame round trip per effect.  HBM traffic is
 // 8 B/px in + 8 B/px out (+ 4 depth / + 16 velocity when used); the 3x3 and bilinear taps of the input are L1 / L2 hits.
-// Arithmetic is IEEE with double-precision transcendentals rounded once to fp32 — the hash of SparkleEffect (fract(sin(x) * 43758.5))
-// and pow(noise, 500 * spread) amplify a last-bit difference of sin() by four orders of magnitude, so "approximately the same sin"
-// is visibly a different sparkle pattern.
+// Arithmetic is IEEE fp32 with libm transcendentals, except where the shader itself amplifies the last bit: the hash of SparkleEffect
+// (fract(sin(x) * 43758.5)) and pow(noise, 500 * spread) turn a one-ulp difference of sin() into a different sparkle pattern, so those two
+// are evaluated in double and rounded once (what "correctly rounded" means for the parity oracle); TAAPass re-evaluates its sRGB curve in
+// double only for the ~0.4 % of texels whose 8-bit rounding is within 2e-3 of a tie.
 #include "rfx_device.cuh"
 #include "rfx_kernels.h"
 
@@ -68,7 +69,7 @@ RFX_D v4 fx_gradual_background(const EffectsArgs& a, v4 inputColor, int x, int y
   const v3 viewPos = view_position(a.cam, uv, view_z(a.cam, a.cam.perspective != 0, depth));
   const v3 worldPos = xyz(mul(a.cam.camera_matrix_world, mk4(viewPos, 1.0f)));
   const float distToCenter = length(mk2(worldPos.x, worldPos.z)) + fmaxf(0.0f, -worldPos.y);
-  const float fade = clampf(powcr(distToCenter, 0.1f) * 15.0f - a.max_distance, 0.0f, 1.0f);
+  const float fade = clampf(powf(distToCenter, 0.1f) * 15.0f - a.max_distance, 0.0f, 1.0f);  // libm fp32 (<= 2 ulp): not amplified
   const v3 c = mix(xyz(inputColor), mk3(a.bg[0], a.bg[1], a.bg[2]), fade);
   return mk4(c, 1.0f);
 }
@@ -97,9 +98,9 @@ RFX_D v4 fx_sparkle(const EffectsArgs& a, v4 inputColor, int x, int y, v2 uv) {
   if (worldPos.y < 0.01f) return inputColor;
   const v3 cameraPos = xyz(mul(a.cam.camera_matrix_world, mk4(0.0f, 0.0f, 0.0f, 1.0f)));
   const float dist = length(worldPos - cameraPos);
-  const float distFactor = expcr(-dist * 0.005f);
+  const float distFactor = expf(-dist * 0.005f);
   float facing = fmaxf(dot(-viewDir, viewNormal), 0.0f);
-  facing = powcr(facing, 4.0f);
+  facing = powf(facing, 4.0f);
   const v3 nw = normalize(worldPos);
   const v2 offset = mk2(nw.x, nw.z) * 1000.0f + mk2(normal.x, normal.z) * 500.0f;
   float noise = nn(offset);
@@ -108,7 +109,7 @@ RFX_D v4 fx_sparkle(const EffectsArgs& a, v4 inputColor, int x, int y, v2 uv) {
   lum = smoothstepf(0.15f, 1.0f, lum);
   const float sparkleFactor = noise * lum * facing * distFactor * 5000.0f * a.intensity;
   const v3 c = xyz(inputColor);
-  const v3 color = c + mk3(powcr(c.x, 4.0f), powcr(c.y, 4.0f), powcr(c.z, 4.0f)) * sparkleFactor;
+  const v3 color = c + mk3(powf(c.x, 4.0f), powf(c.y, 4.0f), powf(c.z, 4.0f)) * sparkleFactor;
   return mk4(color, 1.0f);
 }
 
@@ -130,25 +131,34 @@ __global__ void __launch_bounds__(256) effects_kernel(const __grid_constant__ Ef
 }
 
 // three r151 LinearTosRGB (encodings_pars_fragment)
+template <bool EXACT>
 RFX_D float linear_to_srgb(float v) {
-  const float hi = powcr(v, 0.41666f) * 1.055f - 0.055f, lo = v * 12.92f;
+  const float hi = (EXACT ? powcr(v, 0.41666f) : powf(v, 0.41666f)) * 1.055f - 0.055f, lo = v * 12.92f;
   return mixf(hi, lo, v <= 0.0031308f ? 1.0f : 0.0f);
 }
-RFX_D unsigned to_unorm8(float v) { return (unsigned)lrintf(clampf(v, 0.0f, 1.0f) * 255.0f); }
+template <bool EXACT>
+RFX_D v4 taa_value(const TaaArgs& a, v4 color, v4 acc, float t) {
+  if (a.srgb_output) color = mk4(linear_to_srgb<EXACT>(color.x), linear_to_srgb<EXACT>(color.y), linear_to_srgb<EXACT>(color.z), color.w);
+  if (a.camera_not_moved_frames == 0.0f) return color;
+  return mk4(mixf(acc.x, color.x, t), mixf(acc.y, color.y, t), mixf(acc.z, color.z, t), mixf(acc.w, color.w, t));
+}
+RFX_D bool near_tie(float v) { const float s = clampf(v, 0.0f, 1.0f) * 255.0f; return fabsf((s - floorf(s)) - 0.5f) < 2e-3f; }
+RFX_D unsigned to_unorm8(float v) { return (unsigned)lroundf(clampf(v, 0.0f, 1.0f) * 255.0f); }  // round to nearest, ties away from zero
 
 // taa.frag:6-18 rendered to the canvas (RGBA8)
 __global__ void __launch_bounds__(256) taa_kernel(const __grid_constant__ TaaArgs a) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = a.row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= a.W || y >= a.row1) return;
-  v4 color = tex_h4_linear(a.input, pixel_uv(x, y, a.W, a.H));
-  if (a.srgb_output) color = mk4(linear_to_srgb(color.x), linear_to_srgb(color.y), linear_to_srgb(color.z), color.w);
-  v4 o = color;
+  const v4 color = tex_h4_linear(a.input, pixel_uv(x, y, a.W, a.H));
+  v4 acc = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+  float t = 1.0f;
   if (!(a.camera_not_moved_frames == 0.0f)) {
     const uchar4 h = __ldg((const uchar4*)(a.history.p + pv_off(a.history, x, y, 4)));
-    const v4 acc = mk4(__fdiv_rn((float)h.x, 255.0f), __fdiv_rn((float)h.y, 255.0f), __fdiv_rn((float)h.z, 255.0f), __fdiv_rn((float)h.w, 255.0f));
-    const float t = __fdiv_rn(1.0f, a.camera_not_moved_frames + 1.0f);
-    o = mk4(mixf(acc.x, color.x, t), mixf(acc.y, color.y, t), mixf(acc.z, color.z, t), mixf(acc.w, color.w, t));
+    acc = mk4(__fdiv_rn((float)h.x, 255.0f), __fdiv_rn((float)h.y, 255.0f), __fdiv_rn((float)h.z, 255.0f), __fdiv_rn((float)h.w, 255.0f));
+    t = __fdiv_rn(1.0f, a.camera_not_moved_frames + 1.0f);
   }
+  v4 o = taa_value<false>(a, color, acc, t);
+  if (a.srgb_output && (near_tie(o.x) || near_tie(o.y) || near_tie(o.z))) o = taa_value<true>(a, color, acc, t);  // the libm pow may sit on the other side of the tie
   uchar4 q;
   q.x = (unsigned char)to_unorm8(o.x); q.y = (unsigned char)to_unorm8(o.y); q.z = (unsigned char)to_unorm8(o.z); q.w = (unsigned char)to_unorm8(o.w);
   *((uchar4*)(a.out.p + ((unsigned)y * (unsigned)a.out.pitch + (unsigned)x * 4u))) = q;

@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(256) viewz_kernel(PV depth, OutV vz, int W, in
   else { for (int i = 0; i < 4 && x + i < W; i++) dst[i] = o[i]; }
 }
 cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) {
-  dim3 grid((a.W / 4 + 255) / 256 + 1, a.H);
-  viewz_kernel<<<grid, 256, 0, s>>>(a.depth, vz, a.W, a.H, a.near_mul_far, a.far_minus_near, a.near_minus_far, a.cam.near_plane, a.cam.far_plane,
+  const int W = a.depth.w, H = a.depth.h;  // the depth plane's own size (larger than the render target when resolutionScale < 1)
+  dim3 grid((W / 4 + 255) / 256 + 1, H);
+  viewz_kernel<<<grid, 256, 0, s>>>(a.depth, vz, W, H, a.near_mul_far, a.far_minus_near, a.near_minus_far, a.cam.near_plane, a.cam.far_plane,
                                     a.cam.perspective);
   return cudaGetLastError();
 }
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, PHASE == 1 ? RFX_K1_MARCH_MIN_BLOCKS
   if (!active) return;
 
   const v2 vUv = pixel_uv(x, y, a.W, a.H);
-  const float unpackedDepth = ld_r32f(a.depth, x, y);
+  const float unpackedDepth = a.scaled ? tex_r32f_nearest(a.depth, vUv) : ld_r32f(a.depth, x, y);  // scaled: NEAREST by uv in the full-size plane
   if (unpackedDepth == 1.0f) {  // background :109-113
     if (PHASE == 1) return;
     v4 dl = mk4(0.0f, 0.0f, 0.0f, 1.0f);
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, PHASE == 1 ? RFX_K1_MARCH_MIN_BLOCKS
     st_f4(a.out.p, a.out.pitch, x, y, packTwoVec4(dl, dl));
     return;
   }
-  const float4 g = ld_f4(a.gb, x, y);
+  const float4 g = a.scaled ? tex_f4_nearest(a.gb, vUv) : ld_f4(a.gb, x, y);
   PixelMat m;
   m.diffuse = xyz(floatToVec4(g.x));
   const v3 worldNormal = unpackNormal(g.y);

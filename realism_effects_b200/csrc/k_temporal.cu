@@ -143,11 +143,11 @@ __global__ void __launch_bounds__(kThreads, RFX_K2_MIN_BLOCKS) temporal_kernel(c
   v4 inp[2];
   bool sampled[2] = {false, false};
   if (ITYPE == RFX_INPUT_DIFFUSE_SPECULAR) {
-    unpackTwoVec4(ld_f4(a.input, x, y), inp[0], inp[1]);
+    unpackTwoVec4(a.in_scaled ? tex_f4_nearest(a.input, s.vUv) : ld_f4(a.input, x, y), inp[0], inp[1]);
   } else if (a.input_half) {
     inp[0] = tex_h4_linear(a.input, s.vUv);  // composer buffer: LINEAR, fetched at the pixel centre
   } else {
-    inp[0] = f4v(ld_f4(a.input, x, y));
+    inp[0] = f4v(a.in_scaled ? tex_f4_nearest(a.input, s.vUv) : ld_f4(a.input, x, y));
   }
   constexpr int NIN = ITYPE == RFX_INPUT_DIFFUSE_SPECULAR ? 2 : 1;
 #pragma unroll
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(kThreads, RFX_K2_MIN_BLOCKS) temporal_kernel(c
 #pragma unroll
         for (int dx = -2; dx <= 2; dx++) {
           const int tx = clampi(x + dx, a.W);
-          const float4 e = ld_f4(a.input, tx, ty);
+          // a smaller SSGI target (resolutionScale < 1): the shader's literal NEAREST fetch at vUv + (dx, dy) * invTexSize
+          const float4 e = a.in_scaled ? tex_f4_nearest(a.input, mk2(s.vUv.x + (float)dx * a.inv_w, s.vUv.y + (float)dy * a.inv_h)) : ld_f4(a.input, tx, ty);
 #pragma unroll
           for (int i = 0; i < TC; i++) {
             const unsigned urg = __float_as_uint(rs[i] != 0 ? e.z : e.x), uba = __float_as_uint(rs[i] != 0 ? e.w : e.y);

@@ -428,9 +428,12 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
   if (direct_light && !pv(direct_light, RFX_FMT_RGBA16F, a.direct)) return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_trace: direct light must be RGBA16F");
   if (accumulated && !pv(accumulated, RFX_FMT_RGBA32F, a.accumulated)) return fail(ctx, RFX_ERR_BAD_FORMAT, "ssgi_trace: accumulated must be RGBA32F");
   a.W = (int)out->width; a.H = (int)out->height;
-  if (a.depth.w != a.W || a.depth.h != a.H || a.gb.w != a.W || a.gb.h != a.H || (a.velocity.p && (a.velocity.w != a.W || a.velocity.h != a.H)) ||
-      (a.direct.p && (a.direct.w != a.W || a.direct.h != a.H)) || (a.accumulated.p && (a.accumulated.w != a.W || a.accumulated.h != a.H)))
-    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_trace: all planes must match the output size (resolutionScale != 1 is not supported)");
+  const int TW = a.depth.w, TH = a.depth.h;  // the input planes share one size; the render target may be smaller (resolutionScale < 1, SSGIPass.js:52-57)
+  if (a.gb.w != TW || a.gb.h != TH || (a.velocity.p && (a.velocity.w != TW || a.velocity.h != TH)) ||
+      (a.direct.p && (a.direct.w != TW || a.direct.h != TH)) || (a.accumulated.p && (a.accumulated.w != TW || a.accumulated.h != TH)))
+    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_trace: depth / gbuffer / velocity / direct light / accumulated must have one size");
+  if (a.W > TW || a.H > TH) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "ssgi_trace: the output may be smaller than the input planes (resolutionScale <= 1), not larger");
+  a.scaled = a.W != TW || a.H != TH;
   if (p->steps < 1 || p->refine_steps < 0 || (p->mode != RFX_MODE_SSGI && p->mode != RFX_MODE_SSR)) return fail(ctx, RFX_ERR_INVALID_ARG, "ssgi_trace: bad steps/mode");
   rows(row0, row1, out->height, a.row0, a.row1);
   set_segs(ctx, a.row0, a.row1, a.segs);
@@ -459,24 +462,24 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
                     M[12] == 0.0f && M[13] == 0.0f && M[15] == 0.0f;
   }
   // view-space z plane (scratch): the march taps read it instead of converting depth -> viewZ per tap
-  if (!ctx->viewz || ctx->viewz_w != a.W || ctx->viewz_h != a.H) {
+  if (!ctx->viewz || ctx->viewz_w != TW || ctx->viewz_h != TH) {
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->viewz);
     ctx->viewz = nullptr;
-    ctx->viewz_pitch = ((size_t)a.W * 4 + 255) & ~(size_t)255;
-    CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * a.H));
-    ctx->viewz_w = a.W; ctx->viewz_h = a.H;
+    ctx->viewz_pitch = ((size_t)TW * 4 + 255) & ~(size_t)255;
+    CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * TH));
+    ctx->viewz_w = TW; ctx->viewz_h = TH;
   }
   {  // fast fused kernel: projection rows in texel units (0.5 W P00, 0.5 W P20, 0.5 H P11, 0.5 H P21), word pitch of the viewZ plane
     const float* M = p->cam.projection;
     const float hw = 0.5f * (float)a.W, hh = 0.5f * (float)a.H;
     a.ps_x0 = hw * M[0]; a.ps_x2 = hw * M[8]; a.ps_y1 = hh * M[5]; a.ps_y2 = hh * M[9]; a.ps_hw = hw; a.ps_hh = hh;
     a.vz_pitchw = (int)(ctx->viewz_pitch / 4);
-    a.legacy_fast = ctx->legacy_k1;
+    a.legacy_fast = ctx->legacy_k1 || a.scaled;  // the fused fast kernel addresses texels by pixel index: a scaled target takes the general kernel
     a.march_batch = ctx->k1_batch;
     if (ctx->peer_accumulated) a.acc_peer = *ctx->peer_accumulated;
   }
-  a.phase = ctx->k1_phase;
+  a.phase = a.scaled ? 0 : ctx->k1_phase;
   if (a.phase != 0 && !a.fast) {  // the split phases exist for the fast variant: otherwise phase 1 is empty and phase 2 is the fused kernel
     if (a.phase == 1) return RFX_OK;
     a.phase = 0;
@@ -494,7 +497,7 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     a.rec_pitch = (long long)ctx->k1rec_pitch;
   }
   if (!ctx->viewz_reuse && a.phase != 2) LAUNCHED(launch_viewz(a, OutV{(unsigned char*)ctx->viewz, (long long)ctx->viewz_pitch}, pick(ctx, stream)));
-  a.viewz = PV{(const unsigned char*)ctx->viewz, a.W, a.H, (long long)ctx->viewz_pitch};
+  a.viewz = PV{(const unsigned char*)ctx->viewz, TW, TH, (long long)ctx->viewz_pitch};
   LAUNCHED(launch_ssgi(a, pick(ctx, stream)));
   return RFX_OK;
 }
@@ -518,8 +521,10 @@ rfx_status rfx_temporal_reproject_launch(rfx_ctx* ctx, void* stream, const rfx_t
     if (!pv(history1, hfmt, a.hist1) || !ov(out1, out0->format, a.out1)) return fail(ctx, RFX_ERR_BAD_FORMAT, "temporal: second plane missing / wrong format");
   }
   a.W = (int)out0->width; a.H = (int)out0->height;
-  if (a.input.w != a.W || a.input.h != a.H || a.velocity.w != a.W || a.velocity.h != a.H || a.hist0.w != a.W || a.hist0.h != a.H)
-    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "temporal: plane sizes differ");
+  if (a.velocity.w != a.W || a.velocity.h != a.H || a.hist0.w != a.W || a.hist0.h != a.H || a.input.w > a.W || a.input.h > a.H)
+    return fail(ctx, RFX_ERR_SIZE_MISMATCH, "temporal: plane sizes differ (only the input may be smaller: resolutionScale < 1)");
+  a.in_scaled = a.input.w != a.W || a.input.h != a.H;
+  if (a.in_scaled && a.input_half) return fail(ctx, RFX_ERR_UNSUPPORTED, "temporal: a scaled input is the RGBA32F SSGI target");
   rows(row0, row1, out0->height, a.row0, a.row1);
   set_segs(ctx, a.row0, a.row1, a.segs);
   cam_to_dev(p->cam, a.cam);
@@ -863,8 +868,14 @@ rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt
     delete ch;
     return fail(ctx, RFX_ERR_UNSUPPORTED, "chain_create: denoise_mode must be full / full_temporal / temporal (\"denoised\" hands an array of textures to a sampler in the reference and cannot run there either)");
   }
-  ch->fastpath = ctx->fast_math && opt->mode == RFX_MODE_SSGI && opt->denoise_mode == RFX_DENOISE_FULL;  // latched: the history formats differ between the paths
-  alloc(RFX_FMT_RGBA32F, &ch->ssgi_out);
+  const bool scaled = opt->resolution_scale != 0.0f && opt->resolution_scale != 1.0f;
+  if (scaled && !(opt->resolution_scale > 0.0f && opt->resolution_scale < 1.0f)) { delete ch; return fail(ctx, RFX_ERR_INVALID_ARG, "chain_create: resolution_scale must be in (0, 1]"); }
+  const uint32_t sw = scaled ? (uint32_t)((double)opt->width * (double)opt->resolution_scale) : opt->width;   // renderTarget.setSize(width * scale, height * scale)
+  const uint32_t sh = scaled ? (uint32_t)((double)opt->height * (double)opt->resolution_scale) : opt->height;
+  if (sw == 0 || sh == 0) { delete ch; return fail(ctx, RFX_ERR_INVALID_ARG, "chain_create: resolution_scale leaves an empty SSGI target"); }
+  // latched: the history formats differ between the paths; the fused fast chain needs the full-size SSGI target and the Poisson history
+  ch->fastpath = ctx->fast_math && opt->mode == RFX_MODE_SSGI && opt->denoise_mode == RFX_DENOISE_FULL && !scaled;
+  if (st == RFX_OK) st = rfx_plane_alloc(ctx, RFX_FMT_RGBA32F, sw, sh, &ch->ssgi_out);
   if (opt->denoise_mode != RFX_DENOISE_FULL) alloc(RFX_FMT_RGBA32F, &ch->fb);
   if (ch->fastpath) {
     ialloc(16, &ch->nrdz); ialloc(32, &ch->tr32); ialloc(16, &ch->dnA16); ialloc(16, &ch->dnB16[0]); ialloc(16, &ch->dnB16[1]);
@@ -923,6 +934,7 @@ rfx_status rfx_ssgi_chain_set_options(rfx_ssgi_chain* ch, const rfx_ssgi_chain_o
   if (opt->width != ch->opt.width || opt->height != ch->opt.height) return fail(ch->ctx, RFX_ERR_SIZE_MISMATCH, "chain_set_options: size change needs a new chain");
   if (opt->denoise_iterations < 0 || opt->steps < 1 || opt->refine_steps < 0) return fail(ch->ctx, RFX_ERR_INVALID_ARG, "chain_set_options: bad option value");
   if (opt->denoise_mode != ch->opt.denoise_mode || opt->mode != ch->opt.mode) return fail(ch->ctx, RFX_ERR_UNSUPPORTED, "chain_set_options: mode / denoise_mode are constructor options (Denoiser.js:17-64): create a new chain");
+  if (opt->resolution_scale != ch->opt.resolution_scale) return fail(ch->ctx, RFX_ERR_SIZE_MISMATCH, "chain_set_options: resolution_scale resizes the SSGI target (SSGIEffect.js:193-196 calls setSize): create a new chain");
   const int32_t start = ch->opt.blue_noise_start;
   ch->opt = *opt;
   ch->opt.blue_noise_start = start;  // the blue-noise closures keep their start index for the life of the material
@@ -1190,6 +1202,7 @@ static rfx_status chain_render_impl(rfx_ssgi_chain* ch, void* stream, const rfx_
   rfx_status st = RFX_OK;
   const bool dm_full = o.denoise_mode == RFX_DENOISE_FULL;
   if (!dm_full && ranges) return fail(ctx, RFX_ERR_UNSUPPORTED, "chain: row-range rendering is implemented for denoise_mode full only");
+  if (ranges && ch->ssgi_out.height != o.height) return fail(ctx, RFX_ERR_UNSUPPORTED, "chain: row-range rendering is implemented for resolution_scale 1 only");
   const uint32_t n_launches = 3u + 2u * (uint32_t)o.denoise_iterations;  // K1, K2, K3 passes, K4 (both modes: DenoiserComposePass runs for inputType specular too)
   if (!ranges) n_blocks = 1;
   // what SSGIPass samples as accumulatedTexture = denoiser.texture (Denoiser.js:67-78): the compose target, or the temporal pass's first texture

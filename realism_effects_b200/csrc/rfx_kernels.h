@@ -118,6 +118,7 @@ struct TemporalArgs {
   float inv_w, inv_h;  // invTexSize
   int full_accumulate, texture_count, input_type, log_transform, rs0, rs1, history_linear;
   int input_half, out_half;
+  int in_scaled;  // inputTexture (the SSGI target) is smaller than the output (resolutionScale < 1): NEAREST fetch by uv
   int hist_f32;  // history planes are RGBA32F (denoiseMode "full_temporal" / "temporal")
   int fast;  // SFU variants of log/exp/pow
 };
@@ -148,6 +149,7 @@ struct SsgiArgs {
   float ps_x0, ps_x2, ps_y1, ps_y2, ps_hw, ps_hh;  // projection rows scaled to texel units: tx = (ps_x0*x + ps_x2*z) / -z + ps_hw
   int vz_pitchw;             // viewZ pitch in 4-byte words
   int legacy_fast;           // 1: use the round-1 fast kernel (tools/ A/B comparisons)
+  int scaled;                // the render target (W x H) is smaller than the input planes (resolutionScale < 1): texels are fetched by uv
   int march_batch;           // march steps fetched together before they are tested: 1, 2 or 4
   PeerPV acc_peer;           // `accumulated` in a row-sharded group (n > 1): rows live on their owners
 };

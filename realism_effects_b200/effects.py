@@ -178,13 +178,12 @@ class SSGIEffect(_Reactive):
         c.mode = abi.MODE_SSR if o["mode"] == "ssr" else abi.MODE_SSGI
         c.blue_noise_start = self._blue_start
         c.denoise_mode = abi.DENOISE_MODES[o["denoiseMode"]]
+        c.resolution_scale = float(o["resolutionScale"])
         return c
 
     def setSize(self, width, height, force=False):
         if not force and getattr(self, "_size", None) == (width, height):
             return
-        if self._options["resolutionScale"] != 1:
-            raise abi.RfxError("resolutionScale != 1 is not supported by the CUDA engine yet")
         self._size = (int(width), int(height))
         if self._chain is not None:
             self._chain.close()

@@ -49,6 +49,7 @@ class Opts:
     use_envmap: bool = True
     mode: int = abi.MODE_SSGI
     blue_noise_start: int = 1234567
+    resolution_scale: float = 1.0  # SSGIPass.js:53: only the SSGI target is scaled
     denoise_mode: int = 0  # Denoiser.js:7: 0 "full", 1 "full_temporal" (no Poisson pass), 2 "temporal" (no Poisson pass, no compose)
 
     @property
@@ -155,6 +156,7 @@ def chain_options(inp: Inputs, o: Opts) -> abi.ChainOptions:
     c.roughness_phi, c.specular_phi = o.roughness_phi, o.specular_phi
     c.ssgi_flags, c.mode, c.blue_noise_start = o.flags, o.mode, o.blue_noise_start
     c.denoise_mode = o.denoise_mode
+    c.resolution_scale = o.resolution_scale
     return c
 
 
@@ -188,7 +190,8 @@ def run_oracle_chain(inp: Inputs, o: Opts, capture=("ssgi", "tr0", "tr1", "dn0",
         sp = ssgi_params(o, cam, bn_trace, (inp.env_map.shape[1], inp.env_map.shape[0]))
         rec["_k1_accumulated"] = composed.copy()
         rec["_k1_params"] = sp
-        ssgi = orc.ssgi_trace(sp, fr["depth"], fr["gbuffer"], None, fr["direct"], composed, env, inp.blue)
+        osz = None if o.resolution_scale == 1.0 else (int(W * o.resolution_scale), int(H * o.resolution_scale))
+        ssgi = orc.ssgi_trace(sp, fr["depth"], fr["gbuffer"], None, fr["direct"], composed, env, inp.blue, out_size=osz)
         # K2
         if prev is None:
             prev = fr["cam"]

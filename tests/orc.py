@@ -100,13 +100,15 @@ class Env:
         self.struct = s
 
 
-def ssgi_trace(p: abi.SsgiParams, depth, gbuffer, velocity, direct_light, accumulated, env: Env | None, blue_noise):
-    H, W = depth.shape
+def ssgi_trace(p: abi.SsgiParams, depth, gbuffer, velocity, direct_light, accumulated, env: Env | None, blue_noise, out_size=None):
+    """out_size (W, H): the render target when it is smaller than the input planes (resolutionScale < 1); default = the planes' size"""
+    TH, TW = depth.shape
+    W, H = out_size or (TW, TH)
     out = np.zeros((H, W, 4), np.float32)
     bn = _c(blue_noise, np.uint8)
     lib().orc_ssgi_trace(C.byref(p), C.c_int(W), C.c_int(H), _p(_c(depth, np.float32)), _p(_c(gbuffer, np.float32)),
                          _p(_c(velocity, np.float32)), _p(f16bits(direct_light)), _p(_c(accumulated, np.float32)),
-                         C.byref(env.struct) if env is not None else None, _p(bn), C.c_int(bn.shape[1]), C.c_int(bn.shape[0]), _p(out))
+                         C.byref(env.struct) if env is not None else None, _p(bn), C.c_int(bn.shape[1]), C.c_int(bn.shape[0]), _p(out), C.c_int(TW), C.c_int(TH))
     return out
 
 
@@ -123,7 +125,7 @@ def temporal_reproject(p: abi.TemporalParams, inp, velocity, hist0, hist1, out0_
     else:
         h0, h1 = f16bits(hist0), f16bits(hist1) if hist1 is not None else None
     lib().orc_temporal_reproject(C.byref(p), C.c_int(W), C.c_int(H), _p(inp_c), C.c_int(int(input_half)), _p(_c(velocity, np.float32)),
-                                 _p(h0), _p(h1), _p(o0), _p(o1), C.c_int(int(out_half)), C.c_int(int(hist_float)))
+                                 _p(h0), _p(h1), _p(o0), _p(o1), C.c_int(int(out_half)), C.c_int(int(hist_float)), C.c_int(inp.shape[1]), C.c_int(inp.shape[0]))
     if out_half:
         o0 = o0.view(np.float16)
         o1 = None if o1 is None else o1.view(np.float16)

@@ -228,10 +228,13 @@ def _blue(s: Shader, blue_noise, index: int):
     s.set(blueNoiseSize=[blue_noise.shape[1], blue_noise.shape[0]], blueNoiseIndex=index)
 
 
-def ssgi_trace(p: abi.SsgiParams, depth, gbuffer, velocity, direct_light, accumulated, env, blue_noise):
+def ssgi_trace(p: abi.SsgiParams, depth, gbuffer, velocity, direct_light, accumulated, env, blue_noise, out_size=None):
     """SSGIPass.render  src/ssgi/pass/SSGIPass.js:68-95; material uniforms SSGIMaterial.js:15-42; env SSGIEffect.js:309-366 +
-    EquirectHdrInfoUniform.js:287-303,346-349.  `env` is a tests/orc.Env (host-built tables + mip chain) or None."""
+    EquirectHdrInfoUniform.js:287-303,346-349.  `env` is a tests/orc.Env (host-built tables + mip chain) or None.
+    out_size (W, H): renderTarget.setSize(width * resolutionScale, ...) and the `resolution` uniform (SSGIPass.js:52-57)."""
     H, W = depth.shape
+    if out_size:
+        W, H = out_size
     f = int(p.flags)
     use_env = bool(f & abi.SSGI_USE_ENVMAP) and env is not None
     s = Shader.get("ssgi", steps=int(p.steps), refine_steps=int(p.refine_steps), mode=int(p.mode),

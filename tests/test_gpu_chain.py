@@ -193,3 +193,22 @@ def test_chain_denoise_modes_full_temporal_and_temporal(built, mode, denoise_mod
             engine.SsgiChain(ctx, bad)
         finally:
             ctx.close()
+
+
+@pytest.mark.parametrize("mode,scale", [(abi.MODE_SSGI, 0.5), (abi.MODE_SSGI, 0.75), (abi.MODE_SSR, 0.5)])
+def test_chain_resolution_scale(built, mode, scale):
+    """option resolutionScale (src/ssgi/pass/SSGIPass.js:52-57): K1 renders into a (w * scale) x (h * scale) target and samples the full-size G-buffer by
+    uv; the temporal pass reads that smaller target NEAREST at full size.  3 frames against the oracle chain (= the reference shaders, bit for bit)."""
+    o = ch.Opts(mode=mode, resolution_scale=scale)
+    inp = ch.make_inputs(160, 96, 3)
+    planes = ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed") if mode == abi.MODE_SSGI else ("ssgi", "tr0", "dn0", "composed")
+    ref = ch.run_oracle_chain(inp, o, capture=planes, lean=True)
+    assert ref[0]["ssgi"].shape[:2] == (int(96 * scale), int(160 * scale))
+    for fast in (True, False):
+        got, _ = ch.run_cuda_chain(inp, o, capture=planes, fast_math=fast)
+        for t in range(3):
+            for k in planes:
+                a, b = (ref[t][k][..., :3], got[t][k][..., :3]) if (k == "ssgi" and mode == abi.MODE_SSR) else (ref[t][k], got[t][k])
+                assert a.shape == b.shape, (k, a.shape, b.shape)
+                c = ch.compare(a, b, packed=(k == "ssgi" and mode == abi.MODE_SSGI))
+                assert c["frac_bad"] <= (8e-3 if fast else 1e-3), (fast, t, k, c)
