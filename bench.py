@@ -141,12 +141,13 @@ def frame_planes(f):
 
 
 def env_for_bench():
-    """1024x512 equirect env + CDF tables (the reference demo's HDR is not redistributable into this repo: analytic sky of the same size)"""
+    """The reference demo's environment (example/public/hdr/spree_bank_1k.hdr, 1024x512) decoded like three's RGBELoader, and its
+    importance-sampling tables as `gatherData` builds them for a flipY texture (EquirectHdrInfoUniform.js:149-245, incl. the mirroring un-flip, A4)"""
     from realism_effects_b200 import synth
 
-    env = synth.synthetic_env(1024, 512)
-    marg, cond, total = synth.build_env_cdf(env.astype(np.float32))
-    return env, marg, cond, total
+    img, gl = synth.load_reference_env()
+    marg, cond, total = synth.build_env_cdf(img.astype(np.float32), flip_y=True)
+    return gl, marg, cond, total
 
 
 def chain_options(ch, o, W, H):
@@ -394,7 +395,7 @@ def run_single(args):
         configs = other_configs(ctx, ch, dev, stream, peak)
 
     cfg = {"workload": f"C3 SSGI+PoissonDenoise(denoiseIterations={DENOISE_ITERATIONS} => {2 * DENOISE_ITERATIONS} passes)+compose, steps=20 refineSteps=5, {W}x{H}",
-           "inputs": f"2 alternating synthetic G-buffer frames ({h2d / 1e6:.0f} MB of input planes per frame > 126 MB L2), moving camera, analytic 1024x512 env map + CDF tables",
+           "inputs": f"2 alternating synthetic G-buffer frames ({h2d / 1e6:.0f} MB of input planes per frame > 126 MB L2), moving camera, the reference demo's env map (spree_bank_1k.hdr, 1024x512) + its CDF tables",
            "l2": "inputs larger than L2; no explicit flush", "fast_math": True}
     line = {"metric": "SSGI+denoise Mpixels/s at 4K", "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": 1, "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 accumulate planes)", "data": "synthetic", "impl": "ours", "config": cfg,
@@ -559,7 +560,7 @@ def cpu_baseline_sample(ch, o, inp):
            "sample": f"{frames_n} frame(s) of the same chain at {width}x{height} ({dt:.1f} s of CPU work; first frame => empty history)"}
     rs = reference_shaders()
     if rs is not None:  # the reference's own shaders on the same cores, on a 1/16 sample (the port above also supplies the parity pixels)
-        small = ch.make_inputs(960, 540, 1, env_size=(1024, 512))
+        small = ch.make_inputs(960, 540, 1, reference_env=True)
         t0 = time.perf_counter()
         ch.run_oracle_chain(small, o, capture=("composed",), lean=True, impl=rs)
         dts = time.perf_counter() - t0
@@ -597,7 +598,7 @@ def run_reference(args):
     K, Wm = args.steps, args.warmup
     if args.steps == 100:  # the default K is sized for the GPU arm; a CPU step takes ~0.5 s
         K, Wm = 20, 3
-    inp = ch.make_inputs(sw, sh, 2, env_size=(1024, 512))
+    inp = ch.make_inputs(sw, sh, 2, reference_env=True)
     frames = inp.frames
     cores = int(orc.lib().orc_num_threads())
 

@@ -66,11 +66,12 @@ RFX_D float ssgi_view_z(const SsgiArgs& a, float depth) {
 
 // prepass: viewZ plane = getViewZ(depth), same arithmetic as the shader => bit-identical taps
 __global__ void __launch_bounds__(256) viewz_kernel(PV depth, OutV vz, int W, int H, float near_mul_far, float far_minus_near, float near_minus_far,
-                                                    float near_plane, float far_plane, int perspective) {
+                                                    float near_plane, float far_plane, int perspective, int tiles_x) {
   const int x = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y;
   if (x >= W) return;
   const float* src = (const float*)(depth.p + (long long)y * depth.pitch) + x;
-  float* dst = (float*)(vz.p + (long long)y * vz.pitch) + x;
+  // tiles_x > 0: 8x4-texel tiles, 32 floats each (x is a multiple of 4, so the four texels stay inside one tile row)
+  float* dst = tiles_x > 0 ? (float*)vz.p + ((size_t)((y >> 2) * tiles_x + (x >> 3)) * 32 + ((y & 3) << 3) + (x & 7)) : (float*)(vz.p + (long long)y * vz.pitch) + x;
   float d[4];
   if (x + 3 < W) { const float4 t = __ldg((const float4*)src); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
   else { for (int i = 0; i < 4; i++) d[i] = x + i < W ? __ldg(src + i) : 0.0f; }
@@ -84,7 +85,7 @@ cudaError_t launch_viewz(const SsgiArgs& a, OutV vz, cudaStream_t s) {
   const int W = a.depth.w, H = a.depth.h;  // the depth plane's own size (larger than the render target when resolutionScale < 1)
   dim3 grid((W / 4 + 255) / 256 + 1, H);
   viewz_kernel<<<grid, 256, 0, s>>>(a.depth, vz, W, H, a.near_mul_far, a.far_minus_near, a.near_minus_far, a.cam.near_plane, a.cam.far_plane,
-                                    a.cam.perspective);
+                                    a.cam.perspective, a.vz_tiled ? a.vz_tiles_x : 0);
   return cudaGetLastError();
 }
 
@@ -589,6 +590,7 @@ RFX_D float tap_viewz(const SsgiArgs& a, v3 p) {
     t = mkf2(uv.x * (float)a.W, uv.y * (float)a.H);
   }
   const int ix = clamp_idx(__float2int_rd(f2lo(t)), a.W - 1), iy = clamp_idx(__float2int_rd(f2hi(t)), a.H - 1);
+  if (a.vz_tiled) return __ldg((const float*)a.viewz.p + (((iy >> 2) * a.vz_tiles_x + (ix >> 3)) * 32 + ((iy & 3) << 3) + (ix & 7)));
   return __ldg((const float*)a.viewz.p + (iy * a.vz_pitchw + ix));
 }
 RFX_D v3 fma3(v3 d, float s, v3 p) {

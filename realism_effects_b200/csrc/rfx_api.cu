@@ -53,6 +53,7 @@ struct rfx_ctx {
   int k3_tma = 1;     // RFX_K3_TMA=0 disables the TMA-staged tap tiles of the Poisson passes >= 1 (same bytes out; measured 0.39 vs 0.42 ms per pass at 4K)
   int k1_batch = 4;   // RFX_K1_BATCH: march steps fetched together (1, 2, 4); measured at 4K: 1.195 / 1.119 / 1.079 ms
   int compose_mode = 0;  // RFX_COMPOSE_MODE: arithmetic of the fused K4: 0 IEEE (default: 4.4e-4 of the 4K pixels outside 1e-3), 1 SFU, 2 SFU + Newton (both 6.9e-4, 0.06 ms faster)
+  int k1_vz_tiled = 0;  // RFX_K1_VZ_TILED=1: 8x4-tiled viewZ scratch for the fast K1 (experiment, profiles/r02_optimisation_log.txt)
   int legacy_k1 = 0;  // RFX_LEGACY_K1=1 in the environment: the round-1 fast K1 kernel (A/B timing)
   const PeerPV* peer_accumulated = nullptr;  // set by the native chain in a row-sharded group: K1's `accumulated` rows live on their owners
 };
@@ -91,6 +92,7 @@ rfx_status rfx_ctx_create(int device, rfx_ctx** out) {
   if (const char* e = getenv("RFX_LEGACY_K1")) ctx->legacy_k1 = atoi(e);
   if (const char* e = getenv("RFX_K3_TMA")) ctx->k3_tma = atoi(e);
   if (const char* e = getenv("RFX_K1_BATCH")) ctx->k1_batch = atoi(e);
+  if (const char* e = getenv("RFX_K1_VZ_TILED")) ctx->k1_vz_tiled = atoi(e);
   if (const char* e = getenv("RFX_COMPOSE_MODE")) ctx->compose_mode = atoi(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
@@ -467,7 +469,7 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     cudaFree(ctx->viewz);
     ctx->viewz = nullptr;
     ctx->viewz_pitch = ((size_t)TW * 4 + 255) & ~(size_t)255;
-    CU(cudaMalloc(&ctx->viewz, ctx->viewz_pitch * TH));
+    CU(cudaMalloc(&ctx->viewz, std::max(ctx->viewz_pitch * TH, (size_t)((TW + 7) / 8) * ((TH + 3) / 4) * 128)));  // row-major or 8x4 tiles
     ctx->viewz_w = TW; ctx->viewz_h = TH;
   }
   {  // fast fused kernel: projection rows in texel units (0.5 W P00, 0.5 W P20, 0.5 H P11, 0.5 H P21), word pitch of the viewZ plane
@@ -477,6 +479,8 @@ rfx_status rfx_ssgi_trace_launch(rfx_ctx* ctx, void* stream, const rfx_ssgi_para
     a.vz_pitchw = (int)(ctx->viewz_pitch / 4);
     a.legacy_fast = ctx->legacy_k1 || a.scaled;  // the fused fast kernel addresses texels by pixel index: a scaled target takes the general kernel
     a.march_batch = ctx->k1_batch;
+    a.vz_tiles_x = (TW + 7) / 8;
+    a.vz_tiled = ctx->k1_vz_tiled && a.fast && !a.legacy_fast && ctx->k1_phase == 0;  // only the fused fast kernel reads the tiled layout
     if (ctx->peer_accumulated) a.acc_peer = *ctx->peer_accumulated;
   }
   a.phase = a.scaled ? 0 : ctx->k1_phase;

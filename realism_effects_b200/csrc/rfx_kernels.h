@@ -148,6 +148,8 @@ struct SsgiArgs {
   // fast fused kernel (ssgi_fast_kernel)
   float ps_x0, ps_x2, ps_y1, ps_y2, ps_hw, ps_hh;  // projection rows scaled to texel units: tx = (ps_x0*x + ps_x2*z) / -z + ps_hw
   int vz_pitchw;             // viewZ pitch in 4-byte words
+  int vz_tiled;              // experiment (RFX_K1_VZ_TILED=1): the viewZ scratch is stored as 8x4-texel tiles (one 128-B line each) for the fast kernel's gathers
+  int vz_tiles_x;            // tiles per tile row
   int legacy_fast;           // 1: use the round-1 fast kernel (tools/ A/B comparisons)
   int scaled;                // the render target (W x H) is smaller than the input planes (resolutionScale < 1): texels are fetched by uv
   int march_batch;           // march steps fetched together before they are tested: 1, 2 or 4

@@ -19,6 +19,7 @@ does not touch `oracle/`.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -444,6 +445,19 @@ def build_env_cdf(data_f32: np.ndarray, flip_y: bool = False):
         cols = np.minimum(np.searchsorted(cdf_c[y].astype(np.float64), targets, side="left"), w - 1)
         conditional[y] = (cols + 0.5) / w
     return marginal, conditional, total
+
+
+def load_reference_env():
+    """The reference demo's environment (example/public/hdr/spree_bank_1k.hdr, example/main.js:278; asset made by tools/make_env_asset.py),
+    decoded the way three.js' RGBELoader decodes to HalfFloatType (RGBELoader.js: scale = 2^(e - 128) / 255, clamped to 65504, alpha 1).
+    Returns (image_f16, gl_f16): `image_f16` (H, W, 4) float16 in image-memory order (top scanline first: what `gatherData` reads, with
+    texture.flipY = true) and `gl_f16`, the same rows in GL texel order (row 0 = v 0 = straight down: what the sampler sees)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    rgbe = np.load(os.path.join(here, "assets", "spree_bank_1k_rgbe.npz"))["rgbe"]
+    scale = np.exp2(rgbe[..., 3].astype(np.float64) - 128.0) / 255.0
+    rgb = np.minimum(rgbe[..., :3].astype(np.float64) * scale[..., None], 65504.0)
+    img = np.concatenate([rgb, np.ones_like(rgb[..., :1])], -1).astype(np.float16)
+    return img, np.ascontiguousarray(img[::-1])
 
 
 def load_blue_noise() -> np.ndarray:

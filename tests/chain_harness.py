@@ -78,7 +78,8 @@ class Inputs:
     blue: np.ndarray
 
 
-def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_size=(128, 64), device="cpu") -> Inputs:
+def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_size=(128, 64), device="cpu", reference_env=False) -> Inputs:
+    """reference_env: use the reference demo's environment map (synth.load_reference_env) instead of the small analytic sky"""
     frames = []
     for t in range(n_frames):
         fr = synth.render_frame(width, height, t, device=device, static=static)
@@ -86,8 +87,12 @@ def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_siz
         moved = (t > 0) and not static
         frames.append(dict(depth=fr.depth.cpu().numpy(), gbuffer=fr.gbuffer.cpu().numpy(), velocity=fr.velocity.cpu().numpy(),
                            direct=fr.direct_light.cpu().numpy(), cam=u, moved=moved))
-    env = synth.synthetic_env(*env_size)
-    marg, cond, total = synth.build_env_cdf(env.astype(np.float32), flip_y=False)
+    if reference_env:
+        img, env = synth.load_reference_env()
+        marg, cond, total = synth.build_env_cdf(img.astype(np.float32), flip_y=True)
+    else:
+        env = synth.synthetic_env(*env_size)
+        marg, cond, total = synth.build_env_cdf(env.astype(np.float32), flip_y=False)
     return Inputs(width, height, frames, env, marg, cond, total, synth.load_blue_noise())
 
 
