@@ -474,6 +474,14 @@ typedef struct rfx_group rfx_group;
 #define RFX_GROUP_ID_BYTES 128
 rfx_status rfx_group_get_unique_id(void* id128);   /* rank 0; hand the 128 bytes to the other ranks by any means */
 rfx_status rfx_group_create(rfx_ctx* ctx, const void* id128, int32_t rank, int32_t world, rfx_group** out);  /* collective */
+/* The same group without NCCL / CUDA IPC: `world` members that live in ONE process (one context each — on one device or on several
+ * devices with peer access — or all on the same context).  Create every member with rfx_group_create_inprocess, give every member a
+ * fast SSGI chain with identical options, then attach them all at once: the members read each other's history planes through plain
+ * device pointers.  The host renders a frame by calling rfx_ssgi_chain_render_sharded for every member (any order, same stream or
+ * streams it orders itself) before any member starts the next frame.  Bands are static unless moved with rfx_group_set_bounds.
+ * Besides single-process multi-GPU hosts, this is what lets a 1-GPU box exercise the N-band logic (tests/test_gpu_chain.py). */
+rfx_status rfx_group_create_inprocess(rfx_ctx* ctx, int32_t rank, int32_t world, rfx_group** out);
+rfx_status rfx_group_attach_chains_inprocess(rfx_group* const* groups, rfx_ssgi_chain* const* chains, int32_t world);
 void rfx_group_destroy(rfx_group* group);
 int32_t rfx_group_rank(const rfx_group* group);
 int32_t rfx_group_world(const rfx_group* group);

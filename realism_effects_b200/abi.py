@@ -224,6 +224,8 @@ def _sig(lib):
     U32P = _P(C.c_uint32)
     lib.rfx_group_get_unique_id.argtypes = [vp]
     lib.rfx_group_create.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, _P(vp)]
+    lib.rfx_group_create_inprocess.argtypes = [vp, C.c_int32, C.c_int32, _P(vp)]
+    lib.rfx_group_attach_chains_inprocess.argtypes = [_P(vp), _P(vp), C.c_int32]
     lib.rfx_group_destroy.argtypes = [vp]
     lib.rfx_group_destroy.restype = None
     lib.rfx_group_rank.argtypes = [vp]
@@ -252,7 +254,7 @@ EXPORTS = [
     "rfx_ssgi_chain_reset", "rfx_ssgi_chain_render", "rfx_ssgi_chain_output", "rfx_ssgi_chain_render_host",
     "rfx_ssgi_chain_submit_host", "rfx_ssgi_chain_wait_host", "rfx_ssgi_chain_render_part",
     "rfx_ssgi_chain_set_profiling", "rfx_ssgi_chain_get_profile", "rfx_ssgi_chain_set_options", "rfx_ssgi_chain_render_ranges", "rfx_ssgi_chain_render_blocks",
-    "rfx_plane_download_rows", "rfx_group_get_unique_id", "rfx_group_create", "rfx_group_destroy", "rfx_group_rank", "rfx_group_world", "rfx_group_uses_peer_reads",
+    "rfx_plane_download_rows", "rfx_group_get_unique_id", "rfx_group_create", "rfx_group_create_inprocess", "rfx_group_attach_chains_inprocess", "rfx_group_destroy", "rfx_group_rank", "rfx_group_world", "rfx_group_uses_peer_reads",
     "rfx_group_attach_chain", "rfx_group_get_bounds", "rfx_group_set_bounds", "rfx_group_set_rebalance", "rfx_group_last_costs",
     "rfx_group_begin_frame", "rfx_group_get_last_bounds", "rfx_group_allgather_rows", "rfx_ssgi_chain_render_sharded", "rfx_shard_ranges",
     "rfx_shard_rebalance",

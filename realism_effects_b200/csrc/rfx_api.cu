@@ -53,6 +53,7 @@ struct rfx_ctx {
   int k3_tma = 1;     // RFX_K3_TMA=0 disables the TMA-staged tap tiles of the Poisson passes >= 1 (same bytes out; measured 0.39 vs 0.42 ms per pass at 4K)
   int k1_batch = 4;   // RFX_K1_BATCH: march steps fetched together (1, 2, 4); measured at 4K: 1.195 / 1.119 / 1.079 ms
   int compose_mode = 0;  // RFX_COMPOSE_MODE: arithmetic of the fused K4: 0 IEEE (default: 4.4e-4 of the 4K pixels outside 1e-3), 1 SFU, 2 SFU + Newton (both 6.9e-4, 0.06 ms faster)
+  int debug_no_a_carry = 0;  // RFX_DEBUG_NO_A_CARRY=1: groups leave discarded texels of the A target as they are (the pre-fix behaviour; shows what tests/test_gpu_chain.py's in-process group test catches)
   int k1_vz_tiled = 0;  // RFX_K1_VZ_TILED=1: 8x4-tiled viewZ scratch for the fast K1 (experiment, profiles/r02_optimisation_log.txt)
   int legacy_k1 = 0;  // RFX_LEGACY_K1=1 in the environment: the round-1 fast K1 kernel (A/B timing)
   const PeerPV* peer_accumulated = nullptr;  // set by the native chain in a row-sharded group: K1's `accumulated` rows live on their owners
@@ -93,6 +94,7 @@ rfx_status rfx_ctx_create(int device, rfx_ctx** out) {
   if (const char* e = getenv("RFX_K3_TMA")) ctx->k3_tma = atoi(e);
   if (const char* e = getenv("RFX_K1_BATCH")) ctx->k1_batch = atoi(e);
   if (const char* e = getenv("RFX_K1_VZ_TILED")) ctx->k1_vz_tiled = atoi(e);
+  if (const char* e = getenv("RFX_DEBUG_NO_A_CARRY")) ctx->debug_no_a_carry = atoi(e);
   if (const char* e = getenv("RFX_COMPOSE_MODE")) ctx->compose_mode = atoi(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
@@ -807,10 +809,10 @@ struct rfx_ssgi_chain {
   // fast chain (fast_math on at creation, mode SSGI): interleaved internal planes; history planes are double-buffered by frame
   // parity so that, in a row-sharded group, no rank overwrites rows a peer may still be reading (see rfx_group_*)
   bool fastpath = false;
-  IPlane nrdz, tr32, dnA16, dnB16[2];
+  IPlane nrdz, tr32, dnA16[2], dnB16[2];  // dnA16[1] is used by row-sharded groups only (the A target double-buffered like B, see chain_render_fast)
   rfx_plane composed2[2]{};  // fast chain: composed of frame parity 0 / 1 (composed2[cur] is output 0)
   struct rfx_group* group = nullptr;  // row-sharded group this chain is attached to (rfx_group_attach_chain)
-  PeerPV peer_composed[2]{}, peer_dn[2]{};
+  PeerPV peer_composed[2]{}, peer_dn[2]{}, peer_dnA[2]{};
   uint64_t frame_idx = 0;    // frames completed (advances with the frame's last launch)
   bool views_valid = false;  // tr[]/dnB[] hold the split views of the current frame's interleaved planes
   // host-buffer entry points: two staging sets so frame i+1 uploads while frame i renders; H2D, kernels and D2H each get
@@ -882,7 +884,7 @@ rfx_status rfx_ssgi_chain_create(rfx_ctx* ctx, const rfx_ssgi_chain_options* opt
   if (st == RFX_OK) st = rfx_plane_alloc(ctx, RFX_FMT_RGBA32F, sw, sh, &ch->ssgi_out);
   if (opt->denoise_mode != RFX_DENOISE_FULL) alloc(RFX_FMT_RGBA32F, &ch->fb);
   if (ch->fastpath) {
-    ialloc(16, &ch->nrdz); ialloc(32, &ch->tr32); ialloc(16, &ch->dnA16); ialloc(16, &ch->dnB16[0]); ialloc(16, &ch->dnB16[1]);
+    ialloc(16, &ch->nrdz); ialloc(32, &ch->tr32); ialloc(16, &ch->dnA16[0]); ialloc(16, &ch->dnA16[1]); ialloc(16, &ch->dnB16[0]); ialloc(16, &ch->dnB16[1]);
     alloc(RFX_FMT_RGBA32F, &ch->composed2[0]); alloc(RFX_FMT_RGBA32F, &ch->composed2[1]);
   } else {
     for (int i = 0; i < 2; i++) { alloc(RFX_FMT_RGBA32F, &ch->tr[i]); alloc(RFX_FMT_RGBA16F, &ch->dnA[i]); alloc(RFX_FMT_RGBA16F, &ch->dnB[i]); }
@@ -903,7 +905,7 @@ void rfx_ssgi_chain_destroy(rfx_ssgi_chain* ch) {
                       &ch->in_depth[0], &ch->in_gb[0], &ch->in_vel[0], &ch->in_direct[0], &ch->in_depth[1], &ch->in_gb[1], &ch->in_vel[1], &ch->in_direct[1]};
   for (rfx_plane* p : all) if (p->ptr) rfx_plane_free(ctx, p);
   for (rfx_plane* p : {&ch->composed2[0], &ch->composed2[1]}) if (p->ptr) rfx_plane_free(ctx, p);
-  for (IPlane* p : {&ch->nrdz, &ch->tr32, &ch->dnA16, &ch->dnB16[0], &ch->dnB16[1]}) if (p->p) cudaFree(p->p);
+  for (IPlane* p : {&ch->nrdz, &ch->tr32, &ch->dnA16[0], &ch->dnA16[1], &ch->dnB16[0], &ch->dnB16[1]}) if (p->p) cudaFree(p->p);
   for (int i = 0; i < 2; i++) for (cudaEvent_t e : {ch->ev_up[i], ch->ev_rendered[i], ch->ev_dn[i]}) if (e) cudaEventDestroy(e);
   if (ch->s_up) cudaStreamDestroy(ch->s_up);
   if (ch->s_dn) cudaStreamDestroy(ch->s_dn);
@@ -1137,9 +1139,15 @@ static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_
     if ((st = decode(a.segs)) != RFX_OK) return st;  // the first pass of a frame has the widest rows of all its passes
     a.nrdz = ipv(ch->nrdz, W, H);
     a.first = i == 0;
-    a.in = i == 0 ? ipv(ch->tr32, W, H) : ipv(horizontal ? ch->dnB16[cur] : ch->dnA16, W, H);
-    a.out = iov(horizontal ? ch->dnA16 : ch->dnB16[cur]);
+    // Target A (even passes).  A `discard`ed pixel keeps its texel = last frame's LAST even pass there (A2), and the LINEAR taps of the next
+    // pass read such texels at silhouettes.  One GPU: A is single-buffered and a discard is simply no write.  In a row-sharded group a
+    // rank's A rows outside its band hold the result of whichever even pass last covered them (the ranges shrink pass by pass), not the
+    // last one's, so A is double-buffered by frame parity like B and the discarded texel is carried from the rank that OWNS the row.
+    const int acur = ch->group ? cur : 0;
+    a.in = i == 0 ? ipv(ch->tr32, W, H) : ipv(horizontal ? ch->dnB16[cur] : ch->dnA16[acur], W, H);
+    a.out = iov(horizontal ? ch->dnA16[acur] : ch->dnB16[cur]);
     if (!horizontal) { if (ch->group) a.carry = ch->peer_dn[prev]; else peer_single(a.carry, ipv(ch->dnB16[prev], W, H)); }
+    else if (ch->group && !ctx->debug_no_a_carry) a.carry = ch->peer_dnA[prev];
     a.W = W; a.H = H;
     a.radius = o.radius; a.phi = o.phi; a.luma_phi = o.luma_phi; a.depth_phi = o.depth_phi; a.normal_phi = o.normal_phi;
     a.roughness_phi = o.roughness_phi; a.specular_phi = o.specular_phi;

@@ -171,6 +171,7 @@ struct rfx_group {
   uint64_t frame = 0;
   bool began = false;  // begin_frame already ran for the frame about to be rendered
   bool use_peer = true;  // history rows read in place on their owner (CUDA IPC); false: replicated by an NCCL exchange after every frame
+  bool inprocess = false;  // every member lives in this process: plain device pointers, no NCCL, the host orders the frames
   bool use_flags = false;  // frame barrier through peer-memory flags instead of the NCCL all-gather (RFX_GROUP_BARRIER=flags; needs use_peer)
   unsigned long long* d_sync = nullptr;  // [2][RFX_MAX_PEERS] slots by frame parity: rank r's (frame, ms) word, written by rank r
   SyncPeers sync_peers{};
@@ -224,6 +225,68 @@ rfx_status rfx_group_create(rfx_ctx* ctx, const void* id128, int32_t rank, int32
   return RFX_OK;
 }
 
+rfx_status rfx_group_create_inprocess(rfx_ctx* ctx, int32_t rank, int32_t world, rfx_group** out) {
+  if (!ctx || !out || world < 1 || world > RFX_MAX_PEERS || rank < 0 || rank >= world) return fail(ctx, RFX_ERR_INVALID_ARG, "group_create_inprocess: bad arguments (world <= %d)", RFX_MAX_PEERS);
+  *out = nullptr;
+  CU(cudaSetDevice(ctx->device));
+  rfx_group* g = new rfx_group();
+  g->ctx = ctx; g->rank = rank; g->world = world; g->inprocess = true;
+  bool ok = cudaMalloc(&g->d_t0, 8) == cudaSuccess && cudaMalloc(&g->d_ms, sizeof(float) * (1 + world)) == cudaSuccess &&
+            cudaMemset(g->d_ms, 0, sizeof(float) * (1 + world)) == cudaSuccess &&
+            cudaHostAlloc(&g->h_ms, sizeof(float) * RFX_GROUP_RING * world, cudaHostAllocDefault) == cudaSuccess;
+  for (int i = 0; i < RFX_GROUP_RING && ok; i++) ok = cudaEventCreateWithFlags(&g->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { rfx_group_destroy(g); return fail(ctx, RFX_ERR_CUDA, "group_create_inprocess: allocation failed"); }
+  *out = g;
+  return RFX_OK;
+}
+
+// Attaches chains[r] to groups[r] for every member at once: the peer tables hold the members' own device pointers.
+rfx_status rfx_group_attach_chains_inprocess(rfx_group* const* groups, rfx_ssgi_chain* const* chains, int32_t world) {
+  if (!groups || !chains || world < 1 || world > RFX_MAX_PEERS) return RFX_ERR_INVALID_ARG;
+  for (int r = 0; r < world; r++) {
+    rfx_group* g = groups[r];
+    rfx_ssgi_chain* ch = chains[r];
+    if (!g || !ch) return RFX_ERR_INVALID_ARG;
+    rfx_ctx* ctx = g->ctx;
+    if (!g->inprocess || g->world != world || g->rank != r) return fail(ctx, RFX_ERR_INVALID_ARG, "group_attach_chains_inprocess: member %d is not an in-process member of rank %d / world %d", r, r, world);
+    if (ch->ctx != ctx) return fail(ctx, RFX_ERR_INVALID_ARG, "group_attach_chains_inprocess: chain %d belongs to another context", r);
+    if (!ch->fastpath) return fail(ctx, RFX_ERR_UNSUPPORTED, "group_attach_chains_inprocess: row-sharded groups need the fast SSGI chain (fast_math on, mode SSGI)");
+    if (g->chain || ch->group) return fail(ctx, RFX_ERR_INVALID_ARG, "group_attach_chains_inprocess: already attached");
+    if (ch->opt.width != chains[0]->opt.width || ch->opt.height != chains[0]->opt.height) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "group_attach_chains_inprocess: chain sizes differ");
+    if ((int)ch->opt.height < world * 64) return fail(ctx, RFX_ERR_UNSUPPORTED, "group_attach_chains_inprocess: need at least 64 rows per rank");
+  }
+  const int W = (int)chains[0]->opt.width, H = (int)chains[0]->opt.height, n = world;
+  for (int r = 0; r < n; r++) {
+    rfx_group* g = groups[r];
+    rfx_ssgi_chain* ch = chains[r];
+    for (int b = 0; b < 2; b++) {
+      PeerPV& pc = ch->peer_composed[b];
+      pc = PeerPV{};
+      pc.local = PV{(const unsigned char*)ch->composed2[b].ptr, W, H, (long long)ch->composed2[b].pitch};
+      PeerPV& pd = ch->peer_dn[b];
+      pd = PeerPV{};
+      pd.local = PV{(const unsigned char*)ch->dnB16[b].p, W, H, (long long)ch->dnB16[b].pitch};
+      PeerPV& pa = ch->peer_dnA[b];
+      pa = PeerPV{};
+      pa.local = PV{(const unsigned char*)ch->dnA16[b].p, W, H, (long long)ch->dnA16[b].pitch};
+      pc.n = pd.n = pa.n = n;
+      for (int q = 0; q < n; q++) {
+        pc.base[q] = (const unsigned char*)chains[q]->composed2[b].ptr; pd.base[q] = (const unsigned char*)chains[q]->dnB16[b].p;
+        pa.base[q] = (const unsigned char*)chains[q]->dnA16[b].p;
+      }
+    }
+    g->use_peer = true;
+    g->use_flags = false;
+    g->bounds.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) g->bounds[i] = (uint32_t)(std::lround((double)H * i / n / 16.0) * 16);
+    g->bounds[n] = (uint32_t)H;
+    for (auto& bb : g->bounds_ring) bb = g->bounds;
+    g->chain = ch;
+    ch->group = g;
+  }
+  return RFX_OK;
+}
+
 void rfx_group_destroy(rfx_group* g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
@@ -258,8 +321,8 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     CU(cudaMalloc(&g->d_err, sizeof(int)));
     CU(cudaMemset(g->d_err, 0, sizeof(int)));
   }
-  constexpr int NH = 5;  // exported allocations per rank: composed x2, dn x2, the flag array
-  void* mine[NH] = {ch->composed2[0].ptr, ch->composed2[1].ptr, ch->dnB16[0].p, ch->dnB16[1].p, g->d_sync};
+  constexpr int NH = 7;  // exported allocations per rank: composed x2, dn (B) x2, the flag array, dn (A) x2
+  void* mine[NH] = {ch->composed2[0].ptr, ch->composed2[1].ptr, ch->dnB16[0].p, ch->dnB16[1].p, g->d_sync, ch->dnA16[0].p, ch->dnA16[1].p};
   std::vector<void*> all((size_t)NH * n, nullptr);
   if (n > 1) {
     std::vector<cudaIpcMemHandle_t> hs((size_t)NH * n);
@@ -309,8 +372,14 @@ rfx_status rfx_group_attach_chain(rfx_group* g, rfx_ssgi_chain* ch) {
     PeerPV& pd = ch->peer_dn[b];
     pd = PeerPV{};
     pd.local = PV{(const unsigned char*)ch->dnB16[b].p, W, H, (long long)ch->dnB16[b].pitch};
-    pc.n = pd.n = g->use_peer ? n : 1;
-    for (int r = 0; r < n; r++) { pc.base[r] = (const unsigned char*)all[(size_t)r * NH + b]; pd.base[r] = (const unsigned char*)all[(size_t)r * NH + 2 + b]; }
+    PeerPV& pa = ch->peer_dnA[b];
+    pa = PeerPV{};
+    pa.local = PV{(const unsigned char*)ch->dnA16[b].p, W, H, (long long)ch->dnA16[b].pitch};
+    pc.n = pd.n = pa.n = g->use_peer ? n : 1;
+    for (int r = 0; r < n; r++) {
+      pc.base[r] = (const unsigned char*)all[(size_t)r * NH + b]; pd.base[r] = (const unsigned char*)all[(size_t)r * NH + 2 + b];
+      pa.base[r] = (const unsigned char*)all[(size_t)r * NH + 5 + b];
+    }
   }
   g->sync_peers.n = n;
   for (int r = 0; r < n; r++) g->sync_peers.slots[r] = (unsigned long long*)all[(size_t)r * NH + 4];
@@ -361,7 +430,7 @@ rfx_status rfx_group_begin_frame(rfx_group* g, uint32_t* bounds_out) {
   if (!g->began) {
     g->began = true;
     // cost-driven borders (deterministic on every rank: same gathered times, same arithmetic)
-    if (g->rebalance_every > 0 && g->frame >= (uint64_t)g->rebalance_lag && g->frame % (uint64_t)g->rebalance_every == 0) {
+    if (!g->inprocess && g->rebalance_every > 0 && g->frame >= (uint64_t)g->rebalance_lag && g->frame % (uint64_t)g->rebalance_every == 0) {
       const uint64_t src = g->frame - (uint64_t)g->rebalance_lag;
       const int slot = (int)(src % RFX_GROUP_RING);
       if (g->ev_valid[slot]) {
@@ -417,7 +486,7 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
   const int cur = (int)(ch->frame_idx & 1), prev = cur ^ 1;
   // owners of the data this frame READS (last frame's bands) and of the rows it carries forward
   const std::vector<uint32_t>& pb = g->bounds_ring[(g->frame + RFX_GROUP_RING - 1) % RFX_GROUP_RING];
-  for (PeerPV* p : {&ch->peer_composed[prev], &ch->peer_dn[prev]}) {
+  for (PeerPV* p : {&ch->peer_composed[prev], &ch->peer_dn[prev], &ch->peer_dnA[prev]}) {
     for (int i = 0; i <= n; i++) p->bound[i] = (int)pb[i];
     p->own0 = (int)pb[g->rank]; p->own1 = (int)pb[g->rank + 1];
     if (g->frame == 0 || !g->use_peer) { p->own0 = 0; p->own1 = (int)ch->opt.height; }  // nothing rendered yet (all zero) / replicated planes: every row is local
@@ -441,9 +510,12 @@ rfx_status rfx_ssgi_chain_render_sharded(rfx_ssgi_chain* ch, void* stream, const
     dnp.ptr = ch->dnB16[cur].p; dnp.width = ch->opt.width; dnp.height = ch->opt.height; dnp.pitch = ch->dnB16[cur].pitch; dnp.format = RFX_FMT_RGBA32F;
     if ((st = rfx_group_allgather_rows(g, stream, &ch->composed2[cur], g->bounds.data())) != RFX_OK) return st;
     if ((st = rfx_group_allgather_rows(g, stream, &dnp, g->bounds.data())) != RFX_OK) return st;
+    dnp.ptr = ch->dnA16[cur].p; dnp.pitch = ch->dnA16[cur].pitch;  // the A target's rows too: discarded texels are carried from them (chain_render_fast)
+    if ((st = rfx_group_allgather_rows(g, stream, &dnp, g->bounds.data())) != RFX_OK) return st;
   }
   const int slot = (int)(g->frame % RFX_GROUP_RING);
-  if (!g->use_flags) NC(nccl_api()->AllGather(g->d_ms, g->d_ms + 1, 1, ncclFloat, g->comm, cs));  // every rank's frame is complete when this completes
+  if (g->inprocess) CU(cudaMemcpyAsync(g->d_ms + 1 + g->rank, g->d_ms, sizeof(float), cudaMemcpyDeviceToDevice, cs));  // the host orders the members' frames; only this member's cost is known here
+  else if (!g->use_flags) NC(nccl_api()->AllGather(g->d_ms, g->d_ms + 1, 1, ncclFloat, g->comm, cs));  // every rank's frame is complete when this completes
   CU(cudaMemcpyAsync(g->h_ms + (size_t)slot * n, g->d_ms + 1, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, cs));
   CU(cudaEventRecord(g->ev[slot], cs));
   g->ev_valid[slot] = true;

@@ -390,3 +390,64 @@ class ShardedSsgiChain:
             self.lib.rfx_group_destroy(self.g)
             self.g = None
         self.chain.close()
+
+
+class InProcessGroup:
+    """`world` members of a row-sharded group inside ONE process (rfx_group_create_inprocess / rfx_group_attach_chains_inprocess): every member
+    owns a fast SSGI chain and a band; the members read each other's history planes through plain device pointers.  With one context this
+    renders the bands one after the other on one GPU — the N-band logic (halo recomputation, owner lookup of history rows, carried texels,
+    moving borders) without N GPUs; with one context per device it is a single-process multi-GPU host."""
+
+    def __init__(self, ctxs, chain_options, world: int):
+        import ctypes as C
+
+        from . import abi, engine
+
+        self._C, self.world = C, world
+        self.ctxs = list(ctxs) if isinstance(ctxs, (list, tuple)) else [ctxs] * world
+        assert len(self.ctxs) == world
+        self.lib = self.ctxs[0].lib
+        self.chains = [engine.SsgiChain(c, chain_options) for c in self.ctxs]
+        self.groups = []
+        for r, c in enumerate(self.ctxs):
+            g = C.c_void_p()
+            c._chk(self.lib.rfx_group_create_inprocess(c.h, r, world, C.byref(g)))
+            self.groups.append(g)
+        ga = (C.c_void_p * world)(*[g.value for g in self.groups])
+        ca = (C.c_void_p * world)(*[ch.h.value if hasattr(ch.h, "value") else ch.h for ch in self.chains])
+        self.ctxs[0]._chk(self.lib.rfx_group_attach_chains_inprocess(ga, ca, world))
+
+    @property
+    def bounds(self) -> tuple:
+        b = (self._C.c_uint32 * (self.world + 1))()
+        self.ctxs[0]._chk(self.lib.rfx_group_get_bounds(self.groups[0], b))
+        return tuple(int(x) for x in b)
+
+    def set_bounds(self, bounds):
+        """new borders for the next frame (every member gets the same ones)"""
+        b = (self._C.c_uint32 * (self.world + 1))(*[int(x) for x in bounds])
+        for c, g in zip(self.ctxs, self.groups):
+            c._chk(self.lib.rfx_group_set_bounds(g, b))
+
+    def render(self, cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved: bool):
+        """one frame: every member renders its band; all of them finish before the next frame starts (the host is the barrier)"""
+        self._last_bounds = self.bounds
+        for c, ch in zip(self.ctxs, self.chains):
+            f = ch._frame(cam, depth, gbuffer, velocity, direct_light, camera_pos, camera_moved)
+            c._chk(self.lib.rfx_ssgi_chain_render_sharded(ch.h, None, self._C.byref(f)))
+        for c in set(self.ctxs):
+            c.sync()
+
+    def download(self, which: int = 0):
+        """output `which` of the last frame, assembled from the members' bands"""
+        import numpy as np
+
+        b = self._last_bounds
+        return np.concatenate([ch.download(which)[b[r]:b[r + 1]] for r, ch in enumerate(self.chains)], axis=0)
+
+    def close(self):
+        for c, g in zip(self.ctxs, self.groups):
+            c.sync()
+            self.lib.rfx_group_destroy(g)
+        for ch in self.chains:
+            ch.close()

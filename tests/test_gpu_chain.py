@@ -212,3 +212,48 @@ def test_chain_resolution_scale(built, mode, scale):
                 assert a.shape == b.shape, (k, a.shape, b.shape)
                 c = ch.compare(a, b, packed=(k == "ssgi" and mode == abi.MODE_SSGI))
                 assert c["frac_bad"] <= (8e-3 if fast else 1e-3), (fast, t, k, c)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 5])
+def test_inprocess_group_of_n_bands_is_bit_identical_to_one_chain(built, world):
+    """The row-sharded group's N-band logic on ONE GPU (rfx_group_create_inprocess): every member renders its band with the halo rows recomputed
+    locally and reads last frame's history rows on the member that owns them; the assembled frame — every plane — equals the plain chain byte for
+    byte over 5 frames, with the band borders moved twice (so rows change owner and carried texels / history come from another member)."""
+    from realism_effects_b200 import engine, parallel
+
+    W, H = 320, 64 * world + 112
+    o = ch.Opts(denoise_iterations=2)
+    inp = ch.make_inputs(W, H, 5, fov=75.0)  # a wide view: the sky's silhouette (discarded pixels next to shaded ones) crosses the band borders
+    bg = inp.frames[0]["depth"] == 1.0
+    assert 0.15 < bg.mean() < 0.7
+    ctx = engine.Context(0, inp.blue)
+    try:
+        ctx.set_env(inp.env_map, inp.env_marginal, inp.env_conditional, inp.env_total)
+        copt = ch.chain_options(inp, o)
+        single = engine.SsgiChain(ctx, copt)
+        grp = parallel.InProcessGroup(ctx, copt, world)
+        b = list(grp.bounds)
+        assert b[0] == 0 and b[-1] == H and len(b) == world + 1
+        if world >= 3:  # at least one interior border runs through the silhouette (rows with both discarded and shaded pixels within the halos)
+            assert any(0.0 < bg[max(0, x - 20):x + 20].mean() < 1.0 for x in b[1:-1])
+        for t, fr in enumerate(inp.frames):
+            if t == 2:  # move every interior border down by 16 rows, then (t == 4) up by 32
+                grp.set_bounds([0] + [x + 16 for x in b[1:-1]] + [H])
+            if t == 4:
+                grp.set_bounds([0] + [x - 16 for x in b[1:-1]] + [H])
+            planes = [ctx.upload(fr[k]) for k in ("depth", "gbuffer", "velocity", "direct")]
+            cam = abi.make_camera(fr["cam"])
+            single.render(cam, *planes, fr["cam"]["position"], fr["moved"])
+            grp.render(cam, *planes, fr["cam"]["position"], fr["moved"])
+            for which, name in ((0, "composed"), (1, "ssgi"), (4, "dn0"), (5, "dn1")):
+                a, g = single.download(which), grp.download(which)
+                if a.tobytes() != g.tobytes():
+                    ne = (a.view(np.uint8).reshape(H, -1) != g.view(np.uint8).reshape(H, -1)).any(1)
+                    rows = np.nonzero(ne)[0]
+                    raise AssertionError(f"world {world} frame {t} {name}: rows {rows[0]}..{rows[-1]} differ ({len(rows)} rows); bounds {grp._last_bounds}")
+            for p in planes:
+                p.free()
+        grp.close()
+        single.close()
+    finally:
+        ctx.close()
