@@ -214,7 +214,7 @@ def test_chain_resolution_scale(built, mode, scale):
                 assert c["frac_bad"] <= (8e-3 if fast else 1e-3), (fast, t, k, c)
 
 
-@pytest.mark.parametrize("world", [2, 3, 4, 5])
+@pytest.mark.parametrize("world", [2, 3, 4, 5, 8])
 def test_inprocess_group_of_n_bands_is_bit_identical_to_one_chain(built, world):
     """The row-sharded group's N-band logic on ONE GPU (rfx_group_create_inprocess): every member renders its band with the halo rows recomputed
     locally and reads last frame's history rows on the member that owns them; the assembled frame — every plane — equals the plain chain byte for
