@@ -256,6 +256,19 @@ rfx_status rfx_group_attach_chains_inprocess(rfx_group* const* groups, rfx_ssgi_
     if ((int)ch->opt.height < world * 64) return fail(ctx, RFX_ERR_UNSUPPORTED, "group_attach_chains_inprocess: need at least 64 rows per rank");
   }
   const int W = (int)chains[0]->opt.width, H = (int)chains[0]->opt.height, n = world;
+  for (int r = 0; r < n; r++)  // members on different devices dereference each other's pointers: peer access both ways
+    for (int q = 0; q < n; q++) {
+      const int dr = groups[r]->ctx->device, dq = groups[q]->ctx->device;
+      if (dr == dq) continue;
+      rfx_ctx* ctx = groups[r]->ctx;
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, dr, dq));
+      if (!can) return fail(ctx, RFX_ERR_UNSUPPORTED, "group_attach_chains_inprocess: device %d cannot access device %d (use one process per GPU: rfx_group_create)", dr, dq);
+      CU(cudaSetDevice(dr));
+      const cudaError_t e = cudaDeviceEnablePeerAccess(dq, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, RFX_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", dr, dq, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
   for (int r = 0; r < n; r++) {
     rfx_group* g = groups[r];
     rfx_ssgi_chain* ch = chains[r];

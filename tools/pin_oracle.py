@@ -33,7 +33,7 @@ PLANES = ("ssgi", "tr0", "tr1", "dn0", "dn1", "composed")
 
 def _bits(a):
     a = np.ascontiguousarray(a)
-    return a.view(np.uint16) if a.dtype == np.float16 else a.view(np.uint32)
+    return a.view(np.uint16) if a.dtype == np.float16 else (a if a.dtype == np.uint8 else a.view(np.uint32))
 
 
 def diff(a, b) -> dict:
@@ -56,6 +56,9 @@ CHAIN_CASES = {
     "ssgi_full_temporal": (64, 48, 3, dict(denoise_mode=abi.DENOISE_FULL_TEMPORAL), {}),
     "ssgi_temporal": (64, 48, 3, dict(denoise_mode=abi.DENOISE_TEMPORAL), {}),
     "ssr_full_temporal": (64, 48, 3, dict(mode=abi.MODE_SSR, denoise_mode=abi.DENOISE_FULL_TEMPORAL), {}),
+    "ssgi_scale_0.5": (96, 56, 3, dict(resolution_scale=0.5), {}),
+    "ssgi_scale_0.75": (96, 56, 2, dict(resolution_scale=0.75), {}),
+    "ssr_scale_0.5": (96, 56, 2, dict(mode=abi.MODE_SSR, resolution_scale=0.5), {}),
 }
 
 
@@ -151,6 +154,11 @@ def run_effect_cases(golden: bool):
         return outs
 
     both("ssgi_compose", k5)
+
+    # cosmetic effects (EffectPass merges) and TAAPass
+    both("cosmetic_effects", lambda m: [m.effects(ch.fx_params(f1["cam"], effs, sp), f1["direct"], f1["depth"], f1["velocity"]) for effs, sp in ch.FX_CASES])
+    hist = np.random.default_rng(1).integers(0, 256, (H, W, 4), dtype=np.uint8)
+    both("taa_pass", lambda m: [m.taa(p, f1["direct"], hist) for p in ch.taa_cases()])
     if golden:
         os.makedirs(GOLDEN_DIR, exist_ok=True)
         np.savez_compressed(os.path.join(GOLDEN_DIR, "effects.npz"), **rec)
