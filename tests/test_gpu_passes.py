@@ -298,8 +298,11 @@ def test_abi_error_behaviour(built):
             c.ssgi_trace(p, d, d, None, None, None, out)
         small = c.alloc(abi.FMT_RGBA32F, 32, 32)
         p.flags = 0
-        with pytest.raises(abi.RfxError, match="match the output size"):
+        with pytest.raises(abi.RfxError, match="must have one size"):   # the INPUT planes share one size ...
             c.ssgi_trace(p, d, small, None, None, None, out)
+        big = c.alloc(abi.FMT_RGBA32F, 128, 64)
+        with pytest.raises(abi.RfxError, match="not larger"):           # ... and the target may be smaller (resolutionScale < 1), never larger
+            c.ssgi_trace(p, d, g, None, None, None, big)
         pp = ch.poisson_params(ch.Opts(), 3, True)
         h = c.alloc(abi.FMT_RGBA16F, 64, 32)
         with pytest.raises(abi.RfxError, match="in-place"):
