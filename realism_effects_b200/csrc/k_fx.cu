@@ -18,7 +18,6 @@ namespace {
 
 RFX_D float sincr(float x) { return (float)sin((double)x); }
 RFX_D float powcr(float x, float y) { return (float)pow((double)x, (double)y); }
-RFX_D float expcr(float x) { return (float)exp((double)x); }
 RFX_D v4 add4(v4 a, v4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // SharpnessEffect.js:8-29
@@ -131,9 +130,12 @@ __global__ void __launch_bounds__(256) effects_kernel(const __grid_constant__ Ef
 }
 
 // three r151 LinearTosRGB (encodings_pars_fragment)
+// EXACT = false: v^0.41666 on the SFU (ex2(0.41666 * lg2(v)), relative error ~1e-6, i.e. < 3e-4 of an 8-bit step — two orders inside the
+// tie window that triggers the exact re-evaluation below)
 template <bool EXACT>
 RFX_D float linear_to_srgb(float v) {
-  const float hi = (EXACT ? powcr(v, 0.41666f) : powf(v, 0.41666f)) * 1.055f - 0.055f, lo = v * 12.92f;
+  const float pw = EXACT ? powcr(v, 0.41666f) : (v > 0.0f ? fx_ex2(0.41666f * fx_lg2(v)) : 0.0f);
+  const float hi = pw * 1.055f - 0.055f, lo = v * 12.92f;
   return mixf(hi, lo, v <= 0.0031308f ? 1.0f : 0.0f);
 }
 template <bool EXACT>

@@ -775,13 +775,11 @@ rfx_status rfx_gbuffer_ingest_launch(rfx_ctx* ctx, void* stream, const rfx_inges
     is_second = 0;
     return pv(pl, f0, out);
   };
-  int dummy = 0;
   if (!one_of(albedo, RFX_FMT_RGBA8, RFX_FMT_RGBA16F, a.albedo, a.albedo_half) || !one_of(material, RFX_FMT_RGBA8, RFX_FMT_RGBA16F, a.material, a.material_half) ||
       !one_of(normal, RFX_FMT_RGBA16F, RFX_FMT_RGBA32F, a.normal, a.normal_f32) || !pv(depth, RFX_FMT_R32F, a.depth) ||
       (emissive && !pv(emissive, RFX_FMT_RGBA16F, a.emissive)) || (motion && !one_of(motion, RFX_FMT_RGBA16F, RFX_FMT_RGBA32F, a.motion, a.motion_f32)) ||
       (out_gbuffer && !ov(out_gbuffer, RFX_FMT_RGBA32F, a.out_gb)) || (out_velocity && !ov(out_velocity, RFX_FMT_RGBA32F, a.out_vel)))
     return fail(ctx, RFX_ERR_BAD_FORMAT, "gbuffer_ingest: albedo / material RGBA8|RGBA16F, normal / motion RGBA16F|RGBA32F, emissive RGBA16F, depth R32F, outputs RGBA32F");
-  (void)dummy;
   a.W = (int)depth->width; a.H = (int)depth->height;
   for (const rfx_plane* pl : {albedo, normal, material, emissive, motion, out_gbuffer, out_velocity})
     if (pl && ((int)pl->width != a.W || (int)pl->height != a.H)) return fail(ctx, RFX_ERR_SIZE_MISMATCH, "gbuffer_ingest: plane sizes differ");
