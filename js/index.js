@@ -197,7 +197,7 @@ export class SSREffect extends SSGIEffect {
 export const defaultTemporalReprojectPassOptions = {
 	dilation: false, fullAccumulate: false, neighborhoodClamp: false, neighborhoodClampRadius: 1, neighborhoodClampIntensity: 1, maxBlend: 1,
 	logTransform: false, depthDistance: 2, worldDistance: 4, reprojectSpecular: false, renderTarget: null, copyTextures: true,
-	confidencePower: 0.125, inputType: "diffuse"
+	confidencePower: 0.75, inputType: "diffuse"
 }
 
 // src/temporal-reproject/utils/QuasirandomGenerator.js:11-24, src/taa/TAAUtils.js:3-11

@@ -260,7 +260,7 @@ napi_value TemporalReproject(napi_env env, napi_callback_info info) {  // tempor
   std::memcpy(p.prev_projection, prev.projection, 64); std::memcpy(p.prev_projection_inverse, prev.projection_inverse, 64);
   b.f32("cameraPos", p.camera_pos, 3);
   p.max_blend = (float)b.num("maxBlend", 1); p.neighborhood_clamp_intensity = (float)b.num("neighborhoodClampIntensity", 1); p.keep_data = (float)b.num("keepData", 1);
-  p.confidence_power = (float)b.num("confidencePower", 0.125); p.full_accumulate = (int32_t)b.num("fullAccumulate", 0); p.texture_count = (int32_t)b.num("textureCount", 1);
+  p.confidence_power = (float)b.num("confidencePower", 0.75); p.full_accumulate = (int32_t)b.num("fullAccumulate", 0); p.texture_count = (int32_t)b.num("textureCount", 1);
   p.input_type = (int32_t)b.num("inputType", RFX_INPUT_DIFFUSE); p.log_transform = (int32_t)b.num("logTransform", 0); p.history_linear = (int32_t)b.num("historyLinear", 1);
   b.pair("reprojectSpecular", p.reproject_specular);
   CHECK(c, rfx_temporal_reproject_launch(c, nullptr, &p, unwrap<rfx_plane>(env, argv[2]), unwrap<rfx_plane>(env, argv[3]), unwrap<rfx_plane>(env, argv[4]), unwrap<rfx_plane>(env, argv[5]),

@@ -112,3 +112,66 @@ def test_traa_jitter_r2_sequence_and_view_offset():
     cam.clearViewOffset()
     assert np.array_equal(cam.proj, P0)
     effects.jitter(W, H, object(), 3)  # cameras without setViewOffset are left alone (TAAUtils.js:8)
+
+
+def _js_object(text: str, name: str) -> dict:
+    """the flat `const <name> = { key: literal, ... }` object literal of a reference JS file -> dict (numbers, booleans, strings, null)"""
+    import re
+
+    m = re.search(r"(?:const|let)\s+" + re.escape(name) + r"\s*=\s*\{(.*?)\n\}", text, flags=re.S)
+    assert m, name
+    out = {}
+    for key, val in re.findall(r"^\s*(\w+)\s*:\s*([^,\n/]+?)\s*,?\s*(?://.*)?$", m.group(1), flags=re.M):
+        v = val.strip()
+        if v in ("true", "false"):
+            out[key] = v == "true"
+        elif v == "null":
+            out[key] = None
+        elif v[0] in "\"'":
+            out[key] = v[1:-1]
+        else:
+            try:
+                out[key] = float(v)
+            except ValueError:
+                pass  # an expression (new Color(...), a spread): compared elsewhere
+    return out
+
+
+def test_option_defaults_equal_the_reference_js_tables():
+    """the option tables of effects.py and js/index.js against the reference's own files (SSGIOptions.js, TemporalReprojectPass.js,
+    PoissonDenoisePass.js, AOEffect.js, MotionBlurEffect.js), parsed from the checkout when it is there"""
+    import os
+    import re
+
+    import pytest
+
+    ref = os.environ.get("RFX_REFERENCE_DIR", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("reference checkout absent")
+    from realism_effects_b200 import effects
+
+    rd = lambda rel: open(os.path.join(ref, "src", rel), encoding="utf-8").read()  # noqa: E731
+    tables = [("ssgi/SSGIOptions.js", "defaultSSGIOptions", effects.defaultSSGIOptions),
+              ("temporal-reproject/TemporalReprojectPass.js", "defaultTemporalReprojectPassOptions", effects.defaultTemporalReprojectPassOptions),
+              ("denoise/pass/PoissonDenoisePass.js", "defaultPoissonBlurOptions", effects.defaultPoissonBlurOptions),
+              ("ao/AOEffect.js", "defaultAOOptions", effects.defaultAOOptions)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    js = open(os.path.join(root, "js", "index.js"), encoding="utf-8").read()
+    for rel, name, mine in tables:
+        want = _js_object(rd(rel), name)
+        assert len(want) >= 5, (name, want)
+        for k, v in want.items():
+            assert k in mine, (name, k)
+            got = mine[k]
+            assert (got == v) or (isinstance(v, float) and float(got) == v), (name, k, got, v)
+        # the ES-module mirror carries the same literal values
+        m = re.search(r"export const " + name + r"\s*=\s*\{(.*?)\n\}", js, flags=re.S)
+        assert m, f"js/index.js lacks {name}"
+        for k, v in want.items():
+            lit = "true" if v is True else "false" if v is False else "null" if v is None else (f'"{v}"' if isinstance(v, str) else None)
+            if lit is None:
+                assert re.search(r"\b" + k + r":\s*" + re.escape(("%g" % v)) + r"\b", m.group(1)), (name, k, v)
+            else:
+                assert re.search(r"\b" + k + r":\s*" + re.escape(lit), m.group(1)), (name, k, v)
+    mb = re.search(r"const defaultOptions = \{([^}]*)\}", rd("motion-blur/MotionBlurEffect.js")).group(1)
+    assert {k: float(v) for k, v in re.findall(r"(\w+):\s*([\d.]+)", mb)} == {k: float(v) for k, v in effects.defaultMotionBlurOptions.items()}
