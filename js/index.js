@@ -106,6 +106,11 @@ export class VelocityDepthNormalPass {
 	dispose() { this.rasterPass.dispose() }
 }
 
+// src/temporal-reproject/pass/VelocityPass.js:3-7 — the same pass with the depth / normal outputs switched off
+export class VelocityPass extends VelocityDepthNormalPass {
+	constructor(scene, camera, rasterPass) { super(scene, camera, rasterPass) }
+}
+
 // src/ssgi/SSGIOptions.js:26-48
 export const defaultSSGIOptions = {
 	mode: "ssgi", distance: 10, thickness: 10, denoiseIterations: 1, denoiseKernel: 2, denoiseDiffuse: 10, denoiseSpecular: 10,

@@ -124,6 +124,10 @@ class VelocityDepthNormalPass:
 VelocityPass = VelocityDepthNormalPass  # src/temporal-reproject/pass/VelocityPass.js:3-7
 
 
+class VelocityPass(VelocityDepthNormalPass):
+    """src/temporal-reproject/pass/VelocityPass.js:3-7: the same pass object (the host supplies the plane either way)"""
+
+
 # ---------------------------------------------------------------------------------------------------
 class SSGIEffect(_Reactive):
     """new SSGIEffect(composer, scene, camera, options)   (src/ssgi/SSGIEffect.js:27-141; signature per D6)
@@ -644,14 +648,19 @@ class TAAPass:
         self._last = None
         self.canvas = self.framebufferTexture = None
 
-    def setSize(self, width, height, ctx: engine.Context):
+    def setSize(self, width, height, ctx: "engine.Context | None" = None):
+        """setSize(width, height) as in the reference (:57-66); the planes are allocated on `ctx`, or on the input buffer's context at the next render()"""
         self.dispose()
-        self.canvas = ctx.alloc(abi.FMT_RGBA8, width, height)
-        self.framebufferTexture = ctx.alloc(abi.FMT_RGBA8, width, height)
-        self.needsUpdate = True
+        self._size, self.needsUpdate = (int(width), int(height)), True
+        if ctx is not None:
+            self.canvas = ctx.alloc(abi.FMT_RGBA8, width, height)
+            self.framebufferTexture = ctx.alloc(abi.FMT_RGBA8, width, height)
 
     def render(self, renderer, inputBuffer):
         ctx: engine.Context = inputBuffer.ctx
+        if self.canvas is None:
+            w, h = getattr(self, "_size", (inputBuffer.width, inputBuffer.height))
+            self.canvas, self.framebufferTexture = ctx.alloc(abi.FMT_RGBA8, w, h), ctx.alloc(abi.FMT_RGBA8, w, h)
         self.frame = (self.frame + 1) % 4096
         cam_u = self._camera.uniforms()
         moved = self.needsUpdate or _did_camera_move(cam_u, self._last)

@@ -175,3 +175,25 @@ def test_option_defaults_equal_the_reference_js_tables():
                 assert re.search(r"\b" + k + r":\s*" + re.escape(lit), m.group(1)), (name, k, v)
     mb = re.search(r"const defaultOptions = \{([^}]*)\}", rd("motion-blur/MotionBlurEffect.js")).group(1)
     assert {k: float(v) for k, v in re.findall(r"(\w+):\s*([\d.]+)", mb)} == {k: float(v) for k, v in effects.defaultMotionBlurOptions.items()}
+
+
+def test_plugin_surface_exports_every_class_of_the_reference_index():
+    """src/index.js:16-31 exports 14 names; effects.py and js/index.js carry all of them (the compute behind each is an rfx_* entry point)"""
+    import os
+    import re
+
+    import pytest
+
+    ref = os.environ.get("RFX_REFERENCE_DIR", "/root/reference")
+    idx = os.path.join(ref, "src", "index.js")
+    if not os.path.isfile(idx):
+        pytest.skip("reference checkout absent")
+    names = set(re.findall(r"^\s*(\w+),?\s*$", re.search(r"export \{(.*?)\}", open(idx, encoding="utf-8").read(), flags=re.S).group(1), flags=re.M))
+    assert len(names) == 14
+    from realism_effects_b200 import effects
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    js = set(re.findall(r"export class (\w+)", open(os.path.join(root, "js", "index.js"), encoding="utf-8").read()))
+    for n in names:
+        assert hasattr(effects, n), f"effects.py lacks {n}"
+        assert n in js, f"js/index.js lacks {n}"
