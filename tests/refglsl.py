@@ -12,7 +12,6 @@ oracle/_ref/ is enough to run it (the GPU box has no checkout).  `available()` s
 from __future__ import annotations
 
 import ctypes as C
-import glob
 import json
 import os
 import sys

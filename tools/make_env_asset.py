@@ -2,7 +2,6 @@
 panorama) into realism_effects_b200/assets/spree_bank_1k_rgbe.npz: the raw RGBE8 texels (H, W, 4) uint8 in FILE order (top scanline first).
 SURVEY.md §8(d) names this map as the bench environment.  Run in the build container:  python tools/make_env_asset.py"""
 import os
-import sys
 
 import numpy as np
 

@@ -4,7 +4,7 @@ import os
 import sys
 
 import numpy as np
-import torch
+import torch  # noqa: F401  (initialises CUDA before the engine)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
