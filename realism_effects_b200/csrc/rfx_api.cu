@@ -1141,7 +1141,7 @@ static rfx_status chain_render_fast(rfx_ssgi_chain* ch, void* stream, const rfx_
     // pass read such texels at silhouettes.  One GPU: A is single-buffered and a discard is simply no write.  In a row-sharded group a
     // rank's A rows outside its band hold the result of whichever even pass last covered them (the ranges shrink pass by pass), not the
     // last one's, so A is double-buffered by frame parity like B and the discarded texel is carried from the rank that OWNS the row.
-    const int acur = ch->group ? cur : 0;
+    const int acur = (ch->group && !ctx->debug_no_a_carry) ? cur : 0;  // RFX_DEBUG_NO_A_CARRY: the pre-fix behaviour (single-buffered A, discard = no write)
     a.in = i == 0 ? ipv(ch->tr32, W, H) : ipv(horizontal ? ch->dnB16[cur] : ch->dnA16[acur], W, H);
     a.out = iov(horizontal ? ch->dnA16[acur] : ch->dnB16[cur]);
     if (!horizontal) { if (ch->group) a.carry = ch->peer_dn[prev]; else peer_single(a.carry, ipv(ch->dnB16[prev], W, H)); }

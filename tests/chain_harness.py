@@ -78,11 +78,12 @@ class Inputs:
     blue: np.ndarray
 
 
-def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_size=(128, 64), device="cpu", reference_env=False, fov: float = 40.0) -> Inputs:
+def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_size=(128, 64), device="cpu", reference_env=False, fov: float = 40.0,
+                cam_step=(0.02, 0.0, 0.0)) -> Inputs:
     """reference_env: use the reference demo's environment map (synth.load_reference_env) instead of the small analytic sky"""
     frames = []
     for t in range(n_frames):
-        fr = synth.render_frame(width, height, t, device=device, static=static, fov=fov)
+        fr = synth.render_frame(width, height, t, device=device, static=static, fov=fov, cam_step=cam_step)
         u = fr.cam.uniforms()
         moved = (t > 0) and not static
         frames.append(dict(depth=fr.depth.cpu().numpy(), gbuffer=fr.gbuffer.cpu().numpy(), velocity=fr.velocity.cpu().numpy(),

@@ -42,9 +42,11 @@ def test_shard_plan_ranges():
     assert ShardPlan(2160, 8, 0, 4, 11.0).poisson_halo == 12                      # demo radius 11
 
 
-def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1, bounds_per_frame=None):
+def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1, bounds_per_frame=None, exchange_a=True):
     """The chain of chain_harness.run_oracle_chain, but every pass commits only its planned rows (all owned blocks) into this rank's
-    planes.  bounds_per_frame: explicit (unequal) band borders, one tuple per frame - the adaptive-band mode moves them between frames."""
+    planes.  bounds_per_frame: explicit (unequal) band borders, one tuple per frame - the adaptive-band mode moves them between frames.
+    exchange_a: the A Poisson target's rows take part in the per-frame exchange like B's (what the native group does, by carrying a
+    discarded texel from the rank that owns the row: DESIGN.md §5); False reproduces the pre-fix behaviour."""
     import orc
 
     H, W = inp.height, inp.width
@@ -83,7 +85,7 @@ def sharded_oracle_chain(inp, o, rank, world, all_gather_rows, blocks_per_rank=1
             commit(dst[0], o0, r)
             commit(dst[1], o1, r)
         commit(composed, orc.gi_compose(ch.compose_params(cam), fr["depth"], fr["gbuffer"], dnB[0], dnB[1], composed), next(rngs))
-        for plane in (composed, dnB[0], dnB[1]):
+        for plane in (composed, dnB[0], dnB[1]) + ((dnA[0], dnA[1]) if exchange_a else ()):
             all_gather_rows(plane, plan)
     return dict(composed=composed, dn0=dnB[0], dn1=dnB[1], tr0=tr[0], ssgi=ssgi, plan=plan)
 
@@ -154,6 +156,63 @@ def test_two_rank_sharded_chain_equals_single_process_bit_exact(bpr):
             got = np.frombuffer(planes[k], ref[k].dtype).reshape(ref[k].shape)
             for r0, r1 in blocks:
                 assert got[r0:r1].tobytes() == ref[k][r0:r1].tobytes(), (rank, k)
+
+
+def _worker3(rank, world, port, q, exchange_a):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        o = ch.Opts(steps=6, refine_steps=1, denoise_iterations=2)
+        inp = ch.make_inputs(*WIDE_CASE, fov=75.0)
+
+        def all_gather_rows(plane, plan):  # equal bands: one rank-ordered all-gather per plane
+            b0, b1 = plan.blocks[0]
+            mine = torch.from_numpy(np.ascontiguousarray(plane[b0:b1]).view(np.uint8).reshape(-1))
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            for g, t in enumerate(parts):
+                plane[g * plan.block_rows:(g + 1) * plan.block_rows] = t.numpy().view(plane.dtype).reshape(plan.block_rows, *plane.shape[1:])
+
+        out = sharded_oracle_chain(inp, o, rank, world, all_gather_rows, exchange_a=exchange_a)
+        q.put((rank, {k: v.tobytes() for k, v in out.items() if k != "plan"}))
+    finally:
+        dist.destroy_process_group()
+
+
+WIDE_CASE = (112, 144, 4)  # width, height, frames (fov 75 below: the sky's silhouette runs through the upper band border)
+
+
+def _run3(exchange_a):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker3, args=(r, 3, port, q, exchange_a)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def test_three_ranks_two_denoise_iterations_with_the_a_target_taken_from_its_owner():
+    """world_size 3, denoiseIterations 2 (four Poisson passes: the A target is written twice per frame on shrinking row ranges).  A pixel the
+    shader discards keeps its A texel, and the LINEAR taps of the next pass read it at silhouettes; on rows outside a rank's last A range the
+    local texel is the wrong pass's.  With the A rows coming from their owner every frame (the rule the native group implements by carrying the
+    texel from the owning rank) every rank's frame equals the single-process chain bit for bit.  The failure without the rule needs a pixel
+    that turns from shaded to discarded between two frames right at a band border; this small scene does not have one — the bench frame does:
+    tools/emulate_group_cpu.py reproduces there, pixel for pixel, what the N = 4 GPU run showed (profiles/r02_group_a_target_cpu_emulation.txt)."""
+    o = ch.Opts(steps=6, refine_steps=1, denoise_iterations=2)
+    inp = ch.make_inputs(*WIDE_CASE, fov=75.0)
+    ref = ch.run_oracle_chain(inp, o)[-1]
+    good = _run3(True)
+    for rank, planes in good.items():
+        for k in ("composed", "dn0", "dn1"):
+            assert planes[k] == ref[k].tobytes(), (rank, k)
 
 
 def test_host_path_row_sets_cover_what_each_launch_reads():

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU box (1 GPU): the in-process N-band test with and without the A-target carry (the second must fail: it is what the test catches),
+# GPU box (1 GPU): the in-process N-band test (also once with RFX_DEBUG_NO_A_CARRY=1 = the pre-fix single-buffered A target, for comparison),
 # the rest of the chain tests, then step 6 (tiled-viewZ A/B + ncu of the new kernels).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
