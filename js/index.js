@@ -521,3 +521,23 @@ export class TAAPass {
 	}
 	dispose() { if (this.planes) for (const pl of Object.values(this.planes)) rfx.planeFree(this.ctx, pl); this.planes = null }
 }
+
+// ---- one Node process, several GPUs: a row-sharded group whose members live in this process (rfx_group_create_inprocess) -------------------------
+// Every member owns a context (one per device), a fast SSGI chain with identical options and a band of rows; halo rows are recomputed, last
+// frame's history rows are read in place on the member that owns them.  The per-device planes come from the caller (one PlaneSource per device).
+export class InProcessGroup {
+	constructor(devices, chainOptions) {
+		this.ctxs = devices.map(d => rfx.ctxCreate(d))
+		this.chains = this.ctxs.map(c => rfx.chainCreate(c, chainOptions))
+		this.groups = this.ctxs.map((c, r) => rfx.groupCreateInprocess(c, r, devices.length))
+		rfx.groupAttachChainsInprocess(this.ctxs[0], this.groups, this.chains)
+	}
+	setBounds(bounds) { this.groups.forEach((g, r) => rfx.groupSetBounds(this.ctxs[r], g, bounds)) }
+	// planes[r]: { depth, gbuffer, velocity, directLight } device planes on device r (full frames); all members finish before the next frame starts
+	render(cam, planes, cameraPos, moved) {
+		this.chains.forEach((ch, r) => rfx.chainRenderSharded(this.ctxs[r], ch, cam, planes[r].depth, planes[r].gbuffer, planes[r].velocity, planes[r].directLight, cameraPos, moved))
+		this.ctxs.forEach(c => rfx.ctxSync(c))
+	}
+	output(r, which = 0) { return rfx.chainOutput(this.ctxs[r], this.chains[r], which) }
+	dispose() { this.groups.forEach(g => rfx.groupDestroy(g)); this.chains.forEach(ch => rfx.chainDestroy(ch)); this.ctxs.forEach(c => rfx.ctxDestroy(c)) }
+}

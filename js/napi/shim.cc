@@ -324,6 +324,50 @@ napi_value TraaCompose(napi_env env, napi_callback_info info) {  // traaCompose(
   return undefined(env);
 }
 
+// ---- row-sharded groups inside one process (a Node host drives every GPU from one process: no NCCL, no CUDA IPC) ----------------------------
+napi_value GroupCreateInprocess(napi_env env, napi_callback_info info) {  // groupCreateInprocess(ctx, rank, world) -> group
+  ARGS(3); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  int32_t rank = 0, world = 1; napi_get_value_int32(env, argv[1], &rank); napi_get_value_int32(env, argv[2], &world);
+  rfx_group* g = nullptr;
+  CHECK(c, rfx_group_create_inprocess(c, rank, world, &g), "rfx_group_create_inprocess");
+  return external(env, g);
+}
+napi_value GroupAttachChainsInprocess(napi_env env, napi_callback_info info) {  // groupAttachChainsInprocess(ctx, [groups], [chains])
+  ARGS(3); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  rfx_group* gs[8] = {}; rfx_ssgi_chain* cs[8] = {};
+  int32_t n = 0;
+  for (uint32_t i = 0; i < 8; i++) {
+    napi_value eg, ec;
+    if (napi_get_element(env, argv[1], i, &eg) != napi_ok || napi_get_element(env, argv[2], i, &ec) != napi_ok) break;
+    gs[i] = unwrap<rfx_group>(env, eg); cs[i] = unwrap<rfx_ssgi_chain>(env, ec);
+    if (!gs[i] || !cs[i]) break;
+    n++;
+  }
+  CHECK(c, rfx_group_attach_chains_inprocess(gs, cs, n), "rfx_group_attach_chains_inprocess");
+  return undefined(env);
+}
+napi_value GroupSetBounds(napi_env env, napi_callback_info info) {  // groupSetBounds(ctx, group, [world + 1 ascending rows])
+  ARGS(3); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
+  rfx_group* g = unwrap<rfx_group>(env, argv[1]);
+  uint32_t b[9] = {};
+  const int32_t n = rfx_group_world(g);
+  for (int32_t i = 0; i <= n && i < 9; i++) { napi_value e; double d = 0; if (napi_get_element(env, argv[2], (uint32_t)i, &e) == napi_ok) napi_get_value_double(env, e, &d); b[i] = (uint32_t)d; }
+  CHECK(c, rfx_group_set_bounds(g, b), "rfx_group_set_bounds");
+  return undefined(env);
+}
+napi_value GroupDestroy(napi_env env, napi_callback_info info) { ARGS(1); rfx_group_destroy(unwrap<rfx_group>(env, argv[0])); return undefined(env); }
+napi_value ChainRenderSharded(napi_env env, napi_callback_info info) {  // chainRenderSharded(ctx, chain, camera, depth, gbuffer, velocity, direct|null, cameraPos, moved): this member's band
+  ARGS(9); rfx_ctx* ctx = unwrap<rfx_ctx>(env, argv[0]);
+  rfx_ssgi_frame f{};
+  if (!read_camera(env, argv[2], &f.cam)) { napi_throw_type_error(env, nullptr, "camera: expected Float32Array(16) matrices"); return nullptr; }
+  f.depth = unwrap<rfx_plane>(env, argv[3]); f.gbuffer = unwrap<rfx_plane>(env, argv[4]); f.velocity = unwrap<rfx_plane>(env, argv[5]);
+  f.direct_light = unwrap<rfx_plane>(env, argv[6]);
+  read_f32(env, argv[7], f.camera_pos, 3);
+  bool moved = true; napi_get_value_bool(env, argv[8], &moved); f.camera_moved = moved;
+  CHECK(ctx, rfx_ssgi_chain_render_sharded(unwrap<rfx_ssgi_chain>(env, argv[1]), nullptr, &f), "rfx_ssgi_chain_render_sharded");
+  return undefined(env);
+}
+
 napi_value Effects(napi_env env, napi_callback_info info) {  // effects(ctx, {cam, effects: [ids], sharpness, alphax, alphay, aberration, backgroundColor, maxDistance, spread, intensity, sparklePerspective}, input, depth|null, velocity|null, out)
   ARGS(6); rfx_ctx* c = unwrap<rfx_ctx>(env, argv[0]);
   Obj b{env, argv[1]};
@@ -372,6 +416,8 @@ napi_value Init(napi_env env, napi_value exports) {
       FN("chainReset", ChainReset), FN("chainDestroy", ChainDestroy), FN("ssgiCompose", SsgiCompose), FN("temporalReproject", TemporalReproject),
       FN("poissonDenoise", PoissonDenoise), FN("giCompose", GiCompose), FN("hbao", Hbao), FN("aoCompose", AoCompose), FN("motionBlur", MotionBlur),
       FN("traaCompose", TraaCompose), FN("gbufferIngest", GbufferIngest), FN("effects", Effects), FN("taa", Taa),
+      FN("groupCreateInprocess", GroupCreateInprocess), FN("groupAttachChainsInprocess", GroupAttachChainsInprocess), FN("groupSetBounds", GroupSetBounds),
+      FN("groupDestroy", GroupDestroy), FN("chainRenderSharded", ChainRenderSharded),
   };
 #undef FN
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
