@@ -3,7 +3,7 @@ with the ORACLE as compute (tests/test_sharding_cpu.py: every pass commits only 
 planes are taken from the single-process chain).  It reproduces, pixel for pixel, what the N = 4 GPU run showed before the A-target fix —
 frame 1, rank 2: composed 2 px, dn0 1 px, dn1 1 px, all on row 1615 (profiles/r02_group_diag_n4_before_fix.log) — and shows that taking
 the A Poisson target's rows from the rank that owns them (what csrc/rfx_api.cu now does by carrying discarded texels from the owner) makes the
-band bit-identical.  ~4 min on 8 cores.   python tools/emulate_group_cpu.py [rank]      TEST INFRASTRUCTURE (uses oracle/)."""
+band bit-identical.  ~4 min on 8 cores.   python tools/emulate_group_cpu.py [rank ...]      TEST INFRASTRUCTURE (uses oracle/)."""
 import os
 import sys
 import time
@@ -19,7 +19,7 @@ from test_sharding_cpu import sharded_oracle_chain  # noqa: E402
 
 W, H, world = 3840, 2160, 4
 bounds = (0, 544, 1088, 1616, 2160)  # rfx_group_attach_chain's initial borders for H = 2160, 4 ranks
-rank = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+ranks = [int(a) for a in sys.argv[1:]] or [2]
 o = ch.Opts(denoise_iterations=2)
 frames = []
 for t in (1, 2):  # bench.make_gpu_frames
@@ -34,10 +34,10 @@ print(f"single-process chain, 2 frames: {time.time() - t0:.0f} s", flush=True)
 ref = [{k: r[k] for k in ("composed", "dn0", "dn1")} for r in recs]
 a_ref = [(r["_k3"][2]["out0"], r["_k3"][2]["out1"]) for r in recs]  # the A target after its last pass of each frame
 del recs
-for exchange_a in (False, True):
+for rank, exchange_a in [(r, e) for r in ranks for e in (False, True)]:
     st = {"k": 0, "f": 0}
 
-    def all_gather_rows(plane, plan, st=st, exchange_a=exchange_a):
+    def all_gather_rows(plane, plan, st=st, exchange_a=exchange_a, rank=rank):
         name = ("composed", "dn0", "dn1", "a0", "a1")[st["k"]]
         src = a_ref[st["f"]][int(name[1])] if name[0] == "a" else ref[st["f"]][name]
         for g in range(world):
