@@ -3,7 +3,7 @@ with the ORACLE as compute (tests/test_sharding_cpu.py: every pass commits only 
 planes are taken from the single-process chain).  It reproduces, pixel for pixel, what the N = 4 GPU run showed before the A-target fix —
 frame 1, rank 2: composed 2 px, dn0 1 px, dn1 1 px, all on row 1615 (profiles/r02_group_diag_n4_before_fix.log) — and shows that taking
 the A Poisson target's rows from the rank that owns them (what csrc/rfx_api.cu now does by carrying discarded texels from the owner) makes the
-band bit-identical.  ~4 min on 8 cores.   python tools/emulate_group_cpu.py [rank ...]      TEST INFRASTRUCTURE (uses oracle/)."""
+band bit-identical.  ~4 min on 8 cores.   python tools/emulate_group_cpu.py [--world N] [rank ...]      TEST INFRASTRUCTURE (uses oracle/)."""
 import os
 import sys
 import time
@@ -17,9 +17,13 @@ import chain_harness as ch  # noqa: E402
 from realism_effects_b200 import synth  # noqa: E402
 from test_sharding_cpu import sharded_oracle_chain  # noqa: E402
 
-W, H, world = 3840, 2160, 4
-bounds = (0, 544, 1088, 1616, 2160)  # rfx_group_attach_chain's initial borders for H = 2160, 4 ranks
-ranks = [int(a) for a in sys.argv[1:]] or [2]
+W, H = 3840, 2160
+args = sys.argv[1:]
+world = int(args.pop(args.index("--world") + 1)) if "--world" in args else 4
+if "--world" in args:
+    args.remove("--world")
+bounds = tuple(int(round(H * i / world / 16.0)) * 16 for i in range(world)) + (H,)  # rfx_group_attach_chain's initial borders (4 ranks: 0, 544, 1088, 1616, 2160)
+ranks = [int(a) for a in args] or [2]
 o = ch.Opts(denoise_iterations=2)
 frames = []
 for t in (1, 2):  # bench.make_gpu_frames
