@@ -158,3 +158,22 @@ def test_oracle_equals_reference_shaders_cosmetic_effects_and_taa():
     hist = np.random.default_rng(1).integers(0, 256, (54, 96, 4), dtype=np.uint8)
     for p in ch.taa_cases():
         assert bits(orc.taa(p, f1["direct"], hist)) == bits(refglsl.taa(p, f1["direct"], hist))
+
+
+@needs_ref
+def test_prebuilt_reference_shaders_run_without_the_checkout():
+    """what the GPU box does: no /root/reference there, only the libraries __graft_entry__.build() left in oracle/_ref (bench.py --impl reference, the
+    `reference_shaders` leg of cpu_baseline).  A subprocess with RFX_REFERENCE_DIR pointing nowhere must still run the default chain through them."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    refglsl.prebuild()  # here (checkout present) this is a cache hit; it guarantees the manifest lists every standard variant
+    code = ("import sys; sys.path.insert(0, 'tests'); import numpy as np, chain_harness as ch, refglsl, orc\n"
+            "assert not refglsl.assemble.available() and refglsl.chain_available(0) and refglsl.chain_available(1)\n"
+            "inp = ch.make_inputs(48, 32, 2); o = ch.Opts()\n"
+            "a = ch.run_oracle_chain(inp, o, capture=('composed',), lean=True); b = ch.run_oracle_chain(inp, o, capture=('composed',), lean=True, impl=refglsl)\n"
+            "assert a[1]['composed'].tobytes() == b[1]['composed'].tobytes(); print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, "RFX_REFERENCE_DIR": "/nonexistent"}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
