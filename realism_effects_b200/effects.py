@@ -121,9 +121,6 @@ class VelocityDepthNormalPass:
         pass
 
 
-VelocityPass = VelocityDepthNormalPass  # src/temporal-reproject/pass/VelocityPass.js:3-7
-
-
 class VelocityPass(VelocityDepthNormalPass):
     """src/temporal-reproject/pass/VelocityPass.js:3-7: the same pass object (the host supplies the plane either way)"""
 
