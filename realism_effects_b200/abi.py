@@ -141,8 +141,10 @@ class SsgiHostFrame(C.Structure):
                 ("camera_pos", F3), ("camera_moved", C.c_int32), ("out_composed", C.c_void_p)]
 
 
-def make_camera(u: dict, perspective: bool = True) -> CameraS:
-    """u: dict from synth.Camera.uniforms() (float32 column-major arrays)."""
+def make_camera(u: dict, perspective: "bool | None" = None) -> CameraS:
+    """u: dict from synth.Camera.uniforms() (float32 column-major arrays); perspective: camera.isPerspectiveCamera (default: u["perspective"], else True)."""
+    if perspective is None:
+        perspective = bool(u.get("perspective", True))
     c = CameraS()
     for k in ("projection", "projection_inverse", "camera_matrix_world", "view_matrix"):
         getattr(c, k)[:] = [float(x) for x in np.asarray(u[k], np.float32)]

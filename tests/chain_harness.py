@@ -79,13 +79,18 @@ class Inputs:
 
 
 def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_size=(128, 64), device="cpu", reference_env=False, fov: float = 40.0,
-                cam_step=(0.02, 0.0, 0.0)) -> Inputs:
-    """reference_env: use the reference demo's environment map (synth.load_reference_env) instead of the small analytic sky"""
+                cam_step=(0.02, 0.0, 0.0), orthographic: bool = False) -> Inputs:
+    """reference_env: use the reference demo's environment map (synth.load_reference_env) instead of the small analytic sky.
+    orthographic: the same planes seen through a three.js OrthographicCamera (the shaders' #else branches of PERSPECTIVE_CAMERA): the projection
+    matrices are replaced (Matrix4.makeOrthographic), the depth plane is re-encoded so that the view-space z of every texel is kept, and the
+    camera dict carries perspective=False (abi.make_camera reads it)."""
     frames = []
     for t in range(n_frames):
         fr = synth.render_frame(width, height, t, device=device, static=static, fov=fov, cam_step=cam_step)
         u = fr.cam.uniforms()
         moved = (t > 0) and not static
+        if orthographic:
+            fr.depth = _to_orthographic(u, fr.depth, width / height)
         frames.append(dict(depth=fr.depth.cpu().numpy(), gbuffer=fr.gbuffer.cpu().numpy(), velocity=fr.velocity.cpu().numpy(),
                            direct=fr.direct_light.cpu().numpy(), cam=u, moved=moved))
     if reference_env:
@@ -95,6 +100,22 @@ def make_inputs(width: int, height: int, n_frames: int, *, static=False, env_siz
         env = synth.synthetic_env(*env_size)
         marg, cond, total = synth.build_env_cdf(env.astype(np.float32), flip_y=False)
     return Inputs(width, height, frames, env, marg, cond, total, synth.load_blue_noise())
+
+
+def _to_orthographic(u: dict, depth, aspect: float, half_height: float = 11.0):
+    """in place on the uniform dict `u`; returns the re-encoded depth plane (same torch dtype/device)"""
+    n, f = float(u["near"]), float(u["far"])
+    d = depth.double()
+    view_z = (n * f) / ((f - n) * d - f)  # perspectiveDepthToViewZ
+    od = (view_z + n) / (n - f)  # viewZToOrthographicDepth
+    od = od.clamp(0.0, 1.0).where(d < 1.0, d)  # the background stays exactly 1.0
+    top, right = half_height, half_height * aspect
+    P = np.zeros((4, 4), np.float64)
+    P[0, 0], P[1, 1], P[2, 2], P[2, 3], P[3, 3] = 1.0 / right, 1.0 / top, -2.0 / (f - n), -(f + n) / (f - n), 1.0
+    u["projection"] = np.ascontiguousarray(P.T.reshape(16)).astype(np.float32)
+    u["projection_inverse"] = np.ascontiguousarray(np.linalg.inv(P).T.reshape(16)).astype(np.float32)
+    u["perspective"] = False
+    return od.to(depth.dtype)
 
 
 def next_blue(start: int, counter: int) -> int:
@@ -301,9 +322,9 @@ def compare(a: np.ndarray, b: np.ndarray, packed: bool = False, rtol: float | No
                 bit_equal=float(((a == b) | (np.isnan(a) & np.isnan(b))).mean()))
 
 
-def run_chain_parity(width=192, height=108, frames=2, fast_math=True, **opt_kw) -> dict:
+def run_chain_parity(width=192, height=108, frames=2, fast_math=True, inputs_kw=None, **opt_kw) -> dict:
     o = Opts(**opt_kw)
-    inp = make_inputs(width, height, frames)
+    inp = make_inputs(width, height, frames, **(inputs_kw or {}))
     ref = run_oracle_chain(inp, o)
     got, launches = run_cuda_chain(inp, o, fast_math=fast_math)
     # Chain level: every pass of every frame re-quantises to fp16 (K1 pack, Poisson targets), so a last-ulp difference in one

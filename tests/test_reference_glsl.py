@@ -95,6 +95,7 @@ def test_runtime_sampler_state_and_null_sampler():
 
 
 needs_ref = pytest.mark.skipif(not refglsl.available(), reason="neither the reference checkout nor prebuilt oracle/_ref libraries")
+needs_checkout = pytest.mark.skipif(not refglsl.assemble.available(), reason="builds shader variants outside the prebuilt set: needs the reference checkout")
 
 
 def bits(a):
@@ -177,3 +178,39 @@ def test_prebuilt_reference_shaders_run_without_the_checkout():
             "assert a[1]['composed'].tobytes() == b[1]['composed'].tobytes(); print('ok')")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, "RFX_REFERENCE_DIR": "/nonexistent"}, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@needs_checkout
+@pytest.mark.parametrize("mode", [abi.MODE_SSGI, abi.MODE_SSR])
+def test_oracle_equals_reference_shaders_orthographic_camera(mode):
+    """the `#else` branches of PERSPECTIVE_CAMERA (K1 ray set-up, getViewZ, the view directions of K2 and K4) through a three.js OrthographicCamera"""
+    inp = ch.make_inputs(64, 40, 2, orthographic=True)
+    assert inp.frames[0]["cam"]["perspective"] is False and abi.make_camera(inp.frames[0]["cam"]).perspective == 0
+    o = ch.Opts(mode=mode)
+    planes = ("ssgi", "tr0", "dn0", "composed")
+    a = ch.run_oracle_chain(inp, o, capture=planes, lean=True)
+    b = ch.run_oracle_chain(inp, o, capture=planes, lean=True, impl=refglsl)
+    for f in range(2):
+        for k in planes:
+            assert bits(a[f][k]) == bits(b[f][k]), (f, k)
+    assert float(np.abs(np.asarray(b[1]["composed"], np.float32)).max()) > 0.1
+    p = ch.Opts()  # and it is a different image from the perspective one on the same planes
+    assert bits(ch.run_oracle_chain(ch.make_inputs(64, 40, 1), p, capture=("composed",), lean=True)[0]["composed"]) != bits(a[0]["composed"])
+
+
+@needs_checkout
+def test_random_option_sets_oracle_equals_reference_shaders():
+    """tools/fuzz_pin.py in small: random uniform values, shader variants, frame sizes (odd, portrait) and camera motion; every plane of the chain and of
+    each single pass must be bit-equal between the oracle and the reference's shaders (profiles/r02_fuzz_pin_*.json: 260 cases, 0 differing pixels)"""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_pin
+
+    rng = np.random.default_rng(20260923)
+    for _ in range(4):
+        n, bad = fuzz_pin.run_chain(*fuzz_pin.draw_chain(rng))
+        assert n > 0 and not bad, bad
+    n, bad = fuzz_pin.run_passes(rng)
+    assert n == 9 and not bad, bad

@@ -59,6 +59,10 @@ CHAIN_CASES = {
     "ssgi_scale_0.5": (96, 56, 3, dict(resolution_scale=0.5), {}),
     "ssgi_scale_0.75": (96, 56, 2, dict(resolution_scale=0.75), {}),
     "ssr_scale_0.5": (96, 56, 2, dict(mode=abi.MODE_SSR, resolution_scale=0.5), {}),
+    # OrthographicCamera: the #else branches of PERSPECTIVE_CAMERA in K1 (ray origin / direction), getViewZ, K2's and K4's view directions
+    "ssgi_orthographic": (80, 54, 3, {}, dict(orthographic=True)),
+    "ssr_orthographic": (80, 54, 2, dict(mode=abi.MODE_SSR), dict(orthographic=True)),
+    "ssgi_ortho_missed": (64, 48, 2, dict(missed_rays=True, importance_sampling=False), dict(orthographic=True)),
 }
 
 
