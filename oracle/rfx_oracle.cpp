@@ -13,7 +13,7 @@
 // way the reference's JS assembles it) for the CPU on a GLSL language runtime
 // (oracle/ref/glsl_rt.h) into oracle/_ref/*.so — the reference run here.  This
 // restatement equals those shaders BIT FOR BIT on every plane of every pass: 17 chain
-// configurations + all effect passes (tools/pin_oracle.py), 360 random option sets
+// configurations + all effect passes (tools/pin_oracle.py), 460 random option sets
 // (tools/fuzz_pin.py), the chain at 1920x1080 x 3 frames, 3840x2160 x 2 and 7680x4320 x 2
 // frames (profiles/r02_pin_oracle_*.json, r02_fuzz_pin_seed*.json), checked live by
 // tests/test_reference_glsl.py and, where the checkout is absent, against the committed

@@ -201,7 +201,7 @@ def test_oracle_equals_reference_shaders_orthographic_camera(mode):
 @needs_checkout
 def test_random_option_sets_oracle_equals_reference_shaders():
     """tools/fuzz_pin.py in small: random uniform values, shader variants, frame sizes (odd, portrait) and camera motion; every plane of the chain and of
-    each single pass must be bit-equal between the oracle and the reference's shaders (profiles/r02_fuzz_pin_*.json: 260 cases, 0 differing pixels)"""
+    each single pass must be bit-equal between the oracle and the reference's shaders (profiles/r02_fuzz_pin_seed*.json: 460 cases, 0 differing pixels)"""
     import os
     import sys
 
@@ -213,4 +213,4 @@ def test_random_option_sets_oracle_equals_reference_shaders():
         n, bad = fuzz_pin.run_chain(*fuzz_pin.draw_chain(rng))
         assert n > 0 and not bad, bad
     n, bad = fuzz_pin.run_passes(rng)
-    assert n == 9 and not bad, bad
+    assert n == 11 and not bad, bad

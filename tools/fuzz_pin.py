@@ -119,6 +119,16 @@ def run_passes(rng):
     sp.camera_near, sp.camera_far = float(f1["cam"]["near"]), float(f1["cam"]["far"])
     both("ssgi_compose", lambda m: (m.ssgi_compose(f1["depth"], gi, f1["direct"], sp),))
 
+    # K2 alone, SSGI form (2 planes), on frame 1 of a chain (real history), with the uniform-valued options drawn: maxBlend, neighborhoodClampIntensity,
+    # keepData, fullAccumulate; and the shader-variant ones: logTransform, confidencePower
+    rec = ch.run_oracle_chain(inp, ch.Opts(), capture=("ssgi",))[1]
+    tp = rec["_k2_params"]
+    tp.max_blend, tp.neighborhood_clamp_intensity = float(rng.uniform(0.5, 1.0)), float(rng.uniform(0.0, 1.0))
+    tp.keep_data, tp.full_accumulate = float(rng.integers(0, 2)), int(rng.random() < 0.3)
+    tp.log_transform, tp.confidence_power = int(rng.random() < 0.7), float(rng.choice([0.125, 0.75, 1.0, 4.0]))
+    both("temporal_reproject", lambda m: m.temporal_reproject(tp, rec["ssgi"], f1["velocity"], rec["_k2_hist"][0], rec["_k2_hist"][1],
+                                                               rec["_k2_prev_out"][0], rec["_k2_prev_out"][1]))
+
     # TRAA (K2 single plane + K9)
     both("traa", lambda m: ch.traa_two_frames(m, f0, f1))
 
